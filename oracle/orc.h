@@ -1,0 +1,111 @@
+/*
+ * oracle/orc.h -- TEST INFRASTRUCTURE ONLY. CPU oracle ("orc") for the B200 H.264 encode path.
+ *
+ * What it restates: the work done behind ISVCEncoder::EncodeFrame at
+ * /root/reference/video_codec/VideoEncoderOpenH264.cpp:344 (one I420 frame in -> one Annex-B
+ * access unit out, Baseline / CAVLC / IPPP / 1 reference, policy table at :228-296).
+ * The arithmetic of that call lives in cisco/openh264 (libopenh264.so, dlopen'ed by name at
+ * VideoEncoderOpenH264.cpp:46,203; no version pinned, vendored headers correspond to API ~v2.0.0),
+ * which is absent from /root/reference and from this image. The reference has no tests or golden
+ * vectors, so PARITY WITH OPENH264 IS UNPINNED. What IS pinned:
+ *   - every normative stage (CAVLC, intra/inter prediction, dequant/IDCT, deblocking) by decoding the
+ *     oracle's streams with FFmpeg's independent h264 decoder and comparing with the oracle's own
+ *     reconstruction bit-exactly (tests/test_oracle_decode.py);
+ *   - the CAVLC/deblock/cbp tables against the copies inside that decoder (tests/test_tables.py).
+ * Encoder-side free choices (search pattern, costs, quantiser rounding) follow the standard JM-style
+ * definitions named in SURVEY.md section 2b and are the specification the CUDA path must reproduce
+ * bit-for-bit (same bitstream bytes, same reconstruction).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library. The product (media_b200/csrc) never includes or links anything from oracle/.
+ */
+#ifndef ORC_H
+#define ORC_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- macroblock types used in the per-MB side arrays (shared layout with the CUDA path) ---- */
+enum { ORC_MB_P16x16 = 0, ORC_MB_I16x16 = 1, ORC_MB_I4x4 = 2, ORC_MB_PSKIP = 3 };
+
+/* Per-MB coefficient record: everything CAVLC needs, 816 bytes. Levels are in zig-zag scan order. */
+typedef struct {
+    int16_t luma[16][16];    /* [blkIdx][scan]; for I16x16 index 0 of each block is unused (AC only) */
+    int16_t luma_dc[16];     /* I16x16 only: Intra16x16DCLevel in scan order */
+    int16_t chroma_dc[2][4]; /* [plane][c] raster order of the 2x2 block */
+    int16_t chroma_ac[2][4][16]; /* [plane][blk][scan], index 0 unused */
+} OrcMbCoef;
+
+typedef struct {
+    uint8_t  mb_type;        /* ORC_MB_* */
+    uint8_t  i16_mode;       /* Intra16x16PredMode 0..3 */
+    uint8_t  chroma_mode;    /* intra_chroma_pred_mode 0..3 */
+    uint8_t  cbp;            /* bits 0..3 luma 8x8, bits 4..5 chroma (0,1,2) */
+    int16_t  mv[2];          /* quarter-pel */
+    uint8_t  i4_mode[16];    /* Intra4x4PredMode per blkIdx */
+    uint8_t  nnz[24];        /* total_coeff: 0..15 luma blkIdx, 16..19 Cb, 20..23 Cr (AC count for I16x16/chroma) */
+} OrcMbInfo;
+
+typedef struct OrcEncoder OrcEncoder;
+
+typedef struct {
+    int width, height;       /* display size (even, 16..4096) */
+    int num_slices;          /* >=1, MB-row groups */
+    int search_range;        /* full-pel, multiple of 4: 16/32/64 */
+    int level_idc;           /* 0 = derive from size/fps */
+    int fps;
+} OrcConfig;
+
+OrcEncoder *orc_create(const OrcConfig *cfg);
+void orc_destroy(OrcEncoder *e);
+/* Encode one frame. frame_type: 1 = IDR (SPS+PPS prepended), 0 = P. Returns bytes written or <0. */
+int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap);
+/* Reconstruction of the last encoded frame (after deblocking), cropped to width x height I420. */
+void orc_get_recon(const OrcEncoder *e, uint8_t *i420);
+/* Stage dumps of the last frame for stage-by-stage parity with the CUDA path. */
+const OrcMbInfo *orc_mb_info(const OrcEncoder *e);
+const OrcMbCoef *orc_mb_coef(const OrcEncoder *e);
+int orc_mb_count(const OrcEncoder *e);
+/* coded (padded) planes of the last frame: which = 0 src, 1 recon before deblock, 2 recon after deblock */
+const uint8_t *orc_plane(const OrcEncoder *e, int which, int comp, int *stride, int *w, int *h);
+/* coarse ME results of last P frame: level 2 (1/4), 1 (1/2), 0 (full-pel) MVs in that level's pixel units */
+const int16_t *orc_me_level(const OrcEncoder *e, int level);
+/* best inter cost (SATD + lambda*mv bits) per MB of the last P frame */
+const int32_t *orc_inter_cost(const OrcEncoder *e);
+/* quarter-pel sample of the current reference through the encoder's half-pel planes (== orc_interp_luma) */
+int orc_dbg_qpel(const OrcEncoder *e, int xq, int yq);
+
+/* ---- headers ---- */
+int orc_write_sps(uint8_t *out, int width, int height, int level_idc);
+int orc_write_pps(uint8_t *out);
+int orc_level_for(int width, int height, int fps);
+
+/* ---- kernel-level oracles (bit-exact targets of the per-kernel C-ABI entry points) ---- */
+int  orc_sad(const uint8_t *a, int sa, const uint8_t *b, int sb, int w, int h);
+int  orc_satd4x4(const uint8_t *a, int sa, const uint8_t *b, int sb);
+int  orc_satd16x16(const uint8_t *a, int sa, const uint8_t *b, int sb);
+void orc_dct4x4(const int16_t *res /*16 raster*/, int16_t *coef /*16 raster*/);
+void orc_idct4x4(const int32_t *d /*16 raster dequantised*/, int32_t *r /*16 raster, (x+32)>>6 applied*/);
+/* quantise raster coef -> zigzag levels; intra selects the dead-zone; ac_only skips position 0. Returns nnz */
+int  orc_quant4x4(const int16_t *coef, int16_t *level_zz, int qp, int intra, int ac_only);
+void orc_dequant4x4(const int16_t *level_zz, int32_t *d, int qp, int ac_only);
+void orc_rgba_to_i420(const uint8_t *rgba, int width, int height, uint8_t *i420);
+void orc_nv12_to_i420(const uint8_t *nv12, int width, int height, uint8_t *i420);
+void orc_downsample2(const uint8_t *src, int sstride, int w, int h, uint8_t *dst, int dstride);
+/* luma sample at quarter-pel position (xq,yq) with edge clamping (8.4.2.2.1) */
+int  orc_interp_luma(const uint8_t *ref, int stride, int w, int h, int xq, int yq);
+/* chroma sample at 1/8-pel position */
+int  orc_interp_chroma(const uint8_t *ref, int stride, int w, int h, int x8, int y8);
+/* in-place deblocking of a whole coded frame given per-MB info (8.7) */
+void orc_deblock_frame(uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs, int mbw, int mbh,
+                       const OrcMbInfo *mbi, int qp);
+/* emulation prevention: returns output length */
+int  orc_escape_rbsp(const uint8_t *in, int n, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,621 @@
+/*
+ * oracle/orc_encoder.c -- TEST INFRASTRUCTURE ONLY (see orc.h for scope and pinning status).
+ *
+ * Scalar restatement of one ISVCEncoder::EncodeFrame call (reference call site
+ * /root/reference/video_codec/VideoEncoderOpenH264.cpp:344) for the stream structure the wrapper
+ * fixes at :228-296 (Baseline, CAVLC, IPPP, one reference, deblocking idc 0, SPS+PPS with every
+ * IDR). Normative stages follow ITU-T H.264 (clauses quoted per function); encoder-side choices
+ * (search pattern, costs, mode decision) are the ones written down in DESIGN.md section 3 and are
+ * what media_b200/csrc must reproduce bit for bit. The phases mirror the CUDA pipeline:
+ *   A  pyramid + hierarchical ME + intra/inter choice   (parallel over MBs)
+ *   B  inter MBs: MC, transform, quant, reconstruction   (parallel over MBs)
+ *   C  intra MBs: prediction from reconstructed neighbours, mode decision, transform, recon (wavefront)
+ *   D  MV prediction, P_Skip detection                    (parallel over MBs)
+ *   E  in-loop deblocking                                 (wavefront)
+ *   F  CAVLC + NAL packaging                              (per slice)
+ */
+#include "orc_internal.h"
+#include "h264_tables.h"
+#include <stdlib.h>
+#include <string.h>
+
+#define HP_M 4   /* margin of the half-pel planes, see build_halfpel() */
+
+struct OrcEncoder {
+    OrcConfig cfg;
+    int mbw, mbh, wc, hc;
+    uint8_t *src[3], *rec[3], *dbk[3], *ref[3];
+    uint8_t *srcL1, *srcL2, *refL1, *refL2;
+    uint8_t *hpb, *hph, *hpj;        /* half-pel planes of ref luma, (wc+2M) x (hc+2M) */
+    OrcMbInfo *mbi; OrcMbCoef *coef;
+    int16_t *me[3];                  /* [level][mb*2] */
+    int32_t *inter_cost;
+    uint8_t *pred_y, *pred_c;        /* per-MB inter prediction: 256 luma, 2*64 chroma */
+    int *slice_row0;                 /* num_slices+1 entries */
+    int frame_num, idr_pic_id, have_ref;
+    uint8_t *rbsp; int rbsp_cap;
+};
+
+static inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+static inline int iabs(int v) { return v < 0 ? -v : v; }
+static inline int pxc(const uint8_t *p, int st, int w, int h, int x, int y) { return p[clip3(0, h - 1, y) * st + clip3(0, w - 1, x)]; }
+static inline int median3(int a, int b, int c) { int mx = a > b ? a : b, mn = a < b ? a : b; return c > mx ? mx : (c < mn ? mn : c); }
+
+OrcEncoder *orc_create(const OrcConfig *cfg)
+{
+    OrcEncoder *e = (OrcEncoder *)calloc(1, sizeof *e);
+    e->cfg = *cfg;
+    if (e->cfg.num_slices < 1) e->cfg.num_slices = 1;
+    if (e->cfg.search_range < 4) e->cfg.search_range = 16;
+    if (e->cfg.fps <= 0) e->cfg.fps = 30;
+    e->mbw = (cfg->width + 15) / 16; e->mbh = (cfg->height + 15) / 16;
+    if (e->cfg.num_slices > e->mbh) e->cfg.num_slices = e->mbh;
+    e->wc = e->mbw * 16; e->hc = e->mbh * 16;
+    size_t ny = (size_t)e->wc * e->hc, nc = ny / 4;
+    uint8_t **sets[4] = { e->src, e->rec, e->dbk, e->ref };
+    for (int s = 0; s < 4; s++) { sets[s][0] = calloc(1, ny); sets[s][1] = calloc(1, nc); sets[s][2] = calloc(1, nc); }
+    e->srcL1 = calloc(1, ny / 4); e->refL1 = calloc(1, ny / 4);
+    e->srcL2 = calloc(1, ny / 16); e->refL2 = calloc(1, ny / 16);
+    size_t nh = (size_t)(e->wc + 2 * HP_M) * (e->hc + 2 * HP_M);
+    e->hpb = malloc(nh); e->hph = malloc(nh); e->hpj = malloc(nh);
+    int n = e->mbw * e->mbh;
+    e->mbi = calloc(n, sizeof(OrcMbInfo)); e->coef = calloc(n, sizeof(OrcMbCoef));
+    for (int l = 0; l < 3; l++) e->me[l] = calloc(n * 2, sizeof(int16_t));
+    e->inter_cost = calloc(n, sizeof(int32_t));
+    e->pred_y = malloc((size_t)n * 256); e->pred_c = malloc((size_t)n * 128);
+    e->slice_row0 = calloc(e->cfg.num_slices + 1, sizeof(int));
+    { int base = e->mbh / e->cfg.num_slices, rem = e->mbh % e->cfg.num_slices, r = 0;
+      for (int s = 0; s < e->cfg.num_slices; s++) { e->slice_row0[s] = r; r += base + (s < rem); }
+      e->slice_row0[e->cfg.num_slices] = r; }
+    e->rbsp_cap = n * 1024 + 4096; e->rbsp = malloc(e->rbsp_cap);
+    return e;
+}
+
+void orc_destroy(OrcEncoder *e)
+{
+    if (!e) return;
+    uint8_t **sets[4] = { e->src, e->rec, e->dbk, e->ref };
+    for (int s = 0; s < 4; s++) for (int c = 0; c < 3; c++) free(sets[s][c]);
+    free(e->srcL1); free(e->srcL2); free(e->refL1); free(e->refL2);
+    free(e->hpb); free(e->hph); free(e->hpj);
+    free(e->mbi); free(e->coef); for (int l = 0; l < 3; l++) free(e->me[l]);
+    free(e->inter_cost); free(e->pred_y); free(e->pred_c); free(e->slice_row0); free(e->rbsp); free(e);
+}
+
+const OrcMbInfo *orc_mb_info(const OrcEncoder *e) { return e->mbi; }
+const OrcMbCoef *orc_mb_coef(const OrcEncoder *e) { return e->coef; }
+int orc_mb_count(const OrcEncoder *e) { return e->mbw * e->mbh; }
+const int16_t *orc_me_level(const OrcEncoder *e, int level) { return e->me[level]; }
+const int32_t *orc_inter_cost(const OrcEncoder *e) { return e->inter_cost; }
+const uint8_t *orc_plane(const OrcEncoder *e, int which, int comp, int *stride, int *w, int *h)
+{
+    uint8_t *const *set = which == 0 ? e->src : which == 1 ? e->rec : which == 2 ? e->dbk : e->ref;
+    int sh = comp ? 1 : 0;
+    if (stride) *stride = e->wc >> sh;
+    if (w) *w = e->wc >> sh;
+    if (h) *h = e->hc >> sh;
+    return set[comp];
+}
+void orc_get_recon(const OrcEncoder *e, uint8_t *out)
+{
+    int w = e->cfg.width, h = e->cfg.height;
+    for (int y = 0; y < h; y++) memcpy(out + (size_t)y * w, e->dbk[0] + (size_t)y * e->wc, w);
+    out += (size_t)w * h;
+    for (int c = 1; c < 3; c++, out += (size_t)(w / 2) * (h / 2))
+        for (int y = 0; y < h / 2; y++) memcpy(out + (size_t)y * (w / 2), e->dbk[c] + (size_t)y * (e->wc / 2), w / 2);
+}
+
+static int slice_of_row(const OrcEncoder *e, int row)
+{
+    int s = 0; while (row >= e->slice_row0[s + 1]) s++; return s;
+}
+/* is row `my` the first row of its slice (then no neighbour above is available, 6.4.9) */
+static int row_is_slice_top(const OrcEncoder *e, int my) { return e->slice_row0[slice_of_row(e, my)] == my; }
+
+/* ---- input: copy the display-size I420 frame into the coded-size planes, replicating the last
+ * column/row into the padding (the wrapper hands tightly packed I420, VideoEncoderOpenH264.cpp:354-365) ---- */
+static void load_source(OrcEncoder *e, const uint8_t *in)
+{
+    int w = e->cfg.width, h = e->cfg.height;
+    for (int c = 0; c < 3; c++) {
+        int pw = c ? w / 2 : w, ph = c ? h / 2 : h, cw = c ? e->wc / 2 : e->wc, ch = c ? e->hc / 2 : e->hc;
+        for (int y = 0; y < ch; y++) {
+            const uint8_t *s = in + (size_t)(y < ph ? y : ph - 1) * pw;
+            uint8_t *d = e->src[c] + (size_t)y * cw;
+            memcpy(d, s, pw);
+            for (int x = pw; x < cw; x++) d[x] = s[pw - 1];
+        }
+        in += (size_t)pw * ph;
+    }
+}
+
+/* ---- half-pel planes of the reference luma (8.4.2.2.1), margin HP_M with clamped sources ---- */
+static inline int tap6(int a, int b, int c, int d, int e_, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e_ + f; }
+static void build_halfpel(OrcEncoder *e)
+{
+    const uint8_t *r = e->ref[0]; int w = e->wc, h = e->hc, st = e->wc, ps = w + 2 * HP_M;
+    for (int y = -HP_M; y < h + HP_M; y++)
+        for (int x = -HP_M; x < w + HP_M; x++) {
+            int braw[6];
+            for (int k = 0; k < 6; k++) {
+                int yy = y - 2 + k;
+                braw[k] = tap6(pxc(r, st, w, h, x - 2, yy), pxc(r, st, w, h, x - 1, yy), pxc(r, st, w, h, x, yy),
+                               pxc(r, st, w, h, x + 1, yy), pxc(r, st, w, h, x + 2, yy), pxc(r, st, w, h, x + 3, yy));
+            }
+            size_t o = (size_t)(y + HP_M) * ps + x + HP_M;
+            e->hpb[o] = (uint8_t)clip255((braw[2] + 16) >> 5);
+            e->hph[o] = (uint8_t)clip255((tap6(pxc(r, st, w, h, x, y - 2), pxc(r, st, w, h, x, y - 1), pxc(r, st, w, h, x, y),
+                                               pxc(r, st, w, h, x, y + 1), pxc(r, st, w, h, x, y + 2), pxc(r, st, w, h, x, y + 3)) + 16) >> 5);
+            e->hpj[o] = (uint8_t)clip255((tap6(braw[0], braw[1], braw[2], braw[3], braw[4], braw[5]) + 512) >> 10);
+        }
+}
+static inline int hp(const OrcEncoder *e, const uint8_t *pl, int x, int y)
+{
+    return pl[(size_t)(clip3(-HP_M, e->hc + HP_M - 1, y) + HP_M) * (e->wc + 2 * HP_M) + clip3(-HP_M, e->wc + HP_M - 1, x) + HP_M];
+}
+/* same value as orc_interp_luma(ref, ...) -- tests/test_oracle_kernels.py checks the identity */
+static int qpel_sample(const OrcEncoder *e, int xq, int yq)
+{
+    int x = xq >> 2, y = yq >> 2, w = e->wc, h = e->hc; const uint8_t *r = e->ref[0];
+#define G_ pxc(r, w, w, h, x, y)
+#define H_ pxc(r, w, w, h, x + 1, y)
+#define M_ pxc(r, w, w, h, x, y + 1)
+#define b_ hp(e, e->hpb, x, y)
+#define s_ hp(e, e->hpb, x, y + 1)
+#define h_ hp(e, e->hph, x, y)
+#define m_ hp(e, e->hph, x + 1, y)
+#define j_ hp(e, e->hpj, x, y)
+    switch ((yq & 3) * 4 + (xq & 3)) {
+    case 0:  return G_;
+    case 1:  return (G_ + b_ + 1) >> 1;
+    case 2:  return b_;
+    case 3:  return (H_ + b_ + 1) >> 1;
+    case 4:  return (G_ + h_ + 1) >> 1;
+    case 5:  return (b_ + h_ + 1) >> 1;
+    case 6:  return (b_ + j_ + 1) >> 1;
+    case 7:  return (b_ + m_ + 1) >> 1;
+    case 8:  return h_;
+    case 9:  return (h_ + j_ + 1) >> 1;
+    case 10: return j_;
+    case 11: return (j_ + m_ + 1) >> 1;
+    case 12: return (M_ + h_ + 1) >> 1;
+    case 13: return (h_ + s_ + 1) >> 1;
+    case 14: return (j_ + s_ + 1) >> 1;
+    default: return (m_ + s_ + 1) >> 1;
+    }
+}
+int orc_dbg_qpel(const OrcEncoder *e, int xq, int yq) { return qpel_sample(e, xq, yq); }
+
+static void mc_luma(const OrcEncoder *e, int x0, int y0, int mvx, int mvy, uint8_t *dst /*16x16*/)
+{
+    for (int y = 0; y < 16; y++)
+        for (int x = 0; x < 16; x++) dst[y * 16 + x] = (uint8_t)qpel_sample(e, 4 * (x0 + x) + mvx, 4 * (y0 + y) + mvy);
+}
+static void mc_chroma(const OrcEncoder *e, int comp, int cx0, int cy0, int mvx, int mvy, uint8_t *dst /*8x8*/)
+{
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++)
+            dst[y * 8 + x] = (uint8_t)orc_interp_chroma(e->ref[comp], e->wc / 2, e->wc / 2, e->hc / 2,
+                                                        8 * (cx0 + x) + mvx, 8 * (cy0 + y) + mvy);
+}
+
+static int mv_bits(int mvx, int mvy) { return orc_se_len(mvx) + orc_se_len(mvy); }
+
+/* SAD of a bw x bh block with clamped coordinates on both planes (same dimensions w x h) */
+static int sad_clamped(const uint8_t *a, const uint8_t *b, int w, int h, int ax, int ay, int bx, int by, int bw, int bh)
+{
+    int s = 0;
+    for (int y = 0; y < bh; y++)
+        for (int x = 0; x < bw; x++) s += iabs(pxc(a, w, w, h, ax + x, ay + y) - pxc(b, w, w, h, bx + x, by + y));
+    return s;
+}
+
+/* ---- Phase A: hierarchical motion search for one MB (role of WelsMotionEstimateSearch + MeRefineFracPixel).
+ * Level 2 (1/4 res): 8x8 block centred on the MB, exhaustive +-R/4. Level 1 (1/2 res): 8x8, +-2 around 2*mv2.
+ * Level 0: 16x16, +-2 around 2*mv1 plus the zero vector. Then 8 half-pel and 8 quarter-pel neighbours by SATD.
+ * Every level picks argmin of key = (cost << k) | candidate_index, so ties resolve identically everywhere. ---- */
+static void motion_search(OrcEncoder *e, int mx, int my, int lambda)
+{
+    int mb = my * e->mbw + mx, R4 = e->cfg.search_range / 4, span = 2 * R4 + 1;
+    int w2 = e->wc / 4, h2 = e->hc / 4, w1 = e->wc / 2, h1 = e->hc / 2;
+    uint32_t best = 0xffffffffu; int bx = 0, by = 0;
+    for (int dy = -R4; dy <= R4; dy++)
+        for (int dx = -R4; dx <= R4; dx++) {
+            int c = sad_clamped(e->srcL2, e->refL2, w2, h2, 4 * mx - 2, 4 * my - 2, 4 * mx - 2 + dx, 4 * my - 2 + dy, 8, 8) + iabs(dx) + iabs(dy);
+            uint32_t key = ((uint32_t)c << 11) | (uint32_t)((dy + R4) * span + dx + R4);
+            if (key < best) { best = key; bx = dx; by = dy; }
+        }
+    e->me[2][mb * 2] = (int16_t)bx; e->me[2][mb * 2 + 1] = (int16_t)by;
+    int cx = 2 * bx, cy = 2 * by; best = 0xffffffffu;
+    for (int dy = -2; dy <= 2; dy++)
+        for (int dx = -2; dx <= 2; dx++) {
+            int vx = cx + dx, vy = cy + dy;
+            int c = sad_clamped(e->srcL1, e->refL1, w1, h1, 8 * mx, 8 * my, 8 * mx + vx, 8 * my + vy, 8, 8) + iabs(vx) + iabs(vy);
+            uint32_t key = ((uint32_t)c << 5) | (uint32_t)((dy + 2) * 5 + dx + 2);
+            if (key < best) { best = key; bx = vx; by = vy; }
+        }
+    e->me[1][mb * 2] = (int16_t)bx; e->me[1][mb * 2 + 1] = (int16_t)by;
+    cx = 2 * bx; cy = 2 * by; best = 0xffffffffu;
+    for (int i = 0; i < 26; i++) {
+        int vx = i < 25 ? cx + i % 5 - 2 : 0, vy = i < 25 ? cy + i / 5 - 2 : 0;
+        int c = sad_clamped(e->src[0], e->ref[0], e->wc, e->hc, 16 * mx, 16 * my, 16 * mx + vx, 16 * my + vy, 16, 16)
+              + lambda * mv_bits(4 * vx, 4 * vy);
+        uint32_t key = ((uint32_t)c << 5) | (uint32_t)i;
+        if (key < best) { best = key; bx = vx; by = vy; }
+    }
+    e->me[0][mb * 2] = (int16_t)bx; e->me[0][mb * 2 + 1] = (int16_t)by;
+    /* sub-pel: centre + 8 neighbours at step 2 (half), then at step 1 (quarter) */
+    static const int8_t OX[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 }, OY[9] = { 0, -1, -1, -1, 0, 0, 1, 1, 1 };
+    int qx = 4 * bx, qy = 4 * by; uint8_t pred[256];
+    const uint8_t *s = e->src[0] + (size_t)my * 16 * e->wc + mx * 16;
+    uint32_t centre_key = 0;
+    for (int step = 2; step >= 1; step--) {
+        best = 0xffffffffu; int nx = qx, ny = qy;
+        for (int i = 0; i < 9; i++) {
+            uint32_t key;
+            if (i == 0 && step == 1) key = centre_key & ~15u;
+            else {
+                int vx = qx + step * OX[i], vy = qy + step * OY[i];
+                mc_luma(e, 16 * mx, 16 * my, vx, vy, pred);
+                int c = orc_satd16x16(s, e->wc, pred, 16) + lambda * mv_bits(vx, vy);
+                key = ((uint32_t)c << 4) | (uint32_t)i;
+            }
+            if (key < best) { best = key; nx = qx + step * OX[i]; ny = qy + step * OY[i]; }
+        }
+        qx = nx; qy = ny; centre_key = best;
+    }
+    e->mbi[mb].mv[0] = (int16_t)qx; e->mbi[mb].mv[1] = (int16_t)qy;
+    e->inter_cost[mb] = (int32_t)(best >> 4);
+}
+
+/* ---- Phase A: intra estimate from SOURCE neighbours (V/H/DC 16x16), used only to choose intra vs inter
+ * in P frames without waiting for reconstructed neighbours. ---- */
+static int intra_estimate(const OrcEncoder *e, int mx, int my)
+{
+    const uint8_t *s = e->src[0] + (size_t)my * 16 * e->wc + mx * 16; int st = e->wc;
+    int top = !row_is_slice_top(e, my), left = mx > 0; uint8_t pred[256]; int best = 1 << 30;
+    if (top) { for (int y = 0; y < 16; y++) memcpy(pred + y * 16, s - st, 16);
+               int c = orc_satd16x16(s, st, pred, 16); if (c < best) best = c; }
+    if (left) { for (int y = 0; y < 16; y++) memset(pred + y * 16, s[y * st - 1], 16);
+                int c = orc_satd16x16(s, st, pred, 16); if (c < best) best = c; }
+    int sum = 0, dc;
+    if (top) for (int x = 0; x < 16; x++) sum += s[x - st];
+    if (left) for (int y = 0; y < 16; y++) sum += s[y * st - 1];
+    dc = top && left ? (sum + 16) >> 5 : (top || left) ? (sum + 8) >> 4 : 128;
+    memset(pred, dc, 256);
+    { int c = orc_satd16x16(s, st, pred, 16); if (c < best) best = c; }
+    return best;
+}
+#define ORC_INTRA_BIAS_BITS 16
+
+/* ---- transforms on DC terms ---- */
+static void hadamard4x4(const int *in, int *out)   /* H X H, no scaling */
+{
+    int t[16];
+    for (int y = 0; y < 4; y++) {
+        int a0 = in[y * 4] + in[y * 4 + 3], a1 = in[y * 4 + 1] + in[y * 4 + 2];
+        int a2 = in[y * 4 + 1] - in[y * 4 + 2], a3 = in[y * 4] - in[y * 4 + 3];
+        t[y * 4] = a0 + a1; t[y * 4 + 1] = a3 + a2; t[y * 4 + 2] = a0 - a1; t[y * 4 + 3] = a3 - a2;
+    }
+    for (int x = 0; x < 4; x++) {
+        int a0 = t[x] + t[12 + x], a1 = t[4 + x] + t[8 + x], a2 = t[4 + x] - t[8 + x], a3 = t[x] - t[12 + x];
+        out[x] = a0 + a1; out[4 + x] = a3 + a2; out[8 + x] = a0 - a1; out[12 + x] = a3 - a2;
+    }
+}
+static int quant_dc(int y, int qp)     /* (|y|*MF0 + 2f) >> (qbits+1), intra dead zone */
+{
+    int qbits = 15 + qp / 6, f = (1 << qbits) / 3;
+    int l = (int)(((int64_t)iabs(y) * QUANT_MF[qp % 6][0] + 2 * f) >> (qbits + 1));
+    if (l > 2063) l = 2063;
+    return y < 0 ? -l : l;
+}
+static int quant_dc_inter(int y, int qp)
+{
+    int qbits = 15 + qp / 6, f = (1 << qbits) / 6;
+    int l = (int)(((int64_t)iabs(y) * QUANT_MF[qp % 6][0] + 2 * f) >> (qbits + 1));
+    if (l > 2063) l = 2063;
+    return y < 0 ? -l : l;
+}
+
+/* chroma residual for one MB (both planes): fills coef, nnz, returns chroma cbp (8.5.11 on the decode side) */
+static int code_chroma(OrcEncoder *e, int mx, int my, const uint8_t *pred /*2 x 64*/, int qp, int intra)
+{
+    int mb = my * e->mbw + mx, qpc = CHROMA_QP[qp], cs = e->wc / 2, any_dc = 0, any_ac = 0;
+    OrcMbCoef *co = &e->coef[mb]; OrcMbInfo *mi = &e->mbi[mb];
+    for (int pl = 0; pl < 2; pl++) {
+        const uint8_t *s = e->src[1 + pl] + (size_t)my * 8 * cs + mx * 8;
+        uint8_t *r = e->rec[1 + pl] + (size_t)my * 8 * cs + mx * 8;
+        const uint8_t *p = pred + pl * 64;
+        int16_t c[4][16]; int dc[4];
+        for (int b = 0; b < 4; b++) {
+            int bx = (b & 1) * 4, by = (b >> 1) * 4; int16_t res[16];
+            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++)
+                res[y * 4 + x] = (int16_t)(s[(by + y) * cs + bx + x] - p[(by + y) * 8 + bx + x]);
+            orc_dct4x4(res, c[b]); dc[b] = c[b][0];
+            int n = orc_quant4x4(c[b], co->chroma_ac[pl][b], qpc, intra, 1);
+            mi->nnz[16 + pl * 4 + b] = (uint8_t)n; any_ac |= n;
+        }
+        int h[4] = { dc[0] + dc[1] + dc[2] + dc[3], dc[0] - dc[1] + dc[2] - dc[3], dc[0] + dc[1] - dc[2] - dc[3], dc[0] - dc[1] - dc[2] + dc[3] };
+        int l[4];
+        for (int i = 0; i < 4; i++) { l[i] = intra ? quant_dc(h[i], qpc) : quant_dc_inter(h[i], qpc); co->chroma_dc[pl][i] = (int16_t)l[i]; any_dc |= l[i]; }
+        /* 8.5.11.1/2: inverse 2x2 transform and scaling of chroma DC */
+        int f[4] = { l[0] + l[1] + l[2] + l[3], l[0] - l[1] + l[2] - l[3], l[0] + l[1] - l[2] - l[3], l[0] - l[1] - l[2] + l[3] };
+        for (int b = 0; b < 4; b++) {
+            int bx = (b & 1) * 4, by = (b >> 1) * 4; int32_t d[16], rr[16];
+            orc_dequant4x4(co->chroma_ac[pl][b], d, qpc, 1);
+            d[0] = ((f[b] * 16 * DEQUANT_V[qpc % 6][0]) << (qpc / 6)) >> 5;
+            orc_idct4x4(d, rr);
+            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++)
+                r[(by + y) * cs + bx + x] = (uint8_t)clip255(p[(by + y) * 8 + bx + x] + rr[y * 4 + x]);
+        }
+    }
+    return any_ac ? 2 : (any_dc ? 1 : 0);
+}
+
+/* ---- Phase B: one inter MB ---- */
+static void code_inter_mb(OrcEncoder *e, int mx, int my, int qp)
+{
+    int mb = my * e->mbw + mx, st = e->wc; OrcMbInfo *mi = &e->mbi[mb]; OrcMbCoef *co = &e->coef[mb];
+    uint8_t *py = e->pred_y + (size_t)mb * 256, *pc = e->pred_c + (size_t)mb * 128;
+    mc_luma(e, 16 * mx, 16 * my, mi->mv[0], mi->mv[1], py);
+    mc_chroma(e, 1, 8 * mx, 8 * my, mi->mv[0], mi->mv[1], pc);
+    mc_chroma(e, 2, 8 * mx, 8 * my, mi->mv[0], mi->mv[1], pc + 64);
+    const uint8_t *s = e->src[0] + (size_t)my * 16 * st + mx * 16; uint8_t *r = e->rec[0] + (size_t)my * 16 * st + mx * 16;
+    int cbp = 0;
+    memset(co, 0, sizeof *co);
+    for (int b = 0; b < 16; b++) {
+        int bx = BLK_X[b] * 4, by = BLK_Y[b] * 4; int16_t res[16], c[16]; int32_t d[16], rr[16];
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) res[y * 4 + x] = (int16_t)(s[(by + y) * st + bx + x] - py[(by + y) * 16 + bx + x]);
+        orc_dct4x4(res, c);
+        int n = orc_quant4x4(c, co->luma[b], qp, 0, 0);
+        mi->nnz[b] = (uint8_t)n; if (n) cbp |= 1 << (b >> 2);
+        orc_dequant4x4(co->luma[b], d, qp, 0); orc_idct4x4(d, rr);
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) r[(by + y) * st + bx + x] = (uint8_t)clip255(py[(by + y) * 16 + bx + x] + rr[y * 4 + x]);
+    }
+    cbp |= code_chroma(e, mx, my, pc, qp, 0) << 4;
+    mi->cbp = (uint8_t)cbp; mi->mb_type = ORC_MB_P16x16;
+}
+
+/* ---- intra predictors, 8.3.3 (Intra_16x16) and 8.3.4 (chroma), from the pre-deblock reconstruction ---- */
+static void pred_i16(const uint8_t *r, int st, int mode, int top, int left, uint8_t *p)
+{
+    if (mode == 0) { for (int y = 0; y < 16; y++) memcpy(p + y * 16, r - st, 16); }
+    else if (mode == 1) { for (int y = 0; y < 16; y++) memset(p + y * 16, r[y * st - 1], 16); }
+    else if (mode == 2) {
+        int sum = 0;
+        if (top) for (int x = 0; x < 16; x++) sum += r[x - st];
+        if (left) for (int y = 0; y < 16; y++) sum += r[y * st - 1];
+        memset(p, top && left ? (sum + 16) >> 5 : (top || left) ? (sum + 8) >> 4 : 128, 256);
+    } else {
+        int H = 0, V = 0;
+        for (int i = 0; i < 8; i++) { H += (i + 1) * (r[8 + i - st] - r[6 - i - st]); V += (i + 1) * (r[(8 + i) * st - 1] - r[(6 - i) * st - 1]); }
+        int a = 16 * (r[15 * st - 1] + r[15 - st]), b = (5 * H + 32) >> 6, c = (5 * V + 32) >> 6;
+        for (int y = 0; y < 16; y++) for (int x = 0; x < 16; x++) p[y * 16 + x] = (uint8_t)clip255((a + b * (x - 7) + c * (y - 7) + 16) >> 5);
+    }
+}
+static void pred_chroma(const uint8_t *r, int st, int mode, int top, int left, uint8_t *p /*8x8*/)
+{
+    if (mode == 0) {
+        for (int b = 0; b < 4; b++) {
+            int bx = (b & 1) * 4, by = (b >> 1) * 4, st_ = 0, sl = 0, v;
+            if (top) for (int x = 0; x < 4; x++) st_ += r[bx + x - st];
+            if (left) for (int y = 0; y < 4; y++) sl += r[(by + y) * st - 1];
+            if (b == 0 || b == 3) v = top && left ? (st_ + sl + 4) >> 3 : top ? (st_ + 2) >> 2 : left ? (sl + 2) >> 2 : 128;
+            else if (b == 1) v = top ? (st_ + 2) >> 2 : left ? (sl + 2) >> 2 : 128;
+            else v = left ? (sl + 2) >> 2 : top ? (st_ + 2) >> 2 : 128;
+            for (int y = 0; y < 4; y++) memset(p + (by + y) * 8 + bx, v, 4);
+        }
+    } else if (mode == 1) { for (int y = 0; y < 8; y++) memset(p + y * 8, r[y * st - 1], 8); }
+    else if (mode == 2) { for (int y = 0; y < 8; y++) memcpy(p + y * 8, r - st, 8); }
+    else {
+        int H = 0, V = 0;
+        for (int i = 0; i < 4; i++) { H += (i + 1) * (r[4 + i - st] - r[2 - i - st]); V += (i + 1) * (r[(4 + i) * st - 1] - r[(2 - i) * st - 1]); }
+        int a = 16 * (r[7 * st - 1] + r[7 - st]), b = (34 * H + 32) >> 6, c = (34 * V + 32) >> 6;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) p[y * 8 + x] = (uint8_t)clip255((a + b * (x - 3) + c * (y - 3) + 16) >> 5);
+    }
+}
+static int satd8x8(const uint8_t *a, int sa, const uint8_t *b, int sb)
+{
+    return orc_satd4x4(a, sa, b, sb) + orc_satd4x4(a + 4, sa, b + 4, sb) + orc_satd4x4(a + 4 * sa, sa, b + 4 * sb, sb) + orc_satd4x4(a + 4 * sa + 4, sa, b + 4 * sb + 4, sb);
+}
+
+/* ---- Phase C: one Intra_16x16 MB (roles of WelsMdI16x16, WelsIChromaPred*, WelsHadamardT4Dc_c, WelsDequantIHadamard4x4_c) ---- */
+static void code_intra_mb(OrcEncoder *e, int mx, int my, int qp)
+{
+    int mb = my * e->mbw + mx, st = e->wc, cs = st / 2; OrcMbInfo *mi = &e->mbi[mb]; OrcMbCoef *co = &e->coef[mb];
+    int top = !row_is_slice_top(e, my), left = mx > 0;
+    const uint8_t *s = e->src[0] + (size_t)my * 16 * st + mx * 16; uint8_t *r = e->rec[0] + (size_t)my * 16 * st + mx * 16;
+    uint8_t pred[256], best_pred[256]; uint32_t best = 0xffffffffu; int mode = 2;
+    memset(co, 0, sizeof *co);
+    for (int m = 0; m < 4; m++) {
+        if ((m == 0 && !top) || (m == 1 && !left) || (m == 3 && !(top && left))) continue;
+        pred_i16(r, st, m, top, left, pred);
+        uint32_t key = ((uint32_t)orc_satd16x16(s, st, pred, 16) << 2) | (uint32_t)m;
+        if (key < best) { best = key; mode = m; memcpy(best_pred, pred, 256); }
+    }
+    mi->mb_type = ORC_MB_I16x16; mi->i16_mode = (uint8_t)mode; mi->mv[0] = mi->mv[1] = 0;
+    /* luma: 16 forward transforms, DC Hadamard, quant, and the normative inverse (8.5.2, 8.5.10, 8.5.12) */
+    int16_t c[16][16]; int dcm[16], hd[16], any_ac = 0;
+    for (int b = 0; b < 16; b++) {
+        int bx = BLK_X[b] * 4, by = BLK_Y[b] * 4; int16_t res[16];
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) res[y * 4 + x] = (int16_t)(s[(by + y) * st + bx + x] - best_pred[(by + y) * 16 + bx + x]);
+        orc_dct4x4(res, c[b]);
+        dcm[BLK_Y[b] * 4 + BLK_X[b]] = c[b][0];
+        int n = orc_quant4x4(c[b], co->luma[b], qp, 1, 1);
+        mi->nnz[b] = (uint8_t)n; any_ac |= n;
+    }
+    hadamard4x4(dcm, hd);
+    int lev[16];
+    for (int i = 0; i < 16; i++) lev[i] = quant_dc((hd[i] + 1) >> 1, qp);
+    for (int i = 0; i < 16; i++) co->luma_dc[i] = (int16_t)lev[ZIGZAG4x4[i]];
+    int fdc[16]; hadamard4x4(lev, fdc);
+    int LS = 16 * DEQUANT_V[qp % 6][0];
+    for (int b = 0; b < 16; b++) {
+        int bx = BLK_X[b] * 4, by = BLK_Y[b] * 4; int32_t d[16], rr[16];
+        orc_dequant4x4(co->luma[b], d, qp, 1);
+        int f = fdc[BLK_Y[b] * 4 + BLK_X[b]];
+        d[0] = qp >= 36 ? (f * LS) << (qp / 6 - 6) : (f * LS + (1 << (5 - qp / 6))) >> (6 - qp / 6);
+        orc_idct4x4(d, rr);
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) r[(by + y) * st + bx + x] = (uint8_t)clip255(best_pred[(by + y) * 16 + bx + x] + rr[y * 4 + x]);
+    }
+    /* chroma mode: SATD over both planes, key = cost<<2 | mode */
+    const uint8_t *su = e->src[1] + (size_t)my * 8 * cs + mx * 8, *sv = e->src[2] + (size_t)my * 8 * cs + mx * 8;
+    const uint8_t *ru = e->rec[1] + (size_t)my * 8 * cs + mx * 8, *rv = e->rec[2] + (size_t)my * 8 * cs + mx * 8;
+    uint8_t pc[128], best_pc[128]; int cmode = 0; best = 0xffffffffu;
+    for (int m = 0; m < 4; m++) {
+        if ((m == 1 && !left) || (m == 2 && !top) || (m == 3 && !(top && left))) continue;
+        pred_chroma(ru, cs, m, top, left, pc); pred_chroma(rv, cs, m, top, left, pc + 64);
+        uint32_t key = ((uint32_t)(satd8x8(su, cs, pc, 8) + satd8x8(sv, cs, pc + 64, 8)) << 2) | (uint32_t)m;
+        if (key < best) { best = key; cmode = m; memcpy(best_pc, pc, 128); }
+    }
+    mi->chroma_mode = (uint8_t)cmode;
+    int ccbp = code_chroma(e, mx, my, best_pc, qp, 1);
+    mi->cbp = (uint8_t)((any_ac ? 15 : 0) | (ccbp << 4));
+}
+
+/* ---- Phase D: luma MV prediction for a 16x16 partition (8.4.1.3) and the P_Skip vector (8.4.1.1) ---- */
+static void predict_mv(const OrcEncoder *e, int mx, int my, int *pmx, int *pmy, int *skx, int *sky)
+{
+    int top_ok = !row_is_slice_top(e, my);
+    int availA = mx > 0, availB = top_ok, availC = top_ok && mx + 1 < e->mbw, availD = top_ok && mx > 0;
+    const OrcMbInfo *m = &e->mbi[my * e->mbw + mx];
+    const OrcMbInfo *A = availA ? m - 1 : 0, *B = availB ? m - e->mbw : 0, *C = availC ? m - e->mbw + 1 : (availD ? m - e->mbw - 1 : 0);
+    int availCD = availC || availD;
+    int refA = -1, refB = -1, refC = -1, ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
+#define IS_INTER(p) ((p)->mb_type == ORC_MB_P16x16 || (p)->mb_type == ORC_MB_PSKIP)
+    if (A && IS_INTER(A)) { refA = 0; ax = A->mv[0]; ay = A->mv[1]; }
+    if (B && IS_INTER(B)) { refB = 0; bx = B->mv[0]; by = B->mv[1]; }
+    if (C && IS_INTER(C)) { refC = 0; cx = C->mv[0]; cy = C->mv[1]; }
+    if (!availB && !availCD && availA) { refB = refA; bx = ax; by = ay; refC = refA; cx = ax; cy = ay; }
+    int n = (refA == 0) + (refB == 0) + (refC == 0);
+    if (n == 1) { if (refA == 0) { *pmx = ax; *pmy = ay; } else if (refB == 0) { *pmx = bx; *pmy = by; } else { *pmx = cx; *pmy = cy; } }
+    else { *pmx = median3(ax, bx, cx); *pmy = median3(ay, by, cy); }
+    if (!availA || !availB || (refA == 0 && ax == 0 && ay == 0) || (refB == 0 && bx == 0 && by == 0)) { *skx = 0; *sky = 0; }
+    else { *skx = *pmx; *sky = *pmy; }
+}
+
+/* ---- Phase F: macroblock layer syntax, 7.3.5 (role of WelsSpatialWriteMbSyn + WelsWriteMbResidual) ---- */
+static int nnz_ctx(const OrcEncoder *e, int mx, int my, int idx_cur, int idx_left_mb, int idx_top_mb, int has_left_in, int has_top_in)
+{
+    /* idx_cur unused; the caller passes neighbour indices: inside the MB (has_*_in) or in the adjacent MB */
+    (void)idx_cur;
+    const OrcMbInfo *m = &e->mbi[my * e->mbw + mx];
+    int nA = -1, nB = -1;
+    if (has_left_in) nA = m->nnz[idx_left_mb]; else if (mx > 0) nA = (m - 1)->nnz[idx_left_mb];
+    if (has_top_in) nB = m->nnz[idx_top_mb]; else if (!row_is_slice_top(e, my)) nB = (m - e->mbw)->nnz[idx_top_mb];
+    if (nA >= 0 && nB >= 0) return (nA + nB + 1) >> 1;
+    return nA >= 0 ? nA : (nB >= 0 ? nB : 0);
+}
+static const uint8_t XY2BLK[4][4] = { { 0, 1, 4, 5 }, { 2, 3, 6, 7 }, { 8, 9, 12, 13 }, { 10, 11, 14, 15 } };
+static int luma_nc(const OrcEncoder *e, int mx, int my, int b)
+{
+    int bx = BLK_X[b], by = BLK_Y[b];
+    return nnz_ctx(e, mx, my, b, bx > 0 ? XY2BLK[by][bx - 1] : XY2BLK[by][3], by > 0 ? XY2BLK[by - 1][bx] : XY2BLK[3][bx], bx > 0, by > 0);
+}
+static int chroma_nc(const OrcEncoder *e, int mx, int my, int pl, int b)
+{
+    int bx = b & 1, by = b >> 1, base = 16 + pl * 4;
+    return nnz_ctx(e, mx, my, b, base + by * 2 + (bx > 0 ? 0 : 1), base + (by > 0 ? 0 : 2) + bx, bx > 0, by > 0);
+}
+
+static void write_mb(OrcEncoder *e, BitWriter *b, int mx, int my, int is_p)
+{
+    int mb = my * e->mbw + mx; const OrcMbInfo *mi = &e->mbi[mb]; const OrcMbCoef *co = &e->coef[mb];
+    int cl = mi->cbp & 15, cc = mi->cbp >> 4;
+    if (mi->mb_type == ORC_MB_I16x16) {
+        bw_ue(b, (uint32_t)((is_p ? 5 : 0) + 1 + mi->i16_mode + 4 * cc + (cl ? 12 : 0)));
+        bw_ue(b, mi->chroma_mode);
+        bw_se(b, 0);                                           /* mb_qp_delta */
+        orc_write_residual_block(b, co->luma_dc, 16, luma_nc(e, mx, my, 0));
+        if (cl) for (int k = 0; k < 16; k++) orc_write_residual_block(b, co->luma[k] + 1, 15, luma_nc(e, mx, my, k));
+    } else {
+        int pmx, pmy, sx, sy; predict_mv(e, mx, my, &pmx, &pmy, &sx, &sy);
+        bw_ue(b, 0);                                           /* P_L0_16x16 */
+        bw_se(b, mi->mv[0] - pmx); bw_se(b, mi->mv[1] - pmy);
+        bw_ue(b, CBP_TO_CODENUM_INTER[mi->cbp]);
+        if (mi->cbp) bw_se(b, 0);
+        for (int k = 0; k < 16; k++) if (cl & (1 << (k >> 2))) orc_write_residual_block(b, co->luma[k], 16, luma_nc(e, mx, my, k));
+    }
+    if (cc) { orc_write_residual_block(b, co->chroma_dc[0], 4, -1); orc_write_residual_block(b, co->chroma_dc[1], 4, -1); }
+    if (cc == 2) for (int pl = 0; pl < 2; pl++) for (int k = 0; k < 4; k++)
+        orc_write_residual_block(b, co->chroma_ac[pl][k] + 1, 15, chroma_nc(e, mx, my, pl, k));
+}
+
+int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap)
+{
+    int is_idr = frame_type == 1 || !e->have_ref, n = e->mbw * e->mbh, lambda = LAMBDA_TAB[qp];
+    load_source(e, i420);
+    if (is_idr) { e->frame_num = 0; }
+    if (!is_idr) {
+        /* Phase A */
+        orc_downsample2(e->src[0], e->wc, e->wc, e->hc, e->srcL1, e->wc / 2);
+        orc_downsample2(e->srcL1, e->wc / 2, e->wc / 2, e->hc / 2, e->srcL2, e->wc / 4);
+        orc_downsample2(e->ref[0], e->wc, e->wc, e->hc, e->refL1, e->wc / 2);
+        orc_downsample2(e->refL1, e->wc / 2, e->wc / 2, e->hc / 2, e->refL2, e->wc / 4);
+        build_halfpel(e);
+        for (int my = 0; my < e->mbh; my++)
+            for (int mx = 0; mx < e->mbw; mx++) {
+                int mb = my * e->mbw + mx;
+                memset(&e->mbi[mb], 0, sizeof(OrcMbInfo));
+                motion_search(e, mx, my, lambda);
+                int ie = intra_estimate(e, mx, my);
+                e->mbi[mb].mb_type = (ie + lambda * ORC_INTRA_BIAS_BITS < e->inter_cost[mb]) ? ORC_MB_I16x16 : ORC_MB_P16x16;
+                if (e->mbi[mb].mb_type == ORC_MB_I16x16) e->mbi[mb].mv[0] = e->mbi[mb].mv[1] = 0;
+            }
+        /* Phase B */
+        for (int my = 0; my < e->mbh; my++)
+            for (int mx = 0; mx < e->mbw; mx++)
+                if (e->mbi[my * e->mbw + mx].mb_type == ORC_MB_P16x16) code_inter_mb(e, mx, my, qp);
+    } else {
+        memset(e->mbi, 0, (size_t)n * sizeof(OrcMbInfo));
+        for (int i = 0; i < n; i++) e->mbi[i].mb_type = ORC_MB_I16x16;
+    }
+    /* Phase C */
+    for (int my = 0; my < e->mbh; my++)
+        for (int mx = 0; mx < e->mbw; mx++)
+            if (e->mbi[my * e->mbw + mx].mb_type == ORC_MB_I16x16) code_intra_mb(e, mx, my, qp);
+    /* Phase D */
+    if (!is_idr)
+        for (int my = 0; my < e->mbh; my++)
+            for (int mx = 0; mx < e->mbw; mx++) {
+                OrcMbInfo *mi = &e->mbi[my * e->mbw + mx];
+                if (mi->mb_type != ORC_MB_P16x16 || mi->cbp) continue;
+                int pmx, pmy, sx, sy; predict_mv(e, mx, my, &pmx, &pmy, &sx, &sy);
+                if (mi->mv[0] == sx && mi->mv[1] == sy) mi->mb_type = ORC_MB_PSKIP;
+            }
+    /* Phase E */
+    for (int c = 0; c < 3; c++) memcpy(e->dbk[c], e->rec[c], (size_t)(c ? e->wc / 2 * e->hc / 2 : e->wc * e->hc));
+    orc_deblock_frame(e->dbk[0], e->wc, e->dbk[1], e->dbk[2], e->wc / 2, e->mbw, e->mbh, e->mbi, qp);
+    /* Phase F */
+    int o = 0;
+    if (is_idr) {
+        if (out_cap < 64) return -1;
+        int level = e->cfg.level_idc ? e->cfg.level_idc : orc_level_for(e->cfg.width, e->cfg.height, e->cfg.fps);
+        o += orc_write_sps(out + o, e->cfg.width, e->cfg.height, level);
+        o += orc_write_pps(out + o);
+    }
+    for (int s = 0; s < e->cfg.num_slices; s++) {
+        BitWriter b; bw_init(&b, e->rbsp, e->rbsp_cap);
+        int r0 = e->slice_row0[s], r1 = e->slice_row0[s + 1], run = 0;
+        orc_write_slice_header(&b, r0 * e->mbw, is_idr, e->frame_num, e->idr_pic_id, qp);
+        for (int my = r0; my < r1; my++)
+            for (int mx = 0; mx < e->mbw; mx++) {
+                if (!is_idr) {
+                    if (e->mbi[my * e->mbw + mx].mb_type == ORC_MB_PSKIP) { run++; continue; }
+                    bw_ue(&b, (uint32_t)run); run = 0;
+                }
+                write_mb(e, &b, mx, my, !is_idr);
+            }
+        if (run) bw_ue(&b, (uint32_t)run);
+        bw_trailing(&b);
+        if (b.overflow || o + 5 + b.pos + b.pos / 2 + 16 > out_cap) return -1;
+        out[o] = 0; out[o + 1] = 0; out[o + 2] = 0; out[o + 3] = 1; out[o + 4] = is_idr ? 0x65 : 0x61;
+        o += 5 + orc_escape_rbsp(e->rbsp, b.pos, out + o + 5);
+    }
+    /* the deblocked picture becomes the reference of the next frame */
+    for (int c = 0; c < 3; c++) memcpy(e->ref[c], e->dbk[c], (size_t)(c ? e->wc / 2 * e->hc / 2 : e->wc * e->hc));
+    e->have_ref = 1; e->frame_num = (e->frame_num + 1) & 255;
+    if (is_idr) e->idr_pic_id = (e->idr_pic_id + 1) & 1;
+    return o;
+}
