@@ -1,0 +1,520 @@
+// media_b200/csrc/engine.cu -- host engine and C ABI (include/b200enc.h) of the B200 H.264 encoder.
+//
+// What it stands in for: everything behind ISVCEncoder for the VideoEncoderOpenH264 wrapper
+// (reference: video_codec/VideoEncoderOpenH264.cpp:131-157 init, :228-296 policy, :304-352 per-frame call).
+// One session = one encoder object of the reference (own reference picture, rate-control state, bitstream buffer);
+// a batch advances N sessions of one GPU by one frame with a single chain of kernel launches.
+#include "../../include/b200enc.h"
+#include "h264_dev.cuh"
+#include "k_pre.cuh"
+#include "k_me.cuh"
+#include "k_intra.cuh"
+#include "k_deblock.cuh"
+#include "k_cavlc.cuh"
+#include "k_test.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+#define CU_TRY(expr, fail) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_last_cuda_error = (int)e_; fail; } } while (0)
+
+// ---- session -> GPU placement: least load by pixel rate (analogue of the Netint path's EN_ALLOC_LEAST_LOAD,
+// reference video_codec/VideoEncoderNetint.cpp:300-302,552-554) ----
+std::mutex g_sched_mu;
+std::vector<double> g_dev_load;
+int sched_acquire(int want, double load)
+{
+    std::lock_guard<std::mutex> lk(g_sched_mu);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return -1;
+    if ((int)g_dev_load.size() < n) g_dev_load.resize(n, 0.0);
+    int dev = want;
+    if (dev < 0) { dev = 0; for (int i = 1; i < n; i++) if (g_dev_load[i] < g_dev_load[dev]) dev = i; }
+    if (dev >= n) return -1;
+    g_dev_load[dev] += load;
+    return dev;
+}
+void sched_release(int dev, double load)
+{
+    std::lock_guard<std::mutex> lk(g_sched_mu);
+    if (dev >= 0 && dev < (int)g_dev_load.size()) g_dev_load[dev] -= load;
+}
+
+// ---- host bit writer for the parameter sets (7.3.2.1, 7.3.2.2) ----
+struct HostBits {
+    std::vector<uint8_t> buf; uint32_t acc = 0; int nacc = 0;
+    void put(int n, uint32_t v) { for (int i = n - 1; i >= 0; i--) { acc = (acc << 1) | ((v >> i) & 1); if (++nacc == 8) { buf.push_back((uint8_t)acc); acc = 0; nacc = 0; } } }
+    void ue(uint32_t v) { uint32_t x = v + 1; int l = 0; while ((x >> l) > 1) l++; put(l, 0); put(l + 1, x); }
+    void se(int v) { ue(v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
+    void trailing() { put(1, 1); while (nacc) put(1, 0); }
+};
+void append_nal(std::vector<uint8_t> &out, int hdr, const std::vector<uint8_t> &rbsp)
+{
+    out.insert(out.end(), { 0, 0, 0, 1, (uint8_t)hdr });
+    int zeros = 0;
+    for (uint8_t b : rbsp) {
+        if (zeros >= 2 && b <= 3) { out.push_back(3); zeros = 0; }
+        out.push_back(b); zeros = b == 0 ? zeros + 1 : 0;
+    }
+}
+int level_for(int w, int h, int fps)   // Table A-1: smallest level whose MaxFS and MaxMBPS cover the stream
+{
+    static const struct { int idc, mbps, fs; } L[] = {
+        { 10, 1485, 99 }, { 11, 3000, 396 }, { 12, 6000, 396 }, { 13, 11880, 396 }, { 20, 11880, 396 }, { 21, 19800, 792 },
+        { 22, 20250, 1620 }, { 30, 40500, 1620 }, { 31, 108000, 3600 }, { 32, 216000, 5120 }, { 40, 245760, 8192 },
+        { 42, 522240, 8704 }, { 50, 589824, 22080 }, { 51, 983040, 36864 }, { 52, 2073600, 36864 } };
+    const int fs = ((w + 15) / 16) * ((h + 15) / 16); const long mbps = (long)fs * fps;
+    for (auto &l : L) if (fs <= l.fs && mbps <= l.mbps) return l.idc;
+    return 52;
+}
+std::vector<uint8_t> make_parameter_sets(int w, int h, int level)
+{
+    std::vector<uint8_t> out;
+    const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
+    HostBits s;
+    s.put(8, 66); s.put(8, 0xC0); s.put(8, (uint32_t)level);
+    s.ue(0); s.ue(4); s.ue(2); s.ue(1); s.put(1, 0);
+    s.ue((uint32_t)(mbw - 1)); s.ue((uint32_t)(mbh - 1));
+    s.put(1, 1); s.put(1, 1);
+    const int cr = (mbw * 16 - w) / 2, cb = (mbh * 16 - h) / 2;
+    if (cr || cb) { s.put(1, 1); s.ue(0); s.ue((uint32_t)cr); s.ue(0); s.ue((uint32_t)cb); } else s.put(1, 0);
+    s.put(1, 0); s.trailing();
+    append_nal(out, 0x67, s.buf);
+    HostBits p;
+    p.ue(0); p.ue(0); p.put(1, 0); p.put(1, 0); p.ue(0); p.ue(0); p.ue(0); p.put(1, 0); p.put(2, 0);
+    p.se(0); p.se(0); p.se(0); p.put(1, 1); p.put(1, 0); p.put(1, 0); p.trailing();
+    append_nal(out, 0x68, p.buf);
+    return out;
+}
+
+// ---- rate control: frame-level QP from a bits ~ C / Qstep model with a virtual buffer (host logic; the
+// reference asks openh264 for RC_BITRATE_MODE at video_codec/VideoEncoderOpenH264.cpp:274, target = max bitrate :239-240) ----
+struct RateCtl {
+    double target = 0, vbv = 0, cplx[2] = { 0, 0 }; int last_qp[2] = { 30, 30 }; bool have[2] = { false, false };
+    static double qstep(int qp) { return std::pow(2.0, (qp - 4) / 6.0); }
+    int pick(int type, int w, int h)
+    {
+        if (!have[type]) {
+            if (type == 0 && have[1]) return std::min(51, last_qp[1] + 2);
+            const double bpp = target / ((double)w * h);
+            int qp = bpp > 0.2 ? 24 : bpp > 0.1 ? 28 : bpp > 0.05 ? 32 : bpp > 0.02 ? 36 : 40;
+            return type == 1 ? qp - 2 : qp;
+        }
+        const double weight = type == 1 ? 4.0 : 1.0;
+        double want = target * weight - 0.5 * vbv;
+        want = std::min(std::max(want, 0.3 * target * weight), 2.0 * target * weight);
+        int qp = (int)std::lround(4.0 + 6.0 * std::log2(cplx[type] / want));
+        qp = std::min(std::max(qp, last_qp[type] - 4), last_qp[type] + 4);
+        return std::min(std::max(qp, 12), 48);
+    }
+    void update(int type, int qp, double bits)
+    {
+        const double c = bits * qstep(qp);
+        cplx[type] = have[type] ? 0.5 * cplx[type] + 0.5 * c : c;
+        have[type] = true; last_qp[type] = qp;
+        vbv += bits - target;
+        vbv = std::min(std::max(vbv, -4.0 * target), 30.0 * target);
+    }
+};
+
+struct KernelTime { const char *name; cudaEvent_t ev0, ev1; };
+
+} // namespace
+
+struct b200enc_batch {
+    int device = 0, cap = 0;
+    cudaStream_t stream = nullptr;
+    Sess *h_sess = nullptr, *d_sess = nullptr;
+    WaveCtl *d_ctl = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0; int last_launches = 0;
+    bool profiling = false;
+    std::vector<KernelTime> ktimes; int n_ktimes = 0;
+};
+
+struct b200enc_session {
+    b200enc_config cfg;
+    Geom g;
+    int device = -1; double load = 0;
+    uint8_t *d_pool = nullptr; size_t pool_bytes = 0;
+    // device buffers (sub-allocated from d_pool)
+    uint8_t *input = nullptr, *src[3], *bufA[3], *bufB[3], *rec_pre[3];
+    uint8_t *srcL1, *srcL2, *refL1, *refL2;
+    MbInfo *mbi; MbCoef *coef; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
+    uint32_t *mb_bits, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
+    uint32_t rbsp_words_per_slice = 0;
+    // pinned, device-mapped output: [0..cap) bitstream, then one uint32 size
+    uint8_t *h_out = nullptr, *d_out = nullptr; uint32_t out_cap = 0;
+    bool cur_is_A = true;
+    uint32_t frame_index = 0; int frames_since_idr = 0, frame_num = 0, idr_pic_id = 0; bool force_idr = true, have_ref = false;
+    int last_qp = 26, last_type = 1;
+    RateCtl rc;
+    b200enc_batch *own = nullptr;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int batch_init(b200enc_batch *b, int device, int cap)
+{
+    b->device = device; b->cap = cap;
+    CU_TRY(cudaSetDevice(device), return B200ENC_ENODEV);
+    CU_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), return B200ENC_ENODEV);
+    CU_TRY(cudaHostAlloc(&b->h_sess, sizeof(Sess) * cap, cudaHostAllocDefault), return B200ENC_ENOMEM);
+    CU_TRY(cudaMalloc(&b->d_sess, sizeof(Sess) * cap), return B200ENC_ENOMEM);
+    CU_TRY(cudaMalloc(&b->d_ctl, sizeof(WaveCtl)), return B200ENC_ENOMEM);
+    CU_TRY(cudaEventCreate(&b->ev0), return B200ENC_ENODEV);
+    CU_TRY(cudaEventCreate(&b->ev1), return B200ENC_ENODEV);
+    return B200ENC_OK;
+}
+void batch_free(b200enc_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (auto &k : b->ktimes) { cudaEventDestroy(k.ev0); cudaEventDestroy(k.ev1); }
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->d_ctl) cudaFree(b->d_ctl);
+    if (b->d_sess) cudaFree(b->d_sess);
+    if (b->h_sess) cudaFreeHost(b->h_sess);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+__global__ void k_reset(const Sess *ss, Geom g, int nsess, WaveCtl *ctl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { ctl->ticket_intra = 0; ctl->ticket_dbk = 0; ctl->error = 0; }
+    if (i < nsess * g.mbh) { const Sess &s = ss[i / g.mbh]; s.row_prog_intra[i % g.mbh] = 0; s.row_prog_dbk[i % g.mbh] = 0; }
+}
+
+struct Prof {
+    b200enc_batch *b;
+    void begin(const char *name)
+    {
+        if (!b->profiling) return;
+        if (b->n_ktimes == (int)b->ktimes.size()) { KernelTime k; k.name = name; cudaEventCreate(&k.ev0); cudaEventCreate(&k.ev1); b->ktimes.push_back(k); }
+        b->ktimes[b->n_ktimes].name = name;
+        cudaEventRecord(b->ktimes[b->n_ktimes].ev0, b->stream);
+    }
+    void end() { if (!b->profiling) return; cudaEventRecord(b->ktimes[b->n_ktimes].ev1, b->stream); b->n_ktimes++; }
+};
+
+bool same_shape(const b200enc_session *a, const b200enc_session *c)
+{
+    return a->cfg.width == c->cfg.width && a->cfg.height == c->cfg.height && a->cfg.num_slices == c->cfg.num_slices &&
+           a->cfg.search_range == c->cfg.search_range && a->cfg.input_format == c->cfg.input_format && a->device == c->device;
+}
+
+int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8_t *const *frames, int device_input,
+                const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *infos)
+{
+    if (!b || !ss || n <= 0 || n > b->cap || !frames) return B200ENC_EINVAL;
+    for (int i = 0; i < n; i++) {
+        if (!ss[i] || !frames[i] || ss[i]->device != b->device || !same_shape(ss[0], ss[i])) return B200ENC_EINVAL;
+        for (int j = 0; j < i; j++) if (ss[j] == ss[i]) return B200ENC_EINVAL;
+    }
+    CU_TRY(cudaSetDevice(b->device), return B200ENC_ECUDA);
+    const Geom g = ss[0]->g;
+    const size_t in_bytes = b200enc_frame_bytes(ss[0]);
+    bool any_p = false;
+    for (int i = 0; i < n; i++) {
+        b200enc_session *s = ss[i];
+        const bool idr = s->force_idr || !s->have_ref || s->frames_since_idr >= s->cfg.gop;
+        const int qp = s->cfg.const_qp >= 0 ? s->cfg.const_qp : s->rc.pick(idr ? 1 : 0, s->cfg.width, s->cfg.height);
+        if (idr) { s->frame_num = 0; s->frames_since_idr = 0; }
+        s->last_qp = qp; s->last_type = idr ? 1 : 0;
+        any_p |= !idr;
+        uint8_t **cur = s->cur_is_A ? s->bufA : s->bufB, **ref = s->cur_is_A ? s->bufB : s->bufA;
+        Sess &d = b->h_sess[i];
+        if (device_input) d.input = frames[i];
+        else { d.input = s->input; CU_TRY(cudaMemcpyAsync(s->input, frames[i], in_bytes, cudaMemcpyHostToDevice, b->stream), return B200ENC_ECUDA); }
+        for (int c = 0; c < 3; c++) { d.src[c] = s->src[c]; d.rec[c] = cur[c]; d.ref[c] = ref[c]; }
+        d.srcL1 = s->srcL1; d.srcL2 = s->srcL2; d.refL1 = s->refL1; d.refL2 = s->refL2;
+        d.mbi = s->mbi; d.coef = s->coef; d.me2 = s->me2; d.me1 = s->me1; d.me0 = s->me0; d.inter_cost = s->inter_cost;
+        d.skip_run = s->skip_run; d.mb_bits = s->mb_bits; d.mb_slot = s->mb_slot; d.rbsp = s->rbsp; d.slice_bits = s->slice_bits;
+        d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
+        d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
+        d.qp = qp; d.is_idr = idr; d.frame_num = s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
+        d.rbsp_words_per_slice = s->rbsp_words_per_slice; d.out_cap = s->out_cap;
+    }
+    CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, b->stream), return B200ENC_ECUDA);
+    cudaStream_t st = b->stream;
+    const int nmb = g.mbw * g.mbh;
+    int launches = 0; b->n_ktimes = 0; Prof pf{ b };
+    cudaEventRecord(b->ev0, st);
+    pf.begin("k_reset"); k_reset<<<(n * g.mbh + 255) / 256, 256, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
+    if (ss[0]->cfg.input_format == B200ENC_FMT_RGBA) {
+        pf.begin("k_ingest_rgba"); k_ingest_rgba<<<dim3(((g.wc / 8) * (g.hc / 2) + 255) / 256, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end();
+    } else {
+        pf.begin("k_ingest_planar"); k_ingest_planar<<<dim3(((g.wc / 8) * g.hc * 3 / 2 + 255) / 256, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end();
+    }
+    launches++;
+    if (any_p) {
+        pf.begin("k_downsample0"); k_downsample<<<dim3(((g.wc / 8) * (g.hc / 2) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 0); pf.end();
+        pf.begin("k_downsample1"); k_downsample<<<dim3(((g.wc / 16) * (g.hc / 4) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 1); pf.end();
+        pf.begin("k_me_coarse"); k_me_coarse<<<dim3((nmb + ME_WARPS - 1) / ME_WARPS, 1, n), ME_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end();
+        pf.begin("k_me_fine"); k_me_fine<<<dim3((nmb + ME_WARPS - 1) / ME_WARPS, 1, n), ME_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end();
+        launches += 4;
+    }
+    const int wave_ctas = (n * g.mbh + WAVE_WARPS - 1) / WAVE_WARPS;
+    pf.begin("k_intra_wave"); k_intra_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
+    for (int i = 0; i < n; i++) if (ss[i]->cfg.debug) {
+        uint8_t **cur = ss[i]->cur_is_A ? ss[i]->bufA : ss[i]->bufB;
+        for (int c = 0; c < 3; c++) cudaMemcpyAsync(ss[i]->rec_pre[c], cur[c], (size_t)g.wc * g.hc / (c ? 4 : 1), cudaMemcpyDeviceToDevice, st);
+    }
+    pf.begin("k_pskip_scan"); k_pskip_scan<<<dim3(g.num_slices, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_deblock_wave"); k_deblock_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
+    pf.begin("k_cavlc_mb"); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_slice_pack"); k_slice_pack<<<dim3(g.num_slices, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_nal_pack"); k_nal_pack<<<n, 1024, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    cudaEventRecord(b->ev1, st);
+    WaveCtl ctl;
+    CU_TRY(cudaMemcpyAsync(&ctl, b->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, st), return B200ENC_ECUDA);
+    CU_TRY(cudaStreamSynchronize(st), return B200ENC_ECUDA);
+    CU_TRY(cudaGetLastError(), return B200ENC_ECUDA);
+    cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1);
+    b->last_launches = launches;
+    if (ctl.error) return B200ENC_EWAVE;
+    int rc = B200ENC_OK;
+    for (int i = 0; i < n; i++) {
+        b200enc_session *s = ss[i];
+        const uint32_t size = *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap);
+        if (size >= s->out_cap) rc = B200ENC_EOVERFLOW;
+        if (s->cfg.const_qp < 0) s->rc.update(s->last_type, s->last_qp, 8.0 * size);
+        if (bs) bs[i] = s->h_out;
+        if (bs_size) bs_size[i] = size;
+        if (infos) { infos[i].frame_type = s->last_type; infos[i].qp = s->last_qp; infos[i].size_bytes = size; infos[i].frame_index = s->frame_index; }
+        if (s->last_type == 1) s->idr_pic_id = (s->idr_pic_id + 1) & 1;
+        s->frame_num = (s->frame_num + 1) & 255; s->frames_since_idr++; s->frame_index++;
+        s->force_idr = false; s->have_ref = true; s->cur_is_A = !s->cur_is_A;
+    }
+    return rc;
+}
+
+} // namespace
+
+extern "C" {
+
+void b200enc_default_config(b200enc_config *c)
+{
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    // defaults of the reference wrapper: 720x1280, 30 fps, 5 Mbps, gop 30 (video_codec/VideoEncoderOpenH264.h:13-24)
+    c->width = 720; c->height = 1280; c->fps = 30; c->bitrate = 5000000; c->gop = 30; c->const_qp = -1;
+    c->num_slices = 1; c->search_range = 16; c->input_format = B200ENC_FMT_I420; c->device = -1;
+}
+
+int b200enc_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+int b200enc_last_cuda_error(void) { return g_last_cuda_error; }
+const char *b200enc_strerror(int code)
+{
+    switch (code) {
+    case B200ENC_OK: return "ok";
+    case B200ENC_EINVAL: return "invalid argument or unsupported configuration";
+    case B200ENC_ENODEV: return "no usable CUDA device (this encoder has no CPU fallback)";
+    case B200ENC_ENOMEM: return "out of memory";
+    case B200ENC_ECUDA: return "CUDA error during encode";
+    case B200ENC_ESIZE: return "input buffer smaller than one frame";
+    case B200ENC_EOVERFLOW: return "bitstream larger than the output buffer";
+    case B200ENC_EWAVE: return "wavefront watchdog fired";
+    default: return "unknown error";
+    }
+}
+
+int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
+{
+    if (!cfg || !out) return B200ENC_EINVAL;
+    *out = nullptr;
+    b200enc_config c = *cfg;
+    if (c.num_slices < 1) c.num_slices = 1;
+    if (c.search_range <= 0) c.search_range = 16;
+    if (c.fps <= 0) c.fps = 30;
+    if (c.gop <= 0) c.gop = 30;
+    if (c.width < 16 || c.width > 4096 || c.height < 16 || c.height > 4096 || (c.width & 1) || (c.height & 1)) return B200ENC_EINVAL;
+    if (c.search_range % 4 || c.search_range > 64 || c.num_slices > B200_MAX_SLICES || c.const_qp > 51) return B200ENC_EINVAL;
+    if (c.input_format < 0 || c.input_format > 2) return B200ENC_EINVAL;
+    if (c.const_qp < 0 && c.bitrate <= 0) return B200ENC_EINVAL;
+    b200enc_session *s = new (std::nothrow) b200enc_session();
+    if (!s) return B200ENC_ENOMEM;
+    s->cfg = c;
+    Geom &g = s->g;
+    g.width = c.width; g.height = c.height; g.mbw = (c.width + 15) / 16; g.mbh = (c.height + 15) / 16; g.wc = g.mbw * 16; g.hc = g.mbh * 16;
+    g.num_slices = std::min(c.num_slices, g.mbh); g.search_range = c.search_range; s->cfg.num_slices = g.num_slices;
+    { const int base = g.mbh / g.num_slices, rem = g.mbh % g.num_slices; int r = 0;
+      for (int i = 0; i < g.num_slices; i++) { g.slice_row0[i] = r; r += base + (i < rem); }
+      for (int i = g.num_slices; i <= B200_MAX_SLICES; i++) g.slice_row0[i] = r; }
+    s->load = (double)c.width * c.height * c.fps;
+    s->device = sched_acquire(c.device, s->load);
+    if (s->device < 0) { delete s; return B200ENC_ENODEV; }
+    int rc = B200ENC_OK;
+    do {
+        CU_TRY(cudaSetDevice(s->device), rc = B200ENC_ENODEV; break);
+        const size_t ny = (size_t)g.wc * g.hc, nc = ny / 4, nmb = (size_t)g.mbw * g.mbh;
+        const int max_slice_rows = g.mbh / g.num_slices + (g.mbh % g.num_slices ? 1 : 0);
+        s->rbsp_words_per_slice = (uint32_t)((size_t)max_slice_rows * g.mbw * B200_MB_SLOT_WORDS + 64);
+        const std::vector<uint8_t> ps = make_parameter_sets(c.width, c.height, c.level_idc ? c.level_idc : level_for(c.width, c.height, c.fps));
+        s->hdr_len = (int)ps.size();
+        struct Item { void **p; size_t bytes; };
+        std::vector<Item> items;
+        auto add = [&](auto &ptr, size_t bytes) { items.push_back({ reinterpret_cast<void **>(&ptr), bytes }); };
+        add(s->input, b200enc_frame_bytes(s));
+        for (int k = 0; k < 3; k++) { const size_t b = k ? nc : ny; add(s->src[k], b); add(s->bufA[k], b); add(s->bufB[k], b); add(s->rec_pre[k], c.debug ? b : 16); }
+        add(s->srcL1, ny / 4); add(s->refL1, ny / 4); add(s->srcL2, ny / 16); add(s->refL2, ny / 16);
+        add(s->mbi, nmb * sizeof(MbInfo)); add(s->coef, nmb * sizeof(MbCoef));
+        add(s->me2, nmb * 4); add(s->me1, nmb * 4); add(s->me0, nmb * 4); add(s->inter_cost, nmb * 4);
+        add(s->skip_run, (nmb + B200_MAX_SLICES) * 4); add(s->mb_bits, nmb * 4);
+        add(s->mb_slot, nmb * B200_MB_SLOT_WORDS * 4);
+        add(s->rbsp, (size_t)s->rbsp_words_per_slice * g.num_slices * 4);
+        add(s->slice_bits, B200_MAX_SLICES * 4); add(s->hdr, 256); add(s->row_prog, (size_t)g.mbh * 2 * 4);
+        size_t total = 0;
+        for (auto &it : items) total += align_up(it.bytes, 256);
+        CU_TRY(cudaMalloc(&s->d_pool, total), rc = B200ENC_ENOMEM; break);
+        s->pool_bytes = total;
+        CU_TRY(cudaMemset(s->d_pool, 0, total), rc = B200ENC_ECUDA; break);
+        size_t off = 0;
+        for (auto &it : items) { *it.p = s->d_pool + off; off += align_up(it.bytes, 256); }
+        CU_TRY(cudaMemcpy(s->hdr, ps.data(), ps.size(), cudaMemcpyHostToDevice), rc = B200ENC_ECUDA; break);
+        // output buffer: generous bound on a frame (every MB at the CAVLC worst case is ~1.4 KB; 1/2 of raw + 64 KB covers QP >= ~8 content)
+        s->out_cap = (uint32_t)align_up(std::max<size_t>(ny * 3 / 2, 1 << 16) + (1 << 16), 256);
+        CU_TRY(cudaHostAlloc(&s->h_out, s->out_cap + 256, cudaHostAllocMapped), rc = B200ENC_ENOMEM; break);
+        CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s->d_out), s->h_out, 0), rc = B200ENC_ECUDA; break);
+        memset(s->h_out, 0, s->out_cap + 256);
+        s->own = new (std::nothrow) b200enc_batch();
+        if (!s->own) { rc = B200ENC_ENOMEM; break; }
+        rc = batch_init(s->own, s->device, 1);
+        s->rc.target = (double)c.bitrate / c.fps;
+    } while (0);
+    if (rc != B200ENC_OK) { b200enc_destroy(s); return rc; }
+    *out = s;
+    return B200ENC_OK;
+}
+
+void b200enc_destroy(b200enc_session *s)
+{
+    if (!s) return;
+    if (s->device >= 0) {
+        cudaSetDevice(s->device);
+        if (s->own) batch_free(s->own);
+        if (s->h_out) cudaFreeHost(s->h_out);
+        if (s->d_pool) cudaFree(s->d_pool);
+        sched_release(s->device, s->load);
+    }
+    delete s;
+}
+
+size_t b200enc_frame_bytes(const b200enc_session *s)
+{
+    if (!s) return 0;
+    const size_t px = (size_t)s->cfg.width * s->cfg.height;
+    return s->cfg.input_format == B200ENC_FMT_RGBA ? px * 4 : px * 3 / 2;
+}
+int b200enc_device_of(const b200enc_session *s) { return s ? s->device : -1; }
+int b200enc_force_idr(b200enc_session *s) { if (!s) return B200ENC_EINVAL; s->force_idr = true; return B200ENC_OK; }
+
+int b200enc_encode(b200enc_session *s, const uint8_t *frame, uint32_t size, const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *info)
+{
+    if (!s || !frame) return B200ENC_EINVAL;
+    if (size < b200enc_frame_bytes(s)) return B200ENC_ESIZE;
+    return encode_impl(s->own, &s, 1, &frame, 0, bs, bs_size, info);
+}
+float b200enc_last_kernel_ms(const b200enc_session *s) { return s && s->own ? s->own->last_ms : 0.f; }
+
+int b200enc_batch_create(int device, int max_sessions, b200enc_batch **out)
+{
+    if (!out || max_sessions <= 0 || device < 0 || device >= b200enc_device_count()) return out && b200enc_device_count() == 0 ? B200ENC_ENODEV : B200ENC_EINVAL;
+    b200enc_batch *b = new (std::nothrow) b200enc_batch();
+    if (!b) return B200ENC_ENOMEM;
+    const int rc = batch_init(b, device, max_sessions);
+    if (rc != B200ENC_OK) { batch_free(b); return rc; }
+    *out = b;
+    return B200ENC_OK;
+}
+void b200enc_batch_destroy(b200enc_batch *b) { batch_free(b); }
+int b200enc_batch_encode(b200enc_batch *b, b200enc_session *const *sessions, int n, const uint8_t *const *frames, int device_input,
+                         const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *infos)
+{
+    return encode_impl(b, sessions, n, frames, device_input, bs, bs_size, infos);
+}
+float b200enc_batch_last_kernel_ms(const b200enc_batch *b) { return b ? b->last_ms : 0.f; }
+int b200enc_batch_last_launches(const b200enc_batch *b) { return b ? b->last_launches : 0; }
+int b200enc_batch_set_profiling(b200enc_batch *b, int on) { if (!b) return B200ENC_EINVAL; b->profiling = on != 0; return B200ENC_OK; }
+int b200enc_batch_kernel_times(const b200enc_batch *b, const char **names, float *ms, int cap)
+{
+    if (!b) return 0;
+    int n = 0;
+    for (; n < b->n_ktimes && n < cap; n++) { names[n] = b->ktimes[n].name; cudaEventElapsedTime(&ms[n], b->ktimes[n].ev0, b->ktimes[n].ev1); }
+    return n;
+}
+
+void *b200enc_host_alloc(size_t bytes) { void *p = nullptr; return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : nullptr; }
+void b200enc_host_free(void *p) { if (p) cudaFreeHost(p); }
+void *b200enc_dev_alloc(int device, size_t bytes) { void *p = nullptr; if (cudaSetDevice(device) != cudaSuccess) return nullptr; return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr; }
+int b200enc_dev_upload(int device, void *dst, const void *src, size_t bytes)
+{
+    CU_TRY(cudaSetDevice(device), return B200ENC_ECUDA);
+    CU_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice), return B200ENC_ECUDA);
+    return B200ENC_OK;
+}
+void b200enc_dev_free(int device, void *p) { if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p); }
+
+int b200enc_get_stage(b200enc_session *s, int stage, void *out, size_t cap, size_t *written)
+{
+    if (!s || !out) return B200ENC_EINVAL;
+    CU_TRY(cudaSetDevice(s->device), return B200ENC_ECUDA);
+    const size_t nmb = (size_t)s->g.mbw * s->g.mbh, ny = (size_t)s->g.wc * s->g.hc;
+    uint8_t **last = s->cur_is_A ? s->bufB : s->bufA;     // the frame just encoded (roles were swapped after it)
+    const void *src = nullptr; size_t bytes = 0; uint8_t **planes = nullptr;
+    switch (stage) {
+    case B200ENC_STAGE_MBINFO: src = s->mbi; bytes = nmb * sizeof(MbInfo); break;
+    case B200ENC_STAGE_MBCOEF: src = s->coef; bytes = nmb * sizeof(MbCoef); break;
+    case B200ENC_STAGE_ME2: src = s->me2; bytes = nmb * 4; break;
+    case B200ENC_STAGE_ME1: src = s->me1; bytes = nmb * 4; break;
+    case B200ENC_STAGE_ME0: src = s->me0; bytes = nmb * 4; break;
+    case B200ENC_STAGE_INTER_COST: src = s->inter_cost; bytes = nmb * 4; break;
+    case B200ENC_STAGE_SRC: planes = s->src; break;
+    case B200ENC_STAGE_REC_PRE: if (!s->cfg.debug) return B200ENC_EINVAL; planes = s->rec_pre; break;
+    case B200ENC_STAGE_REC: planes = last; break;
+    default: return B200ENC_EINVAL;
+    }
+    if (planes) {
+        bytes = ny * 3 / 2;
+        if (cap < bytes) return B200ENC_EINVAL;
+        uint8_t *o = static_cast<uint8_t *>(out);
+        CU_TRY(cudaMemcpy(o, planes[0], ny, cudaMemcpyDeviceToHost), return B200ENC_ECUDA);
+        CU_TRY(cudaMemcpy(o + ny, planes[1], ny / 4, cudaMemcpyDeviceToHost), return B200ENC_ECUDA);
+        CU_TRY(cudaMemcpy(o + ny + ny / 4, planes[2], ny / 4, cudaMemcpyDeviceToHost), return B200ENC_ECUDA);
+    } else {
+        if (cap < bytes) return B200ENC_EINVAL;
+        CU_TRY(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost), return B200ENC_ECUDA);
+    }
+    if (written) *written = bytes;
+    return B200ENC_OK;
+}
+
+int b200enc_get_recon(b200enc_session *s, uint8_t *i420, size_t cap)
+{
+    if (!s || !i420 || cap < (size_t)s->cfg.width * s->cfg.height * 3 / 2) return B200ENC_EINVAL;
+    CU_TRY(cudaSetDevice(s->device), return B200ENC_ECUDA);
+    uint8_t **last = s->cur_is_A ? s->bufB : s->bufA;
+    const int w = s->cfg.width, h = s->cfg.height, wc = s->g.wc;
+    CU_TRY(cudaMemcpy2D(i420, w, last[0], wc, w, h, cudaMemcpyDeviceToHost), return B200ENC_ECUDA);
+    CU_TRY(cudaMemcpy2D(i420 + (size_t)w * h, w / 2, last[1], wc / 2, w / 2, h / 2, cudaMemcpyDeviceToHost), return B200ENC_ECUDA);
+    CU_TRY(cudaMemcpy2D(i420 + (size_t)w * h * 5 / 4, w / 2, last[2], wc / 2, w / 2, h / 2, cudaMemcpyDeviceToHost), return B200ENC_ECUDA);
+    return B200ENC_OK;
+}
+
+} // extern "C"
+
+#include "k_test_abi.inl"

@@ -1,0 +1,262 @@
+// media_b200/csrc/h264_dev.cuh -- shared device-side definitions of the B200 H.264 encode path.
+//
+// This path replaces what ISVCEncoder::EncodeFrame does for VideoEncoderOpenH264
+// (reference: video_codec/VideoEncoderOpenH264.cpp:344; policy at :228-296). Tables are the normative
+// ITU-T H.264 ones (clause numbers beside each); the encoder-side choices are specified in DESIGN.md section 3.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+enum { MB_P16x16 = 0, MB_I16x16 = 1, MB_I4x4 = 2, MB_PSKIP = 3 };
+
+// Per-MB side information, 48 bytes. nnz: 0..15 luma blkIdx, 16..19 Cb, 20..23 Cr.
+struct __align__(16) MbInfo {
+    uint8_t mb_type, i16_mode, chroma_mode, cbp;
+    int16_t mv[2];
+    uint8_t i4_mode[16];
+    uint8_t nnz[24];
+};
+// Per-MB quantised levels in zig-zag order, 816 bytes.
+struct __align__(16) MbCoef {
+    int16_t luma[16][16];
+    int16_t luma_dc[16];
+    int16_t chroma_dc[2][4];
+    int16_t chroma_ac[2][4][16];
+};
+static_assert(sizeof(MbInfo) == 48, "MbInfo layout");
+static_assert(sizeof(MbCoef) == 816, "MbCoef layout");
+
+#define B200_MAX_SLICES 35        /* MAX_SLICES_NUM_TMP, vendor/openh264/codec_app_def.h:55-56 */
+#define B200_MB_SLOT_WORDS 352    /* per-MB CAVLC scratch: 11264 bits >= worst case (384 escapes * 28 + tokens) */
+
+// Geometry shared by every session of a batch.
+struct Geom {
+    int width, height;            // display size
+    int mbw, mbh, wc, hc;         // macroblock grid and coded size
+    int num_slices;
+    int slice_row0[B200_MAX_SLICES + 1];
+    int search_range;             // full-pel, multiple of 4
+};
+
+// Per-session, per-frame device descriptor (one array element per session in the batch).
+struct Sess {
+    const uint8_t *input;         // display-size frame in HBM: I420, NV12 or RGBA
+    uint8_t *src[3];              // coded-size source planes
+    uint8_t *rec[3];              // reconstruction of this frame (deblocked in place at the end)
+    uint8_t *ref[3];              // previous frame's deblocked reconstruction
+    uint8_t *srcL1, *srcL2, *refL1, *refL2;
+    MbInfo *mbi; MbCoef *coef;
+    int16_t *me2, *me1, *me0;     // per-level vectors (debug / parity dumps)
+    int32_t *inter_cost;
+    int32_t *skip_run;            // per MB: number of P_Skip MBs immediately before it in its slice
+    uint32_t *mb_bits;            // per MB: bit length of its macroblock_layer() (+ preceding mb_skip_run)
+    uint32_t *mb_slot;            // per MB: B200_MB_SLOT_WORDS words of bits, MSB first
+    uint32_t *rbsp;               // per slice region: concatenated slice_data bits
+    uint32_t *slice_bits;         // per slice: total RBSP bits (header + data + trailing)
+    uint8_t *out;                 // Annex-B access unit (mapped pinned host memory or HBM)
+    uint32_t *out_size;           // bytes written to out
+    const uint8_t *hdr; int hdr_len;   // SPS+PPS NALs, prepended on IDR
+    int *row_prog_intra, *row_prog_dbk; // wavefront progress counters, one per MB row
+    int qp, is_idr, frame_num, idr_pic_id, input_format;
+    uint32_t rbsp_words_per_slice, out_cap;
+};
+
+// ---- normative tables ----
+// Table 9-5 coeff_token: [nC class][4*total_coeff + trailing_ones] (length, bits)
+static __device__ __constant__ uint8_t c_coeff_token_len[4 * 68] = {
+     1,  0,  0,  0,  6,  2,  0,  0,  8,  6,  3,  0,  9,  8,  7,  5, 10,  9,  8,  6, 11, 10,  9,  7, 13, 11, 10,  8, 13, 13, 11,  9,
+    13, 13, 13, 10, 14, 14, 13, 11, 14, 14, 14, 13, 15, 15, 14, 14, 15, 15, 15, 14, 16, 15, 15, 15, 16, 16, 16, 15, 16, 16, 16, 16,
+    16, 16, 16, 16,  2,  0,  0,  0,  6,  2,  0,  0,  6,  5,  3,  0,  7,  6,  6,  4,  8,  6,  6,  4,  8,  7,  7,  5,  9,  8,  8,  6,
+    11,  9,  9,  6, 11, 11, 11,  7, 12, 11, 11,  9, 12, 12, 12, 11, 12, 12, 12, 11, 13, 13, 13, 12, 13, 13, 13, 13, 13, 14, 13, 13,
+    14, 14, 14, 13, 14, 14, 14, 14,  4,  0,  0,  0,  6,  4,  0,  0,  6,  5,  4,  0,  6,  5,  5,  4,  7,  5,  5,  4,  7,  5,  5,  4,
+     7,  6,  6,  4,  7,  6,  6,  4,  8,  7,  7,  5,  8,  8,  7,  6,  9,  8,  8,  7,  9,  9,  8,  8,  9,  9,  9,  8, 10,  9,  9,  9,
+    10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10,  6,  0,  0,  0,  6,  6,  0,  0,  6,  6,  6,  0,  6,  6,  6,  6,  6,  6,  6,  6,
+     6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,
+     6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,  6,
+};
+static __device__ __constant__ uint8_t c_coeff_token_bits[4 * 68] = {
+     1,  0,  0,  0,  5,  1,  0,  0,  7,  4,  1,  0,  7,  6,  5,  3,  7,  6,  5,  3,  7,  6,  5,  4, 15,  6,  5,  4, 11, 14,  5,  4,
+     8, 10, 13,  4, 15, 14,  9,  4, 11, 10, 13, 12, 15, 14,  9, 12, 11, 10, 13,  8, 15,  1,  9, 12, 11, 14, 13,  8,  7, 10,  9, 12,
+     4,  6,  5,  8,  3,  0,  0,  0, 11,  2,  0,  0,  7,  7,  3,  0,  7, 10,  9,  5,  7,  6,  5,  4,  4,  6,  5,  6,  7,  6,  5,  8,
+    15,  6,  5,  4, 11, 14, 13,  4, 15, 10,  9,  4, 11, 14, 13, 12,  8, 10,  9,  8, 15, 14, 13, 12, 11, 10,  9, 12,  7, 11,  6,  8,
+     9,  8, 10,  1,  7,  6,  5,  4, 15,  0,  0,  0, 15, 14,  0,  0, 11, 15, 13,  0,  8, 12, 14, 12, 15, 10, 11, 11, 11,  8,  9, 10,
+     9, 14, 13,  9,  8, 10,  9,  8, 15, 14, 13, 13, 11, 14, 10, 12, 15, 10, 13, 12, 11, 14,  9, 12,  8, 10, 13,  8, 13,  7,  9, 12,
+     9, 12, 11, 10,  5,  8,  7,  6,  1,  4,  3,  2,  3,  0,  0,  0,  0,  1,  0,  0,  4,  5,  6,  0,  8,  9, 10, 11, 12, 13, 14, 15,
+    16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47,
+    48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63,
+};
+static __device__ __constant__ uint8_t c_cdc_token_len[20] = { 2, 0, 0, 0, 6, 1, 0, 0, 6, 6, 3, 0, 6, 7, 7, 6, 6, 8, 8, 7 };
+static __device__ __constant__ uint8_t c_cdc_token_bits[20] = { 1, 0, 0, 0, 7, 1, 0, 0, 4, 6, 1, 0, 3, 3, 2, 5, 2, 3, 2, 0 };
+// Tables 9-7/9-8 total_zeros: [total_coeff-1][total_zeros]
+static __device__ __constant__ uint8_t c_total_zeros_len[15 * 16] = {
+    1, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 9,  3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6, 6, 6, 0,
+    4, 3, 3, 3, 4, 4, 3, 3, 4, 5, 5, 6, 5, 6, 0, 0,  5, 3, 4, 4, 3, 3, 3, 4, 3, 4, 5, 5, 5, 0, 0, 0,
+    4, 4, 4, 3, 3, 3, 3, 3, 4, 5, 4, 5, 0, 0, 0, 0,  6, 5, 3, 3, 3, 3, 3, 3, 4, 3, 6, 0, 0, 0, 0, 0,
+    6, 5, 3, 3, 3, 2, 3, 4, 3, 6, 0, 0, 0, 0, 0, 0,  6, 4, 5, 3, 2, 2, 3, 3, 6, 0, 0, 0, 0, 0, 0, 0,
+    6, 6, 4, 2, 2, 3, 2, 5, 0, 0, 0, 0, 0, 0, 0, 0,  5, 5, 3, 2, 2, 2, 4, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    4, 4, 3, 3, 1, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  4, 4, 2, 1, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    3, 3, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  2, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+};
+static __device__ __constant__ uint8_t c_total_zeros_bits[15 * 16] = {
+    1, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 1,  7, 6, 5, 4, 3, 5, 4, 3, 2, 3, 2, 3, 2, 1, 0, 0,
+    5, 7, 6, 5, 4, 3, 4, 3, 2, 3, 2, 1, 1, 0, 0, 0,  3, 7, 5, 4, 6, 5, 4, 3, 3, 2, 2, 1, 0, 0, 0, 0,
+    5, 4, 3, 7, 6, 5, 4, 3, 2, 1, 1, 0, 0, 0, 0, 0,  1, 1, 7, 6, 5, 4, 3, 2, 1, 1, 0, 0, 0, 0, 0, 0,
+    1, 1, 5, 4, 3, 3, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0,  1, 1, 1, 3, 3, 2, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0,
+    1, 0, 1, 3, 2, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0,  1, 0, 1, 3, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 1, 1, 2, 1, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  0, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+};
+static __device__ __constant__ uint8_t c_cdc_total_zeros_len[12] = { 1, 2, 3, 3, 1, 2, 2, 0, 1, 1, 0, 0 };
+static __device__ __constant__ uint8_t c_cdc_total_zeros_bits[12] = { 1, 1, 1, 0, 1, 1, 0, 0, 1, 0, 0, 0 };
+// Table 9-10 run_before: [min(zeros_left,7)-1][run_before]
+static __device__ __constant__ uint8_t c_run_before_len[7 * 16] = {
+    1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  1, 2, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    2, 2, 2, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  2, 2, 2, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    2, 2, 3, 3, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  2, 3, 3, 3, 3, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    3, 3, 3, 3, 3, 3, 3, 4, 5, 6, 7, 8, 9, 10, 11, 0,
+};
+static __device__ __constant__ uint8_t c_run_before_bits[7 * 16] = {
+    1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    3, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  3, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    3, 2, 3, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  3, 0, 1, 3, 2, 5, 4, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    7, 6, 5, 4, 3, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0,
+};
+// zig-zag scan index -> raster position (Figure 8-8); 4x4 luma block index -> (x, y) (Figure 6-10)
+static __device__ __constant__ uint8_t c_zigzag[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };
+// quantiser multipliers MF[qp%6][class] (JM), LevelScale core v[qp%6][class] (8.5.9); class: 0 (even,even) 1 (odd,odd) 2 rest
+static __device__ __constant__ uint16_t c_quant_mf[6][3] = { { 13107, 5243, 8066 }, { 11916, 4660, 7490 }, { 10082, 4194, 6554 },
+                                                      { 9362, 3647, 5825 }, { 8192, 3355, 5243 }, { 7282, 2893, 4559 } };
+static __device__ __constant__ uint8_t c_dequant_v[6][3] = { { 10, 16, 13 }, { 11, 18, 14 }, { 13, 20, 16 }, { 14, 23, 18 }, { 16, 25, 20 }, { 18, 29, 23 } };
+// Table 8-15 (chroma_qp_index_offset 0)
+static __device__ __constant__ uint8_t c_chroma_qp[52] = {
+     0,  1,  2,  3,  4,  5,  6,  7,  8,  9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25,
+    26, 27, 28, 29, 29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39 };
+// Tables 8-16 / 8-17
+static __device__ __constant__ uint8_t c_alpha[52] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20, 22, 25, 28,
+    32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255 };
+static __device__ __constant__ uint8_t c_beta[52] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7, 8, 8,
+    9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18 };
+static __device__ __constant__ uint8_t c_tc0[52][3] = {
+    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},
+    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,1},{0,0,1},{0,0,1},{0,0,1},{0,1,1},{0,1,1},{1,1,1},
+    {1,1,1},{1,1,1},{1,1,1},{1,1,2},{1,1,2},{1,1,2},{1,1,2},{1,2,3},{1,2,3},{2,2,3},{2,2,4},{2,3,4},
+    {2,3,4},{3,3,5},{3,4,6},{3,4,6},{4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},
+    {9,12,18},{10,13,20},{11,15,23},{13,17,25} };
+// Table 9-4 me(v) for Inter macroblocks, ChromaArrayType 1: cbp -> codeNum
+static __device__ __constant__ uint8_t c_cbp_inter[48] = {
+     0,  2,  3,  7,  4,  8, 17, 13,  5, 18,  9, 14, 10, 15, 16, 11,  1, 32, 33, 36, 34, 37, 44, 40, 35, 45, 38, 41, 39, 42, 43, 19,
+     6, 24, 25, 20, 26, 21, 46, 28, 27, 47, 22, 29, 23, 30, 31, 12 };
+// Lagrangian, round(2^((qp-12)/6)) floored at 1 (encoder-side choice)
+static __device__ __constant__ uint8_t c_lambda[52] = {
+     1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  2,  2,  2,  2,  3,  3,  3,  4,  4,  4,
+     5,  6,  6,  7,  8,  9, 10, 11, 13, 14, 16, 18, 20, 23, 25, 29, 32, 36, 40, 45, 51, 57, 64, 72, 81, 91 };
+
+// ---- small helpers ----
+// packed 4 x u8 sum of absolute differences with accumulate: one VABSDIFF4.U8.ACC on sm_100a
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t acc) { return __vsadu4(a, b) + acc; }
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int blk_x(int b) { return (b & 1) | ((b >> 1) & 2); }      // Figure 6-10
+__device__ __forceinline__ int blk_y(int b) { return ((b >> 1) & 1) | ((b >> 2) & 2); }
+__device__ __forceinline__ int xy2blk(int x, int y) { return (x & 1) | ((y & 1) << 1) | ((x & 2) << 1) | ((y & 2) << 2); }
+__device__ __forceinline__ int pos_class(int pos) { return ((pos & 1) && (pos & 4)) ? 1 : ((pos & 5) ? 2 : 0); }
+__device__ __forceinline__ int se_len(int v) { unsigned x = (v > 0 ? 2u * v - 1u : (unsigned)(-2 * v)) + 1u; return 2 * (31 - __clz(x)) + 1; }
+__device__ __forceinline__ int ue_len(unsigned v) { return 2 * (31 - __clz(v + 1u)) + 1; }
+__device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+__device__ __forceinline__ bool row_is_slice_top(const Geom &g, int my)
+{
+    bool t = false;
+    for (int s = 0; s < g.num_slices; s++) t |= (g.slice_row0[s] == my);
+    return t;
+}
+
+// forward core transform of a 4x4 residual held in registers (role of WelsDctT4_c)
+__device__ __forceinline__ void fdct4x4(int r[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        int a0 = r[y * 4] + r[y * 4 + 3], a1 = r[y * 4 + 1] + r[y * 4 + 2], a2 = r[y * 4 + 1] - r[y * 4 + 2], a3 = r[y * 4] - r[y * 4 + 3];
+        r[y * 4] = a0 + a1; r[y * 4 + 1] = 2 * a3 + a2; r[y * 4 + 2] = a0 - a1; r[y * 4 + 3] = a3 - 2 * a2;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int a0 = r[x] + r[12 + x], a1 = r[4 + x] + r[8 + x], a2 = r[4 + x] - r[8 + x], a3 = r[x] - r[12 + x];
+        r[x] = a0 + a1; r[4 + x] = 2 * a3 + a2; r[8 + x] = a0 - a1; r[12 + x] = a3 - 2 * a2;
+    }
+}
+// inverse core transform with the final (x+32)>>6, 8.5.12.2 (role of WelsIDctT4Rec_c)
+__device__ __forceinline__ void idct4x4(int d[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        int e0 = d[y * 4] + d[y * 4 + 2], e1 = d[y * 4] - d[y * 4 + 2], e2 = (d[y * 4 + 1] >> 1) - d[y * 4 + 3], e3 = d[y * 4 + 1] + (d[y * 4 + 3] >> 1);
+        d[y * 4] = e0 + e3; d[y * 4 + 1] = e1 + e2; d[y * 4 + 2] = e1 - e2; d[y * 4 + 3] = e0 - e3;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int g0 = d[x] + d[8 + x], g1 = d[x] - d[8 + x], g2 = (d[4 + x] >> 1) - d[12 + x], g3 = d[4 + x] + (d[12 + x] >> 1);
+        d[x] = (g0 + g3 + 32) >> 6; d[4 + x] = (g1 + g2 + 32) >> 6; d[8 + x] = (g1 - g2 + 32) >> 6; d[12 + x] = (g0 - g3 + 32) >> 6;
+    }
+}
+// 4x4 Hadamard SATD of a difference block in registers: sum|H d H^T| / 2 (role of WelsSampleSatd4x4_c)
+__device__ __forceinline__ int satd4x4(int d[16])
+{
+    int s = 0;
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        int a0 = d[y * 4] + d[y * 4 + 1], a1 = d[y * 4] - d[y * 4 + 1], a2 = d[y * 4 + 2] + d[y * 4 + 3], a3 = d[y * 4 + 2] - d[y * 4 + 3];
+        d[y * 4] = a0 + a2; d[y * 4 + 1] = a1 + a3; d[y * 4 + 2] = a0 - a2; d[y * 4 + 3] = a1 - a3;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int a0 = d[x] + d[4 + x], a1 = d[x] - d[4 + x], a2 = d[8 + x] + d[12 + x], a3 = d[8 + x] - d[12 + x];
+        s += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
+    }
+    return s >> 1;
+}
+// Quantiser parameters for one QP
+struct QParam { int qbits, f_intra, f_inter, mf[3], v[3], sh; };
+__device__ __forceinline__ QParam make_qparam(int qp)
+{
+    QParam q; int m = qp % 6; q.sh = qp / 6; q.qbits = 15 + q.sh;
+    q.f_intra = (1 << q.qbits) / 3; q.f_inter = (1 << q.qbits) / 6;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { q.mf[i] = c_quant_mf[m][i]; q.v[i] = c_dequant_v[m][i]; }
+    return q;
+}
+#define B200_MAX_LEVEL 2063
+// quantise raster coefficients in c[] -> zig-zag levels lz[], then overwrite c[] with the dequantised values
+// (8.5.12.1, flat scaling). ac_only: position 0 is skipped (level 0, dequantised 0). Returns the number of nonzero levels.
+__device__ __forceinline__ int quant_dequant4x4(int c[16], int16_t lz[16], const QParam &q, int f, bool ac_only)
+{
+    int nnz = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int zz[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };
+        int pos = zz[i], cl = ((pos & 1) && (pos & 4)) ? 1 : ((pos & 5) ? 2 : 0);
+        if (ac_only && i == 0) { lz[0] = 0; c[0] = 0; continue; }
+        int v = c[pos];
+        int l = min((int)(((unsigned)abs(v) * (unsigned)q.mf[cl] + (unsigned)f) >> q.qbits), B200_MAX_LEVEL);
+        l = v < 0 ? -l : l;
+        lz[i] = (int16_t)l; nnz += (l != 0);
+        c[pos] = (l * q.v[cl]) << q.sh;
+    }
+    return nnz;
+}
+__device__ __forceinline__ int quant_dc(int y, const QParam &q, int f)
+{
+    int l = min((int)(((unsigned)abs(y) * (unsigned)q.mf[0] + 2u * (unsigned)f) >> (q.qbits + 1)), B200_MAX_LEVEL);
+    return y < 0 ? -l : l;
+}
+
+// acquire/release on the wavefront progress counters
+__device__ __forceinline__ int ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+} // namespace b200

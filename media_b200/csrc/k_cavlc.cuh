@@ -1,0 +1,380 @@
+// media_b200/csrc/k_cavlc.cuh -- entropy coding and NAL packaging (phases D and F of DESIGN.md 3).
+//
+// Role inside the reference: slice-data writing inside ISVCEncoder::EncodeFrame
+// (video_codec/VideoEncoderOpenH264.cpp:344; openh264's WelsSpatialWriteMbSyn, WelsWriteMbResidual,
+// WriteBlockResidualCavlc, CavlcParamCal_c in the absent libopenh264) and the layout contract of the output
+// buffer (:349-350: all NALs contiguous, 4-byte start codes, SPS+PPS in front of every IDR).
+//   k_pskip_scan : MV prediction (8.4.1.3), P_Skip detection (8.4.1.1), mb_skip_run per MB      [CTA per slice]
+//   k_cavlc_mb   : macroblock_layer() of every coded MB into its own scratch slot; the 28 syntax groups of an MB
+//                  (header, luma DC, 16 luma, 2 chroma DC, 8 chroma AC) are coded by 28 lanes in parallel after a
+//                  warp prefix sum of their code lengths                                          [warp per MB]
+//   k_slice_pack : slice header + bit-exact concatenation of the MB slots by a prefix sum of MB lengths [CTA per slice]
+//   k_nal_pack   : start codes, NAL headers, emulation prevention (7.4.1), final access unit      [CTA per session]
+#pragma once
+#include "h264_dev.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ bool is_inter_type(int t) { return t == MB_P16x16 || t == MB_PSKIP; }
+
+// 8.4.1.3 for a 16x16 partition with one reference picture, and the P_Skip vector of 8.4.1.1
+__device__ __forceinline__ void predict_mv(const Sess &s, const Geom &g, int mx, int my, int &pmx, int &pmy, int &skx, int &sky)
+{
+    const bool top_ok = !row_is_slice_top(g, my);
+    const bool aA = mx > 0, aB = top_ok, aC = top_ok && mx + 1 < g.mbw, aD = top_ok && mx > 0;
+    const MbInfo *m = s.mbi + my * g.mbw + mx;
+    const MbInfo *A = aA ? m - 1 : nullptr, *B = aB ? m - g.mbw : nullptr, *C = aC ? m - g.mbw + 1 : (aD ? m - g.mbw - 1 : nullptr);
+    int refA = -1, refB = -1, refC = -1, ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
+    if (A && is_inter_type(A->mb_type)) { refA = 0; ax = A->mv[0]; ay = A->mv[1]; }
+    if (B && is_inter_type(B->mb_type)) { refB = 0; bx = B->mv[0]; by = B->mv[1]; }
+    if (C && is_inter_type(C->mb_type)) { refC = 0; cx = C->mv[0]; cy = C->mv[1]; }
+    if (!aB && !(aC || aD) && aA) { refB = refA; bx = ax; by = ay; refC = refA; cx = ax; cy = ay; }
+    const int n = (refA == 0) + (refB == 0) + (refC == 0);
+    if (n == 1) { if (refA == 0) { pmx = ax; pmy = ay; } else if (refB == 0) { pmx = bx; pmy = by; } else { pmx = cx; pmy = cy; } }
+    else { pmx = median3(ax, bx, cx); pmy = median3(ay, by, cy); }
+    if (!aA || !aB || (refA == 0 && ax == 0 && ay == 0) || (refB == 0 && bx == 0 && by == 0)) { skx = 0; sky = 0; }
+    else { skx = pmx; sky = pmy; }
+}
+
+// grid: (num_slices, 1, sessions), 256 threads. skip_run[mb] = P_Skip MBs immediately before mb inside the slice;
+// skip_run[n_mb + slice] = trailing run of the slice.
+__global__ void __launch_bounds__(256) k_pskip_scan(const Sess *ss, Geom g)
+{
+    const Sess &s = ss[blockIdx.z];
+    const int sl = blockIdx.x, m0 = g.slice_row0[sl] * g.mbw, m1 = g.slice_row0[sl + 1] * g.mbw, nmb = g.mbw * g.mbh;
+    __shared__ int warp_last[8];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = m0 - 1;
+    __syncthreads();
+    for (int base = m0; base < m1; base += 256) {
+        const int mb = base + threadIdx.x;
+        int last = -1;                       // index of this MB if it is NOT skipped
+        if (mb < m1) {
+            MbInfo *mi = s.mbi + mb;
+            bool skip = false;
+            if (!s.is_idr && mi->mb_type == MB_P16x16 && mi->cbp == 0) {
+                int pmx, pmy, skx, sky; predict_mv(s, g, mb % g.mbw, mb / g.mbw, pmx, pmy, skx, sky);
+                skip = mi->mv[0] == skx && mi->mv[1] == sky;
+                if (skip) mi->mb_type = MB_PSKIP;
+            }
+            if (!skip) last = mb;
+        }
+        // inclusive max-scan of `last` over the block
+        int v = last;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = max(v, t); }
+        if (lane == 31) warp_last[warp] = v;
+        __syncthreads();
+        int prev = carry_s;
+        for (int w = 0; w < warp; w++) prev = max(prev, warp_last[w]);
+        int excl = __shfl_up_sync(0xffffffffu, v, 1);
+        excl = lane == 0 ? prev : max(prev, excl);
+        if (mb < m1) s.skip_run[mb] = mb - 1 - excl;
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = max(prev, v);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s.skip_run[nmb + sl] = m1 - 1 - carry_s;
+}
+
+// ---- bit sink: MSB-first bits into a zeroed word array shared by the lanes of a warp ----
+template <bool WRITE> struct BitSink {
+    uint32_t *w; int pos;
+    __device__ __forceinline__ void put(int n, uint32_t v)
+    {
+        if (WRITE && n > 0) {
+            const int o = pos & 31, wi = pos >> 5;
+            if (o + n <= 32) atomicOr(w + wi, v << (32 - o - n));
+            else { atomicOr(w + wi, v >> (o + n - 32)); atomicOr(w + wi + 1, v << (64 - o - n)); }
+        }
+        pos += n;
+    }
+    __device__ __forceinline__ void ue(uint32_t v) { const int l = 31 - __clz(v + 1u); put(2 * l + 1, v + 1u); }
+    __device__ __forceinline__ void se(int v) { ue(v > 0 ? 2u * v - 1u : (uint32_t)(-2 * v)); }
+};
+
+// residual_block_cavlc (7.3.5.3.2, 9.2) of `maxn` levels lv[0..maxn-1] in scan order; nC < 0 selects the chroma DC tables
+template <bool WRITE> __device__ void code_residual(BitSink<WRITE> &bs, const int16_t *lv, int maxn, int nC)
+{
+    int total = 0, last = -1, t1 = 0; bool t1_open = true;
+    for (int i = maxn - 1; i >= 0; i--) {
+        const int v = lv[i];
+        if (!v) continue;
+        if (last < 0) last = i;
+        total++;
+        if (t1_open && t1 < 3 && (v == 1 || v == -1)) t1++; else t1_open = false;
+    }
+    const int tcls = nC < 2 ? 0 : nC < 4 ? 1 : nC < 8 ? 2 : 3;
+    if (nC < 0) bs.put(c_cdc_token_len[4 * total + t1], c_cdc_token_bits[4 * total + t1]);
+    else bs.put(c_coeff_token_len[tcls * 68 + 4 * total + t1], c_coeff_token_bits[tcls * 68 + 4 * total + t1]);
+    if (!total) return;
+    const int zeros = last + 1 - total;
+    // levels, highest frequency first
+    int k = 0, suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+    for (int i = last; i >= 0; i--) {
+        const int v = lv[i];
+        if (!v) continue;
+        if (k < t1) bs.put(1, v < 0);
+        else {
+            const int a = abs(v);
+            int code = v > 0 ? 2 * a - 2 : 2 * a - 1;
+            if (k == t1 && t1 < 3) code -= 2;
+            if (suffix_len == 0) {
+                if (code < 14) bs.put(code + 1, 1);
+                else if (code < 30) { bs.put(15, 1); bs.put(4, (uint32_t)(code - 14)); }
+                else { bs.put(16, 1); bs.put(12, (uint32_t)(code - 30)); }
+            } else if (code < (15 << suffix_len)) {
+                bs.put((code >> suffix_len) + 1, 1);
+                bs.put(suffix_len, (uint32_t)(code & ((1 << suffix_len) - 1)));
+            } else { bs.put(16, 1); bs.put(12, (uint32_t)(code - (15 << suffix_len))); }
+            if (suffix_len == 0) suffix_len = 1;
+            if (a > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+        }
+        k++;
+    }
+    if (total < maxn) {
+        if (nC < 0) bs.put(c_cdc_total_zeros_len[(total - 1) * 4 + zeros], c_cdc_total_zeros_bits[(total - 1) * 4 + zeros]);
+        else bs.put(c_total_zeros_len[(total - 1) * 16 + zeros], c_total_zeros_bits[(total - 1) * 16 + zeros]);
+    }
+    // run_before for every coefficient but the last (lowest frequency) one
+    int zl = zeros, run = 0; k = 0;
+    for (int i = last - 1; i >= 0 && zl > 0 && k < total - 1; i--) {
+        if (lv[i]) {
+            const int zi = min(zl, 7) - 1;
+            bs.put(c_run_before_len[zi * 16 + run], c_run_before_bits[zi * 16 + run]);
+            zl -= run; run = 0; k++;
+        } else run++;
+    }
+}
+
+struct MbItem { const int16_t *lv; int maxn, nC; bool present; };
+
+// the syntax group coded by `lane` for this MB (lanes 1..27; lane 0 is the MB header)
+__device__ __forceinline__ MbItem mb_item(const Sess &s, const Geom &g, int mx, int my, int lane, const MbInfo *mi, const MbCoef *co)
+{
+    MbItem it; it.present = false; it.lv = co->luma_dc; it.maxn = 16; it.nC = 0;
+    const bool i16 = mi->mb_type == MB_I16x16;
+    const int cl = mi->cbp & 15, cc = mi->cbp >> 4;
+    const bool left = mx > 0, top = !row_is_slice_top(g, my);
+    const MbInfo *ml = mi - 1, *mt = mi - g.mbw;
+    if (lane == 1 || (lane >= 2 && lane < 18)) {
+        const int b = lane == 1 ? 0 : lane - 2, bx = blk_x(b), by = blk_y(b);
+        int nA = -1, nB = -1;
+        if (bx > 0) nA = mi->nnz[xy2blk(bx - 1, by)]; else if (left) nA = ml->nnz[xy2blk(3, by)];
+        if (by > 0) nB = mi->nnz[xy2blk(bx, by - 1)]; else if (top) nB = mt->nnz[xy2blk(bx, 3)];
+        it.nC = (nA >= 0 && nB >= 0) ? (nA + nB + 1) >> 1 : (nA >= 0 ? nA : (nB >= 0 ? nB : 0));
+        if (lane == 1) { it.present = i16; }
+        else if (i16) { it.present = cl != 0; it.lv = co->luma[b] + 1; it.maxn = 15; }
+        else { it.present = (cl >> (b >> 2)) & 1; it.lv = co->luma[b]; it.maxn = 16; }
+    } else if (lane < 20) {
+        it.present = cc != 0; it.lv = co->chroma_dc[lane - 18]; it.maxn = 4; it.nC = -1;
+    } else if (lane < 28) {
+        const int pl = (lane - 20) >> 2, b = (lane - 20) & 3, bx = b & 1, by = b >> 1, base = 16 + pl * 4;
+        int nA = -1, nB = -1;
+        if (bx > 0) nA = mi->nnz[base + by * 2]; else if (left) nA = ml->nnz[base + by * 2 + 1];
+        if (by > 0) nB = mi->nnz[base + bx]; else if (top) nB = mt->nnz[base + 2 + bx];
+        it.nC = (nA >= 0 && nB >= 0) ? (nA + nB + 1) >> 1 : (nA >= 0 ? nA : (nB >= 0 ? nB : 0));
+        it.present = cc == 2; it.lv = co->chroma_ac[pl][b] + 1; it.maxn = 15;
+    }
+    return it;
+}
+
+template <bool WRITE> __device__ void code_mb_header(BitSink<WRITE> &bs, const Sess &s, const Geom &g, int mx, int my, const MbInfo *mi, int skip_run)
+{
+    const int cl = mi->cbp & 15, cc = mi->cbp >> 4;
+    if (!s.is_idr) bs.ue((uint32_t)skip_run);
+    if (mi->mb_type == MB_I16x16) {
+        bs.ue((uint32_t)((s.is_idr ? 0 : 5) + 1 + mi->i16_mode + 4 * cc + (cl ? 12 : 0)));
+        bs.ue(mi->chroma_mode);
+        bs.se(0);
+    } else {
+        int pmx, pmy, skx, sky; predict_mv(s, g, mx, my, pmx, pmy, skx, sky);
+        bs.ue(0);
+        bs.se(mi->mv[0] - pmx); bs.se(mi->mv[1] - pmy);
+        bs.ue(c_cbp_inter[mi->cbp]);
+        if (mi->cbp) bs.se(0);
+    }
+}
+
+#define CAVLC_WARPS 8
+// grid: (ceil(n_mb / CAVLC_WARPS), 1, sessions)
+__global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, Geom g)
+{
+    __shared__ uint32_t slot_all[CAVLC_WARPS][B200_MB_SLOT_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * CAVLC_WARPS + warp;
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    const MbInfo *mi = s.mbi + mb; const MbCoef *co = s.coef + mb;
+    if (mi->mb_type == MB_PSKIP) { if (lane == 0) s.mb_bits[mb] = 0; return; }
+    const int mx = mb % g.mbw, my = mb / g.mbw;
+    uint32_t *slot = slot_all[warp];
+    const int skip_run = s.is_idr ? 0 : s.skip_run[mb];
+    __align__(16) int16_t lv[16];
+    MbItem it = mb_item(s, g, mx, my, lane, mi, co);
+    if (lane >= 1 && lane < 28 && it.present)
+        for (int i = 0; i < it.maxn; i++) lv[i] = it.lv[i];
+    // pass 1: lengths
+    int len = 0;
+    {
+        BitSink<false> bs; bs.w = nullptr; bs.pos = 0;
+        if (lane == 0) code_mb_header<false>(bs, s, g, mx, my, mi, skip_run);
+        else if (lane < 28 && it.present) code_residual<false>(bs, lv, it.maxn, it.nC);
+        len = bs.pos;
+    }
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31), nwords = (total + 31) >> 5;
+    for (int i = lane; i <= nwords && i < B200_MB_SLOT_WORDS; i += 32) slot[i] = 0;
+    __syncwarp();
+    // pass 2: write at the lane's bit offset
+    {
+        BitSink<true> bs; bs.w = slot; bs.pos = incl - len;
+        if (lane == 0) code_mb_header<true>(bs, s, g, mx, my, mi, skip_run);
+        else if (lane < 28 && it.present) code_residual<true>(bs, lv, it.maxn, it.nC);
+    }
+    __syncwarp();
+    uint32_t *dst = s.mb_slot + (size_t)mb * B200_MB_SLOT_WORDS;
+    for (int i = lane; i < nwords; i += 32) dst[i] = slot[i];
+    if (lane == 0) s.mb_bits[mb] = (uint32_t)total;
+}
+
+// ---- slice assembly ----
+__device__ __forceinline__ int block_excl_scan(int v, int *total, int *wsum)   // 256 threads
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < warp) base += wsum[w]; tot += wsum[w]; }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+// grid: (num_slices, 1, sessions), 256 threads
+__global__ void __launch_bounds__(256) k_slice_pack(const Sess *ss, Geom g)
+{
+    const Sess &s = ss[blockIdx.z];
+    const int sl = blockIdx.x, m0 = g.slice_row0[sl] * g.mbw, m1 = g.slice_row0[sl + 1] * g.mbw, nmb = g.mbw * g.mbh;
+    uint32_t *rb = s.rbsp + (size_t)sl * s.rbsp_words_per_slice;
+    __shared__ int wsum[8];
+    __shared__ uint32_t hdr[4];
+    __shared__ int hdr_bits_s, carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // total payload bits of the slice
+    int sum = 0;
+    for (int mb = m0 + threadIdx.x; mb < m1; mb += 256) sum += (int)s.mb_bits[mb];
+    int total; block_excl_scan(sum, &total, wsum);
+    if (threadIdx.x == 0) {      // slice_header(), 7.3.3
+        hdr[0] = hdr[1] = hdr[2] = hdr[3] = 0;
+        BitSink<true> bs; bs.w = hdr; bs.pos = 0;
+        bs.ue((uint32_t)m0);
+        bs.ue(s.is_idr ? 7 : 5);
+        bs.ue(0);
+        bs.put(8, (uint32_t)(s.frame_num & 255));
+        if (s.is_idr) bs.ue((uint32_t)s.idr_pic_id);
+        if (!s.is_idr) { bs.put(1, 0); bs.put(1, 0); }
+        if (s.is_idr) { bs.put(1, 0); bs.put(1, 0); } else bs.put(1, 0);
+        bs.se(s.qp - 26);
+        bs.ue(0); bs.se(0); bs.se(0);
+        hdr_bits_s = bs.pos; carry_s = 0;
+    }
+    __syncthreads();
+    const int hdr_bits = hdr_bits_s;
+    const int trailing_run = s.is_idr ? 0 : s.skip_run[nmb + sl];
+    const int tail_bits = trailing_run ? ue_len((uint32_t)trailing_run) : 0;
+    const int data_end = hdr_bits + total + tail_bits;               // position of the rbsp_stop_one_bit
+    const int all_bits = (data_end + 1 + 7) & ~7;
+    const int nwords = (all_bits + 31) >> 5;
+    for (int i = threadIdx.x; i <= nwords; i += 256) rb[i] = i < 4 ? hdr[i] : 0u;
+    __syncthreads();
+    // MB payloads: chunk-wise exclusive scan of lengths, then each warp shifts its MBs into place
+    for (int base = m0; base < m1; base += 256) {
+        const int mb = base + threadIdx.x;
+        const int len = mb < m1 ? (int)s.mb_bits[mb] : 0;
+        int chunk_total; const int off = carry_s + block_excl_scan(len, &chunk_total, wsum);
+        // hand (mb, offset, len) of this chunk's MBs to the warps through shuffles: warp w copies MBs 32w..32w+31
+        for (int j = 0; j < 32; j++) {
+            const int l = __shfl_sync(0xffffffffu, len, j);
+            if (!l) continue;
+            const int D = hdr_bits + __shfl_sync(0xffffffffu, off, j);
+            const uint32_t *src = s.mb_slot + (size_t)(base + warp * 32 + j) * B200_MB_SLOT_WORDS;
+            const int nw = (l + 31) >> 5, dw = D >> 5, sh = D & 31;
+            for (int i = lane; i <= nw; i += 32) {          // destination word dw + i
+                const uint32_t hi = i > 0 ? src[i - 1] : 0u, lo = i < nw ? src[i] : 0u;
+                const uint32_t v = sh ? (hi << (32 - sh)) | (lo >> sh) : lo;
+                if (v) atomicOr(rb + dw + i, v);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        BitSink<true> bs; bs.w = rb; bs.pos = hdr_bits + total;
+        if (trailing_run) bs.ue((uint32_t)trailing_run);
+        bs.put(1, 1);
+        s.slice_bits[sl] = (uint32_t)all_bits;
+    }
+}
+
+// grid: (sessions), 1024 threads. Output: [SPS PPS] then one NAL per slice with emulation prevention.
+__global__ void __launch_bounds__(1024) k_nal_pack(const Sess *ss, Geom g)
+{
+    const Sess &s = ss[blockIdx.x];
+    __shared__ int wsum[32];
+    __shared__ int out_pos_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) out_pos_s = 0;
+    __syncthreads();
+    if (s.is_idr) {
+        for (int i = threadIdx.x; i < s.hdr_len; i += 1024) s.out[i] = s.hdr[i];
+        __syncthreads();
+        if (threadIdx.x == 0) out_pos_s = s.hdr_len;
+        __syncthreads();
+    }
+    for (int sl = 0; sl < g.num_slices; sl++) {
+        const uint32_t *rb = s.rbsp + (size_t)sl * s.rbsp_words_per_slice;
+        const int nbytes = (int)(s.slice_bits[sl] >> 3);
+        int o0 = out_pos_s;
+        __syncthreads();
+        if (threadIdx.x < 5 && o0 + 5 <= (int)s.out_cap) s.out[o0 + threadIdx.x] = threadIdx.x == 3 ? 1 : threadIdx.x == 4 ? (s.is_idr ? 0x65 : 0x61) : 0;
+        o0 += 5;
+        for (int base = 0; base < nbytes; base += 1024) {
+            const int i = base + threadIdx.x;
+            int b = 256, flag = 0;
+            if (i < nbytes) {
+                b = (rb[i >> 2] >> (24 - 8 * (i & 3))) & 255;
+                if (b <= 3) {
+                    int k = 0;               // zero bytes immediately before i
+                    while (k < i && ((rb[(i - 1 - k) >> 2] >> (24 - 8 * ((i - 1 - k) & 3))) & 255) == 0) k++;
+                    flag = k >= 2 && !(k & 1);
+                }
+            }
+            int incl = flag;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            int pre = 0, tot = 0;
+            for (int w = 0; w < 32; w++) { if (w < warp) pre += wsum[w]; tot += wsum[w]; }
+            if (i < nbytes) {
+                int o = o0 + i + pre + incl - flag;
+                if (o + 2 <= (int)s.out_cap) { if (flag) s.out[o++] = 3; s.out[o] = (uint8_t)b; }
+            }
+            __syncthreads();
+            o0 += tot;
+        }
+        if (threadIdx.x == 0) out_pos_s = o0 + nbytes;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *s.out_size = (uint32_t)min(out_pos_s, (int)s.out_cap);
+}
+
+} // namespace b200

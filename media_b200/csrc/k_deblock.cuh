@@ -1,0 +1,169 @@
+// media_b200/csrc/k_deblock.cuh -- in-loop deblocking filter (H.264 clause 8.7), phase E of DESIGN.md 3.
+//
+// Role inside the reference: the loop filter inside ISVCEncoder::EncodeFrame with iLoopFilterDisableIdc = 0
+// (video_codec/VideoEncoderOpenH264.cpp:295,344; openh264's DeblockingBSCalcEnc_c, DeblockLumaLt4/Eq4,
+// DeblockChromaLt4/Eq4 in the absent libopenh264). The standard filters macroblocks in raster order and each
+// MB reads samples its left, upper and upper-right neighbours have already filtered, so the kernel runs the
+// same 2-MB-lag wavefront as the intra kernel: one warp per MB row, tile staged in shared memory, vertical
+// edges by 16 row-lanes (+16 chroma row-lanes), then horizontal edges by column-lanes.
+#pragma once
+#include "h264_dev.cuh"
+#include "k_intra.cuh"
+
+namespace b200 {
+
+struct DbkSmem {
+    uint32_t y[20 * 5];        // rows -4..15, cols -4..15 (stride 20 bytes)
+    uint32_t c[2][12 * 3];     // rows -4..7, cols -4..7 (stride 12 bytes)
+    uint32_t mbi[3][12];       // current, left, top MbInfo
+};
+
+__device__ __forceinline__ void filter_luma_edge(uint8_t *p, int step, int bs, int alpha, int beta, int tc0)
+{
+    const int p0 = p[-step], p1 = p[-2 * step], p2 = p[-3 * step], q0 = p[0], q1 = p[step], q2 = p[2 * step];
+    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+    const int ap = abs(p2 - p0), aq = abs(q2 - q0);
+    if (bs < 4) {
+        const int tc = tc0 + (ap < beta) + (aq < beta);
+        const int delta = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+        p[-step] = (uint8_t)clip255(p0 + delta);
+        p[0] = (uint8_t)clip255(q0 - delta);
+        if (ap < beta) p[-2 * step] = (uint8_t)(p1 + clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1));
+        if (aq < beta) p[step] = (uint8_t)(q1 + clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1));
+    } else {
+        const int p3 = p[-4 * step], q3 = p[3 * step];
+        const bool small = abs(p0 - q0) < ((alpha >> 2) + 2);
+        if (ap < beta && small) {
+            p[-step] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+            p[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+            p[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+        } else p[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+        if (aq < beta && small) {
+            p[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+            p[step] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+            p[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+        } else p[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+    }
+}
+__device__ __forceinline__ void filter_chroma_edge(uint8_t *p, int step, int bs, int alpha, int beta, int tc0)
+{
+    const int p0 = p[-step], p1 = p[-2 * step], q0 = p[0], q1 = p[step];
+    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+    if (bs < 4) {
+        const int tc = tc0 + 1, delta = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+        p[-step] = (uint8_t)clip255(p0 + delta); p[0] = (uint8_t)clip255(q0 - delta);
+    } else {
+        p[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2); p[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+    }
+}
+
+// boundary strength between 4x4 block (bxp,byp) of MB p and block (bxq,byq) of MB q (8.7.2.1, frame pictures, one reference)
+__device__ __forceinline__ int bs_of(const uint32_t *mp, int bxp, int byp, const uint32_t *mq, int bxq, int byq, bool mb_edge)
+{
+    const MbInfo *p = reinterpret_cast<const MbInfo *>(mp), *q = reinterpret_cast<const MbInfo *>(mq);
+    const bool ip = p->mb_type == MB_I16x16 || p->mb_type == MB_I4x4, iq = q->mb_type == MB_I16x16 || q->mb_type == MB_I4x4;
+    if (ip || iq) return mb_edge ? 4 : 3;
+    if (p->nnz[xy2blk(bxp, byp)] || q->nnz[xy2blk(bxq, byq)]) return 2;
+    if (abs(p->mv[0] - q->mv[0]) >= 4 || abs(p->mv[1] - q->mv[1]) >= 4) return 1;
+    return 0;
+}
+
+__device__ void deblock_mb(const Sess &s, const Geom &g, DbkSmem &sm, int mx, int my, int lane)
+{
+    const int wc = g.wc, cw = wc / 2, mb = my * g.mbw + mx, qp = s.qp, qpc = c_chroma_qp[qp];
+    __syncwarp();
+    for (int i = lane; i < 36; i += 32) {
+        const int which = i / 12, w = i - which * 12;
+        const int src = which == 0 ? mb : which == 1 ? mb - 1 : mb - g.mbw;
+        const bool ok = which == 0 || (which == 1 ? mx > 0 : my > 0);
+        sm.mbi[which][w] = ok ? reinterpret_cast<const uint32_t *>(s.mbi + src)[w] : 0u;
+    }
+    __syncwarp();
+    // lanes 0-15: bS of vertical edge e, segment k; lanes 16-31: horizontal edge e, segment k
+    int bs;
+    {
+        const int e = (lane >> 2) & 3, k = lane & 3; const bool vert = lane < 16;
+        if (e == 0) {
+            if (vert) bs = mx > 0 ? bs_of(sm.mbi[1], 3, k, sm.mbi[0], 0, k, true) : 0;
+            else bs = my > 0 ? bs_of(sm.mbi[2], k, 3, sm.mbi[0], k, 0, true) : 0;
+        } else bs = vert ? bs_of(sm.mbi[0], e - 1, k, sm.mbi[0], e, k, false) : bs_of(sm.mbi[0], k, e - 1, sm.mbi[0], k, e, false);
+    }
+    if (__ballot_sync(0xffffffffu, bs != 0) == 0) return;
+
+    uint8_t *Y = s.rec[0] + (size_t)my * 16 * wc + mx * 16;
+    uint8_t *C[2] = { s.rec[1] + (size_t)my * 8 * cw + mx * 8, s.rec[2] + (size_t)my * 8 * cw + mx * 8 };
+    // stage the tile (rows/cols -4.. of luma, -4.. of chroma); samples outside the picture are never used
+    for (int i = lane; i < 100; i += 32) {
+        const int r = i / 5 - 4, c4 = (i % 5) * 4 - 4;
+        uint32_t v = 0;
+        if ((r >= 0 || my > 0) && (c4 >= 0 || mx > 0)) v = __ldcg(reinterpret_cast<const uint32_t *>(Y + (ptrdiff_t)r * wc + c4));
+        sm.y[i] = v;
+    }
+    for (int i = lane; i < 72; i += 32) {
+        const int pl = i / 36, j = i - pl * 36, r = j / 3 - 4, c4 = (j % 3) * 4 - 4;
+        uint32_t v = 0;
+        if ((r >= 0 || my > 0) && (c4 >= 0 || mx > 0)) v = __ldcg(reinterpret_cast<const uint32_t *>(C[pl] + (ptrdiff_t)r * cw + c4));
+        sm.c[pl][j] = v;
+    }
+    __syncwarp();
+    const int alphaY = c_alpha[qp], betaY = c_beta[qp], alphaC = c_alpha[qpc], betaC = c_beta[qpc];
+    uint8_t *ty = reinterpret_cast<uint8_t *>(sm.y) + 4 * 20 + 4;            // sample (0,0) of the MB
+    uint8_t *tc = reinterpret_cast<uint8_t *>(sm.c[(lane >> 3) & 1]) + 4 * 12 + 4;
+    // vertical edges (filtering across columns), left to right
+#pragma unroll 1
+    for (int e = 0; e < 4; e++) {
+        const int seg = lane < 16 ? lane >> 2 : (lane & 7) >> 1;
+        const int b = __shfl_sync(0xffffffffu, bs, e * 4 + seg);
+        if (b) {
+            if (lane < 16) filter_luma_edge(ty + lane * 20 + 4 * e, 1, b, alphaY, betaY, b < 4 ? c_tc0[qp][b - 1] : 0);
+            else if (!(e & 1)) filter_chroma_edge(tc + (lane & 7) * 12 + 2 * e, 1, b, alphaC, betaC, b < 4 ? c_tc0[qpc][b - 1] : 0);
+        }
+    }
+    __syncwarp();
+    // horizontal edges (filtering across rows), top to bottom
+#pragma unroll 1
+    for (int e = 0; e < 4; e++) {
+        const int seg = lane < 16 ? lane >> 2 : (lane & 7) >> 1;
+        const int b = __shfl_sync(0xffffffffu, bs, 16 + e * 4 + seg);
+        if (b) {
+            if (lane < 16) filter_luma_edge(ty + 4 * e * 20 + lane, 20, b, alphaY, betaY, b < 4 ? c_tc0[qp][b - 1] : 0);
+            else if (!(e & 1)) filter_chroma_edge(tc + 2 * e * 12 + (lane & 7), 12, b, alphaC, betaC, b < 4 ? c_tc0[qpc][b - 1] : 0);
+        }
+    }
+    __syncwarp();
+    // write back: the MB with its 4 left columns, and the 3 rows above it
+    for (int i = lane; i < 100; i += 32) {
+        const int r = i / 5 - 4, c4 = (i % 5) * 4 - 4;
+        const bool st = r >= 0 ? (c4 >= 0 || mx > 0) : (r >= -3 && c4 >= 0 && my > 0);
+        if (st) *reinterpret_cast<uint32_t *>(Y + (ptrdiff_t)r * wc + c4) = sm.y[i];
+    }
+    for (int i = lane; i < 72; i += 32) {
+        const int pl = i / 36, j = i - pl * 36, r = j / 3 - 4, c4 = (j % 3) * 4 - 4;
+        const bool st = r >= 0 ? (c4 >= 0 || mx > 0) : (r >= -2 && c4 >= 0 && my > 0);
+        if (st) *reinterpret_cast<uint32_t *>(C[pl] + (ptrdiff_t)r * cw + c4) = sm.c[pl][j];
+    }
+}
+
+// grid: ceil(sessions * mbh / WAVE_WARPS) CTAs of WAVE_WARPS warps. Slices do not break the wavefront:
+// disable_deblocking_filter_idc = 0 filters across slice boundaries.
+__global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss, Geom g, int nsess, WaveCtl *ctl)
+{
+    __shared__ DbkSmem sm_all[WAVE_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&ctl->ticket_dbk, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= nsess * g.mbh) return;
+    const int my = t / nsess;
+    const Sess &s = ss[t % nsess];
+    int *prog = s.row_prog_dbk;
+    for (int mx = 0; mx < g.mbw; mx++) {
+        if (my > 0 && !wave_wait(prog + my - 1, min(mx + 2, g.mbw), ctl, lane)) return;
+        deblock_mb(s, g, sm_all[warp], mx, my, lane);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(prog + my, mx + 1);
+    }
+}
+
+} // namespace b200

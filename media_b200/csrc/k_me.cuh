@@ -1,0 +1,366 @@
+// media_b200/csrc/k_me.cuh -- motion estimation and inter macroblock coding (phases A and B of DESIGN.md 3).
+//
+// Role inside the reference: the ME / MC / transform part of ISVCEncoder::EncodeFrame
+// (video_codec/VideoEncoderOpenH264.cpp:344; openh264's WelsMotionEstimateSearch, MeRefineFracPixel, McHorVer*,
+// WelsDctT4, WelsQuant4x4, WelsIDctT4Rec live in the absent libopenh264). Everything here is independent per
+// macroblock, so the grid is one warp per MB across all sessions of the batch.
+#pragma once
+#include "h264_dev.cuh"
+
+namespace b200 {
+
+#define ME_WARPS 8
+
+// copy a ww x wh window whose top-left is (x0,y0) from a pw x ph plane into shared memory, clamping coordinates
+// (the reference picture is extended by edge replication, 8.4.2.2.1)
+__device__ __forceinline__ void stage_clamped(uint8_t *dst, int dstride, const uint8_t *__restrict__ plane, int pw, int ph,
+                                              int x0, int y0, int ww, int wh, int lane)
+{
+    for (int r = 0; r < wh; r++) {
+        const uint8_t *row = plane + (size_t)clip3(0, ph - 1, y0 + r) * pw;
+        for (int c = lane; c < ww; c += 32) dst[r * dstride + c] = __ldg(row + clip3(0, pw - 1, x0 + c));
+    }
+}
+__device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *base, int off)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base) + (off >> 2);
+    return __funnelshift_r(w[0], w[1], (off & 3) * 8);
+}
+__device__ __forceinline__ uint32_t warp_min(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+
+// ---- coarse levels: 1/4 resolution exhaustive search, 1/2 resolution refinement ----
+struct CoarseSmem { uint32_t win[(40 * 40 + 8) / 4]; uint32_t src[16]; uint32_t win1[(12 * 12 + 8) / 4]; };
+
+__global__ void __launch_bounds__(ME_WARPS * 32) k_me_coarse(const Sess *ss, Geom g)
+{
+    __shared__ CoarseSmem sm_all[ME_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * ME_WARPS + warp;
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    if (s.is_idr) return;
+    CoarseSmem &sm = sm_all[warp];
+    const int mx = mb % g.mbw, my = mb / g.mbw;
+    const int R4 = g.search_range / 4, span = 2 * R4 + 1, W = 8 + 2 * R4;
+    const int w2 = g.wc / 4, h2 = g.hc / 4, w1 = g.wc / 2, h1 = g.hc / 2;
+    uint8_t *win = reinterpret_cast<uint8_t *>(sm.win), *srcb = reinterpret_cast<uint8_t *>(sm.src), *win1 = reinterpret_cast<uint8_t *>(sm.win1);
+
+    // level 2: 8x8 block centred on the MB (origin 4mx-2, 4my-2), all (2R4+1)^2 displacements
+    stage_clamped(srcb, 8, s.srcL2, w2, h2, 4 * mx - 2, 4 * my - 2, 8, 8, lane);
+    stage_clamped(win, W, s.refL2, w2, h2, 4 * mx - 2 - R4, 4 * my - 2 - R4, W, W, lane);
+    __syncwarp();
+    uint32_t sw[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) sw[i] = sm.src[i];
+    uint32_t best = 0xffffffffu;
+    for (int cand = lane; cand < span * span; cand += 32) {
+        const int dy = cand / span, dx = cand - dy * span;
+        uint32_t sad = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int o = (dy + r) * W + dx;
+            sad = sad4(sw[2 * r], lds_u32_unaligned(win, o), sad);
+            sad = sad4(sw[2 * r + 1], lds_u32_unaligned(win, o + 4), sad);
+        }
+        best = min(best, ((sad + abs(dx - R4) + abs(dy - R4)) << 11) | (uint32_t)cand);
+    }
+    best = warp_min(best);
+    const int c2 = best & 2047, v2x = c2 % span - R4, v2y = c2 / span - R4;
+
+    // level 1: 8x8 block at (8mx, 8my), +-2 around 2*mv2
+    const int cx = 2 * v2x, cy = 2 * v2y;
+    __syncwarp();
+    stage_clamped(srcb, 8, s.srcL1, w1, h1, 8 * mx, 8 * my, 8, 8, lane);
+    stage_clamped(win1, 12, s.refL1, w1, h1, 8 * mx + cx - 2, 8 * my + cy - 2, 12, 12, lane);
+    __syncwarp();
+    best = 0xffffffffu;
+    if (lane < 25) {
+        const int dy = lane / 5, dx = lane - dy * 5;
+        uint32_t sad = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int o = (dy + r) * 12 + dx;
+            sad = sad4(sm.src[2 * r], lds_u32_unaligned(win1, o), sad);
+            sad = sad4(sm.src[2 * r + 1], lds_u32_unaligned(win1, o + 4), sad);
+        }
+        best = ((sad + abs(cx + dx - 2) + abs(cy + dy - 2)) << 5) | (uint32_t)lane;
+    }
+    best = warp_min(best);
+    if (lane == 0) {
+        const int c1 = best & 31;
+        s.me2[mb * 2] = (int16_t)v2x; s.me2[mb * 2 + 1] = (int16_t)v2y;
+        s.me1[mb * 2] = (int16_t)(cx + c1 % 5 - 2); s.me1[mb * 2 + 1] = (int16_t)(cy + c1 / 5 - 2);
+    }
+}
+
+// ---- fine level: full-pel refinement, half/quarter-pel SATD refinement, intra estimate, inter coding ----
+struct FineSmem {
+    uint32_t win[(24 * 24 + 8) / 4];     // full-pel window: 20x20 (stride 20) for the +-2 search, then 24x24 around the winner
+    uint32_t src[64];                    // source MB, 16x16
+    uint8_t plane[4][18 * 18];           // G, b, h, j samples at [-1,16]^2 relative to the best full-pel block (8.4.2.2.1)
+    int16_t braw[24 * 18];               // unrounded horizontal half-pel sums, rows [-3,20]
+    uint8_t nb_top[16], nb_left[16];     // SOURCE neighbours for the intra estimate
+};
+
+// The 16 quarter-pel positions as the average of two samples out of {G,b,h,j} (8.4.2.2.1, Table 8-12):
+// entry = {planeA, dxA, dyA, planeB, dxB, dyB}
+static __device__ __constant__ uint8_t c_qpel_tab[16][6] = {
+    { 0, 0, 0, 0, 0, 0 }, { 0, 0, 0, 1, 0, 0 }, { 1, 0, 0, 1, 0, 0 }, { 0, 1, 0, 1, 0, 0 },
+    { 0, 0, 0, 2, 0, 0 }, { 1, 0, 0, 2, 0, 0 }, { 1, 0, 0, 3, 0, 0 }, { 1, 0, 0, 2, 1, 0 },
+    { 2, 0, 0, 2, 0, 0 }, { 2, 0, 0, 3, 0, 0 }, { 3, 0, 0, 3, 0, 0 }, { 3, 0, 0, 2, 1, 0 },
+    { 0, 0, 1, 2, 0, 0 }, { 2, 0, 0, 1, 0, 1 }, { 3, 0, 0, 1, 0, 1 }, { 2, 1, 0, 1, 0, 1 },
+};
+
+// prediction of one 4x4 block (bx,by in pixels inside the MB) at quarter-pel offset (ox,oy) in [-3,3] from the best full-pel block
+__device__ __forceinline__ void pred_block_qpel(const FineSmem &sm, int bx, int by, int ox, int oy, int p[16])
+{
+    const uint8_t *t = c_qpel_tab[(oy & 3) * 4 + (ox & 3)];
+    const int xi = bx + (ox >> 2) + 1, yi = by + (oy >> 2) + 1;
+    const uint8_t *pa = &sm.plane[t[0]][(yi + t[2]) * 18 + xi + t[1]], *pb = &sm.plane[t[3]][(yi + t[5]) * 18 + xi + t[4]];
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+#pragma unroll
+        for (int x = 0; x < 4; x++) p[y * 4 + x] = (pa[y * 18 + x] + pb[y * 18 + x] + 1) >> 1;
+}
+__device__ __forceinline__ int half_reduce16(int v)   // sum over the 16 lanes of a half-warp
+{
+#pragma unroll
+    for (int o = 8; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void load_src_block(const FineSmem &sm, int bx, int by, int sp[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
+#pragma unroll
+        for (int x = 0; x < 4; x++) sp[y * 4 + x] = (w >> (8 * x)) & 255;
+    }
+}
+
+__global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom g)
+{
+    __shared__ FineSmem sm_all[ME_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * ME_WARPS + warp;
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    if (s.is_idr) return;
+    FineSmem &sm = sm_all[warp];
+    const int mx = mb % g.mbw, my = mb / g.mbw, x0 = mx * 16, y0 = my * 16, wc = g.wc, hc = g.hc;
+    const int qp = s.qp, lambda = c_lambda[qp];
+    uint8_t *win = reinterpret_cast<uint8_t *>(sm.win);
+
+    // source MB and the +-2 window around 2*mv1
+    const int cx = 2 * s.me1[mb * 2], cy = 2 * s.me1[mb * 2 + 1];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int wi = lane + 32 * i;
+        sm.src[wi] = *reinterpret_cast<const uint32_t *>(s.src[0] + (size_t)(y0 + (wi >> 2)) * wc + x0 + (wi & 3) * 4);
+    }
+    stage_clamped(win, 20, s.ref[0], wc, hc, x0 + cx - 2, y0 + cy - 2, 20, 20, lane);
+    // zero-vector candidate, computed cooperatively straight from HBM (always inside the picture)
+    uint32_t zsad;
+    {
+        const uint8_t *rp = s.ref[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8;
+        const uint8_t *sp = s.src[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8;
+        uint2 a = *reinterpret_cast<const uint2 *>(rp), b = *reinterpret_cast<const uint2 *>(sp);
+        zsad = sad4(a.x, b.x, sad4(a.y, b.y, 0));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) zsad += __shfl_xor_sync(0xffffffffu, zsad, o);
+    }
+    __syncwarp();
+    uint32_t best = 0xffffffffu;
+    if (lane < 25) {
+        const int dy = lane / 5, dx = lane - dy * 5;
+        uint32_t sad = 0;
+#pragma unroll 4
+        for (int r = 0; r < 16; r++) {
+            const int o = (dy + r) * 20 + dx;
+#pragma unroll
+            for (int k = 0; k < 4; k++) sad = sad4(sm.src[r * 4 + k], lds_u32_unaligned(win, o + 4 * k), sad);
+        }
+        best = ((sad + lambda * (se_len(4 * (cx + dx - 2)) + se_len(4 * (cy + dy - 2)))) << 5) | (uint32_t)lane;
+    } else if (lane == 25) best = ((zsad + lambda * 2) << 5) | 25u;
+    best = warp_min(best);
+    const int c0 = best & 31;
+    const int fx = c0 < 25 ? cx + c0 % 5 - 2 : 0, fy = c0 < 25 ? cy + c0 / 5 - 2 : 0;   // best full-pel vector
+
+    // half-pel sample planes around the winner
+    __syncwarp();
+    stage_clamped(win, 24, s.ref[0], wc, hc, x0 + fx - 3, y0 + fy - 3, 24, 24, lane);
+    __syncwarp();
+    for (int i = lane; i < 24 * 18; i += 32) {        // braw(x,y), x in [-1,16], y in [-3,20]
+        const int r = i / 18, c = i - r * 18;           // G column of sample x is c + 2 (x = c - 1, G index x + 3)
+        const uint8_t *p = win + r * 24 + c;
+        sm.braw[i] = (int16_t)tap6(p[0], p[1], p[2], p[3], p[4], p[5]);
+    }
+    __syncwarp();
+    for (int i = lane; i < 18 * 18; i += 32) {
+        const int r = i / 18, c = i - r * 18;           // sample (x,y) = (c-1, r-1); G index (c+2, r+2)
+        const uint8_t *p = win + (r + 2) * 24 + c + 2;
+        sm.plane[0][i] = p[0];
+        sm.plane[1][i] = (uint8_t)clip255((sm.braw[(r + 2) * 18 + c] + 16) >> 5);
+        sm.plane[2][i] = (uint8_t)clip255((tap6(p[-48], p[-24], p[0], p[24], p[48], p[72]) + 16) >> 5);
+        const int16_t *q = sm.braw + r * 18 + c;        // braw rows y-2..y+3 = indices r..r+5
+        sm.plane[3][i] = (uint8_t)clip255((tap6(q[0], q[18], q[36], q[54], q[72], q[90]) + 512) >> 10);
+    }
+    __syncwarp();
+
+    // sub-pel refinement by SATD: 16 lanes (one per 4x4 block) evaluate one candidate, two candidates per pass
+    const int hw = lane >> 4, b = lane & 15, bx = blk_x(b) * 4, by = blk_y(b) * 4;
+    int sp[16]; load_src_block(sm, bx, by, sp);
+    int qx = 0, qy = 0;                                 // offset from 4*(fx,fy), quarter-pel units
+    uint32_t centre_key = 0;
+#pragma unroll 1
+    for (int step = 2; step >= 1; step--) {
+        uint32_t bk = step == 1 ? (centre_key & ~15u) : 0xffffffffu;
+#pragma unroll 1
+        for (int pass = 0; pass < 5; pass++) {
+            const int i = 2 * pass + hw + (step == 1 ? 1 : 0);      // step 2: 0..8 (+ one idle slot); step 1: 1..8 (centre known)
+            uint32_t key = 0xffffffffu;
+            // candidate offsets: i=0 centre, then (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1)
+            const int ci = i <= 8 ? i : 0;
+            const int dxs = ci == 0 ? 0 : ((ci - 1 + (ci > 4)) % 3) - 1, dys = ci == 0 ? 0 : ((ci - 1 + (ci > 4)) / 3) - 1;
+            const int ox = qx + step * dxs, oy = qy + step * dys;
+            int p[16]; pred_block_qpel(sm, bx, by, ox, oy, p);
+#pragma unroll
+            for (int k = 0; k < 16; k++) p[k] = sp[k] - p[k];
+            int sat = half_reduce16(satd4x4(p));
+            if (i <= 8) key = ((uint32_t)(sat + lambda * (se_len(4 * fx + ox) + se_len(4 * fy + oy))) << 4) | (uint32_t)i;
+            key = min(key, __shfl_xor_sync(0xffffffffu, key, 16));
+            bk = min(bk, key);
+            if (step == 1 && pass == 3) break;
+        }
+        const int ci = bk & 15;
+        const int dxs = ci == 0 ? 0 : ((ci - 1 + (ci > 4)) % 3) - 1, dys = ci == 0 ? 0 : ((ci - 1 + (ci > 4)) / 3) - 1;
+        qx += step * dxs; qy += step * dys; centre_key = bk;
+    }
+    const int mvx = 4 * fx + qx, mvy = 4 * fy + qy, inter_cost = (int)(centre_key >> 4);
+
+    // intra estimate from source neighbours: V, H, DC 16x16 by SATD
+    const bool top = !row_is_slice_top(g, my), left = mx > 0;
+    if (lane < 16) sm.nb_top[lane] = top ? s.src[0][(size_t)(y0 - 1) * wc + x0 + lane] : 0;
+    else sm.nb_left[lane - 16] = left ? s.src[0][(size_t)(y0 + lane - 16) * wc + x0 - 1] : 0;
+    __syncwarp();
+    int ie = 1 << 30;
+    {
+        int d[16];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) d[y * 4 + x] = sp[y * 4 + x] - (hw == 0 ? sm.nb_top[bx + x] : sm.nb_left[by + y]);
+        int sat = half_reduce16(satd4x4(d));
+        int other = __shfl_xor_sync(0xffffffffu, sat, 16);
+        int sv = hw == 0 ? sat : other, sh = hw == 0 ? other : sat;
+        if (top) ie = min(ie, sv);
+        if (left) ie = min(ie, sh);
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) sum += (top ? sm.nb_top[k] : 0) + (left ? sm.nb_left[k] : 0);
+        const int dc = top && left ? (sum + 16) >> 5 : (top || left) ? (sum + 8) >> 4 : 128;
+#pragma unroll
+        for (int k = 0; k < 16; k++) d[k] = sp[k] - dc;
+        ie = min(ie, half_reduce16(satd4x4(d)));
+    }
+    const bool intra = ie + lambda * 16 < inter_cost;
+
+    MbInfo *mi = s.mbi + mb;
+    if (lane == 0) {
+        s.me0[mb * 2] = (int16_t)fx; s.me0[mb * 2 + 1] = (int16_t)fy; s.inter_cost[mb] = inter_cost;
+    }
+    if (intra) {
+        if (lane < 12) reinterpret_cast<uint32_t *>(mi)[lane] = lane == 0 ? (uint32_t)MB_I16x16 : 0u;
+        return;
+    }
+
+    // ---- phase B: code the inter macroblock ----
+    MbCoef *co = s.coef + mb;
+    const QParam q = make_qparam(qp);
+    int nnz = 0; bool dc_nz = false;
+    if (lane < 16) {
+        int p[16], c[16]; pred_block_qpel(sm, bx, by, qx, qy, p);
+#pragma unroll
+        for (int k = 0; k < 16; k++) c[k] = sp[k] - p[k];
+        fdct4x4(c);
+        __align__(16) int16_t lz[16];
+        nnz = quant_dequant4x4(c, lz, q, q.f_inter, false);
+        idct4x4(c);
+        uint4 *dst = reinterpret_cast<uint4 *>(co->luma[b]);
+        dst[0] = reinterpret_cast<uint4 *>(lz)[0]; dst[1] = reinterpret_cast<uint4 *>(lz)[1];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x++) w |= (uint32_t)clip255(p[y * 4 + x] + c[y * 4 + x]) << (8 * x);
+            *reinterpret_cast<uint32_t *>(s.rec[0] + (size_t)(y0 + by + y) * wc + x0 + bx) = w;
+        }
+    } else if (lane < 24) {
+        const int pl = (lane - 16) >> 2, cb = (lane - 16) & 3, cbx = (cb & 1) * 4, cby = (cb >> 1) * 4;
+        const int cw = wc / 2, ch = hc / 2, cx0 = mx * 8 + cbx, cy0 = my * 8 + cby;
+        const int xi = cx0 + (mvx >> 3), yi = cy0 + (mvy >> 3), fxc = mvx & 7, fyc = mvy & 7;
+        const uint8_t *rp = s.ref[1 + pl];
+        int smp[25];
+#pragma unroll
+        for (int y = 0; y < 5; y++)
+#pragma unroll
+            for (int x = 0; x < 5; x++) smp[y * 5 + x] = __ldg(rp + (size_t)clip3(0, ch - 1, yi + y) * cw + clip3(0, cw - 1, xi + x));
+        int p[16], c[16];
+        const uint8_t *sp_c = s.src[1 + pl] + (size_t)cy0 * cw + cx0;
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            uint32_t w = *reinterpret_cast<const uint32_t *>(sp_c + (size_t)y * cw);
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                p[y * 4 + x] = ((8 - fxc) * (8 - fyc) * smp[y * 5 + x] + fxc * (8 - fyc) * smp[y * 5 + x + 1]
+                              + (8 - fxc) * fyc * smp[y * 5 + 5 + x] + fxc * fyc * smp[y * 5 + 6 + x] + 32) >> 6;
+                c[y * 4 + x] = (int)((w >> (8 * x)) & 255) - p[y * 4 + x];
+            }
+        }
+        fdct4x4(c);
+        const QParam qc = make_qparam(c_chroma_qp[qp]);
+        // 2x2 DC: gather the four DC terms of this plane (lanes 16+4pl .. 19+4pl)
+        int dcs[4], lv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) dcs[k] = __shfl_sync(0x00ff0000u, c[0], 16 + pl * 4 + k);
+        const int hd[4] = { dcs[0] + dcs[1] + dcs[2] + dcs[3], dcs[0] - dcs[1] + dcs[2] - dcs[3], dcs[0] + dcs[1] - dcs[2] - dcs[3], dcs[0] - dcs[1] - dcs[2] + dcs[3] };
+#pragma unroll
+        for (int k = 0; k < 4; k++) { lv[k] = quant_dc(hd[k], qc, qc.f_inter); dc_nz |= lv[k] != 0; }
+        const int fi[4] = { lv[0] + lv[1] + lv[2] + lv[3], lv[0] - lv[1] + lv[2] - lv[3], lv[0] + lv[1] - lv[2] - lv[3], lv[0] - lv[1] - lv[2] + lv[3] };
+        __align__(16) int16_t lz[16];
+        nnz = quant_dequant4x4(c, lz, qc, qc.f_inter, true);
+        c[0] = ((fi[cb] * 16 * qc.v[0]) << qc.sh) >> 5;
+        idct4x4(c);
+        uint4 *dst = reinterpret_cast<uint4 *>(co->chroma_ac[pl][cb]);
+        dst[0] = reinterpret_cast<uint4 *>(lz)[0]; dst[1] = reinterpret_cast<uint4 *>(lz)[1];
+        if (cb == 0) *reinterpret_cast<uint2 *>(co->chroma_dc[pl]) = make_uint2((uint32_t)(uint16_t)lv[0] | ((uint32_t)(uint16_t)lv[1] << 16),
+                                                                              (uint32_t)(uint16_t)lv[2] | ((uint32_t)(uint16_t)lv[3] << 16));
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x++) w |= (uint32_t)clip255(p[y * 4 + x] + c[y * 4 + x]) << (8 * x);
+            *reinterpret_cast<uint32_t *>(s.rec[1 + pl] + (size_t)(cy0 + y) * cw + cx0) = w;
+        }
+    } else if (lane < 26) {
+        reinterpret_cast<uint4 *>(co->luma_dc)[lane - 24] = make_uint4(0, 0, 0, 0);
+    }
+    const uint32_t nzmask = __ballot_sync(0xffffffffu, nnz != 0), dcmask = __ballot_sync(0xffffffffu, dc_nz);
+    int cbp = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if ((nzmask >> (4 * k)) & 15) cbp |= 1 << k;
+    cbp |= ((nzmask >> 16) & 255) ? 32 : ((dcmask ? 16 : 0));
+    if (lane < 24) mi->nnz[lane] = (uint8_t)nnz;
+    if (lane == 0) {
+        reinterpret_cast<uint32_t *>(mi)[0] = (uint32_t)MB_P16x16 | ((uint32_t)cbp << 24);
+        reinterpret_cast<uint32_t *>(mi)[1] = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
+    } else if (lane < 5) reinterpret_cast<uint32_t *>(mi)[1 + lane] = 0;
+}
+
+} // namespace b200

@@ -1,0 +1,141 @@
+// media_b200/csrc/k_test_abi.inl -- b200k_* C entry points (include/b200enc.h): host buffers in, production kernels, host buffers out.
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    explicit DevBuf(size_t n) { if (cudaMalloc(&p, n ? n : 16) != cudaSuccess) p = nullptr; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+void fill_geom(Geom &g, int w, int h, int slices, int range)
+{
+    memset(&g, 0, sizeof g);
+    g.width = w; g.height = h; g.mbw = (w + 15) / 16; g.mbh = (h + 15) / 16; g.wc = g.mbw * 16; g.hc = g.mbh * 16;
+    g.num_slices = slices; g.search_range = range;
+    for (int i = 1; i <= B200_MAX_SLICES; i++) g.slice_row0[i] = g.mbh;
+}
+#define K_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_last_cuda_error = (int)e_; return B200ENC_ECUDA; } } while (0)
+}
+
+extern "C" {
+
+int b200k_convert_to_i420(int device, int fmt, const uint8_t *in, int w, int h, uint8_t *out, int *coded_w, int *coded_h)
+{
+    if (!in || !out || w < 2 || h < 2 || (w & 1) || (h & 1) || fmt < 0 || fmt > 2) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    Geom g; fill_geom(g, w, h, 1, 16);
+    const size_t in_bytes = fmt == B200ENC_FMT_RGBA ? (size_t)w * h * 4 : (size_t)w * h * 3 / 2, ny = (size_t)g.wc * g.hc;
+    DevBuf din(in_bytes), dout(ny * 3 / 2), dsess(sizeof(Sess));
+    if (!din.p || !dout.p || !dsess.p) return B200ENC_ENOMEM;
+    Sess s; memset(&s, 0, sizeof s);
+    s.input = din.as<uint8_t>(); s.src[0] = dout.as<uint8_t>(); s.src[1] = s.src[0] + ny; s.src[2] = s.src[1] + ny / 4; s.input_format = fmt;
+    K_TRY(cudaMemcpy(din.p, in, in_bytes, cudaMemcpyHostToDevice));
+    K_TRY(cudaMemcpy(dsess.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    if (fmt == B200ENC_FMT_RGBA) k_ingest_rgba<<<dim3(((g.wc / 8) * (g.hc / 2) + 255) / 256, 1, 1), 256>>>(dsess.as<Sess>(), g);
+    else k_ingest_planar<<<dim3(((g.wc / 8) * g.hc * 3 / 2 + 255) / 256, 1, 1), 256>>>(dsess.as<Sess>(), g);
+    K_TRY(cudaGetLastError());
+    K_TRY(cudaMemcpy(out, dout.p, ny * 3 / 2, cudaMemcpyDeviceToHost));
+    if (coded_w) *coded_w = g.wc;
+    if (coded_h) *coded_h = g.hc;
+    return B200ENC_OK;
+}
+
+int b200k_downsample2(int device, const uint8_t *in, int w, int h, uint8_t *out)
+{
+    if (!in || !out || w < 8 || h < 2 || (w & 7) || (h & 1)) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    Geom g; memset(&g, 0, sizeof g); g.wc = w; g.hc = h;
+    DevBuf din((size_t)w * h), dout((size_t)w * h / 4), dsess(sizeof(Sess));
+    if (!din.p || !dout.p || !dsess.p) return B200ENC_ENOMEM;
+    Sess s; memset(&s, 0, sizeof s);
+    s.src[0] = din.as<uint8_t>(); s.srcL1 = dout.as<uint8_t>();
+    K_TRY(cudaMemcpy(din.p, in, (size_t)w * h, cudaMemcpyHostToDevice));
+    K_TRY(cudaMemcpy(dsess.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    k_downsample<<<dim3(((w / 8) * (h / 2) + 255) / 256, 1, 1), 256>>>(dsess.as<Sess>(), g, 0);
+    K_TRY(cudaGetLastError());
+    K_TRY(cudaMemcpy(out, dout.p, (size_t)w * h / 4, cudaMemcpyDeviceToHost));
+    return B200ENC_OK;
+}
+
+static int sad_common(int device, const uint8_t *cur, const uint8_t *ref, int stride, int n, const int32_t *xy, int32_t *out, int satd)
+{
+    if (!cur || !ref || !xy || !out || n <= 0 || stride < 16) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    int maxy = 0;
+    for (int i = 0; i < n; i++) { maxy = std::max(maxy, std::max(xy[4 * i + 1], xy[4 * i + 3])); }
+    const size_t bytes = (size_t)stride * (maxy + 16);
+    DevBuf dc(bytes), dr(bytes), dxy((size_t)n * 16), dout((size_t)n * 4);
+    if (!dc.p || !dr.p || !dxy.p || !dout.p) return B200ENC_ENOMEM;
+    K_TRY(cudaMemcpy(dc.p, cur, bytes, cudaMemcpyHostToDevice));
+    K_TRY(cudaMemcpy(dr.p, ref, bytes, cudaMemcpyHostToDevice));
+    K_TRY(cudaMemcpy(dxy.p, xy, (size_t)n * 16, cudaMemcpyHostToDevice));
+    k_test_sad16<<<(n + 127) / 128, 128>>>(dc.as<uint8_t>(), dr.as<uint8_t>(), stride, n, dxy.as<int>(), dout.as<int>(), satd);
+    K_TRY(cudaGetLastError());
+    K_TRY(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return B200ENC_OK;
+}
+int b200k_sad16x16(int device, const uint8_t *cur, const uint8_t *ref, int stride, int n, const int32_t *xy, int32_t *sad) { return sad_common(device, cur, ref, stride, n, xy, sad, 0); }
+int b200k_satd16x16(int device, const uint8_t *cur, const uint8_t *ref, int stride, int n, const int32_t *xy, int32_t *satd) { return sad_common(device, cur, ref, stride, n, xy, satd, 1); }
+
+int b200k_transform_block(int device, const int16_t *res, int n, int qp, int intra, int16_t *levels, int32_t *recon)
+{
+    if (!res || !levels || !recon || n <= 0 || qp < 0 || qp > 51) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    DevBuf dres((size_t)n * 32), dlev((size_t)n * 32), drec((size_t)n * 64);
+    if (!dres.p || !dlev.p || !drec.p) return B200ENC_ENOMEM;
+    K_TRY(cudaMemcpy(dres.p, res, (size_t)n * 32, cudaMemcpyHostToDevice));
+    k_test_transform<<<(n + 127) / 128, 128>>>(dres.as<int16_t>(), n, qp, intra, dlev.as<int16_t>(), drec.as<int>());
+    K_TRY(cudaGetLastError());
+    K_TRY(cudaMemcpy(levels, dlev.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    K_TRY(cudaMemcpy(recon, drec.p, (size_t)n * 64, cudaMemcpyDeviceToHost));
+    return B200ENC_OK;
+}
+
+int b200k_deblock(int device, uint8_t *i420, int mbw, int mbh, const void *mbinfo, int qp)
+{
+    if (!i420 || !mbinfo || mbw <= 0 || mbh <= 0 || qp < 0 || qp > 51) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    Geom g; fill_geom(g, mbw * 16, mbh * 16, 1, 16);
+    const size_t ny = (size_t)g.wc * g.hc, nmb = (size_t)mbw * mbh;
+    DevBuf dpix(ny * 3 / 2), dmbi(nmb * sizeof(MbInfo)), dprog((size_t)mbh * 8), dsess(sizeof(Sess)), dctl(sizeof(WaveCtl));
+    if (!dpix.p || !dmbi.p || !dprog.p || !dsess.p || !dctl.p) return B200ENC_ENOMEM;
+    Sess s; memset(&s, 0, sizeof s);
+    s.rec[0] = dpix.as<uint8_t>(); s.rec[1] = s.rec[0] + ny; s.rec[2] = s.rec[1] + ny / 4; s.mbi = dmbi.as<MbInfo>();
+    s.row_prog_intra = dprog.as<int>(); s.row_prog_dbk = dprog.as<int>() + mbh; s.qp = qp;
+    K_TRY(cudaMemcpy(dpix.p, i420, ny * 3 / 2, cudaMemcpyHostToDevice));
+    K_TRY(cudaMemcpy(dmbi.p, mbinfo, nmb * sizeof(MbInfo), cudaMemcpyHostToDevice));
+    K_TRY(cudaMemcpy(dsess.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    k_reset<<<(mbh + 255) / 256, 256>>>(dsess.as<Sess>(), g, 1, dctl.as<WaveCtl>());
+    k_deblock_wave<<<(mbh + WAVE_WARPS - 1) / WAVE_WARPS, WAVE_WARPS * 32>>>(dsess.as<Sess>(), g, 1, dctl.as<WaveCtl>());
+    K_TRY(cudaGetLastError());
+    K_TRY(cudaMemcpy(i420, dpix.p, ny * 3 / 2, cudaMemcpyDeviceToHost));
+    WaveCtl ctl; K_TRY(cudaMemcpy(&ctl, dctl.p, sizeof ctl, cudaMemcpyDeviceToHost));
+    return ctl.error ? B200ENC_EWAVE : B200ENC_OK;
+}
+
+int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz)
+{
+    if (!ginstr_per_s) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    cudaDeviceProp prop; K_TRY(cudaGetDeviceProperties(&prop, device));
+    const int ctas = prop.multiProcessorCount * 8, iters = 1 << 16;
+    DevBuf dsink((size_t)ctas * 256 * 4), dclk((size_t)ctas * 8);
+    if (!dsink.p || !dclk.p) return B200ENC_ENOMEM;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_vabsdiff4_peak<<<ctas, 256>>>(1u, 1 << 10, dsink.as<uint32_t>(), dclk.as<long long>());
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        k_vabsdiff4_peak<<<ctas, 256>>>(rep + 2u, iters, dsink.as<uint32_t>(), dclk.as<long long>());
+        cudaEventRecord(e1);
+        K_TRY(cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); best_ms = std::min(best_ms, ms);
+    }
+    long long clk = 0; K_TRY(cudaMemcpy(&clk, dclk.p, 8, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double instr = (double)ctas * 256 * iters * 32.0;
+    *ginstr_per_s = instr / (best_ms * 1e-3) / 1e9;
+    if (sm_clock_mhz) *sm_clock_mhz = (int)((double)clk / (best_ms * 1e-3) / 1e6);
+    return B200ENC_OK;
+}
+
+} // extern "C"

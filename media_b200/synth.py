@@ -41,7 +41,8 @@ class Content:
     def frame(self, t):
         w, h = self.w, self.h
         if self.kind == "A":
-            ox, oy = (3 * t) % 64, (-2 * t) % 64
+            tri = lambda v: v % 128 if v % 128 < 64 else 127 - v % 128   # bounce inside the 64-pixel margin: no jumps
+            ox, oy = tri(3 * t), 63 - tri(2 * t)
             y = np.roll(self.ty, (oy, ox), (0, 1))[:h, :w].copy()
             u = np.roll(self.tu, (oy // 2, ox // 2), (0, 1))[:h // 2, :w // 2]
             v = np.roll(self.tv, (oy // 2, ox // 2), (0, 1))[:h // 2, :w // 2]
