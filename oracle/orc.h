@@ -77,6 +77,8 @@ const int16_t *orc_me_level(const OrcEncoder *e, int level);
 const int32_t *orc_inter_cost(const OrcEncoder *e);
 /* quarter-pel sample of the current reference through the encoder's half-pel planes (== orc_interp_luma) */
 int orc_dbg_qpel(const OrcEncoder *e, int xq, int yq);
+/* (re)build the half-pel planes from the current reference picture; orc_encode does this itself for P frames */
+void orc_dbg_build_halfpel(OrcEncoder *e);
 
 /* ---- headers ---- */
 int orc_write_sps(uint8_t *out, int width, int height, int level_idc);

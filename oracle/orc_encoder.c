@@ -186,6 +186,7 @@ static int qpel_sample(const OrcEncoder *e, int xq, int yq)
     }
 }
 int orc_dbg_qpel(const OrcEncoder *e, int xq, int yq) { return qpel_sample(e, xq, yq); }
+void orc_dbg_build_halfpel(OrcEncoder *e) { build_halfpel(e); }
 
 static void mc_luma(const OrcEncoder *e, int x0, int y0, int mvx, int mvy, uint8_t *dst /*16x16*/)
 {

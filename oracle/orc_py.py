@@ -50,6 +50,7 @@ def lib():
         L.orc_me_level.restype = vp; L.orc_me_level.argtypes = [vp, C.c_int]
         L.orc_inter_cost.restype = vp; L.orc_inter_cost.argtypes = [vp]
         L.orc_dbg_qpel.restype = C.c_int; L.orc_dbg_qpel.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_dbg_build_halfpel.argtypes = [vp]
         L.orc_write_sps.restype = C.c_int; L.orc_write_sps.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.orc_write_pps.restype = C.c_int; L.orc_write_pps.argtypes = [vp]
         L.orc_level_for.restype = C.c_int; L.orc_level_for.argtypes = [C.c_int] * 3

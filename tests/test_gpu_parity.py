@@ -1,0 +1,304 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI (include/b200enc.h), against the CPU
+oracle on the same seeded inputs, against the committed golden hashes, and against an independent H.264 decoder.
+Everything here is integer/byte work, so the bar is bit-exact."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import avdec
+from media_b200.synth import Content, i420_to_rgba, psnr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "encode_golden.json")))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=lambda c: c["name"])
+def test_encode_matches_golden(enc, case):
+    """no oracle at run time: hashes of every access unit and reconstruction were produced by oracle/ (tools/make_golden.py)"""
+    g = enc.Session(case["w"], case["h"], const_qp=case["qp"], num_slices=case["slices"], search_range=case["sr"], gop=1000, device=0)
+    c = Content(case["kind"], case["w"], case["h"])
+    for t in range(case["frames"]):
+        bs, info = g.encode(c.frame(t))
+        assert len(bs) == case["au_bytes"][t]
+        assert hashlib.sha256(bs).hexdigest() == case["au_sha256"][t], f"frame {t} bitstream"
+        assert hashlib.sha256(g.recon().tobytes()).hexdigest() == case["recon_sha256"][t], f"frame {t} reconstruction"
+        assert info.frame_type == (1 if t == 0 else 0) and info.qp == case["qp"]
+    g.close()
+
+
+@pytest.mark.parametrize("w,h,kind,qp,slices,sr,frames", [
+    (208, 160, "A", 22, 1, 16, 4), (128, 96, "B", 35, 2, 32, 4), (96, 64, "D", 18, 4, 64, 3), (352, 288, "A", 30, 1, 16, 3),
+    (30, 18, "A", 26, 1, 16, 3), (1920, 1080, "B", 30, 1, 16, 2),
+])
+def test_every_stage_matches_the_oracle(enc, orc, w, h, kind, qp, slices, sr, frames):
+    g = enc.Session(w, h, const_qp=qp, num_slices=slices, search_range=sr, gop=1000, device=0, debug=1)
+    o = orc.Encoder(w, h, num_slices=slices, search_range=sr)
+    c = Content(kind, w, h)
+    ny = g.mbw * g.mbh * 256
+    for t in range(frames):
+        f = c.frame(t)
+        bs, _ = g.encode(f); ref = o.encode(f, t == 0, qp)
+        if t > 0:
+            for lv in (2, 1, 0):
+                assert np.array_equal(g.stage(f"me{lv}"), o.me_level(lv)), f"frame {t} ME level {lv}"
+            inter = o.mb_info()["mb_type"] != 1
+            assert np.array_equal(g.stage("inter_cost"), o.inter_cost())
+        gi, oi = g.stage("mbinfo"), o.mb_info()
+        for fld in ("mb_type", "i16_mode", "chroma_mode", "cbp", "mv", "nnz"):
+            assert np.array_equal(gi[fld], oi[fld]), f"frame {t} mbinfo.{fld}"
+        gc, oc = g.stage("mbcoef"), o.mb_coef()
+        for fld in ("luma", "luma_dc", "chroma_dc", "chroma_ac"):
+            assert np.array_equal(gc[fld], oc[fld]), f"frame {t} coef.{fld}"
+        for name, which in (("src", 0), ("rec_pre", 1), ("rec", 2)):
+            gs = g.stage(name)
+            for comp, (off, sz, ww) in enumerate(((0, ny, g.mbw * 16), (ny, ny // 4, g.mbw * 8), (ny * 5 // 4, ny // 4, g.mbw * 8))):
+                assert np.array_equal(gs[off:off + sz].reshape(-1, ww), o.plane(which, comp)), f"frame {t} {name}[{comp}]"
+        assert bs == ref, f"frame {t} bitstream"
+    g.close()
+
+
+def test_stream_decodes_to_own_reconstruction_1080p(enc):
+    """size-independent property at the BASELINE size: decode(GPU stream) == GPU reconstruction, CBR mode, forced IDR mid-stream"""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    w, h = 1920, 1080
+    g = enc.Session(w, h, fps=30, bitrate=4_000_000, gop=300, const_qp=-1, device=0)
+    c = Content("A", w, h)
+    aus, recs, types = [], [], []
+    for t in range(8):
+        if t == 5:
+            g.force_idr()
+        bs, info = g.encode(c.frame(t)); aus.append(bs); recs.append(g.recon()); types.append(info.frame_type)
+    assert types == [1, 0, 0, 0, 0, 1, 0, 0]
+    dec = avdec.decode_stream(aus)
+    assert len(dec) == 8
+    for t, (d, r) in enumerate(zip(dec, recs)):
+        assert np.array_equal(d, r), f"frame {t}"
+    assert psnr(c.frame(7)[:w * h], recs[7][:w * h]) > 25
+    g.close()
+
+
+def test_4k_eight_slices_range64(enc):
+    """BASELINE.json configs[3]: 3840x2160, 8 slices, +-64 search; stream must decode to the encoder's reconstruction"""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    w, h = 3840, 2160
+    g = enc.Session(w, h, const_qp=30, num_slices=8, search_range=64, gop=1000, device=0)
+    c = Content("C", w, h)
+    base = c.frame(0)
+    Y = base[:w * h].reshape(h, w)
+    aus, recs = [], []
+    for t in range(3):
+        y = np.roll(Y, (7 * t, 40 * t), (0, 1))       # 40 px/frame horizontal motion: needs the wide search
+        f = np.concatenate([y.ravel(), base[w * h:]])
+        bs, _ = g.encode(f); aus.append(bs); recs.append(g.recon())
+    assert sum(1 for i in range(len(aus[1]) - 4) if aus[1][i:i + 5] == b"\0\0\0\1\x61") == 8
+    dec = avdec.decode_stream(aus)
+    assert len(dec) == 3 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+    mv = g.stage("mbinfo")["mv"]
+    assert np.median(mv[:, 0]) == -160       # -40 px in quarter-pel units
+    g.close()
+
+
+def test_batch_equals_individual_sessions(enc):
+    w, h, n = 320, 192, 5
+    cs = [Content("A" if i % 2 else "B", w, h, seed=100 + i) for i in range(n)]
+    solo = []
+    for i in range(n):
+        s = enc.Session(w, h, const_qp=24 + i, gop=3, device=0)
+        solo.append([s.encode(cs[i].frame(t))[0] for t in range(5)]); s.close()
+    ss = [enc.Session(w, h, const_qp=24 + i, gop=3, device=0) for i in range(n)]
+    b = enc.Batch(0, ss)
+    for t in range(5):
+        out, infos = b.encode([cs[i].frame(t) for i in range(n)])
+        for i in range(n):
+            assert out[i] == solo[i][t], f"session {i} frame {t}"
+            assert infos[i].frame_type == (1 if t % 3 == 0 else 0)
+    assert b.launches() >= 8
+    for s in ss:
+        s.close()
+    b.close()
+
+
+def test_device_resident_input_equals_host_input(enc):
+    w, h = 256, 144
+    L = enc.lib()
+    c = Content("A", w, h)
+    s1 = enc.Session(w, h, const_qp=28, device=0); s2 = enc.Session(w, h, const_qp=28, device=0)
+    b = enc.Batch(0, [s2])
+    for t in range(3):
+        f = c.frame(t)
+        ref, _ = s1.encode(f)
+        p = L.b200enc_dev_alloc(0, f.size); enc.check(L.b200enc_dev_upload(0, p, _p(f), f.size))
+        b.encode_ptrs([p], 1)
+        assert b.bitstream(0) == ref
+        L.b200enc_dev_free(0, p)
+    s1.close(); s2.close(); b.close()
+
+
+@pytest.mark.parametrize("w,h", [(64, 32), (1280, 720), (322, 182), (18, 30)])
+def test_rgba_and_nv12_ingest(enc, orc, w, h):
+    L, O = enc.lib(), orc.lib()
+    rng = np.random.default_rng(w * h)
+    wc, hc = (w + 15) // 16 * 16, (h + 15) // 16 * 16
+
+    def pad(i420):
+        out = []
+        for k, (pw, ph, cw, ch) in enumerate(((w, h, wc, hc), (w // 2, h // 2, wc // 2, hc // 2), (w // 2, h // 2, wc // 2, hc // 2))):
+            off = 0 if k == 0 else w * h + (k - 1) * (w // 2) * (h // 2)
+            p = i420[off:off + pw * ph].reshape(ph, pw)
+            out.append(np.pad(p, ((0, ch - ph), (0, cw - pw)), mode="edge").ravel())
+        return np.concatenate(out)
+
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    want = np.zeros(w * h * 3 // 2, np.uint8); O.orc_rgba_to_i420(_p(rgba), w, h, _p(want))
+    got = np.zeros(wc * hc * 3 // 2, np.uint8); cw_, ch_ = C.c_int(), C.c_int()
+    enc.check(L.b200k_convert_to_i420(0, enc.FMT_RGBA, _p(rgba), w, h, _p(got), C.byref(cw_), C.byref(ch_)))
+    assert (cw_.value, ch_.value) == (wc, hc) and np.array_equal(got, pad(want))
+    nv = rng.integers(0, 256, w * h * 3 // 2, dtype=np.uint8)
+    want = np.zeros_like(nv); O.orc_nv12_to_i420(_p(nv), w, h, _p(want))
+    enc.check(L.b200k_convert_to_i420(0, enc.FMT_NV12, _p(nv), w, h, _p(got), None, None))
+    assert np.array_equal(got, pad(want))
+    enc.check(L.b200k_convert_to_i420(0, enc.FMT_I420, _p(nv), w, h, _p(got), None, None))
+    assert np.array_equal(got, pad(nv))
+
+
+def test_rgba_session_equals_i420_session_on_converted_frames(enc, orc):
+    w, h = 320, 176
+    c = Content("B", w, h)
+    sr = enc.Session(w, h, const_qp=26, input_format=enc.FMT_RGBA, device=0); si = enc.Session(w, h, const_qp=26, device=0)
+    for t in range(3):
+        rgba = i420_to_rgba(c.frame(t), w, h)
+        conv = np.zeros(w * h * 3 // 2, np.uint8); orc.lib().orc_rgba_to_i420(_p(rgba), w, h, _p(conv))
+        assert sr.encode(rgba)[0] == si.encode(conv)[0]
+    sr.close(); si.close()
+
+
+def test_downsample_sad_satd_transform_kernels(enc, orc):
+    L, O = enc.lib(), orc.lib()
+    rng = np.random.default_rng(7)
+    w, h = 256, 64
+    a = rng.integers(0, 256, (h, w), dtype=np.uint8); b = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    got = np.zeros((h // 2, w // 2), np.uint8); want = np.zeros_like(got)
+    enc.check(L.b200k_downsample2(0, _p(a), w, h, _p(got))); O.orc_downsample2(_p(a), w, w, h, _p(want), w // 2)
+    assert np.array_equal(got, want)
+    n = 300
+    xy = np.stack([rng.integers(0, w - 16, n), rng.integers(0, h - 16, n), rng.integers(0, w - 16, n), rng.integers(0, h - 16, n)], 1).astype(np.int32)
+    sad = np.zeros(n, np.int32); satd = np.zeros(n, np.int32)
+    enc.check(L.b200k_sad16x16(0, _p(a), _p(b), w, n, _p(xy), _p(sad))); enc.check(L.b200k_satd16x16(0, _p(a), _p(b), w, n, _p(xy), _p(satd)))
+    for i in range(n):
+        pa = a.ctypes.data + int(xy[i, 1]) * w + int(xy[i, 0]); pb = b.ctypes.data + int(xy[i, 3]) * w + int(xy[i, 2])
+        assert sad[i] == O.orc_sad(pa, w, pb, w, 16, 16) and satd[i] == O.orc_satd16x16(pa, w, pb, w)
+    # extremes: all-0 against all-255
+    z = np.zeros((16, 16), np.uint8); f = np.full((16, 16), 255, np.uint8); one = np.zeros((1, 4), np.int32); r = np.zeros(1, np.int32)
+    enc.check(L.b200k_sad16x16(0, _p(z), _p(f), 16, 1, _p(one), _p(r))); assert r[0] == 255 * 256
+    for qp in (0, 17, 26, 38, 51):
+        for intra in (0, 1):
+            res = rng.integers(-255, 256, (200, 16)).astype(np.int16)
+            res[0] = 255; res[1] = -255; res[2] = 0
+            lev = np.zeros((200, 16), np.int16); rec = np.zeros((200, 16), np.int32)
+            enc.check(L.b200k_transform_block(0, _p(res), 200, qp, intra, _p(lev), _p(rec)))
+            for i in range(200):
+                coef = np.zeros(16, np.int16); O.orc_dct4x4(_p(res[i]), _p(coef))
+                lz = np.zeros(16, np.int16); O.orc_quant4x4(_p(coef), _p(lz), qp, intra, 0)
+                d = np.zeros(16, np.int32); O.orc_dequant4x4(_p(lz), _p(d), qp, 0)
+                rr = np.zeros(16, np.int32); O.orc_idct4x4(_p(d), _p(rr))
+                assert np.array_equal(lev[i], lz) and np.array_equal(rec[i], rr), (qp, intra, i)
+
+
+def test_deblock_kernel_on_random_macroblock_info(enc, orc):
+    """adversarial deblocking input: random pixels and random (type, nnz, mv) so every bS value and filter branch is hit"""
+    L, O = enc.lib(), orc.lib()
+    rng = np.random.default_rng(11)
+    mbw, mbh = 7, 5
+    for qp in (20, 32, 45, 51):
+        pix = rng.integers(0, 256, mbw * mbh * 384, dtype=np.uint8)
+        base = rng.integers(60, 200); pix = np.clip(base + rng.integers(-12, 13, pix.size), 0, 255).astype(np.uint8) if qp > 30 else pix
+        mbi = np.zeros(mbw * mbh, enc.MBINFO_DTYPE)
+        mbi["mb_type"] = rng.choice([0, 0, 1, 3], mbw * mbh)
+        mbi["nnz"] = rng.integers(0, 3, (mbw * mbh, 24)) * (rng.random((mbw * mbh, 24)) < 0.3)
+        mbi["mv"] = rng.integers(-9, 10, (mbw * mbh, 2))
+        want = pix.copy(); ny = mbw * mbh * 256
+        O.orc_deblock_frame(want.ctypes.data, mbw * 16, want.ctypes.data + ny, want.ctypes.data + ny + ny // 4, mbw * 8, mbw, mbh, _p(mbi), qp)
+        got = pix.copy()
+        enc.check(L.b200k_deblock(0, _p(got), mbw, mbh, _p(mbi), qp))
+        assert np.array_equal(got, want), qp
+        assert not np.array_equal(got, pix)
+
+
+def test_error_paths(enc):
+    L = enc.lib()
+    with pytest.raises(enc.B200EncError):
+        enc.Session(15, 16, const_qp=26)            # odd / too small
+    with pytest.raises(enc.B200EncError):
+        enc.Session(64, 64, const_qp=26, search_range=18)
+    with pytest.raises(enc.B200EncError):
+        enc.Session(64, 64, const_qp=-1, bitrate=0)
+    s = enc.Session(64, 64, const_qp=26, device=0)
+    f = np.zeros(64 * 64 * 3 // 2 - 1, np.uint8)
+    bs, n = C.c_void_p(), C.c_uint32()
+    assert L.b200enc_encode(s.h, _p(f), f.size, C.byref(bs), C.byref(n), None) == -5     # B200ENC_ESIZE, as the reference rejects short input
+    s2 = enc.Session(128, 64, const_qp=26, device=0)
+    with pytest.raises(enc.B200EncError):
+        enc.Batch(0, [s, s2]).encode([np.zeros(6144, np.uint8), np.zeros(12288, np.uint8)])    # mixed geometry in one batch
+    s.close(); s2.close()
+
+
+def test_cbr_hits_the_target_bitrate(enc):
+    w, h, fps, br = 640, 368, 30, 1_000_000
+    s = enc.Session(w, h, fps=fps, bitrate=br, gop=300, const_qp=-1, device=0)
+    c = Content("A", w, h)
+    sizes, qps = [], []
+    for t in range(90):
+        bs, info = s.encode(c.frame(t)); sizes.append(len(bs)); qps.append(info.qp)
+    rate = sum(sizes[30:]) * 8 * fps / 60
+    assert 0.7 * br < rate < 1.3 * br, (rate, qps[-10:])
+    s.close()
+
+
+def test_video_codec_api_flow(enc):
+    """the cloud-phone caller's flow through libVideoCodec.so: Create -> Init -> Start -> EncodeOneFrame x N (key frame and
+    parameter change through properties) -> Stop -> Destroy (reference: video_codec/VideoEncoderOpenH264.cpp:304-352)"""
+    L = C.CDLL(os.path.join(ROOT, "media_b200", "host", "libVideoCodec.so"))
+    L.vc_create.argtypes = [C.POINTER(C.c_void_p)]
+    for f in ("vc_init", "vc_start", "vc_stop", "vc_reset", "vc_destroy"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.vc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    L.vc_prop_set.argtypes = [C.c_char_p, C.c_char_p]; L.vc_prop_get.argtypes = [C.c_char_p, C.c_char_p]
+    w, h = 720, 1280
+    for k, v in ((b"ro.vmi.demo.video.encode.format", b"3"), (b"ro.sys.vmi.cloudphone", b"video"), (b"ro.hardware.width", b"720"),
+                 (b"ro.hardware.height", b"1280"), (b"ro.hardware.fps", b"30"), (b"persist.vmi.video.encode.bitrate", b"4000000"),
+                 (b"persist.vmi.video.encode.gopsize", b"30"), (b"persist.vmi.video.encode.profile", b"baseline"),
+                 (b"persist.vmi.video.encode.param_adjusting", b"0"), (b"persist.vmi.video.encode.keyframe", b"0")):
+        L.vc_prop_set(k, v)
+    e = C.c_void_p()
+    assert L.vc_create(C.byref(e)) == 0 and L.vc_init(e) == 0 and L.vc_start(e) == 0
+    c = Content("B", w, h)
+    aus = []
+    out, n = C.c_void_p(), C.c_uint32()
+    for t in range(7):
+        f = c.frame(t)
+        if t == 3:
+            L.vc_prop_set(b"persist.vmi.video.encode.keyframe", b"1")
+        if t == 5:
+            L.vc_prop_set(b"persist.vmi.video.encode.bitrate", b"2000000"); L.vc_prop_set(b"persist.vmi.video.encode.param_adjusting", b"1")
+        assert L.vc_encode(e, _p(f), f.size, C.byref(out), C.byref(n)) == 0
+        aus.append(C.string_at(out.value, n.value))
+    assert L.vc_encode(e, _p(f), 100, C.byref(out), C.byref(n)) == 4         # short input -> ENCODE_FAIL
+    buf = C.create_string_buffer(92); L.vc_prop_get(b"persist.vmi.video.encode.keyframe", buf); assert buf.value == b"0"
+    L.vc_prop_get(b"persist.vmi.video.encode.param_adjusting", buf); assert buf.value == b"0"
+    kinds = [a[4] for a in aus]
+    assert kinds == [0x67, 0x61, 0x61, 0x67, 0x61, 0x67, 0x61]     # IDR at 0, forced at 3, encoder reset (new SPS) at 5
+    assert L.vc_stop(e) == 0
+    assert L.vc_destroy(e) == 0
+    if avdec.available():
+        assert len(avdec.decode_stream(aus)) == 7

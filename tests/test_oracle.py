@@ -1,0 +1,183 @@
+"""CPU tests of the oracle (oracle/): it is pinned by (a) FFmpeg's independent H.264 decoder reproducing its
+reconstruction bit for bit, (b) the CAVLC / deblock / QP tables matching the copies inside that decoder's binary,
+(c) the committed golden hashes. The reference itself holds no test vectors for this path."""
+import glob
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import avdec
+from media_b200.synth import Content
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "encode_golden.json")))
+needs_decoder = pytest.mark.skipif(not avdec.available(), reason="libavcodec from the opencv wheel not loadable")
+
+
+def encode_case(orc, c, frames=None):
+    e = orc.Encoder(c["w"], c["h"], num_slices=c["slices"], search_range=c["sr"])
+    content = Content(c["kind"], c["w"], c["h"])
+    aus, recs = [], []
+    for t in range(frames or c["frames"]):
+        aus.append(e.encode(content.frame(t), t == 0, c["qp"])); recs.append(e.recon())
+    return aus, recs
+
+
+@pytest.mark.parametrize("case", [c for c in GOLDEN if c["w"] * c["h"] <= 640 * 360], ids=lambda c: c["name"])
+def test_oracle_matches_golden(orc, case):
+    aus, recs = encode_case(orc, case)
+    assert [hashlib.sha256(a).hexdigest() for a in aus] == case["au_sha256"]
+    assert [hashlib.sha256(r.tobytes()).hexdigest() for r in recs] == case["recon_sha256"]
+    if "stream_hex" in case:
+        assert [a.hex() for a in aus] == case["stream_hex"]
+
+
+@needs_decoder
+@pytest.mark.parametrize("case", [c for c in GOLDEN if c["w"] * c["h"] <= 640 * 360], ids=lambda c: c["name"])
+def test_oracle_stream_decodes_to_its_reconstruction(orc, case):
+    aus, recs = encode_case(orc, case)
+    dec = avdec.decode_stream(aus)
+    assert len(dec) == len(recs)
+    for t, (d, r) in enumerate(zip(dec, recs)):
+        assert np.array_equal(d, r), f"frame {t}: decoder output differs from the oracle reconstruction"
+
+
+@needs_decoder
+def test_golden_stream_decodes_without_the_oracle():
+    case = next(c for c in GOLDEN if "stream_hex" in c)
+    dec = avdec.decode_stream([bytes.fromhex(h) for h in case["stream_hex"]])
+    assert [hashlib.sha256(d.tobytes()).hexdigest() for d in dec] == case["recon_sha256"]
+
+
+@needs_decoder
+def test_forced_idr_and_slices_mid_stream(orc):
+    w, h = 128, 96
+    e = orc.Encoder(w, h, num_slices=3, search_range=32)
+    c = Content("A", w, h)
+    aus, recs = [], []
+    for t in range(6):
+        aus.append(e.encode(c.frame(t), t in (0, 3), 28 + t)); recs.append(e.recon())   # QP changes per frame, IDR at 3
+    assert aus[3][4] == 0x67 and aus[1][4] == 0x61
+    dec = avdec.decode_stream(aus)
+    assert all(np.array_equal(d, r) for d, r in zip(dec, recs)) and len(dec) == 6
+
+
+def test_tables_match_the_independent_decoder():
+    """Tables 9-5, 9-7..9-10, 8-15, 8-16 and the zig-zag scan are present byte for byte inside libavcodec."""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    import cv2
+    d = os.path.join(os.path.dirname(cv2.__file__), "..", "opencv_python_headless.libs")
+    blob = open(glob.glob(os.path.join(d, "libavcodec-*"))[0], "rb").read()
+    for header in (os.path.join(ROOT, "oracle", "h264_tables.h"),):
+        src = open(header).read()
+        tabs = {m.group(1): bytes(int(x) for x in re.findall(r"\d+", m.group(2)))
+                for m in re.finditer(r"static const uint8_t (\w+)\[[^\]]*\](?:\[[^\]]*\])? = \{(.*?)\};", src, re.S)}
+        for name in ("COEFF_TOKEN_LEN", "COEFF_TOKEN_BITS", "CHROMA_DC_COEFF_TOKEN_LEN", "CHROMA_DC_COEFF_TOKEN_BITS", "TOTAL_ZEROS_LEN",
+                     "TOTAL_ZEROS_BITS", "CHROMA_DC_TOTAL_ZEROS_LEN", "CHROMA_DC_TOTAL_ZEROS_BITS", "RUN_BEFORE_LEN", "RUN_BEFORE_BITS",
+                     "ZIGZAG4x4", "CHROMA_QP", "DEBLOCK_ALPHA", "DEBLOCK_BETA"):
+            assert blob.find(tabs[name]) >= 0, name
+
+
+def test_product_tables_equal_oracle_tables():
+    """media_b200/csrc/h264_dev.cuh carries its own copies (the product never includes oracle/); they must agree."""
+    def nums(text, name):
+        m = re.search(name + r"\[[^\]]*\](?:\[[^\]]*\])? = \{(.*?)\};", text, re.S)
+        assert m, name
+        return [int(x) for x in re.findall(r"\d+", m.group(1))]
+    o = open(os.path.join(ROOT, "oracle", "h264_tables.h")).read()
+    p = open(os.path.join(ROOT, "media_b200", "csrc", "h264_dev.cuh")).read()
+    pairs = [("COEFF_TOKEN_LEN", "c_coeff_token_len"), ("COEFF_TOKEN_BITS", "c_coeff_token_bits"), ("CHROMA_DC_COEFF_TOKEN_LEN", "c_cdc_token_len"),
+             ("CHROMA_DC_COEFF_TOKEN_BITS", "c_cdc_token_bits"), ("TOTAL_ZEROS_LEN", "c_total_zeros_len"), ("TOTAL_ZEROS_BITS", "c_total_zeros_bits"),
+             ("CHROMA_DC_TOTAL_ZEROS_LEN", "c_cdc_total_zeros_len"), ("CHROMA_DC_TOTAL_ZEROS_BITS", "c_cdc_total_zeros_bits"),
+             ("RUN_BEFORE_LEN", "c_run_before_len"), ("RUN_BEFORE_BITS", "c_run_before_bits"), ("ZIGZAG4x4", "c_zigzag"), ("QUANT_MF", "c_quant_mf"),
+             ("DEQUANT_V", "c_dequant_v"), ("CHROMA_QP", "c_chroma_qp"), ("DEBLOCK_ALPHA", "c_alpha"), ("DEBLOCK_BETA", "c_beta"), ("DEBLOCK_TC0", "c_tc0"),
+             ("CBP_TO_CODENUM_INTER", "c_cbp_inter"), ("LAMBDA_TAB", "c_lambda")]
+    for a, b in pairs:
+        assert nums(o, a) == nums(p, b), (a, b)
+
+
+def test_transform_round_trip_and_quant(orc):
+    L = orc.lib(); rng = np.random.default_rng(1)
+    for qp in (0, 12, 26, 40, 51):
+        for _ in range(50):
+            res = rng.integers(-255, 256, 16).astype(np.int16)
+            coef = np.zeros(16, np.int16); L.orc_dct4x4(res.ctypes.data, coef.ctypes.data)
+            # forward core transform against the matrix definition Cf X Cf^T
+            Cf = np.array([[1, 1, 1, 1], [2, 1, -1, -2], [1, -1, -1, 1], [1, -2, 2, -1]])
+            assert np.array_equal(coef.reshape(4, 4), Cf @ res.reshape(4, 4).astype(np.int64) @ Cf.T)
+            lz = np.zeros(16, np.int16); n = L.orc_quant4x4(coef.ctypes.data, lz.ctypes.data, qp, 1, 0)
+            assert n == np.count_nonzero(lz)
+            d = np.zeros(16, np.int32); L.orc_dequant4x4(lz.ctypes.data, d.ctypes.data, qp, 0)
+            r = np.zeros(16, np.int32); L.orc_idct4x4(d.ctypes.data, r.ctypes.data)
+            # reconstruction error bounded by the quantiser step (Qstep doubles every 6 QP, 0.625 at QP 0)
+            step = 0.625 * 2 ** (qp / 6)
+            assert np.abs(r - res).max() <= 1.5 * step + 1
+
+
+def test_sad_satd_definitions(orc):
+    L = orc.lib(); rng = np.random.default_rng(2)
+    a = rng.integers(0, 256, (16, 32), dtype=np.uint8); b = rng.integers(0, 256, (16, 32), dtype=np.uint8)
+    assert L.orc_sad(a.ctypes.data, 32, b.ctypes.data, 32, 16, 16) == int(np.abs(a[:, :16].astype(int) - b[:, :16].astype(int)).sum())
+    Hm = np.array([[1, 1, 1, 1], [1, 1, -1, -1], [1, -1, -1, 1], [1, -1, 1, -1]])
+    d = a[:4, :4].astype(int) - b[:4, :4].astype(int)
+    assert L.orc_satd4x4(a.ctypes.data, 32, b.ctypes.data, 32) == int(np.abs(Hm @ d @ Hm.T).sum()) // 2
+    assert L.orc_satd16x16(a.ctypes.data, 32, a.ctypes.data, 32) == 0
+
+
+def test_emulation_prevention_vectors(orc):
+    L = orc.lib()
+    def esc(b):
+        i = np.frombuffer(bytes(b), np.uint8).copy(); o = np.zeros(len(b) * 2 + 4, np.uint8)
+        n = L.orc_escape_rbsp(i.ctypes.data, len(b), o.ctypes.data); return bytes(o[:n])
+    assert esc([0, 0, 0]) == bytes([0, 0, 3, 0])
+    assert esc([0, 0, 1]) == bytes([0, 0, 3, 1])
+    assert esc([0, 0, 4]) == bytes([0, 0, 4])
+    assert esc([0, 0, 0, 0, 0]) == bytes([0, 0, 3, 0, 0, 3, 0])
+    assert esc([1, 0, 0, 3, 0, 0, 2]) == bytes([1, 0, 0, 3, 3, 0, 0, 3, 2])
+
+
+def test_level_table(orc):
+    L = orc.lib()
+    assert L.orc_level_for(1280, 720, 30) == 31 and L.orc_level_for(1920, 1080, 30) == 40
+    assert L.orc_level_for(1920, 1080, 60) == 42 and L.orc_level_for(3840, 2160, 30) == 51 and L.orc_level_for(176, 144, 30) == 11
+
+
+def test_qpel_planes_equal_the_normative_interpolation(orc):
+    """the encoder's half-pel planes give the same samples as the direct 8.4.2.2.1 evaluation, including far outside the picture"""
+    w, h = 48, 32
+    e = orc.Encoder(w, h); c = Content("D", w, h)
+    e.encode(c.frame(0), True, 30)
+    ref = np.ascontiguousarray(e.plane(3, 0)); L = orc.lib()
+    L.orc_dbg_build_halfpel(e.h)             # planes of the current reference (orc_encode builds them for every P frame)
+    rng = np.random.default_rng(3)
+    for _ in range(3000):
+        xq, yq = int(rng.integers(-80, 4 * w + 80)), int(rng.integers(-80, 4 * h + 80))
+        assert L.orc_dbg_qpel(e.h, xq, yq) == L.orc_interp_luma(ref.ctypes.data, w, w, h, xq, yq)
+
+
+def test_colour_conversion_definition(orc):
+    L = orc.lib(); rng = np.random.default_rng(4); w, h = 20, 12
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    out = np.zeros(w * h * 3 // 2, np.uint8); L.orc_rgba_to_i420(rgba.ctypes.data, w, h, out.ctypes.data)
+    R, G, B = (rgba[..., i].astype(int) for i in range(3))
+    assert np.array_equal(out[:w * h].reshape(h, w), ((66 * R + 129 * G + 25 * B + 128) >> 8) + 16)
+    m = lambda P: (P.reshape(h // 2, 2, w // 2, 2).sum((1, 3)) + 2) >> 2
+    r, g, b = m(R), m(G), m(B)
+    assert np.array_equal(out[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), ((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128)
+    assert np.array_equal(out[w * h * 5 // 4:].reshape(h // 2, w // 2), ((112 * r - 94 * g - 18 * b + 128) >> 8) + 128)
+    nv = rng.integers(0, 256, w * h * 3 // 2, dtype=np.uint8); o2 = np.zeros_like(nv); L.orc_nv12_to_i420(nv.ctypes.data, w, h, o2.ctypes.data)
+    assert np.array_equal(o2[w * h:w * h * 5 // 4], nv[w * h::2]) and np.array_equal(o2[w * h * 5 // 4:], nv[w * h + 1::2])
+
+
+def test_static_content_converges_to_skip(orc):
+    w, h = 160, 96
+    e = orc.Encoder(w, h); c = Content("C", w, h)
+    idr = e.encode(c.frame(0), True, 30)
+    for t in range(1, 6):
+        au = e.encode(c.frame(t), False, 30)
+    assert (e.mb_info()["mb_type"] == 3).mean() > 0.8 and len(au) < len(idr) // 20
