@@ -59,17 +59,25 @@ __global__ void __launch_bounds__(256) k_ingest_rgba(const Sess *ss, Geom g)
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= (wc / 8) * (hc / 2)) return;
     const int x = (u % (wc / 8)) * 8, y = (u / (wc / 8)) * 2;
-    uint32_t px[2][8];
-    const bool fast = x + 8 <= w && (w & 3) == 0;
+    uint32_t px[2][8], cpx[2][8];      // luma taps and chroma taps (they differ only inside the padding)
+    const bool fast = x + 8 <= w && y + 2 <= h && (w & 3) == 0;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        const uint8_t *row = s.input + (size_t)min(y + r, h - 1) * w * 4;
         if (fast) {
+            const uint8_t *row = s.input + (size_t)(y + r) * w * 4;
             uint4 a = *reinterpret_cast<const uint4 *>(row + 4 * x), b = *reinterpret_cast<const uint4 *>(row + 4 * x + 16);
             px[r][0] = a.x; px[r][1] = a.y; px[r][2] = a.z; px[r][3] = a.w; px[r][4] = b.x; px[r][5] = b.y; px[r][6] = b.z; px[r][7] = b.w;
-        } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) px[r][i] = *reinterpret_cast<const uint32_t *>(row + 4 * min(x + i, w - 1));
+            for (int i = 0; i < 8; i++) cpx[r][i] = px[r][i];
+        } else {
+            // padding replicates the last luma sample and the last CHROMA sample (not the chroma of a replicated pixel)
+            const uint8_t *row = s.input + (size_t)min(y + r, h - 1) * w * 4;
+            const uint8_t *crow = s.input + (size_t)(2 * min(y / 2, h / 2 - 1) + r) * w * 4;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                px[r][i] = *reinterpret_cast<const uint32_t *>(row + 4 * min(x + i, w - 1));
+                cpx[r][i] = *reinterpret_cast<const uint32_t *>(crow + 4 * (2 * min(x / 2 + i / 2, w / 2 - 1) + (i & 1)));
+            }
         }
     }
     uint32_t yw[2][2] = { { 0, 0 }, { 0, 0 } }, uw = 0, vw = 0;
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(256) k_ingest_rgba(const Sess *ss, Geom g)
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
-            for (int k = 0; k < 2; k++) { uint32_t p = px[r][2 * i + k]; R += p & 255; G += (p >> 8) & 255; B += (p >> 16) & 255; }
+            for (int k = 0; k < 2; k++) { uint32_t p = cpx[r][2 * i + k]; R += p & 255; G += (p >> 8) & 255; B += (p >> 16) & 255; }
         R = (R + 2) >> 2; G = (G + 2) >> 2; B = (B + 2) >> 2;
         uw |= (uint32_t)(((-38 * R - 74 * G + 112 * B + 128) >> 8) + 128) << (8 * i);
         vw |= (uint32_t)(((112 * R - 94 * G - 18 * B + 128) >> 8) + 128) << (8 * i);

@@ -53,13 +53,18 @@ class Content:
         elif self.kind == "C":
             y, u, v = self.ty[:h, :w], self.tu[:h // 2, :w // 2], self.tv[:h // 2, :w // 2]
         elif self.kind == "B":
-            r = np.random.default_rng(SEED + 7919 * t)
-            y = self.by
+            # cumulative screen updates: frame t = base picture with the updates of steps 0..t applied (stateless for the caller)
+            if getattr(self, "_b_t", None) is None or self._b_t > t:
+                self._b_y, self._b_t = self.by.copy(), -1
+            y = self._b_y
             mbw, mbh = (w + 15) // 16, (h + 15) // 16
-            for _ in range(max(1, mbw * mbh // 20)):
-                mx, my = r.integers(0, mbw), r.integers(0, mbh)
-                blk = y[my * 16:my * 16 + 16, mx * 16:mx * 16 + 16]
-                blk[...] = np.where(r.random(blk.shape) < 0.15, 16, r.integers(100, 235)).astype(np.uint8)
+            while self._b_t < t:
+                self._b_t += 1
+                r = np.random.default_rng(SEED + 7919 * self._b_t)
+                for _ in range(max(1, mbw * mbh // 20)):
+                    mx, my = r.integers(0, mbw), r.integers(0, mbh)
+                    blk = y[my * 16:my * 16 + 16, mx * 16:mx * 16 + 16]
+                    blk[...] = np.where(r.random(blk.shape) < 0.15, 16, r.integers(100, 235)).astype(np.uint8)
             u, v = self.bu, self.bv
         else:
             r = np.random.default_rng(SEED + t)

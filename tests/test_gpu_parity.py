@@ -221,8 +221,8 @@ def test_deblock_kernel_on_random_macroblock_info(enc, orc):
     rng = np.random.default_rng(11)
     mbw, mbh = 7, 5
     for qp in (20, 32, 45, 51):
-        pix = rng.integers(0, 256, mbw * mbh * 384, dtype=np.uint8)
-        base = rng.integers(60, 200); pix = np.clip(base + rng.integers(-12, 13, pix.size), 0, 255).astype(np.uint8) if qp > 30 else pix
+        amp = 2 if qp < 30 else 12
+        pix = np.clip(rng.integers(60, 200) + rng.integers(-amp, amp + 1, mbw * mbh * 384), 0, 255).astype(np.uint8)
         mbi = np.zeros(mbw * mbh, enc.MBINFO_DTYPE)
         mbi["mb_type"] = rng.choice([0, 0, 1, 3], mbw * mbh)
         mbi["nnz"] = rng.integers(0, 3, (mbw * mbh, 24)) * (rng.random((mbw * mbh, 24)) < 0.3)
