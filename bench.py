@@ -102,9 +102,15 @@ def run_b200(args):
         C.memmove(p, f.ctypes.data, fb)
         hpool.append(p)
 
-    def new_batch():
-        ss = [enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=-1, search_range=16, device=dev) for _ in range(S)]
-        return ss, enc.Batch(dev, ss)
+    G = max(1, min(args.groups, S))          # independent batches (own stream each) driven by G host threads
+    group_sizes = [S // G + (1 if i < S % G else 0) for i in range(G)]
+
+    def new_groups():
+        groups, sid = [], 0
+        for n in group_sizes:
+            ss = [enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=-1, search_range=16, device=dev) for _ in range(n)]
+            groups.append((ss, enc.Batch(dev, ss), list(range(sid, sid + n)))); sid += n
+        return groups
 
     def barrier():
         torch.cuda.synchronize()
@@ -112,14 +118,31 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batch, ptr_pool, device_input, steps, warmup, step0=0):
-        for k in range(warmup):
-            batch.encode_ptrs([ptr_pool[pool_index(step0 + k, i)] for i in range(S)], device_input)
+    def run_group(grp, ptr_pool, device_input, first, count, acc):
+        ss, batch, ids = grp
+        dev_ms = launches = out_bytes = 0
+        for k in range(first, first + count):
+            sizes = batch.encode_ptrs([ptr_pool[pool_index(k, i)] for i in ids], device_input)
+            dev_ms += batch.kernel_ms(); launches += batch.launches(); out_bytes += sum(sizes[j] for j in range(len(ids)))
+        acc.append((dev_ms, launches, out_bytes))
+
+    def run_all(groups, ptr_pool, device_input, first, count):
+        acc = []
+        if len(groups) == 1:
+            run_group(groups[0], ptr_pool, device_input, first, count, acc)
+        else:
+            ths = [threading.Thread(target=run_group, args=(g, ptr_pool, device_input, first, count, acc)) for g in groups]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        return max(a[0] for a in acc), sum(a[1] for a in acc), sum(a[2] for a in acc)
+
+    def timed(groups, ptr_pool, device_input, steps, warmup, step0=0):
+        run_all(groups, ptr_pool, device_input, step0, warmup)
         barrier()
-        t0 = time.perf_counter(); dev_ms = 0.0; launches = 0; out_bytes = 0
-        for k in range(steps):
-            sizes = batch.encode_ptrs([ptr_pool[pool_index(step0 + warmup + k, i)] for i in range(S)], device_input)
-            dev_ms += batch.kernel_ms(); launches += batch.launches(); out_bytes += sum(sizes[i] for i in range(S))
+        t0 = time.perf_counter()
+        dev_ms, launches, out_bytes = run_all(groups, ptr_pool, device_input, step0 + warmup, steps)
         barrier()
         el = time.perf_counter() - t0
         if use_dist:
@@ -129,17 +152,21 @@ def run_b200(args):
         return el, dev_ms, launches, out_bytes
 
     sampler = ClockSampler(dev); sampler.start()
-    sess, batch = new_batch()
-    el, dev_ms, launches, out_bytes = timed(batch, dpool, 1, args.steps, args.warmup)
+    groups = new_groups()
+    sess = [x for g in groups for x in g[0]]
+    batch = groups[0][1]
+    el, dev_ms, launches, out_bytes = timed(groups, dpool, 1, args.steps, args.warmup)
     clocks = sampler.summary()
     value = world * S * args.steps / el
     # end to end: host pinned frames in, host-visible bitstreams out
-    el_e, dev_ms_e, _, out_bytes_e = timed(batch, hpool, 0, args.steps, 1, step0=args.warmup + args.steps)
+    el_e, dev_ms_e, _, out_bytes_e = timed(groups, hpool, 0, args.steps, 1, step0=args.warmup + args.steps)
     e2e = world * S * args.steps / el_e
     # per-kernel shares of one step (CUDA events around each launch)
     batch.set_profiling(True)
-    batch.encode_ptrs([dpool[pool_index(5, i)] for i in range(S)], 1)
+    pstep = 2 * args.warmup + 2 * args.steps + 1
+    batch.encode_ptrs([dpool[pool_index(pstep, i)] for i in groups[0][2]], 1)
     kt = batch.kernel_times()
+    Sp = len(groups[0][2])               # sessions in the profiled batch
     batch.set_profiling(False)
     tot = sum(ms for _, ms in kt) or 1.0
     top = max(kt, key=lambda x: x[1])
@@ -154,7 +181,7 @@ def run_b200(args):
         npx = W * 1088
         # algorithmic bytes per P frame: src 1.5 + ref 1.5 + recon 1.5 B/px for ME+coding, +3.0 for the in-place deblock pass
         alg_bytes = {"k_me_fine": 4.5 * npx, "k_me_coarse": 2 * 0.3125 * npx, "k_deblock_wave": 3.0 * npx, "k_intra_wave": 3.0 * npx,
-                     "k_cavlc_mb": 8160 * 864.0, "k_ingest_planar": 3.0 * npx, "k_ingest_rgba": 5.5 * npx}.get(top[0], 4.5 * npx) * S
+                     "k_cavlc_mb": 8160 * 864.0, "k_ingest_planar": 3.0 * npx, "k_ingest_rgba": 5.5 * npx}.get(top[0], 4.5 * npx) * Sp
         ach = alg_bytes / (top[1] * 1e-3) / 1e9
         gi, clk = C.c_double(), C.c_int()
         L.b200k_vabsdiff4_peak(dev, C.byref(gi), C.byref(clk))
@@ -162,7 +189,7 @@ def run_b200(args):
         # implemented search, pixel absolute differences per MB: L2 81*64, L1 25*64, L0 26*256; SATD stage counted as 17*256
         absdiff_mb = 81 * 64 + 25 * 64 + 26 * 256 + 17 * 256
         me_ms = me_fine + me_coarse
-        int_ach = (absdiff_mb / 4.0) * 8160 * S / 32.0 / (me_ms * 1e-3) / 1e9 if me_ms > 0 else 0.0   # warp-instructions -> G lane... see DESIGN 5
+        int_ach = (absdiff_mb / 4.0) * 8160 * Sp / 32.0 / (me_ms * 1e-3) / 1e9 if me_ms > 0 else 0.0   # warp-instructions -> G lane... see DESIGN 5
         cpu = cpu_baseline_sample(threads=1, frames=args.cpu_frames) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -170,7 +197,7 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "realtime_30fps_sessions": round(value / FPS, 1),
             "config": {"workload": f"{S} concurrent 1920x1080 sessions per GPU, Baseline CAVLC IPPP, CBR 4 Mbps @30fps each, gop {GOP}, "
-                                   f"search +-16, 1 slice, content A (moving texture); step = one frame of every session",
+                                   f"search +-16, 1 slice, content A (moving texture); step = one frame of every session; {G} batch(es) of {group_sizes[0]} on own streams",
                        "sessions_per_gpu": S, "frames_per_step": S * world, "l2_policy": f"inputs larger than L2: per-step working set ~{S * 20} MB",
                        "parallelism": f"sessions sharded over {world} GPU(s), no collective"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": int(out_bytes_e / args.steps),
@@ -249,7 +276,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sessions", type=int, default=32)
+    ap.add_argument("--sessions", type=int, default=96)
+    ap.add_argument("--groups", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

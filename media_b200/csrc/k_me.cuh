@@ -34,6 +34,37 @@ __device__ __forceinline__ uint32_t warp_min(uint32_t v)
 }
 __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
+// fast window staging: aligned 32-bit loads + funnel shift when the window lies inside the plane, byte-wise clamped otherwise
+template <int WW, int WH>
+__device__ __forceinline__ void stage_window(uint32_t *dstw, const uint8_t *__restrict__ plane, int pw, int ph, int x0, int y0, int lane)
+{
+    constexpr int WPR = WW / 4;
+    if (x0 >= 0 && y0 >= 0 && x0 + WW <= pw && y0 + WH <= ph) {
+        const int sh = (x0 & 3) * 8, pww = pw >> 2;
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(plane + (size_t)y0 * pw + (x0 & ~3));
+        for (int i = lane; i < WPR * WH; i += 32) {
+            const int r = i / WPR, j = i - r * WPR;
+            const uint32_t *p = base + r * pww + j;
+            const uint32_t lo = __ldg(p), hi = sh ? __ldg(p + 1) : 0u;
+            dstw[i] = __funnelshift_r(lo, hi, sh);
+        }
+    } else stage_clamped(reinterpret_cast<uint8_t *>(dstw), WW, plane, pw, ph, x0, y0, WW, WH, lane);
+}
+__device__ __forceinline__ void stage_window_rt(uint32_t *dstw, int W, const uint8_t *__restrict__ plane, int pw, int ph, int x0, int y0, int lane)
+{
+    const int wpr = W >> 2;
+    if (x0 >= 0 && y0 >= 0 && x0 + W <= pw && y0 + W <= ph) {
+        const int sh = (x0 & 3) * 8, pww = pw >> 2;
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(plane + (size_t)y0 * pw + (x0 & ~3));
+        for (int r = 0; r < W; r++)
+            for (int j = lane; j < wpr; j += 32) {
+                const uint32_t *p = base + r * pww + j;
+                const uint32_t lo = __ldg(p), hi = sh ? __ldg(p + 1) : 0u;
+                dstw[r * wpr + j] = __funnelshift_r(lo, hi, sh);
+            }
+    } else stage_clamped(reinterpret_cast<uint8_t *>(dstw), W, plane, pw, ph, x0, y0, W, W, lane);
+}
+
 // ---- coarse levels: 1/4 resolution exhaustive search, 1/2 resolution refinement ----
 struct CoarseSmem { uint32_t win[(40 * 40 + 8) / 4]; uint32_t src[16]; uint32_t win1[(12 * 12 + 8) / 4]; };
 
@@ -49,11 +80,11 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_coarse(const Sess *ss, Geo
     const int mx = mb % g.mbw, my = mb / g.mbw;
     const int R4 = g.search_range / 4, span = 2 * R4 + 1, W = 8 + 2 * R4;
     const int w2 = g.wc / 4, h2 = g.hc / 4, w1 = g.wc / 2, h1 = g.hc / 2;
-    uint8_t *win = reinterpret_cast<uint8_t *>(sm.win), *srcb = reinterpret_cast<uint8_t *>(sm.src), *win1 = reinterpret_cast<uint8_t *>(sm.win1);
+    uint8_t *win = reinterpret_cast<uint8_t *>(sm.win), *win1 = reinterpret_cast<uint8_t *>(sm.win1);
 
     // level 2: 8x8 block centred on the MB (origin 4mx-2, 4my-2), all (2R4+1)^2 displacements
-    stage_clamped(srcb, 8, s.srcL2, w2, h2, 4 * mx - 2, 4 * my - 2, 8, 8, lane);
-    stage_clamped(win, W, s.refL2, w2, h2, 4 * mx - 2 - R4, 4 * my - 2 - R4, W, W, lane);
+    stage_window<8, 8>(sm.src, s.srcL2, w2, h2, 4 * mx - 2, 4 * my - 2, lane);
+    stage_window_rt(sm.win, W, s.refL2, w2, h2, 4 * mx - 2 - R4, 4 * my - 2 - R4, lane);
     __syncwarp();
     uint32_t sw[16];
 #pragma unroll
@@ -76,8 +107,8 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_coarse(const Sess *ss, Geo
     // level 1: 8x8 block at (8mx, 8my), +-2 around 2*mv2
     const int cx = 2 * v2x, cy = 2 * v2y;
     __syncwarp();
-    stage_clamped(srcb, 8, s.srcL1, w1, h1, 8 * mx, 8 * my, 8, 8, lane);
-    stage_clamped(win1, 12, s.refL1, w1, h1, 8 * mx + cx - 2, 8 * my + cy - 2, 12, 12, lane);
+    stage_window<8, 8>(sm.src, s.srcL1, w1, h1, 8 * mx, 8 * my, lane);
+    stage_window<12, 12>(sm.win1, s.refL1, w1, h1, 8 * mx + cx - 2, 8 * my + cy - 2, lane);
     __syncwarp();
     best = 0xffffffffu;
     if (lane < 25) {
@@ -100,12 +131,13 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_coarse(const Sess *ss, Geo
 }
 
 // ---- fine level: full-pel refinement, half/quarter-pel SATD refinement, intra estimate, inter coding ----
+#define PL_STRIDE 24                     /* bytes per row of a sample plane: sample (x,y) at (y+1)*24 + x + 4, x in [-1,16] */
 struct FineSmem {
     uint32_t win[(24 * 24 + 8) / 4];     // full-pel window: 20x20 (stride 20) for the +-2 search, then 24x24 around the winner
     uint32_t src[64];                    // source MB, 16x16
-    uint8_t plane[4][18 * 18];           // G, b, h, j samples at [-1,16]^2 relative to the best full-pel block (8.4.2.2.1)
+    uint32_t plane[4][18 * PL_STRIDE / 4 + 2]; // G, b, h, j samples at [-1,16]^2 relative to the best full-pel block (8.4.2.2.1)
     int16_t braw[24 * 18];               // unrounded horizontal half-pel sums, rows [-3,20]
-    uint8_t nb_top[16], nb_left[16];     // SOURCE neighbours for the intra estimate
+    uint32_t nb_top[4], nb_left[4];      // SOURCE neighbours for the intra estimate
 };
 
 // The 16 quarter-pel positions as the average of two samples out of {G,b,h,j} (8.4.2.2.1, Table 8-12):
@@ -117,31 +149,46 @@ static __device__ __constant__ uint8_t c_qpel_tab[16][6] = {
     { 0, 0, 1, 2, 0, 0 }, { 2, 0, 0, 1, 0, 1 }, { 3, 0, 0, 1, 0, 1 }, { 2, 1, 0, 1, 0, 1 },
 };
 
-// prediction of one 4x4 block (bx,by in pixels inside the MB) at quarter-pel offset (ox,oy) in [-3,3] from the best full-pel block
-__device__ __forceinline__ void pred_block_qpel(const FineSmem &sm, int bx, int by, int ox, int oy, int p[16])
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)   // sum of u8(a_i) * s8(b_i) + c: one IDP.4A
+{
+    int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xfefefefeu) >> 1); }  // per-byte (a+b+1)>>1
+__device__ __forceinline__ uint32_t plane_row(const uint32_t *pl, int o)   // 4 samples starting at byte offset o of a plane
+{
+    const uint32_t *w = pl + (o >> 2);
+    return __funnelshift_r(w[0], w[1], (o & 3) * 8);
+}
+// four rows (packed bytes) of the prediction of one 4x4 block at quarter-pel offset (ox,oy) in [-3,3] from the best full-pel block
+__device__ __forceinline__ void pred_rows_qpel(const FineSmem &sm, int bx, int by, int ox, int oy, uint32_t P[4])
 {
     const uint8_t *t = c_qpel_tab[(oy & 3) * 4 + (ox & 3)];
-    const int xi = bx + (ox >> 2) + 1, yi = by + (oy >> 2) + 1;
-    const uint8_t *pa = &sm.plane[t[0]][(yi + t[2]) * 18 + xi + t[1]], *pb = &sm.plane[t[3]][(yi + t[5]) * 18 + xi + t[4]];
+    const int xo = bx + (ox >> 2) + 4, yo = by + (oy >> 2) + 1;
+    const uint32_t *pa = sm.plane[t[0]], *pb = sm.plane[t[3]];
+    const int oa = (yo + t[2]) * PL_STRIDE + xo + t[1], ob = (yo + t[5]) * PL_STRIDE + xo + t[4];
 #pragma unroll
-    for (int y = 0; y < 4; y++)
+    for (int y = 0; y < 4; y++) P[y] = avg4(plane_row(pa, oa + y * PL_STRIDE), plane_row(pb, ob + y * PL_STRIDE));
+}
+// 4x4 Hadamard SATD of (source block - P): Ts holds the horizontal transforms of the source rows, the prediction
+// rows are folded in with dp4a against the negated +-1 basis; |x+y|+|x-y| = 2 max(|x|,|y|) finishes the columns.
+__device__ __forceinline__ int satd_rows(const uint32_t P[4], const int Ts[16])
+{
+    const uint32_t NH[4] = { 0xffffffffu, 0x0101ffffu, 0xff0101ffu, 0x01ff01ffu };
+    int s = 0;
 #pragma unroll
-        for (int x = 0; x < 4; x++) p[y * 4 + x] = (pa[y * 18 + x] + pb[y * 18 + x] + 1) >> 1;
+    for (int k = 0; k < 4; k++) {
+        const int t0 = dp4a_us(P[0], NH[k], Ts[k]), t1 = dp4a_us(P[1], NH[k], Ts[4 + k]);
+        const int t2 = dp4a_us(P[2], NH[k], Ts[8 + k]), t3 = dp4a_us(P[3], NH[k], Ts[12 + k]);
+        const int a0 = t0 + t1, a1 = t0 - t1, a2 = t2 + t3, a3 = t2 - t3;
+        s += max(abs(a0), abs(a2)) + max(abs(a1), abs(a3));
+    }
+    return s;
 }
 __device__ __forceinline__ int half_reduce16(int v)   // sum over the 16 lanes of a half-warp
 {
 #pragma unroll
     for (int o = 8; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-__device__ __forceinline__ void load_src_block(const FineSmem &sm, int bx, int by, int sp[16])
-{
-#pragma unroll
-    for (int y = 0; y < 4; y++) {
-        uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
-#pragma unroll
-        for (int x = 0; x < 4; x++) sp[y * 4 + x] = (w >> (8 * x)) & 255;
-    }
 }
 
 __global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom g)
@@ -164,7 +211,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom 
         int wi = lane + 32 * i;
         sm.src[wi] = *reinterpret_cast<const uint32_t *>(s.src[0] + (size_t)(y0 + (wi >> 2)) * wc + x0 + (wi & 3) * 4);
     }
-    stage_clamped(win, 20, s.ref[0], wc, hc, x0 + cx - 2, y0 + cy - 2, 20, 20, lane);
+    stage_window<20, 20>(sm.win, s.ref[0], wc, hc, x0 + cx - 2, y0 + cy - 2, lane);
     // zero-vector candidate, computed cooperatively straight from HBM (always inside the picture)
     uint32_t zsad;
     {
@@ -194,7 +241,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom 
 
     // half-pel sample planes around the winner
     __syncwarp();
-    stage_clamped(win, 24, s.ref[0], wc, hc, x0 + fx - 3, y0 + fy - 3, 24, 24, lane);
+    stage_window<24, 24>(sm.win, s.ref[0], wc, hc, x0 + fx - 3, y0 + fy - 3, lane);
     __syncwarp();
     for (int i = lane; i < 24 * 18; i += 32) {        // braw(x,y), x in [-1,16], y in [-3,20]
         const int r = i / 18, c = i - r * 18;           // G column of sample x is c + 2 (x = c - 1, G index x + 3)
@@ -202,72 +249,85 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom 
         sm.braw[i] = (int16_t)tap6(p[0], p[1], p[2], p[3], p[4], p[5]);
     }
     __syncwarp();
-    for (int i = lane; i < 18 * 18; i += 32) {
-        const int r = i / 18, c = i - r * 18;           // sample (x,y) = (c-1, r-1); G index (c+2, r+2)
-        const uint8_t *p = win + (r + 2) * 24 + c + 2;
-        sm.plane[0][i] = p[0];
-        sm.plane[1][i] = (uint8_t)clip255((sm.braw[(r + 2) * 18 + c] + 16) >> 5);
-        sm.plane[2][i] = (uint8_t)clip255((tap6(p[-48], p[-24], p[0], p[24], p[48], p[72]) + 16) >> 5);
-        const int16_t *q = sm.braw + r * 18 + c;        // braw rows y-2..y+3 = indices r..r+5
-        sm.plane[3][i] = (uint8_t)clip255((tap6(q[0], q[18], q[36], q[54], q[72], q[90]) + 512) >> 10);
+    {
+        uint8_t *pl0 = reinterpret_cast<uint8_t *>(sm.plane[0]), *pl1 = reinterpret_cast<uint8_t *>(sm.plane[1]);
+        uint8_t *pl2 = reinterpret_cast<uint8_t *>(sm.plane[2]), *pl3 = reinterpret_cast<uint8_t *>(sm.plane[3]);
+        for (int i = lane; i < 18 * 18; i += 32) {
+            const int r = i / 18, c = i - r * 18;       // sample (x,y) = (c-1, r-1); G index (c+2, r+2)
+            const uint8_t *p = win + (r + 2) * 24 + c + 2;
+            const int o = r * PL_STRIDE + c + 3;
+            pl0[o] = p[0];
+            pl1[o] = (uint8_t)clip255((sm.braw[(r + 2) * 18 + c] + 16) >> 5);
+            pl2[o] = (uint8_t)clip255((tap6(p[-48], p[-24], p[0], p[24], p[48], p[72]) + 16) >> 5);
+            const int16_t *q = sm.braw + r * 18 + c;    // braw rows y-2..y+3 = indices r..r+5
+            pl3[o] = (uint8_t)clip255((tap6(q[0], q[18], q[36], q[54], q[72], q[90]) + 512) >> 10);
+        }
     }
     __syncwarp();
 
     // sub-pel refinement by SATD: 16 lanes (one per 4x4 block) evaluate one candidate, two candidates per pass
     const int hw = lane >> 4, b = lane & 15, bx = blk_x(b) * 4, by = blk_y(b) * 4;
-    int sp[16]; load_src_block(sm, bx, by, sp);
+    int Ts[16];                                         // horizontal Hadamard of the four source rows of this lane's block
+    {
+        const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
+#pragma unroll
+            for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(w, H[k], 0);
+        }
+    }
     int qx = 0, qy = 0;                                 // offset from 4*(fx,fy), quarter-pel units
     uint32_t centre_key = 0;
+    // candidate i: 0 centre, then (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1); packed 2-bit (offset + 1) tables
+    const uint32_t OXP = 0x24891u, OYP = 0x2A501u;
 #pragma unroll 1
     for (int step = 2; step >= 1; step--) {
         uint32_t bk = step == 1 ? (centre_key & ~15u) : 0xffffffffu;
+        const int npass = step == 2 ? 5 : 4;
 #pragma unroll 1
-        for (int pass = 0; pass < 5; pass++) {
+        for (int pass = 0; pass < npass; pass++) {
             const int i = 2 * pass + hw + (step == 1 ? 1 : 0);      // step 2: 0..8 (+ one idle slot); step 1: 1..8 (centre known)
-            uint32_t key = 0xffffffffu;
-            // candidate offsets: i=0 centre, then (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1)
             const int ci = i <= 8 ? i : 0;
-            const int dxs = ci == 0 ? 0 : ((ci - 1 + (ci > 4)) % 3) - 1, dys = ci == 0 ? 0 : ((ci - 1 + (ci > 4)) / 3) - 1;
-            const int ox = qx + step * dxs, oy = qy + step * dys;
-            int p[16]; pred_block_qpel(sm, bx, by, ox, oy, p);
-#pragma unroll
-            for (int k = 0; k < 16; k++) p[k] = sp[k] - p[k];
-            int sat = half_reduce16(satd4x4(p));
+            const int ox = qx + step * ((int)((OXP >> (2 * ci)) & 3) - 1), oy = qy + step * ((int)((OYP >> (2 * ci)) & 3) - 1);
+            uint32_t P[4]; pred_rows_qpel(sm, bx, by, ox, oy, P);
+            const int sat = half_reduce16(satd_rows(P, Ts));
+            uint32_t key = 0xffffffffu;
             if (i <= 8) key = ((uint32_t)(sat + lambda * (se_len(4 * fx + ox) + se_len(4 * fy + oy))) << 4) | (uint32_t)i;
             key = min(key, __shfl_xor_sync(0xffffffffu, key, 16));
             bk = min(bk, key);
-            if (step == 1 && pass == 3) break;
         }
         const int ci = bk & 15;
-        const int dxs = ci == 0 ? 0 : ((ci - 1 + (ci > 4)) % 3) - 1, dys = ci == 0 ? 0 : ((ci - 1 + (ci > 4)) / 3) - 1;
-        qx += step * dxs; qy += step * dys; centre_key = bk;
+        qx += step * ((int)((OXP >> (2 * ci)) & 3) - 1); qy += step * ((int)((OYP >> (2 * ci)) & 3) - 1); centre_key = bk;
     }
     const int mvx = 4 * fx + qx, mvy = 4 * fy + qy, inter_cost = (int)(centre_key >> 4);
 
     // intra estimate from source neighbours: V, H, DC 16x16 by SATD
     const bool top = !row_is_slice_top(g, my), left = mx > 0;
-    if (lane < 16) sm.nb_top[lane] = top ? s.src[0][(size_t)(y0 - 1) * wc + x0 + lane] : 0;
-    else sm.nb_left[lane - 16] = left ? s.src[0][(size_t)(y0 + lane - 16) * wc + x0 - 1] : 0;
+    {
+        uint8_t *nt = reinterpret_cast<uint8_t *>(sm.nb_top), *nl = reinterpret_cast<uint8_t *>(sm.nb_left);
+        if (lane < 16) nt[lane] = top ? s.src[0][(size_t)(y0 - 1) * wc + x0 + lane] : 0;
+        else nl[lane - 16] = left ? s.src[0][(size_t)(y0 + lane - 16) * wc + x0 - 1] : 0;
+    }
     __syncwarp();
     int ie = 1 << 30;
     {
-        int d[16];
+        const uint8_t *nl = reinterpret_cast<const uint8_t *>(sm.nb_left);
+        uint32_t P[4];
 #pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++) d[y * 4 + x] = sp[y * 4 + x] - (hw == 0 ? sm.nb_top[bx + x] : sm.nb_left[by + y]);
-        int sat = half_reduce16(satd4x4(d));
-        int other = __shfl_xor_sync(0xffffffffu, sat, 16);
-        int sv = hw == 0 ? sat : other, sh = hw == 0 ? other : sat;
+        for (int y = 0; y < 4; y++) P[y] = hw == 0 ? sm.nb_top[bx >> 2] : 0x01010101u * nl[by + y];
+        const int sat = half_reduce16(satd_rows(P, Ts));
+        const int other = __shfl_xor_sync(0xffffffffu, sat, 16);
+        const int sv = hw == 0 ? sat : other, sh = hw == 0 ? other : sat;
         if (top) ie = min(ie, sv);
         if (left) ie = min(ie, sh);
         int sum = 0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) sum += (top ? sm.nb_top[k] : 0) + (left ? sm.nb_left[k] : 0);
+        for (int k = 0; k < 4; k++) sum = dp4a_us(sm.nb_top[k], 0x01010101u, dp4a_us(sm.nb_left[k], 0x01010101u, sum));
         const int dc = top && left ? (sum + 16) >> 5 : (top || left) ? (sum + 8) >> 4 : 128;
 #pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = sp[k] - dc;
-        ie = min(ie, half_reduce16(satd4x4(d)));
+        for (int y = 0; y < 4; y++) P[y] = 0x01010101u * (uint32_t)dc;
+        ie = min(ie, half_reduce16(satd_rows(P, Ts)));
     }
     const bool intra = ie + lambda * 16 < inter_cost;
 
@@ -285,9 +345,16 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom 
     const QParam q = make_qparam(qp);
     int nnz = 0; bool dc_nz = false;
     if (lane < 16) {
-        int p[16], c[16]; pred_block_qpel(sm, bx, by, qx, qy, p);
+        int p[16], c[16];
+        {
+            uint32_t P[4]; pred_rows_qpel(sm, bx, by, qx, qy, P);
 #pragma unroll
-        for (int k = 0; k < 16; k++) c[k] = sp[k] - p[k];
+            for (int y = 0; y < 4; y++) {
+                const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
+#pragma unroll
+                for (int x = 0; x < 4; x++) { p[y * 4 + x] = (P[y] >> (8 * x)) & 255; c[y * 4 + x] = (int)((w >> (8 * x)) & 255) - p[y * 4 + x]; }
+            }
+        }
         fdct4x4(c);
         __align__(16) int16_t lz[16];
         nnz = quant_dequant4x4(c, lz, q, q.f_inter, false);
