@@ -150,7 +150,7 @@ struct b200enc_session {
     uint8_t *input = nullptr, *src[3], *bufA[3], *bufB[3], *rec_pre[3];
     uint8_t *srcL1, *srcL2, *refL1, *refL2;
     MbInfo *mbi; MbCoef *coef; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
-    uint32_t *mb_bits, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
+    uint32_t *mb_bits, *mb_off, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
     uint32_t rbsp_words_per_slice = 0;
     // pinned, device-mapped output: [0..cap) bitstream, then one uint32 size
     uint8_t *h_out = nullptr, *d_out = nullptr; uint32_t out_cap = 0;
@@ -243,7 +243,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         for (int c = 0; c < 3; c++) { d.src[c] = s->src[c]; d.rec[c] = cur[c]; d.ref[c] = ref[c]; }
         d.srcL1 = s->srcL1; d.srcL2 = s->srcL2; d.refL1 = s->refL1; d.refL2 = s->refL2;
         d.mbi = s->mbi; d.coef = s->coef; d.me2 = s->me2; d.me1 = s->me1; d.me0 = s->me0; d.inter_cost = s->inter_cost;
-        d.skip_run = s->skip_run; d.mb_bits = s->mb_bits; d.mb_slot = s->mb_slot; d.rbsp = s->rbsp; d.slice_bits = s->slice_bits;
+        d.skip_run = s->skip_run; d.mb_bits = s->mb_bits; d.mb_off = s->mb_off; d.mb_slot = s->mb_slot; d.rbsp = s->rbsp; d.slice_bits = s->slice_bits;
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
         d.qp = qp; d.is_idr = idr; d.frame_num = s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
@@ -277,7 +277,8 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     pf.begin("k_pskip_scan"); k_pskip_scan<<<dim3(g.num_slices, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_deblock_wave"); k_deblock_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
     pf.begin("k_cavlc_mb"); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end(); launches++;
-    pf.begin("k_slice_pack"); k_slice_pack<<<dim3(g.num_slices, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_slice_scan"); k_slice_scan<<<dim3(g.num_slices, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_slice_copy"); k_slice_copy<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_nal_pack"); k_nal_pack<<<n, 1024, 0, st>>>(b->d_sess, g); pf.end(); launches++;
     cudaEventRecord(b->ev1, st);
     WaveCtl ctl;
@@ -374,7 +375,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         add(s->srcL1, ny / 4); add(s->refL1, ny / 4); add(s->srcL2, ny / 16); add(s->refL2, ny / 16);
         add(s->mbi, nmb * sizeof(MbInfo)); add(s->coef, nmb * sizeof(MbCoef));
         add(s->me2, nmb * 4); add(s->me1, nmb * 4); add(s->me0, nmb * 4); add(s->inter_cost, nmb * 4);
-        add(s->skip_run, (nmb + B200_MAX_SLICES) * 4); add(s->mb_bits, nmb * 4);
+        add(s->skip_run, (nmb + B200_MAX_SLICES) * 4); add(s->mb_bits, nmb * 4); add(s->mb_off, nmb * 4);
         add(s->mb_slot, nmb * B200_MB_SLOT_WORDS * 4);
         add(s->rbsp, (size_t)s->rbsp_words_per_slice * g.num_slices * 4);
         add(s->slice_bits, B200_MAX_SLICES * 4); add(s->hdr, 256); add(s->row_prog, (size_t)g.mbh * 2 * 4);

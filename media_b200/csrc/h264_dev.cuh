@@ -52,6 +52,7 @@ struct Sess {
     int32_t *inter_cost;
     int32_t *skip_run;            // per MB: number of P_Skip MBs immediately before it in its slice
     uint32_t *mb_bits;            // per MB: bit length of its macroblock_layer() (+ preceding mb_skip_run)
+    uint32_t *mb_off;             // per MB: bit offset of its payload inside the slice RBSP
     uint32_t *mb_slot;            // per MB: B200_MB_SLOT_WORDS words of bits, MSB first
     uint32_t *rbsp;               // per slice region: concatenated slice_data bits
     uint32_t *slice_bits;         // per slice: total RBSP bits (header + data + trailing)

@@ -8,7 +8,8 @@
 //   k_cavlc_mb   : macroblock_layer() of every coded MB into its own scratch slot; the 28 syntax groups of an MB
 //                  (header, luma DC, 16 luma, 2 chroma DC, 8 chroma AC) are coded by 28 lanes in parallel after a
 //                  warp prefix sum of their code lengths                                          [warp per MB]
-//   k_slice_pack : slice header + bit-exact concatenation of the MB slots by a prefix sum of MB lengths [CTA per slice]
+//   k_slice_scan : slice header + prefix sum of MB lengths -> bit offset of every MB            [CTA per slice]
+//   k_slice_copy : bit-exact concatenation: every MB shifts its slot into place              [warp per MB]
 //   k_nal_pack   : start codes, NAL headers, emulation prevention (7.4.1), final access unit      [CTA per session]
 #pragma once
 #include "h264_dev.cuh"
@@ -257,20 +258,16 @@ __device__ __forceinline__ int block_excl_scan(int v, int *total, int *wsum)   /
     return base + incl - v;
 }
 
-// grid: (num_slices, 1, sessions), 256 threads
-__global__ void __launch_bounds__(256) k_slice_pack(const Sess *ss, Geom g)
+// grid: (num_slices, 1, sessions), 256 threads: bit offset of every MB inside its slice's RBSP (prefix sum of the MB
+// lengths), slice header, zeroed RBSP words, trailing mb_skip_run and rbsp_trailing_bits.
+__global__ void __launch_bounds__(256) k_slice_scan(const Sess *ss, Geom g)
 {
     const Sess &s = ss[blockIdx.z];
     const int sl = blockIdx.x, m0 = g.slice_row0[sl] * g.mbw, m1 = g.slice_row0[sl + 1] * g.mbw, nmb = g.mbw * g.mbh;
     uint32_t *rb = s.rbsp + (size_t)sl * s.rbsp_words_per_slice;
     __shared__ int wsum[8];
     __shared__ uint32_t hdr[4];
-    __shared__ int hdr_bits_s, carry_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // total payload bits of the slice
-    int sum = 0;
-    for (int mb = m0 + threadIdx.x; mb < m1; mb += 256) sum += (int)s.mb_bits[mb];
-    int total; block_excl_scan(sum, &total, wsum);
+    __shared__ int hdr_bits_s;
     if (threadIdx.x == 0) {      // slice_header(), 7.3.3
         hdr[0] = hdr[1] = hdr[2] = hdr[3] = 0;
         BitSink<true> bs; bs.w = hdr; bs.pos = 0;
@@ -283,10 +280,19 @@ __global__ void __launch_bounds__(256) k_slice_pack(const Sess *ss, Geom g)
         if (s.is_idr) { bs.put(1, 0); bs.put(1, 0); } else bs.put(1, 0);
         bs.se(s.qp - 26);
         bs.ue(0); bs.se(0); bs.se(0);
-        hdr_bits_s = bs.pos; carry_s = 0;
+        hdr_bits_s = bs.pos;
     }
     __syncthreads();
     const int hdr_bits = hdr_bits_s;
+    int carry = 0;
+    for (int base = m0; base < m1; base += 256) {
+        const int mb = base + threadIdx.x;
+        const int len = mb < m1 ? (int)s.mb_bits[mb] : 0;
+        int chunk_total; const int off = carry + block_excl_scan(len, &chunk_total, wsum);
+        if (mb < m1) s.mb_off[mb] = (uint32_t)(hdr_bits + off);
+        carry += chunk_total;
+    }
+    const int total = carry;
     const int trailing_run = s.is_idr ? 0 : s.skip_run[nmb + sl];
     const int tail_bits = trailing_run ? ue_len((uint32_t)trailing_run) : 0;
     const int data_end = hdr_bits + total + tail_bits;               // position of the rbsp_stop_one_bit
@@ -294,33 +300,33 @@ __global__ void __launch_bounds__(256) k_slice_pack(const Sess *ss, Geom g)
     const int nwords = (all_bits + 31) >> 5;
     for (int i = threadIdx.x; i <= nwords; i += 256) rb[i] = i < 4 ? hdr[i] : 0u;
     __syncthreads();
-    // MB payloads: chunk-wise exclusive scan of lengths, then each warp shifts its MBs into place
-    for (int base = m0; base < m1; base += 256) {
-        const int mb = base + threadIdx.x;
-        const int len = mb < m1 ? (int)s.mb_bits[mb] : 0;
-        int chunk_total; const int off = carry_s + block_excl_scan(len, &chunk_total, wsum);
-        // hand (mb, offset, len) of this chunk's MBs to the warps through shuffles: warp w copies MBs 32w..32w+31
-        for (int j = 0; j < 32; j++) {
-            const int l = __shfl_sync(0xffffffffu, len, j);
-            if (!l) continue;
-            const int D = hdr_bits + __shfl_sync(0xffffffffu, off, j);
-            const uint32_t *src = s.mb_slot + (size_t)(base + warp * 32 + j) * B200_MB_SLOT_WORDS;
-            const int nw = (l + 31) >> 5, dw = D >> 5, sh = D & 31;
-            for (int i = lane; i <= nw; i += 32) {          // destination word dw + i
-                const uint32_t hi = i > 0 ? src[i - 1] : 0u, lo = i < nw ? src[i] : 0u;
-                const uint32_t v = sh ? (hi << (32 - sh)) | (lo >> sh) : lo;
-                if (v) atomicOr(rb + dw + i, v);
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += chunk_total;
-        __syncthreads();
-    }
     if (threadIdx.x == 0) {
         BitSink<true> bs; bs.w = rb; bs.pos = hdr_bits + total;
         if (trailing_run) bs.ue((uint32_t)trailing_run);
         bs.put(1, 1);
         s.slice_bits[sl] = (uint32_t)all_bits;
+    }
+}
+
+// grid: (ceil(n_mb / CAVLC_WARPS), 1, sessions): every coded MB shifts its slot into place inside the slice RBSP
+__global__ void __launch_bounds__(CAVLC_WARPS * 32) k_slice_copy(const Sess *ss, Geom g)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * CAVLC_WARPS + warp;
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    const int l = (int)s.mb_bits[mb];
+    if (!l) return;
+    const int my = mb / g.mbw;
+    int sl = 0;
+    for (int k = 1; k < g.num_slices; k++) sl += (my >= g.slice_row0[k]);
+    uint32_t *rb = s.rbsp + (size_t)sl * s.rbsp_words_per_slice;
+    const uint32_t *src = s.mb_slot + (size_t)mb * B200_MB_SLOT_WORDS;
+    const int D = (int)s.mb_off[mb], nw = (l + 31) >> 5, dw = D >> 5, sh = D & 31;
+    for (int i = lane; i <= nw; i += 32) {          // destination word dw + i
+        const uint32_t hi = i > 0 ? src[i - 1] : 0u, lo = i < nw ? src[i] : 0u;
+        const uint32_t v = sh ? (hi << (32 - sh)) | (lo >> sh) : lo;
+        if (v) atomicOr(rb + dw + i, v);
     }
 }
 

@@ -68,16 +68,45 @@ __device__ __forceinline__ int bs_of(const uint32_t *mp, int bxp, int byp, const
     return 0;
 }
 
-__device__ void deblock_mb(const Sess &s, const Geom &g, DbkSmem &sm, int mx, int my, int lane)
+// One MB of the row. Software pipeline of the row loop: the MB's own samples and its MbInfo were prefetched into
+// registers one iteration earlier (nobody else touches them before this MB runs), the 4 left columns are carried over
+// from the previous tile in shared memory, and only the rows above are loaded after the wavefront wait.
+struct DbkPrefetch { uint32_t y0, y1, c, info; };
+
+__device__ __forceinline__ void dbk_prefetch(const Sess &s, const Geom &g, int mx, int my, int lane, DbkPrefetch &pf)
 {
-    const int wc = g.wc, cw = wc / 2, mb = my * g.mbw + mx, qp = s.qp, qpc = c_chroma_qp[qp];
+    const int wc = g.wc, cw = wc / 2, mb = my * g.mbw + mx;
+    const uint8_t *Y = s.rec[0] + (size_t)my * 16 * wc + mx * 16;
+    // luma: 64 words, lane l takes words l and l + 32 (row = w / 4, col word = w % 4)
+    pf.y0 = __ldcg(reinterpret_cast<const uint32_t *>(Y + (size_t)(lane >> 2) * wc + (lane & 3) * 4));
+    pf.y1 = __ldcg(reinterpret_cast<const uint32_t *>(Y + (size_t)(8 + (lane >> 2)) * wc + (lane & 3) * 4));
+    // chroma: 2 planes x 8 rows x 2 words
+    const uint8_t *C = s.rec[1 + (lane >> 4)] + (size_t)(my * 8 + ((lane >> 1) & 7)) * cw + mx * 8 + (lane & 1) * 4;
+    pf.c = __ldcg(reinterpret_cast<const uint32_t *>(C));
+    // MbInfo: lanes 0-11 current MB, lanes 12-23 the MB above
+    pf.info = 0;
+    if (lane < 12) pf.info = reinterpret_cast<const uint32_t *>(s.mbi + mb)[lane];
+    else if (lane < 24 && my > 0) pf.info = reinterpret_cast<const uint32_t *>(s.mbi + mb - g.mbw)[lane - 12];
+}
+
+// returns true when the MB wrote samples (a fence is needed before publishing)
+__device__ bool deblock_mb(const Sess &s, const Geom &g, DbkSmem &sm, int mx, int my, int lane, const DbkPrefetch &pf,
+                           const int *prog_above, WaveCtl *ctl, bool &ok)
+{
+    const int wc = g.wc, cw = wc / 2, qp = s.qp, qpc = c_chroma_qp[qp];
+    ok = true;
     __syncwarp();
-    for (int i = lane; i < 36; i += 32) {
-        const int which = i / 12, w = i - which * 12;
-        const int src = which == 0 ? mb : which == 1 ? mb - 1 : mb - g.mbw;
-        const bool ok = which == 0 || (which == 1 ? mx > 0 : my > 0);
-        sm.mbi[which][w] = ok ? reinterpret_cast<const uint32_t *>(s.mbi + src)[w] : 0u;
+    // carry the previous tile's right columns / MbInfo over as this MB's left neighbour, then drop in the prefetched data
+    if (mx > 0) {
+        if (lane < 16) sm.y[(lane + 4) * 5] = sm.y[(lane + 4) * 5 + 4];
+        else sm.c[(lane >> 3) & 1][((lane & 7) + 4) * 3] = sm.c[(lane >> 3) & 1][((lane & 7) + 4) * 3 + 2];
+        if (lane < 12) sm.mbi[1][lane] = sm.mbi[0][lane];
     }
+    __syncwarp();
+    sm.y[((lane >> 2) + 4) * 5 + 1 + (lane & 3)] = pf.y0;
+    sm.y[((lane >> 2) + 12) * 5 + 1 + (lane & 3)] = pf.y1;
+    sm.c[lane >> 4][(((lane >> 1) & 7) + 4) * 3 + 1 + (lane & 1)] = pf.c;
+    if (lane < 12) sm.mbi[0][lane] = pf.info; else if (lane < 24) sm.mbi[2][lane - 12] = pf.info;
     __syncwarp();
     // lanes 0-15: bS of vertical edge e, segment k; lanes 16-31: horizontal edge e, segment k
     int bs;
@@ -88,22 +117,18 @@ __device__ void deblock_mb(const Sess &s, const Geom &g, DbkSmem &sm, int mx, in
             else bs = my > 0 ? bs_of(sm.mbi[2], k, 3, sm.mbi[0], k, 0, true) : 0;
         } else bs = vert ? bs_of(sm.mbi[0], e - 1, k, sm.mbi[0], e, k, false) : bs_of(sm.mbi[0], k, e - 1, sm.mbi[0], k, e, false);
     }
-    if (__ballot_sync(0xffffffffu, bs != 0) == 0) return;
+    if (__ballot_sync(0xffffffffu, bs != 0) == 0) return false;
 
     uint8_t *Y = s.rec[0] + (size_t)my * 16 * wc + mx * 16;
     uint8_t *C[2] = { s.rec[1] + (size_t)my * 8 * cw + mx * 8, s.rec[2] + (size_t)my * 8 * cw + mx * 8 };
-    // stage the tile (rows/cols -4.. of luma, -4.. of chroma); samples outside the picture are never used
-    for (int i = lane; i < 100; i += 32) {
-        const int r = i / 5 - 4, c4 = (i % 5) * 4 - 4;
-        uint32_t v = 0;
-        if ((r >= 0 || my > 0) && (c4 >= 0 || mx > 0)) v = __ldcg(reinterpret_cast<const uint32_t *>(Y + (ptrdiff_t)r * wc + c4));
-        sm.y[i] = v;
-    }
-    for (int i = lane; i < 72; i += 32) {
-        const int pl = i / 36, j = i - pl * 36, r = j / 3 - 4, c4 = (j % 3) * 4 - 4;
-        uint32_t v = 0;
-        if ((r >= 0 || my > 0) && (c4 >= 0 || mx > 0)) v = __ldcg(reinterpret_cast<const uint32_t *>(C[pl] + (ptrdiff_t)r * cw + c4));
-        sm.c[pl][j] = v;
+    if (my > 0) {
+        // the rows above are final once the upper-right neighbour is done
+        if (!wave_wait(prog_above, min(mx + 2, g.mbw), ctl, lane)) { ok = false; return false; }
+        if (lane < 16) sm.y[(lane >> 2) * 5 + 1 + (lane & 3)] = __ldcg(reinterpret_cast<const uint32_t *>(Y + (ptrdiff_t)((lane >> 2) - 4) * wc + (lane & 3) * 4));
+        else if (lane < 24) {
+            const int pl = (lane >> 2) & 1, r = 2 + ((lane >> 1) & 1), w = lane & 1;     // chroma rows -2, -1
+            sm.c[pl][r * 3 + 1 + w] = __ldcg(reinterpret_cast<const uint32_t *>(C[pl] + (ptrdiff_t)(r - 4) * cw + w * 4));
+        }
     }
     __syncwarp();
     const int alphaY = c_alpha[qp], betaY = c_beta[qp], alphaC = c_alpha[qpc], betaC = c_beta[qpc];
@@ -142,6 +167,7 @@ __device__ void deblock_mb(const Sess &s, const Geom &g, DbkSmem &sm, int mx, in
         const bool st = r >= 0 ? (c4 >= 0 || mx > 0) : (r >= -2 && c4 >= 0 && my > 0);
         if (st) *reinterpret_cast<uint32_t *>(C[pl] + (ptrdiff_t)r * cw + c4) = sm.c[pl][j];
     }
+    return true;
 }
 
 // grid: ceil(sessions * mbh / WAVE_WARPS) CTAs of WAVE_WARPS warps. Slices do not break the wavefront:
@@ -157,12 +183,24 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss
     const int my = t / nsess;
     const Sess &s = ss[t % nsess];
     int *prog = s.row_prog_dbk;
+    DbkPrefetch cur, nxt;
+    dbk_prefetch(s, g, 0, my, lane, cur);
+    int published = 0;
     for (int mx = 0; mx < g.mbw; mx++) {
-        if (my > 0 && !wave_wait(prog + my - 1, min(mx + 2, g.mbw), ctl, lane)) return;
-        deblock_mb(s, g, sm_all[warp], mx, my, lane);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release(prog + my, mx + 1);
+        if (mx + 1 < g.mbw) dbk_prefetch(s, g, mx + 1, my, lane, nxt);
+        bool ok;
+        const bool wrote = deblock_mb(s, g, sm_all[warp], mx, my, lane, cur, prog + my - 1, ctl, ok);
+        if (!ok) return;
+        if (wrote) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release(prog + my, mx + 1);
+            published = mx + 1;
+        } else if (mx + 1 - published >= 4 || mx + 1 == g.mbw) {   // nothing written: publish lazily, in strides
+            if (lane == 0) st_release(prog + my, mx + 1);
+            published = mx + 1;
+        }
+        cur = nxt;
     }
 }
 

@@ -12,19 +12,28 @@
 namespace b200 {
 
 #define WAVE_WARPS 4
-#define WAVE_SPIN_LIMIT (1 << 22)
+#define WAVE_TIMEOUT_NS 2000000000ull   /* watchdog: a wait longer than 2 s is an internal error, never a hang */
 
 struct WaveCtl { int ticket_intra, ticket_dbk, error, pad; };
+
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // wait until the row above has finished `need` macroblocks; returns false on timeout / global error
 __device__ __forceinline__ bool wave_wait(const int *prog_above, int need, WaveCtl *ctl, int lane)
 {
     int ok = 1;
     if (lane == 0) {
-        int spins = 0;
-        while (ld_acquire(prog_above) < need) {
-            if (++spins > WAVE_SPIN_LIMIT || ld_acquire(&ctl->error)) { atomicExch(&ctl->error, 1); ok = 0; break; }
-            __nanosleep(40);
+        int cur = ld_acquire(prog_above);
+        if (cur < need) {
+            const unsigned long long t0 = global_ns();
+            int spins = 0;
+            do {
+                // a row that is d macroblocks short of what we need takes d MB-steps (a few us each): sleep accordingly, so
+                // that far-behind rows do not burn the issue slots of the SMs they share with other kernels
+                const int d = need - cur;
+                __nanosleep(d > 1 ? min(d * 1500, 30000) : 32);
+                if ((++spins & 15) == 0 && (ld_acquire(&ctl->error) || global_ns() - t0 > WAVE_TIMEOUT_NS)) { atomicExch(&ctl->error, 1); ok = 0; break; }
+            } while ((cur = ld_acquire(prog_above)) < need);
         }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
