@@ -9,7 +9,12 @@
 
 namespace b200 {
 
+#ifndef ME_WARPS
 #define ME_WARPS 8
+#endif
+#ifndef ME_FINE_MIN_CTAS
+#define ME_FINE_MIN_CTAS 4     /* 64 registers: 4 CTAs of 8 warps per SM (measured 8 % faster than 75-94 registers) */
+#endif
 
 // copy a ww x wh window whose top-left is (x0,y0) from a pw x ph plane into shared memory, clamping coordinates
 // (the reference picture is extended by edge replication, 8.4.2.2.1)
@@ -166,8 +171,13 @@ __device__ __forceinline__ void pred_rows_qpel(const FineSmem &sm, int bx, int b
     const int xo = bx + (ox >> 2) + 4, yo = by + (oy >> 2) + 1;
     const uint32_t *pa = sm.plane[t[0]], *pb = sm.plane[t[3]];
     const int oa = (yo + t[2]) * PL_STRIDE + xo + t[1], ob = (yo + t[5]) * PL_STRIDE + xo + t[4];
+    if (((ox | oy) & 1) == 0) {          // full/half-pel positions are a single plane (both table entries coincide)
 #pragma unroll
-    for (int y = 0; y < 4; y++) P[y] = avg4(plane_row(pa, oa + y * PL_STRIDE), plane_row(pb, ob + y * PL_STRIDE));
+        for (int y = 0; y < 4; y++) P[y] = plane_row(pa, oa + y * PL_STRIDE);
+    } else {
+#pragma unroll
+        for (int y = 0; y < 4; y++) P[y] = avg4(plane_row(pa, oa + y * PL_STRIDE), plane_row(pb, ob + y * PL_STRIDE));
+    }
 }
 // 4x4 Hadamard SATD of (source block - P): Ts holds the horizontal transforms of the source rows, the prediction
 // rows are folded in with dp4a against the negated +-1 basis; |x+y|+|x-y| = 2 max(|x|,|y|) finishes the columns.
@@ -191,7 +201,7 @@ __device__ __forceinline__ int half_reduce16(int v)   // sum over the 16 lanes o
     return v;
 }
 
-__global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom g)
+__global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(const Sess *ss, Geom g)
 {
     __shared__ FineSmem sm_all[ME_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,6 +287,8 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom 
             for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(w, H[k], 0);
         }
     }
+    // se(v) lengths of the 7 possible vector components per axis: lane l holds x offset l-3 (l < 8) or y offset l-11 (l >= 8)
+    const int mvb = se_len(((lane & 8) ? 4 * fy : 4 * fx) + (lane & 7) - 3);
     int qx = 0, qy = 0;                                 // offset from 4*(fx,fy), quarter-pel units
     uint32_t centre_key = 0;
     // candidate i: 0 centre, then (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1); packed 2-bit (offset + 1) tables
@@ -293,7 +305,8 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom 
             uint32_t P[4]; pred_rows_qpel(sm, bx, by, ox, oy, P);
             const int sat = half_reduce16(satd_rows(P, Ts));
             uint32_t key = 0xffffffffu;
-            if (i <= 8) key = ((uint32_t)(sat + lambda * (se_len(4 * fx + ox) + se_len(4 * fy + oy))) << 4) | (uint32_t)i;
+            const int bits = __shfl_sync(0xffffffffu, mvb, ox + 3) + __shfl_sync(0xffffffffu, mvb, oy + 11);
+            if (i <= 8) key = ((uint32_t)(sat + lambda * bits) << 4) | (uint32_t)i;
             key = min(key, __shfl_xor_sync(0xffffffffu, key, 16));
             bk = min(bk, key);
         }
@@ -341,82 +354,83 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_fine(const Sess *ss, Geom 
     }
 
     // ---- phase B: code the inter macroblock ----
+    // lanes 0-15 own the luma 4x4 blocks, lanes 16-23 the chroma blocks; only the prediction differs between them,
+    // the transform / quantiser / reconstruction below is ONE instruction stream for all 24 lanes.
     MbCoef *co = s.coef + mb;
-    const QParam q = make_qparam(qp);
+    const bool is_luma = lane < 16, active = lane < 24;
+    const int pl = (lane >> 2) & 1, cb = lane & 3;                 // chroma plane / block of lanes 16-23
+    const int cw = wc / 2, ch = hc / 2;
+    const int cx0 = mx * 8 + (cb & 1) * 4, cy0 = my * 8 + (cb >> 1) * 4;
     int nnz = 0; bool dc_nz = false;
-    if (lane < 16) {
-        int p[16], c[16];
-        {
-            uint32_t P[4]; pred_rows_qpel(sm, bx, by, qx, qy, P);
-#pragma unroll
-            for (int y = 0; y < 4; y++) {
-                const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
-#pragma unroll
-                for (int x = 0; x < 4; x++) { p[y * 4 + x] = (P[y] >> (8 * x)) & 255; c[y * 4 + x] = (int)((w >> (8 * x)) & 255) - p[y * 4 + x]; }
-            }
-        }
-        fdct4x4(c);
-        __align__(16) int16_t lz[16];
-        nnz = quant_dequant4x4(c, lz, q, q.f_inter, false);
-        idct4x4(c);
-        uint4 *dst = reinterpret_cast<uint4 *>(co->luma[b]);
-        dst[0] = reinterpret_cast<uint4 *>(lz)[0]; dst[1] = reinterpret_cast<uint4 *>(lz)[1];
+    int p[16], c[16];
+    if (is_luma) {
+        uint32_t P[4]; pred_rows_qpel(sm, bx, by, qx, qy, P);
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            uint32_t w = 0;
+            const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
 #pragma unroll
-            for (int x = 0; x < 4; x++) w |= (uint32_t)clip255(p[y * 4 + x] + c[y * 4 + x]) << (8 * x);
-            *reinterpret_cast<uint32_t *>(s.rec[0] + (size_t)(y0 + by + y) * wc + x0 + bx) = w;
+            for (int x = 0; x < 4; x++) { p[y * 4 + x] = (P[y] >> (8 * x)) & 255; c[y * 4 + x] = (int)((w >> (8 * x)) & 255) - p[y * 4 + x]; }
         }
-    } else if (lane < 24) {
-        const int pl = (lane - 16) >> 2, cb = (lane - 16) & 3, cbx = (cb & 1) * 4, cby = (cb >> 1) * 4;
-        const int cw = wc / 2, ch = hc / 2, cx0 = mx * 8 + cbx, cy0 = my * 8 + cby;
+    } else {
+        // chroma motion compensation, 1/8-pel bilinear (8.4.2.2.2), clamped reference coordinates
+        const int pc = active ? pl : 0;
         const int xi = cx0 + (mvx >> 3), yi = cy0 + (mvy >> 3), fxc = mvx & 7, fyc = mvy & 7;
-        const uint8_t *rp = s.ref[1 + pl];
+        const uint8_t *rp = s.ref[1 + pc];
         int smp[25];
 #pragma unroll
         for (int y = 0; y < 5; y++)
 #pragma unroll
             for (int x = 0; x < 5; x++) smp[y * 5 + x] = __ldg(rp + (size_t)clip3(0, ch - 1, yi + y) * cw + clip3(0, cw - 1, xi + x));
-        int p[16], c[16];
-        const uint8_t *sp_c = s.src[1 + pl] + (size_t)cy0 * cw + cx0;
+        const uint8_t *sp_c = s.src[1 + pc] + (size_t)cy0 * cw + cx0;
+        const int w00 = (8 - fxc) * (8 - fyc), w01 = fxc * (8 - fyc), w10 = (8 - fxc) * fyc, w11 = fxc * fyc;
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            uint32_t w = *reinterpret_cast<const uint32_t *>(sp_c + (size_t)y * cw);
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(sp_c + (size_t)y * cw);
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-                p[y * 4 + x] = ((8 - fxc) * (8 - fyc) * smp[y * 5 + x] + fxc * (8 - fyc) * smp[y * 5 + x + 1]
-                              + (8 - fxc) * fyc * smp[y * 5 + 5 + x] + fxc * fyc * smp[y * 5 + 6 + x] + 32) >> 6;
+                p[y * 4 + x] = (w00 * smp[y * 5 + x] + w01 * smp[y * 5 + x + 1] + w10 * smp[y * 5 + 5 + x] + w11 * smp[y * 5 + 6 + x] + 32) >> 6;
                 c[y * 4 + x] = (int)((w >> (8 * x)) & 255) - p[y * 4 + x];
             }
         }
-        fdct4x4(c);
-        const QParam qc = make_qparam(c_chroma_qp[qp]);
-        // 2x2 DC: gather the four DC terms of this plane (lanes 16+4pl .. 19+4pl)
+    }
+    fdct4x4(c);
+    const QParam q = make_qparam(is_luma ? qp : (int)c_chroma_qp[qp]);
+    int dcC = 0;
+    if (!is_luma && active) {
+        // 2x2 DC of this plane (lanes 16+4pl .. 19+4pl): Hadamard, quantise, and the normative inverse (8.5.11)
         int dcs[4], lv[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) dcs[k] = __shfl_sync(0x00ff0000u, c[0], 16 + pl * 4 + k);
         const int hd[4] = { dcs[0] + dcs[1] + dcs[2] + dcs[3], dcs[0] - dcs[1] + dcs[2] - dcs[3], dcs[0] + dcs[1] - dcs[2] - dcs[3], dcs[0] - dcs[1] - dcs[2] + dcs[3] };
 #pragma unroll
-        for (int k = 0; k < 4; k++) { lv[k] = quant_dc(hd[k], qc, qc.f_inter); dc_nz |= lv[k] != 0; }
+        for (int k = 0; k < 4; k++) { lv[k] = quant_dc(hd[k], q, q.f_inter); dc_nz |= lv[k] != 0; }
         const int fi[4] = { lv[0] + lv[1] + lv[2] + lv[3], lv[0] - lv[1] + lv[2] - lv[3], lv[0] + lv[1] - lv[2] - lv[3], lv[0] - lv[1] - lv[2] + lv[3] };
-        __align__(16) int16_t lz[16];
-        nnz = quant_dequant4x4(c, lz, qc, qc.f_inter, true);
-        c[0] = ((fi[cb] * 16 * qc.v[0]) << qc.sh) >> 5;
-        idct4x4(c);
-        uint4 *dst = reinterpret_cast<uint4 *>(co->chroma_ac[pl][cb]);
-        dst[0] = reinterpret_cast<uint4 *>(lz)[0]; dst[1] = reinterpret_cast<uint4 *>(lz)[1];
+        const int f = cb == 0 ? fi[0] : cb == 1 ? fi[1] : cb == 2 ? fi[2] : fi[3];
+        dcC = ((f * 16 * q.v[0]) << q.sh) >> 5;
         if (cb == 0) *reinterpret_cast<uint2 *>(co->chroma_dc[pl]) = make_uint2((uint32_t)(uint16_t)lv[0] | ((uint32_t)(uint16_t)lv[1] << 16),
                                                                               (uint32_t)(uint16_t)lv[2] | ((uint32_t)(uint16_t)lv[3] << 16));
+    }
+    {
+        __align__(16) int16_t lz[16];
+        nnz = quant_dequant4x4(c, lz, q, q.f_inter, !is_luma);
+        if (!is_luma) c[0] = dcC;
+        idct4x4(c);
+        if (active) {
+            uint4 *dst = reinterpret_cast<uint4 *>(is_luma ? co->luma[b] : co->chroma_ac[pl][cb]);
+            dst[0] = reinterpret_cast<uint4 *>(lz)[0]; dst[1] = reinterpret_cast<uint4 *>(lz)[1];
+            uint8_t *rp = is_luma ? s.rec[0] + (size_t)(y0 + by) * wc + x0 + bx : s.rec[1 + pl] + (size_t)cy0 * cw + cx0;
+            const int rst = is_luma ? wc : cw;
 #pragma unroll
-        for (int y = 0; y < 4; y++) {
-            uint32_t w = 0;
+            for (int y = 0; y < 4; y++) {
+                uint32_t w = 0;
 #pragma unroll
-            for (int x = 0; x < 4; x++) w |= (uint32_t)clip255(p[y * 4 + x] + c[y * 4 + x]) << (8 * x);
-            *reinterpret_cast<uint32_t *>(s.rec[1 + pl] + (size_t)(cy0 + y) * cw + cx0) = w;
+                for (int x = 0; x < 4; x++) w |= (uint32_t)clip255(p[y * 4 + x] + c[y * 4 + x]) << (8 * x);
+                *reinterpret_cast<uint32_t *>(rp + (size_t)y * rst) = w;
+            }
+        } else {
+            nnz = 0;
+            if (lane < 26) reinterpret_cast<uint4 *>(co->luma_dc)[lane - 24] = make_uint4(0, 0, 0, 0);
         }
-    } else if (lane < 26) {
-        reinterpret_cast<uint4 *>(co->luma_dc)[lane - 24] = make_uint4(0, 0, 0, 0);
     }
     const uint32_t nzmask = __ballot_sync(0xffffffffu, nnz != 0), dcmask = __ballot_sync(0xffffffffu, dc_nz);
     int cbp = 0;

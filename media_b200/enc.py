@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200enc.so")
+LIB_PATH = os.environ.get("B200ENC_LIB") or os.path.join(_HERE, "csrc", "libb200enc.so")   # override only for A/B experiments
 
 FMT_I420, FMT_NV12, FMT_RGBA = 0, 1, 2
 STAGE = dict(mbinfo=0, mbcoef=1, me2=2, me1=3, me0=4, inter_cost=5, src=6, rec_pre=7, rec=8)
