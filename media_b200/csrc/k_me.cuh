@@ -71,60 +71,80 @@ __device__ __forceinline__ void stage_window_rt(uint32_t *dstw, int W, const uin
 }
 
 // ---- coarse levels: 1/4 resolution exhaustive search, 1/2 resolution refinement ----
-struct CoarseSmem { uint32_t win[(40 * 40 + 8) / 4]; uint32_t src[16]; uint32_t win1[(12 * 12 + 8) / 4]; };
-
-__global__ void __launch_bounds__(ME_WARPS * 32) k_me_coarse(const Sess *ss, Geom g)
+// The search windows are kept as four byte-shifted copies (copy k, word j of a row = bytes 4j+k .. 4j+k+3), so every
+// candidate row is read with aligned 32-bit loads straight into VABSDIFF4.
+template <int MAXR4> struct CoarseSmem {
+    static constexpr int MAXW = 8 + 2 * MAXR4, CW = MAXW * MAXW / 4 + 2;
+    uint32_t win[4][CW]; uint32_t src[16]; uint32_t win1[4][12 * 3 + 2];
+};
+// build copies 1..3 from copy 0 (n words each, rows are contiguous so word j+1 is the right neighbour)
+__device__ __forceinline__ void make_shifted_copies(uint32_t *c0, int copy_stride, int n, int lane)
 {
-    __shared__ CoarseSmem sm_all[ME_WARPS];
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t a = c0[i], b = c0[i + 1];
+        c0[copy_stride + i] = __funnelshift_r(a, b, 8);
+        c0[2 * copy_stride + i] = __funnelshift_r(a, b, 16);
+        c0[3 * copy_stride + i] = __funnelshift_r(a, b, 24);
+    }
+}
+
+template <int MAXR4, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_me_coarse(const Sess *ss, Geom g)
+{
+    typedef CoarseSmem<MAXR4> Smem;
+    __shared__ Smem sm_all[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mb = blockIdx.x * ME_WARPS + warp;
+    const int mb = blockIdx.x * WARPS + warp;
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
     if (s.is_idr) return;
-    CoarseSmem &sm = sm_all[warp];
+    Smem &sm = sm_all[warp];
     const int mx = mb % g.mbw, my = mb / g.mbw;
-    const int R4 = g.search_range / 4, span = 2 * R4 + 1, W = 8 + 2 * R4;
+    const int R4 = g.search_range / 4, span = 2 * R4 + 1, W = 8 + 2 * R4, wpr = W >> 2;
     const int w2 = g.wc / 4, h2 = g.hc / 4, w1 = g.wc / 2, h1 = g.hc / 2;
-    uint8_t *win = reinterpret_cast<uint8_t *>(sm.win), *win1 = reinterpret_cast<uint8_t *>(sm.win1);
 
     // level 2: 8x8 block centred on the MB (origin 4mx-2, 4my-2), all (2R4+1)^2 displacements
     stage_window<8, 8>(sm.src, s.srcL2, w2, h2, 4 * mx - 2, 4 * my - 2, lane);
-    stage_window_rt(sm.win, W, s.refL2, w2, h2, 4 * mx - 2 - R4, 4 * my - 2 - R4, lane);
+    if (R4 == MAXR4) stage_window<8 + 2 * MAXR4, 8 + 2 * MAXR4>(sm.win[0], s.refL2, w2, h2, 4 * mx - 2 - R4, 4 * my - 2 - R4, lane);
+    else stage_window_rt(sm.win[0], W, s.refL2, w2, h2, 4 * mx - 2 - R4, 4 * my - 2 - R4, lane);
     __syncwarp();
+    make_shifted_copies(sm.win[0], Smem::CW, W * wpr, lane);
     uint32_t sw[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) sw[i] = sm.src[i];
+    __syncwarp();
     uint32_t best = 0xffffffffu;
-    for (int cand = lane; cand < span * span; cand += 32) {
-        const int dy = cand / span, dx = cand - dy * span;
-        uint32_t sad = 0;
+    {
+        int dy = lane / span, dx = lane - dy * span;              // candidate = lane + 32k, walked without divisions
+        const int sdy = 32 / span, sdx = 32 - sdy * span;
+        for (int cand = lane; cand < span * span; cand += 32) {
+            const uint32_t *p = sm.win[dx & 3] + dy * wpr + (dx >> 2);
+            uint32_t sad = 0;
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int o = (dy + r) * W + dx;
-            sad = sad4(sw[2 * r], lds_u32_unaligned(win, o), sad);
-            sad = sad4(sw[2 * r + 1], lds_u32_unaligned(win, o + 4), sad);
+            for (int r = 0; r < 8; r++) { sad = sad4(sw[2 * r], p[r * wpr], sad); sad = sad4(sw[2 * r + 1], p[r * wpr + 1], sad); }
+            best = min(best, ((sad + abs(dx - R4) + abs(dy - R4)) << 11) | (uint32_t)cand);
+            dy += sdy; dx += sdx;
+            if (dx >= span) { dx -= span; dy++; }
         }
-        best = min(best, ((sad + abs(dx - R4) + abs(dy - R4)) << 11) | (uint32_t)cand);
     }
     best = warp_min(best);
-    const int c2 = best & 2047, v2x = c2 % span - R4, v2y = c2 / span - R4;
+    const int c2 = best & 2047, v2y = c2 / span - R4, v2x = c2 - (v2y + R4) * span - R4;
 
     // level 1: 8x8 block at (8mx, 8my), +-2 around 2*mv2
     const int cx = 2 * v2x, cy = 2 * v2y;
     __syncwarp();
     stage_window<8, 8>(sm.src, s.srcL1, w1, h1, 8 * mx, 8 * my, lane);
-    stage_window<12, 12>(sm.win1, s.refL1, w1, h1, 8 * mx + cx - 2, 8 * my + cy - 2, lane);
+    stage_window<12, 12>(sm.win1[0], s.refL1, w1, h1, 8 * mx + cx - 2, 8 * my + cy - 2, lane);
+    __syncwarp();
+    make_shifted_copies(sm.win1[0], 12 * 3 + 2, 36, lane);
     __syncwarp();
     best = 0xffffffffu;
     if (lane < 25) {
         const int dy = lane / 5, dx = lane - dy * 5;
+        const uint32_t *p = sm.win1[dx & 3] + dy * 3 + (dx >> 2);
         uint32_t sad = 0;
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int o = (dy + r) * 12 + dx;
-            sad = sad4(sm.src[2 * r], lds_u32_unaligned(win1, o), sad);
-            sad = sad4(sm.src[2 * r + 1], lds_u32_unaligned(win1, o + 4), sad);
-        }
+        for (int r = 0; r < 8; r++) { sad = sad4(sm.src[2 * r], p[r * 3], sad); sad = sad4(sm.src[2 * r + 1], p[r * 3 + 1], sad); }
         best = ((sad + abs(cx + dx - 2) + abs(cy + dy - 2)) << 5) | (uint32_t)lane;
     }
     best = warp_min(best);
@@ -138,7 +158,8 @@ __global__ void __launch_bounds__(ME_WARPS * 32) k_me_coarse(const Sess *ss, Geo
 // ---- fine level: full-pel refinement, half/quarter-pel SATD refinement, intra estimate, inter coding ----
 #define PL_STRIDE 24                     /* bytes per row of a sample plane: sample (x,y) at (y+1)*24 + x + 4, x in [-1,16] */
 struct FineSmem {
-    uint32_t win[(24 * 24 + 8) / 4];     // full-pel window: 20x20 (stride 20) for the +-2 search, then 24x24 around the winner
+    uint32_t win[(24 * 24 + 8) / 4];     // 24x24 full-pel window around the level-0 winner (copy 0 of win0 is staged here first)
+    uint32_t win0[3][20 * 5 + 2];         // byte-shifted copies 1..3 of the 20x20 window of the +-2 search
     uint32_t src[64];                    // source MB, 16x16
     uint32_t plane[4][18 * PL_STRIDE / 4 + 2]; // G, b, h, j samples at [-1,16]^2 relative to the best full-pel block (8.4.2.2.1)
     int16_t braw[24 * 18];               // unrounded horizontal half-pel sums, rows [-3,20]
@@ -212,7 +233,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     FineSmem &sm = sm_all[warp];
     const int mx = mb % g.mbw, my = mb / g.mbw, x0 = mx * 16, y0 = my * 16, wc = g.wc, hc = g.hc;
     const int qp = s.qp, lambda = c_lambda[qp];
-    uint8_t *win = reinterpret_cast<uint8_t *>(sm.win);
+    const uint8_t *win = reinterpret_cast<const uint8_t *>(sm.win);
 
     // source MB and the +-2 window around 2*mv1
     const int cx = 2 * s.me1[mb * 2], cy = 2 * s.me1[mb * 2 + 1];
@@ -233,15 +254,20 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
         for (int o = 16; o; o >>= 1) zsad += __shfl_xor_sync(0xffffffffu, zsad, o);
     }
     __syncwarp();
+    for (int i = lane; i < 100; i += 32) {              // byte-shifted copies of the 20x20 window: aligned candidate reads
+        const uint32_t a = sm.win[i], b = sm.win[i + 1];
+        sm.win0[0][i] = __funnelshift_r(a, b, 8); sm.win0[1][i] = __funnelshift_r(a, b, 16); sm.win0[2][i] = __funnelshift_r(a, b, 24);
+    }
+    __syncwarp();
     uint32_t best = 0xffffffffu;
     if (lane < 25) {
         const int dy = lane / 5, dx = lane - dy * 5;
+        const uint32_t *p = ((dx & 3) ? sm.win0[(dx & 3) - 1] : sm.win) + dy * 5 + (dx >> 2);
         uint32_t sad = 0;
 #pragma unroll 4
         for (int r = 0; r < 16; r++) {
-            const int o = (dy + r) * 20 + dx;
 #pragma unroll
-            for (int k = 0; k < 4; k++) sad = sad4(sm.src[r * 4 + k], lds_u32_unaligned(win, o + 4 * k), sad);
+            for (int k = 0; k < 4; k++) sad = sad4(sm.src[r * 4 + k], p[r * 5 + k], sad);
         }
         best = ((sad + lambda * (se_len(4 * (cx + dx - 2)) + se_len(4 * (cy + dy - 2)))) << 5) | (uint32_t)lane;
     } else if (lane == 25) best = ((zsad + lambda * 2) << 5) | 25u;

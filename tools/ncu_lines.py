@@ -17,7 +17,8 @@ for r in rows[hi + 1:]:
     if len(r) >= len(hdr) and r[ix["Instructions Executed"]].isdigit():
         sass.append((r[ix["Source"]].strip(), int(r[ix["Instructions Executed"]] or 0), int(r[ix["# Samples"]] or 0), int(r[ix["L1 Wavefronts Shared Excessive"]] or 0)))
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "media_b200", "csrc", "libb200enc.so")], cwd=tmp, capture_output=True)
+lib = os.environ.get("NCU_LINES_LIB", os.path.join(ROOT, "media_b200", "csrc", "libb200enc.so"))   # the build the report was taken with
+subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
 # locate the function
@@ -45,5 +46,5 @@ def src(f, ln):
     s = src_cache[f]
     return s[ln - 1].strip()[:110] if 0 < ln <= len(s) else ""
 print(f"kernel {kern}: {tot} warp-instructions, {tots} samples")
-for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("NCU_LINES_TOP", "40"))]:
     print(f"{a[0] / tot * 100:5.1f}% instr {a[1] / tots * 100:5.1f}% samples excess_smem_wavefronts {a[2]:>9d}  {f}:{ln}  {src(f, ln)}")
