@@ -161,6 +161,38 @@ def run_b200(args):
     # end to end: host pinned frames in, host-visible bitstreams out
     el_e, dev_ms_e, _, out_bytes_e = timed(groups, hpool, 0, args.steps, 1, step0=args.warmup + args.steps)
     e2e = world * S * args.steps / el_e
+    # the reference's threading model: one caller thread per session, each blocked in b200enc_encode (what EncodeOneFrame
+    # does); the per-GPU auto_batch scheduler coalesces them. Python threads add overhead, so this is a lower bound.
+    thr = None
+    if args.threads_e2e:
+        for x in sess:
+            x.close()
+        sess = [enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=-1, search_range=16, device=dev, auto_batch=1) for _ in range(S)]
+        b0, f0, b1, f1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        nst = max(4, args.steps)
+
+        def caller(i, first, count):
+            bs, n = C.c_void_p(), C.c_uint32()
+            for k in range(first, first + count):
+                L.b200enc_encode(sess[i].h, hpool[pool_index(k, i)], fb, C.byref(bs), C.byref(n), None)
+
+        def run_callers(first, count):
+            ths = [threading.Thread(target=caller, args=(i, first, count)) for i in range(S)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        run_callers(0, 3)
+        barrier()
+        L.b200enc_scheduler_stats(dev, C.byref(b0), C.byref(f0))
+        t0 = time.perf_counter(); run_callers(3, nst); barrier(); el_t = time.perf_counter() - t0
+        L.b200enc_scheduler_stats(dev, C.byref(b1), C.byref(f1))
+        if use_dist:
+            tt = torch.tensor([el_t], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); el_t = tt[0].item()
+        thr = {"value": round(world * S * nst / el_t, 2), "unit": "frames/s", "caller_threads": S,
+               "avg_batch": round((f1.value - f0.value) / max(1, b1.value - b0.value), 1),
+               "note": "one Python thread per session blocked in b200enc_encode (auto_batch scheduler); host frames in, bitstreams out"}
+        groups = new_groups(); batch = groups[0][1]; sess += [x for g in groups for x in g[0]]
     # per-kernel shares of one step (CUDA events around each launch)
     batch.set_profiling(True)
     pstep = 2 * args.warmup + 2 * args.steps + 1
@@ -216,6 +248,8 @@ def run_b200(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if thr:
+            line["e2e_caller_threads"] = thr
     for s in sess:
         s.close()
     if use_dist:
@@ -280,6 +314,7 @@ def main():
     ap.add_argument("--groups", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--threads-e2e", action="store_true", help="also measure one caller thread per session through the auto_batch scheduler")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -11,6 +11,8 @@
  *                            (video_codec/VideoEncoderOpenH264.cpp:344-350; vendor/openh264/codec_api.h:309)
  *   b200enc_force_idr     <- ISVCEncoder::ForceIntraFrame(true) (video_codec/VideoEncoderOpenH264.cpp:406-415)
  *   b200enc_destroy       <- ISVCEncoder::Uninitialize + WelsDestroySVCEncoder (video_codec/VideoEncoderOpenH264.cpp:379-386)
+ *   auto_batch scheduler  <- the reference's one-thread-per-session model (:294): N caller threads, each in its own
+ *                            EncodeOneFrame, are served by one batch step per GPU
  *   b200enc_batch_*       <- no reference counterpart: N sessions of one GPU advance one frame in one set of kernel
  *                            launches (the reference runs one single-threaded encoder per session, :294)
  *   b200k_*               <- per-kernel entry points for parity tests against oracle/ (openh264's C kernels,
@@ -54,6 +56,8 @@ typedef struct b200enc_config {
     int device;            /* CUDA ordinal, or -1: least-loaded device by pixel rate */
     int level_idc;         /* 0: derive from size and fps (the wrapper's LEVEL_3_2 at :255 is too small for 1080p) */
     int debug;             /* 1: keep stage dumps (pre-deblock reconstruction) for b200enc_get_stage */
+    int auto_batch;        /* 1: concurrent b200enc_encode calls of sessions living on the same GPU are coalesced by a per-GPU
+                              scheduler thread into one batch step (what gives many single-threaded callers GPU-wide throughput) */
 } b200enc_config;
 
 typedef struct b200enc_frame_info {
@@ -79,6 +83,8 @@ size_t b200enc_frame_bytes(const b200enc_session *s);
 int b200enc_last_cuda_error(void);
 const char *b200enc_strerror(int code);
 int b200enc_device_count(void);
+/* statistics of the auto_batch scheduler of `device`: batches run and frames encoded through it */
+int b200enc_scheduler_stats(int device, uint64_t *batches, uint64_t *frames);
 
 /* Batched stepping: all sessions must live on the batch's device and share width/height/slices/search range/format. */
 int b200enc_batch_create(int device, int max_sessions, b200enc_batch **out);

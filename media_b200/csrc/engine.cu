@@ -16,8 +16,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace b200;
@@ -159,6 +165,7 @@ struct b200enc_session {
     int last_qp = 26, last_type = 1;
     RateCtl rc;
     b200enc_batch *own = nullptr;
+    bool in_scheduler = false;
 };
 
 namespace {
@@ -310,6 +317,109 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     return rc;
 }
 
+
+// ---- per-GPU session scheduler (auto_batch): the reference runs one caller thread per session, each blocked in its own
+// EncodeOneFrame (video_codec/VideoEncoderOpenH264.cpp:304-352, iMultipleThreadIdc = 1 at :294). Here those concurrent calls
+// rendezvous in a per-GPU worker that advances all waiting sessions with ONE batch step; while a step runs, the next
+// callers queue up, so batches form by themselves under load and a lone caller only pays the short window. ----
+struct SchedRequest {
+    b200enc_session *s; const uint8_t *frame; const uint8_t *bs = nullptr; uint32_t size = 0; b200enc_frame_info info{};
+    int rc = B200ENC_OK; bool done = false;
+};
+struct DeviceScheduler {
+    static constexpr int WORKERS = 2;      // two batch contexts (streams): one batch uploads/queues while the other computes
+    int device = -1, registered = 0, inflight = 0;
+    std::mutex mu; std::condition_variable cv_submit, cv_done;
+    std::vector<SchedRequest *> pending;
+    std::thread worker[WORKERS]; bool stop = false;
+    b200enc_batch *ctx[WORKERS] = { nullptr, nullptr }; int window_us = 300;
+    std::atomic<uint64_t> batches{ 0 }, frames{ 0 };
+
+    void run(int w)
+    {
+        cudaSetDevice(device);
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_submit.wait(lk, [&] { return stop || !pending.empty(); });
+            if (stop && pending.empty()) return;
+            // short rendezvous window: leave early once every session that is not already being encoded has a frame waiting
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(window_us);
+            while ((int)pending.size() < registered - inflight && !stop)
+                if (cv_submit.wait_until(lk, deadline) == std::cv_status::timeout) break;
+            if (pending.empty()) continue;                 // the other worker took them
+            // one batch = the requests that share the first request's shape (other shapes wait for the next round)
+            std::vector<SchedRequest *> take, rest;
+            for (SchedRequest *r : pending) (same_shape(pending[0]->s, r->s) && (int)take.size() < ctx[w]->cap ? take : rest).push_back(r);
+            pending.swap(rest);
+            const int n = (int)take.size();
+            inflight += n;
+            lk.unlock();
+            std::vector<b200enc_session *> ss(n); std::vector<const uint8_t *> fr(n), bs(n); std::vector<uint32_t> sz(n); std::vector<b200enc_frame_info> inf(n);
+            for (int i = 0; i < n; i++) { ss[i] = take[i]->s; fr[i] = take[i]->frame; }
+            const int rc = encode_impl(ctx[w], ss.data(), n, fr.data(), 0, bs.data(), sz.data(), inf.data());
+            batches++; frames += n;
+            lk.lock();
+            inflight -= n;
+            for (int i = 0; i < n; i++) { take[i]->bs = bs[i]; take[i]->size = sz[i]; take[i]->info = inf[i]; take[i]->rc = rc; take[i]->done = true; }
+            cv_done.notify_all();
+        }
+    }
+};
+std::mutex g_scheds_mu;
+std::vector<std::unique_ptr<DeviceScheduler>> g_scheds;
+
+DeviceScheduler *scheduler_for(int device)
+{
+    std::lock_guard<std::mutex> lk(g_scheds_mu);
+    if ((int)g_scheds.size() <= device) g_scheds.resize(device + 1);
+    if (!g_scheds[device]) {
+        std::unique_ptr<DeviceScheduler> d(new DeviceScheduler());
+        d->device = device;
+        if (const char *e = getenv("B200ENC_BATCH_WINDOW_US")) d->window_us = std::max(0, atoi(e));
+        for (int w = 0; w < DeviceScheduler::WORKERS; w++) {
+            d->ctx[w] = new (std::nothrow) b200enc_batch();
+            if (!d->ctx[w] || batch_init(d->ctx[w], device, 512) != B200ENC_OK) return nullptr;
+        }
+        DeviceScheduler *raw = d.get();
+        for (int w = 0; w < DeviceScheduler::WORKERS; w++) d->worker[w] = std::thread([raw, w] { raw->run(w); });
+        g_scheds[device] = std::move(d);
+    }
+    return g_scheds[device].get();
+}
+void scheduler_register(b200enc_session *s, int delta)
+{
+    DeviceScheduler *d = scheduler_for(s->device);
+    if (!d) return;
+    std::lock_guard<std::mutex> lk(d->mu);
+    d->registered += delta;
+    s->in_scheduler = delta > 0;
+    d->cv_submit.notify_all();
+}
+int scheduler_encode(b200enc_session *s, const uint8_t *frame, const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *info)
+{
+    DeviceScheduler *d = scheduler_for(s->device);
+    if (!d) return B200ENC_ENODEV;
+    SchedRequest req; req.s = s; req.frame = frame;
+    std::unique_lock<std::mutex> lk(d->mu);
+    d->pending.push_back(&req);
+    d->cv_submit.notify_all();
+    d->cv_done.wait(lk, [&] { return req.done; });
+    if (bs) *bs = req.bs;
+    if (bs_size) *bs_size = req.size;
+    if (info) *info = req.info;
+    return req.rc;
+}
+struct SchedulerShutdown {       // join the workers before the CUDA runtime is torn down at process exit
+    ~SchedulerShutdown()
+    {
+        std::lock_guard<std::mutex> lk(g_scheds_mu);
+        for (auto &d : g_scheds) if (d) {
+            { std::lock_guard<std::mutex> l2(d->mu); d->stop = true; d->cv_submit.notify_all(); }
+            for (auto &t : d->worker) if (t.joinable()) t.join();
+        }
+    }
+} g_scheduler_shutdown;
+
 } // namespace
 
 extern "C" {
@@ -325,6 +435,14 @@ void b200enc_default_config(b200enc_config *c)
 
 int b200enc_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 int b200enc_last_cuda_error(void) { return g_last_cuda_error; }
+int b200enc_scheduler_stats(int device, uint64_t *batches, uint64_t *frames)
+{
+    std::lock_guard<std::mutex> lk(g_scheds_mu);
+    if (device < 0 || device >= (int)g_scheds.size() || !g_scheds[device]) return B200ENC_EINVAL;
+    if (batches) *batches = g_scheds[device]->batches.load();
+    if (frames) *frames = g_scheds[device]->frames.load();
+    return B200ENC_OK;
+}
 const char *b200enc_strerror(int code)
 {
     switch (code) {
@@ -402,6 +520,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         if (!s->own) { rc = B200ENC_ENOMEM; break; }
         rc = batch_init(s->own, s->device, 1);
         s->rc.target = (double)c.bitrate / c.fps;
+        if (rc == B200ENC_OK && c.auto_batch) scheduler_register(s, +1);
     } while (0);
     if (rc != B200ENC_OK) { b200enc_destroy(s); return rc; }
     *out = s;
@@ -412,6 +531,7 @@ void b200enc_destroy(b200enc_session *s)
 {
     if (!s) return;
     if (s->device >= 0) {
+        if (s->in_scheduler) scheduler_register(s, -1);
         cudaSetDevice(s->device);
         if (s->own) batch_free(s->own);
         if (s->h_out) cudaFreeHost(s->h_out);
@@ -434,6 +554,7 @@ int b200enc_encode(b200enc_session *s, const uint8_t *frame, uint32_t size, cons
 {
     if (!s || !frame) return B200ENC_EINVAL;
     if (size < b200enc_frame_bytes(s)) return B200ENC_ESIZE;
+    if (s->in_scheduler) return scheduler_encode(s, frame, bs, bs_size, info);
     return encode_impl(s->own, &s, 1, &frame, 0, bs, bs_size, info);
 }
 float b200enc_last_kernel_ms(const b200enc_session *s) { return s && s->own ? s->own->last_ms : 0.f; }

@@ -21,7 +21,7 @@ MBCOEF_DTYPE = np.dtype([("luma", "<i2", (16, 16)), ("luma_dc", "<i2", (16,)),
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "height", "fps", "bitrate", "gop", "const_qp", "num_slices",
-                                       "search_range", "input_format", "device", "level_idc", "debug")]
+                                       "search_range", "input_format", "device", "level_idc", "debug", "auto_batch")]
 
 
 class FrameInfo(C.Structure):
@@ -55,6 +55,7 @@ def lib():
         L.b200enc_last_cuda_error.restype = C.c_int
         L.b200enc_strerror.restype = C.c_char_p; L.b200enc_strerror.argtypes = [C.c_int]
         L.b200enc_device_count.restype = C.c_int
+        L.b200enc_scheduler_stats.restype = C.c_int; L.b200enc_scheduler_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.b200enc_batch_create.restype = C.c_int; L.b200enc_batch_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
         L.b200enc_batch_destroy.argtypes = [vp]
         L.b200enc_batch_encode.restype = C.c_int
@@ -96,9 +97,9 @@ def _p(a):
 
 class Session:
     def __init__(self, width, height, fps=30, bitrate=4_000_000, gop=30, const_qp=-1, num_slices=1, search_range=16,
-                 input_format=FMT_I420, device=-1, level_idc=0, debug=0):
+                 input_format=FMT_I420, device=-1, level_idc=0, debug=0, auto_batch=0):
         L = lib()
-        self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug)
+        self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug, auto_batch)
         self.h = C.c_void_p()
         check(L.b200enc_create(C.byref(self.cfg), C.byref(self.h)), "b200enc_create")
         self.width, self.height = width, height

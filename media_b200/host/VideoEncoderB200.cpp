@@ -14,6 +14,7 @@ const char *KEY_DEVICE = "persist.vmi.b200.encode.device";               // CUDA
 const char *KEY_SLICES = "persist.vmi.b200.encode.slices";
 const char *KEY_SEARCH_RANGE = "persist.vmi.b200.encode.search_range";
 const char *KEY_CONST_QP = "persist.vmi.b200.encode.const_qp";           // test hook: fixed QP instead of rate control
+const char *KEY_AUTO_BATCH = "persist.vmi.b200.encode.auto_batch";       // "0" disables the per-GPU session scheduler (default on)
 }
 
 VideoEncoderB200::VideoEncoderB200() { INFO("VideoEncoderB200 constructor"); }
@@ -109,6 +110,7 @@ EncoderRetCode VideoEncoderB200::InitEncoder()
     cfg.input_format = fmt == "rgba" ? B200ENC_FMT_RGBA : fmt == "nv12" ? B200ENC_FMT_NV12 : B200ENC_FMT_I420;
     const int32_t dev = GetIntEncParam(KEY_DEVICE), slices = GetIntEncParam(KEY_SLICES), range = GetIntEncParam(KEY_SEARCH_RANGE), cqp = GetIntEncParam(KEY_CONST_QP);
     cfg.device = dev >= 0 ? dev : -1;
+    cfg.auto_batch = GetStrEncParam(KEY_AUTO_BATCH) == "0" ? 0 : 1;
     if (slices > 0) cfg.num_slices = slices;
     if (range > 0) cfg.search_range = range;
     if (GetStrEncParam(KEY_CONST_QP) != "" && cqp >= 0 && cqp <= 51) cfg.const_qp = cqp;

@@ -129,6 +129,43 @@ def test_batch_equals_individual_sessions(enc):
     b.close()
 
 
+def test_auto_batch_scheduler_coalesces_concurrent_callers(enc):
+    """N caller threads, one session each, all blocked in b200enc_encode (the reference's threading model): the per-GPU
+    scheduler must serve them with shared batch steps and every stream must equal the one a lone session produces"""
+    import threading
+    w, h, n, frames = 320, 192, 8, 6
+    cs = [Content("A", w, h, seed=200 + i) for i in range(n)]
+    data = [[cs[i].frame(t) for t in range(frames)] for i in range(n)]
+    solo = []
+    for i in range(n):
+        s = enc.Session(w, h, const_qp=26 + (i % 3), gop=1000, device=0)
+        solo.append([s.encode(f)[0] for f in data[i]]); s.close()
+    L = enc.lib()
+    b0, f0 = C.c_uint64(), C.c_uint64()
+    ss = [enc.Session(w, h, const_qp=26 + (i % 3), gop=1000, device=0, auto_batch=1) for i in range(n)]
+    L.b200enc_scheduler_stats(0, C.byref(b0), C.byref(f0))
+    out = [[None] * frames for _ in range(n)]
+    barrier = threading.Barrier(n)
+
+    def worker(i):
+        for t in range(frames):
+            barrier.wait()
+            out[i][t] = ss[i].encode(data[i][t])[0]
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(n)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    b1, f1 = C.c_uint64(), C.c_uint64()
+    L.b200enc_scheduler_stats(0, C.byref(b1), C.byref(f1))
+    for i in range(n):
+        assert out[i] == solo[i], f"session {i}"
+    assert f1.value - f0.value == n * frames
+    assert b1.value - b0.value < n * frames // 2, "concurrent callers were not coalesced into batches"
+    for s in ss:
+        s.close()
+
+
 def test_device_resident_input_equals_host_input(enc):
     w, h = 256, 144
     L = enc.lib()
