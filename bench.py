@@ -232,7 +232,7 @@ def run_b200(args):
                                    f"search +-16, 1 slice, content A (moving texture); step = one frame of every session; {G} batch(es) of {group_sizes[0]} on own streams",
                        "sessions_per_gpu": S, "frames_per_step": S * world, "l2_policy": f"inputs larger than L2: per-step working set ~{S * 20} MB",
                        "parallelism": f"sessions sharded over {world} GPU(s), no collective"},
-            "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": int(out_bytes_e / args.steps),
+            "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": world * S * fb, "d2h_bytes_per_step": int(world * out_bytes_e / args.steps),
                     "ms_per_step": round(el_e / args.steps * 1e3, 4)},
             "gpu_launches": launches,
             "bitrate_mbps_per_session": round(out_bytes * 8 / (S * args.steps) * FPS / 1e6, 3),

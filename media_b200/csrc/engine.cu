@@ -105,21 +105,22 @@ std::vector<uint8_t> make_parameter_sets(int w, int h, int level)
 // ---- rate control: frame-level QP from a bits ~ C / Qstep model with a virtual buffer (host logic; the
 // reference asks openh264 for RC_BITRATE_MODE at video_codec/VideoEncoderOpenH264.cpp:274, target = max bitrate :239-240) ----
 struct RateCtl {
-    double target = 0, vbv = 0, cplx[2] = { 0, 0 }; int last_qp[2] = { 30, 30 }; bool have[2] = { false, false };
+    double target = 0, vbv = 0, cplx[2] = { 0, 0 }; int last_qp[2] = { 30, 30 }; bool have[2] = { false, false }; int fps = 30;
     static double qstep(int qp) { return std::pow(2.0, (qp - 4) / 6.0); }
     int pick(int type, int w, int h)
     {
         if (!have[type]) {
-            if (type == 0 && have[1]) return std::min(51, last_qp[1] + 2);
+            if (type == 0 && have[1]) return std::max(12, last_qp[1] - 3);      // first P after the first IDR
             const double bpp = target / ((double)w * h);
             int qp = bpp > 0.2 ? 24 : bpp > 0.1 ? 28 : bpp > 0.05 ? 32 : bpp > 0.02 ? 36 : 40;
-            return type == 1 ? qp - 2 : qp;
+            return type == 1 ? qp + 5 : qp;    // an intra picture costs ~10x a P picture at equal QP: start it coarser, not finer
         }
+        // spread the buffer error over two seconds; an IDR may take four frame budgets
         const double weight = type == 1 ? 4.0 : 1.0;
-        double want = target * weight - 0.5 * vbv;
-        want = std::min(std::max(want, 0.3 * target * weight), 2.0 * target * weight);
+        double want = target * weight - vbv / (2.0 * fps);
+        want = std::min(std::max(want, 0.5 * target * weight), 1.5 * target * weight);
         int qp = (int)std::lround(4.0 + 6.0 * std::log2(cplx[type] / want));
-        qp = std::min(std::max(qp, last_qp[type] - 4), last_qp[type] + 4);
+        qp = std::min(std::max(qp, last_qp[type] - 3), last_qp[type] + 3);
         return std::min(std::max(qp, 12), 48);
     }
     void update(int type, int qp, double bits)
@@ -128,7 +129,7 @@ struct RateCtl {
         cplx[type] = have[type] ? 0.5 * cplx[type] + 0.5 * c : c;
         have[type] = true; last_qp[type] = qp;
         vbv += bits - target;
-        vbv = std::min(std::max(vbv, -4.0 * target), 30.0 * target);
+        vbv = std::min(std::max(vbv, -2.0 * fps * target), 4.0 * fps * target);
     }
 };
 
@@ -519,7 +520,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         s->own = new (std::nothrow) b200enc_batch();
         if (!s->own) { rc = B200ENC_ENOMEM; break; }
         rc = batch_init(s->own, s->device, 1);
-        s->rc.target = (double)c.bitrate / c.fps;
+        s->rc.target = (double)c.bitrate / c.fps; s->rc.fps = c.fps;
         if (rc == B200ENC_OK && c.auto_batch) scheduler_register(s, +1);
     } while (0);
     if (rc != B200ENC_OK) { b200enc_destroy(s); return rc; }
