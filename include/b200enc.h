@@ -78,6 +78,8 @@ void b200enc_destroy(b200enc_session *s);
 int b200enc_encode(b200enc_session *s, const uint8_t *frame, uint32_t size, const uint8_t **bs, uint32_t *bs_size,
                    b200enc_frame_info *info);
 int b200enc_force_idr(b200enc_session *s);
+/* SPS + PPS NALs of the session (Annex-B), what openh264's EncodeParameterSets returns (vendor/openh264/codec_api.h:316) */
+int b200enc_get_parameter_sets(b200enc_session *s, uint8_t *out, uint32_t cap, uint32_t *len);
 int b200enc_device_of(const b200enc_session *s);
 size_t b200enc_frame_bytes(const b200enc_session *s);
 int b200enc_last_cuda_error(void);

@@ -159,6 +159,7 @@ struct b200enc_session {
     MbInfo *mbi; MbCoef *coef; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
     uint32_t *mb_bits, *mb_off, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
     uint32_t rbsp_words_per_slice = 0;
+    std::vector<uint8_t> param_sets;
     // pinned, device-mapped output: [0..cap) bitstream, then one uint32 size
     uint8_t *h_out = nullptr, *d_out = nullptr; uint32_t out_cap = 0;
     bool cur_is_A = true;
@@ -491,7 +492,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         const int max_slice_rows = g.mbh / g.num_slices + (g.mbh % g.num_slices ? 1 : 0);
         s->rbsp_words_per_slice = (uint32_t)((size_t)max_slice_rows * g.mbw * B200_MB_SLOT_WORDS + 64);
         const std::vector<uint8_t> ps = make_parameter_sets(c.width, c.height, c.level_idc ? c.level_idc : level_for(c.width, c.height, c.fps));
-        s->hdr_len = (int)ps.size();
+        s->hdr_len = (int)ps.size(); s->param_sets = ps;
         struct Item { void **p; size_t bytes; };
         std::vector<Item> items;
         auto add = [&](auto &ptr, size_t bytes) { items.push_back({ reinterpret_cast<void **>(&ptr), bytes }); };
@@ -550,6 +551,13 @@ size_t b200enc_frame_bytes(const b200enc_session *s)
 }
 int b200enc_device_of(const b200enc_session *s) { return s ? s->device : -1; }
 int b200enc_force_idr(b200enc_session *s) { if (!s) return B200ENC_EINVAL; s->force_idr = true; return B200ENC_OK; }
+int b200enc_get_parameter_sets(b200enc_session *s, uint8_t *out, uint32_t cap, uint32_t *len)
+{
+    if (!s || !out || !len || cap < s->param_sets.size()) return B200ENC_EINVAL;
+    memcpy(out, s->param_sets.data(), s->param_sets.size());
+    *len = (uint32_t)s->param_sets.size();
+    return B200ENC_OK;
+}
 
 int b200enc_encode(b200enc_session *s, const uint8_t *frame, uint32_t size, const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *info)
 {

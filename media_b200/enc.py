@@ -50,6 +50,7 @@ def lib():
         L.b200enc_encode.restype = C.c_int
         L.b200enc_encode.argtypes = [vp, vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(FrameInfo)]
         L.b200enc_force_idr.restype = C.c_int; L.b200enc_force_idr.argtypes = [vp]
+        L.b200enc_get_parameter_sets.restype = C.c_int; L.b200enc_get_parameter_sets.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
         L.b200enc_device_of.restype = C.c_int; L.b200enc_device_of.argtypes = [vp]
         L.b200enc_frame_bytes.restype = C.c_size_t; L.b200enc_frame_bytes.argtypes = [vp]
         L.b200enc_last_cuda_error.restype = C.c_int

@@ -339,3 +339,37 @@ def test_video_codec_api_flow(enc):
     assert L.vc_destroy(e) == 0
     if avdec.available():
         assert len(avdec.decode_stream(aus)) == 7
+
+
+def test_openh264_abi_shim_serves_the_wrapper_flow(enc, tmp_path):
+    """media_b200/shim/libopenh264.so behind the openh264 vtable: the stream a client gets through
+    WelsCreateSVCEncoder / InitializeExt / EncodeFrame equals the one the C ABI gives for the same configuration,
+    and SFrameBSInfo is laid out as the reference wrapper expects (VideoEncoderOpenH264.cpp:349-350)"""
+    import subprocess
+    w, h, n, br, gop, force_at = 352, 288, 9, 1_000_000, 30, 5
+    exe = tmp_path / "shim_client"
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "shim_client.cpp"), "-ldl", "-o", str(exe)])
+    c = Content("A", w, h)
+    frames = [c.frame(t) for t in range(n)]
+    (tmp_path / "in.i420").write_bytes(b"".join(f.tobytes() for f in frames))
+    lib = os.path.join(ROOT, "media_b200", "shim", "libopenh264.so")
+    subprocess.check_call([str(exe), lib, str(tmp_path / "in.i420"), str(w), str(h), str(n), str(br), str(gop), str(force_at),
+                           str(tmp_path / "out.h264"), str(tmp_path / "out.info")])
+    s = enc.Session(w, h, fps=30, bitrate=br, gop=gop, const_qp=-1, device=0)
+    want = []
+    for t, f in enumerate(frames):
+        if t == force_at:
+            s.force_idr()
+        want.append(s.encode(f)[0])
+    s.close()
+    got = (tmp_path / "out.h264").read_bytes()
+    assert got == b"".join(want)
+    rows = [l.split() for l in (tmp_path / "out.info").read_text().splitlines()]
+    for t in range(n):
+        _, ftype, size, layers, nals, nal_sum, l0type = (int(x) for x in rows[t])
+        idr = t in (0, force_at)
+        assert size == len(want[t]) == nal_sum
+        assert (ftype, layers, nals, l0type) == ((1, 2, 3, 0) if idr else (3, 1, 1, 1))    # IDR: [SPS PPS] + [slice]; P: [slice]
+    assert rows[n][0] == "ps" and int(rows[n][2]) == 1 and int(rows[n][3]) == 2
+    if avdec.available():
+        assert len(avdec.decode_stream(want)) == n

@@ -106,3 +106,64 @@ def test_session_sharding_over_gloo_world_size_2(tmp_path):
     ids = sorted(sum((r["mine"] for r in rows), []))
     assert ids == list(range(11)) and all(r["t"] == 2.0 and r["tot"] == 11 for r in rows)
     assert abs(len(rows[0]["mine"]) - len(rows[1]["mine"])) <= 1
+
+
+REF = "/root/reference"
+needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "vendor", "openh264")), reason="reference tree only exists in the authoring container")
+
+
+@needs_reference
+def test_openh264_abi_layout_matches_the_vendored_headers(tmp_path):
+    """include/openh264_abi.h is written from scratch; here it is checked field by field against the reference's vendored
+    openh264 headers (vendor/openh264/codec_api.h, codec_app_def.h)"""
+    src = tmp_path / "layout.cpp"
+    pairs = [("SEncParamExt", "oh264::EncParamExt", [("iPicWidth", "width"), ("iTargetBitrate", "target_bitrate"), ("iRCMode", "rc_mode"), ("fMaxFrameRate", "max_frame_rate"),
+              ("iSpatialLayerNum", "spatial_layers"), ("sSpatialLayers", "layers"), ("uiIntraPeriod", "intra_period"), ("iNumRefFrame", "num_ref"),
+              ("iEntropyCodingModeFlag", "entropy_mode"), ("bEnableFrameSkip", "frame_skip"), ("iMaxBitrate", "max_bitrate"), ("iMaxQp", "max_qp"), ("iMinQp", "min_qp"),
+              ("uiMaxNalSize", "max_nal_size"), ("iMultipleThreadIdc", "multiple_thread_idc"), ("iLoopFilterDisableIdc", "loop_filter_disable_idc"),
+              ("bEnableBackgroundDetection", "background_detection"), ("bEnableSceneChangeDetect", "scene_change_detect"), ("iComplexityMode", "complexity"), ("eSpsPpsIdStrategy", "sps_pps_id_strategy")]),
+             ("SSpatialLayerConfig", "oh264::SpatialLayer", [("iVideoWidth", "width"), ("fFrameRate", "frame_rate"), ("iSpatialBitrate", "bitrate"), ("iMaxSpatialBitrate", "max_bitrate"),
+              ("uiProfileIdc", "profile_idc"), ("uiLevelIdc", "level_idc"), ("iDLayerQp", "dlayer_qp"), ("sSliceArgument", "slice")]),
+             ("SSliceArgument", "oh264::SliceArgument", [("uiSliceMode", "mode"), ("uiSliceNum", "num"), ("uiSliceSizeConstraint", "size_constraint")]),
+             ("SSourcePicture", "oh264::SourcePicture", [("iColorFormat", "color_format"), ("iStride", "stride"), ("pData", "data"), ("iPicWidth", "width"), ("iPicHeight", "height"), ("uiTimeStamp", "timestamp")]),
+             ("SLayerBSInfo", "oh264::LayerBSInfo", [("eFrameType", "frame_type"), ("uiLayerType", "layer_type"), ("iNalCount", "nal_count"), ("pNalLengthInByte", "nal_length"), ("pBsBuf", "bs_buf")]),
+             ("SFrameBSInfo", "oh264::FrameBSInfo", [("iLayerNum", "layer_num"), ("sLayerInfo", "layers"), ("eFrameType", "frame_type"), ("iFrameSizeInBytes", "frame_size"), ("uiTimeStamp", "timestamp")]),
+             ("SEncParamBase", "oh264::EncParamBase", [("iPicWidth", "width"), ("iRCMode", "rc_mode"), ("fMaxFrameRate", "max_frame_rate")]),
+             ("SBitrateInfo", "oh264::BitrateInfo", [("iBitrate", "bitrate")])]
+    body = ['#include <cstddef>', '#include "codec_api.h"', '#define WelsCreateSVCEncoder WelsCreateSVCEncoder_abi', '#define WelsDestroySVCEncoder WelsDestroySVCEncoder_abi', '#include "openh264_abi.h"']
+    for a, b, fields in pairs:
+        body.append(f'static_assert(sizeof({a}) == sizeof({b}), "{a} size");')
+        for fa, fb in fields:
+            body.append(f'static_assert(offsetof({a}, {fa}) == offsetof({b}, {fb}), "{a}.{fa}");')
+    body += ['static_assert((int)videoFormatI420 == oh264::kVideoFormatI420 && (int)videoFrameTypeIDR == oh264::kFrameIDR && (int)videoFrameTypeP == oh264::kFrameP, "enums");',
+             'static_assert((int)RC_OFF_MODE == oh264::kRcOff && (int)RC_BITRATE_MODE == oh264::kRcBitrate && (int)SM_FIXEDSLCNUM_SLICE == oh264::kSliceFixedNum, "enums");',
+             'static_assert((int)ENCODER_OPTION_DATAFORMAT == oh264::kOptDataFormat && (int)ENCODER_OPTION_BITRATE == oh264::kOptBitrate && (int)ENCODER_OPTION_RC_MODE == oh264::kOptRcMode && (int)ENCODER_OPTION_FRAME_RATE == oh264::kOptFrameRate, "enums");',
+             'static_assert((int)NON_VIDEO_CODING_LAYER == oh264::kLayerNonVcl && MAX_LAYER_NUM_OF_FRAME == oh264::kMaxLayers, "enums");', 'int main() { return 0; }']
+    src.write_text("\n".join(body))
+    subprocess.check_call(["g++", "-std=c++14", "-I", os.path.join(REF, "vendor", "openh264"), "-I", os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "layout")])
+
+
+@needs_reference
+def test_unmodified_reference_wrapper_loads_the_shim(built, tmp_path):
+    """the reference's own VideoCodecApi.cpp + VideoEncoderOpenH264.cpp, compiled untouched from /root/reference, dlopen
+    "libopenh264.so" = our shim, create the encoder through its vtable and read the defaults; without a GPU InitializeExt
+    then fails and the wrapper reports VIDEO_ENCODER_INIT_FAIL (on a B200 the same flow encodes: see the GPU shim test)"""
+    host = os.path.join(ROOT, "media_b200", "host")
+    srcs = [os.path.join(REF, p) for p in ("video_codec/VideoCodecApi.cpp", "video_codec/VideoEncoderOpenH264.cpp", "video_codec/VideoEncoderNetint.cpp",
+                                           "common/log/MediaLog.cpp", "common/log/MediaLogManager.cpp", "common/prop/Property.cpp")]
+    inc = [os.path.join(host, "shim")] + [os.path.join(REF, p) for p in ("video_codec", "common/log", "common/prop", "vendor/openh264", "vendor/netint")]
+    drv = tmp_path / "drv.cpp"
+    drv.write_text('#include "VideoCodecApi.h"\n#include <sys/system_properties.h>\n#include <cstdio>\n'
+                   'int main() { const char *kv[][2] = {{"ro.vmi.demo.video.encode.format","0"},{"ro.sys.vmi.cloudphone","video"},{"ro.hardware.width","1280"},'
+                   '{"ro.hardware.height","720"},{"ro.hardware.fps","30"},{"persist.vmi.video.encode.bitrate","4000000"},{"persist.vmi.video.encode.gopsize","30"},'
+                   '{"persist.vmi.video.encode.profile","baseline"}};\n for (auto &p : kv) __system_property_set(p[0], p[1]);\n'
+                   ' VideoEncoder *e = nullptr; unsigned c = CreateVideoEncoder(&e); unsigned i = e ? e->InitEncoder() : 99;\n'
+                   ' printf("create=%u init=%u\\n", c, i); if (e) DestroyVideoEncoder(e); return 0; }\n')
+    exe = tmp_path / "drv"
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-w"] + [f"-I{i}" for i in inc] + srcs + [os.path.join(host, "PropertyStore.cpp"), str(drv), "-ldl", "-o", str(exe)])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "media_b200", "shim") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([str(exe)], env=env, capture_output=True, text=True, timeout=120)
+    assert "create=0" in out.stdout, out.stdout + out.stderr
+    import torch
+    assert ("init=0" if torch.cuda.is_available() else "init=2") in out.stdout, out.stdout + out.stderr
+    assert "load openh264 shared lib failed" not in (out.stdout + out.stderr)
