@@ -153,6 +153,10 @@ static __device__ __constant__ uint8_t c_tc0[52][3] = {
 static __device__ __constant__ uint8_t c_cbp_inter[48] = {
      0,  2,  3,  7,  4,  8, 17, 13,  5, 18,  9, 14, 10, 15, 16, 11,  1, 32, 33, 36, 34, 37, 44, 40, 35, 45, 38, 41, 39, 42, 43, 19,
      6, 24, 25, 20, 26, 21, 46, 28, 27, 47, 22, 29, 23, 30, 31, 12 };
+// Table 9-4 me(v) for Intra_4x4 macroblocks, ChromaArrayType 1: cbp -> codeNum
+static __device__ __constant__ uint8_t c_cbp_intra[48] = {
+     3, 29, 30, 17, 31, 18, 37,  8, 32, 38, 19,  9, 20, 10, 11,  2, 16, 33, 34, 21, 35, 22, 39,  4, 36, 40, 23,  5, 24,  6,  7,  1,
+    41, 42, 43, 25, 44, 26, 46, 12, 45, 47, 27, 13, 28, 14, 15,  0 };
 // Lagrangian, round(2^((qp-12)/6)) floored at 1 (encoder-side choice)
 static __device__ __constant__ uint8_t c_lambda[52] = {
      1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  1,  2,  2,  2,  2,  3,  3,  3,  4,  4,  4,

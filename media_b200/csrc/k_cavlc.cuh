@@ -189,6 +189,22 @@ template <bool WRITE> __device__ void code_mb_header(BitSink<WRITE> &bs, const S
         bs.ue((uint32_t)((s.is_idr ? 0 : 5) + 1 + mi->i16_mode + 4 * cc + (cl ? 12 : 0)));
         bs.ue(mi->chroma_mode);
         bs.se(0);
+    } else if (mi->mb_type == MB_I4x4) {
+        // I_NxN (transform_8x8_mode_flag is 0 in the PPS): prev_intra4x4_pred_mode_flag / rem_intra4x4_pred_mode per block, 7.3.5.1, 8.3.1.1
+        bs.ue(s.is_idr ? 0u : 5u);
+        const bool left = mx > 0, top = !row_is_slice_top(g, my);
+        const MbInfo *ml = mi - 1, *mt = mi - g.mbw;
+        const bool l4 = left && ml->mb_type == MB_I4x4, t4 = top && mt->mb_type == MB_I4x4;
+        for (int k = 0; k < 16; k++) {
+            const int bx = blk_x(k), by = blk_y(k);
+            const int ma = bx > 0 ? mi->i4_mode[xy2blk(bx - 1, by)] : !left ? -1 : l4 ? ml->i4_mode[xy2blk(3, by)] : 2;
+            const int mb_ = by > 0 ? mi->i4_mode[xy2blk(bx, by - 1)] : !top ? -1 : t4 ? mt->i4_mode[xy2blk(bx, 3)] : 2;
+            const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_), m = mi->i4_mode[k];
+            if (m == pm) bs.put(1, 1); else bs.put(4, (uint32_t)(m < pm ? m : m - 1));
+        }
+        bs.ue(mi->chroma_mode);
+        bs.ue(c_cbp_intra[mi->cbp]);
+        if (mi->cbp) bs.se(0);
     } else {
         int pmx, pmy, skx, sky; predict_mv(s, g, mx, my, pmx, pmy, skx, sky);
         bs.ue(0);

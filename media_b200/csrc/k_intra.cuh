@@ -1,13 +1,14 @@
 // media_b200/csrc/k_intra.cuh -- Intra_16x16 macroblocks on a macroblock wavefront (phase C of DESIGN.md 3).
 //
 // Role inside the reference: intra prediction, mode decision, transform and reconstruction inside
-// ISVCEncoder::EncodeFrame (video_codec/VideoEncoderOpenH264.cpp:344; openh264's WelsMdI16x16,
-// WelsI16x16LumaPred*, WelsIChromaPred*, WelsHadamardT4Dc, WelsDequantIHadamard4x4 in the absent libopenh264).
+// ISVCEncoder::EncodeFrame (video_codec/VideoEncoderOpenH264.cpp:344; openh264's WelsMdI16x16, WelsMdI4x4,
+// WelsI16x16LumaPred*, WelsI4x4LumaPred*, WelsIChromaPred*, WelsHadamardT4Dc, WelsDequantIHadamard4x4 in the absent libopenh264).
 // One warp owns one macroblock row of one session; rows are handed out through an atomic ticket so that a
 // warp only ever waits on a row that started earlier. Lanes 0-15 own the 16 luma 4x4 blocks, lanes 16-23 the
 // 8 chroma blocks; luma and chroma predictors share one code path parameterised per lane.
 #pragma once
 #include "h264_dev.cuh"
+#include "k_me.cuh"
 
 namespace b200 {
 
@@ -54,7 +55,151 @@ __device__ __forceinline__ void hadamard16(int v[16])
     }
 }
 
-struct IntraSmem { uint8_t top[3][20], left[3][20]; };   // index 0 = the corner sample p[-1,-1]; [comp]
+// top/left: index 0 = the corner sample p[-1,-1]; luma top also carries the 4 samples of the MB above-right (17..20).
+// nb: luma reconstruction of the MB being coded as Intra_4x4 with its border, 17 rows x 24 bytes: sample (x,y) at
+// (y+1)*24 + 4 + x, x in [-1,19] on row y = -1, x in [-1,15] below. F: the filtered edge of one 4x4 block (see c_i4_idx).
+struct IntraSmem {
+    uint8_t top[3][24], left[3][20];
+    uint32_t nb[17 * 6];
+    uint32_t srcw[64];
+    uint8_t F[48];
+    int8_t mg[28];            // Intra4x4PredMode grid, 5x5: row 0 / column 0 = neighbouring MBs (-1 unavailable, 2 not Intra_4x4)
+};
+
+// Intra_4x4 predictors (8.3.1.2.1-9) as lookups into the block's filtered edge. Edge E[0..14] = L3 L3 L2 L1 L0 X T0..T7 T7
+// (left column bottom-up, corner, top row, end samples doubled); F[i] = E[i], F[16+i] = (E[i]+E[i+1]+1)>>1,
+// F[32+i] = (E[i]+2E[i+1]+E[i+2]+2)>>2, F[47] = DC. Entry [mode][y] packs the four F indices of row y, x = 0 in the low byte.
+static __device__ __constant__ uint32_t c_i4_idx[9][4] = {
+    { 0x09080706u, 0x09080706u, 0x09080706u, 0x09080706u },   // 0 vertical
+    { 0x04040404u, 0x03030303u, 0x02020202u, 0x01010101u },   // 1 horizontal
+    { 0x2f2f2f2fu, 0x2f2f2f2fu, 0x2f2f2f2fu, 0x2f2f2f2fu },   // 2 DC
+    { 0x29282726u, 0x2a292827u, 0x2b2a2928u, 0x2c2b2a29u },   // 3 diagonal down-left
+    { 0x27262524u, 0x26252423u, 0x25242322u, 0x24232221u },   // 4 diagonal down-right
+    { 0x18171615u, 0x27262524u, 0x17161523u, 0x26252422u },   // 5 vertical-right
+    { 0x26252414u, 0x24142313u, 0x23132212u, 0x22122111u },   // 6 horizontal-down
+    { 0x19181716u, 0x29282726u, 0x1a191817u, 0x2a292827u },   // 7 vertical-left
+    { 0x21122213u, 0x20112112u, 0x01012011u, 0x01010101u },   // 8 horizontal-up
+};
+#define I4_BIAS_BITS 24       /* fixed cost of choosing Intra_4x4 (16 mode flags), in lambda units */
+
+// Trial coding of the luma of one MB as Intra_4x4: the 16 blocks in decoding order; lanes 0-8 evaluate the nine predictors of a
+// block (SATD + lambda * mode bits, key = cost << 4 | mode), the winner is transformed, quantised and reconstructed at once
+// (the next block predicts from it). Gives up as soon as the running cost reaches `limit` (the Intra_16x16 SATD).
+// On success the levels, nnz and reconstruction are in place; returns true, the luma cbp and the 16 modes (4 bits each).
+__device__ bool intra_try_i4x4(const Sess &s, const Geom &g, IntraSmem &sm, int mx, int my, int lane, int limit,
+                               bool top, bool left, int &cbp_luma, unsigned long long &modes)
+{
+    const int wc = g.wc, mb = my * g.mbw + mx, qp = s.qp, lambda = c_lambda[qp];
+    const bool topright = top && mx + 1 < g.mbw;
+    MbInfo *mi = s.mbi + mb; MbCoef *co = s.coef + mb;
+    uint8_t *nb = reinterpret_cast<uint8_t *>(sm.nb);
+    if (lane < 21) nb[3 + lane] = sm.top[0][lane];
+    if (lane < 16) nb[(lane + 1) * 24 + 3] = sm.left[0][lane + 1];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int wi = lane + 32 * i;
+        sm.srcw[wi] = *reinterpret_cast<const uint32_t *>(s.src[0] + (size_t)(my * 16 + (wi >> 2)) * wc + mx * 16 + (wi & 3) * 4);
+    }
+    if (lane < 25) {
+        const int gy = lane / 5, gx = lane - gy * 5;
+        int v = 2;
+        if (gy == 0 && gx > 0) { v = -1; if (top) { const MbInfo *mt = mi - g.mbw; v = __ldcg(&mt->mb_type) == MB_I4x4 ? (int)__ldcg(&mt->i4_mode[xy2blk(gx - 1, 3)]) : 2; } }
+        else if (gx == 0 && gy > 0) { v = -1; if (left) { const MbInfo *ml = mi - 1; v = __ldcg(&ml->mb_type) == MB_I4x4 ? (int)__ldcg(&ml->i4_mode[xy2blk(3, gy - 1)]) : 2; } }
+        sm.mg[lane] = (int8_t)v;
+    }
+    __syncwarp();
+    const QParam q = make_qparam(qp);
+    uint32_t ix[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++) ix[y] = c_i4_idx[min(lane, 8)][y];
+    int total = lambda * I4_BIAS_BITS;
+    cbp_luma = 0; modes = 0ull;
+#pragma unroll 1
+    for (int b = 0; b < 16; b++) {
+        const int bxb = blk_x(b), byb = blk_y(b), bx = bxb * 4, by = byb * 4;
+        const bool aT = byb > 0 || top, aL = bxb > 0 || left, aX = aT && aL;
+        const bool aTR = byb == 0 ? (bxb < 3 ? top : topright) : !((0xA888u >> b) & 1u);
+        // filtered edge of this block
+        int e = 128;
+        if (lane < 15) {
+            int off;
+            if (lane <= 4) off = (by + (lane == 0 ? 4 : 5 - lane)) * 24 + 3 + bx;
+            else if (lane == 5) off = by * 24 + 3 + bx;
+            else { int t = min(lane - 6, 7); if (!aTR) t = min(t, 3); off = by * 24 + 4 + bx + t; }
+            e = nb[off];
+        }
+        const int e1 = __shfl_down_sync(0xffffffffu, e, 1), e2 = __shfl_down_sync(0xffffffffu, e, 2);
+        if (lane < 15) sm.F[lane] = (uint8_t)e;
+        if (lane < 14) sm.F[16 + lane] = (uint8_t)((e + e1 + 1) >> 1);
+        if (lane < 13) sm.F[32 + lane] = (uint8_t)((e + 2 * e1 + e2 + 2) >> 2);
+        {
+            const int sT = dp4a_us(sm.nb[(by * 24 + 4 + bx) >> 2], 0x01010101u, 0);
+            const int sL = nb[(by + 1) * 24 + 3 + bx] + nb[(by + 2) * 24 + 3 + bx] + nb[(by + 3) * 24 + 3 + bx] + nb[(by + 4) * 24 + 3 + bx];
+            const int dc = aT && aL ? (sT + sL + 4) >> 3 : aT ? (sT + 2) >> 2 : aL ? (sL + 2) >> 2 : 128;
+            if (lane == 15) sm.F[47] = (uint8_t)dc;
+        }
+        __syncwarp();
+        const int ma = sm.mg[(byb + 1) * 5 + bxb], mb_ = sm.mg[byb * 5 + bxb + 1];
+        const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
+        uint32_t P[4], S[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            S[y] = sm.srcw[(by + y) * 4 + bxb];
+            P[y] = (uint32_t)sm.F[ix[y] & 255] | ((uint32_t)sm.F[(ix[y] >> 8) & 255] << 8) | ((uint32_t)sm.F[(ix[y] >> 16) & 255] << 16) | ((uint32_t)sm.F[ix[y] >> 24] << 24);
+        }
+        uint32_t key = 0xffffffffu;
+        {
+            const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
+            int Ts[16];
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(S[y], H[k], 0);
+            const int sat = satd_rows(P, Ts);
+            const bool ok = lane < 9 && (lane == 2 || ((lane == 0 || lane == 3 || lane == 7) ? aT : (lane == 1 || lane == 8) ? aL : aX));
+            if (ok) key = ((uint32_t)(sat + lambda * (lane == pm ? 1 : 4)) << 4) | (uint32_t)lane;
+        }
+        key = warp_min(key);
+        const int wm = key & 15;
+        total += (int)(key >> 4);
+        if (total >= limit) return false;
+#pragma unroll
+        for (int y = 0; y < 4; y++) P[y] = __shfl_sync(0xffffffffu, P[y], wm);
+        // transform, quantise, reconstruct (every lane computes the same block; lanes 0-6 store one piece each)
+        int p[16], c[16];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) { p[y * 4 + x] = (P[y] >> (8 * x)) & 255; c[y * 4 + x] = (int)((S[y] >> (8 * x)) & 255) - p[y * 4 + x]; }
+        fdct4x4(c);
+        __align__(16) int16_t lz[16];
+        const int nnz = quant_dequant4x4(c, lz, q, q.f_intra, false);
+        idct4x4(c);
+        uint32_t R[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x++) w |= (uint32_t)clip255(p[y * 4 + x] + c[y * 4 + x]) << (8 * x);
+            R[y] = w;
+        }
+        if (lane < 4) {
+            const uint32_t r = lane == 0 ? R[0] : lane == 1 ? R[1] : lane == 2 ? R[2] : R[3];
+            sm.nb[((by + lane + 1) * 24 + 4 + bx) >> 2] = r;
+            *reinterpret_cast<uint32_t *>(s.rec[0] + (size_t)(my * 16 + by + lane) * wc + mx * 16 + bx) = r;
+        } else if (lane < 6) {
+            const uint4 lo = reinterpret_cast<uint4 *>(lz)[0], hi = reinterpret_cast<uint4 *>(lz)[1];
+            reinterpret_cast<uint4 *>(co->luma[b])[lane - 4] = lane == 4 ? lo : hi;
+        } else if (lane == 6) {
+            mi->nnz[b] = (uint8_t)nnz;
+            sm.mg[(byb + 1) * 5 + bxb + 1] = (int8_t)wm;
+        }
+        if (nnz) cbp_luma |= 1 << (b >> 2);
+        modes |= (unsigned long long)wm << (4 * b);
+        __syncwarp();
+    }
+    return true;
+}
 
 // predictor kinds shared by luma and chroma: 0 vertical, 1 horizontal, 2 DC, 3 plane (8.3.3 / 8.3.4)
 __device__ __forceinline__ void intra_pred_block(int kind, const uint8_t *T, const uint8_t *L, int bx, int by, int dcv,
@@ -79,15 +224,15 @@ __device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int m
     const bool top = !row_is_slice_top(g, my), left = mx > 0;
     // neighbours from the (pre-deblock) reconstruction; written by other warps / kernels -> L2 loads
     __syncwarp();
-    for (int i = lane; i < 17 + 16 + 2 * (9 + 8); i += 32) {
+    for (int i = lane; i < 21 + 16 + 2 * (9 + 8); i += 32) {
         int comp, idx, is_top;
-        if (i < 33) { comp = 0; is_top = i < 17; idx = is_top ? i : i - 17; }
-        else { int j = i - 33; comp = 1 + j / 17; j %= 17; is_top = j < 9; idx = is_top ? j : j - 9; }
+        if (i < 37) { comp = 0; is_top = i < 21; idx = is_top ? i : i - 21; }
+        else { int j = i - 37; comp = 1 + j / 17; j %= 17; is_top = j < 9; idx = is_top ? j : j - 9; }
         const int n = comp ? 8 : 16, st = comp ? cw : wc, px0 = mx * n, py0 = my * n;
         const uint8_t *r = s.rec[comp];
         if (is_top) {     // idx 0 = corner, 1..n = row above
             int v = 0;
-            if (top && (idx > 0 || left)) v = __ldcg(r + (size_t)(py0 - 1) * st + px0 + idx - 1);
+            if (top && (idx > 0 || left) && (idx <= n || mx + 1 < g.mbw)) v = __ldcg(r + (size_t)(py0 - 1) * st + px0 + idx - 1);
             sm.top[comp][idx] = (uint8_t)v;
             if (idx == 0) sm.left[comp][0] = (uint8_t)v;
         } else {
@@ -144,6 +289,9 @@ __device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int m
     }
     const int mode_id = best & 3, kind = is_luma ? mode_id : (mode_id == 0 ? 2 : mode_id == 2 ? 0 : mode_id);
     const int chroma_mode = __shfl_sync(0xffffffffu, mode_id, 16);
+    // Intra_4x4 on trial against the Intra_16x16 SATD
+    int cbp_luma4 = 0; unsigned long long modes4 = 0ull;
+    const bool use_i4 = intra_try_i4x4(s, g, sm, mx, my, lane, (int)(__shfl_sync(0xffffffffu, best, 0) >> 2), top, left, cbp_luma4, modes4);
 
     int p[16], c[16]; intra_pred_block(kind, T, L, bx, by, dcv, pa, pb, pc, off, p);
 #pragma unroll
@@ -174,7 +322,7 @@ __device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int m
         nnz = quant_dequant4x4(c, lz, q, q.f_intra, true);
         c[0] = dcY;
         const uint8_t inv_zz[16] = { 0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15 };
-        co->luma_dc[inv_zz[ps]] = (int16_t)lev;
+        co->luma_dc[inv_zz[ps]] = use_i4 ? (int16_t)0 : (int16_t)lev;
     } else if (active) {
         const QParam qc = make_qparam(c_chroma_qp[qp]);
         const int pl = comp - 1;
@@ -190,7 +338,7 @@ __device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int m
         if (cb == 0) *reinterpret_cast<uint2 *>(co->chroma_dc[pl]) = make_uint2((uint32_t)(uint16_t)lv[0] | ((uint32_t)(uint16_t)lv[1] << 16),
                                                                               (uint32_t)(uint16_t)lv[2] | ((uint32_t)(uint16_t)lv[3] << 16));
     }
-    if (active) {
+    if (active && !(is_luma && use_i4)) {
         idct4x4(c);
         uint4 *dst = reinterpret_cast<uint4 *>(is_luma ? co->luma[b] : co->chroma_ac[comp - 1][cb]);
         dst[0] = reinterpret_cast<uint4 *>(lz)[0]; dst[1] = reinterpret_cast<uint4 *>(lz)[1];
@@ -206,10 +354,14 @@ __device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int m
     }
     const uint32_t nzmask = __ballot_sync(0xffffffffu, nnz != 0), dcmask = __ballot_sync(0xffffffffu, dc_nz);
     if (lane == 0) {
-        int cbp = (nzmask & 0xffff) ? 15 : 0;
+        int cbp = use_i4 ? cbp_luma4 : ((nzmask & 0xffff) ? 15 : 0);
         cbp |= ((nzmask >> 16) & 255) ? 32 : (dcmask ? 16 : 0);
-        reinterpret_cast<uint32_t *>(mi)[0] = (uint32_t)MB_I16x16 | ((uint32_t)mode_id << 8) | ((uint32_t)chroma_mode << 16) | ((uint32_t)cbp << 24);
-    } else if (lane < 6) reinterpret_cast<uint32_t *>(mi)[lane] = 0;
+        reinterpret_cast<uint32_t *>(mi)[0] = (use_i4 ? (uint32_t)MB_I4x4 : (uint32_t)MB_I16x16 | ((uint32_t)mode_id << 8)) | ((uint32_t)chroma_mode << 16) | ((uint32_t)cbp << 24);
+    } else if (lane == 1) reinterpret_cast<uint32_t *>(mi)[1] = 0;
+    else if (lane < 6) {     // i4_mode[16]: one byte per block
+        const uint32_t nib = use_i4 ? (uint32_t)(modes4 >> (16 * (lane - 2))) & 0xffffu : 0u;
+        reinterpret_cast<uint32_t *>(mi)[lane] = (nib & 15u) | ((nib & 0xf0u) << 4) | ((nib & 0xf00u) << 8) | ((nib & 0xf000u) << 12);
+    }
 }
 
 // grid: ceil(sessions * mbh / WAVE_WARPS) CTAs of WAVE_WARPS warps

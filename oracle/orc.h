@@ -57,6 +57,7 @@ typedef struct {
     int search_range;        /* full-pel, multiple of 4: 16/32/64 */
     int level_idc;           /* 0 = derive from size/fps */
     int fps;
+    int no_i4x4;             /* 1: Intra_16x16 only (quality A/B runs in tests; the product has no such switch) */
 } OrcConfig;
 
 OrcEncoder *orc_create(const OrcConfig *cfg);
@@ -104,6 +105,8 @@ int  orc_interp_chroma(const uint8_t *ref, int stride, int w, int h, int x8, int
 /* in-place deblocking of a whole coded frame given per-MB info (8.7) */
 void orc_deblock_frame(uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs, int mbw, int mbh,
                        const OrcMbInfo *mbi, int qp);
+/* Intra_4x4 predictor of one block (8.3.1.2); avail bits: 1 top, 2 left, 4 corner, 8 top-right. Returns 0 if the mode is unavailable */
+int  orc_pred_i4(const uint8_t *r, int stride, int mode, int avail, uint8_t *pred16);
 /* emulation prevention: returns output length */
 int  orc_escape_rbsp(const uint8_t *in, int n, uint8_t *out);
 

@@ -421,7 +421,137 @@ static int satd8x8(const uint8_t *a, int sa, const uint8_t *b, int sb)
     return orc_satd4x4(a, sa, b, sb) + orc_satd4x4(a + 4, sa, b + 4, sb) + orc_satd4x4(a + 4 * sa, sa, b + 4 * sb, sb) + orc_satd4x4(a + 4 * sa + 4, sa, b + 4 * sb + 4, sb);
 }
 
-/* ---- Phase C: one Intra_16x16 MB (roles of WelsMdI16x16, WelsIChromaPred*, WelsHadamardT4Dc_c, WelsDequantIHadamard4x4_c) ---- */
+/* ---- Intra_4x4 prediction, 8.3.1.2.1-9. r points at the block's top-left sample inside the (pre-deblock) reconstruction;
+ * avail: bit0 top row, bit1 left column, bit2 corner, bit3 top-right (when top is available but top-right is not,
+ * p[4..7,-1] are substituted by p[3,-1], 8.3.1.2). Returns 0 when the mode's neighbours are missing. ---- */
+#define I4_AV_T 1
+#define I4_AV_L 2
+#define I4_AV_X 4
+#define I4_AV_TR 8
+static int pred_i4(const uint8_t *r, int st, int mode, int avail, uint8_t *p /*16*/)
+{
+    int T[8], L[4], X = 128, top = avail & I4_AV_T, left = avail & I4_AV_L, corner = avail & I4_AV_X;
+    for (int i = 0; i < 8; i++) T[i] = 128;
+    for (int i = 0; i < 4; i++) L[i] = 128;
+    if (top) { for (int i = 0; i < 4; i++) T[i] = r[i - st]; for (int i = 4; i < 8; i++) T[i] = (avail & I4_AV_TR) ? r[i - st] : T[3]; }
+    if (left) for (int i = 0; i < 4; i++) L[i] = r[i * st - 1];
+    if (corner) X = r[-st - 1];
+#define PT(i) ((i) < 0 ? X : T[i])      /* p[i,-1] */
+#define PL(i) ((i) < 0 ? X : L[i])      /* p[-1,i] */
+    switch (mode) {
+    case 0: if (!top) return 0; for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) p[y * 4 + x] = (uint8_t)T[x]; return 1;
+    case 1: if (!left) return 0; for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) p[y * 4 + x] = (uint8_t)L[y]; return 1;
+    case 2: {
+        int sT = T[0] + T[1] + T[2] + T[3], sL = L[0] + L[1] + L[2] + L[3];
+        int v = top && left ? (sT + sL + 4) >> 3 : top ? (sT + 2) >> 2 : left ? (sL + 2) >> 2 : 128;
+        memset(p, v, 16); return 1; }
+    case 3: if (!top) return 0;
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++)
+            p[y * 4 + x] = (uint8_t)(x == 3 && y == 3 ? (T[6] + 3 * T[7] + 2) >> 2 : (T[x + y] + 2 * T[x + y + 1] + T[x + y + 2] + 2) >> 2);
+        return 1;
+    case 4: if (!(top && left && corner)) return 0;
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++)
+            p[y * 4 + x] = (uint8_t)(x > y ? (PT(x - y - 2) + 2 * PT(x - y - 1) + PT(x - y) + 2) >> 2
+                                   : x < y ? (PL(y - x - 2) + 2 * PL(y - x - 1) + PL(y - x) + 2) >> 2 : (T[0] + 2 * X + L[0] + 2) >> 2);
+        return 1;
+    case 5: if (!(top && left && corner)) return 0;
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) {
+            int z = 2 * x - y, i = x - (y >> 1), v;
+            if (z >= 0 && !(z & 1)) v = (PT(i - 1) + PT(i) + 1) >> 1;
+            else if (z >= 0) v = (PT(i - 2) + 2 * PT(i - 1) + PT(i) + 2) >> 2;
+            else if (z == -1) v = (L[0] + 2 * X + T[0] + 2) >> 2;
+            else v = (PL(y - 1) + 2 * PL(y - 2) + PL(y - 3) + 2) >> 2;
+            p[y * 4 + x] = (uint8_t)v;
+        }
+        return 1;
+    case 6: if (!(top && left && corner)) return 0;
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) {
+            int z = 2 * y - x, i = y - (x >> 1), v;
+            if (z >= 0 && !(z & 1)) v = (PL(i - 1) + PL(i) + 1) >> 1;
+            else if (z >= 0) v = (PL(i - 2) + 2 * PL(i - 1) + PL(i) + 2) >> 2;
+            else if (z == -1) v = (L[0] + 2 * X + T[0] + 2) >> 2;
+            else v = (PT(x - 1) + 2 * PT(x - 2) + PT(x - 3) + 2) >> 2;
+            p[y * 4 + x] = (uint8_t)v;
+        }
+        return 1;
+    case 7: if (!top) return 0;
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) {
+            int i = x + (y >> 1);
+            p[y * 4 + x] = (uint8_t)((y & 1) ? (T[i] + 2 * T[i + 1] + T[i + 2] + 2) >> 2 : (T[i] + T[i + 1] + 1) >> 1);
+        }
+        return 1;
+    default: if (!left) return 0;
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) {
+            int z = x + 2 * y, i = y + (x >> 1), v;
+            if (z > 5) v = L[3];
+            else if (z == 5) v = (L[2] + 3 * L[3] + 2) >> 2;
+            else if (z & 1) v = (L[i] + 2 * L[i + 1] + L[i + 2] + 2) >> 2;
+            else v = (L[i] + L[i + 1] + 1) >> 1;
+            p[y * 4 + x] = (uint8_t)v;
+        }
+        return 1;
+    }
+#undef PT
+#undef PL
+}
+int orc_pred_i4(const uint8_t *r, int st, int mode, int avail, uint8_t *p) { return pred_i4(r, st, mode, avail, p); }
+
+/* predIntra4x4PredMode of block b (8.3.1.1): min of the left and upper blocks' modes; DC when a neighbouring MB is missing
+ * (then for both) or is not Intra_4x4 (constrained_intra_pred_flag = 0) */
+static int i4_pred_mode(const OrcEncoder *e, int mx, int my, int b)
+{
+    const OrcMbInfo *m = &e->mbi[my * e->mbw + mx];
+    int bx = BLK_X[b], by = BLK_Y[b], ma, mb_;
+    static const uint8_t XY2B[4][4] = { { 0, 1, 4, 5 }, { 2, 3, 6, 7 }, { 8, 9, 12, 13 }, { 10, 11, 14, 15 } };
+    if (bx > 0) ma = m->i4_mode[XY2B[by][bx - 1]];
+    else if (mx == 0) return 2;
+    else ma = (m - 1)->mb_type == ORC_MB_I4x4 ? (m - 1)->i4_mode[XY2B[by][3]] : 2;
+    if (by > 0) mb_ = m->i4_mode[XY2B[by - 1][bx]];
+    else if (row_is_slice_top(e, my)) return 2;
+    else mb_ = (m - e->mbw)->mb_type == ORC_MB_I4x4 ? (m - e->mbw)->i4_mode[XY2B[3][bx]] : 2;
+    return ma < mb_ ? ma : mb_;
+}
+#define ORC_I4_BIAS_BITS 24   /* fixed cost of choosing Intra_4x4 (16 mode flags), in lambda units */
+
+/* Try Intra_4x4 on the luma of one MB: blocks in decoding order, each picks argmin of key = ((SATD + lambda*modebits) << 4) | mode
+ * (modebits 1 when the mode equals its prediction, else 4), is transformed/quantised/reconstructed at once because the next
+ * block predicts from it. Returns the total cost; fills i4_mode, luma levels, nnz, cbp luma bits; reconstruction in e->rec. */
+static int code_intra4x4_luma(OrcEncoder *e, int mx, int my, int qp, int lambda)
+{
+    int mb = my * e->mbw + mx, st = e->wc; OrcMbInfo *mi = &e->mbi[mb]; OrcMbCoef *co = &e->coef[mb];
+    int top = !row_is_slice_top(e, my), left = mx > 0, topright = top && mx + 1 < e->mbw;
+    const uint8_t *s = e->src[0] + (size_t)my * 16 * st + mx * 16; uint8_t *r = e->rec[0] + (size_t)my * 16 * st + mx * 16;
+    int total = lambda * ORC_I4_BIAS_BITS, cbp = 0;
+    mi->mb_type = ORC_MB_I4x4;    /* so that i4_pred_mode() of later blocks sees this MB's own modes */
+    for (int b = 0; b < 16; b++) {
+        int bx = BLK_X[b], by = BLK_Y[b], avail = 0;
+        if (by > 0 || top) avail |= I4_AV_T;
+        if (bx > 0 || left) avail |= I4_AV_L;
+        if ((by > 0 || top) && (bx > 0 || left)) avail |= I4_AV_X;
+        if (by == 0 ? (bx < 3 ? top : topright) : (bx < 3 && b != 3 && b != 11 && b != 7 && b != 13 && b != 15)) avail |= I4_AV_TR;
+        if (b == 3 || b == 11) avail &= ~I4_AV_TR;
+        const uint8_t *sb = s + by * 4 * st + bx * 4; uint8_t *rb = r + by * 4 * st + bx * 4;
+        int pm = i4_pred_mode(e, mx, my, b); uint32_t best = 0xffffffffu; uint8_t pred[16], bp[16];
+        for (int m = 0; m < 9; m++) {
+            if (!pred_i4(rb, st, m, avail, pred)) continue;
+            uint32_t key = ((uint32_t)(orc_satd4x4(sb, st, pred, 4) + lambda * (m == pm ? 1 : 4)) << 4) | (uint32_t)m;
+            if (key < best) { best = key; memcpy(bp, pred, 16); }
+        }
+        mi->i4_mode[b] = (uint8_t)(best & 15); total += (int)(best >> 4);
+        int16_t res[16], c[16]; int32_t d[16], rr[16];
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) res[y * 4 + x] = (int16_t)(sb[y * st + x] - bp[y * 4 + x]);
+        orc_dct4x4(res, c);
+        int n = orc_quant4x4(c, co->luma[b], qp, 1, 0);
+        mi->nnz[b] = (uint8_t)n; if (n) cbp |= 1 << (b >> 2);
+        orc_dequant4x4(co->luma[b], d, qp, 0); orc_idct4x4(d, rr);
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) rb[y * st + x] = (uint8_t)clip255(bp[y * 4 + x] + rr[y * 4 + x]);
+    }
+    mi->cbp = (uint8_t)cbp;
+    return total;
+}
+
+/* ---- Phase C: one intra MB (roles of WelsMdI16x16, WelsMdI4x4, WelsIChromaPred*, WelsHadamardT4Dc_c, WelsDequantIHadamard4x4_c).
+ * Intra_16x16 mode by SATD; Intra_4x4 is coded on trial and kept when its cost is below the Intra_16x16 SATD. ---- */
 static void code_intra_mb(OrcEncoder *e, int mx, int my, int qp)
 {
     int mb = my * e->mbw + mx, st = e->wc, cs = st / 2; OrcMbInfo *mi = &e->mbi[mb]; OrcMbCoef *co = &e->coef[mb];
@@ -435,7 +565,12 @@ static void code_intra_mb(OrcEncoder *e, int mx, int my, int qp)
         uint32_t key = ((uint32_t)orc_satd16x16(s, st, pred, 16) << 2) | (uint32_t)m;
         if (key < best) { best = key; mode = m; memcpy(best_pred, pred, 256); }
     }
-    mi->mb_type = ORC_MB_I16x16; mi->i16_mode = (uint8_t)mode; mi->mv[0] = mi->mv[1] = 0;
+    mi->mv[0] = mi->mv[1] = 0; mi->i16_mode = 0;
+    int use_i4 = e->cfg.no_i4x4 ? 0 : code_intra4x4_luma(e, mx, my, qp, LAMBDA_TAB[qp]) < (int)(best >> 2);
+    int luma_cbp = mi->cbp & 15;
+    if (!use_i4) {
+    memset(co, 0, sizeof *co); memset(mi->i4_mode, 0, 16);
+    mi->mb_type = ORC_MB_I16x16; mi->i16_mode = (uint8_t)mode;
     /* luma: 16 forward transforms, DC Hadamard, quant, and the normative inverse (8.5.2, 8.5.10, 8.5.12) */
     int16_t c[16][16]; int dcm[16], hd[16], any_ac = 0;
     for (int b = 0; b < 16; b++) {
@@ -460,6 +595,8 @@ static void code_intra_mb(OrcEncoder *e, int mx, int my, int qp)
         orc_idct4x4(d, rr);
         for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) r[(by + y) * st + bx + x] = (uint8_t)clip255(best_pred[(by + y) * 16 + bx + x] + rr[y * 4 + x]);
     }
+    luma_cbp = any_ac ? 15 : 0;
+    }
     /* chroma mode: SATD over both planes, key = cost<<2 | mode */
     const uint8_t *su = e->src[1] + (size_t)my * 8 * cs + mx * 8, *sv = e->src[2] + (size_t)my * 8 * cs + mx * 8;
     const uint8_t *ru = e->rec[1] + (size_t)my * 8 * cs + mx * 8, *rv = e->rec[2] + (size_t)my * 8 * cs + mx * 8;
@@ -472,7 +609,7 @@ static void code_intra_mb(OrcEncoder *e, int mx, int my, int qp)
     }
     mi->chroma_mode = (uint8_t)cmode;
     int ccbp = code_chroma(e, mx, my, best_pc, qp, 1);
-    mi->cbp = (uint8_t)((any_ac ? 15 : 0) | (ccbp << 4));
+    mi->cbp = (uint8_t)(luma_cbp | (ccbp << 4));
 }
 
 /* ---- Phase D: luma MV prediction for a 16x16 partition (8.4.1.3) and the P_Skip vector (8.4.1.1) ---- */
@@ -530,6 +667,16 @@ static void write_mb(OrcEncoder *e, BitWriter *b, int mx, int my, int is_p)
         bw_se(b, 0);                                           /* mb_qp_delta */
         orc_write_residual_block(b, co->luma_dc, 16, luma_nc(e, mx, my, 0));
         if (cl) for (int k = 0; k < 16; k++) orc_write_residual_block(b, co->luma[k] + 1, 15, luma_nc(e, mx, my, k));
+    } else if (mi->mb_type == ORC_MB_I4x4) {
+        bw_ue(b, (uint32_t)(is_p ? 5 : 0));                    /* I_NxN; transform_8x8_mode_flag is 0 in the PPS */
+        for (int k = 0; k < 16; k++) {                         /* prev_intra4x4_pred_mode_flag / rem_intra4x4_pred_mode, 7.3.5.1 */
+            int pm = i4_pred_mode(e, mx, my, k), m = mi->i4_mode[k];
+            if (m == pm) bw_put(b, 1, 1); else { bw_put(b, 1, 0); bw_put(b, 3, (uint32_t)(m < pm ? m : m - 1)); }
+        }
+        bw_ue(b, mi->chroma_mode);
+        bw_ue(b, CBP_TO_CODENUM_INTRA[mi->cbp]);
+        if (mi->cbp) bw_se(b, 0);
+        for (int k = 0; k < 16; k++) if (cl & (1 << (k >> 2))) orc_write_residual_block(b, co->luma[k], 16, luma_nc(e, mx, my, k));
     } else {
         int pmx, pmy, sx, sy; predict_mv(e, mx, my, &pmx, &pmy, &sx, &sy);
         bw_ue(b, 0);                                           /* P_L0_16x16 */

@@ -53,7 +53,7 @@ def test_every_stage_matches_the_oracle(enc, orc, w, h, kind, qp, slices, sr, fr
             inter = o.mb_info()["mb_type"] != 1
             assert np.array_equal(g.stage("inter_cost"), o.inter_cost())
         gi, oi = g.stage("mbinfo"), o.mb_info()
-        for fld in ("mb_type", "i16_mode", "chroma_mode", "cbp", "mv", "nnz"):
+        for fld in ("mb_type", "i16_mode", "chroma_mode", "cbp", "mv", "i4_mode", "nnz"):
             assert np.array_equal(gi[fld], oi[fld]), f"frame {t} mbinfo.{fld}"
         gc, oc = g.stage("mbcoef"), o.mb_coef()
         for fld in ("luma", "luma_dc", "chroma_dc", "chroma_ac"):

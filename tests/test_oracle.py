@@ -96,7 +96,7 @@ def test_product_tables_equal_oracle_tables():
              ("CHROMA_DC_TOTAL_ZEROS_LEN", "c_cdc_total_zeros_len"), ("CHROMA_DC_TOTAL_ZEROS_BITS", "c_cdc_total_zeros_bits"),
              ("RUN_BEFORE_LEN", "c_run_before_len"), ("RUN_BEFORE_BITS", "c_run_before_bits"), ("ZIGZAG4x4", "c_zigzag"), ("QUANT_MF", "c_quant_mf"),
              ("DEQUANT_V", "c_dequant_v"), ("CHROMA_QP", "c_chroma_qp"), ("DEBLOCK_ALPHA", "c_alpha"), ("DEBLOCK_BETA", "c_beta"), ("DEBLOCK_TC0", "c_tc0"),
-             ("CBP_TO_CODENUM_INTER", "c_cbp_inter"), ("LAMBDA_TAB", "c_lambda")]
+             ("CBP_TO_CODENUM_INTER", "c_cbp_inter"), ("CBP_TO_CODENUM_INTRA", "c_cbp_intra"), ("LAMBDA_TAB", "c_lambda")]
     for a, b in pairs:
         assert nums(o, a) == nums(p, b), (a, b)
 
