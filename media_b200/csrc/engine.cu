@@ -12,6 +12,7 @@
 #include "k_deblock.cuh"
 #include "k_cavlc.cuh"
 #include "k_test.cuh"
+#include <cuda.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -135,6 +136,23 @@ struct RateCtl {
 
 struct KernelTime { const char *name; cudaEvent_t ev0, ev1; };
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+bool encode_tmap(CUtensorMap *out, void *base, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                 uint32_t b0, uint32_t b1, uint32_t b2)
+{
+    typedef CUresult (*Fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                           const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Fn fn = [] {
+        void *p = nullptr; cudaDriverEntryPointQueryResult qr;
+        return cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess ? reinterpret_cast<Fn>(p) : nullptr;
+    }();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = { d0, d1, d2 }, strides[2] = { stride1, stride2 };
+    const cuuint32_t box[3] = { b0, b1, b2 }, es[3] = { 1, 1, 1 };
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 } // namespace
 
 struct b200enc_batch {
@@ -155,7 +173,9 @@ struct b200enc_session {
     uint8_t *d_pool = nullptr; size_t pool_bytes = 0;
     // device buffers (sub-allocated from d_pool)
     uint8_t *input = nullptr, *src[3], *bufA[3], *bufB[3], *rec_pre[3];
-    uint8_t *srcL1, *srcL2, *refL1, *refL2;
+    uint8_t *srcL1, *srcL2, *refL1, *refL2;      // padded pyramid planes (allocation bases)
+    uint8_t *rpl, *rpc[2];                       // padded reference planes: G,b,h,j contiguous; Cb, Cr
+    void *tmaps;                                 // CUtensorMap[3] in HBM
     MbInfo *mbi; MbCoef *coef; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
     uint32_t *mb_bits, *mb_off, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
     uint32_t rbsp_words_per_slice = 0;
@@ -250,7 +270,13 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         if (device_input) d.input = frames[i];
         else { d.input = s->input; CU_TRY(cudaMemcpyAsync(s->input, frames[i], in_bytes, cudaMemcpyHostToDevice, b->stream), return B200ENC_ECUDA); }
         for (int c = 0; c < 3; c++) { d.src[c] = s->src[c]; d.rec[c] = cur[c]; d.ref[c] = ref[c]; }
-        d.srcL1 = s->srcL1; d.srcL2 = s->srcL2; d.refL1 = s->refL1; d.refL2 = s->refL2;
+        {   // padded planes: hand the kernels the address of the interior sample (0,0)
+            const size_t o1 = (size_t)g.p1 * g.s1 + g.p1, o2 = (size_t)g.p2 * g.s2 + g.p2, ol = (size_t)g.lp * g.ls + g.lp, oc = (size_t)g.cp * g.cs + g.cp;
+            const size_t plane = (size_t)g.ls * (g.hc + 2 * g.lp);
+            d.srcL1 = s->srcL1 + o1; d.refL1 = s->refL1 + o1; d.srcL2 = s->srcL2 + o2; d.refL2 = s->refL2 + o2;
+            for (int k = 0; k < 4; k++) d.rpl[k] = s->rpl + k * plane + ol;
+            d.rpc[0] = s->rpc[0] + oc; d.rpc[1] = s->rpc[1] + oc; d.tmaps = s->tmaps;
+        }
         d.mbi = s->mbi; d.coef = s->coef; d.me2 = s->me2; d.me1 = s->me1; d.me0 = s->me0; d.inter_cost = s->inter_cost;
         d.skip_run = s->skip_run; d.mb_bits = s->mb_bits; d.mb_off = s->mb_off; d.mb_slot = s->mb_slot; d.rbsp = s->rbsp; d.slice_bits = s->slice_bits;
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
@@ -271,8 +297,10 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     }
     launches++;
     if (any_p) {
-        pf.begin("k_downsample0"); k_downsample<<<dim3(((g.wc / 8) * (g.hc / 2) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 0); pf.end();
-        pf.begin("k_downsample1"); k_downsample<<<dim3(((g.wc / 16) * (g.hc / 4) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 1); pf.end();
+        pf.begin("k_refplanes"); k_refplanes<<<dim3((g.ls + RP_TW - 1) / RP_TW, (g.hc + 2 * g.lp + RP_TH - 1) / RP_TH, n), 256, 0, st>>>(b->d_sess, g); pf.end();
+        pf.begin("k_refchroma"); k_refchroma<<<dim3(((g.cs / 4) * (g.hc / 2 + 2 * g.cp) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g); pf.end();
+        pf.begin("k_downsample0"); k_downsample<<<dim3((((g.wc / 2 + 2 * g.p1) / 4) * (g.hc / 2 + 2 * g.p1) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 0); pf.end();
+        pf.begin("k_downsample1"); k_downsample<<<dim3((((g.wc / 4 + 2 * g.p2) / 4) * (g.hc / 4 + 2 * g.p2) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 1); pf.end();
         pf.begin("k_me_coarse");
         {
             if (g.search_range <= 16) k_me_coarse<4, 8><<<dim3((nmb + 7) / 8, 1, n), 256, 0, st>>>(b->d_sess, g);
@@ -280,8 +308,8 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
             else k_me_coarse<16, 4><<<dim3((nmb + 3) / 4, 1, n), 128, 0, st>>>(b->d_sess, g);
         }
         pf.end();
-        pf.begin("k_me_fine"); k_me_fine<<<dim3((nmb + ME_WARPS - 1) / ME_WARPS, 1, n), ME_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end();
-        launches += 4;
+        pf.begin("k_me_fine"); k_me_fine<<<dim3((nmb + ME_WARPS - 1) / ME_WARPS, 1, n), ME_WARPS * 32, 0, st>>>(b->d_sess, g, b->d_ctl); pf.end();
+        launches += 6;
     }
     const int wave_ctas = (n * g.mbh + WAVE_WARPS - 1) / WAVE_WARPS;
     pf.begin("k_intra_wave"); k_intra_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
@@ -455,7 +483,7 @@ const char *b200enc_strerror(int code)
     case B200ENC_ECUDA: return "CUDA error during encode";
     case B200ENC_ESIZE: return "input buffer smaller than one frame";
     case B200ENC_EOVERFLOW: return "bitstream larger than the output buffer";
-    case B200ENC_EWAVE: return "wavefront watchdog fired";
+    case B200ENC_EWAVE: return "device watchdog fired (wavefront wait or TMA transaction)";
     default: return "unknown error";
     }
 }
@@ -482,6 +510,13 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
     { const int base = g.mbh / g.num_slices, rem = g.mbh % g.num_slices; int r = 0;
       for (int i = 0; i < g.num_slices; i++) { g.slice_row0[i] = r; r += base + (i < rem); }
       for (int i = g.num_slices; i <= B200_MAX_SLICES; i++) g.slice_row0[i] = r; }
+    {   // borders of the padded planes: the widest reach of a search window / interpolation tap past the picture edge
+        auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+        g.lp = up(c.search_range + 10, 16); g.ls = g.wc + 2 * g.lp;
+        g.cp = g.lp / 2; g.cs = up(g.wc / 2 + 2 * g.cp, 16);
+        g.p1 = g.lp / 2; g.s1 = up(g.wc / 2 + 2 * g.p1, 16);
+        g.p2 = up(c.search_range / 4 + 5, 4); g.s2 = up(g.wc / 4 + 2 * g.p2, 16);
+    }
     s->load = (double)c.width * c.height * c.fps;
     s->device = sched_acquire(c.device, s->load);
     if (s->device < 0) { delete s; return B200ENC_ENODEV; }
@@ -498,7 +533,10 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         auto add = [&](auto &ptr, size_t bytes) { items.push_back({ reinterpret_cast<void **>(&ptr), bytes }); };
         add(s->input, b200enc_frame_bytes(s));
         for (int k = 0; k < 3; k++) { const size_t b = k ? nc : ny; add(s->src[k], b); add(s->bufA[k], b); add(s->bufB[k], b); add(s->rec_pre[k], c.debug ? b : 16); }
-        add(s->srcL1, ny / 4); add(s->refL1, ny / 4); add(s->srcL2, ny / 16); add(s->refL2, ny / 16);
+        const size_t l1 = (size_t)g.s1 * (g.hc / 2 + 2 * g.p1) + 64, l2 = (size_t)g.s2 * (g.hc / 4 + 2 * g.p2) + 64;
+        const size_t lplane = (size_t)g.ls * (g.hc + 2 * g.lp), cplane = (size_t)g.cs * (g.hc / 2 + 2 * g.cp) + 64;
+        add(s->srcL1, l1); add(s->refL1, l1); add(s->srcL2, l2); add(s->refL2, l2);
+        add(s->rpl, 4 * lplane + 256); add(s->rpc[0], cplane); add(s->rpc[1], cplane); add(s->tmaps, 3 * sizeof(CUtensorMap));
         add(s->mbi, nmb * sizeof(MbInfo)); add(s->coef, nmb * sizeof(MbCoef));
         add(s->me2, nmb * 4); add(s->me1, nmb * 4); add(s->me0, nmb * 4); add(s->inter_cost, nmb * 4);
         add(s->skip_run, (nmb + B200_MAX_SLICES) * 4); add(s->mb_bits, nmb * 4); add(s->mb_off, nmb * 4);
@@ -513,6 +551,14 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         size_t off = 0;
         for (auto &it : items) { *it.p = s->d_pool + off; off += align_up(it.bytes, 256); }
         CU_TRY(cudaMemcpy(s->hdr, ps.data(), ps.size(), cudaMemcpyHostToDevice), rc = B200ENC_ECUDA; break);
+        {   // TMA descriptors of the tiles k_me_fine fetches (u8 elements, no swizzle, zero fill outside the tensor)
+            CUtensorMap tm[3];
+            const uint64_t H = (uint64_t)g.hc + 2 * g.lp;
+            if (!encode_tmap(&tm[0], s->src[0], 2, (uint64_t)g.wc, (uint64_t)g.hc, 1, (uint64_t)g.wc, 0, 16, 16, 1) ||
+                !encode_tmap(&tm[1], s->rpl, 2, (uint64_t)g.ls, H, 1, (uint64_t)g.ls, 0, 48, 20, 1) ||
+                !encode_tmap(&tm[2], s->rpl, 3, (uint64_t)g.ls, H, 4, (uint64_t)g.ls, (uint64_t)g.ls * H, 48, 18, 4)) { rc = B200ENC_ENODEV; break; }
+            CU_TRY(cudaMemcpy(s->tmaps, tm, sizeof tm, cudaMemcpyHostToDevice), rc = B200ENC_ECUDA; break);
+        }
         // output buffer: generous bound on a frame (every MB at the CAVLC worst case is ~1.4 KB; 1/2 of raw + 64 KB covers QP >= ~8 content)
         s->out_cap = (uint32_t)align_up(std::max<size_t>(ny * 3 / 2, 1 << 16) + (1 << 16), 256);
         CU_TRY(cudaHostAlloc(&s->h_out, s->out_cap + 256, cudaHostAllocMapped), rc = B200ENC_ENOMEM; break);

@@ -38,6 +38,9 @@ struct Geom {
     int num_slices;
     int slice_row0[B200_MAX_SLICES + 1];
     int search_range;             // full-pel, multiple of 4
+    // padded reference / pyramid planes (edge-replicated borders, so no motion-search or MC read needs clamping):
+    // pad and row stride of the luma reference planes, of the chroma reference planes, and of pyramid levels 1 and 2
+    int lp, ls, cp, cs, p1, s1, p2, s2;
 };
 
 // Per-session, per-frame device descriptor (one array element per session in the batch).
@@ -46,7 +49,11 @@ struct Sess {
     uint8_t *src[3];              // coded-size source planes
     uint8_t *rec[3];              // reconstruction of this frame (deblocked in place at the end)
     uint8_t *ref[3];              // previous frame's deblocked reconstruction
+    // padded planes; every pointer addresses sample (0,0) of the plane's interior, rows are g.ls / g.cs / g.s1 / g.s2 apart
+    uint8_t *rpl[4];              // reference luma: G (full-pel copy), b, h, j half-pel planes (8.4.2.2.1), built once per frame
+    uint8_t *rpc[2];              // reference Cb, Cr
     uint8_t *srcL1, *srcL2, *refL1, *refL2;
+    const void *tmaps;            // CUtensorMap[3] in HBM: source luma (box 16x16), plane G (box 48x20), planes G,b,h,j (box 48x18x4)
     MbInfo *mbi; MbCoef *coef;
     int16_t *me2, *me1, *me0;     // per-level vectors (debug / parity dumps)
     int32_t *inter_cost;
@@ -63,6 +70,9 @@ struct Sess {
     int qp, is_idr, frame_num, idr_pic_id, input_format;
     uint32_t rbsp_words_per_slice, out_cap;
 };
+
+// per-batch control block: wavefront tickets and the error flag (1 wavefront watchdog, 2 TMA transaction timeout)
+struct WaveCtl { int ticket_intra, ticket_dbk, error, pad; };
 
 // ---- normative tables ----
 // Table 9-5 coeff_token: [nC class][4*total_coeff + trailing_ones] (length, bits)

@@ -15,7 +15,6 @@ namespace b200 {
 #define WAVE_WARPS 4
 #define WAVE_TIMEOUT_NS 2000000000ull   /* watchdog: a wait longer than 2 s is an internal error, never a hang */
 
-struct WaveCtl { int ticket_intra, ticket_dbk, error, pad; };
 
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 

@@ -6,6 +6,7 @@
 // macroblock, so the grid is one warp per MB across all sessions of the batch.
 #pragma once
 #include "h264_dev.cuh"
+#include <cstddef>
 
 namespace b200 {
 
@@ -16,21 +17,6 @@ namespace b200 {
 #define ME_FINE_MIN_CTAS 4     /* 64 registers: 4 CTAs of 8 warps per SM (measured 8 % faster than 75-94 registers) */
 #endif
 
-// copy a ww x wh window whose top-left is (x0,y0) from a pw x ph plane into shared memory, clamping coordinates
-// (the reference picture is extended by edge replication, 8.4.2.2.1)
-__device__ __forceinline__ void stage_clamped(uint8_t *dst, int dstride, const uint8_t *__restrict__ plane, int pw, int ph,
-                                              int x0, int y0, int ww, int wh, int lane)
-{
-    for (int r = 0; r < wh; r++) {
-        const uint8_t *row = plane + (size_t)clip3(0, ph - 1, y0 + r) * pw;
-        for (int c = lane; c < ww; c += 32) dst[r * dstride + c] = __ldg(row + clip3(0, pw - 1, x0 + c));
-    }
-}
-__device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *base, int off)
-{
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(base) + (off >> 2);
-    return __funnelshift_r(w[0], w[1], (off & 3) * 8);
-}
 __device__ __forceinline__ uint32_t warp_min(uint32_t v)
 {
 #pragma unroll
@@ -39,35 +25,31 @@ __device__ __forceinline__ uint32_t warp_min(uint32_t v)
 }
 __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
-// fast window staging: aligned 32-bit loads + funnel shift when the window lies inside the plane, byte-wise clamped otherwise
+// Window staging from a PADDED plane (`org` addresses sample (0,0); the border makes every search window addressable, so
+// there is no clamping): aligned 32-bit loads + funnel shift. ww must be a multiple of 4.
 template <int WW, int WH>
-__device__ __forceinline__ void stage_window(uint32_t *dstw, const uint8_t *__restrict__ plane, int pw, int ph, int x0, int y0, int lane)
+__device__ __forceinline__ void stage_window(uint32_t *dstw, const uint8_t *__restrict__ org, int stride, int x0, int y0, int lane)
 {
     constexpr int WPR = WW / 4;
-    if (x0 >= 0 && y0 >= 0 && x0 + WW <= pw && y0 + WH <= ph) {
-        const int sh = (x0 & 3) * 8, pww = pw >> 2;
-        const uint32_t *base = reinterpret_cast<const uint32_t *>(plane + (size_t)y0 * pw + (x0 & ~3));
-        for (int i = lane; i < WPR * WH; i += 32) {
-            const int r = i / WPR, j = i - r * WPR;
-            const uint32_t *p = base + r * pww + j;
-            const uint32_t lo = __ldg(p), hi = sh ? __ldg(p + 1) : 0u;
-            dstw[i] = __funnelshift_r(lo, hi, sh);
-        }
-    } else stage_clamped(reinterpret_cast<uint8_t *>(dstw), WW, plane, pw, ph, x0, y0, WW, WH, lane);
+    const int sh = (x0 & 3) * 8, sw = stride >> 2;
+    const uint32_t *base = reinterpret_cast<const uint32_t *>(org + (ptrdiff_t)y0 * stride + (x0 & ~3));
+    for (int i = lane; i < WPR * WH; i += 32) {
+        const int r = i / WPR, j = i - r * WPR;
+        const uint32_t *p = base + r * sw + j;
+        const uint32_t lo = __ldg(p), hi = sh ? __ldg(p + 1) : 0u;
+        dstw[i] = __funnelshift_r(lo, hi, sh);
+    }
 }
-__device__ __forceinline__ void stage_window_rt(uint32_t *dstw, int W, const uint8_t *__restrict__ plane, int pw, int ph, int x0, int y0, int lane)
+__device__ __forceinline__ void stage_window_rt(uint32_t *dstw, int W, const uint8_t *__restrict__ org, int stride, int x0, int y0, int lane)
 {
-    const int wpr = W >> 2;
-    if (x0 >= 0 && y0 >= 0 && x0 + W <= pw && y0 + W <= ph) {
-        const int sh = (x0 & 3) * 8, pww = pw >> 2;
-        const uint32_t *base = reinterpret_cast<const uint32_t *>(plane + (size_t)y0 * pw + (x0 & ~3));
-        for (int r = 0; r < W; r++)
-            for (int j = lane; j < wpr; j += 32) {
-                const uint32_t *p = base + r * pww + j;
-                const uint32_t lo = __ldg(p), hi = sh ? __ldg(p + 1) : 0u;
-                dstw[r * wpr + j] = __funnelshift_r(lo, hi, sh);
-            }
-    } else stage_clamped(reinterpret_cast<uint8_t *>(dstw), W, plane, pw, ph, x0, y0, W, W, lane);
+    const int wpr = W >> 2, sh = (x0 & 3) * 8, sw = stride >> 2;
+    const uint32_t *base = reinterpret_cast<const uint32_t *>(org + (ptrdiff_t)y0 * stride + (x0 & ~3));
+    for (int r = 0; r < W; r++)
+        for (int j = lane; j < wpr; j += 32) {
+            const uint32_t *p = base + r * sw + j;
+            const uint32_t lo = __ldg(p), hi = sh ? __ldg(p + 1) : 0u;
+            dstw[r * wpr + j] = __funnelshift_r(lo, hi, sh);
+        }
 }
 
 // ---- coarse levels: 1/4 resolution exhaustive search, 1/2 resolution refinement ----
@@ -101,12 +83,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_me_coarse(const Sess *ss, Geom g
     Smem &sm = sm_all[warp];
     const int mx = mb % g.mbw, my = mb / g.mbw;
     const int R4 = g.search_range / 4, span = 2 * R4 + 1, W = 8 + 2 * R4, wpr = W >> 2;
-    const int w2 = g.wc / 4, h2 = g.hc / 4, w1 = g.wc / 2, h1 = g.hc / 2;
 
     // level 2: 8x8 block centred on the MB (origin 4mx-2, 4my-2), all (2R4+1)^2 displacements
-    stage_window<8, 8>(sm.src, s.srcL2, w2, h2, 4 * mx - 2, 4 * my - 2, lane);
-    if (R4 == MAXR4) stage_window<8 + 2 * MAXR4, 8 + 2 * MAXR4>(sm.win[0], s.refL2, w2, h2, 4 * mx - 2 - R4, 4 * my - 2 - R4, lane);
-    else stage_window_rt(sm.win[0], W, s.refL2, w2, h2, 4 * mx - 2 - R4, 4 * my - 2 - R4, lane);
+    stage_window<8, 8>(sm.src, s.srcL2, g.s2, 4 * mx - 2, 4 * my - 2, lane);
+    if (R4 == MAXR4) stage_window<8 + 2 * MAXR4, 8 + 2 * MAXR4>(sm.win[0], s.refL2, g.s2, 4 * mx - 2 - R4, 4 * my - 2 - R4, lane);
+    else stage_window_rt(sm.win[0], W, s.refL2, g.s2, 4 * mx - 2 - R4, 4 * my - 2 - R4, lane);
     __syncwarp();
     make_shifted_copies(sm.win[0], Smem::CW, W * wpr, lane);
     uint32_t sw[16];
@@ -133,8 +114,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_me_coarse(const Sess *ss, Geom g
     // level 1: 8x8 block at (8mx, 8my), +-2 around 2*mv2
     const int cx = 2 * v2x, cy = 2 * v2y;
     __syncwarp();
-    stage_window<8, 8>(sm.src, s.srcL1, w1, h1, 8 * mx, 8 * my, lane);
-    stage_window<12, 12>(sm.win1[0], s.refL1, w1, h1, 8 * mx + cx - 2, 8 * my + cy - 2, lane);
+    stage_window<8, 8>(sm.src, s.srcL1, g.s1, 8 * mx, 8 * my, lane);
+    stage_window<12, 12>(sm.win1[0], s.refL1, g.s1, 8 * mx + cx - 2, 8 * my + cy - 2, lane);
     __syncwarp();
     make_shifted_copies(sm.win1[0], 12 * 3 + 2, 36, lane);
     __syncwarp();
@@ -156,15 +137,48 @@ __global__ void __launch_bounds__(WARPS * 32) k_me_coarse(const Sess *ss, Geom g
 }
 
 // ---- fine level: full-pel refinement, half/quarter-pel SATD refinement, intra estimate, inter coding ----
-#define PL_STRIDE 24                     /* bytes per row of a sample plane: sample (x,y) at (y+1)*24 + x + 4, x in [-1,16] */
-struct FineSmem {
-    uint32_t win[(24 * 24 + 8) / 4];     // 24x24 full-pel window around the level-0 winner (copy 0 of win0 is staged here first)
-    uint32_t win0[3][20 * 5 + 2];         // byte-shifted copies 1..3 of the 20x20 window of the +-2 search
-    uint32_t src[64];                    // source MB, 16x16
-    uint32_t plane[4][18 * PL_STRIDE / 4 + 2]; // G, b, h, j samples at [-1,16]^2 relative to the best full-pel block (8.4.2.2.1)
-    int16_t braw[24 * 18];               // unrounded horizontal half-pel sums, rows [-3,20]
-    uint32_t nb_top[4], nb_left[4];      // SOURCE neighbours for the intra estimate
+// TMA (cp.async.bulk.tensor) moves the three tiles of a macroblock into shared memory: the source MB, the 20x20 full-pel
+// window, and the [-1,16]^2 windows of the four reference planes G, b, h, j in one 3-D box. The innermost TMA coordinate
+// must be 16-byte aligned (measured on B200: any other value raises an illegal-instruction fault), so boxes are 48 bytes
+// wide, start at the aligned column below the window and the kernel carries the 0..15 byte offset.
+#define PL_STRIDE 48                     /* bytes per row of the TMA boxes */
+#define PL_ROWS 18
+struct __align__(128) FineSmem {
+    uint32_t plane[4][PL_ROWS * PL_STRIDE / 4];   // G, b, h, j: sample (x,y) of the best full-pel block at (y+1)*48 + o1 + 4 + x (3456 B)
+    uint32_t src[64];                             // source MB, 16x16 (256 B)
+    uint32_t win[20 * PL_STRIDE / 4];             // 20 rows of plane G around the level-0 centre; window column c at byte o0 + c (960 B)
+    uint32_t nb_top[4], nb_left[4];               // SOURCE neighbours for the intra estimate
+    unsigned long long bar[2];                    // mbarriers: [0] source + window, [1] planes
+    uint32_t pad_[20];
 };
+static_assert(sizeof(FineSmem) % 128 == 0 && offsetof(FineSmem, src) % 128 == 0 && offsetof(FineSmem, win) % 128 == 0, "TMA destinations must be 128-byte aligned");
+// the four byte-shifted copies of the 20x20 window live in the plane area until the planes are fetched
+#define WIN0_WORDS (20 * 5 + 2)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait (phase 0): a transaction that never completes must not hang the GPU; returns false on timeout
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar)
+{
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 18) && !ok; spin++)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int x, int y, int z, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
 
 // The 16 quarter-pel positions as the average of two samples out of {G,b,h,j} (8.4.2.2.1, Table 8-12):
 // entry = {planeA, dxA, dyA, planeB, dxB, dyB}
@@ -185,19 +199,22 @@ __device__ __forceinline__ uint32_t plane_row(const uint32_t *pl, int o)   // 4 
     const uint32_t *w = pl + (o >> 2);
     return __funnelshift_r(w[0], w[1], (o & 3) * 8);
 }
-// four rows (packed bytes) of the prediction of one 4x4 block at quarter-pel offset (ox,oy) in [-3,3] from the best full-pel block
-__device__ __forceinline__ void pred_rows_qpel(const FineSmem &sm, int bx, int by, int ox, int oy, uint32_t P[4])
+// four rows (packed bytes) of the prediction of one 4x4 block at quarter-pel offset (ox,oy) in [-3,3] from the best full-pel
+// block; o1 = byte offset of the window inside the TMA box; P[y] receives row (y ^ rx): the callers permute the rows of the
+// lower two block rows (rx = 1) so that the 16 block lanes of a half-warp hit 16 different banks at the 48-byte row pitch,
+// and the Hadamard SATD is invariant under that (dyadic) permutation as long as the source rows are permuted alike.
+__device__ __forceinline__ void pred_rows_qpel(const FineSmem &sm, int o1, int bx, int by, int ox, int oy, int rx, uint32_t P[4])
 {
     const uint8_t *t = c_qpel_tab[(oy & 3) * 4 + (ox & 3)];
-    const int xo = bx + (ox >> 2) + 4, yo = by + (oy >> 2) + 1;
+    const int xo = o1 + bx + (ox >> 2) + 4, yo = by + (oy >> 2) + 1;
     const uint32_t *pa = sm.plane[t[0]], *pb = sm.plane[t[3]];
     const int oa = (yo + t[2]) * PL_STRIDE + xo + t[1], ob = (yo + t[5]) * PL_STRIDE + xo + t[4];
     if (((ox | oy) & 1) == 0) {          // full/half-pel positions are a single plane (both table entries coincide)
 #pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = plane_row(pa, oa + y * PL_STRIDE);
+        for (int y = 0; y < 4; y++) P[y] = plane_row(pa, oa + (y ^ rx) * PL_STRIDE);
     } else {
 #pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = avg4(plane_row(pa, oa + y * PL_STRIDE), plane_row(pb, ob + y * PL_STRIDE));
+        for (int y = 0; y < 4; y++) P[y] = avg4(plane_row(pa, oa + (y ^ rx) * PL_STRIDE), plane_row(pb, ob + (y ^ rx) * PL_STRIDE));
     }
 }
 // 4x4 Hadamard SATD of (source block - P): Ts holds the horizontal transforms of the source rows, the prediction
@@ -222,7 +239,7 @@ __device__ __forceinline__ int half_reduce16(int v)   // sum over the 16 lanes o
     return v;
 }
 
-__global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(const Sess *ss, Geom g)
+__global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(const Sess *ss, Geom g, WaveCtl *err)
 {
     __shared__ FineSmem sm_all[ME_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,19 +248,21 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     const Sess &s = ss[blockIdx.z];
     if (s.is_idr) return;
     FineSmem &sm = sm_all[warp];
-    const int mx = mb % g.mbw, my = mb / g.mbw, x0 = mx * 16, y0 = my * 16, wc = g.wc, hc = g.hc;
+    const int mx = mb % g.mbw, my = mb / g.mbw, x0 = mx * 16, y0 = my * 16, wc = g.wc;
     const int qp = s.qp, lambda = c_lambda[qp];
-    const uint8_t *win = reinterpret_cast<const uint8_t *>(sm.win);
+    const char *tmaps = static_cast<const char *>(s.tmaps);
 
-    // source MB and the +-2 window around 2*mv1
+    // source MB and the +-2 window around 2*mv1, fetched by TMA
     const int cx = 2 * s.me1[mb * 2], cy = 2 * s.me1[mb * 2 + 1];
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        int wi = lane + 32 * i;
-        sm.src[wi] = *reinterpret_cast<const uint32_t *>(s.src[0] + (size_t)(y0 + (wi >> 2)) * wc + x0 + (wi & 3) * 4);
+    const int X0 = g.lp + x0 + cx - 2, o0 = X0 & 15;
+    if (lane == 0) {
+        mbar_init(&sm.bar[0]); mbar_init(&sm.bar[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sm.bar[0], 256 + 20 * PL_STRIDE);
+        tma_load_2d(sm.src, tmaps, x0, y0, &sm.bar[0]);
+        tma_load_2d(sm.win, tmaps + 128, X0 & ~15, g.lp + y0 + cy - 2, &sm.bar[0]);
     }
-    stage_window<20, 20>(sm.win, s.ref[0], wc, hc, x0 + cx - 2, y0 + cy - 2, lane);
-    // zero-vector candidate, computed cooperatively straight from HBM (always inside the picture)
+    // zero-vector candidate, computed cooperatively straight from HBM while the tiles are in flight
     uint32_t zsad;
     {
         const uint8_t *rp = s.ref[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8;
@@ -254,15 +273,22 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
         for (int o = 16; o; o >>= 1) zsad += __shfl_xor_sync(0xffffffffu, zsad, o);
     }
     __syncwarp();
-    for (int i = lane; i < 100; i += 32) {              // byte-shifted copies of the 20x20 window: aligned candidate reads
-        const uint32_t a = sm.win[i], b = sm.win[i + 1];
-        sm.win0[0][i] = __funnelshift_r(a, b, 8); sm.win0[1][i] = __funnelshift_r(a, b, 16); sm.win0[2][i] = __funnelshift_r(a, b, 24);
+    bool tma_ok = mbar_wait(&sm.bar[0]);
+    uint32_t *win0 = sm.plane[0];                       // four byte-shifted copies of the 20x20 window: aligned candidate reads
+    for (int i = lane; i < 100; i += 32) {
+        const int r = i / 5, j = i - r * 5;
+        const uint32_t *row = sm.win + r * (PL_STRIDE / 4);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int off = o0 + 4 * j + k;
+            win0[k * WIN0_WORDS + i] = __funnelshift_r(row[off >> 2], row[(off >> 2) + 1], (off & 3) * 8);
+        }
     }
     __syncwarp();
     uint32_t best = 0xffffffffu;
     if (lane < 25) {
         const int dy = lane / 5, dx = lane - dy * 5;
-        const uint32_t *p = ((dx & 3) ? sm.win0[(dx & 3) - 1] : sm.win) + dy * 5 + (dx >> 2);
+        const uint32_t *p = win0 + (dx & 3) * WIN0_WORDS + dy * 5 + (dx >> 2);
         uint32_t sad = 0;
 #pragma unroll 4
         for (int r = 0; r < 16; r++) {
@@ -275,44 +301,35 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     const int c0 = best & 31;
     const int fx = c0 < 25 ? cx + c0 % 5 - 2 : 0, fy = c0 < 25 ? cy + c0 / 5 - 2 : 0;   // best full-pel vector
 
-    // half-pel sample planes around the winner
+    // the four reference planes around the winner: one 3-D TMA box (the shifted copies above are dead by now)
+    const int X1 = g.lp + x0 + fx - 4, o1 = X1 & 15;
     __syncwarp();
-    stage_window<24, 24>(sm.win, s.ref[0], wc, hc, x0 + fx - 3, y0 + fy - 3, lane);
-    __syncwarp();
-    for (int i = lane; i < 24 * 18; i += 32) {        // braw(x,y), x in [-1,16], y in [-3,20]
-        const int r = i / 18, c = i - r * 18;           // G column of sample x is c + 2 (x = c - 1, G index x + 3)
-        const uint8_t *p = win + r * 24 + c;
-        sm.braw[i] = (int16_t)tap6(p[0], p[1], p[2], p[3], p[4], p[5]);
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&sm.bar[1], 4 * PL_ROWS * PL_STRIDE);
+        tma_load_3d(sm.plane, tmaps + 256, X1 & ~15, g.lp + y0 + fy - 1, 0, &sm.bar[1]);
     }
-    __syncwarp();
-    {
-        uint8_t *pl0 = reinterpret_cast<uint8_t *>(sm.plane[0]), *pl1 = reinterpret_cast<uint8_t *>(sm.plane[1]);
-        uint8_t *pl2 = reinterpret_cast<uint8_t *>(sm.plane[2]), *pl3 = reinterpret_cast<uint8_t *>(sm.plane[3]);
-        for (int i = lane; i < 18 * 18; i += 32) {
-            const int r = i / 18, c = i - r * 18;       // sample (x,y) = (c-1, r-1); G index (c+2, r+2)
-            const uint8_t *p = win + (r + 2) * 24 + c + 2;
-            const int o = r * PL_STRIDE + c + 3;
-            pl0[o] = p[0];
-            pl1[o] = (uint8_t)clip255((sm.braw[(r + 2) * 18 + c] + 16) >> 5);
-            pl2[o] = (uint8_t)clip255((tap6(p[-48], p[-24], p[0], p[24], p[48], p[72]) + 16) >> 5);
-            const int16_t *q = sm.braw + r * 18 + c;    // braw rows y-2..y+3 = indices r..r+5
-            pl3[o] = (uint8_t)clip255((tap6(q[0], q[18], q[36], q[54], q[72], q[90]) + 512) >> 10);
-        }
-    }
-    __syncwarp();
-
     // sub-pel refinement by SATD: 16 lanes (one per 4x4 block) evaluate one candidate, two candidates per pass
-    const int hw = lane >> 4, b = lane & 15, bx = blk_x(b) * 4, by = blk_y(b) * 4;
-    int Ts[16];                                         // horizontal Hadamard of the four source rows of this lane's block
+    const int hw = lane >> 4, b = lane & 15, bx = blk_x(b) * 4, by = blk_y(b) * 4, rx = (b >> 3) & 1;
+    int Ts[16];                                         // horizontal Hadamard of the four source rows (row y ^ rx) of this lane's block
     {
         const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
+            const uint32_t w = sm.src[(by + (y ^ rx)) * 4 + (bx >> 2)];
 #pragma unroll
             for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(w, H[k], 0);
         }
     }
+    const bool top = !row_is_slice_top(g, my), left = mx > 0;
+    {
+        uint8_t *nt = reinterpret_cast<uint8_t *>(sm.nb_top), *nl = reinterpret_cast<uint8_t *>(sm.nb_left);
+        if (lane < 16) nt[lane] = top ? s.src[0][(size_t)(y0 - 1) * wc + x0 + lane] : 0;
+        else nl[lane - 16] = left ? s.src[0][(size_t)(y0 + lane - 16) * wc + x0 - 1] : 0;
+    }
+    tma_ok &= mbar_wait(&sm.bar[1]);
+    if (!tma_ok && lane == 0) atomicExch(&err->error, 2);
+    __syncwarp();
     // se(v) lengths of the 7 possible vector components per axis: lane l holds x offset l-3 (l < 8) or y offset l-11 (l >= 8)
     const int mvb = se_len(((lane & 8) ? 4 * fy : 4 * fx) + (lane & 7) - 3);
     int qx = 0, qy = 0;                                 // offset from 4*(fx,fy), quarter-pel units
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
             const int i = 2 * pass + hw + (step == 1 ? 1 : 0);      // step 2: 0..8 (+ one idle slot); step 1: 1..8 (centre known)
             const int ci = i <= 8 ? i : 0;
             const int ox = qx + step * ((int)((OXP >> (2 * ci)) & 3) - 1), oy = qy + step * ((int)((OYP >> (2 * ci)) & 3) - 1);
-            uint32_t P[4]; pred_rows_qpel(sm, bx, by, ox, oy, P);
+            uint32_t P[4]; pred_rows_qpel(sm, o1, bx, by, ox, oy, rx, P);
             const int sat = half_reduce16(satd_rows(P, Ts));
             uint32_t key = 0xffffffffu;
             const int bits = __shfl_sync(0xffffffffu, mvb, ox + 3) + __shfl_sync(0xffffffffu, mvb, oy + 11);
@@ -341,20 +358,13 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     }
     const int mvx = 4 * fx + qx, mvy = 4 * fy + qy, inter_cost = (int)(centre_key >> 4);
 
-    // intra estimate from source neighbours: V, H, DC 16x16 by SATD
-    const bool top = !row_is_slice_top(g, my), left = mx > 0;
-    {
-        uint8_t *nt = reinterpret_cast<uint8_t *>(sm.nb_top), *nl = reinterpret_cast<uint8_t *>(sm.nb_left);
-        if (lane < 16) nt[lane] = top ? s.src[0][(size_t)(y0 - 1) * wc + x0 + lane] : 0;
-        else nl[lane - 16] = left ? s.src[0][(size_t)(y0 + lane - 16) * wc + x0 - 1] : 0;
-    }
-    __syncwarp();
+    // intra estimate from source neighbours (staged above): V, H, DC 16x16 by SATD
     int ie = 1 << 30;
     {
         const uint8_t *nl = reinterpret_cast<const uint8_t *>(sm.nb_left);
         uint32_t P[4];
 #pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = hw == 0 ? sm.nb_top[bx >> 2] : 0x01010101u * nl[by + y];
+        for (int y = 0; y < 4; y++) P[y] = hw == 0 ? sm.nb_top[bx >> 2] : 0x01010101u * nl[by + (y ^ rx)];
         const int sat = half_reduce16(satd_rows(P, Ts));
         const int other = __shfl_xor_sync(0xffffffffu, sat, 16);
         const int sv = hw == 0 ? sat : other, sh = hw == 0 ? other : sat;
@@ -385,12 +395,12 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     MbCoef *co = s.coef + mb;
     const bool is_luma = lane < 16, active = lane < 24;
     const int pl = (lane >> 2) & 1, cb = lane & 3;                 // chroma plane / block of lanes 16-23
-    const int cw = wc / 2, ch = hc / 2;
+    const int cw = wc / 2;
     const int cx0 = mx * 8 + (cb & 1) * 4, cy0 = my * 8 + (cb >> 1) * 4;
     int nnz = 0; bool dc_nz = false;
     int p[16], c[16];
     if (is_luma) {
-        uint32_t P[4]; pred_rows_qpel(sm, bx, by, qx, qy, P);
+        uint32_t P[4]; pred_rows_qpel(sm, o1, bx, by, qx, qy, 0, P);
 #pragma unroll
         for (int y = 0; y < 4; y++) {
             const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
@@ -398,15 +408,15 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
             for (int x = 0; x < 4; x++) { p[y * 4 + x] = (P[y] >> (8 * x)) & 255; c[y * 4 + x] = (int)((w >> (8 * x)) & 255) - p[y * 4 + x]; }
         }
     } else {
-        // chroma motion compensation, 1/8-pel bilinear (8.4.2.2.2), clamped reference coordinates
+        // chroma motion compensation, 1/8-pel bilinear (8.4.2.2.2), from the edge-extended reference chroma planes
         const int pc = active ? pl : 0;
         const int xi = cx0 + (mvx >> 3), yi = cy0 + (mvy >> 3), fxc = mvx & 7, fyc = mvy & 7;
-        const uint8_t *rp = s.ref[1 + pc];
+        const uint8_t *rp = s.rpc[pc] + (ptrdiff_t)yi * g.cs + xi;
         int smp[25];
 #pragma unroll
         for (int y = 0; y < 5; y++)
 #pragma unroll
-            for (int x = 0; x < 5; x++) smp[y * 5 + x] = __ldg(rp + (size_t)clip3(0, ch - 1, yi + y) * cw + clip3(0, cw - 1, xi + x));
+            for (int x = 0; x < 5; x++) smp[y * 5 + x] = __ldg(rp + y * g.cs + x);
         const uint8_t *sp_c = s.src[1 + pc] + (size_t)cy0 * cw + cx0;
         const int w00 = (8 - fxc) * (8 - fyc), w01 = fxc * (8 - fyc), w10 = (8 - fxc) * fyc, w11 = fxc * fyc;
 #pragma unroll

@@ -106,26 +106,104 @@ __global__ void __launch_bounds__(256) k_ingest_rgba(const Sess *ss, Geom g)
 }
 
 // 2x2 box filter with rounding (role of DyadicBilinearDownsampler_c). level 0: full -> 1/2, level 1: 1/2 -> 1/4.
+// The output planes carry an edge-replicated border of g.p1 / g.p2 samples (the coarse search windows reach outside the
+// picture and the oracle clamps coordinates per level), so the kernel covers the padded area and clamps into the interior.
 // grid: (ceil(units/256), 2 {src, ref}, sessions); a unit is 4 output pixels.
 __global__ void __launch_bounds__(256) k_downsample(const Sess *ss, Geom g, int level)
 {
     const Sess &s = ss[blockIdx.z];
     if (s.is_idr) return;
     const int iw = g.wc >> level, ih = g.hc >> level, ow = iw / 2, oh = ih / 2;
+    const int is = level == 0 ? g.wc : g.s1, os = level == 0 ? g.s1 : g.s2, po = level == 0 ? g.p1 : g.p2;
     const uint8_t *in = blockIdx.y == 0 ? (level == 0 ? s.src[0] : s.srcL1) : (level == 0 ? s.ref[0] : s.refL1);
     uint8_t *out = blockIdx.y == 0 ? (level == 0 ? s.srcL1 : s.srcL2) : (level == 0 ? s.refL1 : s.refL2);
+    const int upr = (ow + 2 * po) / 4;
     int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= (ow / 4) * oh) return;
-    const int x = (u % (ow / 4)) * 4, y = u / (ow / 4);
-    uint2 a = *reinterpret_cast<const uint2 *>(in + (size_t)(2 * y) * iw + 2 * x);
-    uint2 b = *reinterpret_cast<const uint2 *>(in + (size_t)(2 * y + 1) * iw + 2 * x);
-    uint32_t aw[2] = { a.x, a.y }, bw[2] = { b.x, b.y }, o = 0;
+    if (u >= upr * (oh + 2 * po)) return;
+    const int x = (u % upr) * 4 - po, y = u / upr - po, cy = min(max(y, 0), oh - 1);
+    uint32_t o = 0;
+    if (x >= 0 && x + 4 <= ow) {
+        uint2 a = *reinterpret_cast<const uint2 *>(in + (size_t)(2 * cy) * is + 2 * x);
+        uint2 b = *reinterpret_cast<const uint2 *>(in + (size_t)(2 * cy + 1) * is + 2 * x);
+        uint32_t aw[2] = { a.x, a.y }, bw[2] = { b.x, b.y };
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t p = aw[i >> 1] >> (16 * (i & 1)), q = bw[i >> 1] >> (16 * (i & 1));
-        o |= (((p & 255) + ((p >> 8) & 255) + (q & 255) + ((q >> 8) & 255) + 2) >> 2) << (8 * i);
+        for (int i = 0; i < 4; i++) {
+            uint32_t p = aw[i >> 1] >> (16 * (i & 1)), q = bw[i >> 1] >> (16 * (i & 1));
+            o |= (((p & 255) + ((p >> 8) & 255) + (q & 255) + ((q >> 8) & 255) + 2) >> 2) << (8 * i);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int cx = min(max(x + i, 0), ow - 1);
+            const uint8_t *p = in + (size_t)(2 * cy) * is + 2 * cx;
+            o |= (uint32_t)((p[0] + p[1] + p[is] + p[is + 1] + 2) >> 2) << (8 * i);
+        }
     }
-    *reinterpret_cast<uint32_t *>(out + (size_t)y * ow + x) = o;
+    *reinterpret_cast<uint32_t *>(out + (ptrdiff_t)y * os + x) = o;
+}
+
+// Reference planes of a P picture, built once per frame from the previous deblocked reconstruction: plane G is the
+// edge-extended picture itself, b / h / j are the half-sample planes of 8.4.2.2.1 (6-tap horizontally, vertically, and both
+// from the unrounded intermediate). All carry a border of g.lp samples, so sub-pel search and motion compensation read them
+// without clamping and the search windows can be fetched by TMA. HBM stream: 1 B read, 4 B written per padded sample.
+#define RP_TW 64
+#define RP_TH 16
+__device__ __forceinline__ int rp_tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+// grid: (ceil(ls / RP_TW), ceil((hc + 2 lp) / RP_TH), sessions), 256 threads
+__global__ void __launch_bounds__(256) k_refplanes(const Sess *ss, Geom g)
+{
+    const Sess &s = ss[blockIdx.z];
+    if (s.is_idr) return;
+    __shared__ uint8_t tile[RP_TH + 5][RP_TW + 8];
+    __shared__ int16_t braw[RP_TH + 5][RP_TW];
+    const int X0 = blockIdx.x * RP_TW - g.lp, Y0 = blockIdx.y * RP_TH - g.lp, wc = g.wc, hc = g.hc;
+    const uint8_t *ref = s.ref[0];
+    for (int i = threadIdx.x; i < (RP_TH + 5) * (RP_TW + 5); i += 256) {
+        const int r = i / (RP_TW + 5), c = i - r * (RP_TW + 5);
+        tile[r][c] = ref[(size_t)min(max(Y0 - 2 + r, 0), hc - 1) * wc + min(max(X0 - 2 + c, 0), wc - 1)];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (RP_TH + 5) * RP_TW; i += 256) {
+        const int r = i / RP_TW, c = i - r * RP_TW;
+        const uint8_t *p = &tile[r][c];
+        braw[r][c] = (int16_t)rp_tap6(p[0], p[1], p[2], p[3], p[4], p[5]);
+    }
+    __syncthreads();
+    const int row = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
+    if (X0 + c4 >= wc + g.lp || Y0 + row >= hc + g.lp) return;
+    uint32_t wG = 0, wb = 0, wh = 0, wj = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = c4 + k;
+        const int G = tile[row + 2][x + 2];
+        const int b = min(max((braw[row + 2][x] + 16) >> 5, 0), 255);
+        const int h = min(max((rp_tap6(tile[row][x + 2], tile[row + 1][x + 2], tile[row + 2][x + 2], tile[row + 3][x + 2], tile[row + 4][x + 2], tile[row + 5][x + 2]) + 16) >> 5, 0), 255);
+        const int j = min(max((rp_tap6(braw[row][x], braw[row + 1][x], braw[row + 2][x], braw[row + 3][x], braw[row + 4][x], braw[row + 5][x]) + 512) >> 10, 0), 255);
+        wG |= (uint32_t)G << (8 * k); wb |= (uint32_t)b << (8 * k); wh |= (uint32_t)h << (8 * k); wj |= (uint32_t)j << (8 * k);
+    }
+    const ptrdiff_t o = (ptrdiff_t)(Y0 + row) * g.ls + X0 + c4;
+    *reinterpret_cast<uint32_t *>(s.rpl[0] + o) = wG; *reinterpret_cast<uint32_t *>(s.rpl[1] + o) = wb;
+    *reinterpret_cast<uint32_t *>(s.rpl[2] + o) = wh; *reinterpret_cast<uint32_t *>(s.rpl[3] + o) = wj;
+}
+
+// edge-extended copies of the reference chroma planes (border g.cp). grid: (ceil(units/256), 2 {Cb, Cr}, sessions); unit = 4 samples
+__global__ void __launch_bounds__(256) k_refchroma(const Sess *ss, Geom g)
+{
+    const Sess &s = ss[blockIdx.z];
+    if (s.is_idr) return;
+    const int cw = g.wc / 2, ch = g.hc / 2, upr = g.cs / 4;
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= upr * (ch + 2 * g.cp)) return;
+    const int x = (u % upr) * 4 - g.cp, y = u / upr - g.cp;
+    const uint8_t *row = s.ref[1 + blockIdx.y] + (size_t)min(max(y, 0), ch - 1) * cw;
+    uint32_t o;
+    if (x >= 0 && x + 4 <= cw) o = *reinterpret_cast<const uint32_t *>(row + x);
+    else {
+        o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) o |= (uint32_t)row[min(max(x + i, 0), cw - 1)] << (8 * i);
+    }
+    *reinterpret_cast<uint32_t *>(s.rpc[blockIdx.y] + (ptrdiff_t)y * g.cs + x) = o;
 }
 
 } // namespace b200

@@ -43,7 +43,7 @@ int b200k_downsample2(int device, const uint8_t *in, int w, int h, uint8_t *out)
 {
     if (!in || !out || w < 8 || h < 2 || (w & 7) || (h & 1)) return B200ENC_EINVAL;
     if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
-    Geom g; memset(&g, 0, sizeof g); g.wc = w; g.hc = h;
+    Geom g; memset(&g, 0, sizeof g); g.wc = w; g.hc = h; g.p1 = 0; g.s1 = w / 2;
     DevBuf din((size_t)w * h), dout((size_t)w * h / 4), dsess(sizeof(Sess));
     if (!din.p || !dout.p || !dsess.p) return B200ENC_ENOMEM;
     Sess s; memset(&s, 0, sizeof s);
