@@ -17,12 +17,7 @@ namespace b200 {
 #define ME_FINE_MIN_CTAS 4     /* 64 registers: 4 CTAs of 8 warps per SM (measured 8 % faster than 75-94 registers) */
 #endif
 
-__device__ __forceinline__ uint32_t warp_min(uint32_t v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }   // one REDUX.MIN
 __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
 // Window staging from a PADDED plane (`org` addresses sample (0,0); the border makes every search window addressable, so

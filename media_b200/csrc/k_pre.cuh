@@ -147,43 +147,83 @@ __global__ void __launch_bounds__(256) k_downsample(const Sess *ss, Geom g, int 
 // from the unrounded intermediate). All carry a border of g.lp samples, so sub-pel search and motion compensation read them
 // without clamping and the search windows can be fetched by TMA. HBM stream: 1 B read, 4 B written per padded sample.
 #define RP_TW 64
-#define RP_TH 16
-__device__ __forceinline__ int rp_tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
-// grid: (ceil(ls / RP_TW), ceil((hc + 2 lp) / RP_TH), sessions), 256 threads
+#define RP_TH 32
+__device__ __forceinline__ int rp_dp4a(uint32_t a, uint32_t b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int rp_dp2a(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+// grid: (ceil(ls / RP_TW), ceil((hc + 2 lp) / RP_TH), sessions), 256 threads; a CTA produces a 64x32 tile of all four planes.
+//   stage 1  the (32+5) x 72-byte source tile as words (plain 32-bit loads when the tile lies inside the picture)
+//   stage 2  unrounded horizontal 6-tap sums by two IDP.4A per sample ({1,-5,20,20} and {-5,1,0,0} against funnel-shifted
+//            words), stored as vertical pairs (row r in the low, row r+1 in the high 16 bits)
+//   stage 3  j = three IDP.2A over the pairs; h = the vertical 6-tap on bytes unpacked to 16x2 lanes (two samples per
+//            integer op, clamped with VIMNMX.S16x2); b = rounded stage-2 sums; four 32-bit stores per thread
 __global__ void __launch_bounds__(256) k_refplanes(const Sess *ss, Geom g)
 {
     const Sess &s = ss[blockIdx.z];
     if (s.is_idr) return;
-    __shared__ uint8_t tile[RP_TH + 5][RP_TW + 8];
-    __shared__ int16_t braw[RP_TH + 5][RP_TW];
+    __shared__ uint32_t tile[RP_TH + 5][18];                  // row r: y = Y0 - 2 + r; word j: x = X0 - 4 + 4j ..
+    __shared__ __align__(16) uint32_t pair[RP_TH + 4][RP_TW];
     const int X0 = blockIdx.x * RP_TW - g.lp, Y0 = blockIdx.y * RP_TH - g.lp, wc = g.wc, hc = g.hc;
     const uint8_t *ref = s.ref[0];
-    for (int i = threadIdx.x; i < (RP_TH + 5) * (RP_TW + 5); i += 256) {
-        const int r = i / (RP_TW + 5), c = i - r * (RP_TW + 5);
-        tile[r][c] = ref[(size_t)min(max(Y0 - 2 + r, 0), hc - 1) * wc + min(max(X0 - 2 + c, 0), wc - 1)];
+    const bool inside = X0 - 4 >= 0 && X0 + 68 <= wc && Y0 - 2 >= 0 && Y0 + RP_TH + 3 <= hc;
+    for (int i = threadIdx.x; i < (RP_TH + 5) * 18; i += 256) {
+        const int r = i / 18, j = i - r * 18, x = X0 - 4 + 4 * j;
+        uint32_t w;
+        if (inside) w = *reinterpret_cast<const uint32_t *>(ref + (size_t)(Y0 - 2 + r) * wc + x);
+        else {
+            const uint8_t *row = ref + (size_t)min(max(Y0 - 2 + r, 0), hc - 1) * wc;
+            w = (uint32_t)row[min(max(x, 0), wc - 1)] | ((uint32_t)row[min(max(x + 1, 0), wc - 1)] << 8) |
+                ((uint32_t)row[min(max(x + 2, 0), wc - 1)] << 16) | ((uint32_t)row[min(max(x + 3, 0), wc - 1)] << 24);
+        }
+        tile[r][j] = w;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (RP_TH + 5) * RP_TW; i += 256) {
-        const int r = i / RP_TW, c = i - r * RP_TW;
-        const uint8_t *p = &tile[r][c];
-        braw[r][c] = (int16_t)rp_tap6(p[0], p[1], p[2], p[3], p[4], p[5]);
-    }
-    __syncthreads();
-    const int row = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
-    if (X0 + c4 >= wc + g.lp || Y0 + row >= hc + g.lp) return;
-    uint32_t wG = 0, wb = 0, wh = 0, wj = 0;
+    const uint32_t WLO = 0x1414FB01u, WHI = 0x000001FBu;     // {1,-5,20,20}, {-5,1,0,0} as signed bytes
+    for (int i = threadIdx.x; i < (RP_TH + 4) * 16; i += 256) {
+        const int r = i >> 4, j = i & 15;
+        int v[2][4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = c4 + k;
-        const int G = tile[row + 2][x + 2];
-        const int b = min(max((braw[row + 2][x] + 16) >> 5, 0), 255);
-        const int h = min(max((rp_tap6(tile[row][x + 2], tile[row + 1][x + 2], tile[row + 2][x + 2], tile[row + 3][x + 2], tile[row + 4][x + 2], tile[row + 5][x + 2]) + 16) >> 5, 0), 255);
-        const int j = min(max((rp_tap6(braw[row][x], braw[row + 1][x], braw[row + 2][x], braw[row + 3][x], braw[row + 4][x], braw[row + 5][x]) + 512) >> 10, 0), 255);
-        wG |= (uint32_t)G << (8 * k); wb |= (uint32_t)b << (8 * k); wh |= (uint32_t)h << (8 * k); wj |= (uint32_t)j << (8 * k);
+        for (int q = 0; q < 2; q++) {
+            const uint32_t A = tile[r + q][j], B = tile[r + q][j + 1], C = tile[r + q][j + 2];
+            v[q][0] = rp_dp4a(__funnelshift_r(A, B, 16), WLO, rp_dp4a(__funnelshift_r(B, C, 16), WHI, 0));
+            v[q][1] = rp_dp4a(__funnelshift_r(A, B, 24), WLO, rp_dp4a(__funnelshift_r(B, C, 24), WHI, 0));
+            v[q][2] = rp_dp4a(B, WLO, rp_dp4a(C, WHI, 0));
+            v[q][3] = rp_dp4a(__funnelshift_r(B, C, 8), WLO, rp_dp4a(C >> 8, WHI, 0));
+        }
+        uint4 o;
+        o.x = __byte_perm((uint32_t)v[0][0], (uint32_t)v[1][0], 0x5410); o.y = __byte_perm((uint32_t)v[0][1], (uint32_t)v[1][1], 0x5410);
+        o.z = __byte_perm((uint32_t)v[0][2], (uint32_t)v[1][2], 0x5410); o.w = __byte_perm((uint32_t)v[0][3], (uint32_t)v[1][3], 0x5410);
+        *reinterpret_cast<uint4 *>(&pair[r][4 * j]) = o;
     }
-    const ptrdiff_t o = (ptrdiff_t)(Y0 + row) * g.ls + X0 + c4;
-    *reinterpret_cast<uint32_t *>(s.rpl[0] + o) = wG; *reinterpret_cast<uint32_t *>(s.rpl[1] + o) = wb;
-    *reinterpret_cast<uint32_t *>(s.rpl[2] + o) = wh; *reinterpret_cast<uint32_t *>(s.rpl[3] + o) = wj;
+    __syncthreads();
+    for (int i = threadIdx.x; i < RP_TH * 16; i += 256) {
+        const int y = i >> 4, c = i & 15;
+        if (X0 + 4 * c >= wc + g.lp || Y0 + y >= hc + g.lp) continue;
+        const uint4 Q0 = *reinterpret_cast<const uint4 *>(&pair[y][4 * c]), Q1 = *reinterpret_cast<const uint4 *>(&pair[y + 2][4 * c]);
+        const uint4 Q2 = *reinterpret_cast<const uint4 *>(&pair[y + 4][4 * c]);
+        const uint32_t q0[4] = { Q0.x, Q0.y, Q0.z, Q0.w }, q1[4] = { Q1.x, Q1.y, Q1.z, Q1.w }, q2[4] = { Q2.x, Q2.y, Q2.z, Q2.w };
+        uint32_t wb = 0, wj = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int j = rp_dp2a(q0[k], 0xFB01u, rp_dp2a(q1[k], 0x1414u, rp_dp2a(q2[k], 0x01FBu, 512))) >> 10;
+            const int b = ((int)(short)(q1[k] & 0xffffu) + 16) >> 5;
+            wj |= (uint32_t)__vimin_s32_relu(j, 255) << (8 * k);
+            wb |= (uint32_t)__vimin_s32_relu(b, 255) << (8 * k);
+        }
+        uint32_t e[6], o[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) { const uint32_t w = tile[y + r][c + 1]; e[r] = w & 0x00ff00ffu; o[r] = (w >> 8) & 0x00ff00ffu; }
+        // per 16-bit lane: tap + 16 + 2560 stays in [26, 13286] (no borrow between lanes); 2560 = 80 << 5 is removed after the shift
+        const uint32_t K = (16u + 2560u) * 0x00010001u;
+        uint32_t he = (e[0] + e[5]) + 20u * (e[2] + e[3]) + K - 5u * (e[1] + e[4]);
+        uint32_t ho = (o[0] + o[5]) + 20u * (o[2] + o[3]) + K - 5u * (o[1] + o[4]);
+        he = __vmins2(__vmaxs2((he >> 5) & 0x07ff07ffu, 0x00500050u), 0x014f014fu) - 0x00500050u;
+        ho = __vmins2(__vmaxs2((ho >> 5) & 0x07ff07ffu, 0x00500050u), 0x014f014fu) - 0x00500050u;
+        const ptrdiff_t off = (ptrdiff_t)(Y0 + y) * g.ls + X0 + 4 * c;
+        *reinterpret_cast<uint32_t *>(s.rpl[0] + off) = tile[y + 2][c + 1];
+        *reinterpret_cast<uint32_t *>(s.rpl[1] + off) = wb;
+        *reinterpret_cast<uint32_t *>(s.rpl[2] + off) = he | (ho << 8);
+        *reinterpret_cast<uint32_t *>(s.rpl[3] + off) = wj;
+    }
 }
 
 // edge-extended copies of the reference chroma planes (border g.cp). grid: (ceil(units/256), 2 {Cb, Cr}, sessions); unit = 4 samples
