@@ -9,13 +9,16 @@
 
 namespace b200 {
 
-enum { MB_P16x16 = 0, MB_I16x16 = 1, MB_I4x4 = 2, MB_PSKIP = 3 };
+enum { MB_P16x16 = 0, MB_I16x16 = 1, MB_I4x4 = 2, MB_PSKIP = 3, MB_P8x8 = 4 };
 
 // Per-MB side information, 48 bytes. nnz: 0..15 luma blkIdx, 16..19 Cb, 20..23 Cr.
 struct __align__(16) MbInfo {
     uint8_t mb_type, i16_mode, chroma_mode, cbp;
-    int16_t mv[2];
-    uint8_t i4_mode[16];
+    int16_t mv[2];                // the 16x16 vector (partition 0 for P_8x8)
+    union {
+        uint8_t i4_mode[16];      // intra MBs: Intra4x4PredMode per blkIdx
+        int16_t mv8[4][2];        // inter MBs: vector of each 8x8 partition (all equal for P_L0_16x16 / P_Skip)
+    };
     uint8_t nnz[24];
 };
 // Per-MB quantised levels in zig-zag order, 816 bytes.
@@ -273,5 +276,10 @@ __device__ __forceinline__ int quant_dc(int y, const QParam &q, int f)
 // acquire/release on the wavefront progress counters
 __device__ __forceinline__ int ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+// publish pattern of the wavefront kernels: every lane fences its own stores (one MEMBAR.ALL.GPU per warp, cheaper than the
+// MEMBAR.SC of __threadfence()), the warp converges, then one lane stores the counter with a plain strong store
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed(int *p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_relaxed(const int *p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 } // namespace b200

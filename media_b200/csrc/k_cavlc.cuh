@@ -16,24 +16,47 @@
 
 namespace b200 {
 
-__device__ __forceinline__ bool is_inter_type(int t) { return t == MB_P16x16 || t == MB_PSKIP; }
+__device__ __forceinline__ bool is_inter_type(int t) { return t == MB_P16x16 || t == MB_PSKIP || t == MB_P8x8; }
 
-// 8.4.1.3 for a 16x16 partition with one reference picture, and the P_Skip vector of 8.4.1.1
+// Neighbouring partition for MV prediction (6.4.11.7): the 8x8 partition covering luma location (x,y) relative to MB (mx,my).
+// Partitions of the current MB with index >= cur_part are not decoded yet. One reference picture: ref is 0 for inter, -1 else.
+struct NbMv { int avail, ref, x, y; };
+__device__ __forceinline__ NbMv nb_at(const Sess &s, const Geom &g, int mx, int my, int x, int y, int cur_part)
+{
+    NbMv r; r.avail = 0; r.ref = -1; r.x = 0; r.y = 0;
+    const int nx = mx + (x < 0 ? -1 : x > 15 ? 1 : 0), ny = my - (y < 0);
+    if (nx < 0 || nx >= g.mbw) return r;
+    if (ny != my && row_is_slice_top(g, my)) return r;
+    if (ny == my && nx > mx) return r;
+    const int part = (((y + 16) & 15) >> 3) * 2 + (((x + 16) & 15) >> 3);
+    if (nx == mx && ny == my && part >= cur_part) return r;
+    const MbInfo *m = s.mbi + ny * g.mbw + nx;
+    r.avail = 1;
+    if (is_inter_type(m->mb_type)) {
+        const uint32_t v = reinterpret_cast<const uint32_t *>(m)[2 + part];
+        r.ref = 0; r.x = (int)(int16_t)(v & 0xffffu); r.y = (int)(int16_t)(v >> 16);
+    }
+    return r;
+}
+// 8.4.1.3 for the 16x16 partition (part < 0) or the 8x8 partition `part`; A and B are returned for the P_Skip rule
+__device__ __forceinline__ void predict_mv_part(const Sess &s, const Geom &g, int mx, int my, int part, int &pmx, int &pmy, NbMv &A, NbMv &B)
+{
+    const int px = part < 0 ? 0 : (part & 1) * 8, py = part < 0 ? 0 : (part >> 1) * 8, w = part < 0 ? 16 : 8, cur = part < 0 ? 0 : part;
+    A = nb_at(s, g, mx, my, px - 1, py, cur); B = nb_at(s, g, mx, my, px, py - 1, cur);
+    NbMv C = nb_at(s, g, mx, my, px + w, py - 1, cur);
+    if (!C.avail) C = nb_at(s, g, mx, my, px - 1, py - 1, cur);
+    NbMv b2 = B;
+    if (!B.avail && !C.avail && A.avail) { b2 = A; C = A; }
+    const int n = (A.ref == 0) + (b2.ref == 0) + (C.ref == 0);
+    if (n == 1) { const NbMv &o = A.ref == 0 ? A : b2.ref == 0 ? b2 : C; pmx = o.x; pmy = o.y; }
+    else { pmx = median3(A.x, b2.x, C.x); pmy = median3(A.y, b2.y, C.y); }
+}
+// 16x16 prediction and the P_Skip vector of 8.4.1.1
 __device__ __forceinline__ void predict_mv(const Sess &s, const Geom &g, int mx, int my, int &pmx, int &pmy, int &skx, int &sky)
 {
-    const bool top_ok = !row_is_slice_top(g, my);
-    const bool aA = mx > 0, aB = top_ok, aC = top_ok && mx + 1 < g.mbw, aD = top_ok && mx > 0;
-    const MbInfo *m = s.mbi + my * g.mbw + mx;
-    const MbInfo *A = aA ? m - 1 : nullptr, *B = aB ? m - g.mbw : nullptr, *C = aC ? m - g.mbw + 1 : (aD ? m - g.mbw - 1 : nullptr);
-    int refA = -1, refB = -1, refC = -1, ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
-    if (A && is_inter_type(A->mb_type)) { refA = 0; ax = A->mv[0]; ay = A->mv[1]; }
-    if (B && is_inter_type(B->mb_type)) { refB = 0; bx = B->mv[0]; by = B->mv[1]; }
-    if (C && is_inter_type(C->mb_type)) { refC = 0; cx = C->mv[0]; cy = C->mv[1]; }
-    if (!aB && !(aC || aD) && aA) { refB = refA; bx = ax; by = ay; refC = refA; cx = ax; cy = ay; }
-    const int n = (refA == 0) + (refB == 0) + (refC == 0);
-    if (n == 1) { if (refA == 0) { pmx = ax; pmy = ay; } else if (refB == 0) { pmx = bx; pmy = by; } else { pmx = cx; pmy = cy; } }
-    else { pmx = median3(ax, bx, cx); pmy = median3(ay, by, cy); }
-    if (!aA || !aB || (refA == 0 && ax == 0 && ay == 0) || (refB == 0 && bx == 0 && by == 0)) { skx = 0; sky = 0; }
+    NbMv A, B;
+    predict_mv_part(s, g, mx, my, -1, pmx, pmy, A, B);
+    if (!A.avail || !B.avail || (A.ref == 0 && A.x == 0 && A.y == 0) || (B.ref == 0 && B.x == 0 && B.y == 0)) { skx = 0; sky = 0; }
     else { skx = pmx; sky = pmy; }
 }
 
@@ -204,6 +227,16 @@ template <bool WRITE> __device__ void code_mb_header(BitSink<WRITE> &bs, const S
         }
         bs.ue(mi->chroma_mode);
         bs.ue(c_cbp_intra[mi->cbp]);
+        if (mi->cbp) bs.se(0);
+    } else if (mi->mb_type == MB_P8x8) {
+        // P_8x8 with four P_L0_8x8 sub-macroblocks (7.3.5.2); ref_idx_l0 is not coded with one reference picture
+        bs.ue(3);
+        for (int q = 0; q < 4; q++) bs.ue(0);
+        for (int q = 0; q < 4; q++) {
+            int pmx, pmy; NbMv A, B; predict_mv_part(s, g, mx, my, q, pmx, pmy, A, B);
+            bs.se(mi->mv8[q][0] - pmx); bs.se(mi->mv8[q][1] - pmy);
+        }
+        bs.ue(c_cbp_inter[mi->cbp]);
         if (mi->cbp) bs.se(0);
     } else {
         int pmx, pmy, skx, sky; predict_mv(s, g, mx, my, pmx, pmy, skx, sky);

@@ -64,7 +64,8 @@ __device__ __forceinline__ int bs_of(const uint32_t *mp, int bxp, int byp, const
     const bool ip = p->mb_type == MB_I16x16 || p->mb_type == MB_I4x4, iq = q->mb_type == MB_I16x16 || q->mb_type == MB_I4x4;
     if (ip || iq) return mb_edge ? 4 : 3;
     if (p->nnz[xy2blk(bxp, byp)] || q->nnz[xy2blk(bxq, byq)]) return 2;
-    if (abs(p->mv[0] - q->mv[0]) >= 4 || abs(p->mv[1] - q->mv[1]) >= 4) return 1;
+    const int16_t *vp = p->mv8[(byp >> 1) * 2 + (bxp >> 1)], *vq = q->mv8[(byq >> 1) * 2 + (bxq >> 1)];
+    if (abs(vp[0] - vq[0]) >= 4 || abs(vp[1] - vq[1]) >= 4) return 1;
     return 0;
 }
 
@@ -192,12 +193,12 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss
         const bool wrote = deblock_mb(s, g, sm_all[warp], mx, my, lane, cur, prog + my - 1, ctl, ok);
         if (!ok) return;
         if (wrote) {
-            __threadfence();
+            fence_acq_rel_gpu();
             __syncwarp();
-            if (lane == 0) st_release(prog + my, mx + 1);
+            if (lane == 0) st_relaxed(prog + my, mx + 1);
             published = mx + 1;
         } else if (mx + 1 - published >= 4 || mx + 1 == g.mbw) {   // nothing written: publish lazily, in strides
-            if (lane == 0) st_release(prog + my, mx + 1);
+            if (lane == 0) st_relaxed(prog + my, mx + 1);
             published = mx + 1;
         }
         cur = nxt;

@@ -393,9 +393,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_intra_wave(const Sess *ss, 
         }
         if (!slice_top && !wave_wait(prog + my - 1, min(nx + 2, g.mbw), ctl, lane)) return;
         intra_code_mb(s, g, sm, nx, my, lane);
-        __threadfence();
+        fence_acq_rel_gpu();
         __syncwarp();
-        if (lane == 0) st_release(prog + my, nx + 1);
+        if (lane == 0) st_relaxed(prog + my, nx + 1);
         mx = nx + 1;
     }
     __syncwarp();

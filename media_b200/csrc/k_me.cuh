@@ -149,6 +149,7 @@ struct __align__(128) FineSmem {
 static_assert(sizeof(FineSmem) % 128 == 0 && offsetof(FineSmem, src) % 128 == 0 && offsetof(FineSmem, win) % 128 == 0, "TMA destinations must be 128-byte aligned");
 // the four byte-shifted copies of the 20x20 window live in the plane area until the planes are fetched
 #define WIN0_WORDS (20 * 5 + 2)
+#define P8X8_BIAS_BITS 8        /* extra header bits of P_8x8 over P_L0_16x16: mb_type ue(3) vs ue(0), four sub_mb_type ue(0) */
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory"); }
@@ -250,6 +251,18 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     // source MB and the +-2 window around 2*mv1, fetched by TMA
     const int cx = 2 * s.me1[mb * 2], cy = 2 * s.me1[mb * 2 + 1];
     const int X0 = g.lp + x0 + cx - 2, o0 = X0 & 15;
+    const bool top = !row_is_slice_top(g, my), left = mx > 0;
+    // estimate of the MV predictor for the rate terms below: 8.4.1.3 median over the LEVEL-1 vectors of the neighbours (x8)
+    int ppx, ppy;
+    {
+        int ax = 0, ay = 0, tx = 0, ty = 0, rx = 0, ry = 0;
+        const int16_t *m1 = s.me1;
+        if (left) { ax = m1[(mb - 1) * 2]; ay = m1[(mb - 1) * 2 + 1]; }
+        if (top) { tx = m1[(mb - g.mbw) * 2]; ty = m1[(mb - g.mbw) * 2 + 1]; }
+        const int nc = top && mx + 1 < g.mbw ? mb - g.mbw + 1 : (top && left ? mb - g.mbw - 1 : -1);
+        if (nc >= 0) { rx = m1[nc * 2]; ry = m1[nc * 2 + 1]; }
+        ppx = 8 * median3(ax, tx, rx); ppy = 8 * median3(ay, ty, ry);
+    }
     if (lane == 0) {
         mbar_init(&sm.bar[0]); mbar_init(&sm.bar[1]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -290,8 +303,8 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
 #pragma unroll
             for (int k = 0; k < 4; k++) sad = sad4(sm.src[r * 4 + k], p[r * 5 + k], sad);
         }
-        best = ((sad + lambda * (se_len(4 * (cx + dx - 2)) + se_len(4 * (cy + dy - 2)))) << 5) | (uint32_t)lane;
-    } else if (lane == 25) best = ((zsad + lambda * 2) << 5) | 25u;
+        best = ((sad + lambda * (se_len(4 * (cx + dx - 2) - ppx) + se_len(4 * (cy + dy - 2) - ppy))) << 5) | (uint32_t)lane;
+    } else if (lane == 25) best = ((zsad + lambda * (se_len(-ppx) + se_len(-ppy))) << 5) | 25u;
     best = warp_min(best);
     const int c0 = best & 31;
     const int fx = c0 < 25 ? cx + c0 % 5 - 2 : 0, fy = c0 < 25 ? cy + c0 / 5 - 2 : 0;   // best full-pel vector
@@ -316,7 +329,6 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
             for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(w, H[k], 0);
         }
     }
-    const bool top = !row_is_slice_top(g, my), left = mx > 0;
     {
         uint8_t *nt = reinterpret_cast<uint8_t *>(sm.nb_top), *nl = reinterpret_cast<uint8_t *>(sm.nb_left);
         if (lane < 16) nt[lane] = top ? s.src[0][(size_t)(y0 - 1) * wc + x0 + lane] : 0;
@@ -326,11 +338,16 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     if (!tma_ok && lane == 0) atomicExch(&err->error, 2);
     __syncwarp();
     // se(v) lengths of the 7 possible vector components per axis: lane l holds x offset l-3 (l < 8) or y offset l-11 (l >= 8)
-    const int mvb = se_len(((lane & 8) ? 4 * fy : 4 * fx) + (lane & 7) - 3);
+    const int mvb = se_len(((lane & 8) ? 4 * fy - ppy : 4 * fx - ppx) + (lane & 7) - 3);
     int qx = 0, qy = 0;                                 // offset from 4*(fx,fy), quarter-pel units
     uint32_t centre_key = 0;
     // candidate i: 0 centre, then (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1); packed 2-bit (offset + 1) tables
     const uint32_t OXP = 0x24891u, OYP = 0x2A501u;
+    // P_8x8: every candidate's SATD is also summed per 8x8 quadrant (the first two steps of the 16-lane reduction) and each
+    // quadrant keeps its own best candidate: key = (SATD8x8 + lambda * bits) << 5 | sequence number (0..8 half-pel ring,
+    // 9..16 quarter-pel ring). All lanes of a quadrant hold the same bq.
+    uint32_t bq = 0xffffffffu;
+    int hx = 0, hy = 0;                                 // half-pel winner = centre of the quarter-pel ring
 #pragma unroll 1
     for (int step = 2; step >= 1; step--) {
         uint32_t bk = step == 1 ? (centre_key & ~15u) : 0xffffffffu;
@@ -341,17 +358,36 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
             const int ci = i <= 8 ? i : 0;
             const int ox = qx + step * ((int)((OXP >> (2 * ci)) & 3) - 1), oy = qy + step * ((int)((OYP >> (2 * ci)) & 3) - 1);
             uint32_t P[4]; pred_rows_qpel(sm, o1, bx, by, ox, oy, rx, P);
-            const int sat = half_reduce16(satd_rows(P, Ts));
-            uint32_t key = 0xffffffffu;
+            int sq = satd_rows(P, Ts);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2);       // this lane's 8x8 quadrant
+            int sat = sq + __shfl_xor_sync(0xffffffffu, sq, 4); sat += __shfl_xor_sync(0xffffffffu, sat, 8);
+            uint32_t key = 0xffffffffu, kq = 0xffffffffu;
             const int bits = __shfl_sync(0xffffffffu, mvb, ox + 3) + __shfl_sync(0xffffffffu, mvb, oy + 11);
-            if (i <= 8) key = ((uint32_t)(sat + lambda * bits) << 4) | (uint32_t)i;
+            if (i <= 8) {
+                key = ((uint32_t)(sat + lambda * bits) << 4) | (uint32_t)i;
+                kq = ((uint32_t)(sq + lambda * bits) << 5) | (uint32_t)(step == 2 ? i : 8 + i);
+            }
             key = min(key, __shfl_xor_sync(0xffffffffu, key, 16));
-            bk = min(bk, key);
+            kq = min(kq, __shfl_xor_sync(0xffffffffu, kq, 16));
+            bk = min(bk, key); bq = min(bq, kq);
         }
         const int ci = bk & 15;
         qx += step * ((int)((OXP >> (2 * ci)) & 3) - 1); qy += step * ((int)((OYP >> (2 * ci)) & 3) - 1); centre_key = bk;
+        if (step == 2) { hx = qx; hy = qy; }
     }
-    const int mvx = 4 * fx + qx, mvy = 4 * fy + qy, inter_cost = (int)(centre_key >> 4);
+    const int cost16 = (int)(centre_key >> 4);
+    // this lane's quadrant vector (offset from the full-pel winner) and the P_8x8 cost
+    int lx, ly;
+    {
+        const int sq_ = bq & 31, ci = sq_ < 9 ? sq_ : sq_ - 8, st = sq_ < 9 ? 2 : 1;
+        lx = (sq_ < 9 ? 0 : hx) + st * ((int)((OXP >> (2 * ci)) & 3) - 1); ly = (sq_ < 9 ? 0 : hy) + st * ((int)((OYP >> (2 * ci)) & 3) - 1);
+    }
+    const int c8q = (int)(bq >> 5);
+    const int cost8 = __shfl_sync(0xffffffffu, c8q, 0) + __shfl_sync(0xffffffffu, c8q, 4) + __shfl_sync(0xffffffffu, c8q, 8) +
+                      __shfl_sync(0xffffffffu, c8q, 12) + lambda * P8X8_BIAS_BITS;
+    const bool use8 = cost8 < cost16;
+    if (!use8) { lx = qx; ly = qy; }
+    const int inter_cost = use8 ? cost8 : cost16;
 
     // intra estimate from source neighbours (staged above): V, H, DC 16x16 by SATD
     int ie = 1 << 30;
@@ -394,8 +430,11 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     const int cx0 = mx * 8 + (cb & 1) * 4, cy0 = my * 8 + (cb >> 1) * 4;
     int nnz = 0; bool dc_nz = false;
     int p[16], c[16];
+    // the vector of this lane's 8x8 partition: luma lanes own it, chroma block cb lies under partition cb
+    const int plx = __shfl_sync(0xffffffffu, lx, is_luma ? lane : 4 * cb), ply = __shfl_sync(0xffffffffu, ly, is_luma ? lane : 4 * cb);
+    const int mvx = 4 * fx + plx, mvy = 4 * fy + ply;
     if (is_luma) {
-        uint32_t P[4]; pred_rows_qpel(sm, o1, bx, by, qx, qy, 0, P);
+        uint32_t P[4]; pred_rows_qpel(sm, o1, bx, by, plx, ply, 0, P);
 #pragma unroll
         for (int y = 0; y < 4; y++) {
             const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
@@ -469,10 +508,13 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     for (int k = 0; k < 4; k++) if ((nzmask >> (4 * k)) & 15) cbp |= 1 << k;
     cbp |= ((nzmask >> 16) & 255) ? 32 : ((dcmask ? 16 : 0));
     if (lane < 24) mi->nnz[lane] = (uint8_t)nnz;
+    // word 0: type, cbp; word 1: vector of partition 0 (= the 16x16 vector); words 2-5: the four partition vectors
+    const uint32_t mvw = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
+    const uint32_t mvq = __shfl_sync(0xffffffffu, mvw, lane == 0 ? 0 : 4 * ((lane - 1) & 3));
     if (lane == 0) {
-        reinterpret_cast<uint32_t *>(mi)[0] = (uint32_t)MB_P16x16 | ((uint32_t)cbp << 24);
-        reinterpret_cast<uint32_t *>(mi)[1] = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
-    } else if (lane < 5) reinterpret_cast<uint32_t *>(mi)[1 + lane] = 0;
+        reinterpret_cast<uint32_t *>(mi)[0] = (use8 ? (uint32_t)MB_P8x8 : (uint32_t)MB_P16x16) | ((uint32_t)cbp << 24);
+        reinterpret_cast<uint32_t *>(mi)[1] = mvq;
+    } else if (lane < 5) reinterpret_cast<uint32_t *>(mi)[1 + lane] = mvq;
 }
 
 } // namespace b200

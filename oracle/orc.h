@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 /* ---- macroblock types used in the per-MB side arrays (shared layout with the CUDA path) ---- */
-enum { ORC_MB_P16x16 = 0, ORC_MB_I16x16 = 1, ORC_MB_I4x4 = 2, ORC_MB_PSKIP = 3 };
+enum { ORC_MB_P16x16 = 0, ORC_MB_I16x16 = 1, ORC_MB_I4x4 = 2, ORC_MB_PSKIP = 3, ORC_MB_P8x8 = 4 };
 
 /* Per-MB coefficient record: everything CAVLC needs, 816 bytes. Levels are in zig-zag scan order. */
 typedef struct {
@@ -44,8 +44,11 @@ typedef struct {
     uint8_t  i16_mode;       /* Intra16x16PredMode 0..3 */
     uint8_t  chroma_mode;    /* intra_chroma_pred_mode 0..3 */
     uint8_t  cbp;            /* bits 0..3 luma 8x8, bits 4..5 chroma (0,1,2) */
-    int16_t  mv[2];          /* quarter-pel */
-    uint8_t  i4_mode[16];    /* Intra4x4PredMode per blkIdx */
+    int16_t  mv[2];          /* quarter-pel; the 16x16 vector (partition 0 for P_8x8) */
+    union {
+        uint8_t i4_mode[16]; /* intra MBs: Intra4x4PredMode per blkIdx */
+        int16_t mv8[4][2];   /* inter MBs: vector of each 8x8 partition (all equal for P_L0_16x16 / P_Skip) */
+    };
     uint8_t  nnz[24];        /* total_coeff: 0..15 luma blkIdx, 16..19 Cb, 20..23 Cr (AC count for I16x16/chroma) */
 } OrcMbInfo;
 
@@ -58,6 +61,7 @@ typedef struct {
     int level_idc;           /* 0 = derive from size/fps */
     int fps;
     int no_i4x4;             /* 1: Intra_16x16 only (quality A/B runs in tests; the product has no such switch) */
+    int no_p8x8;             /* 1: P_L0_16x16 only (same purpose) */
 } OrcConfig;
 
 OrcEncoder *orc_create(const OrcConfig *cfg);

@@ -188,19 +188,22 @@ static int qpel_sample(const OrcEncoder *e, int xq, int yq)
 int orc_dbg_qpel(const OrcEncoder *e, int xq, int yq) { return qpel_sample(e, xq, yq); }
 void orc_dbg_build_halfpel(OrcEncoder *e) { build_halfpel(e); }
 
-static void mc_luma(const OrcEncoder *e, int x0, int y0, int mvx, int mvy, uint8_t *dst /*16x16*/)
+/* luma prediction of a bw x bh block whose top-left sample is (x0,y0), written into a 16-wide buffer */
+static void mc_luma_blk(const OrcEncoder *e, int x0, int y0, int bw, int bh, int mvx, int mvy, uint8_t *dst /*stride 16*/)
 {
-    for (int y = 0; y < 16; y++)
-        for (int x = 0; x < 16; x++) dst[y * 16 + x] = (uint8_t)qpel_sample(e, 4 * (x0 + x) + mvx, 4 * (y0 + y) + mvy);
+    for (int y = 0; y < bh; y++)
+        for (int x = 0; x < bw; x++) dst[y * 16 + x] = (uint8_t)qpel_sample(e, 4 * (x0 + x) + mvx, 4 * (y0 + y) + mvy);
 }
-static void mc_chroma(const OrcEncoder *e, int comp, int cx0, int cy0, int mvx, int mvy, uint8_t *dst /*8x8*/)
+static void mc_luma(const OrcEncoder *e, int x0, int y0, int mvx, int mvy, uint8_t *dst /*16x16*/) { mc_luma_blk(e, x0, y0, 16, 16, mvx, mvy, dst); }
+static void mc_chroma_blk(const OrcEncoder *e, int comp, int cx0, int cy0, int bw, int bh, int mvx, int mvy, uint8_t *dst /*stride 8*/)
 {
-    for (int y = 0; y < 8; y++)
-        for (int x = 0; x < 8; x++)
+    for (int y = 0; y < bh; y++)
+        for (int x = 0; x < bw; x++)
             dst[y * 8 + x] = (uint8_t)orc_interp_chroma(e->ref[comp], e->wc / 2, e->wc / 2, e->hc / 2,
                                                         8 * (cx0 + x) + mvx, 8 * (cy0 + y) + mvy);
 }
 
+#define ORC_P8X8_BIAS_BITS 8   /* extra header bits of P_8x8 over P_L0_16x16: mb_type ue(3) vs ue(0), four sub_mb_type ue(0) */
 static int mv_bits(int mvx, int mvy) { return orc_se_len(mvx) + orc_se_len(mvy); }
 
 /* SAD of a bw x bh block with clamped coordinates on both planes (same dimensions w x h) */
@@ -237,37 +240,69 @@ static void motion_search(OrcEncoder *e, int mx, int my, int lambda)
             if (key < best) { best = key; bx = vx; by = vy; }
         }
     e->me[1][mb * 2] = (int16_t)bx; e->me[1][mb * 2 + 1] = (int16_t)by;
+    /* Estimate of this MB's MV predictor for the rate term of levels 0 and below: the 8.4.1.3 median taken over the LEVEL-1
+     * vectors of the left, upper and upper-right (else upper-left) neighbours, scaled to quarter-pel (x8). It needs no final
+     * vector of any neighbour, so the search stays independent per MB; missing neighbours count as zero vectors. */
+    int ppx, ppy;
+    {
+        int top = !row_is_slice_top(e, my), ax = 0, ay = 0, tx = 0, ty = 0, rx = 0, ry = 0;
+        const int16_t *m1 = e->me[1];
+        if (mx > 0) { ax = m1[(mb - 1) * 2]; ay = m1[(mb - 1) * 2 + 1]; }
+        if (top) { tx = m1[(mb - e->mbw) * 2]; ty = m1[(mb - e->mbw) * 2 + 1]; }
+        if (top && mx + 1 < e->mbw) { rx = m1[(mb - e->mbw + 1) * 2]; ry = m1[(mb - e->mbw + 1) * 2 + 1]; }
+        else if (top && mx > 0) { rx = m1[(mb - e->mbw - 1) * 2]; ry = m1[(mb - e->mbw - 1) * 2 + 1]; }
+        ppx = 8 * median3(ax, tx, rx); ppy = 8 * median3(ay, ty, ry);
+    }
     cx = 2 * bx; cy = 2 * by; best = 0xffffffffu;
     for (int i = 0; i < 26; i++) {
         int vx = i < 25 ? cx + i % 5 - 2 : 0, vy = i < 25 ? cy + i / 5 - 2 : 0;
         int c = sad_clamped(e->src[0], e->ref[0], e->wc, e->hc, 16 * mx, 16 * my, 16 * mx + vx, 16 * my + vy, 16, 16)
-              + lambda * mv_bits(4 * vx, 4 * vy);
+              + lambda * mv_bits(4 * vx - ppx, 4 * vy - ppy);
         uint32_t key = ((uint32_t)c << 5) | (uint32_t)i;
         if (key < best) { best = key; bx = vx; by = vy; }
     }
     e->me[0][mb * 2] = (int16_t)bx; e->me[0][mb * 2 + 1] = (int16_t)by;
-    /* sub-pel: centre + 8 neighbours at step 2 (half), then at step 1 (quarter) */
+    /* sub-pel: centre + 8 neighbours at step 2 (half), then at step 1 (quarter). Every candidate's SATD is also kept per 8x8
+     * quadrant: each quadrant remembers its own best candidate (key = (SATD8x8 + lambda*mv bits) << 5 | candidate sequence
+     * number), which is the motion search of the four P_L0_8x8 partitions at no extra SATD work. */
     static const int8_t OX[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 }, OY[9] = { 0, -1, -1, -1, 0, 0, 1, 1, 1 };
     int qx = 4 * bx, qy = 4 * by; uint8_t pred[256];
     const uint8_t *s = e->src[0] + (size_t)my * 16 * e->wc + mx * 16;
-    uint32_t centre_key = 0;
+    uint32_t centre_key = 0, bestq[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu }; int mvq[4][2] = { { 0 } };
     for (int step = 2; step >= 1; step--) {
         best = 0xffffffffu; int nx = qx, ny = qy;
         for (int i = 0; i < 9; i++) {
             uint32_t key;
             if (i == 0 && step == 1) key = centre_key & ~15u;
             else {
-                int vx = qx + step * OX[i], vy = qy + step * OY[i];
+                int vx = qx + step * OX[i], vy = qy + step * OY[i], bits = mv_bits(vx - ppx, vy - ppy), tot = 0;
                 mc_luma(e, 16 * mx, 16 * my, vx, vy, pred);
-                int c = orc_satd16x16(s, e->wc, pred, 16) + lambda * mv_bits(vx, vy);
-                key = ((uint32_t)c << 4) | (uint32_t)i;
+                for (int q = 0; q < 4; q++) {
+                    int o = (q >> 1) * 8 * e->wc + (q & 1) * 8, po = (q >> 1) * 8 * 16 + (q & 1) * 8;
+                    int sq = orc_satd4x4(s + o, e->wc, pred + po, 16) + orc_satd4x4(s + o + 4, e->wc, pred + po + 4, 16)
+                           + orc_satd4x4(s + o + 4 * e->wc, e->wc, pred + po + 64, 16) + orc_satd4x4(s + o + 4 * e->wc + 4, e->wc, pred + po + 68, 16);
+                    uint32_t kq = ((uint32_t)(sq + lambda * bits) << 5) | (uint32_t)(step == 2 ? i : 8 + i);
+                    if (kq < bestq[q]) { bestq[q] = kq; mvq[q][0] = vx; mvq[q][1] = vy; }
+                    tot += sq;
+                }
+                key = ((uint32_t)(tot + lambda * bits) << 4) | (uint32_t)i;
             }
             if (key < best) { best = key; nx = qx + step * OX[i]; ny = qy + step * OY[i]; }
         }
         qx = nx; qy = ny; centre_key = best;
     }
-    e->mbi[mb].mv[0] = (int16_t)qx; e->mbi[mb].mv[1] = (int16_t)qy;
-    e->inter_cost[mb] = (int32_t)(best >> 4);
+    OrcMbInfo *mi = &e->mbi[mb];
+    int cost16 = (int)(best >> 4), cost8 = lambda * ORC_P8X8_BIAS_BITS;
+    for (int q = 0; q < 4; q++) cost8 += (int)(bestq[q] >> 5);
+    mi->mv[0] = (int16_t)qx; mi->mv[1] = (int16_t)qy;
+    if (cost8 < cost16 && !e->cfg.no_p8x8) {
+        mi->mb_type = ORC_MB_P8x8; e->inter_cost[mb] = cost8;
+        for (int q = 0; q < 4; q++) { mi->mv8[q][0] = (int16_t)mvq[q][0]; mi->mv8[q][1] = (int16_t)mvq[q][1]; }
+        mi->mv[0] = mi->mv8[0][0]; mi->mv[1] = mi->mv8[0][1];
+    } else {
+        mi->mb_type = ORC_MB_P16x16; e->inter_cost[mb] = cost16;
+        for (int q = 0; q < 4; q++) { mi->mv8[q][0] = (int16_t)qx; mi->mv8[q][1] = (int16_t)qy; }
+    }
 }
 
 /* ---- Phase A: intra estimate from SOURCE neighbours (V/H/DC 16x16), used only to choose intra vs inter
@@ -359,9 +394,12 @@ static void code_inter_mb(OrcEncoder *e, int mx, int my, int qp)
 {
     int mb = my * e->mbw + mx, st = e->wc; OrcMbInfo *mi = &e->mbi[mb]; OrcMbCoef *co = &e->coef[mb];
     uint8_t *py = e->pred_y + (size_t)mb * 256, *pc = e->pred_c + (size_t)mb * 128;
-    mc_luma(e, 16 * mx, 16 * my, mi->mv[0], mi->mv[1], py);
-    mc_chroma(e, 1, 8 * mx, 8 * my, mi->mv[0], mi->mv[1], pc);
-    mc_chroma(e, 2, 8 * mx, 8 * my, mi->mv[0], mi->mv[1], pc + 64);
+    for (int q = 0; q < 4; q++) {      /* one vector per 8x8 partition (all equal for P_L0_16x16) */
+        int ox = (q & 1) * 8, oy = (q >> 1) * 8, vx = mi->mv8[q][0], vy = mi->mv8[q][1];
+        mc_luma_blk(e, 16 * mx + ox, 16 * my + oy, 8, 8, vx, vy, py + oy * 16 + ox);
+        mc_chroma_blk(e, 1, 8 * mx + ox / 2, 8 * my + oy / 2, 4, 4, vx, vy, pc + (oy / 2) * 8 + ox / 2);
+        mc_chroma_blk(e, 2, 8 * mx + ox / 2, 8 * my + oy / 2, 4, 4, vx, vy, pc + 64 + (oy / 2) * 8 + ox / 2);
+    }
     const uint8_t *s = e->src[0] + (size_t)my * 16 * st + mx * 16; uint8_t *r = e->rec[0] + (size_t)my * 16 * st + mx * 16;
     int cbp = 0;
     memset(co, 0, sizeof *co);
@@ -375,7 +413,7 @@ static void code_inter_mb(OrcEncoder *e, int mx, int my, int qp)
         for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) r[(by + y) * st + bx + x] = (uint8_t)clip255(py[(by + y) * 16 + bx + x] + rr[y * 4 + x]);
     }
     cbp |= code_chroma(e, mx, my, pc, qp, 0) << 4;
-    mi->cbp = (uint8_t)cbp; mi->mb_type = ORC_MB_P16x16;
+    mi->cbp = (uint8_t)cbp;
 }
 
 /* ---- intra predictors, 8.3.3 (Intra_16x16) and 8.3.4 (chroma), from the pre-deblock reconstruction ---- */
@@ -612,24 +650,44 @@ static void code_intra_mb(OrcEncoder *e, int mx, int my, int qp)
     mi->cbp = (uint8_t)(luma_cbp | (ccbp << 4));
 }
 
-/* ---- Phase D: luma MV prediction for a 16x16 partition (8.4.1.3) and the P_Skip vector (8.4.1.1) ---- */
+/* ---- Phase D: luma MV prediction (8.4.1.3, neighbours per 6.4.11.7) for the 16x16 partition or one 8x8 partition, and
+ * the P_Skip vector (8.4.1.1). One reference picture, so refIdx is 0 for inter neighbours and -1 for intra ones. ---- */
+#define IS_INTER(p) ((p)->mb_type == ORC_MB_P16x16 || (p)->mb_type == ORC_MB_PSKIP || (p)->mb_type == ORC_MB_P8x8)
+typedef struct { int avail, ref, x, y; } NbMv;
+/* the partition covering luma location (x,y) relative to MB (mx,my); partitions of the current MB with index >= cur_part
+ * are not decoded yet */
+static NbMv nb_at(const OrcEncoder *e, int mx, int my, int x, int y, int cur_part)
+{
+    NbMv r = { 0, -1, 0, 0 };
+    int nx = mx + (x < 0 ? -1 : x > 15 ? 1 : 0), ny = my - (y < 0);
+    if (nx < 0 || nx >= e->mbw) return r;
+    if (ny != my && row_is_slice_top(e, my)) return r;
+    if (ny == my && nx > mx) return r;
+    int part = (((y + 16) & 15) >> 3) * 2 + (((x + 16) & 15) >> 3);
+    if (nx == mx && ny == my && part >= cur_part) return r;
+    const OrcMbInfo *m = &e->mbi[ny * e->mbw + nx];
+    r.avail = 1;
+    if (IS_INTER(m)) { r.ref = 0; r.x = m->mv8[part][0]; r.y = m->mv8[part][1]; }
+    return r;
+}
+/* part < 0: the 16x16 partition; else the 8x8 partition `part` */
+static void predict_mv_part(const OrcEncoder *e, int mx, int my, int part, int *pmx, int *pmy, NbMv *outA, NbMv *outB)
+{
+    int px = part < 0 ? 0 : (part & 1) * 8, py = part < 0 ? 0 : (part >> 1) * 8, w = part < 0 ? 16 : 8, cur = part < 0 ? 0 : part;
+    NbMv A = nb_at(e, mx, my, px - 1, py, cur), B = nb_at(e, mx, my, px, py - 1, cur), C = nb_at(e, mx, my, px + w, py - 1, cur);
+    if (!C.avail) C = nb_at(e, mx, my, px - 1, py - 1, cur);
+    if (outA) *outA = A;
+    if (outB) *outB = B;
+    if (!B.avail && !C.avail && A.avail) { B = A; C = A; }
+    int n = (A.ref == 0) + (B.ref == 0) + (C.ref == 0);
+    if (n == 1) { const NbMv *o = A.ref == 0 ? &A : B.ref == 0 ? &B : &C; *pmx = o->x; *pmy = o->y; }
+    else { *pmx = median3(A.x, B.x, C.x); *pmy = median3(A.y, B.y, C.y); }
+}
 static void predict_mv(const OrcEncoder *e, int mx, int my, int *pmx, int *pmy, int *skx, int *sky)
 {
-    int top_ok = !row_is_slice_top(e, my);
-    int availA = mx > 0, availB = top_ok, availC = top_ok && mx + 1 < e->mbw, availD = top_ok && mx > 0;
-    const OrcMbInfo *m = &e->mbi[my * e->mbw + mx];
-    const OrcMbInfo *A = availA ? m - 1 : 0, *B = availB ? m - e->mbw : 0, *C = availC ? m - e->mbw + 1 : (availD ? m - e->mbw - 1 : 0);
-    int availCD = availC || availD;
-    int refA = -1, refB = -1, refC = -1, ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
-#define IS_INTER(p) ((p)->mb_type == ORC_MB_P16x16 || (p)->mb_type == ORC_MB_PSKIP)
-    if (A && IS_INTER(A)) { refA = 0; ax = A->mv[0]; ay = A->mv[1]; }
-    if (B && IS_INTER(B)) { refB = 0; bx = B->mv[0]; by = B->mv[1]; }
-    if (C && IS_INTER(C)) { refC = 0; cx = C->mv[0]; cy = C->mv[1]; }
-    if (!availB && !availCD && availA) { refB = refA; bx = ax; by = ay; refC = refA; cx = ax; cy = ay; }
-    int n = (refA == 0) + (refB == 0) + (refC == 0);
-    if (n == 1) { if (refA == 0) { *pmx = ax; *pmy = ay; } else if (refB == 0) { *pmx = bx; *pmy = by; } else { *pmx = cx; *pmy = cy; } }
-    else { *pmx = median3(ax, bx, cx); *pmy = median3(ay, by, cy); }
-    if (!availA || !availB || (refA == 0 && ax == 0 && ay == 0) || (refB == 0 && bx == 0 && by == 0)) { *skx = 0; *sky = 0; }
+    NbMv A, B;
+    predict_mv_part(e, mx, my, -1, pmx, pmy, &A, &B);
+    if (!A.avail || !B.avail || (A.ref == 0 && A.x == 0 && A.y == 0) || (B.ref == 0 && B.x == 0 && B.y == 0)) { *skx = 0; *sky = 0; }
     else { *skx = *pmx; *sky = *pmy; }
 }
 
@@ -677,6 +735,16 @@ static void write_mb(OrcEncoder *e, BitWriter *b, int mx, int my, int is_p)
         bw_ue(b, CBP_TO_CODENUM_INTRA[mi->cbp]);
         if (mi->cbp) bw_se(b, 0);
         for (int k = 0; k < 16; k++) if (cl & (1 << (k >> 2))) orc_write_residual_block(b, co->luma[k], 16, luma_nc(e, mx, my, k));
+    } else if (mi->mb_type == ORC_MB_P8x8) {
+        bw_ue(b, 3);                                           /* P_8x8 */
+        for (int q = 0; q < 4; q++) bw_ue(b, 0);               /* sub_mb_type P_L0_8x8; ref_idx_l0 is not coded with one reference */
+        for (int q = 0; q < 4; q++) {
+            int pmx, pmy; predict_mv_part(e, mx, my, q, &pmx, &pmy, 0, 0);
+            bw_se(b, mi->mv8[q][0] - pmx); bw_se(b, mi->mv8[q][1] - pmy);
+        }
+        bw_ue(b, CBP_TO_CODENUM_INTER[mi->cbp]);
+        if (mi->cbp) bw_se(b, 0);
+        for (int k = 0; k < 16; k++) if (cl & (1 << (k >> 2))) orc_write_residual_block(b, co->luma[k], 16, luma_nc(e, mx, my, k));
     } else {
         int pmx, pmy, sx, sy; predict_mv(e, mx, my, &pmx, &pmy, &sx, &sy);
         bw_ue(b, 0);                                           /* P_L0_16x16 */
@@ -708,13 +776,12 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
                 memset(&e->mbi[mb], 0, sizeof(OrcMbInfo));
                 motion_search(e, mx, my, lambda);
                 int ie = intra_estimate(e, mx, my);
-                e->mbi[mb].mb_type = (ie + lambda * ORC_INTRA_BIAS_BITS < e->inter_cost[mb]) ? ORC_MB_I16x16 : ORC_MB_P16x16;
-                if (e->mbi[mb].mb_type == ORC_MB_I16x16) e->mbi[mb].mv[0] = e->mbi[mb].mv[1] = 0;
+                if (ie + lambda * ORC_INTRA_BIAS_BITS < e->inter_cost[mb]) { memset(&e->mbi[mb], 0, sizeof(OrcMbInfo)); e->mbi[mb].mb_type = ORC_MB_I16x16; }
             }
         /* Phase B */
         for (int my = 0; my < e->mbh; my++)
             for (int mx = 0; mx < e->mbw; mx++)
-                if (e->mbi[my * e->mbw + mx].mb_type == ORC_MB_P16x16) code_inter_mb(e, mx, my, qp);
+                if (e->mbi[my * e->mbw + mx].mb_type == ORC_MB_P16x16 || e->mbi[my * e->mbw + mx].mb_type == ORC_MB_P8x8) code_inter_mb(e, mx, my, qp);
     } else {
         memset(e->mbi, 0, (size_t)n * sizeof(OrcMbInfo));
         for (int i = 0; i < n; i++) e->mbi[i].mb_type = ORC_MB_I16x16;

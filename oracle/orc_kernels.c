@@ -280,7 +280,8 @@ static int boundary_strength(const OrcMbInfo *mp, int bxp, int byp, const OrcMbI
     static const uint8_t XY2BLK[4][4] = { { 0, 1, 4, 5 }, { 2, 3, 6, 7 }, { 8, 9, 12, 13 }, { 10, 11, 14, 15 } };
     if (mb_is_intra(mp) || mb_is_intra(mq)) return mb_edge ? 4 : 3;
     if (mp->nnz[XY2BLK[byp][bxp]] || mq->nnz[XY2BLK[byq][bxq]]) return 2;
-    if (iabs(mp->mv[0] - mq->mv[0]) >= 4 || iabs(mp->mv[1] - mq->mv[1]) >= 4) return 1;
+    const int16_t *vp = mp->mv8[(byp >> 1) * 2 + (bxp >> 1)], *vq = mq->mv8[(byq >> 1) * 2 + (bxq >> 1)];
+    if (iabs(vp[0] - vq[0]) >= 4 || iabs(vp[1] - vq[1]) >= 4) return 1;
     return 0;
 }
 

@@ -261,9 +261,13 @@ def test_deblock_kernel_on_random_macroblock_info(enc, orc):
         amp = 2 if qp < 30 else 12
         pix = np.clip(rng.integers(60, 200) + rng.integers(-amp, amp + 1, mbw * mbh * 384), 0, 255).astype(np.uint8)
         mbi = np.zeros(mbw * mbh, enc.MBINFO_DTYPE)
-        mbi["mb_type"] = rng.choice([0, 0, 1, 3], mbw * mbh)
+        mbi["mb_type"] = rng.choice([0, 0, 1, 3, 4], mbw * mbh)
         mbi["nnz"] = rng.integers(0, 3, (mbw * mbh, 24)) * (rng.random((mbw * mbh, 24)) < 0.3)
-        mbi["mv"] = rng.integers(-9, 10, (mbw * mbh, 2))
+        mv8 = np.repeat(rng.integers(-9, 10, (mbw * mbh, 1, 2)), 4, axis=1)          # one vector per 8x8 partition ...
+        split = mbi["mb_type"] == 4
+        mv8[split] = rng.integers(-9, 10, (int(split.sum()), 4, 2))                  # ... different ones inside P_8x8 MBs
+        mbi["mv"] = mv8[:, 0]
+        mbi["i4_mode"] = mv8.astype("<i2").reshape(mbw * mbh, 8).view(np.uint8).reshape(mbw * mbh, 16)   # union with mv8[4][2]
         want = pix.copy(); ny = mbw * mbh * 256
         O.orc_deblock_frame(want.ctypes.data, mbw * 16, want.ctypes.data + ny, want.ctypes.data + ny + ny // 4, mbw * 8, mbw, mbh, _p(mbi), qp)
         got = pix.copy()
