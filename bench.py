@@ -193,12 +193,21 @@ def run_b200(args):
                "avg_batch": round((f1.value - f0.value) / max(1, b1.value - b0.value), 1),
                "note": "one Python thread per session blocked in b200enc_encode (auto_batch scheduler); host frames in, bitstreams out"}
         groups = new_groups(); batch = groups[0][1]; sess += [x for g in groups for x in g[0]]
-    # per-kernel shares of one step (CUDA events around each launch)
-    batch.set_profiling(True)
-    pstep = 2 * args.warmup + 2 * args.steps + 1
-    batch.encode_ptrs([dpool[pool_index(pstep, i)] for i in groups[0][2]], 1)
+    # per-kernel shares of one P step over ALL sessions of the GPU in a single batch (CUDA events around each launch on the
+    # batch's stream); fresh sessions, so two untimed frames first (IDR + one P)
+    for g_ in groups:
+        g_[1].close()
+    for x in sess:
+        x.close()
+    sess = [enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=-1, search_range=16, device=dev) for _ in range(S)]
+    batch = enc.Batch(dev, sess)
+    groups = [(sess, batch, list(range(S)))]
+    for k in range(3):
+        if k == 2:
+            batch.set_profiling(True)
+        batch.encode_ptrs([dpool[pool_index(k, i)] for i in range(S)], 1)
     kt = batch.kernel_times()
-    Sp = len(groups[0][2])               # sessions in the profiled batch
+    Sp = S                               # sessions in the profiled batch
     batch.set_profiling(False)
     tot = sum(ms for _, ms in kt) or 1.0
     top = max(kt, key=lambda x: x[1])
@@ -213,13 +222,13 @@ def run_b200(args):
         npx = W * 1088
         # algorithmic bytes per P frame: src 1.5 + ref 1.5 + recon 1.5 B/px for ME+coding, +3.0 for the in-place deblock pass
         alg_bytes = {"k_me_fine": 4.5 * npx, "k_me_coarse": 2 * 0.3125 * npx, "k_deblock_wave": 3.0 * npx, "k_intra_wave": 3.0 * npx,
-                     "k_cavlc_mb": 8160 * 864.0, "k_ingest_planar": 3.0 * npx, "k_ingest_rgba": 5.5 * npx}.get(top[0], 4.5 * npx) * Sp
+                     "k_cavlc_mb": 8160 * 864.0, "k_ingest_planar": 3.0 * npx, "k_ingest_rgba": 5.5 * npx, "k_refplanes": 5.0 * npx}.get(top[0], 4.5 * npx) * Sp
         ach = alg_bytes / (top[1] * 1e-3) / 1e9
         gi, clk = C.c_double(), C.c_int()
         L.b200k_vabsdiff4_peak(dev, C.byref(gi), C.byref(clk))
         me_fine = dict(kt).get("k_me_fine", 0.0); me_coarse = dict(kt).get("k_me_coarse", 0.0)
         # implemented search, pixel absolute differences per MB: L2 81*64, L1 25*64, L0 26*256; SATD stage counted as 17*256
-        absdiff_mb = 81 * 64 + 25 * 64 + 26 * 256 + 17 * 256
+        absdiff_mb = 81 * 64 + 25 * 64 + 26 * 256 + 17 * 256 + 3 * 256      # + the intra estimate's three 16x16 SATDs
         me_ms = me_fine + me_coarse
         int_ach = (absdiff_mb / 4.0) * 8160 * Sp / 32.0 / (me_ms * 1e-3) / 1e9 if me_ms > 0 else 0.0   # warp-instructions -> G lane... see DESIGN 5
         cpu = cpu_baseline_sample(threads=1, frames=args.cpu_frames) if world == 1 and not args.no_cpu else None
@@ -252,6 +261,7 @@ def run_b200(args):
             line["e2e_caller_threads"] = thr
     for s in sess:
         s.close()
+    batch.close()
     if use_dist:
         dist.barrier(); dist.destroy_process_group()
     if line:

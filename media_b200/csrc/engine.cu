@@ -509,7 +509,9 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
     g.num_slices = std::min(c.num_slices, g.mbh); g.search_range = c.search_range; s->cfg.num_slices = g.num_slices;
     { const int base = g.mbh / g.num_slices, rem = g.mbh % g.num_slices; int r = 0;
       for (int i = 0; i < g.num_slices; i++) { g.slice_row0[i] = r; r += base + (i < rem); }
-      for (int i = g.num_slices; i <= B200_MAX_SLICES; i++) g.slice_row0[i] = r; }
+      for (int i = g.num_slices; i <= B200_MAX_SLICES; i++) g.slice_row0[i] = r;
+      memset(g.slice_top, 0, sizeof g.slice_top);
+      for (int i = 0; i < g.num_slices; i++) g.slice_top[g.slice_row0[i] >> 5] |= 1u << (g.slice_row0[i] & 31); }
     {   // borders of the padded planes: the widest reach of a search window / interpolation tap past the picture edge
         auto up = [](int v, int a) { return (v + a - 1) / a * a; };
         g.lp = up(c.search_range + 10, 16); g.ls = g.wc + 2 * g.lp;

@@ -44,6 +44,7 @@ struct Geom {
     // padded reference / pyramid planes (edge-replicated borders, so no motion-search or MC read needs clamping):
     // pad and row stride of the luma reference planes, of the chroma reference planes, and of pyramid levels 1 and 2
     int lp, ls, cp, cs, p1, s1, p2, s2;
+    uint32_t slice_top[8];        // bit my set: MB row my is the first row of a slice (mbh <= 256)
 };
 
 // Per-session, per-frame device descriptor (one array element per session in the batch).
@@ -187,12 +188,7 @@ __device__ __forceinline__ int pos_class(int pos) { return ((pos & 1) && (pos & 
 __device__ __forceinline__ int se_len(int v) { unsigned x = (v > 0 ? 2u * v - 1u : (unsigned)(-2 * v)) + 1u; return 2 * (31 - __clz(x)) + 1; }
 __device__ __forceinline__ int ue_len(unsigned v) { return 2 * (31 - __clz(v + 1u)) + 1; }
 __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
-__device__ __forceinline__ bool row_is_slice_top(const Geom &g, int my)
-{
-    bool t = false;
-    for (int s = 0; s < g.num_slices; s++) t |= (g.slice_row0[s] == my);
-    return t;
-}
+__device__ __forceinline__ bool row_is_slice_top(const Geom &g, int my) { return (g.slice_top[my >> 5] >> (my & 31)) & 1u; }
 
 // forward core transform of a 4x4 residual held in registers (role of WelsDctT4_c)
 __device__ __forceinline__ void fdct4x4(int r[16])
