@@ -24,12 +24,45 @@ import numpy as np  # noqa: E402
 W, H, FPS, BITRATE, GOP = 1920, 1080, 30, 4_000_000, 300
 METRIC = "1080p H.264 encode frames/s per GPU"
 POOL_FRAMES = 16
+FMT, SLICES, SR, CQP, KIND, LABEL = 0, 1, 16, -1, "A", "Baseline CAVLC IPPP, CBR 4 Mbps @30fps each, gop 300, search +-16, 1 slice, content A (moving texture)"
+# Secondary workloads (BASELINE.json configs 2-4); the default, and what the driver runs, is the 1080p session workload above.
+WORKLOADS = {
+    "1080p": {},
+    "single": dict(sessions=1, groups=1, LABEL="ONE 1080p stream (config 2): Baseline CAVLC IPPP, CBR 4 Mbps @30fps, gop 300, search +-16, 1 slice, content A; latency-bound by construction"),
+    "rgba720": dict(W=1280, H=720, FMT=2, KIND="B", sessions=64, groups=2, BITRATE=2_000_000, METRIC="720p RGBA->I420 + H.264 encode frames/s per GPU",
+                    LABEL="RGBA8888 cloud-phone framebuffers (config 3), on-GPU RGBA->I420 + encode, Baseline CAVLC IPPP, CBR 2 Mbps @30fps each, gop 300, search +-16, content B (screen-like)"),
+    "4k": dict(W=3840, H=2160, SLICES=8, SR=64, CQP=26, sessions=1, groups=1, METRIC="2160p H.264 encode frames/s per GPU",
+               LABEL="ONE 3840x2160 stream (config 4): 8 slices, search +-64 + quarter-pel, const QP 26, content A; latency-bound by construction"),
+}
 
 
-def make_pool(n=POOL_FRAMES, kind="A"):
-    from media_b200.synth import Content
-    c = Content(kind, W, H)
-    return [c.frame(t) for t in range(n)]
+def apply_workload(args):
+    g = globals()
+    for k, v in WORKLOADS[args.workload].items():
+        if k in ("sessions", "groups"):
+            if getattr(args, k) is None:
+                setattr(args, k, v)
+        else:
+            g[k] = v
+    if args.sessions is None:
+        args.sessions = 96
+    if args.groups is None:
+        args.groups = 3
+
+
+def frame_bytes():
+    return W * H * 4 if FMT == 2 else W * H * 3 // 2
+
+
+def new_session(enc, dev, **kw):
+    return enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=CQP, num_slices=SLICES, search_range=SR, input_format=FMT, device=dev, **kw)
+
+
+def make_pool(n=POOL_FRAMES):
+    from media_b200.synth import Content, i420_to_rgba
+    c = Content(KIND, W, H)
+    fr = [c.frame(t) for t in range(n)]
+    return [np.ascontiguousarray(i420_to_rgba(f, W, H)).ravel() for f in fr] if FMT == 2 else fr
 
 
 def pool_index(step, sess, n=POOL_FRAMES):
@@ -86,7 +119,7 @@ def run_b200(args):
     S = args.sessions
     L = enc.lib()
     pool = make_pool()
-    fb = W * H * 3 // 2
+    fb = frame_bytes()
     # device-resident pool and pinned host pool
     import ctypes as C
     dpool = []
@@ -108,7 +141,7 @@ def run_b200(args):
     def new_groups():
         groups, sid = [], 0
         for n in group_sizes:
-            ss = [enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=-1, search_range=16, device=dev) for _ in range(n)]
+            ss = [new_session(enc, dev) for _ in range(n)]
             groups.append((ss, enc.Batch(dev, ss), list(range(sid, sid + n)))); sid += n
         return groups
 
@@ -167,7 +200,7 @@ def run_b200(args):
     if args.threads_e2e:
         for x in sess:
             x.close()
-        sess = [enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=-1, search_range=16, device=dev, auto_batch=1) for _ in range(S)]
+        sess = [new_session(enc, dev, auto_batch=1) for _ in range(S)]
         b0, f0, b1, f1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         nst = max(4, args.steps)
 
@@ -199,7 +232,7 @@ def run_b200(args):
         g_[1].close()
     for x in sess:
         x.close()
-    sess = [enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=-1, search_range=16, device=dev) for _ in range(S)]
+    sess = [new_session(enc, dev) for _ in range(S)]
     batch = enc.Batch(dev, sess)
     groups = [(sess, batch, list(range(S)))]
     for k in range(3):
@@ -219,27 +252,39 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        npx = W * 1088
+        npx = ((W + 15) // 16 * 16) * ((H + 15) // 16 * 16)
+        nmb = npx // 256
         # algorithmic bytes per P frame: src 1.5 + ref 1.5 + recon 1.5 B/px for ME+coding, +3.0 for the in-place deblock pass
         alg_bytes = {"k_me_fine": 4.5 * npx, "k_me_coarse": 2 * 0.3125 * npx, "k_deblock_wave": 3.0 * npx, "k_intra_wave": 3.0 * npx,
-                     "k_cavlc_mb": 8160 * 864.0, "k_ingest_planar": 3.0 * npx, "k_ingest_rgba": 5.5 * npx, "k_refplanes": 5.0 * npx}.get(top[0], 4.5 * npx) * Sp
+                     "k_cavlc_mb": nmb * 864.0, "k_ingest_planar": 3.0 * npx, "k_ingest_rgba": 5.5 * npx, "k_refplanes": 5.0 * npx}.get(top[0], 4.5 * npx) * Sp
         ach = alg_bytes / (top[1] * 1e-3) / 1e9
         gi, clk = C.c_double(), C.c_int()
         L.b200k_vabsdiff4_peak(dev, C.byref(gi), C.byref(clk))
         me_fine = dict(kt).get("k_me_fine", 0.0); me_coarse = dict(kt).get("k_me_coarse", 0.0)
         # implemented search, pixel absolute differences per MB: L2 81*64, L1 25*64, L0 26*256; SATD stage counted as 17*256
-        absdiff_mb = 81 * 64 + 25 * 64 + 26 * 256 + 17 * 256 + 3 * 256      # + the intra estimate's three 16x16 SATDs
+        absdiff_mb = (2 * SR // 4 + 1) ** 2 * 64 + 25 * 64 + 26 * 256 + 17 * 256 + 3 * 256      # + the intra estimate's three 16x16 SATDs
         me_ms = me_fine + me_coarse
-        int_ach = (absdiff_mb / 4.0) * 8160 * Sp / 32.0 / (me_ms * 1e-3) / 1e9 if me_ms > 0 else 0.0   # warp-instructions -> G lane... see DESIGN 5
+        int_ach = (absdiff_mb / 4.0) * nmb * Sp / 32.0 / (me_ms * 1e-3) / 1e9 if me_ms > 0 else 0.0   # warp-instructions -> G lane... see DESIGN 5
         cpu = cpu_baseline_sample(threads=1, frames=args.cpu_frames) if world == 1 and not args.no_cpu else None
+        # DRAM traffic and pipe utilisation of the dominant kernel from the committed `ncu --set full` capture (profiles/), scaled
+        # from that capture's sessions per launch to this run's
+        traffic, ncu_note = None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))
+            k = prof["kernels"][top[0]]
+            traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) * Sp / prof["sessions_per_launch"]
+            ncu_note = {"source": "profiles/r01_ncu_kernels.json", "alu_pipe_pct_of_peak": k["alu_pipe_pct"], "sm_throughput_pct_of_peak": k["sm_throughput_pct"],
+                        "warp_instructions_per_mb_1080p": round(k["warp_instructions"] / (8160 * prof["sessions_per_launch"]), 1)}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(el / args.steps * 1e3, 4), "device_ms_per_step": round(dev_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "realtime_30fps_sessions": round(value / FPS, 1),
-            "config": {"workload": f"{S} concurrent 1920x1080 sessions per GPU, Baseline CAVLC IPPP, CBR 4 Mbps @30fps each, gop {GOP}, "
-                                   f"search +-16, 1 slice, content A (moving texture); step = one frame of every session; {G} batch(es) of {group_sizes[0]} on own streams",
-                       "sessions_per_gpu": S, "frames_per_step": S * world, "l2_policy": f"inputs larger than L2: per-step working set ~{S * 20} MB",
+            "value_per_gpu": round(value / world, 2), "realtime_30fps_sessions": round(value / FPS, 1),
+            "config": {"workload": f"{S} concurrent {W}x{H} sessions per GPU, {LABEL}; step = one frame of every session; {G} batch(es) of {group_sizes[0]} on own streams",
+                       "sessions_per_gpu": S, "frames_per_step": S * world, "l2_policy": (f"inputs larger than L2: per-step working set ~{S * npx * 10 // 1000000} MB" if S * npx * 10 > 130e6 else
+                                     f"working set ~{S * npx * 10 // 1000000} MB fits L2; every step encodes a different frame of the pool, reference planes are rewritten each step"),
                        "parallelism": f"sessions sharded over {world} GPU(s), no collective"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": world * S * fb, "d2h_bytes_per_step": int(world * out_bytes_e / args.steps),
                     "ms_per_step": round(el_e / args.steps * 1e3, 4)},
@@ -247,7 +292,7 @@ def run_b200(args):
             "bitrate_mbps_per_session": round(out_bytes * 8 / (S * args.steps) * FPS / 1e6, 3),
             "kernel_ms": {k: round(v, 4) for k, v in kt},
             "roofline": {"bound": "hbm", "kernel": top[0], "share_of_step": round(top[1] / tot, 3), "achieved": round(ach, 1), "peak": hbm_peak,
-                         "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None,
+                         "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": traffic, "ncu": ncu_note,
                          "note": "the encode path is INT-ALU/latency bound, not HBM bound (SURVEY 8d); see roofline_int"},
             "roofline_int": {"kernels": "k_me_coarse+k_me_fine", "achieved_gwarp_instr_s": round(int_ach, 2),
                              "peak_gwarp_instr_s": round(gi.value / 32.0, 2), "peak_glane_instr_s": round(gi.value, 1), "sm_clock_mhz_in_peak_run": clk.value,
@@ -272,9 +317,9 @@ def _cpu_worker(args):
     frames, qps = args
     from oracle import orc_py
     from media_b200.synth import Content
-    c = Content("A", W, H)
+    c = Content(KIND, W, H)
     fs = [c.frame(t) for t in range(frames + 1)]
-    e = orc_py.Encoder(W, H, search_range=16)
+    e = orc_py.Encoder(W, H, num_slices=SLICES, search_range=SR)
     e.encode(fs[0], True, qps[0])
     t0 = time.perf_counter()
     for t in range(1, frames + 1):
@@ -293,7 +338,7 @@ def cpu_baseline_sample(threads, frames):
             times = pool.map(_cpu_worker, [(frames, qps)] * threads)
     fps = sum(frames / t for t in times)
     return {"value": round(fps, 3), "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"{threads} session(s) x {frames} P frames of 1920x1080 content A at QP 34 after one IDR (CPU restatement oracle/, gcc -O2, NOT openh264: libopenh264 is absent from the image)"}
+            "sample": f"{threads} session(s) x {frames} P frames of {W}x{H} content {KIND} at QP 34 after one IDR (CPU restatement oracle/, gcc -O2, NOT openh264: libopenh264 is absent from the image)"}
 
 
 def run_reference(args):
@@ -309,7 +354,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": best["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "1920x1080 sessions, Baseline CAVLC IPPP, content A; CPU restatement of the path, one single-threaded encoder per host core"},
+        "config": {"workload": f"{W}x{H} sessions, {LABEL}; CPU restatement of the path, one single-threaded encoder per host core"},
         "cpu_baseline": best, "e2e": {"value": best["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -320,12 +365,14 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sessions", type=int, default=96)
-    ap.add_argument("--groups", type=int, default=3)
+    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--sessions", type=int, default=None)
+    ap.add_argument("--groups", type=int, default=None)
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--threads-e2e", action="store_true", help="also measure one caller thread per session through the auto_batch scheduler")
     args = ap.parse_args()
+    apply_workload(args)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

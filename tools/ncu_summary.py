@@ -2,6 +2,8 @@
 (first profiled launch of each). usage: python tools/ncu_summary.py <report.ncu-rep>"""
 import csv, subprocess, sys
 rep = sys.argv[1]
+json_out = sys.argv[2] if len(sys.argv) > 2 else None      # optional: also write the per-kernel counters as JSON (read by bench.py)
+sessions = int(sys.argv[3]) if len(sys.argv) > 3 else 32     # sessions per launch in the profiled command
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -28,3 +30,29 @@ for r in rows[2:]:
             pass
         cells.append(f"{v} {u}".strip())
     print(f"| {name} | " + " | ".join(cells) + " |")
+
+if json_out:
+    import json
+    out = {"source": rep.split("/")[-1], "sessions_per_launch": sessions, "kernels": {}}
+    seen = set()
+    def num(r, m):
+        try:
+            return float(r[ix[m]])
+        except (KeyError, ValueError):
+            return None
+    def to_bytes(r, m):
+        v = num(r, m)
+        if v is None:
+            return None
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[ix[m]], 1)
+    for r in rows[2:]:
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+        if name in seen:
+            continue
+        seen.add(name)
+        out["kernels"][name] = {"dram_bytes_read": to_bytes(r, "dram__bytes_read.sum"), "dram_bytes_write": to_bytes(r, "dram__bytes_write.sum"),
+                                "alu_pipe_pct": num(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                                "sm_throughput_pct": num(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+                                "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                                "warp_instructions": num(r, "smsp__inst_executed.sum"), "registers": num(r, "launch__registers_per_thread")}
+    json.dump(out, open(json_out, "w"), indent=1)
