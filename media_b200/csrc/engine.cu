@@ -157,7 +157,8 @@ bool encode_tmap(CUtensorMap *out, void *base, int rank, uint64_t d0, uint64_t d
 
 struct b200enc_batch {
     int device = 0, cap = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;    // stream2: entropy coding runs beside the deblocking wavefront
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Sess *h_sess = nullptr, *d_sess = nullptr;
     WaveCtl *d_ctl = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -199,6 +200,9 @@ int batch_init(b200enc_batch *b, int device, int cap)
     b->device = device; b->cap = cap;
     CU_TRY(cudaSetDevice(device), return B200ENC_ENODEV);
     CU_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), return B200ENC_ENODEV);
+    CU_TRY(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking), return B200ENC_ENODEV);
+    CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), return B200ENC_ENODEV);
+    CU_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming), return B200ENC_ENODEV);
     CU_TRY(cudaHostAlloc(&b->h_sess, sizeof(Sess) * cap, cudaHostAllocDefault), return B200ENC_ENOMEM);
     CU_TRY(cudaMalloc(&b->d_sess, sizeof(Sess) * cap), return B200ENC_ENOMEM);
     CU_TRY(cudaMalloc(&b->d_ctl, sizeof(WaveCtl)), return B200ENC_ENOMEM);
@@ -217,6 +221,9 @@ void batch_free(b200enc_batch *b)
     if (b->d_ctl) cudaFree(b->d_ctl);
     if (b->d_sess) cudaFree(b->d_sess);
     if (b->h_sess) cudaFreeHost(b->h_sess);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
+    if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -230,14 +237,16 @@ __global__ void k_reset(const Sess *ss, Geom g, int nsess, WaveCtl *ctl)
 
 struct Prof {
     b200enc_batch *b;
-    void begin(const char *name)
+    cudaStream_t cur;
+    void begin(const char *name, cudaStream_t st)
     {
         if (!b->profiling) return;
         if (b->n_ktimes == (int)b->ktimes.size()) { KernelTime k; k.name = name; cudaEventCreate(&k.ev0); cudaEventCreate(&k.ev1); b->ktimes.push_back(k); }
-        b->ktimes[b->n_ktimes].name = name;
-        cudaEventRecord(b->ktimes[b->n_ktimes].ev0, b->stream);
+        b->ktimes[b->n_ktimes].name = name; cur = st;
+        cudaEventRecord(b->ktimes[b->n_ktimes].ev0, st);
     }
-    void end() { if (!b->profiling) return; cudaEventRecord(b->ktimes[b->n_ktimes].ev1, b->stream); b->n_ktimes++; }
+    void begin(const char *name) { begin(name, b->stream); }
+    void end() { if (!b->profiling) return; cudaEventRecord(b->ktimes[b->n_ktimes].ev1, cur); b->n_ktimes++; }
 };
 
 bool same_shape(const b200enc_session *a, const b200enc_session *c)
@@ -287,7 +296,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, b->stream), return B200ENC_ECUDA);
     cudaStream_t st = b->stream;
     const int nmb = g.mbw * g.mbh;
-    int launches = 0; b->n_ktimes = 0; Prof pf{ b };
+    int launches = 0; b->n_ktimes = 0; Prof pf{ b, b->stream };
     cudaEventRecord(b->ev0, st);
     pf.begin("k_reset"); k_reset<<<(n * g.mbh + 255) / 256, 256, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
     if (ss[0]->cfg.input_format == B200ENC_FMT_RGBA) {
@@ -318,11 +327,16 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         for (int c = 0; c < 3; c++) cudaMemcpyAsync(ss[i]->rec_pre[c], cur[c], (size_t)g.wc * g.hc / (c ? 4 : 1), cudaMemcpyDeviceToDevice, st);
     }
     pf.begin("k_pskip_scan"); k_pskip_scan<<<dim3(g.num_slices, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    // fork: the entropy coder only needs MbInfo / MbCoef / skip runs, the deblocking wavefront only reconstruction + MbInfo;
+    // the latency-bound wavefront and the issue-bound CAVLC chain overlap on two streams and join before the read-back
+    cudaStream_t s2 = b->stream2;
+    cudaEventRecord(b->ev_fork, st); cudaStreamWaitEvent(s2, b->ev_fork, 0);
     pf.begin("k_deblock_wave"); k_deblock_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
-    pf.begin("k_cavlc_mb"); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end(); launches++;
-    pf.begin("k_slice_scan"); k_slice_scan<<<dim3(g.num_slices, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end(); launches++;
-    pf.begin("k_slice_copy"); k_slice_copy<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end(); launches++;
-    pf.begin("k_nal_pack"); k_nal_pack<<<n, 1024, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_cavlc_mb", s2); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_slice_scan", s2); k_slice_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_slice_copy", s2); k_slice_copy<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_nal_pack", s2); k_nal_pack<<<n, 1024, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
+    cudaEventRecord(b->ev_join, s2); cudaStreamWaitEvent(st, b->ev_join, 0);
     cudaEventRecord(b->ev1, st);
     WaveCtl ctl;
     CU_TRY(cudaMemcpyAsync(&ctl, b->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, st), return B200ENC_ECUDA);

@@ -181,3 +181,64 @@ def test_static_content_converges_to_skip(orc):
     for t in range(1, 6):
         au = e.encode(c.frame(t), False, 30)
     assert (e.mb_info()["mb_type"] == 3).mean() > 0.8 and len(au) < len(idr) // 20
+
+
+@needs_decoder
+def test_intra4x4_every_mode_is_used_and_decodes(orc):
+    """Intra_4x4 (8.3.1.2): across a few contents every one of the nine predictors gets chosen somewhere, I_NxN syntax
+    (prev_intra4x4_pred_mode / rem_intra4x4_pred_mode, Intra cbp table) decodes to the oracle's reconstruction"""
+    used = np.zeros(9, bool); w, h = 192, 128
+    for kind, qp in (("A", 24), ("B", 30), ("D", 36)):
+        e = orc.Encoder(w, h, num_slices=2); c = Content(kind, w, h)
+        au = e.encode(c.frame(0), True, qp); mi = e.mb_info()
+        i4 = mi["mb_type"] == 2
+        assert i4.any()
+        used[np.unique(mi["i4_mode"][i4])] = True
+        assert (mi["i4_mode"][mi["mb_type"] == 1] == 0).all()
+        dec = avdec.decode_stream([au])
+        assert np.array_equal(dec[0], e.recon())
+    assert used.all(), used
+
+
+def test_intra4x4_predictors_against_the_formulas(orc):
+    """orc_pred_i4 vs a direct numpy transcription of 8.3.1.2.1-9 for the modes with closed forms (V, H, DC, DDL, VL, HU)"""
+    import ctypes as C
+    L = orc.lib(); L.orc_pred_i4.restype = C.c_int; L.orc_pred_i4.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for _ in range(100):
+        img = rng.integers(0, 256, (8, 16), dtype=np.uint8); st = 16; bx, by = 4, 2
+        T = img[by - 1, bx:bx + 8].astype(int); Lf = img[by:by + 4, bx - 1].astype(int)
+        def run(mode, avail=15):
+            out = np.zeros(16, np.uint8); assert L.orc_pred_i4(img.ctypes.data + by * st + bx, st, mode, avail, out.ctypes.data) == 1
+            return out.reshape(4, 4)
+        assert np.array_equal(run(0), np.tile(T[:4], (4, 1)))
+        assert np.array_equal(run(1), np.tile(Lf[:, None], (1, 4)))
+        assert (run(2) == (T[:4].sum() + Lf.sum() + 4) >> 3).all()
+        ddl = np.array([[(T[x + y] + 2 * T[x + y + 1] + T[min(x + y + 2, 7)] + 2) >> 2 for x in range(4)] for y in range(4)])
+        assert np.array_equal(run(3), ddl)
+        vl = np.array([[((T[x + (y >> 1)] + T[x + (y >> 1) + 1] + 1) >> 1) if y % 2 == 0 else ((T[x + (y >> 1)] + 2 * T[x + (y >> 1) + 1] + T[x + (y >> 1) + 2] + 2) >> 2)
+                        for x in range(4)] for y in range(4)])
+        assert np.array_equal(run(7), vl)
+        T2 = T.copy(); T2[4:] = T2[3]                  # top-right unavailable: p[4..7,-1] := p[3,-1]
+        assert np.array_equal(run(3, 7), np.array([[(T2[x + y] + 2 * T2[x + y + 1] + T2[min(x + y + 2, 7)] + 2) >> 2 for x in range(4)] for y in range(4)]))
+        out = np.zeros(16, np.uint8)
+        assert L.orc_pred_i4(img.ctypes.data + by * st + bx, st, 4, 3, out.ctypes.data) == 0     # diagonal down-right needs the corner
+
+
+@needs_decoder
+def test_p8x8_partitions_decode_and_predictor_estimate_pays(orc):
+    """P_8x8 macroblocks (sub_mb_type P_L0_8x8, partition MV prediction 8.4.1.3 / 6.4.11.7, per-partition bS) occur and decode;
+    switching them off (oracle-only flag) still decodes, so both syntaxes are exercised"""
+    w, h = 320, 192
+    for no8 in (0, 1):
+        e = orc.Encoder(w, h, num_slices=2, search_range=32, no_p8x8=no8); c = Content("A", w, h)
+        aus, recs, n8 = [], [], 0
+        for t in range(5):
+            aus.append(e.encode(c.frame(t), t == 0, 22)); recs.append(e.recon())
+            mi = e.mb_info(); n8 += int((mi["mb_type"] == 4).sum())
+            inter = np.isin(mi["mb_type"], (0, 3))
+            mv8 = mi["i4_mode"].view("<i2").reshape(-1, 4, 2)          # union with mv8[4][2]
+            assert (mv8[inter] == mi["mv"][inter][:, None, :]).all()    # 16x16 / skip MBs carry their vector in all four partitions
+        assert (n8 > 0) == (no8 == 0)
+        dec = avdec.decode_stream(aus)
+        assert len(dec) == 5 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
