@@ -366,17 +366,18 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
 // EncodeOneFrame (video_codec/VideoEncoderOpenH264.cpp:304-352, iMultipleThreadIdc = 1 at :294). Here those concurrent calls
 // rendezvous in a per-GPU worker that advances all waiting sessions with ONE batch step; while a step runs, the next
 // callers queue up, so batches form by themselves under load and a lone caller only pays the short window. ----
+bool next_is_idr(const b200enc_session *s) { return s->force_idr || !s->have_ref || s->frames_since_idr >= s->cfg.gop; }
 struct SchedRequest {
     b200enc_session *s; const uint8_t *frame; const uint8_t *bs = nullptr; uint32_t size = 0; b200enc_frame_info info{};
     int rc = B200ENC_OK; bool done = false;
 };
 struct DeviceScheduler {
-    static constexpr int WORKERS = 2;      // two batch contexts (streams): one batch uploads/queues while the other computes
+    static constexpr int WORKERS = 3;      // two batch contexts (streams): one batch uploads/queues while the other computes
     int device = -1, registered = 0, inflight = 0;
     std::mutex mu; std::condition_variable cv_submit, cv_done;
     std::vector<SchedRequest *> pending;
     std::thread worker[WORKERS]; bool stop = false;
-    b200enc_batch *ctx[WORKERS] = { nullptr, nullptr }; int window_us = 300;
+    b200enc_batch *ctx[WORKERS] = { nullptr, nullptr, nullptr }; int window_us = 300;
     std::atomic<uint64_t> batches{ 0 }, frames{ 0 };
 
     void run(int w)
@@ -391,9 +392,13 @@ struct DeviceScheduler {
             while ((int)pending.size() < registered - inflight && !stop)
                 if (cv_submit.wait_until(lk, deadline) == std::cv_status::timeout) break;
             if (pending.empty()) continue;                 // the other worker took them
-            // one batch = the requests that share the first request's shape (other shapes wait for the next round)
+            // one batch = the requests that share the first request's shape AND frame kind (others wait for the next round or
+            // the other worker): an IDR costs several times a P frame on the intra wavefront, so key frames travel in their own
+            // batch and do not hold back the P frames of the sessions that happen to arrive with them
             std::vector<SchedRequest *> take, rest;
-            for (SchedRequest *r : pending) (same_shape(pending[0]->s, r->s) && (int)take.size() < ctx[w]->cap ? take : rest).push_back(r);
+            const bool kind0 = next_is_idr(pending[0]->s);
+            for (SchedRequest *r : pending)
+                (same_shape(pending[0]->s, r->s) && next_is_idr(r->s) == kind0 && (int)take.size() < ctx[w]->cap ? take : rest).push_back(r);
             pending.swap(rest);
             const int n = (int)take.size();
             inflight += n;

@@ -62,7 +62,9 @@ struct IntraSmem {
     uint32_t nb[17 * 6];
     uint32_t srcw[64];
     uint8_t F[48];
-    int8_t mg[28];            // Intra4x4PredMode grid, 5x5: row 0 / column 0 = neighbouring MBs (-1 unavailable, 2 not Intra_4x4)
+    int8_t mg[28];
+    __align__(16) int dq[16];  // dequantised coefficients of the Intra_4x4 block in flight (raster), then its row-transformed values
+    int tf[16];            // Intra4x4PredMode grid, 5x5: row 0 / column 0 = neighbouring MBs (-1 unavailable, 2 not Intra_4x4)
 };
 
 // Intra_4x4 predictors (8.3.1.2.1-9) as lookups into the block's filtered edge. Edge E[0..14] = L3 L3 L2 L1 L0 X T0..T7 T7
@@ -111,6 +113,12 @@ __device__ bool intra_try_i4x4(const Sess &s, const Geom &g, IntraSmem &sm, int 
     uint32_t ix[4];
 #pragma unroll
     for (int y = 0; y < 4; y++) ix[y] = c_i4_idx[min(lane, 8)][y];
+    // per-lane transform constants: the zig-zag position this lane quantises, its horizontal basis as signed bytes for IDP.4A
+    // (rows of Cf = {1,1,1,1},{2,1,-1,-2},{1,-1,-1,1},{1,-2,2,-1}), its vertical basis, and its quantiser entries
+    const int zpos = c_zigzag[lane & 15], fi = zpos >> 2, fj = zpos & 3;
+    const uint32_t WX = fj == 0 ? 0x01010101u : fj == 1 ? 0xFEFF0102u : fj == 2 ? 0x01FFFF01u : 0xFF02FE01u;
+    const int wy0 = fi == 1 ? 2 : 1, wy1 = fi == 0 ? 1 : fi == 1 ? 1 : fi == 2 ? -1 : -2, wy2 = fi == 0 ? 1 : fi == 1 ? -1 : fi == 2 ? -1 : 2, wy3 = fi == 0 ? 1 : fi == 1 ? -2 : fi == 2 ? 1 : -1;
+    const int qcl = pos_class(zpos), qmf = qcl == 0 ? q.mf[0] : qcl == 1 ? q.mf[1] : q.mf[2], qv = qcl == 0 ? q.v[0] : qcl == 1 ? q.v[1] : q.v[2];
     int total = lambda * I4_BIAS_BITS;
     cbp_luma = 0; modes = 0ull;
 #pragma unroll 1
@@ -164,38 +172,48 @@ __device__ bool intra_try_i4x4(const Sess &s, const Geom &g, IntraSmem &sm, int 
         if (total >= limit) return false;
 #pragma unroll
         for (int y = 0; y < 4; y++) P[y] = __shfl_sync(0xffffffffu, P[y], wm);
-        // transform, quantise, reconstruct (every lane computes the same block; lanes 0-6 store one piece each)
-        int p[16], c[16];
-#pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++) { p[y * 4 + x] = (P[y] >> (8 * x)) & 255; c[y * 4 + x] = (int)((S[y] >> (8 * x)) & 255) - p[y * 4 + x]; }
-        fdct4x4(c);
-        __align__(16) int16_t lz[16];
-        const int nnz = quant_dequant4x4(c, lz, q, q.f_intra, false);
-        idct4x4(c);
-        uint32_t R[4];
-#pragma unroll
-        for (int y = 0; y < 4; y++) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int x = 0; x < 4; x++) w |= (uint32_t)clip255(p[y * 4 + x] + c[y * 4 + x]) << (8 * x);
-            R[y] = w;
+        // transform, quantise, reconstruct, spread over 16 lanes (lanes 16-31 mirror them): lane l owns the coefficient at
+        // zig-zag index l for the forward transform + quantiser (its value is one IDP.4A per row against the lane's horizontal
+        // basis, then four multiply-adds with its vertical basis), and the sample (y,x) = (l>>2, l&3) for the inverse transform
+        // (8.5.12.2, rows then columns, exchanged through shared memory) and the reconstruction.
+        int level, dq;
+        {
+            const int t0 = dp4a_us(S[0], WX, 0) - dp4a_us(P[0], WX, 0), t1 = dp4a_us(S[1], WX, 0) - dp4a_us(P[1], WX, 0);
+            const int t2 = dp4a_us(S[2], WX, 0) - dp4a_us(P[2], WX, 0), t3 = dp4a_us(S[3], WX, 0) - dp4a_us(P[3], WX, 0);
+            const int cf = wy0 * t0 + wy1 * t1 + wy2 * t2 + wy3 * t3;
+            const int l = min((int)(((unsigned)abs(cf) * (unsigned)qmf + (unsigned)q.f_intra) >> q.qbits), B200_MAX_LEVEL);
+            level = cf < 0 ? -l : l;
+            dq = (level * qv) << q.sh;
         }
-        if (lane < 4) {
-            const uint32_t r = lane == 0 ? R[0] : lane == 1 ? R[1] : lane == 2 ? R[2] : R[3];
-            sm.nb[((by + lane + 1) * 24 + 4 + bx) >> 2] = r;
-            *reinterpret_cast<uint32_t *>(s.rec[0] + (size_t)(my * 16 + by + lane) * wc + mx * 16 + bx) = r;
-        } else if (lane < 6) {
-            const uint4 lo = reinterpret_cast<uint4 *>(lz)[0], hi = reinterpret_cast<uint4 *>(lz)[1];
-            reinterpret_cast<uint4 *>(co->luma[b])[lane - 4] = lane == 4 ? lo : hi;
-        } else if (lane == 6) {
-            mi->nnz[b] = (uint8_t)nnz;
-            sm.mg[(byb + 1) * 5 + bxb + 1] = (int8_t)wm;
+        const uint32_t nzm = __ballot_sync(0xffffffffu, level != 0) & 0xffffu;
+        if (lane < 16) { sm.dq[zpos] = dq; co->luma[b][lane] = (int16_t)level; }
+        __syncwarp();
+        const int py = (lane >> 2) & 3, pxl = lane & 3;
+        {
+            const int4 d = *reinterpret_cast<const int4 *>(&sm.dq[py * 4]);
+            const int e0 = d.x + d.z, e1 = d.x - d.z, e2 = (d.y >> 1) - d.w, e3 = d.y + (d.w >> 1);
+            const int f = pxl == 0 ? e0 + e3 : pxl == 1 ? e1 + e2 : pxl == 2 ? e1 - e2 : e0 - e3;
+            if (lane < 16) sm.tf[lane] = f;
         }
-        if (nnz) cbp_luma |= 1 << (b >> 2);
+        __syncwarp();
+        {
+            const int f0 = sm.tf[pxl], f1 = sm.tf[4 + pxl], f2 = sm.tf[8 + pxl], f3 = sm.tf[12 + pxl];
+            const int g0 = f0 + f2, g1 = f0 - f2, g2 = (f1 >> 1) - f3, g3 = f1 + (f3 >> 1);
+            const int r = ((py == 0 ? g0 + g3 : py == 1 ? g1 + g2 : py == 2 ? g1 - g2 : g0 - g3) + 32) >> 6;
+            const uint32_t Pr = py == 0 ? P[0] : py == 1 ? P[1] : py == 2 ? P[2] : P[3];
+            const int pix = clip255((int)((Pr >> (8 * pxl)) & 255u) + r);
+            if (lane < 16) nb[(by + py + 1) * 24 + 4 + bx + pxl] = (uint8_t)pix;
+            else if (lane == 16) { mi->nnz[b] = (uint8_t)__popc(nzm); sm.mg[(byb + 1) * 5 + bxb + 1] = (int8_t)wm; }
+        }
+        if (nzm) cbp_luma |= 1 << (b >> 2);
         modes |= (unsigned long long)wm << (4 * b);
         __syncwarp();
+    }
+    // the reconstruction of the whole MB goes out at once: 16 rows x 4 words
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int wi = lane + 32 * i, r = wi >> 2, cw4 = wi & 3;
+        *reinterpret_cast<uint32_t *>(s.rec[0] + (size_t)(my * 16 + r) * wc + mx * 16 + cw4 * 4) = sm.nb[((r + 1) * 24 + 4 + cw4 * 4) >> 2];
     }
     return true;
 }
