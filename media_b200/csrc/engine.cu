@@ -158,6 +158,7 @@ bool encode_tmap(CUtensorMap *out, void *base, int rank, uint64_t d0, uint64_t d
 struct b200enc_batch {
     int device = 0, cap = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;    // stream2: entropy coding runs beside the deblocking wavefront
+    cudaStream_t stream_hi = nullptr;                   // high-priority twin of `stream`: batches made only of IDR frames (long wavefront)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Sess *h_sess = nullptr, *d_sess = nullptr;
     WaveCtl *d_ctl = nullptr;
@@ -201,6 +202,8 @@ int batch_init(b200enc_batch *b, int device, int cap)
     CU_TRY(cudaSetDevice(device), return B200ENC_ENODEV);
     CU_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), return B200ENC_ENODEV);
     CU_TRY(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking), return B200ENC_ENODEV);
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      CU_TRY(cudaStreamCreateWithPriority(&b->stream_hi, cudaStreamNonBlocking, hi), return B200ENC_ENODEV); }
     CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), return B200ENC_ENODEV);
     CU_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming), return B200ENC_ENODEV);
     CU_TRY(cudaHostAlloc(&b->h_sess, sizeof(Sess) * cap, cudaHostAllocDefault), return B200ENC_ENOMEM);
@@ -224,6 +227,7 @@ void batch_free(b200enc_batch *b)
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->stream2) cudaStreamDestroy(b->stream2);
+    if (b->stream_hi) { cudaStreamSynchronize(b->stream_hi); cudaStreamDestroy(b->stream_hi); }
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -237,7 +241,7 @@ __global__ void k_reset(const Sess *ss, Geom g, int nsess, WaveCtl *ctl)
 
 struct Prof {
     b200enc_batch *b;
-    cudaStream_t cur;
+    cudaStream_t mainst, cur;
     void begin(const char *name, cudaStream_t st)
     {
         if (!b->profiling) return;
@@ -245,7 +249,7 @@ struct Prof {
         b->ktimes[b->n_ktimes].name = name; cur = st;
         cudaEventRecord(b->ktimes[b->n_ktimes].ev0, st);
     }
-    void begin(const char *name) { begin(name, b->stream); }
+    void begin(const char *name) { begin(name, mainst); }
     void end() { if (!b->profiling) return; cudaEventRecord(b->ktimes[b->n_ktimes].ev1, cur); b->n_ktimes++; }
 };
 
@@ -267,17 +271,18 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     const Geom g = ss[0]->g;
     const size_t in_bytes = b200enc_frame_bytes(ss[0]);
     bool any_p = false;
+    for (int i = 0; i < n; i++) any_p |= !(ss[i]->force_idr || !ss[i]->have_ref || ss[i]->frames_since_idr >= ss[i]->cfg.gop);
+    cudaStream_t st = any_p ? b->stream : b->stream_hi;      // a batch of key frames only gets the high-priority stream
     for (int i = 0; i < n; i++) {
         b200enc_session *s = ss[i];
         const bool idr = s->force_idr || !s->have_ref || s->frames_since_idr >= s->cfg.gop;
         const int qp = s->cfg.const_qp >= 0 ? s->cfg.const_qp : s->rc.pick(idr ? 1 : 0, s->cfg.width, s->cfg.height);
         if (idr) { s->frame_num = 0; s->frames_since_idr = 0; }
         s->last_qp = qp; s->last_type = idr ? 1 : 0;
-        any_p |= !idr;
         uint8_t **cur = s->cur_is_A ? s->bufA : s->bufB, **ref = s->cur_is_A ? s->bufB : s->bufA;
         Sess &d = b->h_sess[i];
         if (device_input) d.input = frames[i];
-        else { d.input = s->input; CU_TRY(cudaMemcpyAsync(s->input, frames[i], in_bytes, cudaMemcpyHostToDevice, b->stream), return B200ENC_ECUDA); }
+        else { d.input = s->input; CU_TRY(cudaMemcpyAsync(s->input, frames[i], in_bytes, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA); }
         for (int c = 0; c < 3; c++) { d.src[c] = s->src[c]; d.rec[c] = cur[c]; d.ref[c] = ref[c]; }
         {   // padded planes: hand the kernels the address of the interior sample (0,0)
             const size_t o1 = (size_t)g.p1 * g.s1 + g.p1, o2 = (size_t)g.p2 * g.s2 + g.p2, ol = (size_t)g.lp * g.ls + g.lp, oc = (size_t)g.cp * g.cs + g.cp;
@@ -293,10 +298,9 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         d.qp = qp; d.is_idr = idr; d.frame_num = s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
         d.rbsp_words_per_slice = s->rbsp_words_per_slice; d.out_cap = s->out_cap;
     }
-    CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, b->stream), return B200ENC_ECUDA);
-    cudaStream_t st = b->stream;
+    CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
     const int nmb = g.mbw * g.mbh;
-    int launches = 0; b->n_ktimes = 0; Prof pf{ b, b->stream };
+    int launches = 0; b->n_ktimes = 0; Prof pf{ b, st, st };
     cudaEventRecord(b->ev0, st);
     pf.begin("k_reset"); k_reset<<<(n * g.mbh + 255) / 256, 256, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
     if (ss[0]->cfg.input_format == B200ENC_FMT_RGBA) {

@@ -377,3 +377,15 @@ def test_openh264_abi_shim_serves_the_wrapper_flow(enc, tmp_path):
     assert rows[n][0] == "ps" and int(rows[n][2]) == 1 and int(rows[n][3]) == 2
     if avdec.available():
         assert len(avdec.decode_stream(want)) == n
+
+
+def test_realtime_paced_sessions_through_the_scheduler(enc):
+    """BASELINE config 5 in miniature: 12 caller threads, one session each, paced at 30 fps through b200enc_encode (auto_batch);
+    no frame may finish after the next capture time and every session must keep its frame rate"""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "rt_sessions.bin")
+    if not os.path.exists(exe):
+        pytest.skip("tools/rt_sessions.bin not built")
+    out = subprocess.run([exe, "12", "2", "640", "368", "30", "1000000"], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+    r = json.loads(out)
+    assert r["errors"] == 0 and r["late_frames"] == 0 and r["achieved_fps_per_session"] > 29.0 and r["latency_ms"]["p99"] < 33.3, r
