@@ -51,7 +51,7 @@ __device__ __forceinline__ void stage_window_rt(uint32_t *dstw, int W, const uin
 // The search windows are kept as four byte-shifted copies (copy k, word j of a row = bytes 4j+k .. 4j+k+3), so every
 // candidate row is read with aligned 32-bit loads straight into VABSDIFF4.
 template <int MAXR4> struct CoarseSmem {
-    static constexpr int MAXW = 8 + 2 * MAXR4, CW = MAXW * MAXW / 4 + 2;
+    static constexpr int MAXW = 8 + 2 * MAXR4, CW = MAXW * MAXW / 4 + 8;   // +8: fewest bank conflicts of the candidate reads at R = 16 (modelled)
     uint32_t win[4][CW]; uint32_t src[16]; uint32_t win1[4][12 * 3 + 2];
 };
 // build copies 1..3 from copy 0 (n words each, rows are contiguous so word j+1 is the right neighbour)
@@ -148,7 +148,7 @@ struct __align__(128) FineSmem {
 };
 static_assert(sizeof(FineSmem) % 128 == 0 && offsetof(FineSmem, src) % 128 == 0 && offsetof(FineSmem, win) % 128 == 0, "TMA destinations must be 128-byte aligned");
 // the four byte-shifted copies of the 20x20 window live in the plane area until the planes are fetched
-#define WIN0_WORDS (20 * 5 + 2)
+#define WIN0_WORDS 127          /* >= 20 * 5 + 2; 127 makes the 25 candidate reads of a row hit 25 different banks */
 #define P8X8_BIAS_BITS 8        /* extra header bits of P_8x8 over P_L0_16x16: mb_type ue(3) vs ue(0), four sub_mb_type ue(0) */
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -157,13 +157,18 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// bounded wait (phase 0): a transaction that never completes must not hang the GPU; returns false on timeout
+// bounded wait (phase 0): a transaction that never completes must not hang the GPU; returns false after 2 s
 __device__ __forceinline__ bool mbar_wait(unsigned long long *bar)
 {
-    uint32_t ok = 0;
-    for (int spin = 0; spin < (1 << 18) && !ok; spin++)
+    uint32_t ok = 0; unsigned long long t0 = 0;
+    for (unsigned spin = 0; !ok; spin++) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
-    return ok != 0;
+        if (!ok && (spin & 1023u) == 1023u) {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (!t0) t0 = t; else if (t - t0 > 2000000000ull) return false;
+        }
+    }
+    return true;
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, unsigned long long *bar)
 {
