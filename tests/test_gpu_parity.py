@@ -79,6 +79,11 @@ def test_stream_decodes_to_own_reconstruction_1080p(enc):
             g.force_idr()
         bs, info = g.encode(c.frame(t)); aus.append(bs); recs.append(g.recon()); types.append(info.frame_type)
     assert types == [1, 0, 0, 0, 0, 1, 0, 0]
+    from test_oracle import consumer_header_scan      # the repo's decoder-side header scan (video_decoder/VideoDecoderNetint.cpp:737-860)
+    for t in (0, 5):
+        sps, pps, hdr, stop = consumer_header_scan(aus[t])
+        assert sps and pps and hdr <= 4096 and stop == 5
+    assert consumer_header_scan(aus[1]) == (False, False, 0, 1)
     dec = avdec.decode_stream(aus)
     assert len(dec) == 8
     for t, (d, r) in enumerate(zip(dec, recs)):

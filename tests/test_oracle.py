@@ -242,3 +242,53 @@ def test_p8x8_partitions_decode_and_predictor_estimate_pays(orc):
         assert (n8 > 0) == (no8 == 0)
         dec = avdec.decode_stream(aus)
         assert len(dec) == 5 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+
+
+def consumer_header_scan(au):
+    """What the repo's own decoder-side consumer does with an access unit before feeding its ASIC
+    (reference video_decoder/VideoDecoderNetint.cpp:737-792 DeviceDecSessionWrite, :794-841 FindNextNonVclNalu, :843-860
+    FindNalStartCode): walk the non-VCL NALs from the front, collect SPS/PPS into a 4 KB header buffer, stop at the first VCL NAL.
+    Returns (sps_found, pps_found, header_bytes, type of the NAL the scan stopped at)."""
+    buf, sps, pps, hdr = bytes(au), False, False, 0
+    def find_start(b):
+        i = 0
+        while not (b[i:i + 3] == b"\0\0\1" or b[i:i + 4] == b"\0\0\0\1"):
+            i += 1
+            if i + 3 > len(b):
+                return -1
+        return i
+    while len(buf) > 3:
+        i = find_start(buf)
+        if i < 0:
+            return sps, pps, hdr, -1
+        if buf[i + 2] != 1:
+            i += 1
+        i += 3
+        t = buf[i] & 0x1f
+        if 1 <= t <= 5:                       # SLICE .. IDR_SLICE: VCL, stop
+            return sps, pps, hdr, t
+        while buf[i:i + 3] not in (b"\0\0\0", b"\0\0\1"):
+            i += 1
+            if i + 3 > len(buf):
+                i = len(buf); break
+        sps |= t == 7; pps |= t == 8
+        if t in (7, 8):
+            hdr += i
+        buf = buf[i:]
+        if sps and pps:
+            nxt = find_start(buf)
+            return sps, pps, hdr, (buf[nxt + (4 if buf[nxt + 2] != 1 else 3)] & 0x1f) if nxt >= 0 else -1
+    return sps, pps, hdr, -1
+
+
+def test_downstream_consumer_finds_the_parameter_sets(orc):
+    """every IDR access unit carries SPS and PPS in front of the first VCL NAL (4-byte start codes, well inside
+    the consumer's 4 KB header buffer); P access units start with a VCL NAL"""
+    e = orc.Encoder(320, 180, num_slices=3); c = Content("A", 320, 180)
+    idr = e.encode(c.frame(0), True, 26); p = e.encode(c.frame(1), False, 26)
+    sps, pps, hdr, stop = consumer_header_scan(idr)
+    assert sps and pps and 0 < hdr <= 4096 and stop == 5
+    assert idr[:5] == b"\0\0\0\1\x67"
+    assert consumer_header_scan(p) == (False, False, 0, 1)
+    case = next(c for c in GOLDEN if "stream_hex" in c)
+    assert consumer_header_scan(bytes.fromhex(case["stream_hex"][0]))[:2] == (True, True)
