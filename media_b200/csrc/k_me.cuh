@@ -190,6 +190,10 @@ static __device__ __constant__ uint8_t c_qpel_tab[16][6] = {
     { 0, 0, 1, 2, 0, 0 }, { 2, 0, 0, 1, 0, 1 }, { 3, 0, 0, 1, 0, 1 }, { 2, 1, 0, 1, 0, 1 },
 };
 
+// the same table as byte offsets into FineSmem::plane (plane * 18 * 48 + dy * 48 + dx): sample A in the low, sample B in the high half
+static __device__ __constant__ uint32_t c_qpel_off[16] = { 0x00000000u, 0x03600000u, 0x03600360u, 0x03600001u, 0x06c00000u, 0x06c00360u, 0x0a200360u, 0x06c10360u, 0x06c006c0u, 0x0a2006c0u, 0x0a200a20u, 0x06c10a20u, 0x06c00030u, 0x039006c0u, 0x03900a20u, 0x039006c1u };
+static_assert(PL_ROWS * PL_STRIDE == 864, "c_qpel_off was generated for 18 rows of 48 bytes per plane");
+
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)   // sum of u8(a_i) * s8(b_i) + c: one IDP.4A
 {
     int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
@@ -206,16 +210,17 @@ __device__ __forceinline__ uint32_t plane_row(const uint32_t *pl, int o)   // 4 
 // and the Hadamard SATD is invariant under that (dyadic) permutation as long as the source rows are permuted alike.
 __device__ __forceinline__ void pred_rows_qpel(const FineSmem &sm, int o1, int bx, int by, int ox, int oy, int rx, uint32_t P[4])
 {
-    const uint8_t *t = c_qpel_tab[(oy & 3) * 4 + (ox & 3)];
-    const int xo = o1 + bx + (ox >> 2) + 4, yo = by + (oy >> 2) + 1;
-    const uint32_t *pa = sm.plane[t[0]], *pb = sm.plane[t[3]];
-    const int oa = (yo + t[2]) * PL_STRIDE + xo + t[1], ob = (yo + t[5]) * PL_STRIDE + xo + t[4];
+    const uint32_t t = c_qpel_off[(oy & 3) * 4 + (ox & 3)];
+    const int common = (by + (oy >> 2) + 1) * PL_STRIDE + o1 + bx + (ox >> 2) + 4;
+    const uint32_t *base = sm.plane[0];
+    const int oa = common + (int)(t & 0xffffu);
     if (((ox | oy) & 1) == 0) {          // full/half-pel positions are a single plane (both table entries coincide)
 #pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = plane_row(pa, oa + (y ^ rx) * PL_STRIDE);
+        for (int y = 0; y < 4; y++) P[y] = plane_row(base, oa + (y ^ rx) * PL_STRIDE);
     } else {
+        const int ob = common + (int)(t >> 16);
 #pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = avg4(plane_row(pa, oa + (y ^ rx) * PL_STRIDE), plane_row(pb, ob + (y ^ rx) * PL_STRIDE));
+        for (int y = 0; y < 4; y++) P[y] = avg4(plane_row(base, oa + (y ^ rx) * PL_STRIDE), plane_row(base, ob + (y ^ rx) * PL_STRIDE));
     }
 }
 // 4x4 Hadamard SATD of (source block - P): Ts holds the horizontal transforms of the source rows, the prediction
