@@ -263,6 +263,18 @@ __device__ __forceinline__ int quant_dequant4x4(int c[16], int16_t lz[16], const
     }
     return nnz;
 }
+// would quant_dequant4x4 produce any nonzero level? (the early-skip test of the motion search)
+__device__ __forceinline__ bool quant_any_nonzero(const int c[16], const QParam &q, int f, bool ac_only)
+{
+    bool nz = false;
+#pragma unroll
+    for (int pos = 0; pos < 16; pos++) {
+        if (ac_only && pos == 0) continue;
+        const int cl = ((pos & 1) && (pos & 4)) ? 1 : ((pos & 5) ? 2 : 0);
+        nz |= (((unsigned)abs(c[pos]) * (unsigned)q.mf[cl] + (unsigned)f) >> q.qbits) != 0u;
+    }
+    return nz;
+}
 __device__ __forceinline__ int quant_dc(int y, const QParam &q, int f)
 {
     int l = min((int)(((unsigned)abs(y) * (unsigned)q.mf[0] + 2u * (unsigned)f) >> (q.qbits + 1)), B200_MAX_LEVEL);

@@ -282,16 +282,56 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     }
     // zero-vector candidate, computed cooperatively straight from HBM while the tiles are in flight
     uint32_t zsad;
+    uint2 zref;
     {
         const uint8_t *rp = s.ref[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8;
         const uint8_t *sp = s.src[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8;
         uint2 a = *reinterpret_cast<const uint2 *>(rp), b = *reinterpret_cast<const uint2 *>(sp);
-        zsad = sad4(a.x, b.x, sad4(a.y, b.y, 0));
+        zsad = sad4(a.x, b.x, sad4(a.y, b.y, 0)); zref = a;
 #pragma unroll
         for (int o = 16; o; o >>= 1) zsad += __shfl_xor_sync(0xffffffffu, zsad, o);
     }
     __syncwarp();
     bool tma_ok = mbar_wait(&sm.bar[0]);
+    // EARLY SKIP: with a zero predictor estimate, a macroblock whose zero-vector residual quantises to nothing in
+    // luma and chroma is final -- P_L0_16x16, vector (0,0), cbp 0, reconstruction = reference. Static screen content (the bulk of
+    // a cloud-phone framebuffer) never enters the search. Lanes 0-15 test the luma blocks, 16-23 the chroma blocks.
+    if (ppx == 0 && ppy == 0) {
+        const bool isl = lane < 16, act = lane < 24;
+        const int cw = wc / 2, pl = (lane >> 2) & 1, cb = lane & 3, b = lane & 15;
+        const int st = isl ? wc : cw;
+        const size_t off = isl ? (size_t)(y0 + blk_y(b) * 4) * wc + x0 + blk_x(b) * 4 : (size_t)(my * 8 + (cb >> 1) * 4) * cw + mx * 8 + (cb & 1) * 4;
+        const uint8_t *sp = s.src[isl ? 0 : 1 + pl] + off, *rp = s.ref[isl ? 0 : 1 + pl] + off;
+        int c[16];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const uint32_t ws = *reinterpret_cast<const uint32_t *>(sp + (size_t)y * st), wr = *reinterpret_cast<const uint32_t *>(rp + (size_t)y * st);
+#pragma unroll
+            for (int x = 0; x < 4; x++) c[y * 4 + x] = (int)((ws >> (8 * x)) & 255) - (int)((wr >> (8 * x)) & 255);
+        }
+        fdct4x4(c);
+        const QParam q = make_qparam(isl ? qp : (int)c_chroma_qp[qp]);
+        bool nz = quant_any_nonzero(c, q, q.f_inter, !isl);
+        {   // chroma DC: 2x2 Hadamard of the four DC terms of the lane's plane (lanes 16+4pl .. 19+4pl)
+            int dcs[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) dcs[k] = __shfl_sync(0xffffffffu, c[0], 16 + pl * 4 + k);
+            const int hd[4] = { dcs[0] + dcs[1] + dcs[2] + dcs[3], dcs[0] - dcs[1] + dcs[2] - dcs[3], dcs[0] + dcs[1] - dcs[2] - dcs[3], dcs[0] - dcs[1] - dcs[2] + dcs[3] };
+            if (!isl) for (int k = 0; k < 4; k++) nz |= quant_dc(hd[k], q, q.f_inter) != 0;
+        }
+        if (__ballot_sync(0xffffffffu, act && nz) == 0) {
+            const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
+            const size_t co_ = (size_t)(my * 8 + crow) * cw + mx * 8 + chalf * 4;
+            *reinterpret_cast<uint2 *>(s.rec[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8) = zref;
+            *reinterpret_cast<uint32_t *>(s.rec[1 + cpl] + co_) = *reinterpret_cast<const uint32_t *>(s.ref[1 + cpl] + co_);
+            uint4 *cz = reinterpret_cast<uint4 *>(s.coef + mb);
+            cz[lane] = make_uint4(0, 0, 0, 0);
+            if (lane < 51 - 32) cz[32 + lane] = make_uint4(0, 0, 0, 0);
+            if (lane < 12) reinterpret_cast<uint32_t *>(s.mbi + mb)[lane] = 0u;      // P_L0_16x16, cbp 0, zero vectors, nnz 0
+            if (lane == 0) { s.me0[mb * 2] = 0; s.me0[mb * 2 + 1] = 0; s.inter_cost[mb] = 0; }
+            return;
+        }
+    }
     uint32_t *win0 = sm.plane[0];                       // four byte-shifted copies of the 20x20 window: aligned candidate reads
     for (int i = lane; i < 100; i += 32) {
         const int r = i / 5, j = i - r * 5;

@@ -219,7 +219,35 @@ static int sad_clamped(const uint8_t *a, const uint8_t *b, int w, int h, int ax,
  * Level 2 (1/4 res): 8x8 block centred on the MB, exhaustive +-R/4. Level 1 (1/2 res): 8x8, +-2 around 2*mv2.
  * Level 0: 16x16, +-2 around 2*mv1 plus the zero vector. Then 8 half-pel and 8 quarter-pel neighbours by SATD.
  * Every level picks argmin of key = (cost << k) | candidate_index, so ties resolve identically everywhere. ---- */
-static void motion_search(OrcEncoder *e, int mx, int my, int lambda)
+static int quant_dc_inter(int y, int qp);
+/* Early skip test: would the macroblock, predicted from the reference at the ZERO vector, quantise to all-zero levels in
+ * luma and chroma (same transform / inter dead zone as code_inter_mb and code_chroma)? */
+static int zero_vector_residual_vanishes(const OrcEncoder *e, int mx, int my, int qp)
+{
+    int st = e->wc, cs = st / 2, qpc = CHROMA_QP[qp];
+    const uint8_t *s = e->src[0] + (size_t)my * 16 * st + mx * 16, *r = e->ref[0] + (size_t)my * 16 * st + mx * 16;
+    for (int b = 0; b < 16; b++) {
+        int bx = BLK_X[b] * 4, by = BLK_Y[b] * 4; int16_t res[16], c[16], lz[16];
+        for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) res[y * 4 + x] = (int16_t)(s[(by + y) * st + bx + x] - r[(by + y) * st + bx + x]);
+        orc_dct4x4(res, c);
+        if (orc_quant4x4(c, lz, qp, 0, 0)) return 0;
+    }
+    for (int pl = 0; pl < 2; pl++) {
+        const uint8_t *sc = e->src[1 + pl] + (size_t)my * 8 * cs + mx * 8, *rc = e->ref[1 + pl] + (size_t)my * 8 * cs + mx * 8;
+        int dc[4];
+        for (int b = 0; b < 4; b++) {
+            int bx = (b & 1) * 4, by = (b >> 1) * 4; int16_t res[16], c[16], lz[16];
+            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) res[y * 4 + x] = (int16_t)(sc[(by + y) * cs + bx + x] - rc[(by + y) * cs + bx + x]);
+            orc_dct4x4(res, c); dc[b] = c[0];
+            if (orc_quant4x4(c, lz, qpc, 0, 1)) return 0;
+        }
+        int h[4] = { dc[0] + dc[1] + dc[2] + dc[3], dc[0] - dc[1] + dc[2] - dc[3], dc[0] + dc[1] - dc[2] - dc[3], dc[0] - dc[1] - dc[2] + dc[3] };
+        for (int i = 0; i < 4; i++) if (quant_dc_inter(h[i], qpc)) return 0;
+    }
+    return 1;
+}
+
+static void motion_search(OrcEncoder *e, int mx, int my, int lambda, int qp)
 {
     int mb = my * e->mbw + mx, R4 = e->cfg.search_range / 4, span = 2 * R4 + 1;
     int w2 = e->wc / 4, h2 = e->hc / 4, w1 = e->wc / 2, h1 = e->hc / 2;
@@ -252,6 +280,14 @@ static void motion_search(OrcEncoder *e, int mx, int my, int lambda)
         if (top && mx + 1 < e->mbw) { rx = m1[(mb - e->mbw + 1) * 2]; ry = m1[(mb - e->mbw + 1) * 2 + 1]; }
         else if (top && mx > 0) { rx = m1[(mb - e->mbw - 1) * 2]; ry = m1[(mb - e->mbw - 1) * 2 + 1]; }
         ppx = 8 * median3(ax, tx, rx); ppy = 8 * median3(ay, ty, ry);
+    }
+    /* EARLY SKIP: with a zero predictor estimate, a macroblock whose zero-vector residual quantises to nothing is
+     * final -- P_L0_16x16, vector (0,0), cbp 0 (P_Skip follows in phase D when the normative skip vector is zero too). Static
+     * screen content never enters the search. */
+    if (ppx == 0 && ppy == 0 && zero_vector_residual_vanishes(e, mx, my, qp)) {
+        OrcMbInfo *mi0 = &e->mbi[mb];
+        mi0->mb_type = ORC_MB_P16x16; e->me[0][mb * 2] = e->me[0][mb * 2 + 1] = 0; e->inter_cost[mb] = 0;
+        return;                              /* mbi was zeroed by the caller: mv = mv8 = 0 */
     }
     cx = 2 * bx; cy = 2 * by; best = 0xffffffffu;
     for (int i = 0; i < 26; i++) {
@@ -774,7 +810,7 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
             for (int mx = 0; mx < e->mbw; mx++) {
                 int mb = my * e->mbw + mx;
                 memset(&e->mbi[mb], 0, sizeof(OrcMbInfo));
-                motion_search(e, mx, my, lambda);
+                motion_search(e, mx, my, lambda, qp);
                 int ie = intra_estimate(e, mx, my);
                 if (ie + lambda * ORC_INTRA_BIAS_BITS < e->inter_cost[mb]) { memset(&e->mbi[mb], 0, sizeof(OrcMbInfo)); e->mbi[mb].mb_type = ORC_MB_I16x16; }
             }
