@@ -394,3 +394,21 @@ def test_realtime_paced_sessions_through_the_scheduler(enc):
     out = subprocess.run([exe, "12", "2", "640", "368", "30", "1000000"], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
     r = json.loads(out)
     assert r["errors"] == 0 and r["late_frames"] == 0 and r["achieved_fps_per_session"] > 29.0 and r["latency_ms"]["p99"] < 33.3, r
+
+
+def test_random_geometries_and_qps_match_the_oracle(enc, orc):
+    """seeded sweep over odd sizes, every QP range, slice counts and search ranges: bitstream and reconstruction bit-exact"""
+    rng = np.random.default_rng(20261018)
+    for trial in range(14):
+        w = int(rng.integers(8, 120)) * 2; h = int(rng.integers(8, 90)) * 2
+        qp = int(rng.choice([0, 7, 13, 19, 24, 28, 33, 38, 44, 51])); slices = int(rng.integers(1, 5)); sr = int(rng.choice([16, 32, 64]))
+        kind = str(rng.choice(["A", "B", "C", "D"]))
+        g = enc.Session(w, h, const_qp=qp, num_slices=slices, search_range=sr, gop=1000, device=0)
+        o = orc.Encoder(w, h, num_slices=slices, search_range=sr)
+        c = Content(kind, w, h, seed=int(rng.integers(1, 1 << 30)))
+        for t in range(3):
+            f = c.frame(t)
+            bs, _ = g.encode(f); ref = o.encode(f, t == 0, qp)
+            assert bs == ref, f"trial {trial}: {w}x{h} qp {qp} slices {slices} sr {sr} content {kind} frame {t}: bitstream"
+            assert np.array_equal(g.recon(), o.recon()), f"trial {trial} frame {t}: reconstruction"
+        g.close()
