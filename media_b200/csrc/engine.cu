@@ -316,9 +316,13 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         pf.begin("k_downsample1"); k_downsample<<<dim3((((g.wc / 4 + 2 * g.p2) / 4) * (g.hc / 4 + 2 * g.p2) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 1); pf.end();
         pf.begin("k_me_coarse");
         {
-            if (g.search_range <= 16) k_me_coarse<4, 8><<<dim3((nmb + 7) / 8, 1, n), 256, 0, st>>>(b->d_sess, g);
-            else if (g.search_range <= 32) k_me_coarse<8, 8><<<dim3((nmb + 7) / 8, 1, n), 256, 0, st>>>(b->d_sess, g);
-            else k_me_coarse<16, 4><<<dim3((nmb + 3) / 4, 1, n), 128, 0, st>>>(b->d_sess, g);
+            const dim3 g8((nmb + 7) / 8, 1, n), g4((nmb + 3) / 4, 1, n);
+            if (g.search_range == 16) k_me_coarse<4, 8, true><<<g8, 256, 0, st>>>(b->d_sess, g);
+            else if (g.search_range < 16) k_me_coarse<4, 8, false><<<g8, 256, 0, st>>>(b->d_sess, g);
+            else if (g.search_range == 32) k_me_coarse<8, 8, true><<<g8, 256, 0, st>>>(b->d_sess, g);
+            else if (g.search_range < 32) k_me_coarse<8, 8, false><<<g8, 256, 0, st>>>(b->d_sess, g);
+            else if (g.search_range == 64) k_me_coarse<16, 4, true><<<g4, 128, 0, st>>>(b->d_sess, g);
+            else k_me_coarse<16, 4, false><<<g4, 128, 0, st>>>(b->d_sess, g);
         }
         pf.end();
         pf.begin("k_me_fine"); k_me_fine<<<dim3((nmb + ME_WARPS - 1) / ME_WARPS, 1, n), ME_WARPS * 32, 0, st>>>(b->d_sess, g, b->d_ctl); pf.end();

@@ -204,7 +204,25 @@ __device__ __forceinline__ MbItem mb_item(const Sess &s, const Geom &g, int mx, 
     return it;
 }
 
-template <bool WRITE> __device__ void code_mb_header(BitSink<WRITE> &bs, const Sess &s, const Geom &g, int mx, int my, const MbInfo *mi, int skip_run)
+// motion vector differences of an inter MB, predicted once (8.4.1.3) and used by both passes of the header lane:
+// mvd[0..1] for P_L0_16x16, mvd[2q..2q+1] for partition q of P_8x8
+__device__ __forceinline__ void mb_mvds(const Sess &s, const Geom &g, int mx, int my, const MbInfo *mi, int mvd[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) mvd[k] = 0;
+    if (mi->mb_type == MB_P8x8) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int pmx, pmy; NbMv A, B; predict_mv_part(s, g, mx, my, q, pmx, pmy, A, B);
+            mvd[2 * q] = mi->mv8[q][0] - pmx; mvd[2 * q + 1] = mi->mv8[q][1] - pmy;
+        }
+    } else if (mi->mb_type == MB_P16x16) {
+        int pmx, pmy, skx, sky; predict_mv(s, g, mx, my, pmx, pmy, skx, sky);
+        mvd[0] = mi->mv[0] - pmx; mvd[1] = mi->mv[1] - pmy;
+    }
+}
+
+template <bool WRITE> __device__ void code_mb_header(BitSink<WRITE> &bs, const Sess &s, const Geom &g, int mx, int my, const MbInfo *mi, int skip_run, const int mvd[8])
 {
     const int cl = mi->cbp & 15, cc = mi->cbp >> 4;
     if (!s.is_idr) bs.ue((uint32_t)skip_run);
@@ -232,16 +250,13 @@ template <bool WRITE> __device__ void code_mb_header(BitSink<WRITE> &bs, const S
         // P_8x8 with four P_L0_8x8 sub-macroblocks (7.3.5.2); ref_idx_l0 is not coded with one reference picture
         bs.ue(3);
         for (int q = 0; q < 4; q++) bs.ue(0);
-        for (int q = 0; q < 4; q++) {
-            int pmx, pmy; NbMv A, B; predict_mv_part(s, g, mx, my, q, pmx, pmy, A, B);
-            bs.se(mi->mv8[q][0] - pmx); bs.se(mi->mv8[q][1] - pmy);
-        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) { bs.se(mvd[2 * q]); bs.se(mvd[2 * q + 1]); }
         bs.ue(c_cbp_inter[mi->cbp]);
         if (mi->cbp) bs.se(0);
     } else {
-        int pmx, pmy, skx, sky; predict_mv(s, g, mx, my, pmx, pmy, skx, sky);
         bs.ue(0);
-        bs.se(mi->mv[0] - pmx); bs.se(mi->mv[1] - pmy);
+        bs.se(mvd[0]); bs.se(mvd[1]);
         bs.ue(c_cbp_inter[mi->cbp]);
         if (mi->cbp) bs.se(0);
     }
@@ -265,11 +280,13 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, G
     MbItem it = mb_item(s, g, mx, my, lane, mi, co);
     if (lane >= 1 && lane < 28 && it.present)
         for (int i = 0; i < it.maxn; i++) lv[i] = it.lv[i];
+    int mvd[8];
+    if (lane == 0) mb_mvds(s, g, mx, my, mi, mvd);
     // pass 1: lengths
     int len = 0;
     {
         BitSink<false> bs; bs.w = nullptr; bs.pos = 0;
-        if (lane == 0) code_mb_header<false>(bs, s, g, mx, my, mi, skip_run);
+        if (lane == 0) code_mb_header<false>(bs, s, g, mx, my, mi, skip_run, mvd);
         else if (lane < 28 && it.present) code_residual<false>(bs, lv, it.maxn, it.nC);
         len = bs.pos;
     }
@@ -282,7 +299,7 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, G
     // pass 2: write at the lane's bit offset
     {
         BitSink<true> bs; bs.w = slot; bs.pos = incl - len;
-        if (lane == 0) code_mb_header<true>(bs, s, g, mx, my, mi, skip_run);
+        if (lane == 0) code_mb_header<true>(bs, s, g, mx, my, mi, skip_run, mvd);
         else if (lane < 28 && it.present) code_residual<true>(bs, lv, it.maxn, it.nC);
     }
     __syncwarp();

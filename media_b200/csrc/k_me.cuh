@@ -65,7 +65,8 @@ __device__ __forceinline__ void make_shifted_copies(uint32_t *c0, int copy_strid
     }
 }
 
-template <int MAXR4, int WARPS>
+// EXACT: the search range equals 4 * MAXR4 (the usual 16 / 32 / 64), so every window dimension and divisor is a compile-time constant
+template <int MAXR4, int WARPS, bool EXACT>
 __global__ void __launch_bounds__(WARPS * 32) k_me_coarse(const Sess *ss, Geom g)
 {
     typedef CoarseSmem<MAXR4> Smem;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_me_coarse(const Sess *ss, Geom g
     if (s.is_idr) return;
     Smem &sm = sm_all[warp];
     const int mx = mb % g.mbw, my = mb / g.mbw;
-    const int R4 = g.search_range / 4, span = 2 * R4 + 1, W = 8 + 2 * R4, wpr = W >> 2;
+    const int R4 = EXACT ? MAXR4 : g.search_range / 4, span = 2 * R4 + 1, W = 8 + 2 * R4, wpr = W >> 2;
 
     // level 2: 8x8 block centred on the MB (origin 4mx-2, 4my-2), all (2R4+1)^2 displacements
     stage_window<8, 8>(sm.src, s.srcL2, g.s2, 4 * mx - 2, 4 * my - 2, lane);
