@@ -9,8 +9,39 @@
 #pragma once
 #include "h264_dev.cuh"
 #include "k_intra.cuh"
+#include <cstdio>
 
 namespace b200 {
+
+#ifdef DBK_TIMING
+#define DBK_T(i) do { const long long t_ = clock64(); dbk_t[i] += t_ - dbk_last; dbk_last = t_; } while (0)
+#else
+#define DBK_T(i) do { } while (0)
+#endif
+
+// the few session fields the row loop needs, held in registers: every fence / strong access in the loop is a compiler memory
+// barrier, so reading them through `const Sess &` re-fetched them from L2 several times per macroblock (1 800 cycles measured)
+struct DbkCtx { uint8_t *rec[3]; const MbInfo *mbi; int qp; };
+
+// write-back slots of a lane: word lane + 32k of the luma tile (20 rows x 5 words) / of the two chroma tiles (2 x 12 rows x 3 words);
+// flags: 1 slot exists and is ever stored, 2 it lies in the rows above the MB, 4 it is not in the 4 left columns, 8 (chroma) plane
+struct DbkWb { int oy[4], oc[3]; int fy[4], fc[3]; };
+__device__ __forceinline__ void dbk_wb_init(DbkWb &wb, int wc, int lane)
+{
+    const int cw = wc / 2;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = lane + 32 * k, r = i / 5 - 4, c4 = (i % 5) * 4 - 4;
+        wb.oy[k] = r * wc + c4;
+        wb.fy[k] = ((i < 100 && r >= -3) ? 1 : 0) | (r < 0 ? 2 : 0) | (c4 >= 0 ? 4 : 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int i = lane + 32 * k, pl = i / 36, j = i - pl * 36, r = j / 3 - 4, c4 = (j % 3) * 4 - 4;
+        wb.oc[k] = r * cw + c4;
+        wb.fc[k] = ((i < 72 && r >= -2) ? 1 : 0) | (r < 0 ? 2 : 0) | (c4 >= 0 ? 4 : 0) | (pl ? 8 : 0);
+    }
+}
 
 struct DbkSmem {
     uint32_t y[20 * 5];        // rows -4..15, cols -4..15 (stride 20 bytes)
@@ -18,42 +49,37 @@ struct DbkSmem {
     uint32_t mbi[3][12];       // current, left, top MbInfo
 };
 
-__device__ __forceinline__ void filter_luma_edge(uint8_t *p, int step, int bs, int alpha, int beta, int tc0)
+// One edge position of one line of samples, luma or chroma in the same instruction stream (8.7.2.3 / 8.7.2.4): the 16 luma
+// lines and the 16 chroma lines of a macroblock edge are filtered by the 32 lanes at once instead of one after the other.
+// Chroma uses only p1..q1, tc = tc0 + 1 and the weak bS = 4 filter; the selects below fold that in.
+__device__ __forceinline__ void filter_edge(uint8_t *p, int step, int bs, int alpha, int beta, int tc0, bool chroma)
 {
-    const int p0 = p[-step], p1 = p[-2 * step], p2 = p[-3 * step], q0 = p[0], q1 = p[step], q2 = p[2 * step];
+    const int p0 = p[-step], p1 = p[-2 * step], q0 = p[0], q1 = p[step];
     if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-    const int ap = abs(p2 - p0), aq = abs(q2 - q0);
+    int p2 = 0, q2 = 0;
+    if (!chroma) { p2 = p[-3 * step]; q2 = p[2 * step]; }
+    const bool ap = !chroma && abs(p2 - p0) < beta, aq = !chroma && abs(q2 - q0) < beta;
     if (bs < 4) {
-        const int tc = tc0 + (ap < beta) + (aq < beta);
+        const int tc = chroma ? tc0 + 1 : tc0 + (int)ap + (int)aq;
         const int delta = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
         p[-step] = (uint8_t)clip255(p0 + delta);
         p[0] = (uint8_t)clip255(q0 - delta);
-        if (ap < beta) p[-2 * step] = (uint8_t)(p1 + clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1));
-        if (aq < beta) p[step] = (uint8_t)(q1 + clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1));
+        if (ap) p[-2 * step] = (uint8_t)(p1 + clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1));
+        if (aq) p[step] = (uint8_t)(q1 + clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1));
     } else {
-        const int p3 = p[-4 * step], q3 = p[3 * step];
         const bool small = abs(p0 - q0) < ((alpha >> 2) + 2);
-        if (ap < beta && small) {
+        if (ap && small) {
+            const int p3 = p[-4 * step];
             p[-step] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
             p[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
             p[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
         } else p[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        if (aq < beta && small) {
+        if (aq && small) {
+            const int q3 = p[3 * step];
             p[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
             p[step] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
             p[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
         } else p[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-    }
-}
-__device__ __forceinline__ void filter_chroma_edge(uint8_t *p, int step, int bs, int alpha, int beta, int tc0)
-{
-    const int p0 = p[-step], p1 = p[-2 * step], q0 = p[0], q1 = p[step];
-    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-    if (bs < 4) {
-        const int tc = tc0 + 1, delta = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
-        p[-step] = (uint8_t)clip255(p0 + delta); p[0] = (uint8_t)clip255(q0 - delta);
-    } else {
-        p[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2); p[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
     }
 }
 
@@ -74,7 +100,7 @@ __device__ __forceinline__ int bs_of(const uint32_t *mp, int bxp, int byp, const
 // from the previous tile in shared memory, and only the rows above are loaded after the wavefront wait.
 struct DbkPrefetch { uint32_t y0, y1, c, info; };
 
-__device__ __forceinline__ void dbk_prefetch(const Sess &s, const Geom &g, int mx, int my, int lane, DbkPrefetch &pf)
+__device__ __forceinline__ void dbk_prefetch(const DbkCtx &s, const Geom &g, int mx, int my, int lane, DbkPrefetch &pf)
 {
     const int wc = g.wc, cw = wc / 2, mb = my * g.mbw + mx;
     const uint8_t *Y = s.rec[0] + (size_t)my * 16 * wc + mx * 16;
@@ -82,7 +108,7 @@ __device__ __forceinline__ void dbk_prefetch(const Sess &s, const Geom &g, int m
     pf.y0 = __ldcg(reinterpret_cast<const uint32_t *>(Y + (size_t)(lane >> 2) * wc + (lane & 3) * 4));
     pf.y1 = __ldcg(reinterpret_cast<const uint32_t *>(Y + (size_t)(8 + (lane >> 2)) * wc + (lane & 3) * 4));
     // chroma: 2 planes x 8 rows x 2 words
-    const uint8_t *C = s.rec[1 + (lane >> 4)] + (size_t)(my * 8 + ((lane >> 1) & 7)) * cw + mx * 8 + (lane & 1) * 4;
+    const uint8_t *C = ((lane >> 4) ? s.rec[2] : s.rec[1]) + (size_t)(my * 8 + ((lane >> 1) & 7)) * cw + mx * 8 + (lane & 1) * 4;
     pf.c = __ldcg(reinterpret_cast<const uint32_t *>(C));
     // MbInfo: lanes 0-11 current MB, lanes 12-23 the MB above
     pf.info = 0;
@@ -91,8 +117,12 @@ __device__ __forceinline__ void dbk_prefetch(const Sess &s, const Geom &g, int m
 }
 
 // returns true when the MB wrote samples (a fence is needed before publishing)
-__device__ bool deblock_mb(const Sess &s, const Geom &g, DbkSmem &sm, int mx, int my, int lane, const DbkPrefetch &pf,
-                           const int *prog_above, WaveCtl *ctl, bool &ok)
+__device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const DbkWb &wb, int mx, int my, int lane, const DbkPrefetch &pf,
+                           const int *prog_above, WaveCtl *ctl, bool &ok
+#ifdef DBK_TIMING
+                           , long long *dbk_t, long long &dbk_last
+#endif
+                           )
 {
     const int wc = g.wc, cw = wc / 2, qp = s.qp, qpc = c_chroma_qp[qp];
     ok = true;
@@ -118,6 +148,7 @@ __device__ bool deblock_mb(const Sess &s, const Geom &g, DbkSmem &sm, int mx, in
             else bs = my > 0 ? bs_of(sm.mbi[2], k, 3, sm.mbi[0], k, 0, true) : 0;
         } else bs = vert ? bs_of(sm.mbi[0], e - 1, k, sm.mbi[0], e, k, false) : bs_of(sm.mbi[0], k, e - 1, sm.mbi[0], k, e, false);
     }
+    DBK_T(1);
     if (__ballot_sync(0xffffffffu, bs != 0) == 0) return false;
 
     uint8_t *Y = s.rec[0] + (size_t)my * 16 * wc + mx * 16;
@@ -132,42 +163,45 @@ __device__ bool deblock_mb(const Sess &s, const Geom &g, DbkSmem &sm, int mx, in
         }
     }
     __syncwarp();
+    DBK_T(2);
     const int alphaY = c_alpha[qp], betaY = c_beta[qp], alphaC = c_alpha[qpc], betaC = c_beta[qpc];
     uint8_t *ty = reinterpret_cast<uint8_t *>(sm.y) + 4 * 20 + 4;            // sample (0,0) of the MB
     uint8_t *tc = reinterpret_cast<uint8_t *>(sm.c[(lane >> 3) & 1]) + 4 * 12 + 4;
-    // vertical edges (filtering across columns), left to right
+    const bool isc = lane >= 16;
+    const int qpl = isc ? qpc : qp, alphaL = isc ? alphaC : alphaY, betaL = isc ? betaC : betaY;
+    const int seg = isc ? (lane & 7) >> 1 : lane >> 2;
+    // vertical edges (filtering across columns), left to right; chroma lines take part in the even ones
 #pragma unroll 1
     for (int e = 0; e < 4; e++) {
-        const int seg = lane < 16 ? lane >> 2 : (lane & 7) >> 1;
         const int b = __shfl_sync(0xffffffffu, bs, e * 4 + seg);
-        if (b) {
-            if (lane < 16) filter_luma_edge(ty + lane * 20 + 4 * e, 1, b, alphaY, betaY, b < 4 ? c_tc0[qp][b - 1] : 0);
-            else if (!(e & 1)) filter_chroma_edge(tc + (lane & 7) * 12 + 2 * e, 1, b, alphaC, betaC, b < 4 ? c_tc0[qpc][b - 1] : 0);
-        }
+        uint8_t *p = isc ? tc + (lane & 7) * 12 + 2 * e : ty + lane * 20 + 4 * e;
+        if (b && !(isc && (e & 1))) filter_edge(p, 1, b, alphaL, betaL, b < 4 ? c_tc0[qpl][b - 1] : 0, isc);
     }
     __syncwarp();
+    DBK_T(3);
     // horizontal edges (filtering across rows), top to bottom
 #pragma unroll 1
     for (int e = 0; e < 4; e++) {
-        const int seg = lane < 16 ? lane >> 2 : (lane & 7) >> 1;
         const int b = __shfl_sync(0xffffffffu, bs, 16 + e * 4 + seg);
-        if (b) {
-            if (lane < 16) filter_luma_edge(ty + 4 * e * 20 + lane, 20, b, alphaY, betaY, b < 4 ? c_tc0[qp][b - 1] : 0);
-            else if (!(e & 1)) filter_chroma_edge(tc + 2 * e * 12 + (lane & 7), 12, b, alphaC, betaC, b < 4 ? c_tc0[qpc][b - 1] : 0);
-        }
+        uint8_t *p = isc ? tc + 2 * e * 12 + (lane & 7) : ty + 4 * e * 20 + lane;
+        if (b && !(isc && (e & 1))) filter_edge(p, isc ? 12 : 20, b, alphaL, betaL, b < 4 ? c_tc0[qpl][b - 1] : 0, isc);
     }
     __syncwarp();
-    // write back: the MB with its 4 left columns, and the 3 rows above it
-    for (int i = lane; i < 100; i += 32) {
-        const int r = i / 5 - 4, c4 = (i % 5) * 4 - 4;
-        const bool st = r >= 0 ? (c4 >= 0 || mx > 0) : (r >= -3 && c4 >= 0 && my > 0);
-        if (st) *reinterpret_cast<uint32_t *>(Y + (ptrdiff_t)r * wc + c4) = sm.y[i];
+    DBK_T(4);
+    // write back: the MB with its 4 left columns, and the 3 rows above it (per-lane store slots precomputed once per row)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int f = wb.fy[k];
+        const bool st = (f & 1) && ((f & 2) ? ((f & 4) && my > 0) : ((f & 4) || mx > 0));
+        if (st) *reinterpret_cast<uint32_t *>(Y + wb.oy[k]) = sm.y[lane + 32 * k];
     }
-    for (int i = lane; i < 72; i += 32) {
-        const int pl = i / 36, j = i - pl * 36, r = j / 3 - 4, c4 = (j % 3) * 4 - 4;
-        const bool st = r >= 0 ? (c4 >= 0 || mx > 0) : (r >= -2 && c4 >= 0 && my > 0);
-        if (st) *reinterpret_cast<uint32_t *>(C[pl] + (ptrdiff_t)r * cw + c4) = sm.c[pl][j];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int f = wb.fc[k];
+        const bool st = (f & 1) && ((f & 2) ? ((f & 4) && my > 0) : ((f & 4) || mx > 0));
+        if (st) *reinterpret_cast<uint32_t *>(C[(f >> 3) & 1] + wb.oc[k]) = sm.c[0][lane + 32 * k];
     }
+    DBK_T(5);
     return true;
 }
 
@@ -182,15 +216,25 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= nsess * g.mbh) return;
     const int my = t / nsess;
-    const Sess &s = ss[t % nsess];
-    int *prog = s.row_prog_dbk;
+    const Sess &sg = ss[t % nsess];
+    int *prog = sg.row_prog_dbk;
+    DbkCtx s; s.rec[0] = sg.rec[0]; s.rec[1] = sg.rec[1]; s.rec[2] = sg.rec[2]; s.mbi = sg.mbi; s.qp = sg.qp;
+    DbkWb wb; dbk_wb_init(wb, g.wc, lane);
     DbkPrefetch cur, nxt;
     dbk_prefetch(s, g, 0, my, lane, cur);
     int published = 0;
+#ifdef DBK_TIMING
+    long long dbk_t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, dbk_last = clock64(); int dbk_n = 0;
+#endif
     for (int mx = 0; mx < g.mbw; mx++) {
         if (mx + 1 < g.mbw) dbk_prefetch(s, g, mx + 1, my, lane, nxt);
+        DBK_T(0);
         bool ok;
-        const bool wrote = deblock_mb(s, g, sm_all[warp], mx, my, lane, cur, prog + my - 1, ctl, ok);
+#ifdef DBK_TIMING
+        const bool wrote = deblock_mb(s, g, sm_all[warp], wb, mx, my, lane, cur, prog + my - 1, ctl, ok, dbk_t, dbk_last); dbk_n += wrote;
+#else
+        const bool wrote = deblock_mb(s, g, sm_all[warp], wb, mx, my, lane, cur, prog + my - 1, ctl, ok);
+#endif
         if (!ok) return;
         if (wrote) {
             fence_acq_rel_gpu();
@@ -201,8 +245,14 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss
             if (lane == 0) st_relaxed(prog + my, mx + 1);
             published = mx + 1;
         }
+        DBK_T(6);
         cur = nxt;
     }
+#ifdef DBK_TIMING
+    if (lane == 0 && my == 0 && t % nsess == 0)
+        printf("dbk row0: %d MBs (%d filtered) cycles/MB: prefetch %lld stage+bs %lld wait+above %lld vert %lld horz %lld writeback %lld fence+publish %lld\n", g.mbw, dbk_n,
+               dbk_t[0] / g.mbw, dbk_t[1] / g.mbw, dbk_t[2] / g.mbw, dbk_t[3] / g.mbw, dbk_t[4] / g.mbw, dbk_t[5] / g.mbw, dbk_t[6] / g.mbw);
+#endif
 }
 
 } // namespace b200
