@@ -83,11 +83,19 @@ static __device__ __constant__ uint32_t c_i4_idx[9][4] = {
 };
 #define I4_BIAS_BITS 24       /* fixed cost of choosing Intra_4x4 (16 mode flags), in lambda units */
 
+// the session fields the row loop needs, in registers (every fence / strong access is a compiler memory barrier, and the L1
+// invalidation behind the acquire makes re-reading them through `const Sess &` an L2 round trip each)
+struct IntraCtx {
+    uint8_t *rec0, *rec1, *rec2; const uint8_t *src0, *src1, *src2; MbInfo *mbi; MbCoef *coef; int qp, is_idr;
+    __device__ __forceinline__ uint8_t *rec(int c) const { return c == 0 ? rec0 : c == 1 ? rec1 : rec2; }
+    __device__ __forceinline__ const uint8_t *src(int c) const { return c == 0 ? src0 : c == 1 ? src1 : src2; }
+};
+
 // Trial coding of the luma of one MB as Intra_4x4: the 16 blocks in decoding order; lanes 0-8 evaluate the nine predictors of a
 // block (SATD + lambda * mode bits, key = cost << 4 | mode), the winner is transformed, quantised and reconstructed at once
 // (the next block predicts from it). Gives up as soon as the running cost reaches `limit` (the Intra_16x16 SATD).
 // On success the levels, nnz and reconstruction are in place; returns true, the luma cbp and the 16 modes (4 bits each).
-__device__ bool intra_try_i4x4(const Sess &s, const Geom &g, IntraSmem &sm, int mx, int my, int lane, int limit,
+__device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, int mx, int my, int lane, int limit,
                                bool top, bool left, int &cbp_luma, unsigned long long &modes)
 {
     const int wc = g.wc, mb = my * g.mbw + mx, qp = s.qp, lambda = c_lambda[qp];
@@ -99,7 +107,7 @@ __device__ bool intra_try_i4x4(const Sess &s, const Geom &g, IntraSmem &sm, int 
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const int wi = lane + 32 * i;
-        sm.srcw[wi] = *reinterpret_cast<const uint32_t *>(s.src[0] + (size_t)(my * 16 + (wi >> 2)) * wc + mx * 16 + (wi & 3) * 4);
+        sm.srcw[wi] = *reinterpret_cast<const uint32_t *>(s.src0 + (size_t)(my * 16 + (wi >> 2)) * wc + mx * 16 + (wi & 3) * 4);
     }
     if (lane < 25) {
         const int gy = lane / 5, gx = lane - gy * 5;
@@ -213,7 +221,7 @@ __device__ bool intra_try_i4x4(const Sess &s, const Geom &g, IntraSmem &sm, int 
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const int wi = lane + 32 * i, r = wi >> 2, cw4 = wi & 3;
-        *reinterpret_cast<uint32_t *>(s.rec[0] + (size_t)(my * 16 + r) * wc + mx * 16 + cw4 * 4) = sm.nb[((r + 1) * 24 + 4 + cw4 * 4) >> 2];
+        *reinterpret_cast<uint32_t *>(s.rec0 + (size_t)(my * 16 + r) * wc + mx * 16 + cw4 * 4) = sm.nb[((r + 1) * 24 + 4 + cw4 * 4) >> 2];
     }
     return true;
 }
@@ -235,7 +243,7 @@ __device__ __forceinline__ void intra_pred_block(int kind, const uint8_t *T, con
         }
 }
 
-__device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int mx, int my, int lane)
+__device__ void intra_code_mb(const IntraCtx &s, const Geom &g, IntraSmem &sm, int mx, int my, int lane)
 {
     const int wc = g.wc, cw = wc / 2, mb = my * g.mbw + mx, qp = s.qp;
     const bool top = !row_is_slice_top(g, my), left = mx > 0;
@@ -246,7 +254,7 @@ __device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int m
         if (i < 37) { comp = 0; is_top = i < 21; idx = is_top ? i : i - 21; }
         else { int j = i - 37; comp = 1 + j / 17; j %= 17; is_top = j < 9; idx = is_top ? j : j - 9; }
         const int n = comp ? 8 : 16, st = comp ? cw : wc, px0 = mx * n, py0 = my * n;
-        const uint8_t *r = s.rec[comp];
+        const uint8_t *r = s.rec(comp);
         if (is_top) {     // idx 0 = corner, 1..n = row above
             int v = 0;
             if (top && (idx > 0 || left) && (idx <= n || mx + 1 < g.mbw)) v = __ldcg(r + (size_t)(py0 - 1) * st + px0 + idx - 1);
@@ -266,7 +274,7 @@ __device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int m
     // source block
     int sp[16];
     {
-        const uint8_t *spx = s.src[comp] + (size_t)(my * n + by) * st + mx * n + bx;
+        const uint8_t *spx = s.src(comp) + (size_t)(my * n + by) * st + mx * n + bx;
 #pragma unroll
         for (int y = 0; y < 4; y++) {
             uint32_t w = *reinterpret_cast<const uint32_t *>(spx + (size_t)y * st);
@@ -359,7 +367,7 @@ __device__ void intra_code_mb(const Sess &s, const Geom &g, IntraSmem &sm, int m
         idct4x4(c);
         uint4 *dst = reinterpret_cast<uint4 *>(is_luma ? co->luma[b] : co->chroma_ac[comp - 1][cb]);
         dst[0] = reinterpret_cast<uint4 *>(lz)[0]; dst[1] = reinterpret_cast<uint4 *>(lz)[1];
-        uint8_t *rp = s.rec[comp] + (size_t)(my * n + by) * st + mx * n + bx;
+        uint8_t *rp = s.rec(comp) + (size_t)(my * n + by) * st + mx * n + bx;
 #pragma unroll
         for (int y = 0; y < 4; y++) {
             uint32_t w = 0;
@@ -391,9 +399,11 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_intra_wave(const Sess *ss, 
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= nsess * g.mbh) return;
     const int my = t / nsess;
-    const Sess &s = ss[t % nsess];
+    const Sess &sg = ss[t % nsess];
     IntraSmem &sm = sm_all[warp];
-    int *prog = s.row_prog_intra;
+    int *prog = sg.row_prog_intra;
+    IntraCtx s; s.rec0 = sg.rec[0]; s.rec1 = sg.rec[1]; s.rec2 = sg.rec[2]; s.src0 = sg.src[0]; s.src1 = sg.src[1]; s.src2 = sg.src[2];
+    s.mbi = sg.mbi; s.coef = sg.coef; s.qp = sg.qp; s.is_idr = sg.is_idr;
     const bool slice_top = row_is_slice_top(g, my);
     int mx = 0;
     while (mx < g.mbw) {
