@@ -102,16 +102,18 @@ __global__ void __launch_bounds__(256) k_pskip_scan(const Sess *ss, Geom g)
     if (threadIdx.x == 0) s.skip_run[nmb + sl] = m1 - 1 - carry_s;
 }
 
-// ---- bit sink: MSB-first bits into a zeroed word array shared by the lanes of a warp ----
-template <bool WRITE> struct BitSink {
-    uint32_t *w; int pos;
+// ---- bit sink, MSB first. MODE 0: count only; MODE 1: OR into a zeroed word array shared by the lanes of a warp;
+// MODE 2: collect up to 64 bits in a register (pos keeps counting past 64, which is how the caller sees an overflow) ----
+template <int MODE> struct BitSink {
+    uint32_t *w; int pos; unsigned long long acc;
     __device__ __forceinline__ void put(int n, uint32_t v)
     {
-        if (WRITE && n > 0) {
+        if (MODE == 1 && n > 0) {
             const int o = pos & 31, wi = pos >> 5;
             if (o + n <= 32) atomicOr(w + wi, v << (32 - o - n));
             else { atomicOr(w + wi, v >> (o + n - 32)); atomicOr(w + wi + 1, v << (64 - o - n)); }
         }
+        if (MODE == 2 && n > 0 && pos + n <= 64) acc |= (unsigned long long)v << (64 - pos - n);
         pos += n;
     }
     __device__ __forceinline__ void ue(uint32_t v) { const int l = 31 - __clz(v + 1u); put(2 * l + 1, v + 1u); }
@@ -119,7 +121,7 @@ template <bool WRITE> struct BitSink {
 };
 
 // residual_block_cavlc (7.3.5.3.2, 9.2) of `maxn` levels lv[0..maxn-1] in scan order; nC < 0 selects the chroma DC tables
-template <bool WRITE> __device__ void code_residual(BitSink<WRITE> &bs, const int16_t *lv, int maxn, int nC)
+template <int MODE> __device__ void code_residual(BitSink<MODE> &bs, const int16_t *lv, int maxn, int nC)
 {
     int total = 0, last = -1, t1 = 0; bool t1_open = true;
     for (int i = maxn - 1; i >= 0; i--) {
@@ -222,7 +224,7 @@ __device__ __forceinline__ void mb_mvds(const Sess &s, const Geom &g, int mx, in
     }
 }
 
-template <bool WRITE> __device__ void code_mb_header(BitSink<WRITE> &bs, const Sess &s, const Geom &g, int mx, int my, const MbInfo *mi, int skip_run, const int mvd[8])
+template <int MODE> __device__ void code_mb_header(BitSink<MODE> &bs, const Sess &s, const Geom &g, int mx, int my, const MbInfo *mi, int skip_run, const int mvd[8])
 {
     const int cl = mi->cbp & 15, cc = mi->cbp >> 4;
     if (!s.is_idr) bs.ue((uint32_t)skip_run);
@@ -282,13 +284,13 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, G
         for (int i = 0; i < it.maxn; i++) lv[i] = it.lv[i];
     int mvd[8];
     if (lane == 0) mb_mvds(s, g, mx, my, mi, mvd);
-    // pass 1: lengths
-    int len = 0;
+    // pass 1: every lane codes its syntax group into a 64-bit register (and counts its length)
+    int len = 0; unsigned long long acc = 0ull;
     {
-        BitSink<false> bs; bs.w = nullptr; bs.pos = 0;
-        if (lane == 0) code_mb_header<false>(bs, s, g, mx, my, mi, skip_run, mvd);
-        else if (lane < 28 && it.present) code_residual<false>(bs, lv, it.maxn, it.nC);
-        len = bs.pos;
+        BitSink<2> bs; bs.w = nullptr; bs.pos = 0; bs.acc = 0ull;
+        if (lane == 0) code_mb_header<2>(bs, s, g, mx, my, mi, skip_run, mvd);
+        else if (lane < 28 && it.present) code_residual<2>(bs, lv, it.maxn, it.nC);
+        len = bs.pos; acc = bs.acc;
     }
     int incl = len;
 #pragma unroll
@@ -296,11 +298,21 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, G
     const int total = __shfl_sync(0xffffffffu, incl, 31), nwords = (total + 31) >> 5;
     for (int i = lane; i <= nwords && i < B200_MB_SLOT_WORDS; i += 32) slot[i] = 0;
     __syncwarp();
-    // pass 2: write at the lane's bit offset
-    {
-        BitSink<true> bs; bs.w = slot; bs.pos = incl - len;
-        if (lane == 0) code_mb_header<true>(bs, s, g, mx, my, mi, skip_run, mvd);
-        else if (lane < 28 && it.present) code_residual<true>(bs, lv, it.maxn, it.nC);
+    if (__ballot_sync(0xffffffffu, len > 64) == 0) {
+        // the usual case: no group is longer than 64 bits; drop the registers in at the lanes' bit offsets
+        if (len > 0) {
+            const int off = incl - len, o = off & 31, wi = off >> 5;
+            const uint32_t hi = (uint32_t)(acc >> 32), lo = (uint32_t)acc;
+            const uint32_t w0 = hi >> o, w1 = o ? (hi << (32 - o)) | (lo >> o) : lo, w2 = o ? lo << (32 - o) : 0u;
+            if (w0) atomicOr(slot + wi, w0);
+            if (w1) atomicOr(slot + wi + 1, w1);
+            if (w2) atomicOr(slot + wi + 2, w2);
+        }
+    } else {
+        // pass 2 (long groups: high-rate intra blocks): code again, writing at the lane's bit offset
+        BitSink<1> bs; bs.w = slot; bs.pos = incl - len; bs.acc = 0ull;
+        if (lane == 0) code_mb_header<1>(bs, s, g, mx, my, mi, skip_run, mvd);
+        else if (lane < 28 && it.present) code_residual<1>(bs, lv, it.maxn, it.nC);
     }
     __syncwarp();
     uint32_t *dst = s.mb_slot + (size_t)mb * B200_MB_SLOT_WORDS;
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(256) k_slice_scan(const Sess *ss, Geom g)
     __shared__ int hdr_bits_s;
     if (threadIdx.x == 0) {      // slice_header(), 7.3.3
         hdr[0] = hdr[1] = hdr[2] = hdr[3] = 0;
-        BitSink<true> bs; bs.w = hdr; bs.pos = 0;
+        BitSink<1> bs; bs.w = hdr; bs.pos = 0; bs.acc = 0ull;
         bs.ue((uint32_t)m0);
         bs.ue(s.is_idr ? 7 : 5);
         bs.ue(0);
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(256) k_slice_scan(const Sess *ss, Geom g)
     for (int i = threadIdx.x; i <= nwords; i += 256) rb[i] = i < 4 ? hdr[i] : 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
-        BitSink<true> bs; bs.w = rb; bs.pos = hdr_bits + total;
+        BitSink<1> bs; bs.w = rb; bs.pos = hdr_bits + total; bs.acc = 0ull;
         if (trailing_run) bs.ue((uint32_t)trailing_run);
         bs.put(1, 1);
         s.slice_bits[sl] = (uint32_t)all_bits;
