@@ -588,8 +588,9 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
                 !encode_tmap(&tm[2], s->rpl, 3, (uint64_t)g.ls, H, 4, (uint64_t)g.ls, (uint64_t)g.ls * H, 48, 18, 4)) { rc = B200ENC_ENODEV; break; }
             CU_TRY(cudaMemcpy(s->tmaps, tm, sizeof tm, cudaMemcpyHostToDevice), rc = B200ENC_ECUDA; break);
         }
-        // output buffer: generous bound on a frame (every MB at the CAVLC worst case is ~1.4 KB; 1/2 of raw + 64 KB covers QP >= ~8 content)
-        s->out_cap = (uint32_t)align_up(std::max<size_t>(ny * 3 / 2, 1 << 16) + (1 << 16), 256);
+        // output buffer: twice the raw frame + 64 KB (CAVLC without I_PCM can exceed the raw size on noise at very low QP:
+        // 1.75x measured at QP 0); a frame that still does not fit is reported as B200ENC_EOVERFLOW, never truncated silently
+        s->out_cap = (uint32_t)align_up(std::max<size_t>(ny * 3, 1 << 16) + (1 << 16), 256);
         CU_TRY(cudaHostAlloc(&s->h_out, s->out_cap + 256, cudaHostAllocMapped), rc = B200ENC_ENOMEM; break);
         CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s->d_out), s->h_out, 0), rc = B200ENC_ECUDA; break);
         memset(s->h_out, 0, s->out_cap + 256);
