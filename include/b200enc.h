@@ -56,6 +56,8 @@ typedef struct b200enc_config {
     int device;            /* CUDA ordinal, or -1: least-loaded device by pixel rate */
     int level_idc;         /* 0: derive from size and fps (the wrapper's LEVEL_3_2 at :255 is too small for 1080p) */
     int debug;             /* 1: keep stage dumps (pre-deblock reconstruction) for b200enc_get_stage */
+    int scene_change;      /* 1 (default): a P frame whose macroblocks come out >= 2/5 intra after motion estimation is coded as an
+                              IDR instead (the wrapper asks openh264 for bEnableSceneChangeDetect, VideoEncoderOpenH264.cpp:283) */
     int auto_batch;        /* 1: concurrent b200enc_encode calls of sessions living on the same GPU are coalesced by a per-GPU
                               scheduler thread into one batch step (what gives many single-threaded callers GPU-wide throughput) */
 } b200enc_config;

@@ -295,7 +295,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         d.skip_run = s->skip_run; d.mb_bits = s->mb_bits; d.mb_off = s->mb_off; d.mb_slot = s->mb_slot; d.rbsp = s->rbsp; d.slice_bits = s->slice_bits;
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
-        d.qp = qp; d.is_idr = idr; d.frame_num = s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
+        d.qp = qp; d.is_idr = idr; d.frame_num = s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format; d.scene_change = s->cfg.scene_change && !idr;
         d.rbsp_words_per_slice = s->rbsp_words_per_slice; d.out_cap = s->out_cap;
     }
     CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
@@ -326,7 +326,8 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         }
         pf.end();
         pf.begin("k_me_fine"); k_me_fine<<<dim3((nmb + ME_WARPS - 1) / ME_WARPS, 1, n), ME_WARPS * 32, 0, st>>>(b->d_sess, g, b->d_ctl); pf.end();
-        launches += 6;
+        pf.begin("k_scene_change"); k_scene_change<<<n, 256, 0, st>>>(b->d_sess, g); pf.end();
+        launches += 7;
     }
     const int wave_ctas = (n * g.mbh + WAVE_WARPS - 1) / WAVE_WARPS;
     pf.begin("k_intra_wave"); k_intra_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
@@ -357,6 +358,10 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     for (int i = 0; i < n; i++) {
         b200enc_session *s = ss[i];
         const uint32_t size = *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap);
+        if (s->last_type == 0 && *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap + 4)) {
+            // scene change: the device coded this P picture as an IDR (k_scene_change); follow it on the host side
+            s->last_type = 1; s->frame_num = 0; s->frames_since_idr = 0;
+        }
         if (size >= s->out_cap) rc = B200ENC_EOVERFLOW;
         if (s->cfg.const_qp < 0) s->rc.update(s->last_type, s->last_qp, 8.0 * size);
         if (bs) bs[i] = s->h_out;
@@ -487,7 +492,7 @@ void b200enc_default_config(b200enc_config *c)
     memset(c, 0, sizeof *c);
     // defaults of the reference wrapper: 720x1280, 30 fps, 5 Mbps, gop 30 (video_codec/VideoEncoderOpenH264.h:13-24)
     c->width = 720; c->height = 1280; c->fps = 30; c->bitrate = 5000000; c->gop = 30; c->const_qp = -1;
-    c->num_slices = 1; c->search_range = 16; c->input_format = B200ENC_FMT_I420; c->device = -1;
+    c->num_slices = 1; c->search_range = 16; c->input_format = B200ENC_FMT_I420; c->device = -1; c->scene_change = 1;
 }
 
 int b200enc_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }

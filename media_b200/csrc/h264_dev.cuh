@@ -72,6 +72,7 @@ struct Sess {
     const uint8_t *hdr; int hdr_len;   // SPS+PPS NALs, prepended on IDR
     int *row_prog_intra, *row_prog_dbk; // wavefront progress counters, one per MB row
     int qp, is_idr, frame_num, idr_pic_id, input_format;
+    int scene_change;             // 1: k_scene_change may turn this P picture into an IDR (then is_idr / frame_num are rewritten on the device)
     uint32_t rbsp_words_per_slice, out_cap;
 };
 

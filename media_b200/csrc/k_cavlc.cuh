@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(1024) k_nal_pack(const Sess *ss, Geom g)
         if (threadIdx.x == 0) out_pos_s = o0 + nbytes;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *s.out_size = (uint32_t)min(out_pos_s, (int)s.out_cap);
+    if (threadIdx.x == 0) { s.out_size[0] = (uint32_t)min(out_pos_s, (int)s.out_cap); s.out_size[1] = (uint32_t)s.is_idr; }   // size, then the frame kind actually coded
 }
 
 } // namespace b200

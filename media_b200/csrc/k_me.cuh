@@ -568,4 +568,27 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     } else if (lane < 5) reinterpret_cast<uint32_t *>(mi)[1 + lane] = mvq;
 }
 
+// Scene change (phase A'): the wrapper asks openh264 for bEnableSceneChangeDetect (video_codec/VideoEncoderOpenH264.cpp:283). Here
+// a P picture whose macroblocks came out >= 2/5 intra from the motion search (normal P pictures: a few percent) is coded as an IDR instead: the session's descriptor
+// is rewritten on the device (is_idr, frame_num), every MB is marked intra, and the host reads the kind back with the size.
+// grid: (sessions), 256 threads
+__global__ void __launch_bounds__(256) k_scene_change(Sess *ss, Geom g)
+{
+    Sess &s = ss[blockIdx.x];
+    if (s.is_idr || !s.scene_change) return;
+    __shared__ int cnt_s;
+    if (threadIdx.x == 0) cnt_s = 0;
+    __syncthreads();
+    const int nmb = g.mbw * g.mbh;
+    int c = 0;
+    for (int mb = threadIdx.x; mb < nmb; mb += 256) c += s.mbi[mb].mb_type == MB_I16x16;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&cnt_s, c);
+    __syncthreads();
+    if (5 * cnt_s < 2 * nmb) return;
+    for (int i = threadIdx.x; i < nmb * 12; i += 256) reinterpret_cast<uint32_t *>(s.mbi)[i] = (i % 12) == 0 ? (uint32_t)MB_I16x16 : 0u;
+    if (threadIdx.x == 0) { s.is_idr = 1; s.frame_num = 0; }
+}
+
 } // namespace b200

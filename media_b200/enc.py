@@ -21,7 +21,7 @@ MBCOEF_DTYPE = np.dtype([("luma", "<i2", (16, 16)), ("luma_dc", "<i2", (16,)),
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "height", "fps", "bitrate", "gop", "const_qp", "num_slices",
-                                       "search_range", "input_format", "device", "level_idc", "debug", "auto_batch")]
+                                       "search_range", "input_format", "device", "level_idc", "debug", "scene_change", "auto_batch")]
 
 
 class FrameInfo(C.Structure):
@@ -98,9 +98,9 @@ def _p(a):
 
 class Session:
     def __init__(self, width, height, fps=30, bitrate=4_000_000, gop=30, const_qp=-1, num_slices=1, search_range=16,
-                 input_format=FMT_I420, device=-1, level_idc=0, debug=0, auto_batch=0):
+                 input_format=FMT_I420, device=-1, level_idc=0, debug=0, auto_batch=0, scene_change=1):
         L = lib()
-        self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug, auto_batch)
+        self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug, scene_change, auto_batch)
         self.h = C.c_void_p()
         check(L.b200enc_create(C.byref(self.cfg), C.byref(self.h)), "b200enc_create")
         self.width, self.height = width, height

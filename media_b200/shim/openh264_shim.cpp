@@ -49,6 +49,7 @@ public:
         cfg_.const_qp = p->rc_mode == kRcOff ? (l.dlayer_qp >= 0 && l.dlayer_qp <= 51 ? l.dlayer_qp : 26) : -1;
         if (cfg_.const_qp < 0 && cfg_.bitrate <= 0) cfg_.bitrate = 1000000;
         cfg_.num_slices = l.slice.mode == kSliceFixedNum && l.slice.num > 0 ? (int)l.slice.num : 1;
+        cfg_.scene_change = p->scene_change_detect ? 1 : 0;                       // bEnableSceneChangeDetect (the wrapper sets it, :283)
         cfg_.auto_batch = 1;
         // entropy_mode = 1 (CABAC, requested by the wrapper at :291) and profile main/high are accepted: the stream is Constrained Baseline / CAVLC
         return create();

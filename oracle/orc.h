@@ -62,12 +62,15 @@ typedef struct {
     int fps;
     int no_i4x4;             /* 1: Intra_16x16 only (quality A/B runs in tests; the product has no such switch) */
     int no_p8x8;             /* 1: P_L0_16x16 only (same purpose) */
+    int no_scene_change;     /* 1: never turn a P frame into an IDR (b200enc_config.scene_change = 0) */
 } OrcConfig;
 
 OrcEncoder *orc_create(const OrcConfig *cfg);
 void orc_destroy(OrcEncoder *e);
 /* Encode one frame. frame_type: 1 = IDR (SPS+PPS prepended), 0 = P. Returns bytes written or <0. */
 int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap);
+/* 1 when the last frame was coded as an IDR (requested, first frame, or scene change), else 0 */
+int orc_last_frame_was_idr(const OrcEncoder *e);
 /* Reconstruction of the last encoded frame (after deblocking), cropped to width x height I420. */
 void orc_get_recon(const OrcEncoder *e, uint8_t *i420);
 /* Stage dumps of the last frame for stage-by-stage parity with the CUDA path. */

@@ -32,7 +32,7 @@ struct OrcEncoder {
     int32_t *inter_cost;
     uint8_t *pred_y, *pred_c;        /* per-MB inter prediction: 256 luma, 2*64 chroma */
     int *slice_row0;                 /* num_slices+1 entries */
-    int frame_num, idr_pic_id, have_ref;
+    int frame_num, idr_pic_id, have_ref, last_idr;
     uint8_t *rbsp; int rbsp_cap;
 };
 
@@ -83,6 +83,7 @@ void orc_destroy(OrcEncoder *e)
     free(e->inter_cost); free(e->pred_y); free(e->pred_c); free(e->slice_row0); free(e->rbsp); free(e);
 }
 
+int orc_last_frame_was_idr(const OrcEncoder *e) { return e->last_idr; }
 const OrcMbInfo *orc_mb_info(const OrcEncoder *e) { return e->mbi; }
 const OrcMbCoef *orc_mb_coef(const OrcEncoder *e) { return e->coef; }
 int orc_mb_count(const OrcEncoder *e) { return e->mbw * e->mbh; }
@@ -814,6 +815,15 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
                 int ie = intra_estimate(e, mx, my);
                 if (ie + lambda * ORC_INTRA_BIAS_BITS < e->inter_cost[mb]) { memset(&e->mbi[mb], 0, sizeof(OrcMbInfo)); e->mbi[mb].mb_type = ORC_MB_I16x16; }
             }
+        /* Scene change (the wrapper enables openh264's detector, VideoEncoderOpenH264.cpp:283): when at least 2/5 of the MBs came out
+         * intra from the motion search, the picture is coded as an IDR instead */
+        int n_intra = 0;
+        for (int i = 0; i < n; i++) n_intra += e->mbi[i].mb_type == ORC_MB_I16x16;
+        if (!e->cfg.no_scene_change && 5 * n_intra >= 2 * n) {
+            is_idr = 1; e->frame_num = 0;
+            memset(e->mbi, 0, (size_t)n * sizeof(OrcMbInfo));
+            for (int i = 0; i < n; i++) e->mbi[i].mb_type = ORC_MB_I16x16;
+        } else
         /* Phase B */
         for (int my = 0; my < e->mbh; my++)
             for (int mx = 0; mx < e->mbw; mx++)
@@ -866,7 +876,7 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
     }
     /* the deblocked picture becomes the reference of the next frame */
     for (int c = 0; c < 3; c++) memcpy(e->ref[c], e->dbk[c], (size_t)(c ? e->wc / 2 * e->hc / 2 : e->wc * e->hc));
-    e->have_ref = 1; e->frame_num = (e->frame_num + 1) & 255;
+    e->have_ref = 1; e->frame_num = (e->frame_num + 1) & 255; e->last_idr = is_idr;
     if (is_idr) e->idr_pic_id = (e->idr_pic_id + 1) & 1;
     return o;
 }

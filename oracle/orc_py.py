@@ -22,7 +22,7 @@ def build(force=False):
 
 class OrcConfig(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("num_slices", C.c_int),
-                ("search_range", C.c_int), ("level_idc", C.c_int), ("fps", C.c_int), ("no_i4x4", C.c_int), ("no_p8x8", C.c_int)]
+                ("search_range", C.c_int), ("level_idc", C.c_int), ("fps", C.c_int), ("no_i4x4", C.c_int), ("no_p8x8", C.c_int), ("no_scene_change", C.c_int)]
 
 
 MBINFO_DTYPE = np.dtype([("mb_type", "u1"), ("i16_mode", "u1"), ("chroma_mode", "u1"), ("cbp", "u1"),
@@ -43,6 +43,7 @@ def lib():
         L.orc_destroy.argtypes = [vp]
         L.orc_encode.restype = C.c_int; L.orc_encode.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int]
         L.orc_get_recon.argtypes = [vp, vp]
+        L.orc_last_frame_was_idr.restype = C.c_int; L.orc_last_frame_was_idr.argtypes = [vp]
         L.orc_mb_info.restype = vp; L.orc_mb_info.argtypes = [vp]
         L.orc_mb_coef.restype = vp; L.orc_mb_coef.argtypes = [vp]
         L.orc_mb_count.restype = C.c_int; L.orc_mb_count.argtypes = [vp]
@@ -78,9 +79,9 @@ def _p(a):
 class Encoder:
     """One oracle session: encode(i420, idr, qp) -> Annex-B bytes; stage dumps as numpy arrays."""
 
-    def __init__(self, width, height, num_slices=1, search_range=16, fps=30, level_idc=0, no_i4x4=0, no_p8x8=0):
+    def __init__(self, width, height, num_slices=1, search_range=16, fps=30, level_idc=0, no_i4x4=0, no_p8x8=0, scene_change=1):
         self.L = lib()
-        self.cfg = OrcConfig(width, height, num_slices, search_range, level_idc, fps, no_i4x4, no_p8x8)
+        self.cfg = OrcConfig(width, height, num_slices, search_range, level_idc, fps, no_i4x4, no_p8x8, 0 if scene_change else 1)
         self.h = self.L.orc_create(C.byref(self.cfg))
         self.width, self.height = width, height
         self.mbw, self.mbh = (width + 15) // 16, (height + 15) // 16
@@ -100,6 +101,9 @@ class Encoder:
         if n < 0:
             raise RuntimeError("orc_encode failed")
         return self._out[:n].tobytes()
+
+    def last_was_idr(self):
+        return bool(self.L.orc_last_frame_was_idr(self.h))
 
     def recon(self):
         out = np.zeros(self.width * self.height * 3 // 2, np.uint8)

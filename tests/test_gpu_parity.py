@@ -31,7 +31,7 @@ def test_encode_matches_golden(enc, case):
         assert len(bs) == case["au_bytes"][t]
         assert hashlib.sha256(bs).hexdigest() == case["au_sha256"][t], f"frame {t} bitstream"
         assert hashlib.sha256(g.recon().tobytes()).hexdigest() == case["recon_sha256"][t], f"frame {t} reconstruction"
-        assert info.frame_type == (1 if t == 0 else 0) and info.qp == case["qp"]
+        assert info.frame_type == (1 if bs[4] == 0x67 else 0) and (t > 0 or info.frame_type == 1) and info.qp == case["qp"]   # noise content: scene-change IDRs
     g.close()
 
 
@@ -411,4 +411,23 @@ def test_random_geometries_and_qps_match_the_oracle(enc, orc):
             bs, _ = g.encode(f); ref = o.encode(f, t == 0, qp)
             assert bs == ref, f"trial {trial}: {w}x{h} qp {qp} slices {slices} sr {sr} content {kind} frame {t}: bitstream"
             assert np.array_equal(g.recon(), o.recon()), f"trial {trial} frame {t}: reconstruction"
+        g.close()
+
+
+def test_scene_change_idr_matches_the_oracle(enc, orc):
+    """a cut to unrelated content: the device turns the P picture into an IDR (k_scene_change), the host follows (frame type,
+    frame_num, GOP counter), bit-exact with the oracle; scene_change = 0 keeps it a P picture"""
+    w, h = 256, 160
+    a, b = Content("A", w, h, seed=1), Content("A", w, h, seed=99)
+    frames = [a.frame(0), a.frame(1), b.frame(2), b.frame(3), b.frame(4)]
+    for detect in (1, 0):
+        g = enc.Session(w, h, const_qp=28, gop=1000, device=0, scene_change=detect)
+        o = orc.Encoder(w, h, scene_change=detect)
+        types = []
+        for t, f in enumerate(frames):
+            bs, info = g.encode(f); ref = o.encode(f, t == 0, 28)
+            assert bs == ref and np.array_equal(g.recon(), o.recon()), (detect, t)
+            assert info.frame_type == int(o.last_was_idr())
+            types.append(info.frame_type)
+        assert types == ([1, 0, 1, 0, 0] if detect else [1, 0, 0, 0, 0])
         g.close()

@@ -292,3 +292,21 @@ def test_downstream_consumer_finds_the_parameter_sets(orc):
     assert consumer_header_scan(p) == (False, False, 0, 1)
     case = next(c for c in GOLDEN if "stream_hex" in c)
     assert consumer_header_scan(bytes.fromhex(case["stream_hex"][0]))[:2] == (True, True)
+
+
+@needs_decoder
+def test_scene_change_turns_a_p_frame_into_an_idr(orc):
+    """a cut to unrelated content makes >= 2/5 of the macroblocks intra after the motion search: the picture is coded as an IDR
+    (SPS + PPS in front, frame_num restarts) and the stream stays decodable; with the detector off it remains a P picture"""
+    w, h = 256, 160
+    a, b = Content("A", w, h, seed=1), Content("A", w, h, seed=99)
+    for detect in (1, 0):
+        e = orc.Encoder(w, h, scene_change=detect)
+        frames = [a.frame(0), a.frame(1), b.frame(2), b.frame(3)]
+        aus, recs, kinds = [], [], []
+        for t, f in enumerate(frames):
+            aus.append(e.encode(f, t == 0, 28)); recs.append(e.recon()); kinds.append(e.last_was_idr())
+        assert kinds == ([True, False, True, False] if detect else [True, False, False, False])
+        assert (aus[2][4] == 0x67) == bool(detect)
+        dec = avdec.decode_stream(aus)
+        assert len(dec) == 4 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
