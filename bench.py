@@ -116,6 +116,12 @@ def run_b200(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if use_dist else 0
+    try:        # keep this rank's caller threads and its pinned frame pool on the NUMA node of its GPU (8 ranks share a two-socket host)
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(dev))
+    except Exception:
+        pass
     S = args.sessions
     L = enc.lib()
     pool = make_pool()
