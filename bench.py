@@ -28,6 +28,8 @@ FMT, SLICES, SR, CQP, KIND, LABEL = 0, 1, 16, -1, "A", "Baseline CAVLC IPPP, CBR
 # Secondary workloads (BASELINE.json configs 2-4); the default, and what the driver runs, is the 1080p session workload above.
 WORKLOADS = {
     "1080p": {},
+    "portrait720": dict(W=720, H=1280, CQP=26, sessions=1, groups=1, METRIC="720x1280 H.264 encode frames/s per GPU",
+                        LABEL="ONE 720x1280 portrait stream (config 1): Baseline CAVLC, const QP 26, gop 300, search +-16, 1 slice, content A; latency-bound by construction"),
     "single": dict(sessions=1, groups=1, LABEL="ONE 1080p stream (config 2): Baseline CAVLC IPPP, CBR 4 Mbps @30fps, gop 300, search +-16, 1 slice, content A; latency-bound by construction"),
     "rgba720": dict(W=1280, H=720, FMT=2, KIND="B", sessions=64, groups=2, BITRATE=2_000_000, METRIC="720p RGBA->I420 + H.264 encode frames/s per GPU",
                     LABEL="RGBA8888 cloud-phone framebuffers (config 3), on-GPU RGBA->I420 + encode, Baseline CAVLC IPPP, CBR 2 Mbps @30fps each, gop 300, search +-16, content B (screen-like)"),

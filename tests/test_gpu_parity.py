@@ -431,3 +431,24 @@ def test_scene_change_idr_matches_the_oracle(enc, orc):
             types.append(info.frame_type)
         assert types == ([1, 0, 1, 0, 0] if detect else [1, 0, 0, 0, 0])
         g.close()
+
+
+def test_config1_portrait_720x1280_60_frames_const_qp26(enc, orc):
+    """BASELINE.json configs[0]: 720x1280 portrait I420, 60 frames, Baseline CAVLC, const QP 26 -- the CUDA stream decodes to the
+    encoder's reconstruction over all 60 frames and is bit-exact with the oracle on the first 6"""
+    w, h, qp = 720, 1280, 26
+    g = enc.Session(w, h, const_qp=qp, gop=1000, device=0)
+    o = orc.Encoder(w, h)
+    c = Content("A", w, h)
+    aus, recs = [], []
+    for t in range(60):
+        f = c.frame(t)
+        bs, info = g.encode(f); aus.append(bs); recs.append(g.recon())
+        if t < 6:
+            assert bs == o.encode(f, t == 0, qp), f"frame {t}"
+        assert info.qp == qp and info.frame_type == (1 if t == 0 else 0)
+    if avdec.available():
+        dec = avdec.decode_stream(aus)
+        assert len(dec) == 60 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+    assert psnr(c.frame(59)[:w * h], recs[59][:w * h]) > 36
+    g.close()
