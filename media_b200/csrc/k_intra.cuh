@@ -13,6 +13,12 @@
 namespace b200 {
 
 #define WAVE_WARPS 4
+#ifdef INTRA_TIMING
+__device__ long long g_intra_t[8];
+#define INTRA_T(i) do { if (lane == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long *)&g_intra_t[i], (unsigned long long)(t_ - it_last)); it_last = t_; } } while (0)
+#else
+#define INTRA_T(i) do { } while (0)
+#endif
 #define WAVE_TIMEOUT_NS 2000000000ull   /* watchdog: a wait longer than 2 s is an internal error, never a hang */
 
 
@@ -127,8 +133,15 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
     const uint32_t WX = fj == 0 ? 0x01010101u : fj == 1 ? 0xFEFF0102u : fj == 2 ? 0x01FFFF01u : 0xFF02FE01u;
     const int wy0 = fi == 1 ? 2 : 1, wy1 = fi == 0 ? 1 : fi == 1 ? 1 : fi == 2 ? -1 : -2, wy2 = fi == 0 ? 1 : fi == 1 ? -1 : fi == 2 ? -1 : 2, wy3 = fi == 0 ? 1 : fi == 1 ? -2 : fi == 2 ? 1 : -1;
     const int qcl = pos_class(zpos), qmf = qcl == 0 ? q.mf[0] : qcl == 1 ? q.mf[1] : q.mf[2], qv = qcl == 0 ? q.v[0] : qcl == 1 ? q.v[1] : q.v[2];
+    // edge gather offsets of this lane relative to the block origin (lanes 0-4: L3 L3 L2 L1 L0, 5: corner, 6-14: T0..T7 T7;
+    // without a top-right neighbour T4..T7 repeat T3)
+    const int rel_tr = lane <= 4 ? (lane == 0 ? 4 : 5 - lane) * 24 + 3 : lane == 5 ? 3 : 4 + min(lane - 6, 7);
+    const int rel_notr = lane <= 5 ? rel_tr : 4 + min(lane - 6, 3);
     int total = lambda * I4_BIAS_BITS;
     cbp_luma = 0; modes = 0ull;
+#ifdef INTRA_TIMING
+    long long it_last = clock64();
+#endif
 #pragma unroll 1
     for (int b = 0; b < 16; b++) {
         const int bxb = blk_x(b), byb = blk_y(b), bx = bxb * 4, by = byb * 4;
@@ -136,13 +149,7 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
         const bool aTR = byb == 0 ? (bxb < 3 ? top : topright) : !((0xA888u >> b) & 1u);
         // filtered edge of this block
         int e = 128;
-        if (lane < 15) {
-            int off;
-            if (lane <= 4) off = (by + (lane == 0 ? 4 : 5 - lane)) * 24 + 3 + bx;
-            else if (lane == 5) off = by * 24 + 3 + bx;
-            else { int t = min(lane - 6, 7); if (!aTR) t = min(t, 3); off = by * 24 + 4 + bx + t; }
-            e = nb[off];
-        }
+        if (lane < 15) e = nb[by * 24 + bx + (aTR ? rel_tr : rel_notr)];
         const int e1 = __shfl_down_sync(0xffffffffu, e, 1), e2 = __shfl_down_sync(0xffffffffu, e, 2);
         if (lane < 15) sm.F[lane] = (uint8_t)e;
         if (lane < 14) sm.F[16 + lane] = (uint8_t)((e + e1 + 1) >> 1);
@@ -154,6 +161,7 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
             if (lane == 15) sm.F[47] = (uint8_t)dc;
         }
         __syncwarp();
+        INTRA_T(4);
         const int ma = sm.mg[(byb + 1) * 5 + bxb], mb_ = sm.mg[byb * 5 + bxb + 1];
         const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
         uint32_t P[4], S[4];
@@ -180,6 +188,7 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
         if (total >= limit) return false;
 #pragma unroll
         for (int y = 0; y < 4; y++) P[y] = __shfl_sync(0xffffffffu, P[y], wm);
+        INTRA_T(5);
         // transform, quantise, reconstruct, spread over 16 lanes (lanes 16-31 mirror them): lane l owns the coefficient at
         // zig-zag index l for the forward transform + quantiser (its value is one IDP.4A per row against the lane's horizontal
         // basis, then four multiply-adds with its vertical basis), and the sample (y,x) = (l>>2, l&3) for the inverse transform
@@ -216,6 +225,7 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
         if (nzm) cbp_luma |= 1 << (b >> 2);
         modes |= (unsigned long long)wm << (4 * b);
         __syncwarp();
+        INTRA_T(6);
     }
     // the reconstruction of the whole MB goes out at once: 16 rows x 4 words
 #pragma unroll
@@ -247,41 +257,57 @@ __device__ void intra_code_mb(const IntraCtx &s, const Geom &g, IntraSmem &sm, i
 {
     const int wc = g.wc, cw = wc / 2, mb = my * g.mbw + mx, qp = s.qp;
     const bool top = !row_is_slice_top(g, my), left = mx > 0;
-    // neighbours from the (pre-deblock) reconstruction; written by other warps / kernels -> L2 loads
-    __syncwarp();
-    for (int i = lane; i < 21 + 16 + 2 * (9 + 8); i += 32) {
-        int comp, idx, is_top;
-        if (i < 37) { comp = 0; is_top = i < 21; idx = is_top ? i : i - 21; }
-        else { int j = i - 37; comp = 1 + j / 17; j %= 17; is_top = j < 9; idx = is_top ? j : j - 9; }
-        const int n = comp ? 8 : 16, st = comp ? cw : wc, px0 = mx * n, py0 = my * n;
-        const uint8_t *r = s.rec(comp);
-        if (is_top) {     // idx 0 = corner, 1..n = row above
-            int v = 0;
-            if (top && (idx > 0 || left) && (idx <= n || mx + 1 < g.mbw)) v = __ldcg(r + (size_t)(py0 - 1) * st + px0 + idx - 1);
-            sm.top[comp][idx] = (uint8_t)v;
-            if (idx == 0) sm.left[comp][0] = (uint8_t)v;
-        } else {
-            sm.left[comp][idx + 1] = left ? __ldcg(r + (size_t)(py0 + idx) * st + px0 - 1) : 0;
-        }
-    }
-    __syncwarp();
+#ifdef INTRA_TIMING
+    long long it_last = clock64();
+#endif
+    // source block of this lane and the neighbours from the (pre-deblock) reconstruction (written by other warps / kernels ->
+    // L2 loads): all global loads of the MB are issued back to back, then consumed
     const bool is_luma = lane < 16, active = lane < 24;
     const int comp = is_luma ? 0 : (lane < 20 ? 1 : 2);
     const int cb = lane & 3, b = lane & 15;
     const int bx = is_luma ? blk_x(b) * 4 : (cb & 1) * 4, by = is_luma ? blk_y(b) * 4 : (cb >> 1) * 4;
     const int n = is_luma ? 16 : 8, half = n / 2, st = is_luma ? wc : cw;
-    const uint8_t *T = sm.top[comp] + 1, *L = sm.left[comp] + 1;
-    // source block
-    int sp[16];
+    uint32_t spw[4];
     {
         const uint8_t *spx = s.src(comp) + (size_t)(my * n + by) * st + mx * n + bx;
 #pragma unroll
-        for (int y = 0; y < 4; y++) {
-            uint32_t w = *reinterpret_cast<const uint32_t *>(spx + (size_t)y * st);
+        for (int y = 0; y < 4; y++) spw[y] = *reinterpret_cast<const uint32_t *>(spx + (size_t)y * st);
+    }
+    __syncwarp();
+    int nbv[3];
 #pragma unroll
-            for (int x = 0; x < 4; x++) sp[y * 4 + x] = (w >> (8 * x)) & 255;
+    for (int k = 0; k < 3; k++) {
+        const int i = lane + 32 * k;
+        int ncomp, idx, is_top;
+        if (i < 37) { ncomp = 0; is_top = i < 21; idx = is_top ? i : i - 21; }
+        else { int j = i - 37; ncomp = 1 + j / 17; j %= 17; is_top = j < 9; idx = is_top ? j : j - 9; }
+        const int nn = ncomp ? 8 : 16, nst = ncomp ? cw : wc, px0 = mx * nn, py0 = my * nn;
+        const uint8_t *r = s.rec(ncomp);
+        int v = 0;
+        if (i < 21 + 16 + 2 * (9 + 8)) {
+            if (is_top) { if (top && (idx > 0 || left) && (idx <= nn || mx + 1 < g.mbw)) v = __ldcg(r + (size_t)(py0 - 1) * nst + px0 + idx - 1); }
+            else if (left) v = __ldcg(r + (size_t)(py0 + idx) * nst + px0 - 1);
+        }
+        nbv[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int i = lane + 32 * k;
+        int ncomp, idx, is_top;
+        if (i < 37) { ncomp = 0; is_top = i < 21; idx = is_top ? i : i - 21; }
+        else { int j = i - 37; ncomp = 1 + j / 17; j %= 17; is_top = j < 9; idx = is_top ? j : j - 9; }
+        if (i < 21 + 16 + 2 * (9 + 8)) {
+            if (is_top) { sm.top[ncomp][idx] = (uint8_t)nbv[k]; if (idx == 0) sm.left[ncomp][0] = (uint8_t)nbv[k]; }
+            else sm.left[ncomp][idx + 1] = (uint8_t)nbv[k];
         }
     }
+    __syncwarp();
+    const uint8_t *T = sm.top[comp] + 1, *L = sm.left[comp] + 1;
+    int sp[16];
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+#pragma unroll
+        for (int x = 0; x < 4; x++) sp[y * 4 + x] = (spw[y] >> (8 * x)) & 255;
     // DC value and plane parameters of this lane's component
     int dcv, pa, pb, pc;
     {
@@ -298,6 +324,7 @@ __device__ void intra_code_mb(const IntraCtx &s, const Geom &g, IntraSmem &sm, i
         pa = 16 * (L[n - 1] + T[n - 1]); pb = (coef * H + 32) >> 6; pc = (coef * V + 32) >> 6;
     }
     const int off = half - 1;
+    INTRA_T(0);
     // mode decision: key = (SATD << 2) | mode id; luma ids V0 H1 DC2 P3, chroma ids DC0 H1 V2 P3
     uint32_t best = 0xffffffffu;
 #pragma unroll 1
@@ -316,11 +343,13 @@ __device__ void intra_code_mb(const IntraCtx &s, const Geom &g, IntraSmem &sm, i
     const int chroma_mode = __shfl_sync(0xffffffffu, mode_id, 16);
     // Intra_4x4 on trial against the Intra_16x16 SATD
     int cbp_luma4 = 0; unsigned long long modes4 = 0ull;
+    INTRA_T(1);
     const bool use_i4 = intra_try_i4x4(s, g, sm, mx, my, lane, (int)(__shfl_sync(0xffffffffu, best, 0) >> 2), top, left, cbp_luma4, modes4);
 
     int p[16], c[16]; intra_pred_block(kind, T, L, bx, by, dcv, pa, pb, pc, off, p);
 #pragma unroll
     for (int k = 0; k < 16; k++) c[k] = sp[k] - p[k];
+    INTRA_T(2);
     fdct4x4(c);
     MbCoef *co = s.coef + mb; MbInfo *mi = s.mbi + mb;
     int nnz = 0; bool dc_nz = false;
@@ -377,6 +406,10 @@ __device__ void intra_code_mb(const IntraCtx &s, const Geom &g, IntraSmem &sm, i
         }
         mi->nnz[lane] = (uint8_t)nnz;
     }
+    INTRA_T(3);
+#ifdef INTRA_TIMING
+    if (lane == 0) atomicAdd((unsigned long long *)&g_intra_t[7], 1ull);
+#endif
     const uint32_t nzmask = __ballot_sync(0xffffffffu, nnz != 0), dcmask = __ballot_sync(0xffffffffu, dc_nz);
     if (lane == 0) {
         int cbp = use_i4 ? cbp_luma4 : ((nzmask & 0xffff) ? 15 : 0);

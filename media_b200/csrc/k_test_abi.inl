@@ -140,3 +140,12 @@ int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz)
 }
 
 } // extern "C"
+
+#ifdef INTRA_TIMING
+extern "C" int b200k_intra_timing(long long *out8, int reset)
+{
+    if (cudaMemcpyFromSymbol(out8, b200::g_intra_t, sizeof(long long) * 8) != cudaSuccess) return -1;
+    if (reset) { long long z[8] = { 0 }; cudaMemcpyToSymbol(b200::g_intra_t, z, sizeof z); }
+    return 0;
+}
+#endif
