@@ -147,6 +147,22 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
         const int bxb = blk_x(b), byb = blk_y(b), bx = bxb * 4, by = byb * 4;
         const bool aT = byb > 0 || top, aL = bxb > 0 || left, aX = aT && aL;
         const bool aTR = byb == 0 ? (bxb < 3 ? top : topright) : !((0xA888u >> b) & 1u);
+        // work that does not depend on the previous block's reconstruction first: source rows, their horizontal Hadamard
+        // transforms, the predicted mode and this lane's cost terms
+        uint32_t S[4]; int Ts[16];
+        {
+            const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+                S[y] = sm.srcw[(by + y) * 4 + bxb];
+#pragma unroll
+                for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(S[y], H[k], 0);
+            }
+        }
+        const int ma = sm.mg[(byb + 1) * 5 + bxb], mb_ = sm.mg[byb * 5 + bxb + 1];
+        const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
+        const bool ok = lane < 9 && (lane == 2 || ((lane == 0 || lane == 3 || lane == 7) ? aT : (lane == 1 || lane == 8) ? aL : aX));
+        const int mode_cost = lambda * (lane == pm ? 1 : 4);
         // filtered edge of this block
         int e = 128;
         if (lane < 15) e = nb[by * 24 + bx + (aTR ? rel_tr : rel_notr)];
@@ -162,25 +178,14 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
         }
         __syncwarp();
         INTRA_T(4);
-        const int ma = sm.mg[(byb + 1) * 5 + bxb], mb_ = sm.mg[byb * 5 + bxb + 1];
-        const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
-        uint32_t P[4], S[4];
+        uint32_t P[4];
 #pragma unroll
-        for (int y = 0; y < 4; y++) {
-            S[y] = sm.srcw[(by + y) * 4 + bxb];
+        for (int y = 0; y < 4; y++)
             P[y] = (uint32_t)sm.F[ix[y] & 255] | ((uint32_t)sm.F[(ix[y] >> 8) & 255] << 8) | ((uint32_t)sm.F[(ix[y] >> 16) & 255] << 16) | ((uint32_t)sm.F[ix[y] >> 24] << 24);
-        }
         uint32_t key = 0xffffffffu;
         {
-            const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
-            int Ts[16];
-#pragma unroll
-            for (int y = 0; y < 4; y++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(S[y], H[k], 0);
             const int sat = satd_rows(P, Ts);
-            const bool ok = lane < 9 && (lane == 2 || ((lane == 0 || lane == 3 || lane == 7) ? aT : (lane == 1 || lane == 8) ? aL : aX));
-            if (ok) key = ((uint32_t)(sat + lambda * (lane == pm ? 1 : 4)) << 4) | (uint32_t)lane;
+            if (ok) key = ((uint32_t)(sat + mode_cost) << 4) | (uint32_t)lane;
         }
         key = warp_min(key);
         const int wm = key & 15;
