@@ -293,7 +293,9 @@ def run_b200(args):
             "config": {"workload": f"{S} concurrent {W}x{H} sessions per GPU, {LABEL}; step = one frame of every session; {G} batch(es) of {group_sizes[0]} on own streams",
                        "sessions_per_gpu": S, "frames_per_step": S * world, "l2_policy": (f"inputs larger than L2: per-step working set ~{S * npx * 10 // 1000000} MB" if S * npx * 10 > 130e6 else
                                      f"working set ~{S * npx * 10 // 1000000} MB fits L2; every step encodes a different frame of the pool, reference planes are rewritten each step"),
-                       "parallelism": f"sessions sharded over {world} GPU(s), no collective"},
+                       "parallelism": f"sessions sharded over {world} GPU(s), no collective",
+                       "timing": "value/ms_per_step: host clock between a device synchronize + barrier on both sides (max over ranks; an upper bound of the device time of "
+                                 "the overlapping batch streams); device_ms_per_step: CUDA events on the batch streams (slowest batch group); kernel_ms: CUDA events per launch"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": world * S * fb, "d2h_bytes_per_step": int(world * out_bytes_e / args.steps),
                     "ms_per_step": round(el_e / args.steps * 1e3, 4)},
             "gpu_launches": launches,
