@@ -52,6 +52,22 @@ typedef struct {
     uint8_t  nnz[24];        /* total_coeff: 0..15 luma blkIdx, 16..19 Cb, 20..23 Cr (AC count for I16x16/chroma) */
 } OrcMbInfo;
 
+/* Per-MB side record of the CABAC back end (shared layout with the CUDA path): what context selection needs from a neighbour
+ * beyond OrcMbInfo. 20 bytes. */
+typedef struct {
+    union {
+        int16_t mvd[4][2];   /* inter MBs: mvd_l0 of each 8x8 partition (replicated for P_L0_16x16; 0 for P_Skip) */
+        uint8_t i4_syn[16];  /* Intra_4x4: 8 = prev_intra4x4_pred_mode_flag set, else rem_intra4x4_pred_mode 0..7 */
+    };
+    uint8_t dc_cbf;          /* coded_block_flag of the DC blocks: bit 0 Intra16x16DCLevel, bit 1 Cb DC, bit 2 Cr DC */
+    uint8_t pad[3];
+} OrcMbSide;
+/* bin-list entry (16 bits): regular bins ctxIdx | bin << 10 | (repeat - 1) << 11 (repeat consecutive equal bins of one context,
+ * used for the unary prefixes); ctxIdx 276 = terminate bin; ctxIdx ORC_CTX_BYPASS0 + n (n = 1..6) = n bypass bins held in
+ * bits 10..10+n-1, the first one most significant */
+#define ORC_CTX_BYPASS0 0x3F8
+#define ORC_CABAC_NCTX 460
+
 typedef struct OrcEncoder OrcEncoder;
 
 typedef struct {
@@ -63,6 +79,8 @@ typedef struct {
     int no_i4x4;             /* 1: Intra_16x16 only (quality A/B runs in tests; the product has no such switch) */
     int no_p8x8;             /* 1: P_L0_16x16 only (same purpose) */
     int no_scene_change;     /* 1: never turn a P frame into an IDR (b200enc_config.scene_change = 0) */
+    int profile;             /* 0 Constrained Baseline / CAVLC; 1 Main / CABAC; 2 High / CABAC (4x4 transform only), the wrapper's
+                                persist.vmi.video.encode.profile values (VideoEncoderOpenH264.cpp:248-253) */
 } OrcConfig;
 
 OrcEncoder *orc_create(const OrcConfig *cfg);
@@ -88,9 +106,15 @@ int orc_dbg_qpel(const OrcEncoder *e, int xq, int yq);
 /* (re)build the half-pel planes from the current reference picture; orc_encode does this itself for P frames */
 void orc_dbg_build_halfpel(OrcEncoder *e);
 
+/* CABAC stage dumps of the last frame: side records, and the bin list of slice s (returns the count) */
+const OrcMbSide *orc_mb_side(const OrcEncoder *e);
+int orc_slice_bins(const OrcEncoder *e, int s, const uint16_t **bins);
+/* codes a bin list (ending with a terminate bin of value 1) into bytes; returns the length */
+int orc_cabac_code_bins(const uint16_t *bins, int n, int slice_qp, int is_p, uint8_t *out, int cap);
+
 /* ---- headers ---- */
-int orc_write_sps(uint8_t *out, int width, int height, int level_idc);
-int orc_write_pps(uint8_t *out);
+int orc_write_sps(uint8_t *out, int width, int height, int level_idc, int profile);
+int orc_write_pps(uint8_t *out, int profile);
 int orc_level_for(int width, int height, int fps);
 
 /* ---- kernel-level oracles (bit-exact targets of the per-kernel C-ABI entry points) ---- */

@@ -64,14 +64,20 @@ static int finish_nal(uint8_t *out, int nal_hdr, const uint8_t *rbsp, int n)
     return 5 + orc_escape_rbsp(rbsp, n, out + 5);
 }
 
-int orc_write_sps(uint8_t *out, int width, int height, int level_idc)
+int orc_write_sps(uint8_t *out, int width, int height, int level_idc, int profile)
 {
     uint8_t tmp[64]; BitWriter b; bw_init(&b, tmp, sizeof tmp);
     int mbw = (width + 15) / 16, mbh = (height + 15) / 16;
-    bw_put(&b, 8, 66);            /* profile_idc: Baseline */
-    bw_put(&b, 8, 0xC0);          /* constraint_set0/1 = 1 (constrained baseline) */
+    bw_put(&b, 8, profile == 2 ? 100 : profile == 1 ? 77 : 66);   /* profile_idc: High / Main / Baseline */
+    bw_put(&b, 8, profile == 2 ? 0 : profile == 1 ? 0x40 : 0xC0); /* constraint_set1 (Main-conformant); Baseline: set0/1 = constrained baseline */
     bw_put(&b, 8, (uint32_t)level_idc);
     bw_ue(&b, 0);                 /* seq_parameter_set_id */
+    if (profile == 2) {           /* 7.3.2.1.1, profile_idc 100 */
+        bw_ue(&b, 1);             /* chroma_format_idc 4:2:0 */
+        bw_ue(&b, 0); bw_ue(&b, 0); /* bit_depth_luma/chroma_minus8 */
+        bw_put(&b, 1, 0);         /* qpprime_y_zero_transform_bypass_flag */
+        bw_put(&b, 1, 0);         /* seq_scaling_matrix_present_flag */
+    }
     bw_ue(&b, 4);                 /* log2_max_frame_num_minus4 -> 8-bit frame_num */
     bw_ue(&b, 2);                 /* pic_order_cnt_type */
     bw_ue(&b, 1);                 /* max_num_ref_frames */
@@ -88,11 +94,11 @@ int orc_write_sps(uint8_t *out, int width, int height, int level_idc)
     return finish_nal(out, 0x67, tmp, b.pos);
 }
 
-int orc_write_pps(uint8_t *out)
+int orc_write_pps(uint8_t *out, int profile)
 {
     uint8_t tmp[32]; BitWriter b; bw_init(&b, tmp, sizeof tmp);
     bw_ue(&b, 0); bw_ue(&b, 0);   /* pps id, sps id */
-    bw_put(&b, 1, 0);             /* entropy_coding_mode_flag: CAVLC */
+    bw_put(&b, 1, profile ? 1 : 0); /* entropy_coding_mode_flag: CAVLC / CABAC */
     bw_put(&b, 1, 0);             /* bottom_field_pic_order_in_frame_present_flag */
     bw_ue(&b, 0);                 /* num_slice_groups_minus1 */
     bw_ue(&b, 0); bw_ue(&b, 0);   /* num_ref_idx_l0/l1_default_active_minus1 */
@@ -108,7 +114,7 @@ int orc_write_pps(uint8_t *out)
     return finish_nal(out, 0x68, tmp, b.pos);
 }
 
-void orc_write_slice_header(BitWriter *b, int first_mb, int is_idr, int frame_num, int idr_pic_id, int qp)
+void orc_write_slice_header(BitWriter *b, int first_mb, int is_idr, int frame_num, int idr_pic_id, int qp, int cabac)
 {
     bw_ue(b, (uint32_t)first_mb);
     bw_ue(b, is_idr ? 7 : 5);     /* slice_type: I(7) / P(5), "all slices of this picture" */
@@ -121,6 +127,7 @@ void orc_write_slice_header(BitWriter *b, int first_mb, int is_idr, int frame_nu
     }
     if (is_idr) { bw_put(b, 1, 0); bw_put(b, 1, 0); }   /* no_output_of_prior_pics, long_term_reference */
     else bw_put(b, 1, 0);         /* adaptive_ref_pic_marking_mode_flag */
+    if (cabac && !is_idr) bw_ue(b, 0); /* cabac_init_idc */
     bw_se(b, qp - 26);            /* slice_qp_delta */
     bw_ue(b, 0);                  /* disable_deblocking_filter_idc = 0 (VideoEncoderOpenH264.cpp:295) */
     bw_se(b, 0); bw_se(b, 0);     /* slice_alpha_c0_offset_div2, slice_beta_offset_div2 */

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define ORC_MB_BINS_MAX 4096   /* bound of one MB's bin list: 384 levels of at most 2 + 14 + 27 + 1 bins (|level| <= 2064) is far above real use; checked */
 #define HP_M 4   /* margin of the half-pel planes, see build_halfpel() */
 
 struct OrcEncoder {
@@ -34,6 +35,9 @@ struct OrcEncoder {
     int *slice_row0;                 /* num_slices+1 entries */
     int frame_num, idr_pic_id, have_ref, last_idr;
     uint8_t *rbsp; int rbsp_cap;
+    OrcMbSide *side;                 /* CABAC side records */
+    uint16_t *bins; int bins_cap;    /* CABAC bin lists of the last frame, slice after slice */
+    int *slice_bin0;                 /* num_slices+1 offsets into bins */
 };
 
 static inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -69,6 +73,9 @@ OrcEncoder *orc_create(const OrcConfig *cfg)
       for (int s = 0; s < e->cfg.num_slices; s++) { e->slice_row0[s] = r; r += base + (s < rem); }
       e->slice_row0[e->cfg.num_slices] = r; }
     e->rbsp_cap = n * 1024 + 4096; e->rbsp = malloc(e->rbsp_cap);
+    e->side = calloc(n, sizeof(OrcMbSide));
+    e->bins_cap = n * ORC_MB_BINS_MAX; e->bins = malloc((size_t)e->bins_cap * 2);
+    e->slice_bin0 = calloc(e->cfg.num_slices + 1, sizeof(int));
     return e;
 }
 
@@ -80,7 +87,7 @@ void orc_destroy(OrcEncoder *e)
     free(e->srcL1); free(e->srcL2); free(e->refL1); free(e->refL2);
     free(e->hpb); free(e->hph); free(e->hpj);
     free(e->mbi); free(e->coef); for (int l = 0; l < 3; l++) free(e->me[l]);
-    free(e->inter_cost); free(e->pred_y); free(e->pred_c); free(e->slice_row0); free(e->rbsp); free(e);
+    free(e->inter_cost); free(e->pred_y); free(e->pred_c); free(e->slice_row0); free(e->rbsp); free(e->side); free(e->bins); free(e->slice_bin0); free(e);
 }
 
 int orc_last_frame_was_idr(const OrcEncoder *e) { return e->last_idr; }
@@ -795,6 +802,42 @@ static void write_mb(OrcEncoder *e, BitWriter *b, int mx, int my, int is_p)
         orc_write_residual_block(b, co->chroma_ac[pl][k] + 1, 15, chroma_nc(e, mx, my, pl, k));
 }
 
+/* ---- CABAC side records (mvd per partition, Intra_4x4 mode syntax, DC coded_block_flags): parallel over MBs ---- */
+static void cabac_side_records(OrcEncoder *e, int is_idr)
+{
+    (void)is_idr;
+    for (int my = 0; my < e->mbh; my++)
+        for (int mx = 0; mx < e->mbw; mx++) {
+            int mb = my * e->mbw + mx; const OrcMbInfo *mi = &e->mbi[mb]; const OrcMbCoef *co = &e->coef[mb]; OrcMbSide *sd = &e->side[mb];
+            memset(sd, 0, sizeof *sd);
+            if (mi->mb_type == ORC_MB_P16x16) {
+                int pmx, pmy, sx, sy; predict_mv(e, mx, my, &pmx, &pmy, &sx, &sy);
+                for (int q = 0; q < 4; q++) { sd->mvd[q][0] = (int16_t)(mi->mv[0] - pmx); sd->mvd[q][1] = (int16_t)(mi->mv[1] - pmy); }
+            } else if (mi->mb_type == ORC_MB_P8x8) {
+                for (int q = 0; q < 4; q++) {
+                    int pmx, pmy; predict_mv_part(e, mx, my, q, &pmx, &pmy, 0, 0);
+                    sd->mvd[q][0] = (int16_t)(mi->mv8[q][0] - pmx); sd->mvd[q][1] = (int16_t)(mi->mv8[q][1] - pmy);
+                }
+            } else if (mi->mb_type == ORC_MB_I4x4) {
+                for (int k = 0; k < 16; k++) { int pm = i4_pred_mode(e, mx, my, k), m = mi->i4_mode[k]; sd->i4_syn[k] = (uint8_t)(m == pm ? 8 : m < pm ? m : m - 1); }
+            }
+            if (mi->mb_type == ORC_MB_PSKIP) continue;
+            int dc = 0;
+            if (mi->mb_type == ORC_MB_I16x16) for (int i = 0; i < 16; i++) dc |= co->luma_dc[i] != 0;
+            if (mi->cbp >> 4) for (int p = 0; p < 2; p++) for (int i = 0; i < 4; i++) dc |= (co->chroma_dc[p][i] != 0) << (1 + p);
+            sd->dc_cbf = (uint8_t)dc;
+        }
+}
+const OrcMbSide *orc_mb_side(const OrcEncoder *e) { return e->side; }
+int orc_slice_bins(const OrcEncoder *e, int s, const uint16_t **bins) { *bins = e->bins + e->slice_bin0[s]; return e->slice_bin0[s + 1] - e->slice_bin0[s]; }
+int orc_cabac_code_bins(const uint16_t *bins, int n, int slice_qp, int is_p, uint8_t *out, int cap)
+{
+    BitWriter b; bw_init(&b, out, cap);
+    orc_cabac_code(&b, bins, n, slice_qp, is_p);
+    while (b.nacc) bw_put(&b, 1, 0);
+    return b.overflow ? -1 : b.pos;
+}
+
 int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap)
 {
     int is_idr = frame_type == 1 || !e->have_ref, n = e->mbw * e->mbh, lambda = LAMBDA_TAB[qp];
@@ -853,13 +896,29 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
     if (is_idr) {
         if (out_cap < 64) return -1;
         int level = e->cfg.level_idc ? e->cfg.level_idc : orc_level_for(e->cfg.width, e->cfg.height, e->cfg.fps);
-        o += orc_write_sps(out + o, e->cfg.width, e->cfg.height, level);
-        o += orc_write_pps(out + o);
+        o += orc_write_sps(out + o, e->cfg.width, e->cfg.height, level, e->cfg.profile);
+        o += orc_write_pps(out + o, e->cfg.profile);
     }
+    if (e->cfg.profile) cabac_side_records(e, is_idr);
     for (int s = 0; s < e->cfg.num_slices; s++) {
         BitWriter b; bw_init(&b, e->rbsp, e->rbsp_cap);
         int r0 = e->slice_row0[s], r1 = e->slice_row0[s + 1], run = 0;
-        orc_write_slice_header(&b, r0 * e->mbw, is_idr, e->frame_num, e->idr_pic_id, qp);
+        orc_write_slice_header(&b, r0 * e->mbw, is_idr, e->frame_num, e->idr_pic_id, qp, e->cfg.profile != 0);
+        if (e->cfg.profile) {
+            /* slice_data() with entropy_coding_mode_flag = 1 (7.3.4): cabac_alignment_one_bit, then one arithmetic codeword */
+            while (b.nacc) bw_put(&b, 1, 1);
+            int nb = e->slice_bin0[s];
+            for (int my = r0; my < r1; my++)
+                for (int mx = 0; mx < e->mbw; mx++) {
+                    int k = orc_cabac_mb_bins(e->mbi, e->coef, e->side, e->mbw, mx, my, my > r0, !is_idr, my == r1 - 1 && mx == e->mbw - 1,
+                                              e->bins + nb, e->bins_cap - nb);
+                    if (k > ORC_MB_BINS_MAX || nb + k > e->bins_cap) return -1;
+                    nb += k;
+                }
+            e->slice_bin0[s + 1] = nb;
+            orc_cabac_code(&b, e->bins + e->slice_bin0[s], nb - e->slice_bin0[s], qp, !is_idr);
+            while (b.nacc) bw_put(&b, 1, 0);                   /* the flush wrote the stop bit; rbsp_alignment_zero_bit */
+        } else {
         for (int my = r0; my < r1; my++)
             for (int mx = 0; mx < e->mbw; mx++) {
                 if (!is_idr) {
@@ -870,6 +929,7 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
             }
         if (run) bw_ue(&b, (uint32_t)run);
         bw_trailing(&b);
+        }
         if (b.overflow || o + 5 + b.pos + b.pos / 2 + 16 > out_cap) return -1;
         out[o] = 0; out[o + 1] = 0; out[o + 2] = 0; out[o + 3] = 1; out[o + 4] = is_idr ? 0x65 : 0x61;
         o += 5 + orc_escape_rbsp(e->rbsp, b.pos, out + o + 5);

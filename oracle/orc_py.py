@@ -22,14 +22,15 @@ def build(force=False):
 
 class OrcConfig(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("num_slices", C.c_int),
-                ("search_range", C.c_int), ("level_idc", C.c_int), ("fps", C.c_int), ("no_i4x4", C.c_int), ("no_p8x8", C.c_int), ("no_scene_change", C.c_int)]
+                ("search_range", C.c_int), ("level_idc", C.c_int), ("fps", C.c_int), ("no_i4x4", C.c_int), ("no_p8x8", C.c_int), ("no_scene_change", C.c_int), ("profile", C.c_int)]
 
 
 MBINFO_DTYPE = np.dtype([("mb_type", "u1"), ("i16_mode", "u1"), ("chroma_mode", "u1"), ("cbp", "u1"),
                          ("mv", "<i2", (2,)), ("i4_mode", "u1", (16,)), ("nnz", "u1", (24,))])
 MBCOEF_DTYPE = np.dtype([("luma", "<i2", (16, 16)), ("luma_dc", "<i2", (16,)),
                          ("chroma_dc", "<i2", (2, 4)), ("chroma_ac", "<i2", (2, 4, 16))])
-assert MBINFO_DTYPE.itemsize == 48 and MBCOEF_DTYPE.itemsize == 816
+MBSIDE_DTYPE = np.dtype([("mvd", "<i2", (4, 2)), ("dc_cbf", "u1"), ("pad", "u1", (3,))])     # mvd aliases i4_syn[16] for Intra_4x4 MBs
+assert MBINFO_DTYPE.itemsize == 48 and MBCOEF_DTYPE.itemsize == 816 and MBSIDE_DTYPE.itemsize == 20
 
 _lib = None
 
@@ -52,8 +53,11 @@ def lib():
         L.orc_inter_cost.restype = vp; L.orc_inter_cost.argtypes = [vp]
         L.orc_dbg_qpel.restype = C.c_int; L.orc_dbg_qpel.argtypes = [vp, C.c_int, C.c_int]
         L.orc_dbg_build_halfpel.argtypes = [vp]
-        L.orc_write_sps.restype = C.c_int; L.orc_write_sps.argtypes = [vp, C.c_int, C.c_int, C.c_int]
-        L.orc_write_pps.restype = C.c_int; L.orc_write_pps.argtypes = [vp]
+        L.orc_write_sps.restype = C.c_int; L.orc_write_sps.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_write_pps.restype = C.c_int; L.orc_write_pps.argtypes = [vp, C.c_int]
+        L.orc_mb_side.restype = vp; L.orc_mb_side.argtypes = [vp]
+        L.orc_slice_bins.restype = C.c_int; L.orc_slice_bins.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.orc_cabac_code_bins.restype = C.c_int; L.orc_cabac_code_bins.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
         L.orc_level_for.restype = C.c_int; L.orc_level_for.argtypes = [C.c_int] * 3
         L.orc_sad.restype = C.c_int; L.orc_sad.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int]
         L.orc_satd4x4.restype = C.c_int; L.orc_satd4x4.argtypes = [vp, C.c_int, vp, C.c_int]
@@ -79,9 +83,9 @@ def _p(a):
 class Encoder:
     """One oracle session: encode(i420, idr, qp) -> Annex-B bytes; stage dumps as numpy arrays."""
 
-    def __init__(self, width, height, num_slices=1, search_range=16, fps=30, level_idc=0, no_i4x4=0, no_p8x8=0, scene_change=1):
+    def __init__(self, width, height, num_slices=1, search_range=16, fps=30, level_idc=0, no_i4x4=0, no_p8x8=0, scene_change=1, profile=0):
         self.L = lib()
-        self.cfg = OrcConfig(width, height, num_slices, search_range, level_idc, fps, no_i4x4, no_p8x8, 0 if scene_change else 1)
+        self.cfg = OrcConfig(width, height, num_slices, search_range, level_idc, fps, no_i4x4, no_p8x8, 0 if scene_change else 1, profile)
         self.h = self.L.orc_create(C.byref(self.cfg))
         self.width, self.height = width, height
         self.mbw, self.mbh = (width + 15) // 16, (height + 15) // 16
@@ -119,6 +123,16 @@ class Encoder:
         n = self.L.orc_mb_count(self.h)
         buf = (C.c_uint8 * (n * 816)).from_address(self.L.orc_mb_coef(self.h))
         return np.frombuffer(buf, MBCOEF_DTYPE).copy()
+
+    def mb_side(self):
+        n = self.L.orc_mb_count(self.h)
+        buf = (C.c_uint8 * (n * 20)).from_address(self.L.orc_mb_side(self.h))
+        return np.frombuffer(buf, MBSIDE_DTYPE).copy()
+
+    def slice_bins(self, s):
+        p = C.c_void_p()
+        n = self.L.orc_slice_bins(self.h, s, C.byref(p))
+        return np.frombuffer((C.c_uint16 * n).from_address(p.value), np.uint16).copy() if n else np.zeros(0, np.uint16)
 
     def plane(self, which, comp):
         st, w, h = C.c_int(), C.c_int(), C.c_int()
