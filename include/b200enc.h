@@ -60,6 +60,8 @@ typedef struct b200enc_config {
                               IDR instead (the wrapper asks openh264 for bEnableSceneChangeDetect, VideoEncoderOpenH264.cpp:283) */
     int auto_batch;        /* 1: concurrent b200enc_encode calls of sessions living on the same GPU are coalesced by a per-GPU
                               scheduler thread into one batch step (what gives many single-threaded callers GPU-wide throughput) */
+    int profile;           /* 0: Constrained Baseline, CAVLC; 1: Main, CABAC; 2: High, CABAC (4x4 transform) -- the wrapper's profile property
+                              baseline / main / high (VideoEncoderOpenH264.cpp:186-188,248-253) with iEntropyCodingModeFlag = 1 (:291) */
 } b200enc_config;
 
 typedef struct b200enc_frame_info {
@@ -121,7 +123,11 @@ enum {
     B200ENC_STAGE_INTER_COST = 5,  /* n_mb int32 */
     B200ENC_STAGE_SRC = 6,         /* coded-size I420 source planes */
     B200ENC_STAGE_REC_PRE = 7,     /* coded-size reconstruction before deblocking (debug = 1 only) */
-    B200ENC_STAGE_REC = 8          /* coded-size reconstruction after deblocking */
+    B200ENC_STAGE_REC = 8,         /* coded-size reconstruction after deblocking */
+    B200ENC_STAGE_MBSIDE = 9,      /* CABAC sessions: n_mb * 20 bytes (mvd / Intra_4x4 mode syntax / DC coded_block_flags) */
+    B200ENC_STAGE_BIN_COUNT = 10,  /* CABAC sessions: n_mb uint32, bin-list entries per MB */
+    B200ENC_STAGE_BIN_OFF = 11,    /* CABAC sessions: n_mb uint32, offset of the MB's entries inside its slice's list */
+    B200ENC_STAGE_BINS = 12        /* CABAC sessions: n_mb * 3136 uint16; the list of a slice starts at first_mb * 3136 */
 };
 int b200enc_get_stage(b200enc_session *s, int stage, void *out, size_t cap, size_t *written);
 /* display-size I420 reconstruction of the last frame */
@@ -135,6 +141,8 @@ int b200k_sad16x16(int device, const uint8_t *cur, const uint8_t *ref, int strid
 int b200k_satd16x16(int device, const uint8_t *cur, const uint8_t *ref, int stride, int n_blocks, const int32_t *xy, int32_t *satd);
 int b200k_transform_block(int device, const int16_t *residual /* n*16 */, int n, int qp, int intra, int16_t *levels_zz /* n*16 */, int32_t *recon_residual /* n*16 */);
 int b200k_deblock(int device, uint8_t *i420_coded, int mbw, int mbh, const void *mbinfo, int qp);
+/* the CABAC arithmetic coder (9.3.4.2) on a bin list ending with a terminate bin of value 1 (entry format: oracle/orc.h) */
+int b200k_cabac_code(int device, const uint16_t *bins, int n, int qp, int is_p, uint8_t *out, int cap, int *out_len);
 /* microbenchmark: register-resident VABSDIFF4.U8.ACC issue rate, giga lane-instructions per second, and the SM clock seen */
 int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz);
 

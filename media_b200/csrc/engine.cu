@@ -11,6 +11,7 @@
 #include "k_intra.cuh"
 #include "k_deblock.cuh"
 #include "k_cavlc.cuh"
+#include "k_cabac.cuh"
 #include "k_test.cuh"
 #include <cuda.h>
 #include <cmath>
@@ -83,13 +84,16 @@ int level_for(int w, int h, int fps)   // Table A-1: smallest level whose MaxFS 
     for (auto &l : L) if (fs <= l.fs && mbps <= l.mbps) return l.idc;
     return 52;
 }
-std::vector<uint8_t> make_parameter_sets(int w, int h, int level)
+// profile: 0 Constrained Baseline / CAVLC, 1 Main / CABAC, 2 High / CABAC (4x4 transform only; 7.3.2.1.1 adds the chroma format fields)
+std::vector<uint8_t> make_parameter_sets(int w, int h, int level, int profile)
 {
     std::vector<uint8_t> out;
     const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
     HostBits s;
-    s.put(8, 66); s.put(8, 0xC0); s.put(8, (uint32_t)level);
-    s.ue(0); s.ue(4); s.ue(2); s.ue(1); s.put(1, 0);
+    s.put(8, profile == 2 ? 100 : profile == 1 ? 77 : 66); s.put(8, profile == 2 ? 0 : profile == 1 ? 0x40 : 0xC0); s.put(8, (uint32_t)level);
+    s.ue(0);
+    if (profile == 2) { s.ue(1); s.ue(0); s.ue(0); s.put(1, 0); s.put(1, 0); }
+    s.ue(4); s.ue(2); s.ue(1); s.put(1, 0);
     s.ue((uint32_t)(mbw - 1)); s.ue((uint32_t)(mbh - 1));
     s.put(1, 1); s.put(1, 1);
     const int cr = (mbw * 16 - w) / 2, cb = (mbh * 16 - h) / 2;
@@ -97,7 +101,7 @@ std::vector<uint8_t> make_parameter_sets(int w, int h, int level)
     s.put(1, 0); s.trailing();
     append_nal(out, 0x67, s.buf);
     HostBits p;
-    p.ue(0); p.ue(0); p.put(1, 0); p.put(1, 0); p.ue(0); p.ue(0); p.ue(0); p.put(1, 0); p.put(2, 0);
+    p.ue(0); p.ue(0); p.put(1, profile ? 1 : 0); p.put(1, 0); p.ue(0); p.ue(0); p.ue(0); p.put(1, 0); p.put(2, 0);
     p.se(0); p.se(0); p.se(0); p.put(1, 1); p.put(1, 0); p.put(1, 0); p.trailing();
     append_nal(out, 0x68, p.buf);
     return out;
@@ -180,6 +184,7 @@ struct b200enc_session {
     void *tmaps;                                 // CUtensorMap[3] in HBM
     MbInfo *mbi; MbCoef *coef; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
     uint32_t *mb_bits, *mb_off, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
+    MbSide *side; uint16_t *bins; uint32_t *slice_nbins;   // CABAC (profile main / high)
     uint32_t rbsp_words_per_slice = 0;
     std::vector<uint8_t> param_sets;
     // pinned, device-mapped output: [0..cap) bitstream, then one uint32 size
@@ -256,7 +261,8 @@ struct Prof {
 bool same_shape(const b200enc_session *a, const b200enc_session *c)
 {
     return a->cfg.width == c->cfg.width && a->cfg.height == c->cfg.height && a->cfg.num_slices == c->cfg.num_slices &&
-           a->cfg.search_range == c->cfg.search_range && a->cfg.input_format == c->cfg.input_format && a->device == c->device;
+           a->cfg.search_range == c->cfg.search_range && a->cfg.input_format == c->cfg.input_format && a->device == c->device &&
+           (a->cfg.profile != 0) == (c->cfg.profile != 0);
 }
 
 int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8_t *const *frames, int device_input,
@@ -293,6 +299,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         }
         d.mbi = s->mbi; d.coef = s->coef; d.me2 = s->me2; d.me1 = s->me1; d.me0 = s->me0; d.inter_cost = s->inter_cost;
         d.skip_run = s->skip_run; d.mb_bits = s->mb_bits; d.mb_off = s->mb_off; d.mb_slot = s->mb_slot; d.rbsp = s->rbsp; d.slice_bits = s->slice_bits;
+        d.side = s->side; d.bins = s->bins; d.slice_nbins = s->slice_nbins;
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
         d.qp = qp; d.is_idr = idr; d.frame_num = s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format; d.scene_change = s->cfg.scene_change && !idr;
@@ -341,9 +348,20 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     cudaStream_t s2 = b->stream2;
     cudaEventRecord(b->ev_fork, st); cudaStreamWaitEvent(s2, b->ev_fork, 0);
     pf.begin("k_deblock_wave"); k_deblock_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
+    if (ss[0]->cfg.profile) {
+        // CABAC: side records, entry counts, offsets, bin lists (all parallel over MBs), then one warp per slice runs the coder
+        const dim3 gb((nmb + CABAC_WARPS - 1) / CABAC_WARPS, 1, n);
+        pf.begin("k_cabac_side", s2); k_cabac_side<<<dim3((nmb + 255) / 256, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_count", s2); k_cabac_bins<0><<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_scan", s2); k_cabac_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_bins", s2); k_cabac_bins<1><<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_code", s2); k_cabac_code<<<dim3(g.num_slices, 1, n), 32, 0, s2>>>(b->d_sess, g); pf.end();
+        launches += 5;
+    } else {
     pf.begin("k_cavlc_mb", s2); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_slice_scan", s2); k_slice_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_slice_copy", s2); k_slice_copy<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
+    }
     pf.begin("k_nal_pack", s2); k_nal_pack<<<n, 1024, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
     cudaEventRecord(b->ev_join, s2); cudaStreamWaitEvent(st, b->ev_join, 0);
     cudaEventRecord(b->ev1, st);
@@ -533,6 +551,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
     if (c.search_range % 4 || c.search_range > 64 || c.num_slices > B200_MAX_SLICES || c.const_qp > 51) return B200ENC_EINVAL;
     if (c.input_format < 0 || c.input_format > 2) return B200ENC_EINVAL;
     if (c.const_qp < 0 && c.bitrate <= 0) return B200ENC_EINVAL;
+    if (c.profile < 0 || c.profile > 2) return B200ENC_EINVAL;
     b200enc_session *s = new (std::nothrow) b200enc_session();
     if (!s) return B200ENC_ENOMEM;
     s->cfg = c;
@@ -560,7 +579,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         const size_t ny = (size_t)g.wc * g.hc, nc = ny / 4, nmb = (size_t)g.mbw * g.mbh;
         const int max_slice_rows = g.mbh / g.num_slices + (g.mbh % g.num_slices ? 1 : 0);
         s->rbsp_words_per_slice = (uint32_t)((size_t)max_slice_rows * g.mbw * B200_MB_SLOT_WORDS + 64);
-        const std::vector<uint8_t> ps = make_parameter_sets(c.width, c.height, c.level_idc ? c.level_idc : level_for(c.width, c.height, c.fps));
+        const std::vector<uint8_t> ps = make_parameter_sets(c.width, c.height, c.level_idc ? c.level_idc : level_for(c.width, c.height, c.fps), c.profile);
         s->hdr_len = (int)ps.size(); s->param_sets = ps;
         struct Item { void **p; size_t bytes; };
         std::vector<Item> items;
@@ -576,6 +595,8 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         add(s->skip_run, (nmb + B200_MAX_SLICES) * 4); add(s->mb_bits, nmb * 4); add(s->mb_off, nmb * 4);
         add(s->mb_slot, nmb * B200_MB_SLOT_WORDS * 4);
         add(s->rbsp, (size_t)s->rbsp_words_per_slice * g.num_slices * 4);
+        add(s->side, c.profile ? nmb * sizeof(MbSide) : 16); add(s->slice_nbins, B200_MAX_SLICES * 4);
+        add(s->bins, c.profile ? (nmb * B200_MB_BIN_SLOT + CABAC_CHUNK) * sizeof(uint16_t) : 16);
         add(s->slice_bits, B200_MAX_SLICES * 4); add(s->hdr, 256); add(s->row_prog, (size_t)g.mbh * 2 * 4);
         size_t total = 0;
         for (auto &it : items) total += align_up(it.bytes, 256);
@@ -701,6 +722,10 @@ int b200enc_get_stage(b200enc_session *s, int stage, void *out, size_t cap, size
     case B200ENC_STAGE_ME1: src = s->me1; bytes = nmb * 4; break;
     case B200ENC_STAGE_ME0: src = s->me0; bytes = nmb * 4; break;
     case B200ENC_STAGE_INTER_COST: src = s->inter_cost; bytes = nmb * 4; break;
+    case B200ENC_STAGE_MBSIDE: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->side; bytes = nmb * sizeof(MbSide); break;
+    case B200ENC_STAGE_BIN_COUNT: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->mb_bits; bytes = nmb * 4; break;
+    case B200ENC_STAGE_BIN_OFF: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->mb_off; bytes = nmb * 4; break;
+    case B200ENC_STAGE_BINS: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->bins; bytes = nmb * B200_MB_BIN_SLOT * sizeof(uint16_t); break;
     case B200ENC_STAGE_SRC: planes = s->src; break;
     case B200ENC_STAGE_REC_PRE: if (!s->cfg.debug) return B200ENC_EINVAL; planes = s->rec_pre; break;
     case B200ENC_STAGE_REC: planes = last; break;

@@ -28,10 +28,21 @@ struct __align__(16) MbCoef {
     int16_t chroma_dc[2][4];
     int16_t chroma_ac[2][4][16];
 };
+// Per-MB side record of the CABAC back end, 20 bytes: what context selection needs from a neighbour beyond MbInfo.
+struct __align__(4) MbSide {
+    union {
+        int16_t mvd[4][2];        // inter MBs: mvd_l0 of each 8x8 partition (replicated for P_L0_16x16, 0 for P_Skip)
+        uint8_t i4_syn[16];       // Intra_4x4: 8 = prev_intra4x4_pred_mode_flag set, else rem_intra4x4_pred_mode
+    };
+    uint8_t dc_cbf;               // coded_block_flag of the DC blocks: bit 0 Intra16x16DCLevel, bit 1 Cb DC, bit 2 Cr DC
+    uint8_t pad[3];
+};
+static_assert(sizeof(MbSide) == 20, "MbSide layout");
 static_assert(sizeof(MbInfo) == 48, "MbInfo layout");
 static_assert(sizeof(MbCoef) == 816, "MbCoef layout");
 
 #define B200_MAX_SLICES 35        /* MAX_SLICES_NUM_TMP, vendor/openh264/codec_app_def.h:55-56 */
+#define B200_MB_BIN_SLOT 3136     /* CABAC bin-list entries reserved per MB: 384 levels * 8 + 27 coded_block_flags + header < 3136 */
 #define B200_MB_SLOT_WORDS 352    /* per-MB CAVLC scratch: 11264 bits >= worst case (384 escapes * 28 + tokens) */
 
 // Geometry shared by every session of a batch.
@@ -67,6 +78,9 @@ struct Sess {
     uint32_t *mb_slot;            // per MB: B200_MB_SLOT_WORDS words of bits, MSB first
     uint32_t *rbsp;               // per slice region: concatenated slice_data bits
     uint32_t *slice_bits;         // per slice: total RBSP bits (header + data + trailing)
+    // CABAC (profile main / high): side records, the slices' bin lists (slice base = first MB * B200_MB_BIN_SLOT entries; mb_bits /
+    // mb_off then hold every MB's entry count / offset inside its slice's list), entries per slice
+    MbSide *side; uint16_t *bins; uint32_t *slice_nbins;
     uint8_t *out;                 // Annex-B access unit (mapped pinned host memory or HBM)
     uint32_t *out_size;           // bytes written to out
     const uint8_t *hdr; int hdr_len;   // SPS+PPS NALs, prepended on IDR

@@ -139,6 +139,23 @@ int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz)
     return B200ENC_OK;
 }
 
+
+int b200k_cabac_code(int device, const uint16_t *bins, int n, int qp, int is_p, uint8_t *out, int cap, int *out_len)
+{
+    if (!bins || n <= 0 || !out || !out_len || cap <= 0) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    const size_t padded = ((size_t)n + CABAC_CHUNK - 1) / CABAC_CHUNK * CABAC_CHUNK;
+    DevBuf dbins(padded * 2), dout((size_t)cap + 16), dlen(sizeof(int));
+    if (!dbins.p || !dout.p || !dlen.p) return B200ENC_ENOMEM;
+    K_TRY(cudaMemset(dbins.p, 0, padded * 2));
+    K_TRY(cudaMemcpy(dbins.p, bins, (size_t)n * 2, cudaMemcpyHostToDevice));
+    k_cabac_code_test<<<1, 32>>>(dbins.as<uint16_t>(), n, qp, is_p, dout.as<uint8_t>(), dlen.as<int>());
+    K_TRY(cudaGetLastError());
+    K_TRY(cudaMemcpy(out_len, dlen.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*out_len > cap) return B200ENC_EOVERFLOW;
+    K_TRY(cudaMemcpy(out, dout.p, (size_t)*out_len, cudaMemcpyDeviceToHost));
+    return B200ENC_OK;
+}
 } // extern "C"
 
 #ifdef INTRA_TIMING

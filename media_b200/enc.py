@@ -11,17 +11,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200ENC_LIB") or os.path.join(_HERE, "csrc", "libb200enc.so")   # override only for A/B experiments
 
 FMT_I420, FMT_NV12, FMT_RGBA = 0, 1, 2
-STAGE = dict(mbinfo=0, mbcoef=1, me2=2, me1=3, me0=4, inter_cost=5, src=6, rec_pre=7, rec=8)
+STAGE = dict(mbinfo=0, mbcoef=1, me2=2, me1=3, me0=4, inter_cost=5, src=6, rec_pre=7, rec=8, mbside=9, bin_count=10, bin_off=11, bins=12)
+PROFILE_BASELINE, PROFILE_MAIN, PROFILE_HIGH = 0, 1, 2
+MB_BIN_SLOT = 3136
 
 MBINFO_DTYPE = np.dtype([("mb_type", "u1"), ("i16_mode", "u1"), ("chroma_mode", "u1"), ("cbp", "u1"),
                          ("mv", "<i2", (2,)), ("i4_mode", "u1", (16,)), ("nnz", "u1", (24,))])
 MBCOEF_DTYPE = np.dtype([("luma", "<i2", (16, 16)), ("luma_dc", "<i2", (16,)),
                          ("chroma_dc", "<i2", (2, 4)), ("chroma_ac", "<i2", (2, 4, 16))])
+MBSIDE_DTYPE = np.dtype([("mvd", "<i2", (4, 2)), ("dc_cbf", "u1"), ("pad", "u1", (3,))])     # mvd aliases i4_syn[16] for Intra_4x4 MBs
 
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "height", "fps", "bitrate", "gop", "const_qp", "num_slices",
-                                       "search_range", "input_format", "device", "level_idc", "debug", "scene_change", "auto_batch")]
+                                       "search_range", "input_format", "device", "level_idc", "debug", "scene_change", "auto_batch", "profile")]
 
 
 class FrameInfo(C.Structure):
@@ -81,6 +84,7 @@ def lib():
         L.b200k_satd16x16.restype = C.c_int; L.b200k_satd16x16.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, vp, vp]
         L.b200k_transform_block.restype = C.c_int; L.b200k_transform_block.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]
         L.b200k_deblock.restype = C.c_int; L.b200k_deblock.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int]
+        L.b200k_cabac_code.restype = C.c_int; L.b200k_cabac_code.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
         L.b200k_vabsdiff4_peak.restype = C.c_int; L.b200k_vabsdiff4_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -98,9 +102,9 @@ def _p(a):
 
 class Session:
     def __init__(self, width, height, fps=30, bitrate=4_000_000, gop=30, const_qp=-1, num_slices=1, search_range=16,
-                 input_format=FMT_I420, device=-1, level_idc=0, debug=0, auto_batch=0, scene_change=1):
+                 input_format=FMT_I420, device=-1, level_idc=0, debug=0, auto_batch=0, scene_change=1, profile=PROFILE_BASELINE):
         L = lib()
-        self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug, scene_change, auto_batch)
+        self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug, scene_change, auto_batch, profile)
         self.h = C.c_void_p()
         check(L.b200enc_create(C.byref(self.cfg), C.byref(self.h)), "b200enc_create")
         self.width, self.height = width, height
@@ -140,7 +144,7 @@ class Session:
         n = self.mbw * self.mbh
         ny = self.mbw * self.mbh * 256
         sizes = dict(mbinfo=n * 48, mbcoef=n * 816, me2=n * 4, me1=n * 4, me0=n * 4, inter_cost=n * 4,
-                     src=ny * 3 // 2, rec_pre=ny * 3 // 2, rec=ny * 3 // 2)
+                     src=ny * 3 // 2, rec_pre=ny * 3 // 2, rec=ny * 3 // 2, mbside=n * 20, bin_count=n * 4, bin_off=n * 4, bins=n * MB_BIN_SLOT * 2)
         buf = np.zeros(sizes[name], np.uint8)
         wr = C.c_size_t()
         check(lib().b200enc_get_stage(self.h, STAGE[name], _p(buf), buf.size, C.byref(wr)), f"get_stage({name})")
@@ -152,6 +156,12 @@ class Session:
             return buf.view(np.int16).reshape(n, 2)
         if name == "inter_cost":
             return buf.view(np.int32)
+        if name == "mbside":
+            return buf.view(MBSIDE_DTYPE)
+        if name in ("bin_count", "bin_off"):
+            return buf.view(np.uint32)
+        if name == "bins":
+            return buf.view(np.uint16)
         return buf
 
 

@@ -100,12 +100,13 @@ EncoderRetCode VideoEncoderB200::InitEncoder()
 {
     if (!GetRoEncParam() || !GetPersistEncParam()) { ERR("init encoder failed: GetEncParam failed"); return VIDEO_ENCODER_INIT_FAIL; }
     m_encParams = m_tmpEncParams;
-    if (m_encParams.profile != "baseline")
-        WARN("profile[%s] requested: this encoder emits Constrained Baseline / CAVLC streams (decodable by any Main/High decoder)", m_encParams.profile.c_str());
     b200enc_config cfg;
     b200enc_default_config(&cfg);
     cfg.width = (int)m_encParams.width; cfg.height = (int)m_encParams.height; cfg.fps = (int)m_encParams.framerate;
     cfg.bitrate = (int)m_encParams.bitrate; cfg.gop = (int)m_encParams.gopsize;
+    // profile property -> uiProfileIdc as in the reference (VideoEncoderOpenH264.cpp:248-253); the wrapper asks for CABAC (:291), which the
+    // Baseline profile does not have, so baseline stays CAVLC and main / high are coded with CABAC
+    cfg.profile = m_encParams.profile == "high" ? 2 : m_encParams.profile == "main" ? 1 : 0;
     const std::string fmt = GetStrEncParam(KEY_INPUT_FORMAT);
     cfg.input_format = fmt == "rgba" ? B200ENC_FMT_RGBA : fmt == "nv12" ? B200ENC_FMT_NV12 : B200ENC_FMT_I420;
     const int32_t dev = GetIntEncParam(KEY_DEVICE), slices = GetIntEncParam(KEY_SLICES), range = GetIntEncParam(KEY_SEARCH_RANGE), cqp = GetIntEncParam(KEY_CONST_QP);

@@ -51,7 +51,8 @@ public:
         cfg_.num_slices = l.slice.mode == kSliceFixedNum && l.slice.num > 0 ? (int)l.slice.num : 1;
         cfg_.scene_change = p->scene_change_detect ? 1 : 0;                       // bEnableSceneChangeDetect (the wrapper sets it, :283)
         cfg_.auto_batch = 1;
-        // entropy_mode = 1 (CABAC, requested by the wrapper at :291) and profile main/high are accepted: the stream is Constrained Baseline / CAVLC
+        // entropy_mode = 1 (CABAC, requested by the wrapper at :291) takes effect for profile main (77) / high (100); Baseline has no CABAC
+        cfg_.profile = !p->entropy_mode ? 0 : l.profile_idc == 100 ? 2 : l.profile_idc == 77 ? 1 : 0;
         return create();
     }
     int Uninitialize() override { if (s_) { b200enc_destroy(s_); s_ = nullptr; } return 0; }

@@ -453,3 +453,124 @@ def test_config1_portrait_720x1280_60_frames_const_qp26(enc, orc):
         assert len(dec) == 60 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
     assert psnr(c.frame(59)[:w * h], recs[59][:w * h]) > 36
     g.close()
+
+
+# ---- CABAC back end (profile main / high; the wrapper's iEntropyCodingModeFlag = 1, VideoEncoderOpenH264.cpp:291) ----
+def _random_bins(rng, n, kind):
+    """a bin list in the oracle's entry format ending with the terminate bin of value 1"""
+    if kind == "mixed":
+        ctx = rng.integers(0, 460, n); ctx[ctx == 276] = 275
+        e = ctx | (rng.integers(0, 2, n) << 10) | (np.where(rng.random(n) < 0.1, rng.integers(0, 13, n), 0) << 11)
+        byp = rng.random(n) < 0.25
+        k = rng.integers(1, 7, n)
+        e = np.where(byp, (0x3F8 + k) | ((rng.integers(0, 64, n) & ((1 << k) - 1)) << 10), e)
+        term = rng.random(n) < 0.02
+        e = np.where(term, 276, e)
+    elif kind == "skewed":        # long runs of the most probable symbol: few output bits, carries and 0xFF runs
+        ctx = rng.integers(0, 8, n)
+        e = ctx | ((rng.random(n) < 0.02).astype(np.int64) << 10) | (rng.integers(0, 32, n) << 11)
+    else:                          # bypass only: low stays near the top of its range
+        k = rng.integers(1, 7, n)
+        e = (0x3F8 + k) | ((np.full(n, 63) & ((1 << k) - 1)) << 10)
+        e[rng.random(n) < 0.1] = 0x3F8 + 1
+    return np.concatenate([e, [276 | (1 << 10)]]).astype(np.uint16)
+
+
+@pytest.mark.parametrize("kind", ["mixed", "skewed", "bypass"])
+def test_cabac_coder_matches_the_oracle_on_random_bins(enc, orc, kind):
+    """the arithmetic coder alone (9.3.4.2): the kernel's byte-wise carry handling against the oracle's bit-serial flow charts"""
+    rng = np.random.default_rng(20261018)
+    L, O = enc.lib(), orc.lib()
+    for n in (1, 2, 7, 100, 1023, 1024, 1025, 5000, 60000):
+        for qp, is_p in ((26, 0), (40, 1), (0, 1), (51, 0)):
+            bins = _random_bins(rng, n, kind)
+            ref = np.zeros(bins.size * 8 + 64, np.uint8)
+            rn = O.orc_cabac_code_bins(_p(bins), bins.size, qp, is_p, _p(ref), ref.size)
+            out = np.zeros(ref.size, np.uint8); on = C.c_int()
+            assert L.b200k_cabac_code(0, _p(bins), bins.size, qp, is_p, _p(out), out.size, C.byref(on)) == 0
+            assert on.value == rn and np.array_equal(out[:rn], ref[:rn]), (kind, n, qp, is_p)
+
+
+@pytest.mark.parametrize("w,h,kind,qp,slices,sr,frames,profile", [
+    (208, 160, "A", 22, 1, 16, 4, 1), (128, 96, "B", 35, 2, 32, 4, 2), (96, 64, "D", 12, 4, 64, 3, 1), (352, 288, "A", 30, 1, 16, 3, 2),
+    (30, 18, "A", 26, 1, 16, 3, 1), (640, 368, "A", 40, 3, 16, 3, 1),
+])
+def test_cabac_every_stage_matches_the_oracle(enc, orc, w, h, kind, qp, slices, sr, frames, profile):
+    g = enc.Session(w, h, const_qp=qp, num_slices=slices, search_range=sr, gop=1000, device=0, profile=profile)
+    o = orc.Encoder(w, h, num_slices=slices, search_range=sr, profile=profile)
+    c = Content(kind, w, h)
+    rows = [o.mbh // slices * s + min(s, o.mbh % slices) for s in range(slices + 1)]
+    for t in range(frames):
+        f = c.frame(t)
+        bs, _ = g.encode(f); ref = o.encode(f, t == 0, qp)
+        oi = o.mb_info(); gs, os_ = g.stage("mbside"), o.mb_side()
+        assert np.array_equal(gs["dc_cbf"], os_["dc_cbf"]), f"frame {t} dc_cbf"
+        assert np.array_equal(gs["mvd"], os_["mvd"]), f"frame {t} mvd / i4 syntax"
+        cnt, off, bins = g.stage("bin_count"), g.stage("bin_off"), g.stage("bins")
+        for s in range(slices):
+            m0, m1 = rows[s] * o.mbw, rows[s + 1] * o.mbw
+            ob = o.slice_bins(s)
+            assert int(cnt[m0:m1].sum()) == ob.size, f"frame {t} slice {s}: entry count"
+            assert np.array_equal(off[m0:m1], np.concatenate([[0], np.cumsum(cnt[m0:m1])[:-1]])), f"frame {t} slice {s}: offsets"
+            gb = bins[m0 * enc.MB_BIN_SLOT: m0 * enc.MB_BIN_SLOT + ob.size]
+            if not np.array_equal(gb, ob):
+                i = int(np.argmax(gb != ob)); mb = m0 + int(np.searchsorted(np.cumsum(cnt[m0:m1]), i, side="right"))
+                raise AssertionError(f"frame {t} slice {s}: bin list differs at entry {i} (MB {mb}, type {oi['mb_type'][mb]}): {gb[i]:#x} vs {ob[i]:#x}")
+        assert bs == ref, f"frame {t} bitstream"
+        assert np.array_equal(g.recon(), o.recon()), f"frame {t} reconstruction"
+    g.close()
+
+
+@pytest.mark.parametrize("profile", [1, 2])
+def test_cabac_stream_decodes_to_own_reconstruction_1080p(enc, profile):
+    """size-independent property at the BASELINE size: an independent decoder reproduces the GPU reconstruction from the Main / High stream;
+    the same frames cost fewer bytes than with CAVLC at equal reconstruction"""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    w, h = 1920, 1080
+    g = enc.Session(w, h, bitrate=4_000_000, gop=4, device=0, profile=profile)
+    b = enc.Session(w, h, bitrate=4_000_000, gop=4, device=0)
+    c = Content("A", w, h)
+    aus, recs, cav = [], [], 0
+    for t in range(6):
+        f = c.frame(t)
+        bs, info = g.encode(f); aus.append(bs); recs.append(g.recon())
+        cav += len(b.encode(f)[0])
+    assert aus[0][4] == 0x67 and aus[0][5] == (77 if profile == 1 else 100)
+    dec = avdec.decode_stream(aus)
+    assert len(dec) == 6 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+    g.close(); b.close()
+
+
+def test_cabac_through_the_video_codec_api_profile_property(enc):
+    """persist.vmi.video.encode.profile = main / high drives the sibling into CABAC (reference: VideoEncoderOpenH264.cpp:248-253,291);
+    a profile change through param_adjusting resets the encoder and the next IDR carries the new SPS"""
+    L = C.CDLL(os.path.join(ROOT, "media_b200", "host", "libVideoCodec.so"))
+    L.vc_create.argtypes = [C.POINTER(C.c_void_p)]
+    for f in ("vc_init", "vc_start", "vc_stop", "vc_reset", "vc_destroy"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.vc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    L.vc_prop_set.argtypes = [C.c_char_p, C.c_char_p]
+    w, h = 320, 240
+    for k, v in ((b"ro.vmi.demo.video.encode.format", b"3"), (b"ro.sys.vmi.cloudphone", b"video"), (b"ro.hardware.width", b"320"),
+                 (b"ro.hardware.height", b"240"), (b"ro.hardware.fps", b"30"), (b"persist.vmi.video.encode.bitrate", b"2000000"),
+                 (b"persist.vmi.video.encode.gopsize", b"30"), (b"persist.vmi.video.encode.profile", b"main"),
+                 (b"persist.vmi.video.encode.param_adjusting", b"0"), (b"persist.vmi.video.encode.keyframe", b"0")):
+        L.vc_prop_set(k, v)
+    e = C.c_void_p()
+    assert L.vc_create(C.byref(e)) == 0 and L.vc_init(e) == 0 and L.vc_start(e) == 0
+    c = Content("A", w, h)
+    aus = []
+    out, n = C.c_void_p(), C.c_uint32()
+    for t in range(6):
+        f = c.frame(t)
+        if t == 3:
+            L.vc_prop_set(b"persist.vmi.video.encode.profile", b"high"); L.vc_prop_set(b"persist.vmi.video.encode.param_adjusting", b"1")
+        assert L.vc_encode(e, _p(f), f.size, C.byref(out), C.byref(n)) == 0
+        aus.append(C.string_at(out.value, n.value))
+    assert [a[4] for a in aus] == [0x67, 0x61, 0x61, 0x67, 0x61, 0x61]
+    assert aus[0][5] == 77 and aus[3][5] == 100                      # profile_idc of the two SPSs
+    assert L.vc_stop(e) == 0 and L.vc_destroy(e) == 0
+    L.vc_prop_set(b"persist.vmi.video.encode.profile", b"baseline")
+    if avdec.available():
+        assert len(avdec.decode_stream(aus)) == 6
