@@ -24,10 +24,12 @@ import numpy as np  # noqa: E402
 W, H, FPS, BITRATE, GOP = 1920, 1080, 30, 4_000_000, 300
 METRIC = "1080p H.264 encode frames/s per GPU"
 POOL_FRAMES = 16
+PROFILE = 0   # 0 Constrained Baseline / CAVLC (BASELINE.json's configuration), 1 Main / CABAC, 2 High / CABAC
 FMT, SLICES, SR, CQP, KIND, LABEL = 0, 1, 16, -1, "A", "Baseline CAVLC IPPP, CBR 4 Mbps @30fps each, gop 300, search +-16, 1 slice, content A (moving texture)"
 # Secondary workloads (BASELINE.json configs 2-4); the default, and what the driver runs, is the 1080p session workload above.
 WORKLOADS = {
     "1080p": {},
+    "1080p-main": dict(PROFILE=1, LABEL="Main profile CABAC IPPP (the wrapper's iEntropyCodingModeFlag = 1 with profile main), CBR 4 Mbps @30fps each, gop 300, search +-16, 1 slice, content A (moving texture)"),
     "portrait720": dict(W=720, H=1280, CQP=26, sessions=1, groups=1, METRIC="720x1280 H.264 encode frames/s per GPU",
                         LABEL="ONE 720x1280 portrait stream (config 1): Baseline CAVLC, const QP 26, gop 300, search +-16, 1 slice, content A; latency-bound by construction"),
     "single": dict(sessions=1, groups=1, LABEL="ONE 1080p stream (config 2): Baseline CAVLC IPPP, CBR 4 Mbps @30fps, gop 300, search +-16, 1 slice, content A; latency-bound by construction"),
@@ -57,7 +59,7 @@ def frame_bytes():
 
 
 def new_session(enc, dev, **kw):
-    return enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=CQP, num_slices=SLICES, search_range=SR, input_format=FMT, device=dev, **kw)
+    return enc.Session(W, H, fps=FPS, bitrate=BITRATE, gop=GOP, const_qp=CQP, num_slices=SLICES, search_range=SR, input_format=FMT, device=dev, profile=PROFILE, **kw)
 
 
 def make_pool(n=POOL_FRAMES):
@@ -329,7 +331,7 @@ def _cpu_worker(args):
     from media_b200.synth import Content
     c = Content(KIND, W, H)
     fs = [c.frame(t) for t in range(frames + 1)]
-    e = orc_py.Encoder(W, H, num_slices=SLICES, search_range=SR)
+    e = orc_py.Encoder(W, H, num_slices=SLICES, search_range=SR, profile=PROFILE)
     e.encode(fs[0], True, qps[0])
     t0 = time.perf_counter()
     for t in range(1, frames + 1):

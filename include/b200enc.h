@@ -143,6 +143,9 @@ int b200k_transform_block(int device, const int16_t *residual /* n*16 */, int n,
 int b200k_deblock(int device, uint8_t *i420_coded, int mbw, int mbh, const void *mbinfo, int qp);
 /* the CABAC arithmetic coder (9.3.4.2) on a bin list ending with a terminate bin of value 1 (entry format: oracle/orc.h) */
 int b200k_cabac_code(int device, const uint16_t *bins, int n, int qp, int is_p, uint8_t *out, int cap, int *out_len);
+/* the coder kernel `reps` times on `copies` independent copies of one list (one CTA each): average device ms per launch; stats[8]
+ * = phase cycle counts in a -DCABAC_TIMING build, else zeros */
+int b200k_cabac_code_bench(int device, const uint16_t *bins, int n, int qp, int is_p, int reps, int copies, float *ms, long long *stats);
 /* microbenchmark: register-resident VABSDIFF4.U8.ACC issue rate, giga lane-instructions per second, and the SM clock seen */
 int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz);
 

@@ -355,7 +355,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         pf.begin("k_cabac_count", s2); k_cabac_bins<0><<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
         pf.begin("k_cabac_scan", s2); k_cabac_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
         pf.begin("k_cabac_bins", s2); k_cabac_bins<1><<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
-        pf.begin("k_cabac_code", s2); k_cabac_code<<<dim3(g.num_slices, 1, n), 32, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_code", s2); k_cabac_code<<<dim3(g.num_slices, 1, n), 96, 0, s2>>>(b->d_sess, g); pf.end();
         launches += 5;
     } else {
     pf.begin("k_cavlc_mb", s2); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
@@ -596,7 +596,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         add(s->mb_slot, nmb * B200_MB_SLOT_WORDS * 4);
         add(s->rbsp, (size_t)s->rbsp_words_per_slice * g.num_slices * 4);
         add(s->side, c.profile ? nmb * sizeof(MbSide) : 16); add(s->slice_nbins, B200_MAX_SLICES * 4);
-        add(s->bins, c.profile ? (nmb * B200_MB_BIN_SLOT + CABAC_CHUNK) * sizeof(uint16_t) : 16);
+        add(s->bins, c.profile ? (nmb * B200_MB_BIN_SLOT + 64) * sizeof(uint16_t) : 16);
         add(s->slice_bits, B200_MAX_SLICES * 4); add(s->hdr, 256); add(s->row_prog, (size_t)g.mbh * 2 * 4);
         size_t total = 0;
         for (auto &it : items) total += align_up(it.bytes, 256);

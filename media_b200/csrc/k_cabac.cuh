@@ -12,8 +12,8 @@
 //                   (header, luma DC, 16 luma, 2 chroma DC, 8 chroma AC, end_of_slice). COUNT pass: entries per MB;
 //                   WRITE pass: entries stored at the MB's offset in the slice's bin list                         [warp per MB]
 //   k_cabac_scan  : prefix sum of the per-MB entry counts inside a slice                                           [CTA per slice]
-//   k_cabac_code  : slice header + the arithmetic coder over the slice's bin list; the list streams through shared memory by
-//                   cp.async double buffering, one lane runs the range/low recurrence                               [warp per slice]
+//   k_cabac_code  : slice header + the arithmetic coder over the slice's bin list: a producer warp resolves the per-context
+//                   probability states 32 entries at a time, one thread runs the range/low recurrence, one resolves carries and writes bytes [3 warps per slice]
 // Entry format (shared with the oracle, oracle/orc.h): ctxIdx | bin << 10 | (repeat - 1) << 11; ctxIdx 276 = terminate;
 // ctxIdx 0x3F8 + n = n bypass bins in bits 10.., first bin most significant.
 #pragma once
@@ -306,19 +306,26 @@ template <bool SWAP> struct CabacOut {
     }
     __device__ __forceinline__ void finish() { if (hold >= 0) store(hold); while (n_ff > 0) { store(0xff); n_ff--; } hold = -1; }
 };
-struct CabacTables {      // shared-memory copies: (pStateIdx << 1 | valMPS) -> next state, pStateIdx -> the four rangeTabLPS values in one word
+struct CabacTables {      // shared-memory copies: (pStateIdx << 1 | valMPS) -> next states, pStateIdx -> the four rangeTabLPS values in one word
     uint32_t range_lps[64];
-    uint8_t next_mps[128], next_lps[128];
+    uint32_t lps_range[64];       // per pStateIdx: low byte of the RENORMALISED range after an LPS for each of the four quantised ranges (bit 8 is always set)
+    uint32_t lps_shift[64];       // per pStateIdx: the four renormalisation shifts after an LPS, one byte each
+    uint16_t next[128];           // next state after an MPS (low byte) / after an LPS (high byte)
     uint8_t state[CABAC_NCTX + 4];
 };
 __device__ __forceinline__ void cabac_tables_init(CabacTables &t, int qp, bool is_p, int lane)
 {
-    for (int i = lane; i < 64; i += 32)
-        t.range_lps[i] = c_cabac_range_lps[i * 4] | (c_cabac_range_lps[i * 4 + 1] << 8) | (c_cabac_range_lps[i * 4 + 2] << 16) | (c_cabac_range_lps[i * 4 + 3] << 24);
+    for (int i = lane; i < 64; i += 32) {
+        uint32_t w = 0, r = 0, sh = 0;
+        for (int q = 0; q < 4; q++) {
+            const uint32_t v = c_cabac_range_lps[i * 4 + q]; const int k = __clz(v) - 23;
+            w |= v << (8 * q); r |= ((v << k) & 255u) << (8 * q); sh |= (uint32_t)k << (8 * q);
+        }
+        t.range_lps[i] = w; t.lps_range[i] = r; t.lps_shift[i] = sh;
+    }
     for (int i = lane; i < 128; i += 32) {
         const int p = i >> 1, mps = i & 1;
-        t.next_mps[i] = (uint8_t)((c_cabac_next_mps[p] << 1) | mps);
-        t.next_lps[i] = (uint8_t)((c_cabac_next_lps[p] << 1) | (p == 0 ? 1 - mps : mps));
+        t.next[i] = (uint16_t)(((c_cabac_next_mps[p] << 1) | mps) | (((c_cabac_next_lps[p] << 1) | (p == 0 ? 1 - mps : mps)) << 8));
     }
     const int q = clip3(0, 51, qp);
     for (int i = lane; i < CABAC_NCTX; i += 32) {                           // 9.3.1.1
@@ -327,116 +334,229 @@ __device__ __forceinline__ void cabac_tables_init(CabacTables &t, int qp, bool i
         t.state[i] = (uint8_t)(pre <= 63 ? (63 - pre) << 1 : ((pre - 64) << 1) | 1);
     }
 }
-struct CabacCore { uint32_t low, range; int nb; };
-// codes entries e[0..n) with the calling thread
-template <bool SWAP> __device__ __forceinline__ void cabac_run(CabacCore &c, CabacOut<SWAP> &o, CabacTables &t, const uint16_t *e, int n)
-{
-    uint32_t low = c.low, range = c.range; int nb = c.nb;
-    for (int i = 0; i < n; i++) {
-        const uint32_t v = e[i]; const int ctx = v & 1023;
-        if (ctx > CABAC_BYPASS0) {
-            const int k = ctx - CABAC_BYPASS0;
-            low = (low << k) + ((v >> 10) & ((1u << k) - 1u)) * range; nb += k;
-        } else if (ctx == 276) {
-            range -= 2;
-            if ((v >> 10) & 1) {                                            // end_of_slice_flag = 1: EncodeFlush, 9.3.4.5
-                low += range; low |= 1u;                                    // the last of the ten bits is the rbsp_stop_one_bit
-                int width = nb + 10; const int pad = (8 - (width & 7)) & 7;
-                low <<= pad; width += pad;                                  // rbsp_alignment_zero_bit
-                while (width >= 8) { width -= 8; o.byte((int)(low >> width)); low &= (1u << width) - 1u; }
-                o.finish(); nb = -1; range = 510; low = 0;
-                continue;
-            }
-            const int sh = range < 256u; range <<= sh; low <<= sh; nb += sh;
-        } else {
-            int st = t.state[ctx]; const int bin = (v >> 10) & 1;
-            for (int rep = (int)(v >> 11); rep >= 0; rep--) {
-                const uint32_t rlps = (t.range_lps[st >> 1] >> ((range >> 3) & 24)) & 255u;
-                range -= rlps;
-                if (bin != (st & 1)) { low += range; range = rlps; st = t.next_lps[st]; } else st = t.next_mps[st];
-                const int sh = __clz(range) - 23;                           // range < 512: shift up to bit 8
-                range <<= sh; low <<= sh; nb += sh;
-                if (nb >= 8) { nb -= 8; o.byte((int)(low >> (nb + 10))); low &= (1u << (nb + 10)) - 1u; }
-            }
-            t.state[ctx] = (uint8_t)st;
-            continue;
-        }
-        if (nb >= 8) { nb -= 8; o.byte((int)(low >> (nb + 10))); low &= (1u << (nb + 10)) - 1u; }
-    }
-    c.low = low; c.range = range; c.nb = nb;
-}
 
-#define CABAC_CHUNK 1024        /* entries per shared-memory buffer (2 KB); every lane brings in four 16-byte pieces */
-__device__ __forceinline__ void cabac_fetch(uint16_t *dst, const uint16_t *src, int lane)
+// The coder of one slice is a producer / consumer pair of warps around a ring of per-bin records in shared memory:
+//  * the probability-state recurrence (9.3.4.2's pStateIdx / valMPS updates) only couples bins of the SAME context, so the producer
+//    warp resolves 32 list entries at a time: lanes that share a context (match_any) take turns in list order, all others go at once.
+//    Every bin becomes a record {the four rangeTabLPS values of its state, LPS?}; bypass strings and terminate bins pass through;
+//  * what is left for the consumer (one lane) is the codIRange / codILow recurrence alone: byte select, subtract, select,
+//    count-leading-zeros, shift -- no table walk and no dependent shared-memory load on its critical path.
+#define CABAC_RING 2048           /* records; one producer step adds at most 32 entries * 32 repeats = 1024 */
+// record (every kind goes through the same branch-free step):
+//   regular bin : .x the four rangeTabLPS values of its state, .z the renormalised ranges after an LPS (low bytes), .w the LPS shifts,
+//                 .y bit 31 = the bin is the LPS
+//   bypass bins : .x = .z = .w = 0 (an "MPS" that leaves the range alone), .y = number of bins | value << 8
+//   terminate 0 : an MPS with rangeTabLPS = 2 (9.3.4.5: codIRange -= 2, RenormE)
+// the terminate bin of value 1 that ends the slice is not queued: the consumer flushes when the ring has drained
+struct CabacRing { uint4 rec[CABAC_RING]; volatile uint32_t wr, rd; volatile int done; };
+#ifdef CABAC_TIMING       // phase cycle counts of the coder pair (tools/cabac_coder_bench.py): [0] consumer total [1] consumer waiting [2] records
+__device__ long long g_cabac_t[8];   // [3] producer total [4] producer waiting for room [5] producer turn loops [6] steps [7] turns
+#define CT_CLK() clock64()
+#define CT_ADD(i, v) (g_cabac_t[i] += (v))
+#else
+#define CT_CLK() 0ll
+#define CT_ADD(i, v) ((void)0)
+#endif
+
+__device__ __forceinline__ void cabac_produce(CabacRing &ring, CabacTables &t, const uint16_t *bins, int n, int lane)
 {
+    uint32_t wr = 0;
+    const long long t_begin = CT_CLK(); long long t_wait = 0, t_turn = 0, n_turn = 0;
+    uint32_t vnext = lane < n ? bins[lane] : 0xffffu;
+    for (int base = 0; base < n; base += 32) {
+        const uint32_t v = vnext;
+        vnext = base + 32 + lane < n ? bins[base + 32 + lane] : 0xffffu;    // the next step's entries are in flight during this one
+        const bool valid = base + lane < n;
+        const int ctx = v & 1023;
+        const bool regular = valid && ctx < CABAC_BYPASS0 && ctx != 276, final = valid && ctx == 276 && ((v >> 10) & 1);
+        const int rep = regular ? (int)(v >> 11) : 0, nrec = valid && !final ? rep + 1 : 0;
+        int incl = nrec;
 #pragma unroll
-    for (int k = 0; k < CABAC_CHUNK / 8 / 32; k++) {
-        const int i = (k * 32 + lane) * 8;
-        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + i);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src + i) : "memory");
+        for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t at = wr + (uint32_t)(incl - nrec);
+        const long long t0 = CT_CLK();
+        while (wr + (uint32_t)total - ring.rd > CABAC_RING) __nanosleep(64);       // room in the ring
+        const long long t1 = CT_CLK(); t_wait += t1 - t0;
+        const uint32_t peers = __match_any_sync(0xffffffffu, regular ? ctx : 0x10000 + lane);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int turns = __reduce_max_sync(0xffffffffu, regular ? rank : 0);
+        for (int r = 0; r <= turns; r++) {
+            if (regular && rank == r) {
+                int st = t.state[ctx]; const int bin = (v >> 10) & 1;
+                for (int k = 0; k <= rep; k++) {
+                    const int lps = bin != (st & 1);
+                    ring.rec[(at + k) & (CABAC_RING - 1)] = make_uint4(t.range_lps[st >> 1], (uint32_t)lps << 31, t.lps_range[st >> 1], t.lps_shift[st >> 1]);
+                    const int nx = t.next[st]; st = lps ? nx >> 8 : nx & 255;
+                }
+                t.state[ctx] = (uint8_t)st;
+            }
+            __syncwarp();
+        }
+        t_turn += CT_CLK() - t1; n_turn += turns + 1;
+        if (valid && !regular && !final) {
+            if (ctx == 276) ring.rec[at & (CABAC_RING - 1)] = make_uint4(0x02020202u, 0u, 0u, 0u);
+            else { const int k = ctx - CABAC_BYPASS0; ring.rec[at & (CABAC_RING - 1)] = make_uint4(0u, (uint32_t)k | (((v >> 10) & ((1u << k) - 1u)) << 8), 0u, 0u); }
+        }
+        __threadfence_block(); __syncwarp();
+        wr += (uint32_t)total;
+        if (lane == 0) ring.wr = wr;
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    __threadfence_block(); __syncwarp();
+    if (lane == 0) { ring.done = 1; CT_ADD(3, CT_CLK() - t_begin); CT_ADD(4, t_wait); CT_ADD(5, t_turn); CT_ADD(6, (n + 31) / 32); CT_ADD(7, n_turn); }
 }
-// one warp codes bins[0..n) (n entries, buffer readable up to the next multiple of CABAC_CHUNK)
-template <bool SWAP> __device__ __forceinline__ void cabac_code_list(CabacOut<SWAP> &o, CabacTables &t, uint16_t (*buf)[CABAC_CHUNK], const uint16_t *bins, int n, int lane)
+
+// bytes leave the range/low recurrence as 9-bit values (a byte and the carry into the earlier ones) through a second queue; the
+// writer thread resolves the carries and stores the bytes. 0xFFFF = the slice is flushed.
+#define CABAC_OUTQ 1024
+struct CabacOutQ { uint16_t v[CABAC_OUTQ]; volatile uint32_t wr, rd; volatile int done; };
+
+// one record of the ring through the recurrence, without a branch; bytes go to the queue (qw = private write index)
+__device__ __forceinline__ void cabac_step(const uint4 rec, uint32_t &low, uint32_t &range, int &nb, CabacOutQ &oq, uint32_t &qw)
 {
-    CabacCore c; c.low = 0; c.range = 510; c.nb = -1;
-    const int nch = (n + CABAC_CHUNK - 1) / CABAC_CHUNK;
-    if (nch > 0) cabac_fetch(buf[0], bins, lane);
-    for (int ch = 0; ch < nch; ch++) {
-        if (ch + 1 < nch) { cabac_fetch(buf[(ch + 1) & 1], bins + (size_t)(ch + 1) * CABAC_CHUNK, lane); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) cabac_run<SWAP>(c, o, t, buf[ch & 1], min(CABAC_CHUNK, n - ch * CABAC_CHUNK));
-        __syncwarp();
+    const uint32_t sel = range >> 6;                                        // 4..7: byte qCodIRangeIdx of the second PRMT operand
+    const uint32_t rmps = range - __byte_perm(0u, rec.x, sel);
+    const bool lps = (int)rec.y < 0;
+    const uint32_t one = rmps < 256u;                                       // after an MPS at most one shift
+    const uint32_t sh = lps ? __byte_perm(0u, rec.w, sel) : max(one, __byte_perm(rec.y, 0u, 0x4440u));
+    low = ((low + (lps ? rmps : 0u)) << sh) + __byte_perm(rec.y, 0u, 0x4441u) * range;
+    range = lps ? 256u | __byte_perm(0u, rec.z, sel) : rmps << one;
+    nb += (int)sh;
+    const bool full = nb >= 8;
+    nb -= full ? 8 : 0;
+    if (full) oq.v[qw & (CABAC_OUTQ - 1)] = (uint16_t)(low >> (nb + 10));
+    low &= full ? (1u << (nb + 10)) - 1u : 0xffffffffu;
+    qw += full;
+}
+// the calling thread drains the ring until the producer is done
+__device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
+{
+    uint32_t low = 0, range = 510; int nb = -1;
+    uint32_t rd = 0, qw = 0;
+    const long long t_begin = CT_CLK(); long long t_wait = 0;
+    for (;;) {
+        uint32_t wr = ring.wr;
+        if (wr == rd) {
+            const long long t0 = CT_CLK();
+            if (ring.done) { wr = ring.wr; if (wr == rd) break; } else { __nanosleep(32); t_wait += CT_CLK() - t0; continue; }
+        }
+        __threadfence_block();
+        uint32_t avail = min(wr - rd, 256u);
+        while (qw + avail - oq.rd > CABAC_OUTQ) __nanosleep(32);            // a record emits at most one byte
+        for (; avail >= 8u; avail -= 8u, rd += 8u) {
+            uint4 r[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) r[i] = ring.rec[(rd + i) & (CABAC_RING - 1)];
+#pragma unroll
+            for (int i = 0; i < 8; i++) cabac_step(r[i], low, range, nb, oq, qw);
+        }
+        for (; avail; avail--, rd++) cabac_step(ring.rec[rd & (CABAC_RING - 1)], low, range, nb, oq, qw);
+        __threadfence_block();
+        ring.rd = rd; oq.wr = qw;
+    }
+    {   // the slice's last bin, end_of_slice_flag = 1: EncodeFlush, 9.3.4.5
+        range -= 2; low += range; low |= 1u;                                // the last of the ten bits is the rbsp_stop_one_bit
+        int width = nb + 10; const int pad = (8 - (width & 7)) & 7;
+        low <<= pad; width += pad;                                          // rbsp_alignment_zero_bit
+        while (qw + 8u - oq.rd > CABAC_OUTQ) __nanosleep(32);
+        while (width >= 8) { width -= 8; oq.v[qw++ & (CABAC_OUTQ - 1)] = (uint16_t)(low >> width); low &= (1u << width) - 1u; }
+        oq.v[qw++ & (CABAC_OUTQ - 1)] = 0xFFFFu;
+        __threadfence_block();
+        oq.wr = qw;
+    }
+    __threadfence_block();
+    oq.done = 1;
+    CT_ADD(0, CT_CLK() - t_begin); CT_ADD(1, t_wait); CT_ADD(2, rd);
+}
+// the calling thread turns the queue into bytes
+template <bool SWAP> __device__ __forceinline__ void cabac_write(CabacOutQ &oq, CabacOut<SWAP> &o)
+{
+    uint32_t rd = 0;
+    for (;;) {
+        uint32_t wr = oq.wr;
+        if (wr == rd) { if (oq.done) { wr = oq.wr; if (wr == rd) break; } else { __nanosleep(64); continue; } }
+        __threadfence_block();
+        for (; rd != wr; rd++) { const int v = oq.v[rd & (CABAC_OUTQ - 1)]; if (v == 0xFFFF) o.finish(); else o.byte(v); }
+        oq.rd = rd;
     }
 }
 
-// grid: (num_slices, 1, sessions), one warp
-__global__ void __launch_bounds__(32) k_cabac_code(const Sess *ss, Geom g)
+// 96 threads: warp 1 produces records, lane 0 of warp 0 runs the recurrence, lane 0 of warp 2 writes the bytes. bins[0..n) is one slice's list.
+template <bool SWAP> __device__ __forceinline__ void cabac_code_list(CabacOut<SWAP> &o, CabacTables &t, CabacRing &ring, CabacOutQ &oq, const uint16_t *bins, int n)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 1) cabac_produce(ring, t, bins, n, lane);
+    else if (warp == 0) { if (lane == 0) cabac_consume(ring, oq); }
+    else if (lane == 0) cabac_write<SWAP>(oq, o);
+}
+#define CABAC_INIT_QUEUES() do { if (threadIdx.x == 0) { ring.wr = 0; ring.rd = 0; ring.done = 0; oq.wr = 0; oq.rd = 0; oq.done = 0; } } while (0)
+
+// grid: (num_slices, 1, sessions), 96 threads
+__global__ void __launch_bounds__(96) k_cabac_code(const Sess *ss, Geom g)
 {
     const Sess &s = ss[blockIdx.z];
-    const int sl = blockIdx.x, m0 = g.slice_row0[sl] * g.mbw, lane = threadIdx.x;
+    const int sl = blockIdx.x, m0 = g.slice_row0[sl] * g.mbw, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *rb = s.rbsp + (size_t)sl * s.rbsp_words_per_slice;
     __shared__ CabacTables tabs;
-    __shared__ __align__(16) uint16_t buf[2][CABAC_CHUNK];
+    __shared__ CabacRing ring;
+    __shared__ CabacOutQ oq;
     __shared__ int hdr_bytes_s;
-    cabac_tables_init(tabs, s.qp, !s.is_idr, lane);
-    if (lane < 8) rb[lane] = 0;
-    __syncwarp();
-    if (lane == 0) {             // slice_header(), 7.3.3, then cabac_alignment_one_bit
-        BitSink<1> bs; bs.w = rb; bs.pos = 0; bs.acc = 0ull;
-        bs.ue((uint32_t)m0);
-        bs.ue(s.is_idr ? 7 : 5);
-        bs.ue(0);
-        bs.put(8, (uint32_t)(s.frame_num & 255));
-        if (s.is_idr) bs.ue((uint32_t)s.idr_pic_id);
-        if (!s.is_idr) { bs.put(1, 0); bs.put(1, 0); }
-        if (s.is_idr) { bs.put(1, 0); bs.put(1, 0); } else bs.put(1, 0);
-        if (!s.is_idr) bs.ue(0);                                            // cabac_init_idc
-        bs.se(s.qp - 26);
-        bs.ue(0); bs.se(0); bs.se(0);
-        const int pad = (8 - (bs.pos & 7)) & 7;
-        if (pad) bs.put(pad, (1u << pad) - 1u);
-        hdr_bytes_s = bs.pos >> 3;
+    CABAC_INIT_QUEUES();
+    if (warp == 1) cabac_tables_init(tabs, s.qp, !s.is_idr, lane);
+    else if (warp == 0) {
+        if (lane < 8) rb[lane] = 0;
+        __syncwarp();
+        if (lane == 0) {             // slice_header(), 7.3.3, then cabac_alignment_one_bit
+            BitSink<1> bs; bs.w = rb; bs.pos = 0; bs.acc = 0ull;
+            bs.ue((uint32_t)m0);
+            bs.ue(s.is_idr ? 7 : 5);
+            bs.ue(0);
+            bs.put(8, (uint32_t)(s.frame_num & 255));
+            if (s.is_idr) bs.ue((uint32_t)s.idr_pic_id);
+            if (!s.is_idr) { bs.put(1, 0); bs.put(1, 0); }
+            if (s.is_idr) { bs.put(1, 0); bs.put(1, 0); } else bs.put(1, 0);
+            if (!s.is_idr) bs.ue(0);                                        // cabac_init_idc
+            bs.se(s.qp - 26);
+            bs.ue(0); bs.se(0); bs.se(0);
+            const int pad = (8 - (bs.pos & 7)) & 7;
+            if (pad) bs.put(pad, (1u << pad) - 1u);
+            hdr_bytes_s = bs.pos >> 3;
+        }
     }
-    __syncwarp();
+    __syncthreads();
     CabacOut<true> o; o.base = reinterpret_cast<uint8_t *>(rb); o.pos = hdr_bytes_s; o.hold = -1; o.n_ff = 0;
-    cabac_code_list<true>(o, tabs, buf, s.bins + (size_t)m0 * B200_MB_BIN_SLOT, (int)s.slice_nbins[sl], lane);
-    if (lane == 0) s.slice_bits[sl] = (uint32_t)o.pos * 8u;
+    cabac_code_list<true>(o, tabs, ring, oq, s.bins + (size_t)m0 * B200_MB_BIN_SLOT, (int)s.slice_nbins[sl]);
+    if (threadIdx.x == 64) s.slice_bits[sl] = (uint32_t)o.pos * 8u;
 }
 
 // test entry: code one bin list into plain bytes (b200k_cabac_code)
-__global__ void __launch_bounds__(32) k_cabac_code_test(const uint16_t *bins, int n, int qp, int is_p, uint8_t *out, int *out_len)
+__global__ void __launch_bounds__(96) k_cabac_code_test(const uint16_t *bins, int n, int qp, int is_p, uint8_t *out, int *out_len)
 {
     __shared__ CabacTables tabs;
-    __shared__ __align__(16) uint16_t buf[2][CABAC_CHUNK];
-    const int lane = threadIdx.x;
-    cabac_tables_init(tabs, qp, is_p != 0, lane);
-    __syncwarp();
+    __shared__ CabacRing ring;
+    __shared__ CabacOutQ oq;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    CABAC_INIT_QUEUES();
+    if (warp == 1) cabac_tables_init(tabs, qp, is_p != 0, lane);
+    __syncthreads();
     CabacOut<false> o; o.base = out; o.pos = 0; o.hold = -1; o.n_ff = 0;
-    cabac_code_list<false>(o, tabs, buf, bins, n, lane);
-    if (lane == 0) *out_len = o.pos;
+    cabac_code_list<false>(o, tabs, ring, oq, bins, n);
+    if (threadIdx.x == 64) *out_len = o.pos;
+}
+
+// bench entry: `gridDim.x` independent copies of one list, each coded by its own CTA (b200k_cabac_code_bench)
+__global__ void __launch_bounds__(96) k_cabac_code_multi(const uint16_t *bins, int bins_stride, int n, int qp, int is_p, uint8_t *out, int out_stride, int *out_len)
+{
+    __shared__ CabacTables tabs;
+    __shared__ CabacRing ring;
+    __shared__ CabacOutQ oq;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    CABAC_INIT_QUEUES();
+    if (warp == 1) cabac_tables_init(tabs, qp, is_p != 0, lane);
+    __syncthreads();
+    CabacOut<false> o; o.base = out + (size_t)blockIdx.x * out_stride; o.pos = 0; o.hold = -1; o.n_ff = 0;
+    cabac_code_list<false>(o, tabs, ring, oq, bins + (size_t)blockIdx.x * bins_stride, n);
+    if (threadIdx.x == 64) out_len[blockIdx.x] = o.pos;
 }
 
 } // namespace b200

@@ -144,16 +144,47 @@ int b200k_cabac_code(int device, const uint16_t *bins, int n, int qp, int is_p, 
 {
     if (!bins || n <= 0 || !out || !out_len || cap <= 0) return B200ENC_EINVAL;
     if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
-    const size_t padded = ((size_t)n + CABAC_CHUNK - 1) / CABAC_CHUNK * CABAC_CHUNK;
+    const size_t padded = (size_t)n + 64;
     DevBuf dbins(padded * 2), dout((size_t)cap + 16), dlen(sizeof(int));
     if (!dbins.p || !dout.p || !dlen.p) return B200ENC_ENOMEM;
     K_TRY(cudaMemset(dbins.p, 0, padded * 2));
     K_TRY(cudaMemcpy(dbins.p, bins, (size_t)n * 2, cudaMemcpyHostToDevice));
-    k_cabac_code_test<<<1, 32>>>(dbins.as<uint16_t>(), n, qp, is_p, dout.as<uint8_t>(), dlen.as<int>());
+    k_cabac_code_test<<<1, 96>>>(dbins.as<uint16_t>(), n, qp, is_p, dout.as<uint8_t>(), dlen.as<int>());
     K_TRY(cudaGetLastError());
     K_TRY(cudaMemcpy(out_len, dlen.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (*out_len > cap) return B200ENC_EOVERFLOW;
     K_TRY(cudaMemcpy(out, dout.p, (size_t)*out_len, cudaMemcpyDeviceToHost));
+    return B200ENC_OK;
+}
+
+// the coder kernel `reps` times on one bin list: average device time per run (CUDA events) and, in a -DCABAC_TIMING build, the phase
+// cycle counts of the producer / consumer pair summed over the runs (tools/cabac_coder_bench.py)
+int b200k_cabac_code_bench(int device, const uint16_t *bins, int n, int qp, int is_p, int reps, int copies, float *ms, long long *stats)
+{
+    if (!bins || n <= 0 || reps <= 0 || copies <= 0 || !ms) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    const size_t padded = (size_t)n + 64;
+    DevBuf dbins(padded * 2 * copies), dout(((size_t)n * 8 + 64) * copies), dlen(sizeof(int) * copies);
+    if (!dbins.p || !dout.p || !dlen.p) return B200ENC_ENOMEM;
+    for (int c = 0; c < copies; c++) K_TRY(cudaMemcpy(dbins.as<uint16_t>() + c * padded, bins, (size_t)n * 2, cudaMemcpyHostToDevice));
+#ifdef CABAC_TIMING
+    { long long z[8] = { 0 }; K_TRY(cudaMemcpyToSymbol(g_cabac_t, z, sizeof z)); }
+#endif
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    for (int r = 0; r < reps; r++)
+        k_cabac_code_multi<<<copies, 96>>>(dbins.as<uint16_t>(), (int)padded, n, qp, is_p, dout.as<uint8_t>(), n * 8 + 64, dlen.as<int>());
+    cudaEventRecord(e1);
+    K_TRY(cudaEventSynchronize(e1));
+    K_TRY(cudaGetLastError());
+    cudaEventElapsedTime(ms, e0, e1); *ms /= reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) {
+        memset(stats, 0, 8 * sizeof(long long));
+#ifdef CABAC_TIMING
+        K_TRY(cudaMemcpyFromSymbol(stats, g_cabac_t, 8 * sizeof(long long)));
+#endif
+    }
     return B200ENC_OK;
 }
 } // extern "C"
