@@ -24,7 +24,7 @@ def _p(a):
 @pytest.mark.parametrize("case", GOLDEN, ids=lambda c: c["name"])
 def test_encode_matches_golden(enc, case):
     """no oracle at run time: hashes of every access unit and reconstruction were produced by oracle/ (tools/make_golden.py)"""
-    g = enc.Session(case["w"], case["h"], const_qp=case["qp"], num_slices=case["slices"], search_range=case["sr"], gop=1000, device=0)
+    g = enc.Session(case["w"], case["h"], const_qp=case["qp"], num_slices=case["slices"], search_range=case["sr"], gop=1000, device=0, profile=case.get("profile", 0))
     c = Content(case["kind"], case["w"], case["h"])
     for t in range(case["frames"]):
         bs, info = g.encode(c.frame(t))

@@ -19,7 +19,7 @@ needs_decoder = pytest.mark.skipif(not avdec.available(), reason="libavcodec fro
 
 
 def encode_case(orc, c, frames=None):
-    e = orc.Encoder(c["w"], c["h"], num_slices=c["slices"], search_range=c["sr"])
+    e = orc.Encoder(c["w"], c["h"], num_slices=c["slices"], search_range=c["sr"], profile=c.get("profile", 0))
     content = Content(c["kind"], c["w"], c["h"])
     aus, recs = [], []
     for t in range(frames or c["frames"]):
@@ -48,9 +48,11 @@ def test_oracle_stream_decodes_to_its_reconstruction(orc, case):
 
 @needs_decoder
 def test_golden_stream_decodes_without_the_oracle():
-    case = next(c for c in GOLDEN if "stream_hex" in c)
-    dec = avdec.decode_stream([bytes.fromhex(h) for h in case["stream_hex"]])
-    assert [hashlib.sha256(d.tobytes()).hexdigest() for d in dec] == case["recon_sha256"]
+    cases = [c for c in GOLDEN if "stream_hex" in c]
+    assert {c.get("profile", 0) for c in cases} == {0, 1}          # a CAVLC and a CABAC stream are committed byte for byte
+    for case in cases:
+        dec = avdec.decode_stream([bytes.fromhex(h) for h in case["stream_hex"]])
+        assert [hashlib.sha256(d.tobytes()).hexdigest() for d in dec] == case["recon_sha256"], case["name"]
 
 
 @needs_decoder
@@ -81,6 +83,65 @@ def test_tables_match_the_independent_decoder():
                      "TOTAL_ZEROS_BITS", "CHROMA_DC_TOTAL_ZEROS_LEN", "CHROMA_DC_TOTAL_ZEROS_BITS", "RUN_BEFORE_LEN", "RUN_BEFORE_BITS",
                      "ZIGZAG4x4", "CHROMA_QP", "DEBLOCK_ALPHA", "DEBLOCK_BETA"):
             assert blob.find(tabs[name]) >= 0, name
+
+
+def test_cabac_tables_match_the_independent_decoder():
+    """Tables 9-12..9-23 (m, n for ctxIdx 0..459, I slices and cabac_init_idc 0), 9-44 (rangeTabLPS) and 9-45 (state transitions)
+    as committed in oracle/cabac_tables.h against the copies inside libavcodec"""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    import cv2
+    d = os.path.join(os.path.dirname(cv2.__file__), "..", "opencv_python_headless.libs")
+    blob = open(glob.glob(os.path.join(d, "libavcodec-*"))[0], "rb").read()
+    src = open(os.path.join(ROOT, "oracle", "cabac_tables.h")).read()
+    tabs = {m.group(1): [int(x) for x in re.findall(r"-?\d+", m.group(2))]
+            for m in re.finditer(r"static const u?int8_t (\w+)\[[^\]]*\] = \{(.*?)\};", src, re.S)}
+    assert len(tabs["CABAC_INIT_I"]) == 920 and len(tabs["CABAC_INIT_P0"]) == 920
+    for name in ("CABAC_INIT_I", "CABAC_INIT_P0"):         # the decoder's tables run to ctxIdx 1023; ours are their first 460 rows
+        assert blob.find(np.array(tabs[name], np.int8).tobytes()) >= 0, name
+    ns = blob.find(bytes([9, 8, 7, 7, 6, 6, 6, 6, 5, 5, 5, 5, 5, 5, 5, 5]))      # ff_h264_cabac_tables: norm_shift, lps_range, mlps_state
+    assert ns >= 0
+    lps, ml = blob[ns + 512: ns + 1024], blob[ns + 1024: ns + 1280]
+    for s_ in range(64):
+        for q in range(4):
+            assert lps[q * 128 + 2 * s_] == lps[q * 128 + 2 * s_ + 1] == tabs["CABAC_RANGE_LPS"][s_ * 4 + q]
+        assert ml[128 + 2 * s_] // 2 == tabs["CABAC_NEXT_MPS"][s_] and ml[127 - 2 * s_] // 2 == tabs["CABAC_NEXT_LPS"][s_]
+    # spot values of the standard itself
+    assert tabs["CABAC_RANGE_LPS"][:4] == [128, 176, 208, 240] and tabs["CABAC_RANGE_LPS"][-4:] == [2, 2, 2, 2]
+    assert tabs["CABAC_INIT_I"][:6] == [20, -15, 2, 54, 3, 74] and tabs["CABAC_INIT_P0"][22:26] == [23, 33, 23, 2]
+
+
+def test_product_cabac_tables_equal_oracle_tables():
+    def nums(text, name):
+        m = re.search(name + r"\[[^\]]*\] = \{(.*?)\};", text, re.S)
+        assert m, name
+        return [int(x) for x in re.findall(r"-?\d+", m.group(1))]
+    o = open(os.path.join(ROOT, "oracle", "cabac_tables.h")).read()
+    p = open(os.path.join(ROOT, "media_b200", "csrc", "cabac_tables.cuh")).read()
+    for a, b in (("CABAC_INIT_I", "c_cabac_init_i"), ("CABAC_INIT_P0", "c_cabac_init_p0"), ("CABAC_RANGE_LPS", "c_cabac_range_lps"),
+                 ("CABAC_NEXT_LPS", "c_cabac_next_lps"), ("CABAC_NEXT_MPS", "c_cabac_next_mps")):
+        assert nums(o, a) == nums(p, b) and len(nums(o, a)) > 0, (a, b)
+
+
+def test_cabac_changes_only_the_entropy_coding(orc):
+    """same frames, same QP: Main / High (CABAC) and Baseline (CAVLC) sessions reconstruct identically, CABAC is smaller, and the
+    arithmetic coder run on the dumped bin list alone reproduces the slice payload"""
+    w, h = 176, 144
+    c = Content("A", w, h)
+    e0, e1 = orc.Encoder(w, h), orc.Encoder(w, h, profile=1)
+    for t in range(4):
+        a0, a1 = e0.encode(c.frame(t), t == 0, 28), e1.encode(c.frame(t), t == 0, 28)
+        assert np.array_equal(e0.recon(), e1.recon()) and len(a1) < len(a0)
+        assert np.array_equal(e0.mb_info(), e1.mb_info())
+        bins = e1.slice_bins(0)
+        assert bins[-1] == (276 | 1 << 10) and int((bins & 1023 == 276).sum()) == e1.mbw * e1.mbh        # one end_of_slice_flag per MB
+        out = np.zeros(bins.size * 4 + 64, np.uint8)
+        n = orc.lib().orc_cabac_code_bins(bins.ctypes.data, bins.size, 28, int(t > 0), out.ctypes.data, out.size)
+        payload = out[:n].tobytes()
+        # Annex-B slice NAL: unescape, then the payload sits after the byte-aligned slice header
+        nal = a1[a1.rfind(b"\x00\x00\x00\x01") + 5:]
+        rbsp = nal.replace(b"\x00\x00\x03", b"\x00\x00")
+        assert rbsp.endswith(payload)
 
 
 def test_product_tables_equal_oracle_tables():

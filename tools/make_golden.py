@@ -23,11 +23,18 @@ CASES = [
     dict(name="qp0_48x48", w=48, h=48, kind="D", frames=2, qp=0, slices=1, sr=16),
     dict(name="one_mb", w=16, h=16, kind="A", frames=3, qp=26, slices=1, sr=16),
     dict(name="p720_A_qp26", w=1280, h=720, kind="A", frames=3, qp=26, slices=1, sr=16),
+    # CABAC back end (profile 1 = Main, 2 = High; the wrapper's iEntropyCodingModeFlag = 1, VideoEncoderOpenH264.cpp:291)
+    dict(name="main_qcif_A_qp26", w=176, h=144, kind="A", frames=5, qp=26, slices=1, sr=16, profile=1),
+    dict(name="main_tiny_A_qp26", w=64, h=48, kind="A", frames=3, qp=26, slices=1, sr=16, profile=1, keep_stream=True),
+    dict(name="high_screen_320x180_3sl_sr32", w=320, h=180, kind="B", frames=4, qp=26, slices=3, sr=32, profile=2),
+    dict(name="main_noise_qp12_96x80", w=96, h=80, kind="D", frames=3, qp=12, slices=2, sr=16, profile=1),
+    dict(name="main_one_mb", w=16, h=16, kind="A", frames=3, qp=26, slices=1, sr=16, profile=1),
+    dict(name="high_p720_A_qp30", w=1280, h=720, kind="A", frames=3, qp=30, slices=1, sr=16, profile=2),
 ]
 
 out = []
 for c in CASES:
-    e = orc_py.Encoder(c["w"], c["h"], num_slices=c["slices"], search_range=c["sr"])
+    e = orc_py.Encoder(c["w"], c["h"], num_slices=c["slices"], search_range=c["sr"], profile=c.get("profile", 0))
     content = Content(c["kind"], c["w"], c["h"])
     aus, recs = [], []
     for t in range(c["frames"]):
