@@ -50,7 +50,8 @@ typedef struct b200enc_config {
     int bitrate;           /* bits per second, CBR target used when const_qp < 0 (:239-240) */
     int gop;               /* IDR period in frames (uiIntraPeriod, :242) */
     int const_qp;          /* 0..51: fixed QP for every frame; < 0: rate control */
-    int num_slices;        /* MB-row groups, 1..35; reference uses SM_SINGLE_SLICE (:247) */
+    int num_slices;        /* MB-row groups, 1..35; 0 = automatic: 1 with CAVLC (the reference's SM_SINGLE_SLICE, :247), one per ~17 MB rows with
+                              CABAC, whose arithmetic coder is a serial chain per slice */
     int search_range;      /* full-pel, multiple of 4 in 4..64 */
     int input_format;      /* B200ENC_FMT_* */
     int device;            /* CUDA ordinal, or -1: least-loaded device by pixel rate */

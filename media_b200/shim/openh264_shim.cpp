@@ -48,11 +48,12 @@ public:
         cfg_.gop = p->intra_period ? (int)p->intra_period : 1 << 30;               // 0 = only the first frame is intra
         cfg_.const_qp = p->rc_mode == kRcOff ? (l.dlayer_qp >= 0 && l.dlayer_qp <= 51 ? l.dlayer_qp : 26) : -1;
         if (cfg_.const_qp < 0 && cfg_.bitrate <= 0) cfg_.bitrate = 1000000;
-        cfg_.num_slices = l.slice.mode == kSliceFixedNum && l.slice.num > 0 ? (int)l.slice.num : 1;
+        cfg_.num_slices = l.slice.mode == kSliceFixedNum && l.slice.num > 0 ? (int)l.slice.num : 1;       // SM_SINGLE_SLICE (the wrapper, :247)
         cfg_.scene_change = p->scene_change_detect ? 1 : 0;                       // bEnableSceneChangeDetect (the wrapper sets it, :283)
         cfg_.auto_batch = 1;
         // entropy_mode = 1 (CABAC, requested by the wrapper at :291) takes effect for profile main (77) / high (100); Baseline has no CABAC
         cfg_.profile = !p->entropy_mode ? 0 : l.profile_idc == 100 ? 2 : l.profile_idc == 77 ? 1 : 0;
+        if (cfg_.profile && l.slice.mode != kSliceFixedNum) cfg_.num_slices = 0;    // CABAC: the engine's automatic slice count (the coder is serial per slice)
         return create();
     }
     int Uninitialize() override { if (s_) { b200enc_destroy(s_); s_ = nullptr; } return 0; }

@@ -3,7 +3,7 @@
 // cloud-phone caller does with EncodeOneFrame, reference video_codec/VideoEncoderOpenH264.cpp:304-352, iMultipleThreadIdc = 1 at :294).
 // The per-GPU auto_batch scheduler of libb200enc coalesces the concurrent calls. Prints one JSON line: latency percentiles of the
 // encode call, frames that finished after the next frame's capture time ("late"), and the sessions' achieved frame rate.
-// usage: rt_sessions <sessions> <seconds> [width height fps bitrate input_format(0 i420 | 2 rgba) devices]
+// usage: rt_sessions <sessions> <seconds> [width height fps bitrate input_format(0 i420 | 2 rgba) devices(0 = all) profile(0 baseline | 1 main | 2 high) slices]
 #include "../include/b200enc.h"
 #include <algorithm>
 #include <atomic>
@@ -21,7 +21,8 @@ int main(int argc, char **argv)
     const int N = argc > 1 ? atoi(argv[1]) : 8; const double seconds = argc > 2 ? atof(argv[2]) : 3.0;
     const int W = argc > 3 ? atoi(argv[3]) : 1920, H = argc > 4 ? atoi(argv[4]) : 1080, fps = argc > 5 ? atoi(argv[5]) : 30;
     const int bitrate = argc > 6 ? atoi(argv[6]) : 4000000, fmt = argc > 7 ? atoi(argv[7]) : 0;
-    int ndev = b200enc_device_count(); if (argc > 8) ndev = std::min(ndev, atoi(argv[8]));
+    int ndev = b200enc_device_count(); if (argc > 8 && atoi(argv[8]) > 0) ndev = std::min(ndev, atoi(argv[8]));
+    const int profile = argc > 9 ? atoi(argv[9]) : 0, slices = argc > 10 ? atoi(argv[10]) : 1;      // 0 Baseline / CAVLC, 1 Main / CABAC, 2 High / CABAC
     if (ndev <= 0) { printf("{\"error\": \"no CUDA device\"}\n"); return 1; }
     // frame pool in pinned memory: a translating band-limited texture (deterministic), shared by all sessions
     const int POOL = 8; const size_t fb = fmt == 2 ? (size_t)W * H * 4 : (size_t)W * H * 3 / 2;
@@ -45,7 +46,7 @@ int main(int argc, char **argv)
     std::vector<b200enc_session *> sess(N, nullptr);
     for (int i = 0; i < N; i++) {
         b200enc_config c; b200enc_default_config(&c);
-        c.width = W; c.height = H; c.fps = fps; c.bitrate = bitrate; c.gop = 300; c.input_format = fmt; c.auto_batch = 1; c.device = i % ndev;
+        c.width = W; c.height = H; c.fps = fps; c.bitrate = bitrate; c.gop = 300; c.input_format = fmt; c.auto_batch = 1; c.device = i % ndev; c.profile = profile; c.num_slices = slices;
         const int rc = b200enc_create(&c, &sess[i]);
         if (rc) { printf("{\"error\": \"create %d failed: %s\"}\n", i, b200enc_strerror(rc)); return 1; }
     }
