@@ -24,7 +24,7 @@ int main(int argc, char **argv)
     // the wrapper's policy (VideoEncoderOpenH264.cpp:236-255, 270-296)
     p.width = w; p.height = hgt; p.target_bitrate = bitrate; p.max_bitrate = bitrate; p.max_frame_rate = 30.f; p.intra_period = gop;
     p.layers[0].width = w; p.layers[0].height = hgt; p.layers[0].frame_rate = 30.f; p.layers[0].bitrate = bitrate;
-    p.layers[0].slice.mode = kSliceSingle; p.layers[0].profile_idc = 66; p.layers[0].level_idc = 32;
+    p.layers[0].slice.mode = kSliceSingle; p.layers[0].profile_idc = argc > 11 ? atoi(argv[11]) : 66; p.layers[0].level_idc = 32;
     p.usage = 0; p.rc_mode = kRcBitrate; p.frame_skip = 0; p.temporal_layers = 1; p.spatial_layers = 1; p.sps_pps_id_strategy = 0;
     p.background_detection = 1; p.scene_change_detect = 1; p.complexity = 2; p.num_ref = 1; p.entropy_mode = 1; p.max_nal_size = 0;
     p.multiple_thread_idc = 1; p.loop_filter_disable_idc = 0;

@@ -350,7 +350,8 @@ def test_video_codec_api_flow(enc):
         assert len(avdec.decode_stream(aus)) == 7
 
 
-def test_openh264_abi_shim_serves_the_wrapper_flow(enc, tmp_path):
+@pytest.mark.parametrize("profile_idc,profile", [(66, 0), (77, 1), (100, 2)])
+def test_openh264_abi_shim_serves_the_wrapper_flow(enc, tmp_path, profile_idc, profile):
     """media_b200/shim/libopenh264.so behind the openh264 vtable: the stream a client gets through
     WelsCreateSVCEncoder / InitializeExt / EncodeFrame equals the one the C ABI gives for the same configuration,
     and SFrameBSInfo is laid out as the reference wrapper expects (VideoEncoderOpenH264.cpp:349-350)"""
@@ -363,8 +364,10 @@ def test_openh264_abi_shim_serves_the_wrapper_flow(enc, tmp_path):
     (tmp_path / "in.i420").write_bytes(b"".join(f.tobytes() for f in frames))
     lib = os.path.join(ROOT, "media_b200", "shim", "libopenh264.so")
     subprocess.check_call([str(exe), lib, str(tmp_path / "in.i420"), str(w), str(h), str(n), str(br), str(gop), str(force_at),
-                           str(tmp_path / "out.h264"), str(tmp_path / "out.info")])
-    s = enc.Session(w, h, fps=30, bitrate=br, gop=gop, const_qp=-1, device=0)
+                           str(tmp_path / "out.h264"), str(tmp_path / "out.info"), str(profile_idc)])
+    # the client sets iEntropyCodingModeFlag = 1 and SM_SINGLE_SLICE like the wrapper (:247,291): CABAC for uiProfileIdc 77 / 100 with the
+    # engine's automatic slice count, CAVLC and one slice for 66
+    s = enc.Session(w, h, fps=30, bitrate=br, gop=gop, const_qp=-1, device=0, profile=profile, num_slices=0 if profile else 1)
     want = []
     for t, f in enumerate(frames):
         if t == force_at:
@@ -378,7 +381,8 @@ def test_openh264_abi_shim_serves_the_wrapper_flow(enc, tmp_path):
         _, ftype, size, layers, nals, nal_sum, l0type = (int(x) for x in rows[t])
         idr = t in (0, force_at)
         assert size == len(want[t]) == nal_sum
-        assert (ftype, layers, nals, l0type) == ((1, 2, 3, 0) if idr else (3, 1, 1, 1))    # IDR: [SPS PPS] + [slice]; P: [slice]
+        ns = 1 if profile == 0 else max(1, min(8, ((h + 15) // 16 + 8) // 17))              # slice NALs per picture
+        assert (ftype, layers, nals, l0type) == ((1, 2, 2 + ns, 0) if idr else (3, 1, ns, 1))    # IDR: [SPS PPS] + [slices]; P: [slices]
     assert rows[n][0] == "ps" and int(rows[n][2]) == 1 and int(rows[n][3]) == 2
     if avdec.available():
         assert len(avdec.decode_stream(want)) == n
@@ -421,13 +425,13 @@ def test_scene_change_idr_matches_the_oracle(enc, orc):
     w, h = 256, 160
     a, b = Content("A", w, h, seed=1), Content("A", w, h, seed=99)
     frames = [a.frame(0), a.frame(1), b.frame(2), b.frame(3), b.frame(4)]
-    for detect in (1, 0):
-        g = enc.Session(w, h, const_qp=28, gop=1000, device=0, scene_change=detect)
-        o = orc.Encoder(w, h, scene_change=detect)
+    for detect, profile in ((1, 0), (0, 0), (1, 1)):
+        g = enc.Session(w, h, const_qp=28, gop=1000, device=0, scene_change=detect, profile=profile)
+        o = orc.Encoder(w, h, scene_change=detect, profile=profile)
         types = []
         for t, f in enumerate(frames):
             bs, info = g.encode(f); ref = o.encode(f, t == 0, 28)
-            assert bs == ref and np.array_equal(g.recon(), o.recon()), (detect, t)
+            assert bs == ref and np.array_equal(g.recon(), o.recon()), (detect, profile, t)
             assert info.frame_type == int(o.last_was_idr())
             types.append(info.frame_type)
         assert types == ([1, 0, 1, 0, 0] if detect else [1, 0, 0, 0, 0])
@@ -574,3 +578,45 @@ def test_cabac_through_the_video_codec_api_profile_property(enc):
     L.vc_prop_set(b"persist.vmi.video.encode.profile", b"baseline")
     if avdec.available():
         assert len(avdec.decode_stream(aus)) == 6
+
+
+def test_cabac_random_geometries_and_qps_match_the_oracle(enc, orc):
+    """seeded sweep over odd sizes, every QP range (0 and 51 included), slice counts, search ranges and both CABAC profiles"""
+    rng = np.random.default_rng(20261019)
+    for trial in range(12):
+        w = int(rng.integers(8, 120)) * 2; h = int(rng.integers(8, 90)) * 2
+        qp = int([0, 51, 7, 13, 19, 24, 28, 33, 38, 44][trial % 10]); slices = int(rng.integers(1, 5)); sr = int(rng.choice([16, 32, 64]))
+        kind = str(rng.choice(["A", "B", "C", "D"])); profile = 1 + trial % 2
+        g = enc.Session(w, h, const_qp=qp, num_slices=slices, search_range=sr, gop=1000, device=0, profile=profile)
+        o = orc.Encoder(w, h, num_slices=slices, search_range=sr, profile=profile)
+        c = Content(kind, w, h, seed=int(rng.integers(1, 1 << 30)))
+        for t in range(3):
+            f = c.frame(t)
+            bs, _ = g.encode(f); ref = o.encode(f, t == 0, qp)
+            assert bs == ref, f"trial {trial}: {w}x{h} qp {qp} slices {slices} sr {sr} content {kind} profile {profile} frame {t}: bitstream"
+            assert np.array_equal(g.recon(), o.recon()), f"trial {trial} frame {t}: reconstruction"
+        g.close()
+
+
+def test_cabac_batch_of_rgba_sessions_equals_individual_sessions(enc, orc):
+    """CABAC sessions in one batch step (RGBA framebuffers, automatic slice count) produce what each produces alone, and CABAC and CAVLC
+    sessions do not mix in a batch"""
+    w, h, n = 320, 192, 5
+    cs = [Content("B", w, h, seed=10 + i) for i in range(n)]
+    solo = []
+    for i in range(n):
+        s = enc.Session(w, h, const_qp=30, gop=1000, device=0, input_format=enc.FMT_RGBA, profile=1, num_slices=0)
+        solo.append([s.encode(i420_to_rgba(cs[i].frame(t), w, h))[0] for t in range(3)]); s.close()
+    ss = [enc.Session(w, h, const_qp=30, gop=1000, device=0, input_format=enc.FMT_RGBA, profile=1, num_slices=0) for _ in range(n)]
+    b = enc.Batch(0, ss)
+    for t in range(3):
+        bs, _ = b.encode([i420_to_rgba(cs[i].frame(t), w, h) for i in range(n)])
+        assert [x for x in bs] == [solo[i][t] for i in range(n)], f"frame {t}"
+    b.close()
+    mixed = [ss[0], enc.Session(w, h, const_qp=30, gop=1000, device=0, input_format=enc.FMT_RGBA)]
+    bm = enc.Batch(0, mixed)
+    with pytest.raises(enc.B200EncError):
+        bm.encode([i420_to_rgba(cs[0].frame(3), w, h)] * 2)
+    bm.close()
+    for s in ss + mixed[1:]:
+        s.close()
