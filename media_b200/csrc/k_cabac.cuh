@@ -361,7 +361,7 @@ __device__ long long g_cabac_t[8];   // [3] producer total [4] producer waiting 
 __device__ __forceinline__ void cabac_produce(CabacRing &ring, CabacTables &t, const uint16_t *bins, int n, int lane)
 {
     uint32_t wr = 0;
-    const long long t_begin = CT_CLK(); long long t_wait = 0, t_turn = 0, n_turn = 0;
+    [[maybe_unused]] const long long t_begin = CT_CLK(); [[maybe_unused]] long long t_wait = 0, t_turn = 0, n_turn = 0;
     uint32_t vnext = lane < n ? bins[lane] : 0xffffu;
     for (int base = 0; base < n; base += 32) {
         const uint32_t v = vnext;
@@ -433,7 +433,7 @@ __device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
 {
     uint32_t low = 0, range = 510; int nb = -1;
     uint32_t rd = 0, qw = 0;
-    const long long t_begin = CT_CLK(); long long t_wait = 0;
+    [[maybe_unused]] const long long t_begin = CT_CLK(); [[maybe_unused]] long long t_wait = 0;
     for (;;) {
         uint32_t wr = ring.wr;
         if (wr == rd) {
