@@ -343,9 +343,9 @@ __device__ __forceinline__ void cabac_tables_init(CabacTables &t, int qp, bool i
 //    count-leading-zeros, shift -- no table walk and no dependent shared-memory load on its critical path.
 #define CABAC_RING 2048           /* records; one producer step adds at most 32 entries * 32 repeats = 1024 */
 // record (every kind goes through the same branch-free step):
-//   regular bin : .x the four rangeTabLPS values of its state, .z the renormalised ranges after an LPS (low bytes), .w the LPS shifts,
-//                 .y bit 31 = the bin is the LPS
-//   bypass bins : .x = .z = .w = 0 (an "MPS" that leaves the range alone), .y = number of bins | value << 8
+//   regular bin : .x the four rangeTabLPS values of its state, .y bit 31 = the bin is the LPS; if it is: .z the renormalised ranges after
+//                 the LPS (low bytes) and .w the shifts, one byte per quantised range; else .z = .w = 0
+//   bypass bins : .x = .z = 0 (an "MPS" that leaves the range alone), .y = value, .w = number of bins in every byte
 //   terminate 0 : an MPS with rangeTabLPS = 2 (9.3.4.5: codIRange -= 2, RenormE)
 // the terminate bin of value 1 that ends the slice is not queued: the consumer flushes when the ring has drained
 struct CabacRing { uint4 rec[CABAC_RING]; volatile uint32_t wr, rd; volatile int done; };
@@ -379,24 +379,38 @@ __device__ __forceinline__ void cabac_produce(CabacRing &ring, CabacTables &t, c
         while (wr + (uint32_t)total - ring.rd > CABAC_RING) __nanosleep(64);       // room in the ring
         const long long t1 = CT_CLK(); t_wait += t1 - t0;
         const uint32_t peers = __match_any_sync(0xffffffffu, regular ? ctx : 0x10000 + lane);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const uint32_t before = peers & ((1u << lane) - 1u);
+        const int rank = __popc(before), pred = before ? 31 - __clz(before) : lane;   // the lane that holds this context just before me
         const int turns = __reduce_max_sync(0xffffffffu, regular ? rank : 0);
+        // the lanes of a group take turns in list order; the state travels from lane to lane through a shuffle and only the last
+        // lane of a group writes it back
+        int st = regular ? t.state[ctx] : 0;
+        const int bin = (v >> 10) & 1;
+        const bool closes = (peers >> lane) == 1u;                                  // no later lane shares the context: writes the state back
         for (int r = 0; r <= turns; r++) {
-            if (regular && rank == r) {
-                int st = t.state[ctx]; const int bin = (v >> 10) & 1;
-                for (int k = 0; k <= rep; k++) {
-                    const int lps = bin != (st & 1);
-                    ring.rec[(at + k) & (CABAC_RING - 1)] = make_uint4(t.range_lps[st >> 1], (uint32_t)lps << 31, t.lps_range[st >> 1], t.lps_shift[st >> 1]);
-                    const int nx = t.next[st]; st = lps ? nx >> 8 : nx & 255;
+            // straight-line body for every lane (the lanes whose turn it is not compute on their own state and store nothing); only an
+            // entry that repeats its bin takes the warp through the loop below
+            const bool mine = regular && rank == r;
+            int lps = bin != (st & 1), p = st >> 1;
+            const uint4 rec = make_uint4(t.range_lps[p], (uint32_t)lps << 31, lps ? t.lps_range[p] : 0u, lps ? t.lps_shift[p] : 0u);
+            if (mine) ring.rec[at & (CABAC_RING - 1)] = rec;
+            int nx = t.next[st], s1 = lps ? nx >> 8 : nx & 255;
+            if (__any_sync(0xffffffffu, mine && rep > 0)) {
+                if (mine) for (int k = 1; k <= rep; k++) {
+                    lps = bin != (s1 & 1); p = s1 >> 1;
+                    ring.rec[(at + k) & (CABAC_RING - 1)] = make_uint4(t.range_lps[p], (uint32_t)lps << 31, lps ? t.lps_range[p] : 0u, lps ? t.lps_shift[p] : 0u);
+                    nx = t.next[s1]; s1 = lps ? nx >> 8 : nx & 255;
                 }
-                t.state[ctx] = (uint8_t)st;
             }
-            __syncwarp();
+            if (mine) st = s1;
+            if (mine && closes) t.state[ctx] = (uint8_t)st;
+            const int handed = __shfl_sync(0xffffffffu, st, pred);
+            if (regular && rank == r + 1) st = handed;
         }
         t_turn += CT_CLK() - t1; n_turn += turns + 1;
         if (valid && !regular && !final) {
             if (ctx == 276) ring.rec[at & (CABAC_RING - 1)] = make_uint4(0x02020202u, 0u, 0u, 0u);
-            else { const int k = ctx - CABAC_BYPASS0; ring.rec[at & (CABAC_RING - 1)] = make_uint4(0u, (uint32_t)k | (((v >> 10) & ((1u << k) - 1u)) << 8), 0u, 0u); }
+            else { const int k = ctx - CABAC_BYPASS0; ring.rec[at & (CABAC_RING - 1)] = make_uint4(0u, (v >> 10) & ((1u << k) - 1u), 0u, 0x01010101u * (uint32_t)k); }
         }
         __threadfence_block(); __syncwarp();
         wr += (uint32_t)total;
@@ -406,31 +420,34 @@ __device__ __forceinline__ void cabac_produce(CabacRing &ring, CabacTables &t, c
     if (lane == 0) { ring.done = 1; CT_ADD(3, CT_CLK() - t_begin); CT_ADD(4, t_wait); CT_ADD(5, t_turn); CT_ADD(6, (n + 31) / 32); CT_ADD(7, n_turn); }
 }
 
-// bytes leave the range/low recurrence as 9-bit values (a byte and the carry into the earlier ones) through a second queue; the
-// writer thread resolves the carries and stores the bytes. 0xFFFF = the slice is flushed.
+// bytes leave the range/low recurrence through a second queue as 16-bit values: the new byte and, above it, the byte before it READ AGAIN
+// (low is never masked, so a carry that arrived since shows as a changed upper byte); the writer thread turns that into carries, holds
+// back the last byte that is not 0xFF and stores the bytes.
 #define CABAC_OUTQ 1024
 struct CabacOutQ { uint16_t v[CABAC_OUTQ]; volatile uint32_t wr, rd; volatile int done; };
 
-// one record of the ring through the recurrence, without a branch; bytes go to the queue (qw = private write index)
-__device__ __forceinline__ void cabac_step(const uint4 rec, uint32_t &low, uint32_t &range, int &nb, CabacOutQ &oq, uint32_t &qw)
+// one record of the ring through the recurrence, without a branch but the one around the byte store; oq_base = shared-space address of
+// the queue, qw = private write index
+__device__ __forceinline__ void cabac_step(const uint4 rec, uint32_t &low, uint32_t &range, int &nb, uint32_t oq_base, uint32_t &qw)
 {
     const uint32_t sel = range >> 6;                                        // 4..7: byte qCodIRangeIdx of the second PRMT operand
     const uint32_t rmps = range - __byte_perm(0u, rec.x, sel);
     const bool lps = (int)rec.y < 0;
     const uint32_t one = rmps < 256u;                                       // after an MPS at most one shift
-    const uint32_t sh = lps ? __byte_perm(0u, rec.w, sel) : max(one, __byte_perm(rec.y, 0u, 0x4440u));
-    low = ((low + (lps ? rmps : 0u)) << sh) + __byte_perm(rec.y, 0u, 0x4441u) * range;
+    const uint32_t sh = max(__byte_perm(0u, rec.w, sel), one);              // LPS: its shift (>= 1 >= one); bypass: the bin count; MPS: one
+    low = ((low + (lps ? rmps : 0u)) << sh) + (rec.y & 63u) * range;        // bypass value * range (0 for regular bins)
     range = lps ? 256u | __byte_perm(0u, rec.z, sel) : rmps << one;
     nb += (int)sh;
-    const bool full = nb >= 8;
-    nb -= full ? 8 : 0;
-    if (full) oq.v[qw & (CABAC_OUTQ - 1)] = (uint16_t)(low >> (nb + 10));
-    low &= full ? (1u << (nb + 10)) - 1u : 0xffffffffu;
-    qw += full;
+    if (nb >= 8) {
+        nb -= 8;
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(oq_base + ((qw & (CABAC_OUTQ - 1)) << 1)), "h"((unsigned short)(low >> (nb + 10))) : "memory");
+        qw++;
+    }
 }
 // the calling thread drains the ring until the producer is done
 __device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
 {
+    const uint32_t oq_base = (uint32_t)__cvta_generic_to_shared(oq.v);
     uint32_t low = 0, range = 510; int nb = -1;
     uint32_t rd = 0, qw = 0;
     [[maybe_unused]] const long long t_begin = CT_CLK(); [[maybe_unused]] long long t_wait = 0;
@@ -448,9 +465,9 @@ __device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
 #pragma unroll
             for (int i = 0; i < 8; i++) r[i] = ring.rec[(rd + i) & (CABAC_RING - 1)];
 #pragma unroll
-            for (int i = 0; i < 8; i++) cabac_step(r[i], low, range, nb, oq, qw);
+            for (int i = 0; i < 8; i++) cabac_step(r[i], low, range, nb, oq_base, qw);
         }
-        for (; avail; avail--, rd++) cabac_step(ring.rec[rd & (CABAC_RING - 1)], low, range, nb, oq, qw);
+        for (; avail; avail--, rd++) cabac_step(ring.rec[rd & (CABAC_RING - 1)], low, range, nb, oq_base, qw);
         __threadfence_block();
         ring.rd = rd; oq.wr = qw;
     }
@@ -459,8 +476,7 @@ __device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
         int width = nb + 10; const int pad = (8 - (width & 7)) & 7;
         low <<= pad; width += pad;                                          // rbsp_alignment_zero_bit
         while (qw + 8u - oq.rd > CABAC_OUTQ) __nanosleep(32);
-        while (width >= 8) { width -= 8; oq.v[qw++ & (CABAC_OUTQ - 1)] = (uint16_t)(low >> width); low &= (1u << width) - 1u; }
-        oq.v[qw++ & (CABAC_OUTQ - 1)] = 0xFFFFu;
+        while (width >= 8) { width -= 8; oq.v[qw++ & (CABAC_OUTQ - 1)] = (uint16_t)(low >> width); }
         __threadfence_block();
         oq.wr = qw;
     }
@@ -471,14 +487,19 @@ __device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
 // the calling thread turns the queue into bytes
 template <bool SWAP> __device__ __forceinline__ void cabac_write(CabacOutQ &oq, CabacOut<SWAP> &o)
 {
-    uint32_t rd = 0;
+    uint32_t rd = 0; int last = -1;                        // the byte taken before this one, as it was then
     for (;;) {
         uint32_t wr = oq.wr;
         if (wr == rd) { if (oq.done) { wr = oq.wr; if (wr == rd) break; } else { __nanosleep(64); continue; } }
         __threadfence_block();
-        for (; rd != wr; rd++) { const int v = oq.v[rd & (CABAC_OUTQ - 1)]; if (v == 0xFFFF) o.finish(); else o.byte(v); }
+        for (; rd != wr; rd++) {
+            const int v = oq.v[rd & (CABAC_OUTQ - 1)], cur = v & 255;
+            const int carry = last >= 0 && (v >> 8) != last;       // the byte before changed (by one): a carry went through it
+            o.byte(cur | (carry << 8)); last = cur;
+        }
         oq.rd = rd;
     }
+    o.finish();
 }
 
 // 96 threads: warp 1 produces records, lane 0 of warp 0 runs the recurrence, lane 0 of warp 2 writes the bytes. bins[0..n) is one slice's list.
