@@ -49,6 +49,9 @@ def apply_workload(args):
                 setattr(args, k, v)
         else:
             g[k] = v
+    if getattr(args, "slices", None) is not None:
+        g["SLICES"] = args.slices
+        g["LABEL"] += f" [slices overridden: {args.slices}]"
     if args.sessions is None:
         args.sessions = 96
     if args.groups is None:
@@ -381,6 +384,7 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--sessions", type=int, default=None)
     ap.add_argument("--groups", type=int, default=None)
+    ap.add_argument("--slices", type=int, default=None, help="override the workload's slice count (0 = the engine's automatic count)")
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--threads-e2e", action="store_true", help="also measure one caller thread per session through the auto_batch scheduler")

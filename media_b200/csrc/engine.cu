@@ -29,7 +29,7 @@
 #include <vector>
 
 using namespace b200;
-#define B200_CABAC_SMEM_KB 0
+#define B200_CABAC_SMEM_KB 100   /* default slab for the coder CTAs (see k_cabac_code launch); B200ENC_CABAC_SMEM_KB overrides */
 
 namespace {
 
