@@ -202,10 +202,18 @@ namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int cabac_slab_kb()
+{
+    static const int kb = [] { const char *e = getenv("B200ENC_CABAC_SMEM_KB"); return std::min(std::max(e ? atoi(e) : B200_CABAC_SMEM_KB, 0), 180); }();
+    return kb;
+}
+
 int batch_init(b200enc_batch *b, int device, int cap)
 {
     b->device = device; b->cap = cap;
     CU_TRY(cudaSetDevice(device), return B200ENC_ENODEV);
+    // function attributes are per device: every batch context sets the coder's dynamic shared-memory limit on its own device
+    if (cabac_slab_kb() > 0) CU_TRY(cudaFuncSetAttribute(k_cabac_code, cudaFuncAttributeMaxDynamicSharedMemorySize, cabac_slab_kb() * 1024), return B200ENC_ENODEV);
     CU_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), return B200ENC_ENODEV);
     CU_TRY(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking), return B200ENC_ENODEV);
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -358,8 +366,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         pf.begin("k_cabac_bins", s2); k_cabac_bins<1><<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
         // the coder threads are latency chains: every slot they lose to a co-resident throughput kernel's warps stretches the frame. Asking for
         // a slab of dynamic shared memory they do not use keeps the shared-memory-hungry kernels of the other batches off their SMs
-        static const int hog_kb = [] { const char *e = getenv("B200ENC_CABAC_SMEM_KB"); const int kb = e ? atoi(e) : B200_CABAC_SMEM_KB;
-                                       if (kb > 0) cudaFuncSetAttribute(k_cabac_code, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024); return kb; }();
+        const int hog_kb = cabac_slab_kb();
         pf.begin("k_cabac_code", s2); k_cabac_code<<<dim3(g.num_slices, 1, n), 96, (size_t)hog_kb * 1024, s2>>>(b->d_sess, g); pf.end();
         launches += 5;
     } else {
