@@ -61,7 +61,7 @@ typedef struct b200enc_config {
                               IDR instead (the wrapper asks openh264 for bEnableSceneChangeDetect, VideoEncoderOpenH264.cpp:283) */
     int auto_batch;        /* 1: concurrent b200enc_encode calls of sessions living on the same GPU are coalesced by a per-GPU
                               scheduler thread into one batch step (what gives many single-threaded callers GPU-wide throughput) */
-    int profile;           /* 0: Constrained Baseline, CAVLC; 1: Main, CABAC; 2: High, CABAC (4x4 transform) -- the wrapper's profile property
+    int profile;           /* 0: Constrained Baseline, CAVLC; 1: Main, CABAC; 2: High, CABAC, 8x8 transform on inter MBs (transform_8x8_mode_flag) -- the wrapper's profile property
                               baseline / main / high (VideoEncoderOpenH264.cpp:186-188,248-253) with iEntropyCodingModeFlag = 1 (:291) */
 } b200enc_config;
 
@@ -141,6 +141,8 @@ int b200k_downsample2(int device, const uint8_t *in, int width, int height, uint
 int b200k_sad16x16(int device, const uint8_t *cur, const uint8_t *ref, int stride, int n_blocks, const int32_t *xy /* 4 ints per block: cx, cy, rx, ry */, int32_t *sad);
 int b200k_satd16x16(int device, const uint8_t *cur, const uint8_t *ref, int stride, int n_blocks, const int32_t *xy, int32_t *satd);
 int b200k_transform_block(int device, const int16_t *residual /* n*16 */, int n, int qp, int intra, int16_t *levels_zz /* n*16 */, int32_t *recon_residual /* n*16 */);
+/* the 8x8 transform chain of the High profile (residual -> transform -> quant -> 8.5.13 scaling / inverse): n blocks of 64 */
+int b200k_transform_block8(int device, const int16_t *residual /* n*64 raster */, int n, int qp, int intra, int16_t *levels_zz /* n*64, 8x8 zig-zag */, int32_t *recon_residual /* n*64 */);
 int b200k_deblock(int device, uint8_t *i420_coded, int mbw, int mbh, const void *mbinfo, int qp);
 /* the CABAC arithmetic coder (9.3.4.2) on a bin list ending with a terminate bin of value 1 (entry format: oracle/orc.h) */
 int b200k_cabac_code(int device, const uint16_t *bins, int n, int qp, int is_p, uint8_t *out, int cap, int *out_len);

@@ -8,6 +8,7 @@
 #include "h264_dev.cuh"
 #include "k_pre.cuh"
 #include "k_me.cuh"
+#include "k_t8.cuh"
 #include "k_intra.cuh"
 #include "k_deblock.cuh"
 #include "k_cavlc.cuh"
@@ -85,7 +86,8 @@ int level_for(int w, int h, int fps)   // Table A-1: smallest level whose MaxFS 
     for (auto &l : L) if (fs <= l.fs && mbps <= l.mbps) return l.idc;
     return 52;
 }
-// profile: 0 Constrained Baseline / CAVLC, 1 Main / CABAC, 2 High / CABAC (4x4 transform only; 7.3.2.1.1 adds the chroma format fields)
+// profile: 0 Constrained Baseline / CAVLC, 1 Main / CABAC, 2 High / CABAC with transform_8x8_mode_flag (7.3.2.1.1 adds the chroma
+// format fields to the SPS, 7.3.2.2 the transform / scaling-matrix / second chroma offset tail to the PPS)
 std::vector<uint8_t> make_parameter_sets(int w, int h, int level, int profile)
 {
     std::vector<uint8_t> out;
@@ -103,7 +105,9 @@ std::vector<uint8_t> make_parameter_sets(int w, int h, int level, int profile)
     append_nal(out, 0x67, s.buf);
     HostBits p;
     p.ue(0); p.ue(0); p.put(1, profile ? 1 : 0); p.put(1, 0); p.ue(0); p.ue(0); p.ue(0); p.put(1, 0); p.put(2, 0);
-    p.se(0); p.se(0); p.se(0); p.put(1, 1); p.put(1, 0); p.put(1, 0); p.trailing();
+    p.se(0); p.se(0); p.se(0); p.put(1, 1); p.put(1, 0); p.put(1, 0);
+    if (profile == 2) { p.put(1, 1); p.put(1, 0); p.se(0); }
+    p.trailing();
     append_nal(out, 0x68, p.buf);
     return out;
 }
@@ -312,6 +316,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
         d.qp = qp; d.is_idr = idr; d.frame_num = s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format; d.scene_change = s->cfg.scene_change && !idr;
+        d.t8x8 = s->cfg.profile == 2;
         d.rbsp_words_per_slice = s->rbsp_words_per_slice; d.out_cap = s->out_cap;
     }
     CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
@@ -344,6 +349,9 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         pf.begin("k_me_fine"); k_me_fine<<<dim3((nmb + ME_WARPS - 1) / ME_WARPS, 1, n), ME_WARPS * 32, 0, st>>>(b->d_sess, g, b->d_ctl); pf.end();
         pf.begin("k_scene_change"); k_scene_change<<<n, 256, 0, st>>>(b->d_sess, g); pf.end();
         launches += 7;
+        bool any_t8 = false;
+        for (int i = 0; i < n; i++) any_t8 |= ss[i]->cfg.profile == 2;
+        if (any_t8) { pf.begin("k_inter_t8"); k_inter_t8<<<dim3((nmb + T8_WARPS - 1) / T8_WARPS, 1, n), T8_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end(); launches++; }
     }
     const int wave_ctas = (n * g.mbh + WAVE_WARPS - 1) / WAVE_WARPS;
     pf.begin("k_intra_wave"); k_intra_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;

@@ -13,7 +13,7 @@ enum { MB_P16x16 = 0, MB_I16x16 = 1, MB_I4x4 = 2, MB_PSKIP = 3, MB_P8x8 = 4 };
 
 // Per-MB side information, 48 bytes. nnz: 0..15 luma blkIdx, 16..19 Cb, 20..23 Cr.
 struct __align__(16) MbInfo {
-    uint8_t mb_type, i16_mode, chroma_mode, cbp;
+    uint8_t mb_type, i16_mode, chroma_mode, cbp;   // i16_mode: bits 0..1 Intra16x16PredMode, bit 2 transform_size_8x8_flag (inter MBs)
     int16_t mv[2];                // the 16x16 vector (partition 0 for P_8x8)
     union {
         uint8_t i4_mode[16];      // intra MBs: Intra4x4PredMode per blkIdx
@@ -23,7 +23,7 @@ struct __align__(16) MbInfo {
 };
 // Per-MB quantised levels in zig-zag order, 816 bytes.
 struct __align__(16) MbCoef {
-    int16_t luma[16][16];
+    int16_t luma[16][16];         // with transform_size_8x8_flag: luma[4*b8 .. 4*b8+3] = the 64 levels of 8x8 block b8, 8x8 zig-zag order
     int16_t luma_dc[16];
     int16_t chroma_dc[2][4];
     int16_t chroma_ac[2][4][16];
@@ -87,6 +87,7 @@ struct Sess {
     int *row_prog_intra, *row_prog_dbk; // wavefront progress counters, one per MB row
     int qp, is_idr, frame_num, idr_pic_id, input_format;
     int scene_change;             // 1: k_scene_change may turn this P picture into an IDR (then is_idr / frame_num are rewritten on the device)
+    int t8x8;                     // 1: PPS transform_8x8_mode_flag (High profile): inter MBs may take the 8x8 transform (k_inter_t8)
     uint32_t rbsp_words_per_slice, out_cap;
 };
 
@@ -203,6 +204,7 @@ __device__ __forceinline__ int pos_class(int pos) { return ((pos & 1) && (pos & 
 __device__ __forceinline__ int se_len(int v) { unsigned x = (v > 0 ? 2u * v - 1u : (unsigned)(-2 * v)) + 1u; return 2 * (31 - __clz(x)) + 1; }
 __device__ __forceinline__ int ue_len(unsigned v) { return 2 * (31 - __clz(v + 1u)) + 1; }
 __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+__device__ __forceinline__ bool mb_t8(const MbInfo *m) { return (m->i16_mode >> 2) & 1; }   // transform_size_8x8_flag
 __device__ __forceinline__ bool row_is_slice_top(const Geom &g, int my) { return (g.slice_top[my >> 5] >> (my & 31)) & 1u; }
 
 // forward core transform of a 4x4 residual held in registers (role of WelsDctT4_c)

@@ -97,6 +97,41 @@ template <int W> __device__ void bin_residual(BinSink<W> &s, const int16_t *lv, 
     }
 }
 
+// Table 9-43 (frame coded blocks): ctxIdxInc of significant_coeff_flag / last_significant_coeff_flag of ctxBlockCat 5 by levelListIdx
+static __device__ __constant__ uint8_t c_cabac_sig8[63] = {
+    0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7,
+    7, 6, 11, 12, 13, 11, 6, 7, 8, 9, 14, 10, 9, 8, 6, 11, 12, 13, 11, 6, 9, 14, 10, 9, 11, 12, 13, 11, 14, 10, 12 };
+static __device__ __constant__ uint8_t c_cabac_last8[63] = {
+    0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2,
+    3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8 };
+// residual_block_cabac of an 8x8 luma block (ctxBlockCat 5, 64 levels in 8x8 zig-zag order read from the MB's coefficient record): no
+// coded_block_flag (inferred 1 with the cbp bit); significance map contexts 402.. / 417.., magnitudes 426..
+template <int W> __device__ void bin_residual8(BinSink<W> &s, const int16_t *lv)
+{
+    int last = -1;
+    for (int i = 0; i < 64; i++) if (lv[i]) last = i;
+    for (int i = 0; i < 63; i++) {
+        const int v = lv[i];
+        s.put(402 + c_cabac_sig8[i], v != 0);
+        if (v) { s.put(417 + c_cabac_last8[i], i == last); if (i == last) break; }
+    }
+    int eq1 = 0, gt1 = 0;
+    for (int i = last; i >= 0; i--) {
+        const int v = lv[i];
+        if (!v) continue;
+        const int a = abs(v) - 1;
+        s.put(426 + (gt1 ? 0 : min(4, 1 + eq1)), a > 0);
+        uint32_t bits = (uint32_t)(v < 0); int len = 1;
+        if (a > 0) {
+            const int inc = 5 + min(4, gt1);
+            if (min(a, 14) > 1) s.run(426 + inc, 1, min(a, 14) - 1);
+            if (a < 14) s.put(426 + inc, 0); else egk_sign(a - 14, 0, v < 0, bits, len);
+            gt1++;
+        } else eq1++;
+        s.bypass(bits, len);
+    }
+}
+
 __device__ __forceinline__ bool is_intra_type(int t) { return t == MB_I16x16 || t == MB_I4x4; }
 
 // grid: (ceil(n_mb / 256), 1, sessions)
@@ -168,6 +203,9 @@ template <int W> __device__ void bin_mb_header(BinSink<W> &s, const Sess &se, co
             s.put(c_m1, m->i16_mode >> 1); s.put(c_m0, m->i16_mode & 1);
         }
     }
+    // transform_size_8x8_flag (7.3.5; ctxIdx 399 + the neighbours' flags): 0 for I_NxN (Intra_4x4 only), coded for inter MBs behind the cbp
+    const int t8inc = (L && mb_t8(L)) + (T && mb_t8(T));
+    if (t == MB_I4x4 && se.t8x8) s.put(399 + t8inc, 0);
     if (t == MB_I4x4)
         for (int k = 0; k < 16; k++) {
             const int r = sd->i4_syn[k];
@@ -197,6 +235,7 @@ template <int W> __device__ void bin_mb_header(BinSink<W> &s, const Sess &se, co
         s.put(77 + (L && (L->cbp >> 4)) + 2 * (T && (T->cbp >> 4)), cc != 0);
         if (cc) s.put(81 + (L && (L->cbp >> 4) == 2) + 2 * (T && (T->cbp >> 4) == 2), cc == 2);
     }
+    if (!intra && cl && se.t8x8) s.put(399 + t8inc, mb_t8(m));              // every inter MB here has partitions of 8x8 at least
     if (t == MB_I16x16 || m->cbp) s.put(60, 0);                              // mb_qp_delta = 0
 }
 
@@ -220,7 +259,9 @@ __device__ __forceinline__ CabacItem cabac_item(const Sess &se, const Geom &g, i
         if (bx) a = m->nnz[xy2blk(bx - 1, by)] != 0; else if (L) a = L->nnz[xy2blk(3, by)] != 0;
         if (by) b = m->nnz[xy2blk(bx, by - 1)] != 0; else if (T) b = T->nnz[xy2blk(bx, 3)] != 0;
         it.present = (cl >> (k >> 2)) & 1;
-        if (i16) { it.lv = co->luma[k] + 1; it.n = 15; it.cat = 1; } else { it.lv = co->luma[k]; it.n = 16; it.cat = 2; }
+        if (i16) { it.lv = co->luma[k] + 1; it.n = 15; it.cat = 1; }
+        else if (mb_t8(m)) { it.lv = co->luma[k]; it.n = 64; it.cat = 5; it.present = it.present && !(k & 3); }   // the lane of an 8x8 block's first 4x4 codes all of it
+        else { it.lv = co->luma[k]; it.n = 16; it.cat = 2; }
     } else if (lane < 20) {
         const int p = lane - 18;
         if (L) a = (L->cbp >> 4) && ((sL->dc_cbf >> (1 + p)) & 1);
@@ -249,7 +290,7 @@ template <int WRITE> __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac
     const int mx = mb % g.mbw, my = mb / g.mbw;
     __align__(16) int16_t lv[16];
     CabacItem it = cabac_item(s, g, mx, my, lane, mi, co);
-    if (lane >= 1 && lane < 28 && it.present)
+    if (lane >= 1 && lane < 28 && it.present && it.cat != 5)
         for (int i = 0; i < it.n; i++) lv[i] = it.lv[i];
     int sl = 0;
     for (int k = 1; k < g.num_slices; k++) sl += (my >= g.slice_row0[k]);
@@ -258,7 +299,7 @@ template <int WRITE> __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac
     {
         BinSink<0> bs; bs.p = nullptr; bs.n = 0;
         if (lane == 0) bin_mb_header<0>(bs, s, g, mx, my, mi);
-        else if (lane < 28) { if (it.present) bin_residual<0>(bs, lv, it.n, it.cat, it.inc); }
+        else if (lane < 28) { if (it.present) { if (it.cat == 5) bin_residual8<0>(bs, it.lv); else bin_residual<0>(bs, lv, it.n, it.cat, it.inc); } }
         else if (lane == 28) bs.put(276, last_mb);
         cnt = bs.n;
     }
@@ -268,7 +309,7 @@ template <int WRITE> __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac
     if (!WRITE) { if (lane == 31) s.mb_bits[mb] = (uint32_t)incl; return; }
     BinSink<1> bs; bs.p = s.bins + (size_t)g.slice_row0[sl] * g.mbw * B200_MB_BIN_SLOT + s.mb_off[mb] + (incl - cnt); bs.n = 0;
     if (lane == 0) bin_mb_header<1>(bs, s, g, mx, my, mi);
-    else if (lane < 28) { if (it.present) bin_residual<1>(bs, lv, it.n, it.cat, it.inc); }
+    else if (lane < 28) { if (it.present) { if (it.cat == 5) bin_residual8<1>(bs, it.lv); else bin_residual<1>(bs, lv, it.n, it.cat, it.inc); } }
     else if (lane == 28) bs.put(276, last_mb);
 }
 

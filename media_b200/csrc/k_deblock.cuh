@@ -146,7 +146,8 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
         if (e == 0) {
             if (vert) bs = mx > 0 ? bs_of(sm.mbi[1], 3, k, sm.mbi[0], 0, k, true) : 0;
             else bs = my > 0 ? bs_of(sm.mbi[2], k, 3, sm.mbi[0], k, 0, true) : 0;
-        } else bs = vert ? bs_of(sm.mbi[0], e - 1, k, sm.mbi[0], e, k, false) : bs_of(sm.mbi[0], k, e - 1, sm.mbi[0], k, e, false);
+        } else if ((e & 1) && ((sm.mbi[0][0] >> 10) & 1u)) bs = 0;      // transform_size_8x8_flag: only the 8x8 transform edges are filtered
+        else bs = vert ? bs_of(sm.mbi[0], e - 1, k, sm.mbi[0], e, k, false) : bs_of(sm.mbi[0], k, e - 1, sm.mbi[0], k, e, false);
     }
     DBK_T(1);
     if (__ballot_sync(0xffffffffu, bs != 0) == 0) return false;

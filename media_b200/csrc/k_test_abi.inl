@@ -91,6 +91,20 @@ int b200k_transform_block(int device, const int16_t *res, int n, int qp, int int
     return B200ENC_OK;
 }
 
+int b200k_transform_block8(int device, const int16_t *res, int n, int qp, int intra, int16_t *levels, int32_t *recon)
+{
+    if (!res || !levels || !recon || n <= 0 || qp < 0 || qp > 51) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    DevBuf dres((size_t)n * 128), dlev((size_t)n * 128), drec((size_t)n * 256);
+    if (!dres.p || !dlev.p || !drec.p) return B200ENC_ENOMEM;
+    K_TRY(cudaMemcpy(dres.p, res, (size_t)n * 128, cudaMemcpyHostToDevice));
+    k_test_transform8<<<(n + 4 * T8_WARPS - 1) / (4 * T8_WARPS), T8_WARPS * 32>>>(dres.as<int16_t>(), n, qp, intra, dlev.as<int16_t>(), drec.as<int>());
+    K_TRY(cudaGetLastError());
+    K_TRY(cudaMemcpy(levels, dlev.p, (size_t)n * 128, cudaMemcpyDeviceToHost));
+    K_TRY(cudaMemcpy(recon, drec.p, (size_t)n * 256, cudaMemcpyDeviceToHost));
+    return B200ENC_OK;
+}
+
 int b200k_deblock(int device, uint8_t *i420, int mbw, int mbh, const void *mbinfo, int qp)
 {
     if (!i420 || !mbinfo || mbw <= 0 || mbh <= 0 || qp < 0 || qp > 51) return B200ENC_EINVAL;

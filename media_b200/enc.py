@@ -83,6 +83,7 @@ def lib():
         L.b200k_sad16x16.restype = C.c_int; L.b200k_sad16x16.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, vp, vp]
         L.b200k_satd16x16.restype = C.c_int; L.b200k_satd16x16.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, vp, vp]
         L.b200k_transform_block.restype = C.c_int; L.b200k_transform_block.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        L.b200k_transform_block8.restype = C.c_int; L.b200k_transform_block8.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]
         L.b200k_deblock.restype = C.c_int; L.b200k_deblock.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int]
         L.b200k_cabac_code.restype = C.c_int; L.b200k_cabac_code.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
         L.b200k_vabsdiff4_peak.restype = C.c_int; L.b200k_vabsdiff4_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]

@@ -33,7 +33,8 @@ enum { ORC_MB_P16x16 = 0, ORC_MB_I16x16 = 1, ORC_MB_I4x4 = 2, ORC_MB_PSKIP = 3, 
 
 /* Per-MB coefficient record: everything CAVLC needs, 816 bytes. Levels are in zig-zag scan order. */
 typedef struct {
-    int16_t luma[16][16];    /* [blkIdx][scan]; for I16x16 index 0 of each block is unused (AC only) */
+    int16_t luma[16][16];    /* [blkIdx][scan]; for I16x16 index 0 of each block is unused (AC only); with transform_size_8x8_flag
+                                luma[4*b8] .. luma[4*b8+3] hold the 64 levels of 8x8 block b8 in 8x8 zig-zag order */
     int16_t luma_dc[16];     /* I16x16 only: Intra16x16DCLevel in scan order */
     int16_t chroma_dc[2][4]; /* [plane][c] raster order of the 2x2 block */
     int16_t chroma_ac[2][4][16]; /* [plane][blk][scan], index 0 unused */
@@ -41,7 +42,7 @@ typedef struct {
 
 typedef struct {
     uint8_t  mb_type;        /* ORC_MB_* */
-    uint8_t  i16_mode;       /* Intra16x16PredMode 0..3 */
+    uint8_t  i16_mode;       /* bits 0..1 Intra16x16PredMode; bit 2 transform_size_8x8_flag (inter MBs of High-profile streams) */
     uint8_t  chroma_mode;    /* intra_chroma_pred_mode 0..3 */
     uint8_t  cbp;            /* bits 0..3 luma 8x8, bits 4..5 chroma (0,1,2) */
     int16_t  mv[2];          /* quarter-pel; the 16x16 vector (partition 0 for P_8x8) */
@@ -79,9 +80,11 @@ typedef struct {
     int no_i4x4;             /* 1: Intra_16x16 only (quality A/B runs in tests; the product has no such switch) */
     int no_p8x8;             /* 1: P_L0_16x16 only (same purpose) */
     int no_scene_change;     /* 1: never turn a P frame into an IDR (b200enc_config.scene_change = 0) */
-    int profile;             /* 0 Constrained Baseline / CAVLC; 1 Main / CABAC; 2 High / CABAC (4x4 transform only), the wrapper's
-                                persist.vmi.video.encode.profile values (VideoEncoderOpenH264.cpp:248-253) */
+    int profile;             /* 0 Constrained Baseline / CAVLC; 1 Main / CABAC; 2 High / CABAC with the 8x8 transform on inter MBs, the
+                                wrapper's persist.vmi.video.encode.profile values (VideoEncoderOpenH264.cpp:248-253) */
+    int no_t8x8;             /* 1: High profile without the 8x8 transform (transform_8x8_mode_flag = 0; quality A/B runs) */
 } OrcConfig;
+#define ORC_MB_T8(m) (((m)->i16_mode >> 2) & 1)
 
 OrcEncoder *orc_create(const OrcConfig *cfg);
 void orc_destroy(OrcEncoder *e);
@@ -114,7 +117,7 @@ int orc_cabac_code_bins(const uint16_t *bins, int n, int slice_qp, int is_p, uin
 
 /* ---- headers ---- */
 int orc_write_sps(uint8_t *out, int width, int height, int level_idc, int profile);
-int orc_write_pps(uint8_t *out, int profile);
+int orc_write_pps(uint8_t *out, int profile, int transform8x8);
 int orc_level_for(int width, int height, int fps);
 
 /* ---- kernel-level oracles (bit-exact targets of the per-kernel C-ABI entry points) ---- */
@@ -126,6 +129,12 @@ void orc_idct4x4(const int32_t *d /*16 raster dequantised*/, int32_t *r /*16 ras
 /* quantise raster coef -> zigzag levels; intra selects the dead-zone; ac_only skips position 0. Returns nnz */
 int  orc_quant4x4(const int16_t *coef, int16_t *level_zz, int qp, int intra, int ac_only);
 void orc_dequant4x4(const int16_t *level_zz, int32_t *d, int qp, int ac_only);
+/* 8x8 transform of the High profile: forward transform (rows, then columns), quantiser (64 levels in 8x8 zig-zag order; returns nnz),
+ * 8.5.13 scaling and inverse transform ((x+32)>>6 applied) */
+void orc_dct8x8(const int16_t *res /*64 raster*/, int32_t *coef /*64 raster*/);
+int  orc_quant8x8(const int32_t *coef, int16_t *level_zz, int qp, int intra);
+void orc_dequant8x8(const int16_t *level_zz, int32_t *d, int qp);
+void orc_idct8x8(const int32_t *d, int32_t *r);
 void orc_rgba_to_i420(const uint8_t *rgba, int width, int height, uint8_t *i420);
 void orc_nv12_to_i420(const uint8_t *nv12, int width, int height, uint8_t *i420);
 void orc_downsample2(const uint8_t *src, int sstride, int w, int h, uint8_t *dst, int dstride);

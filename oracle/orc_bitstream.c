@@ -94,7 +94,7 @@ int orc_write_sps(uint8_t *out, int width, int height, int level_idc, int profil
     return finish_nal(out, 0x67, tmp, b.pos);
 }
 
-int orc_write_pps(uint8_t *out, int profile)
+int orc_write_pps(uint8_t *out, int profile, int transform8x8)
 {
     uint8_t tmp[32]; BitWriter b; bw_init(&b, tmp, sizeof tmp);
     bw_ue(&b, 0); bw_ue(&b, 0);   /* pps id, sps id */
@@ -110,6 +110,11 @@ int orc_write_pps(uint8_t *out, int profile)
     bw_put(&b, 1, 1);             /* deblocking_filter_control_present_flag */
     bw_put(&b, 1, 0);             /* constrained_intra_pred_flag */
     bw_put(&b, 1, 0);             /* redundant_pic_cnt_present_flag */
+    if (transform8x8) {           /* High profile tail of 7.3.2.2 */
+        bw_put(&b, 1, 1);         /* transform_8x8_mode_flag */
+        bw_put(&b, 1, 0);         /* pic_scaling_matrix_present_flag */
+        bw_se(&b, 0);             /* second_chroma_qp_index_offset */
+    }
     bw_trailing(&b);
     return finish_nal(out, 0x68, tmp, b.pos);
 }

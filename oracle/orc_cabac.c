@@ -14,6 +14,7 @@
  */
 #include "orc_internal.h"
 #include "cabac_tables.h"
+#include "h264_tables.h"
 #include <stdlib.h>
 
 typedef struct { uint16_t *p; int n, cap; } Bins;
@@ -89,6 +90,32 @@ static void put_residual(Bins *s, const int16_t *c, int n, int cat, int cbf_inc)
     }
 }
 
+/* residual_block_cabac for ctxBlockCat 5 (8x8 luma block, 64 levels): no coded_block_flag (inferred 1 with the cbp bit); the
+ * significance map contexts come from Table 9-43 */
+static void put_residual8(Bins *s, const int16_t *c)
+{
+    int last = -1;
+    for (int i = 0; i < 64; i++) if (c[i]) last = i;
+    for (int i = 0; i < 63; i++) {
+        put(s, 402 + CABAC_SIG8[i], c[i] != 0);
+        if (c[i]) { put(s, 417 + CABAC_LAST8[i], i == last); if (i == last) break; }
+    }
+    int eq1 = 0, gt1 = 0;
+    for (int i = last; i >= 0; i--) {
+        if (!c[i]) continue;
+        int a = iabs(c[i]) - 1, base = 426;
+        put(s, base + (gt1 ? 0 : imin(4, 1 + eq1)), a > 0);
+        uint32_t bits = (uint32_t)(c[i] < 0); int len = 1;
+        if (a > 0) {
+            int inc = 5 + imin(4, gt1);
+            if (imin(a, 14) > 1) put_run(s, base + inc, 1, imin(a, 14) - 1);
+            if (a < 14) put(s, base + inc, 0); else egk_sign(a - 14, 0, c[i] < 0, &bits, &len);
+            gt1++;
+        } else eq1++;
+        put_bypass(s, bits, len);
+    }
+}
+
 #define IS_INTRA(m) ((m)->mb_type == ORC_MB_I16x16 || (m)->mb_type == ORC_MB_I4x4)
 static const uint8_t XY2BLK[4][4] = { { 0, 1, 4, 5 }, { 2, 3, 6, 7 }, { 8, 9, 12, 13 }, { 10, 11, 14, 15 } };
 static const uint8_t BX[16] = { 0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3 }, BY[16] = { 0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3 };
@@ -99,7 +126,7 @@ static int nb_cbf_cac(const OrcMbInfo *nb, int idx, int cur_intra) { return nb ?
 
 /* Bins of one macroblock; mb_skip_flag and end_of_slice_flag included. last = 1 for the last MB of the slice. */
 int orc_cabac_mb_bins(const OrcMbInfo *mbi, const OrcMbCoef *coef, const OrcMbSide *side, int mbw, int mx, int my, int top_avail,
-                      int is_p, int last, uint16_t *out, int cap)
+                      int is_p, int last, int transform8x8, uint16_t *out, int cap)
 {
     Bins s = { out, 0, cap };
     int mb = my * mbw + mx;
@@ -127,6 +154,9 @@ int orc_cabac_mb_bins(const OrcMbInfo *mbi, const OrcMbCoef *coef, const OrcMbSi
             put(&s, c_m1, m->i16_mode >> 1); put(&s, c_m0, m->i16_mode & 1);
         }
     }
+    /* transform_size_8x8_flag (7.3.5, ctxIdx 399 + the neighbours' flags, 9.3.3.1.1.10): 0 for I_NxN (Intra_4x4 only) */
+    int t8inc = (L && ORC_MB_T8(L)) + (T && ORC_MB_T8(T));
+    if (m->mb_type == ORC_MB_I4x4 && transform8x8) put(&s, 399 + t8inc, 0);
     if (m->mb_type == ORC_MB_I4x4)
         for (int k = 0; k < 16; k++) {                                                     /* prev_intra4x4_pred_mode_flag / rem_intra4x4_pred_mode */
             int r = sd->i4_syn[k];
@@ -160,12 +190,16 @@ int orc_cabac_mb_bins(const OrcMbInfo *mbi, const OrcMbCoef *coef, const OrcMbSi
         put(&s, 77 + (L && (L->cbp >> 4)) + 2 * (T && (T->cbp >> 4)), cc != 0);
         if (cc) put(&s, 81 + (L && (L->cbp >> 4) == 2) + 2 * (T && (T->cbp >> 4) == 2), cc == 2);
     }
+    if (!intra && cl && transform8x8) put(&s, 399 + t8inc, ORC_MB_T8(m));                  /* every inter MB here has 8x8 partitions at least */
     if (m->mb_type == ORC_MB_I16x16 || m->cbp) put(&s, 60, 0);                             /* mb_qp_delta = 0; the previous MB's is 0 too */
     /* residual */
     if (m->mb_type == ORC_MB_I16x16) {
         int a = L ? (L->mb_type == ORC_MB_I16x16 && (sL->dc_cbf & 1)) : 1, b = T ? (T->mb_type == ORC_MB_I16x16 && (sT->dc_cbf & 1)) : 1;
         put_residual(&s, co->luma_dc, 16, 0, a + 2 * b);
     }
+    if (ORC_MB_T8(m)) {
+        for (int b8 = 0; b8 < 4; b8++) if (cl & (1 << b8)) put_residual8(&s, co->luma[4 * b8]);
+    } else
     for (int k = 0; k < 16; k++) {
         if (!(cl & (1 << (k >> 2)))) continue;
         int bx = BX[k], by = BY[k];

@@ -21,6 +21,7 @@
 
 #define ORC_MB_BINS_MAX 4096   /* bound of one MB's bin list: 384 levels of at most 2 + 14 + 27 + 1 bins (|level| <= 2064) is far above real use; checked */
 #define HP_M 4   /* margin of the half-pel planes, see build_halfpel() */
+#define T8X8_ON(e) ((e)->cfg.profile == 2 && !(e)->cfg.no_t8x8)   /* PPS transform_8x8_mode_flag */
 
 struct OrcEncoder {
     OrcConfig cfg;
@@ -433,6 +434,14 @@ static int code_chroma(OrcEncoder *e, int mx, int my, const uint8_t *pred /*2 x 
     return any_ac ? 2 : (any_dc ? 1 : 0);
 }
 
+/* rate estimate of one residual block in half bits: per nonzero level 2 * (3 + min(|level|, 16)) (significance, last, sign, unary
+ * magnitude), 1 per zero before the last nonzero level (a significance flag of ~half a bit) */
+static int level_cost2(const int16_t *lv, int n)
+{
+    int c = 0, last = -1, nz = 0;
+    for (int i = 0; i < n; i++) { int a = iabs(lv[i]); if (a) { c += 2 * (3 + (a < 16 ? a : 16)); last = i; nz++; } }
+    return c + (last + 1 - nz);
+}
 /* ---- Phase B: one inter MB ---- */
 static void code_inter_mb(OrcEncoder *e, int mx, int my, int qp)
 {
@@ -455,6 +464,37 @@ static void code_inter_mb(OrcEncoder *e, int mx, int my, int qp)
         mi->nnz[b] = (uint8_t)n; if (n) cbp |= 1 << (b >> 2);
         orc_dequant4x4(co->luma[b], d, qp, 0); orc_idct4x4(d, rr);
         for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) r[(by + y) * st + bx + x] = (uint8_t)clip255(py[(by + y) * 16 + bx + x] + rr[y * 4 + x]);
+    }
+    /* High profile: the luma residual is coded again with the 8x8 transform (four 8x8 blocks, 8x8 zig-zag levels in luma[4*b8..]) and
+     * the macroblock takes transform_size_8x8_flag = 1 when that wins the rate-distortion comparison J = 64 SSD + 27 lambda^2 B
+     * (lambda_mode = 27/32 lambda^2, B in half bits), at least one 8x8 level being nonzero. */
+    if (T8X8_ON(e) && cbp) {
+        int16_t l8[4][64]; int n8[4], b4 = 0, b8_ = 0, any8 = 0; int64_t d4 = 0, d8 = 0; uint8_t r8[256];
+        for (int b = 0; b < 16; b++) if (cbp & (1 << (b >> 2))) b4 += 1 + level_cost2(co->luma[b], 16);
+        for (int y = 0; y < 16; y++) for (int x = 0; x < 16; x++) { int d = s[y * st + x] - r[y * st + x]; d4 += d * d; }
+        for (int b8 = 0; b8 < 4; b8++) {
+            int ox = (b8 & 1) * 8, oy = (b8 >> 1) * 8; int16_t res[64]; int32_t c[64], d[64], rr[64];
+            for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) res[y * 8 + x] = (int16_t)(s[(oy + y) * st + ox + x] - py[(oy + y) * 16 + ox + x]);
+            orc_dct8x8(res, c);
+            n8[b8] = orc_quant8x8(c, l8[b8], qp, 0); any8 |= n8[b8];
+            b8_ += level_cost2(l8[b8], 64);
+            orc_dequant8x8(l8[b8], d, qp); orc_idct8x8(d, rr);
+            for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+                int v = clip255(py[(oy + y) * 16 + ox + x] + rr[y * 8 + x]), dd = s[(oy + y) * st + ox + x] - v;
+                r8[(oy + y) * 16 + ox + x] = (uint8_t)v; d8 += dd * dd;
+            }
+        }
+        int64_t l2 = 27 * (int64_t)LAMBDA_TAB[qp] * LAMBDA_TAB[qp];
+        if (any8 && 64 * d8 + l2 * (b8_ + 4) < 64 * d4 + l2 * b4) {   /* + 2 bits: the flag's minority value */
+            cbp = 0;
+            for (int b8 = 0; b8 < 4; b8++) {
+                memcpy(co->luma[4 * b8], l8[b8], sizeof l8[b8]);
+                for (int k = 0; k < 4; k++) mi->nnz[4 * b8 + k] = (uint8_t)n8[b8];
+                if (n8[b8]) cbp |= 1 << b8;
+            }
+            for (int y = 0; y < 16; y++) memcpy(r + y * st, r8 + y * 16, 16);
+            mi->i16_mode = 4;      /* transform_size_8x8_flag */
+        }
     }
     cbp |= code_chroma(e, mx, my, pc, qp, 0) << 4;
     mi->cbp = (uint8_t)cbp;
@@ -897,7 +937,7 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
         if (out_cap < 64) return -1;
         int level = e->cfg.level_idc ? e->cfg.level_idc : orc_level_for(e->cfg.width, e->cfg.height, e->cfg.fps);
         o += orc_write_sps(out + o, e->cfg.width, e->cfg.height, level, e->cfg.profile);
-        o += orc_write_pps(out + o, e->cfg.profile);
+        o += orc_write_pps(out + o, e->cfg.profile, T8X8_ON(e));
     }
     if (e->cfg.profile) cabac_side_records(e, is_idr);
     for (int s = 0; s < e->cfg.num_slices; s++) {
@@ -911,7 +951,7 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
             for (int my = r0; my < r1; my++)
                 for (int mx = 0; mx < e->mbw; mx++) {
                     int k = orc_cabac_mb_bins(e->mbi, e->coef, e->side, e->mbw, mx, my, my > r0, !is_idr, my == r1 - 1 && mx == e->mbw - 1,
-                                              e->bins + nb, e->bins_cap - nb);
+                                              T8X8_ON(e), e->bins + nb, e->bins_cap - nb);
                     if (k > ORC_MB_BINS_MAX || nb + k > e->bins_cap) return -1;
                     nb += k;
                 }

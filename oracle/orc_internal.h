@@ -16,7 +16,7 @@ void bw_trailing(BitWriter *b);
 int  orc_se_len(int v);
 void orc_write_slice_header(BitWriter *b, int first_mb, int is_idr, int frame_num, int idr_pic_id, int qp, int cabac);
 int  orc_cabac_mb_bins(const OrcMbInfo *mbi, const OrcMbCoef *coef, const OrcMbSide *side, int mbw, int mx, int my, int top_avail,
-                       int is_p, int last, uint16_t *out, int cap);
+                       int is_p, int last, int transform8x8, uint16_t *out, int cap);
 void orc_cabac_code(BitWriter *bw, const uint16_t *bins, int n, int slice_qp, int is_p);
 void orc_write_residual_block(BitWriter *b, const int16_t *coef, int max, int nC);
 

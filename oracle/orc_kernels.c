@@ -117,6 +117,60 @@ void orc_dequant4x4(const int16_t *lz, int32_t *d, int qp, int ac_only)
     }
 }
 
+/* ---- 8x8 transform of the High profile (transform_size_8x8_flag = 1) ----
+ * forward: the integer 8x8 transform matching 8.5.13's inverse (rows then columns; encoder side, the JM / x264 butterfly) */
+static void fdct8_1d(const int *x, int *y)
+{
+    int a0 = x[0] + x[7], a1 = x[1] + x[6], a2 = x[2] + x[5], a3 = x[3] + x[4];
+    int a4 = x[0] - x[7], a5 = x[1] - x[6], a6 = x[2] - x[5], a7 = x[3] - x[4];
+    int b0 = a0 + a3, b1 = a1 + a2, b2 = a0 - a3, b3 = a1 - a2;
+    int b4 = a5 + a6 + ((a4 >> 1) + a4), b5 = a4 - a7 - ((a6 >> 1) + a6), b6 = a4 + a7 - ((a5 >> 1) + a5), b7 = a5 - a6 + ((a7 >> 1) + a7);
+    y[0] = b0 + b1; y[1] = b4 + (b7 >> 2); y[2] = b2 + (b3 >> 1); y[3] = b5 + (b6 >> 2);
+    y[4] = b0 - b1; y[5] = b6 - (b5 >> 2); y[6] = (b2 >> 1) - b3; y[7] = (b4 >> 2) - b7;
+}
+void orc_dct8x8(const int16_t *r, int32_t *c)
+{
+    int t[64], in[8], out[8];
+    for (int y = 0; y < 8; y++) { for (int x = 0; x < 8; x++) in[x] = r[y * 8 + x]; fdct8_1d(in, out); for (int x = 0; x < 8; x++) t[y * 8 + x] = out[x]; }
+    for (int x = 0; x < 8; x++) { for (int y = 0; y < 8; y++) in[y] = t[y * 8 + x]; fdct8_1d(in, out); for (int y = 0; y < 8; y++) c[y * 8 + x] = out[y]; }
+}
+/* quantise raster coefficients -> 64 levels in 8x8 zig-zag order (JM: (|c| * MF + f) >> (16 + qp/6), dead zone 1/3 intra, 1/6 inter,
+ * levels clipped to +-2063 like the 4x4 quantiser). Returns the number of nonzero levels. */
+int orc_quant8x8(const int32_t *c, int16_t *lz, int qp, int intra)
+{
+    int qbits = 16 + qp / 6, m = qp % 6, n = 0; int64_t f = ((int64_t)1 << qbits) / (intra ? 3 : 6);
+    for (int i = 0; i < 64; i++) {
+        int pos = ZIGZAG8x8[i], v = c[pos];
+        int l = (int)(((int64_t)iabs(v) * QUANT8_MF[m][pos_class8(pos >> 3, pos & 7)] + f) >> qbits);
+        if (l > 2063) l = 2063;
+        lz[i] = (int16_t)(v < 0 ? -l : l); n += l != 0;
+    }
+    return n;
+}
+/* 8.5.13 scaling (flat_8x8_16 weights): LevelScale8x8 = 16 * normAdjust8x8 */
+void orc_dequant8x8(const int16_t *lz, int32_t *d, int qp)
+{
+    int sh = qp / 6, m = qp % 6;
+    for (int i = 0; i < 64; i++) {
+        int pos = ZIGZAG8x8[i], ls = 16 * DEQUANT8_V[m][pos_class8(pos >> 3, pos & 7)];
+        d[pos] = qp >= 36 ? (lz[i] * ls) << (sh - 6) : (lz[i] * ls + (1 << (5 - sh))) >> (6 - sh);
+    }
+}
+/* 8.5.13 inverse transform: each row, then each column, then (x + 32) >> 6 */
+static void idct8_1d(const int *d, int *o)
+{
+    int a0 = d[0] + d[4], a1 = -d[3] + d[5] - d[7] - (d[7] >> 1), a2 = d[0] - d[4], a3 = d[1] + d[7] - d[3] - (d[3] >> 1);
+    int a4 = (d[2] >> 1) - d[6], a5 = -d[1] + d[7] + d[5] + (d[5] >> 1), a6 = d[2] + (d[6] >> 1), a7 = d[3] + d[5] + d[1] + (d[1] >> 1);
+    int b0 = a0 + a6, b1 = a1 + (a7 >> 2), b2 = a2 + a4, b3 = a3 + (a5 >> 2), b4 = a2 - a4, b5 = (a3 >> 2) - a5, b6 = a0 - a6, b7 = a7 - (a1 >> 2);
+    o[0] = b0 + b7; o[1] = b2 + b5; o[2] = b4 + b3; o[3] = b6 + b1; o[4] = b6 - b1; o[5] = b4 - b3; o[6] = b2 - b5; o[7] = b0 - b7;
+}
+void orc_idct8x8(const int32_t *d, int32_t *r)
+{
+    int t[64], in[8], out[8];
+    for (int y = 0; y < 8; y++) { for (int x = 0; x < 8; x++) in[x] = d[y * 8 + x]; idct8_1d(in, out); for (int x = 0; x < 8; x++) t[y * 8 + x] = out[x]; }
+    for (int x = 0; x < 8; x++) { for (int y = 0; y < 8; y++) in[y] = t[y * 8 + x]; idct8_1d(in, out); for (int y = 0; y < 8; y++) r[y * 8 + x] = (out[y] + 32) >> 6; }
+}
+
 /* ---- colour conversion: BT.601 limited range, 8-bit fixed point; chroma from the 2x2 mean RGB.
  * No reference function computes this (the reference only accepts I420,
  * VideoEncoderOpenH264.cpp:256,262,358): definition is ours, see SURVEY.md 8c. ---- */
@@ -302,6 +356,8 @@ void orc_deblock_frame(uint8_t *Y, int ys, uint8_t *U, uint8_t *V, int cs, int m
                     if (e == 0) {
                         bsv[0][k] = mx > 0 ? boundary_strength(q - 1, 3, k, q, 0, k, 1) : 0;
                         bsh[0][k] = my > 0 ? boundary_strength(q - mbw, k, 3, q, k, 0, 1) : 0;
+                    } else if ((e & 1) && ORC_MB_T8(q)) {
+                        bsv[e][k] = bsh[e][k] = 0;     /* transform_size_8x8_flag: only the 8x8 transform block edges are filtered (8.7) */
                     } else {
                         bsv[e][k] = boundary_strength(q, e - 1, k, q, e, k, 0);
                         bsh[e][k] = boundary_strength(q, k, e - 1, q, k, e, 0);

@@ -257,6 +257,26 @@ def test_downsample_sad_satd_transform_kernels(enc, orc):
                 assert np.array_equal(lev[i], lz) and np.array_equal(rec[i], rr), (qp, intra, i)
 
 
+def test_transform8x8_kernel_matches_the_oracle(enc, orc):
+    """the 8x8 transform chain of the High profile (forward, quantiser, 8.5.13 scaling and inverse), extremes included"""
+    L, O = enc.lib(), orc.lib()
+    rng = np.random.default_rng(8)
+    for qp in (0, 11, 26, 35, 36, 44, 51):
+        for intra in (0, 1):
+            n = 131                                                       # not a multiple of the four blocks a warp takes
+            res = rng.integers(-255, 256, (n, 64)).astype(np.int16)
+            res[0] = 255; res[1] = -255; res[2] = 0; res[3] = np.where(np.arange(64) % 2, 255, -255); res[4] = np.where((np.arange(64) // 8) % 2, 255, -255)
+            res[5:40] = rng.integers(-6, 7, (35, 64))                       # small residuals: the dead zone decides
+            lev = np.zeros((n, 64), np.int16); rec = np.zeros((n, 64), np.int32)
+            enc.check(L.b200k_transform_block8(0, _p(res), n, qp, intra, _p(lev), _p(rec)))
+            for i in range(n):
+                coef = np.zeros(64, np.int32); O.orc_dct8x8(_p(res[i]), _p(coef))
+                lz = np.zeros(64, np.int16); O.orc_quant8x8(_p(coef), _p(lz), qp, intra)
+                d = np.zeros(64, np.int32); O.orc_dequant8x8(_p(lz), _p(d), qp)
+                rr = np.zeros(64, np.int32); O.orc_idct8x8(_p(d), _p(rr))
+                assert np.array_equal(lev[i], lz) and np.array_equal(rec[i], rr), (qp, intra, i)
+
+
 def test_deblock_kernel_on_random_macroblock_info(enc, orc):
     """adversarial deblocking input: random pixels and random (type, nnz, mv) so every bS value and filter branch is hit"""
     L, O = enc.lib(), orc.lib()
@@ -267,6 +287,7 @@ def test_deblock_kernel_on_random_macroblock_info(enc, orc):
         pix = np.clip(rng.integers(60, 200) + rng.integers(-amp, amp + 1, mbw * mbh * 384), 0, 255).astype(np.uint8)
         mbi = np.zeros(mbw * mbh, enc.MBINFO_DTYPE)
         mbi["mb_type"] = rng.choice([0, 0, 1, 3, 4], mbw * mbh)
+        mbi["i16_mode"] = np.where((mbi["mb_type"] == 0) | (mbi["mb_type"] == 4), 4 * rng.integers(0, 2, mbw * mbh), 0)   # transform_size_8x8_flag on some inter MBs
         mbi["nnz"] = rng.integers(0, 3, (mbw * mbh, 24)) * (rng.random((mbw * mbh, 24)) < 0.3)
         mv8 = np.repeat(rng.integers(-9, 10, (mbw * mbh, 1, 2)), 4, axis=1)          # one vector per 8x8 partition ...
         split = mbi["mb_type"] == 4
@@ -497,7 +518,7 @@ def test_cabac_coder_matches_the_oracle_on_random_bins(enc, orc, kind):
 
 @pytest.mark.parametrize("w,h,kind,qp,slices,sr,frames,profile", [
     (208, 160, "A", 22, 1, 16, 4, 1), (128, 96, "B", 35, 2, 32, 4, 2), (96, 64, "D", 12, 4, 64, 3, 1), (352, 288, "A", 30, 1, 16, 3, 2),
-    (30, 18, "A", 26, 1, 16, 3, 1), (640, 368, "A", 40, 3, 16, 3, 1),
+    (30, 18, "A", 26, 1, 16, 3, 1), (640, 368, "A", 40, 3, 16, 3, 1), (640, 368, "A", 32, 2, 16, 4, 2), (320, 240, "B", 24, 1, 16, 4, 2), (176, 144, "D", 44, 1, 16, 3, 2),
 ])
 def test_cabac_every_stage_matches_the_oracle(enc, orc, w, h, kind, qp, slices, sr, frames, profile):
     g = enc.Session(w, h, const_qp=qp, num_slices=slices, search_range=sr, gop=1000, device=0, profile=profile)
@@ -508,6 +529,11 @@ def test_cabac_every_stage_matches_the_oracle(enc, orc, w, h, kind, qp, slices, 
         f = c.frame(t)
         bs, _ = g.encode(f); ref = o.encode(f, t == 0, qp)
         oi = o.mb_info(); gs, os_ = g.stage("mbside"), o.mb_side()
+        gi = g.stage("mbinfo")
+        for fld in ("mb_type", "i16_mode", "cbp", "nnz"):                 # i16_mode bit 2 = transform_size_8x8_flag (High profile)
+            assert np.array_equal(gi[fld], oi[fld]), f"frame {t} MbInfo.{fld}: first MB {int(np.argmax((gi[fld] != oi[fld]).reshape(len(oi), -1).any(1)))}"
+        coded = (oi["mb_type"] != 3)
+        assert np.array_equal(g.stage("mbcoef")["luma"][coded & ((oi["cbp"] & 15) != 0)], o.mb_coef()["luma"][coded & ((oi["cbp"] & 15) != 0)]), f"frame {t} luma levels"
         assert np.array_equal(gs["dc_cbf"], os_["dc_cbf"]), f"frame {t} dc_cbf"
         assert np.array_equal(gs["mvd"], os_["mvd"]), f"frame {t} mvd / i4 syntax"
         cnt, off, bins = g.stage("bin_count"), g.stage("bin_off"), g.stage("bins")

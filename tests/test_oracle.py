@@ -81,7 +81,7 @@ def test_tables_match_the_independent_decoder():
                 for m in re.finditer(r"static const uint8_t (\w+)\[[^\]]*\](?:\[[^\]]*\])? = \{(.*?)\};", src, re.S)}
         for name in ("COEFF_TOKEN_LEN", "COEFF_TOKEN_BITS", "CHROMA_DC_COEFF_TOKEN_LEN", "CHROMA_DC_COEFF_TOKEN_BITS", "TOTAL_ZEROS_LEN",
                      "TOTAL_ZEROS_BITS", "CHROMA_DC_TOTAL_ZEROS_LEN", "CHROMA_DC_TOTAL_ZEROS_BITS", "RUN_BEFORE_LEN", "RUN_BEFORE_BITS",
-                     "ZIGZAG4x4", "CHROMA_QP", "DEBLOCK_ALPHA", "DEBLOCK_BETA"):
+                     "ZIGZAG4x4", "CHROMA_QP", "DEBLOCK_ALPHA", "DEBLOCK_BETA", "ZIGZAG8x8", "DEQUANT8_V", "CABAC_SIG8", "CABAC_LAST8"):
             assert blob.find(tabs[name]) >= 0, name
 
 
@@ -160,6 +160,13 @@ def test_product_tables_equal_oracle_tables():
              ("CBP_TO_CODENUM_INTER", "c_cbp_inter"), ("CBP_TO_CODENUM_INTRA", "c_cbp_intra"), ("LAMBDA_TAB", "c_lambda")]
     for a, b in pairs:
         assert nums(o, a) == nums(p, b), (a, b)
+    # the 8x8 transform / CABAC ctxBlockCat 5 tables live beside their kernels
+    t8 = open(os.path.join(ROOT, "media_b200", "csrc", "k_t8.cuh")).read(); cb = open(os.path.join(ROOT, "media_b200", "csrc", "k_cabac.cuh")).read()
+    for a, b, text in (("ZIGZAG8x8", "c_zigzag8", t8), ("DEQUANT8_V", "c_dequant8_v", t8), ("QUANT8_MF", "c_quant8_mf", t8),
+                       ("CABAC_SIG8", "c_cabac_sig8", cb), ("CABAC_LAST8", "c_cabac_last8", cb)):
+        assert nums(o, a) == nums(text, b), (a, b)
+    zz = nums(t8, "c_zigzag8"); izz = nums(t8, "c_izigzag8")
+    assert sorted(zz) == list(range(64)) and all(izz[zz[i]] == i for i in range(64))
 
 
 def test_transform_round_trip_and_quant(orc):
@@ -178,6 +185,47 @@ def test_transform_round_trip_and_quant(orc):
             # reconstruction error bounded by the quantiser step (Qstep doubles every 6 QP, 0.625 at QP 0)
             step = 0.625 * 2 ** (qp / 6)
             assert np.abs(r - res).max() <= 1.5 * step + 1
+
+
+def test_transform8x8_round_trip_and_definition(orc):
+    """the 8x8 transform pair of the High profile: the inverse is 8.5.13's (checked through the decoder round trips below), the forward one
+    must invert it up to the quantiser step, and a constant block must land in the DC coefficient alone"""
+    L = orc.lib(); rng = np.random.default_rng(3)
+    flat = np.full(64, 7, np.int16); coef = np.zeros(64, np.int32); L.orc_dct8x8(flat.ctypes.data, coef.ctypes.data)
+    assert coef[0] == 64 * 7 and not coef[1:].any()
+    for qp in (0, 12, 26, 35, 36, 40, 51):
+        for _ in range(40):
+            res = rng.integers(-255, 256, 64).astype(np.int16)
+            L.orc_dct8x8(res.ctypes.data, coef.ctypes.data)
+            lz = np.zeros(64, np.int16); n = L.orc_quant8x8(coef.ctypes.data, lz.ctypes.data, qp, 1)
+            assert n == np.count_nonzero(lz)
+            d = np.zeros(64, np.int32); L.orc_dequant8x8(lz.ctypes.data, d.ctypes.data, qp)
+            r = np.zeros(64, np.int32); L.orc_idct8x8(d.ctypes.data, r.ctypes.data)
+            step = 0.625 * 2 ** (qp / 6)
+            assert np.abs(r - res).max() <= 2.0 * step + 1, (qp, np.abs(r - res).max())
+
+
+@pytest.mark.parametrize("w,h,kind,qp,slices", [(176, 144, "A", 26, 1), (320, 240, "A", 32, 2), (320, 240, "B", 24, 1), (640, 368, "A", 40, 3), (208, 160, "D", 44, 1)])
+def test_high_profile_8x8_transform_streams_decode(orc, w, h, kind, qp, slices):
+    """High profile: PPS transform_8x8_mode_flag = 1, inter MBs choose between the 4x4 and the 8x8 transform (transform_size_8x8_flag,
+    ctxBlockCat 5 residual blocks, deblocking of the 8x8 transform edges only); FFmpeg must reproduce the oracle's reconstruction"""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    o = orc.Encoder(w, h, num_slices=slices, profile=2); o4 = orc.Encoder(w, h, num_slices=slices, profile=2, no_t8x8=1)
+    c = Content(kind, w, h)
+    aus, recs, n8 = [], [], 0
+    for t in range(5):
+        f = c.frame(t)
+        aus.append(o.encode(f, t == 0, qp)); recs.append(o.recon()); o4.encode(f, t == 0, qp)
+        mi = o.mb_info(); t8 = (mi["i16_mode"] >> 2) & 1
+        assert not t8[(mi["mb_type"] != 0) & (mi["mb_type"] != 4)].any() and ((mi["cbp"][t8 == 1] & 15) != 0).all()
+        for m in np.flatnonzero(t8):                               # the four nnz of an 8x8 block carry its level count
+            assert all(len(set(mi["nnz"][m][4 * b: 4 * b + 4])) == 1 for b in range(4))
+        n8 += int(t8.sum())
+        assert not ((o4.mb_info()["i16_mode"] >> 2) & 1).any()
+    assert n8 > 0 or kind == "D"
+    dec = avdec.decode_stream(aus)
+    assert len(dec) == 5 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
 
 
 def test_sad_satd_definitions(orc):
