@@ -31,6 +31,7 @@ WORKLOADS = {
     "1080p": {},
     "1080p-main": dict(PROFILE=1, SLICES=4, LABEL="Main profile CABAC IPPP (the wrapper's iEntropyCodingModeFlag = 1 with profile main), CBR 4 Mbps @30fps each, gop 300, search +-16, 4 slices (the CABAC default at 1080p), content A (moving texture)"),
     "1080p-main-1slice": dict(PROFILE=1, LABEL="Main profile CABAC IPPP, CBR 4 Mbps @30fps each, gop 300, search +-16, 1 slice, content A (moving texture)"),
+    "1080p-high": dict(PROFILE=2, SLICES=4, LABEL="High profile CABAC IPPP with the 8x8 transform on inter MBs (profile high), CBR 4 Mbps @30fps each, gop 300, search +-16, 4 slices, content A (moving texture)"),
     "portrait720": dict(W=720, H=1280, CQP=26, sessions=1, groups=1, METRIC="720x1280 H.264 encode frames/s per GPU",
                         LABEL="ONE 720x1280 portrait stream (config 1): Baseline CAVLC, const QP 26, gop 300, search +-16, 1 slice, content A; latency-bound by construction"),
     "single": dict(sessions=1, groups=1, LABEL="ONE 1080p stream (config 2): Baseline CAVLC IPPP, CBR 4 Mbps @30fps, gop 300, search +-16, 1 slice, content A; latency-bound by construction"),

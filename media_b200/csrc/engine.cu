@@ -169,6 +169,7 @@ struct b200enc_batch {
     cudaStream_t stream = nullptr, stream2 = nullptr;    // stream2: entropy coding runs beside the deblocking wavefront
     cudaStream_t stream_hi = nullptr;                   // high-priority twin of `stream`: batches made only of IDR frames (long wavefront)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_wave0 = nullptr, ev_wave1 = nullptr;  // hand-over to / from the high-priority stream the wavefront kernels run on
     Sess *h_sess = nullptr, *d_sess = nullptr;
     WaveCtl *d_ctl = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -212,6 +213,12 @@ int cabac_slab_kb()
     return kb;
 }
 
+bool wave_prio()
+{
+    static const bool on = [] { const char *e = getenv("B200ENC_WAVE_PRIO"); return e ? atoi(e) != 0 : false; }();
+    return on;
+}
+
 int batch_init(b200enc_batch *b, int device, int cap)
 {
     b->device = device; b->cap = cap;
@@ -224,6 +231,8 @@ int batch_init(b200enc_batch *b, int device, int cap)
       CU_TRY(cudaStreamCreateWithPriority(&b->stream_hi, cudaStreamNonBlocking, hi), return B200ENC_ENODEV); }
     CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), return B200ENC_ENODEV);
     CU_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming), return B200ENC_ENODEV);
+    CU_TRY(cudaEventCreateWithFlags(&b->ev_wave0, cudaEventDisableTiming), return B200ENC_ENODEV);
+    CU_TRY(cudaEventCreateWithFlags(&b->ev_wave1, cudaEventDisableTiming), return B200ENC_ENODEV);
     CU_TRY(cudaHostAlloc(&b->h_sess, sizeof(Sess) * cap, cudaHostAllocDefault), return B200ENC_ENOMEM);
     CU_TRY(cudaMalloc(&b->d_sess, sizeof(Sess) * cap), return B200ENC_ENOMEM);
     CU_TRY(cudaMalloc(&b->d_ctl, sizeof(WaveCtl)), return B200ENC_ENOMEM);
@@ -244,6 +253,8 @@ void batch_free(b200enc_batch *b)
     if (b->h_sess) cudaFreeHost(b->h_sess);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
+    if (b->ev_wave0) cudaEventDestroy(b->ev_wave0);
+    if (b->ev_wave1) cudaEventDestroy(b->ev_wave1);
     if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream_hi) { cudaStreamSynchronize(b->stream_hi); cudaStreamDestroy(b->stream_hi); }
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -354,17 +365,23 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         if (any_t8) { pf.begin("k_inter_t8"); k_inter_t8<<<dim3((nmb + T8_WARPS - 1) / T8_WARPS, 1, n), T8_WARPS * 32, 0, st>>>(b->d_sess, g); pf.end(); launches++; }
     }
     const int wave_ctas = (n * g.mbh + WAVE_WARPS - 1) / WAVE_WARPS;
-    pf.begin("k_intra_wave"); k_intra_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
+    // The wavefront kernels are dependent chains per MB row (latency-bound, few warps). On the batch's high-priority stream their CTAs are
+    // placed ahead of the queued CTAs of other batches' throughput kernels (k_me_fine alone is 32 640 CTAs per 32 sessions) instead of
+    // behind them, so the chains of one batch run underneath the motion search of the next.
+    cudaStream_t sw = wave_prio() ? b->stream_hi : st;
+    if (sw != st) { cudaEventRecord(b->ev_wave0, st); cudaStreamWaitEvent(sw, b->ev_wave0, 0); }
+    pf.begin("k_intra_wave", sw); k_intra_wave<<<wave_ctas, WAVE_WARPS * 32, 0, sw>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
     for (int i = 0; i < n; i++) if (ss[i]->cfg.debug) {
         uint8_t **cur = ss[i]->cur_is_A ? ss[i]->bufA : ss[i]->bufB;
-        for (int c = 0; c < 3; c++) cudaMemcpyAsync(ss[i]->rec_pre[c], cur[c], (size_t)g.wc * g.hc / (c ? 4 : 1), cudaMemcpyDeviceToDevice, st);
+        for (int c = 0; c < 3; c++) cudaMemcpyAsync(ss[i]->rec_pre[c], cur[c], (size_t)g.wc * g.hc / (c ? 4 : 1), cudaMemcpyDeviceToDevice, sw);
     }
-    pf.begin("k_pskip_scan"); k_pskip_scan<<<dim3(g.num_slices, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_pskip_scan", sw); k_pskip_scan<<<dim3(g.num_slices, 1, n), 256, 0, sw>>>(b->d_sess, g); pf.end(); launches++;
     // fork: the entropy coder only needs MbInfo / MbCoef / skip runs, the deblocking wavefront only reconstruction + MbInfo;
     // the latency-bound wavefront and the issue-bound CAVLC chain overlap on two streams and join before the read-back
     cudaStream_t s2 = b->stream2;
-    cudaEventRecord(b->ev_fork, st); cudaStreamWaitEvent(s2, b->ev_fork, 0);
-    pf.begin("k_deblock_wave"); k_deblock_wave<<<wave_ctas, WAVE_WARPS * 32, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
+    cudaEventRecord(b->ev_fork, sw); cudaStreamWaitEvent(s2, b->ev_fork, 0);
+    pf.begin("k_deblock_wave", sw); k_deblock_wave<<<wave_ctas, WAVE_WARPS * 32, 0, sw>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
+    if (sw != st) { cudaEventRecord(b->ev_wave1, sw); cudaStreamWaitEvent(st, b->ev_wave1, 0); }
     if (ss[0]->cfg.profile) {
         // CABAC: side records, entry counts, offsets, bin lists (all parallel over MBs), then one warp per slice runs the coder
         const dim3 gb((nmb + CABAC_WARPS - 1) / CABAC_WARPS, 1, n);

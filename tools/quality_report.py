@@ -20,3 +20,18 @@ for kind in "AB":
                 bits.append(len(au) * 8); ps.append(psnr(f[:W * H], e.recon()[:W * H]))
             types = np.bincount(e.mb_info()["mb_type"], minlength=5).tolist()
             print(f"| {kind} | {qp} | {name} | {bits[0] / 8192:.1f} | {np.mean(bits[1:]) / 1000:.1f} | {np.mean(ps):.2f} | {' / '.join(map(str, types))} |")
+
+# High profile: the 8x8 transform on inter macroblocks against the same stream without it (transform_8x8_mode_flag = 0)
+print()
+print("| content | QP | High profile | P-frame kbit/frame | Y-PSNR dB (P frames) | inter MBs with transform_size_8x8_flag (last frame) |")
+print("|---|---|---|---|---|---|")
+for kind in "AB":
+    for qp in (24, 30, 36, 42):
+        for name, kw in (("4x4 only", dict(no_t8x8=1)), ("4x4 / 8x8", {})):
+            e = orc_py.Encoder(W, H, profile=2, **kw); c = Content(kind, W, H)
+            bits, ps = [], []
+            for t in range(FRAMES):
+                f = c.frame(t); au = e.encode(f, t == 0, qp)
+                bits.append(len(au) * 8); ps.append(psnr(f[:W * H], e.recon()[:W * H]))
+            mi = e.mb_info(); inter = (mi["mb_type"] == 0) | (mi["mb_type"] == 4)
+            print(f"| {kind} | {qp} | {name} | {np.mean(bits[1:]) / 1000:.1f} | {np.mean(ps[1:]):.2f} | {int(((mi['i16_mode'] >> 2) & 1).sum())} of {int(inter.sum())} |")
