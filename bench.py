@@ -54,9 +54,9 @@ def apply_workload(args):
         g["SLICES"] = args.slices
         g["LABEL"] += f" [slices overridden: {args.slices}]"
     if args.sessions is None:
-        args.sessions = 96
+        args.sessions = 128
     if args.groups is None:
-        args.groups = 3
+        args.groups = 4
 
 
 def frame_bytes():

@@ -206,12 +206,17 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
     return true;
 }
 
-// grid: ceil(sessions * mbh / WAVE_WARPS) CTAs of WAVE_WARPS warps. Slices do not break the wavefront:
+// grid: up to ceil(sessions * mbh / WAVE_WARPS) CTAs of WAVE_WARPS persistent warps. Slices do not break the wavefront:
 // disable_deblocking_filter_idc = 0 filters across slice boundaries.
 __global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss, Geom g, int nsess, WaveCtl *ctl)
 {
     __shared__ DbkSmem sm_all[WAVE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DbkWb wb; dbk_wb_init(wb, g.wc, lane);
+    // persistent warps: a warp takes the next (row, session) ticket until none is left. Tickets are handed out in wavefront order and a
+    // row only ever waits on a row with an earlier ticket, so any number of resident warps makes progress; the grid is sized to the rows a
+    // wavefront keeps busy at once (engine.cu) instead of one warp per row holding its registers while it waits for its turn.
+    for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&ctl->ticket_dbk, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
@@ -220,7 +225,6 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss
     const Sess &sg = ss[t % nsess];
     int *prog = sg.row_prog_dbk;
     DbkCtx s; s.rec[0] = sg.rec[0]; s.rec[1] = sg.rec[1]; s.rec[2] = sg.rec[2]; s.mbi = sg.mbi; s.qp = sg.qp;
-    DbkWb wb; dbk_wb_init(wb, g.wc, lane);
     DbkPrefetch cur, nxt;
     dbk_prefetch(s, g, 0, my, lane, cur);
     int published = 0;
@@ -254,6 +258,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss
         printf("dbk row0: %d MBs (%d filtered) cycles/MB: prefetch %lld stage+bs %lld wait+above %lld vert %lld horz %lld writeback %lld fence+publish %lld\n", g.mbw, dbk_n,
                dbk_t[0] / g.mbw, dbk_t[1] / g.mbw, dbk_t[2] / g.mbw, dbk_t[3] / g.mbw, dbk_t[4] / g.mbw, dbk_t[5] / g.mbw, dbk_t[6] / g.mbw);
 #endif
+    __syncwarp();
+    }
 }
 
 } // namespace b200
