@@ -13,6 +13,9 @@
 
 namespace b200 {
 
+#ifndef DBK_MIN_CTAS
+#define DBK_MIN_CTAS 6      /* resident CTAs per SM the register allocation must allow: 76 registers, no spills (8 -> 64 registers spills and is slower) */
+#endif
 #ifdef DBK_TIMING
 #define DBK_T(i) do { const long long t_ = clock64(); dbk_t[i] += t_ - dbk_last; dbk_last = t_; } while (0)
 #else
@@ -208,7 +211,7 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
 
 // grid: up to ceil(sessions * mbh / WAVE_WARPS) CTAs of WAVE_WARPS persistent warps. Slices do not break the wavefront:
 // disable_deblocking_filter_idc = 0 filters across slice boundaries.
-__global__ void __launch_bounds__(WAVE_WARPS * 32) k_deblock_wave(const Sess *ss, Geom g, int nsess, WaveCtl *ctl)
+__global__ void __launch_bounds__(WAVE_WARPS * 32, DBK_MIN_CTAS) k_deblock_wave(const Sess *ss, Geom g, int nsess, WaveCtl *ctl)
 {
     __shared__ DbkSmem sm_all[WAVE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
