@@ -226,12 +226,6 @@ int dbk_resident_pct()
     return pct;
 }
 
-int intra_resident_pct()
-{
-    static const int pct = [] { const char *e = getenv("B200ENC_INTRA_RESIDENT"); return std::min(std::max(e ? atoi(e) : 100, 5), 100); }();
-    return pct;
-}
-
 int batch_init(b200enc_batch *b, int device, int cap)
 {
     b->device = device; b->cap = cap;
@@ -383,13 +377,12 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     // behind them, so the chains of one batch run underneath the motion search of the next.
     cudaStream_t sw = wave_prio() ? b->stream_hi : st;
     if (sw != st) { cudaEventRecord(b->ev_wave0, st); cudaStreamWaitEvent(sw, b->ev_wave0, 0); }
-    // Resident wavefront warps. A 2-MB-lag wavefront over mbh rows of mbw MBs keeps mbh * mbw / (mbw + 2 mbh) rows busy on average (47 % at
+    // Resident deblocking warps. A 2-MB-lag wavefront over mbh rows of mbw MBs keeps mbh * mbw / (mbw + 2 mbh) rows busy on average (47 % at
     // 1080p); warps beyond that only hold registers while they wait for their turn and push the other batches' motion search off the SMs
     // (one warp per row of 32 x 1080p sessions is 69 % of the GPU's register file for k_deblock_wave). Small batches keep every row
     // resident (floor: one CTA per SM), because there the wavefront's own latency is all that matters.
     auto resident_ctas = [&](int pct) { return std::max(1, std::min(wave_ctas, std::max(148, (n * ((g.mbh * pct + 99) / 100) + WAVE_WARPS - 1) / WAVE_WARPS))); };
-    const int intra_ctas = resident_ctas(intra_resident_pct());
-    pf.begin("k_intra_wave", sw); k_intra_wave<<<intra_ctas, WAVE_WARPS * 32, 0, sw>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
+    pf.begin("k_intra_wave", sw); k_intra_wave<<<wave_ctas, WAVE_WARPS * 32, 0, sw>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
     for (int i = 0; i < n; i++) if (ss[i]->cfg.debug) {
         uint8_t **cur = ss[i]->cur_is_A ? ss[i]->bufA : ss[i]->bufB;
         for (int c = 0; c < 3; c++) cudaMemcpyAsync(ss[i]->rec_pre[c], cur[c], (size_t)g.wc * g.hc / (c ? 4 : 1), cudaMemcpyDeviceToDevice, sw);

@@ -432,15 +432,13 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_intra_wave(const Sess *ss, 
 {
     __shared__ IntraSmem sm_all[WAVE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    IntraSmem &sm = sm_all[warp];
-    // persistent warps taking (row, session) tickets in wavefront order, see k_deblock_wave
-    for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&ctl->ticket_intra, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= nsess * g.mbh) return;
     const int my = t / nsess;
     const Sess &sg = ss[t % nsess];
+    IntraSmem &sm = sm_all[warp];
     int *prog = sg.row_prog_intra;
     IntraCtx s; s.rec0 = sg.rec[0]; s.rec1 = sg.rec[1]; s.rec2 = sg.rec[2]; s.src0 = sg.src[0]; s.src1 = sg.src[1]; s.src2 = sg.src[2];
     s.mbi = sg.mbi; s.coef = sg.coef; s.qp = sg.qp; s.is_idr = sg.is_idr;
@@ -468,8 +466,6 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_intra_wave(const Sess *ss, 
     }
     __syncwarp();
     if (lane == 0) { __threadfence(); st_release(prog + my, g.mbw); }
-    __syncwarp();
-    }
 }
 
 } // namespace b200
