@@ -188,7 +188,7 @@ struct b200enc_session {
     uint8_t *srcL1, *srcL2, *refL1, *refL2;      // padded pyramid planes (allocation bases)
     uint8_t *rpl, *rpc[2];                       // padded reference planes: G,b,h,j contiguous; Cb, Cr
     void *tmaps;                                 // CUtensorMap[3] in HBM
-    MbInfo *mbi; MbCoef *coef; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
+    MbInfo *mbi; MbCoef *coef; uint4 *dbk_bs; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
     uint32_t *mb_bits, *mb_off, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
     MbSide *side; uint16_t *bins; uint32_t *slice_nbins;   // CABAC (profile main / high)
     uint32_t rbsp_words_per_slice = 0;
@@ -328,7 +328,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
             for (int k = 0; k < 4; k++) d.rpl[k] = s->rpl + k * plane + ol;
             d.rpc[0] = s->rpc[0] + oc; d.rpc[1] = s->rpc[1] + oc; d.tmaps = s->tmaps;
         }
-        d.mbi = s->mbi; d.coef = s->coef; d.me2 = s->me2; d.me1 = s->me1; d.me0 = s->me0; d.inter_cost = s->inter_cost;
+        d.mbi = s->mbi; d.coef = s->coef; d.dbk_bs = s->dbk_bs; d.me2 = s->me2; d.me1 = s->me1; d.me0 = s->me0; d.inter_cost = s->inter_cost;
         d.skip_run = s->skip_run; d.mb_bits = s->mb_bits; d.mb_off = s->mb_off; d.mb_slot = s->mb_slot; d.rbsp = s->rbsp; d.slice_bits = s->slice_bits;
         d.side = s->side; d.bins = s->bins; d.slice_nbins = s->slice_nbins;
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
@@ -392,6 +392,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     // the latency-bound wavefront and the issue-bound CAVLC chain overlap on two streams and join before the read-back
     cudaStream_t s2 = b->stream2;
     cudaEventRecord(b->ev_fork, sw); cudaStreamWaitEvent(s2, b->ev_fork, 0);
+    pf.begin("k_deblock_bs", sw); k_deblock_bs<<<dim3((nmb + 7) / 8, 1, n), 256, 0, sw>>>(b->d_sess, g); pf.end(); launches++;
     const int dbk_ctas = resident_ctas(dbk_resident_pct());
     pf.begin("k_deblock_wave", sw); k_deblock_wave<<<dbk_ctas, WAVE_WARPS * 32, 0, sw>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
     if (sw != st) { cudaEventRecord(b->ev_wave1, sw); cudaStreamWaitEvent(st, b->ev_wave1, 0); }
@@ -645,7 +646,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         const size_t lplane = (size_t)g.ls * (g.hc + 2 * g.lp), cplane = (size_t)g.cs * (g.hc / 2 + 2 * g.cp) + 64;
         add(s->srcL1, l1); add(s->refL1, l1); add(s->srcL2, l2); add(s->refL2, l2);
         add(s->rpl, 4 * lplane + 256); add(s->rpc[0], cplane); add(s->rpc[1], cplane); add(s->tmaps, 3 * sizeof(CUtensorMap));
-        add(s->mbi, nmb * sizeof(MbInfo)); add(s->coef, nmb * sizeof(MbCoef));
+        add(s->mbi, nmb * sizeof(MbInfo)); add(s->coef, nmb * sizeof(MbCoef)); add(s->dbk_bs, nmb * sizeof(uint4));
         add(s->me2, nmb * 4); add(s->me1, nmb * 4); add(s->me0, nmb * 4); add(s->inter_cost, nmb * 4);
         add(s->skip_run, (nmb + B200_MAX_SLICES) * 4); add(s->mb_bits, nmb * 4); add(s->mb_off, nmb * 4);
         add(s->mb_slot, nmb * B200_MB_SLOT_WORDS * 4);

@@ -70,6 +70,7 @@ struct Sess {
     uint8_t *srcL1, *srcL2, *refL1, *refL2;
     const void *tmaps;            // CUtensorMap[3] in HBM: source luma (box 16x16), plane G (box 48x20), planes G,b,h,j (box 48x18x4)
     MbInfo *mbi; MbCoef *coef;
+    uint4 *dbk_bs;                // per MB: the 32 boundary strengths as bit planes (k_deblock_bs)
     int16_t *me2, *me1, *me0;     // per-level vectors (debug / parity dumps)
     int32_t *inter_cost;
     int32_t *skip_run;            // per MB: number of P_Skip MBs immediately before it in its slice

@@ -24,7 +24,7 @@ namespace b200 {
 
 // the few session fields the row loop needs, held in registers: every fence / strong access in the loop is a compiler memory
 // barrier, so reading them through `const Sess &` re-fetched them from L2 several times per macroblock (1 800 cycles measured)
-struct DbkCtx { uint8_t *rec[3]; const MbInfo *mbi; int qp; };
+struct DbkCtx { uint8_t *rec[3]; const uint4 *bs; int qp; };
 
 // write-back slots of a lane: word lane + 32k of the luma tile (20 rows x 5 words) / of the two chroma tiles (2 x 12 rows x 3 words);
 // flags: 1 slot exists and is ever stored, 2 it lies in the rows above the MB, 4 it is not in the 4 left columns, 8 (chroma) plane
@@ -49,7 +49,6 @@ __device__ __forceinline__ void dbk_wb_init(DbkWb &wb, int wc, int lane)
 struct DbkSmem {
     uint32_t y[20 * 5];        // rows -4..15, cols -4..15 (stride 20 bytes)
     uint32_t c[2][12 * 3];     // rows -4..7, cols -4..7 (stride 12 bytes)
-    uint32_t mbi[3][12];       // current, left, top MbInfo
 };
 
 // One edge position of one line of samples, luma or chroma in the same instruction stream (8.7.2.3 / 8.7.2.4): the 16 luma
@@ -87,9 +86,8 @@ __device__ __forceinline__ void filter_edge(uint8_t *p, int step, int bs, int al
 }
 
 // boundary strength between 4x4 block (bxp,byp) of MB p and block (bxq,byq) of MB q (8.7.2.1, frame pictures, one reference)
-__device__ __forceinline__ int bs_of(const uint32_t *mp, int bxp, int byp, const uint32_t *mq, int bxq, int byq, bool mb_edge)
+__device__ __forceinline__ int bs_of(const MbInfo *p, int bxp, int byp, const MbInfo *q, int bxq, int byq, bool mb_edge)
 {
-    const MbInfo *p = reinterpret_cast<const MbInfo *>(mp), *q = reinterpret_cast<const MbInfo *>(mq);
     const bool ip = p->mb_type == MB_I16x16 || p->mb_type == MB_I4x4, iq = q->mb_type == MB_I16x16 || q->mb_type == MB_I4x4;
     if (ip || iq) return mb_edge ? 4 : 3;
     if (p->nnz[xy2blk(bxp, byp)] || q->nnz[xy2blk(bxq, byq)]) return 2;
@@ -98,10 +96,33 @@ __device__ __forceinline__ int bs_of(const uint32_t *mp, int bxp, int byp, const
     return 0;
 }
 
+// Boundary strengths of every macroblock, ahead of the wavefront: they only depend on the MbInfo records (types, nnz, vectors), not on
+// samples, so they are computed fully in parallel -- warp per MB, lanes 0-15 = vertical edge e, segment k (lane = 4e + k), lanes 16-31 the
+// horizontal ones -- and stored as three bit planes of the 32 values (x, y, z = bits 0, 1, 2 of bS by lane; w = their OR). In the row loop
+// of k_deblock_wave this was 48 % of the executed instructions and a third of the stall samples (ncu, profiles/r01_ncu_summary.md).
+// grid: (ceil(n_mb / 8), 1, sessions), 256 threads
+__global__ void __launch_bounds__(256) k_deblock_bs(const Sess *ss, Geom g)
+{
+    const int lane = threadIdx.x & 31, mb = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    const int mx = mb % g.mbw, my = mb / g.mbw;
+    const MbInfo *q = s.mbi + mb;
+    const int e = (lane >> 2) & 3, k = lane & 3; const bool vert = lane < 16;
+    int bs;
+    if (e == 0) {
+        if (vert) bs = mx > 0 ? bs_of(q - 1, 3, k, q, 0, k, true) : 0;
+        else bs = my > 0 ? bs_of(q - g.mbw, k, 3, q, k, 0, true) : 0;
+    } else if ((e & 1) && mb_t8(q)) bs = 0;                           // transform_size_8x8_flag: only the 8x8 transform edges are filtered
+    else bs = vert ? bs_of(q, e - 1, k, q, e, k, false) : bs_of(q, k, e - 1, q, k, e, false);
+    const uint32_t b0 = __ballot_sync(0xffffffffu, bs & 1), b1 = __ballot_sync(0xffffffffu, bs & 2), b2 = __ballot_sync(0xffffffffu, bs & 4);
+    if (lane == 0) s.dbk_bs[mb] = make_uint4(b0, b1, b2, b0 | b1 | b2);
+}
+
 // One MB of the row. Software pipeline of the row loop: the MB's own samples and its MbInfo were prefetched into
 // registers one iteration earlier (nobody else touches them before this MB runs), the 4 left columns are carried over
 // from the previous tile in shared memory, and only the rows above are loaded after the wavefront wait.
-struct DbkPrefetch { uint32_t y0, y1, c, info; };
+struct DbkPrefetch { uint32_t y0, y1, c; uint4 bs; };
 
 __device__ __forceinline__ void dbk_prefetch(const DbkCtx &s, const Geom &g, int mx, int my, int lane, DbkPrefetch &pf)
 {
@@ -113,10 +134,7 @@ __device__ __forceinline__ void dbk_prefetch(const DbkCtx &s, const Geom &g, int
     // chroma: 2 planes x 8 rows x 2 words
     const uint8_t *C = ((lane >> 4) ? s.rec[2] : s.rec[1]) + (size_t)(my * 8 + ((lane >> 1) & 7)) * cw + mx * 8 + (lane & 1) * 4;
     pf.c = __ldcg(reinterpret_cast<const uint32_t *>(C));
-    // MbInfo: lanes 0-11 current MB, lanes 12-23 the MB above
-    pf.info = 0;
-    if (lane < 12) pf.info = reinterpret_cast<const uint32_t *>(s.mbi + mb)[lane];
-    else if (lane < 24 && my > 0) pf.info = reinterpret_cast<const uint32_t *>(s.mbi + mb - g.mbw)[lane - 12];
+    pf.bs = __ldg(s.bs + mb);        // the MB's 32 boundary strengths (k_deblock_bs), one broadcast load
 }
 
 // returns true when the MB wrote samples (a fence is needed before publishing)
@@ -134,26 +152,16 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
     if (mx > 0) {
         if (lane < 16) sm.y[(lane + 4) * 5] = sm.y[(lane + 4) * 5 + 4];
         else sm.c[(lane >> 3) & 1][((lane & 7) + 4) * 3] = sm.c[(lane >> 3) & 1][((lane & 7) + 4) * 3 + 2];
-        if (lane < 12) sm.mbi[1][lane] = sm.mbi[0][lane];
     }
     __syncwarp();
     sm.y[((lane >> 2) + 4) * 5 + 1 + (lane & 3)] = pf.y0;
     sm.y[((lane >> 2) + 12) * 5 + 1 + (lane & 3)] = pf.y1;
     sm.c[lane >> 4][(((lane >> 1) & 7) + 4) * 3 + 1 + (lane & 1)] = pf.c;
-    if (lane < 12) sm.mbi[0][lane] = pf.info; else if (lane < 24) sm.mbi[2][lane - 12] = pf.info;
     __syncwarp();
-    // lanes 0-15: bS of vertical edge e, segment k; lanes 16-31: horizontal edge e, segment k
-    int bs;
-    {
-        const int e = (lane >> 2) & 3, k = lane & 3; const bool vert = lane < 16;
-        if (e == 0) {
-            if (vert) bs = mx > 0 ? bs_of(sm.mbi[1], 3, k, sm.mbi[0], 0, k, true) : 0;
-            else bs = my > 0 ? bs_of(sm.mbi[2], k, 3, sm.mbi[0], k, 0, true) : 0;
-        } else if ((e & 1) && ((sm.mbi[0][0] >> 10) & 1u)) bs = 0;      // transform_size_8x8_flag: only the 8x8 transform edges are filtered
-        else bs = vert ? bs_of(sm.mbi[0], e - 1, k, sm.mbi[0], e, k, false) : bs_of(sm.mbi[0], k, e - 1, sm.mbi[0], k, e, false);
-    }
+    // lanes 0-15: bS of vertical edge e, segment k; lanes 16-31: horizontal edge e, segment k (precomputed by k_deblock_bs)
+    const int bs = (int)(((pf.bs.x >> lane) & 1u) | (((pf.bs.y >> lane) & 1u) << 1) | (((pf.bs.z >> lane) & 1u) << 2));
     DBK_T(1);
-    if (__ballot_sync(0xffffffffu, bs != 0) == 0) return false;
+    if (pf.bs.w == 0u) return false;
 
     uint8_t *Y = s.rec[0] + (size_t)my * 16 * wc + mx * 16;
     uint8_t *C[2] = { s.rec[1] + (size_t)my * 8 * cw + mx * 8, s.rec[2] + (size_t)my * 8 * cw + mx * 8 };
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, DBK_MIN_CTAS) k_deblock_wave(
     const int my = t / nsess;
     const Sess &sg = ss[t % nsess];
     int *prog = sg.row_prog_dbk;
-    DbkCtx s; s.rec[0] = sg.rec[0]; s.rec[1] = sg.rec[1]; s.rec[2] = sg.rec[2]; s.mbi = sg.mbi; s.qp = sg.qp;
+    DbkCtx s; s.rec[0] = sg.rec[0]; s.rec[1] = sg.rec[1]; s.rec[2] = sg.rec[2]; s.bs = sg.dbk_bs; s.qp = sg.qp;
     DbkPrefetch cur, nxt;
     dbk_prefetch(s, g, 0, my, lane, cur);
     int published = 0;
