@@ -103,16 +103,25 @@ __device__ __forceinline__ int bs_of(const MbInfo *p, int bxp, int byp, const Mb
 // grid: (ceil(n_mb / 8), 1, sessions), 256 threads
 __global__ void __launch_bounds__(256) k_deblock_bs(const Sess *ss, Geom g)
 {
-    const int lane = threadIdx.x & 31, mb = blockIdx.x * 8 + (threadIdx.x >> 5);
+    __shared__ uint32_t info_all[8][3][12];                           // per warp: MbInfo of the current, left and upper MB
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, mb = blockIdx.x * 8 + warp;
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
     const int mx = mb % g.mbw, my = mb / g.mbw;
-    const MbInfo *q = s.mbi + mb;
+    uint32_t (*info)[12] = info_all[warp];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(s.mbi + mb);
+        if (lane < 12) info[0][lane] = src[lane];
+        else if (lane < 24) { if (mx > 0) info[1][lane - 12] = src[lane - 24]; }                       // (mb - 1) * 12 + lane - 12
+        if (lane < 12 && my > 0) info[2][lane] = src[lane - 12 * g.mbw];
+    }
+    __syncwarp();
+    const MbInfo *q = reinterpret_cast<const MbInfo *>(info[0]), *ql = reinterpret_cast<const MbInfo *>(info[1]), *qt = reinterpret_cast<const MbInfo *>(info[2]);
     const int e = (lane >> 2) & 3, k = lane & 3; const bool vert = lane < 16;
     int bs;
     if (e == 0) {
-        if (vert) bs = mx > 0 ? bs_of(q - 1, 3, k, q, 0, k, true) : 0;
-        else bs = my > 0 ? bs_of(q - g.mbw, k, 3, q, k, 0, true) : 0;
+        if (vert) bs = mx > 0 ? bs_of(ql, 3, k, q, 0, k, true) : 0;
+        else bs = my > 0 ? bs_of(qt, k, 3, q, k, 0, true) : 0;
     } else if ((e & 1) && mb_t8(q)) bs = 0;                           // transform_size_8x8_flag: only the 8x8 transform edges are filtered
     else bs = vert ? bs_of(q, e - 1, k, q, e, k, false) : bs_of(q, k, e - 1, q, k, e, false);
     const uint32_t b0 = __ballot_sync(0xffffffffu, bs & 1), b1 = __ballot_sync(0xffffffffu, bs & 2), b2 = __ballot_sync(0xffffffffu, bs & 4);

@@ -1,14 +1,16 @@
+# end-of-round capture: every command first runs to exit 0 without ncu; a number printed under ncu is never a bench value
 set -x
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r01m.log 2>&1
-python bench.py > gpurun_out/bench_r01m.json 2> gpurun_out/bench_r01m.err
-python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_r01m.json 2> gpurun_out/bench_ref_r01m.err
-python bench.py --no-cpu --workload 1080p-main > gpurun_out/bench_main_r01m.json 2> gpurun_out/bench_main_r01m.err
-python bench.py --no-cpu --workload 1080p-high > gpurun_out/bench_high_r01m.json 2> gpurun_out/bench_high_r01m.err
+python -m pytest tests -m gpu -q > gpurun_out/gpu_tests_r01n.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r01n.log 2>&1
+python bench.py > gpurun_out/bench_r01n.json 2> gpurun_out/bench_r01n.err
+python bench.py --no-cpu --steps 100 --warmup 10 > gpurun_out/bench_long_r01n.json 2> gpurun_out/bench_long_r01n.err
+python bench.py --no-cpu --workload 1080p-main > gpurun_out/bench_main_r01n.json 2> gpurun_out/bench_main_r01n.err
+python bench.py --no-cpu --workload 1080p-high > gpurun_out/bench_high_r01n.json 2> gpurun_out/bench_high_r01n.err
+python bench.py --no-cpu --workload single > gpurun_out/bench_single_r01n.json 2> gpurun_out/bench_single_r01n.err
+python bench.py --no-cpu --workload 4k > gpurun_out/bench_4k_r01n.json 2> gpurun_out/bench_4k_r01n.err
+python bench.py --no-cpu --workload rgba720 > gpurun_out/bench_rgba_r01n.json 2> gpurun_out/bench_rgba_r01n.err
 B="python bench.py --steps 3 --warmup 3 --sessions 32 --groups 1 --no-cpu"
-$B > gpurun_out/plain_m.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01m.csv $B > gpurun_out/ncu_lm.log 2>&1
-ncu --set full --clock-control none --import-source on --launch-skip 41 -c 16 -f -o gpurun_out/prof_r01m $B > gpurun_out/ncu_fm.log 2>&1
-H="python bench.py --steps 3 --warmup 3 --sessions 32 --groups 1 --no-cpu --workload 1080p-high"
-$H > gpurun_out/plain_mh.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_high_r01m.csv $H > gpurun_out/ncu_lmh.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:inter_t8 -c 1 -f -o gpurun_out/prof_high_r01m $H > gpurun_out/ncu_fmh.log 2>&1
+$B > gpurun_out/plain_n.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01n.csv $B > gpurun_out/ncu_ln.log 2>&1
+ncu --set full --clock-control none --import-source on --launch-skip 44 -c 17 -f -o gpurun_out/prof_r01n $B > gpurun_out/ncu_fn.log 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -3
-tail -c 400 gpurun_out/bench_r01m.json
+tail -2 gpurun_out/gpu_tests_r01n.log; tail -1 gpurun_out/smoke_r01n.log
