@@ -292,6 +292,21 @@ def run_b200(args):
                         "warp_instructions_per_mb_1080p": round(k["warp_instructions"] / (8160 * prof["sessions_per_launch"]), 1)}
         except Exception:
             pass
+        # instruction-issue roofline of the dominant kernel: executed warp-instructions per launch (committed ncu capture, scaled to this
+        # run's sessions and macroblock count) over its live CUDA-event time, against SMs x 4 schedulers x the SM clock sampled under load
+        issue = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))
+            wi = prof["kernels"][top[0]]["warp_instructions"] * Sp / prof["sessions_per_launch"] * nmb / 8160.0
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_issue = sms * 4 * mhz * 1e6 / 1e9
+            ach_issue = wi / (top[1] * 1e-3) / 1e9
+            issue = {"kernel": top[0], "warp_instructions_per_launch": round(wi), "achieved_gwarp_instr_s": round(ach_issue, 1), "peak_gwarp_instr_s": round(peak_issue, 1),
+                     "frac": round(ach_issue / peak_issue, 4), "sms": sms, "sm_mhz": mhz,
+                     "note": "all executed warp-instructions (ncu smsp__inst_executed.sum of the committed capture) over the live kernel time; the kernel is issue-bound, this is the roofline that bounds it"}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(el / args.steps * 1e3, 4), "device_ms_per_step": round(dev_ms / args.steps, 4),
@@ -315,6 +330,7 @@ def run_b200(args):
                              "peak_gwarp_instr_s": round(gi.value / 32.0, 2), "peak_glane_instr_s": round(gi.value, 1), "sm_clock_mhz_in_peak_run": clk.value,
                              "frac": round(int_ach / (gi.value / 32.0), 4) if gi.value else None,
                              "unit": "G warp-instr/s of VABSDIFF4-equivalent work (px-absdiff/4/32)"},
+            "roofline_issue": issue,
             "clocks": clocks,
         }
         if cpu:

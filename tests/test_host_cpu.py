@@ -167,3 +167,18 @@ def test_unmodified_reference_wrapper_loads_the_shim(built, tmp_path):
     import torch
     assert ("init=0" if torch.cuda.is_available() else "init=2") in out.stdout, out.stdout + out.stderr
     assert "load openh264 shared lib failed" not in (out.stdout + out.stderr)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` times the CPU restatement of the path on the host cores (the arm the driver runs beside ours) and prints one
+    JSON line with our arm's metric / unit / config; no GPU is needed for it"""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "1080p H.264 encode frames/s per GPU" and line["unit"] == "frames/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "1920x1080" in cb["sample"]
