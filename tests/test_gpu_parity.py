@@ -646,3 +646,24 @@ def test_cabac_batch_of_rgba_sessions_equals_individual_sessions(enc, orc):
     bm.close()
     for s in ss + mixed[1:]:
         s.close()
+
+
+def test_main_and_high_sessions_share_a_batch(enc, orc):
+    """Main and High sessions of one geometry travel in one batch (both CABAC): the 8x8 transform pass, the transform_size_8x8_flag bins and the PPS
+    are per session, so every stream must equal its own oracle stream"""
+    w, h, n, qp = 320, 192, 4, 30
+    profiles = [1, 2, 2, 1]
+    cs = [Content("A", w, h, seed=300 + i) for i in range(n)]
+    ss = [enc.Session(w, h, const_qp=qp, gop=1000, device=0, profile=profiles[i], num_slices=2) for i in range(n)]
+    os_ = [orc.Encoder(w, h, num_slices=2, profile=profiles[i]) for i in range(n)]
+    b = enc.Batch(0, ss)
+    for t in range(4):
+        frames = [cs[i].frame(t) for i in range(n)]
+        out, _ = b.encode(frames)
+        for i in range(n):
+            assert out[i] == os_[i].encode(frames[i], t == 0, qp), f"session {i} (profile {profiles[i]}) frame {t}"
+    t8 = [int(((s.stage("mbinfo")["i16_mode"] >> 2) & 1).sum()) for s in ss]
+    assert t8[0] == 0 and t8[3] == 0 and t8[1] + t8[2] > 0
+    for s in ss:
+        s.close()
+    b.close()
