@@ -228,6 +228,24 @@ def test_high_profile_8x8_transform_streams_decode(orc, w, h, kind, qp, slices):
     assert len(dec) == 5 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
 
 
+def test_high_profile_random_geometries_decode(orc):
+    """seeded sweep of High-profile streams (odd sizes, QP 0..51, 1-3 slices, both search ranges, contents A / B / D) through the independent decoder"""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    rng = np.random.default_rng(77); total8 = 0
+    for trial in range(30):
+        w = int(rng.integers(1, 24)) * 16 + int(rng.integers(0, 8)) * 2; h = int(rng.integers(1, 16)) * 16 + int(rng.integers(0, 8)) * 2
+        qp = int(rng.choice([0, 8, 18, 26, 33, 36, 41, 47, 51])); slices = int(rng.integers(1, 4)); sr = int(rng.choice([16, 32]))
+        kind = str(rng.choice(["A", "B", "D"]))
+        o = orc.Encoder(w, h, num_slices=slices, search_range=sr, profile=2); c = Content(kind, w, h)
+        aus, recs = [], []
+        for t in range(4):
+            aus.append(o.encode(c.frame(t), t == 0, qp)); recs.append(o.recon()); total8 += int(((o.mb_info()["i16_mode"] >> 2) & 1).sum())
+        dec = avdec.decode_stream(aus)
+        assert len(dec) == 4 and all(np.array_equal(a, b) for a, b in zip(dec, recs)), (trial, w, h, qp, slices, sr, kind)
+    assert total8 > 100
+
+
 def test_sad_satd_definitions(orc):
     L = orc.lib(); rng = np.random.default_rng(2)
     a = rng.integers(0, 256, (16, 32), dtype=np.uint8); b = rng.integers(0, 256, (16, 32), dtype=np.uint8)
