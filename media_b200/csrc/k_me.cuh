@@ -215,13 +215,21 @@ __device__ __forceinline__ void pred_rows_qpel(const FineSmem &sm, int o1, int b
     const int common = (by + (oy >> 2) + 1) * PL_STRIDE + o1 + bx + (ox >> 2) + 4;
     const uint32_t *base = sm.plane[0];
     const int oa = common + (int)(t & 0xffffu);
+    // The row pitch (48 bytes) is a multiple of 4, so the byte shift is the same for all four rows, and rows y ^ rx are words
+    // {rx*12, 12 - rx*12} and the same + 24: two base pointers per plane, the rest are immediate offsets.
+    const int rxw = rx * (PL_STRIDE / 4);
+    const uint32_t *a0 = base + (oa >> 2) + rxw, *a1 = base + (oa >> 2) + (PL_STRIDE / 4) - rxw;
+    const int sa = (oa & 3) * 8;
+    const uint32_t A0 = __funnelshift_r(a0[0], a0[1], sa), A1 = __funnelshift_r(a1[0], a1[1], sa);
+    const uint32_t A2 = __funnelshift_r(a0[PL_STRIDE / 2], a0[PL_STRIDE / 2 + 1], sa), A3 = __funnelshift_r(a1[PL_STRIDE / 2], a1[PL_STRIDE / 2 + 1], sa);
     if (((ox | oy) & 1) == 0) {          // full/half-pel positions are a single plane (both table entries coincide)
-#pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = plane_row(base, oa + (y ^ rx) * PL_STRIDE);
+        P[0] = A0; P[1] = A1; P[2] = A2; P[3] = A3;
     } else {
         const int ob = common + (int)(t >> 16);
-#pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = avg4(plane_row(base, oa + (y ^ rx) * PL_STRIDE), plane_row(base, ob + (y ^ rx) * PL_STRIDE));
+        const uint32_t *b0 = base + (ob >> 2) + rxw, *b1 = base + (ob >> 2) + (PL_STRIDE / 4) - rxw;
+        const int sb = (ob & 3) * 8;
+        P[0] = avg4(A0, __funnelshift_r(b0[0], b0[1], sb)); P[1] = avg4(A1, __funnelshift_r(b1[0], b1[1], sb));
+        P[2] = avg4(A2, __funnelshift_r(b0[PL_STRIDE / 2], b0[PL_STRIDE / 2 + 1], sb)); P[3] = avg4(A3, __funnelshift_r(b1[PL_STRIDE / 2], b1[PL_STRIDE / 2 + 1], sb));
     }
 }
 // 4x4 Hadamard SATD of (source block - P): Ts holds the horizontal transforms of the source rows, the prediction
