@@ -446,7 +446,7 @@ def test_scene_change_idr_matches_the_oracle(enc, orc):
     w, h = 256, 160
     a, b = Content("A", w, h, seed=1), Content("A", w, h, seed=99)
     frames = [a.frame(0), a.frame(1), b.frame(2), b.frame(3), b.frame(4)]
-    for detect, profile in ((1, 0), (0, 0), (1, 1)):
+    for detect, profile in ((1, 0), (0, 0), (1, 1), (1, 2)):
         g = enc.Session(w, h, const_qp=28, gop=1000, device=0, scene_change=detect, profile=profile)
         o = orc.Encoder(w, h, scene_change=detect, profile=profile)
         types = []
