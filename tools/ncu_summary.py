@@ -54,5 +54,7 @@ if json_out:
                                 "alu_pipe_pct": num(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                                 "sm_throughput_pct": num(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
                                 "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
-                                "warp_instructions": num(r, "smsp__inst_executed.sum"), "registers": num(r, "launch__registers_per_thread")}
+                                "warp_instructions": num(r, "smsp__inst_executed.sum"), "registers": num(r, "launch__registers_per_thread"),
+                                "time_us": (num(r, "gpu__time_duration.sum") or 0.0) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[ix["gpu__time_duration.sum"]], 1.0),
+                                "grid": num(r, "launch__grid_size")}
     json.dump(out, open(json_out, "w"), indent=1)
