@@ -29,7 +29,10 @@ extern "C" {
 #endif
 
 /* ---- macroblock types used in the per-MB side arrays (shared layout with the CUDA path) ---- */
-enum { ORC_MB_P16x16 = 0, ORC_MB_I16x16 = 1, ORC_MB_I4x4 = 2, ORC_MB_PSKIP = 3, ORC_MB_P8x8 = 4 };
+enum { ORC_MB_P16x16 = 0, ORC_MB_I16x16 = 1, ORC_MB_I4x4 = 2, ORC_MB_PSKIP = 3, ORC_MB_P8x8 = 4,
+       ORC_MB_I8x8 = 5 /* I_NxN with transform_size_8x8_flag = 1; oracle only so far (OrcConfig.intra8x8), the CUDA path does not produce it */ };
+#define ORC_MB_IS_INTRA(m) ((m)->mb_type == ORC_MB_I16x16 || (m)->mb_type == ORC_MB_I4x4 || (m)->mb_type == ORC_MB_I8x8)
+#define ORC_MB_IS_INXN(m) ((m)->mb_type == ORC_MB_I4x4 || (m)->mb_type == ORC_MB_I8x8)
 
 /* Per-MB coefficient record: everything CAVLC needs, 816 bytes. Levels are in zig-zag scan order. */
 typedef struct {
@@ -47,7 +50,7 @@ typedef struct {
     uint8_t  cbp;            /* bits 0..3 luma 8x8, bits 4..5 chroma (0,1,2) */
     int16_t  mv[2];          /* quarter-pel; the 16x16 vector (partition 0 for P_8x8) */
     union {
-        uint8_t i4_mode[16]; /* intra MBs: Intra4x4PredMode per blkIdx */
+        uint8_t i4_mode[16]; /* intra MBs: Intra4x4PredMode per blkIdx (Intra_8x8: the 8x8 block's mode in all four of its entries) */
         int16_t mv8[4][2];   /* inter MBs: vector of each 8x8 partition (all equal for P_L0_16x16 / P_Skip) */
     };
     uint8_t  nnz[24];        /* total_coeff: 0..15 luma blkIdx, 16..19 Cb, 20..23 Cr (AC count for I16x16/chroma) */
@@ -83,6 +86,8 @@ typedef struct {
     int profile;             /* 0 Constrained Baseline / CAVLC; 1 Main / CABAC; 2 High / CABAC with the 8x8 transform on inter MBs, the
                                 wrapper's persist.vmi.video.encode.profile values (VideoEncoderOpenH264.cpp:248-253) */
     int no_t8x8;             /* 1: High profile without the 8x8 transform (transform_8x8_mode_flag = 0; quality A/B runs) */
+    int intra8x8;            /* 1: High profile intra MBs may also take Intra_8x8 (8.3.2). GROUNDWORK for the next round: pinned by the decoder
+                                round trip on the CPU, not yet built in CUDA, so the product and every parity test run with 0 */
 } OrcConfig;
 #define ORC_MB_T8(m) (((m)->i16_mode >> 2) & 1)
 

@@ -116,7 +116,7 @@ static void put_residual8(Bins *s, const int16_t *c)
     }
 }
 
-#define IS_INTRA(m) ((m)->mb_type == ORC_MB_I16x16 || (m)->mb_type == ORC_MB_I4x4)
+#define IS_INTRA(m) ORC_MB_IS_INTRA(m)
 static const uint8_t XY2BLK[4][4] = { { 0, 1, 4, 5 }, { 2, 3, 6, 7 }, { 8, 9, 12, 13 }, { 10, 11, 14, 15 } };
 static const uint8_t BX[16] = { 0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3 }, BY[16] = { 0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3 };
 
@@ -145,7 +145,7 @@ int orc_cabac_mb_bins(const OrcMbInfo *mbi, const OrcMbCoef *coef, const OrcMbSi
     } else {
         int b0, c_cl, c_cc, c_cc2, c_m1, c_m0;
         if (is_p) { put(&s, 14, 1); b0 = 17; c_cl = 18; c_cc = 19; c_cc2 = 19; c_m1 = 20; c_m0 = 20; }
-        else { b0 = 3 + (L && L->mb_type != ORC_MB_I4x4) + (T && T->mb_type != ORC_MB_I4x4); c_cl = 6; c_cc = 7; c_cc2 = 8; c_m1 = 9; c_m0 = 10; }
+        else { b0 = 3 + (L && !ORC_MB_IS_INXN(L)) + (T && !ORC_MB_IS_INXN(T)); c_cl = 6; c_cc = 7; c_cc2 = 8; c_m1 = 9; c_m0 = 10; }
         put(&s, b0, m->mb_type == ORC_MB_I16x16);
         if (m->mb_type == ORC_MB_I16x16) {
             put(&s, 276, 0);                                                               /* not I_PCM */
@@ -156,7 +156,13 @@ int orc_cabac_mb_bins(const OrcMbInfo *mbi, const OrcMbCoef *coef, const OrcMbSi
     }
     /* transform_size_8x8_flag (7.3.5, ctxIdx 399 + the neighbours' flags, 9.3.3.1.1.10): 0 for I_NxN (Intra_4x4 only) */
     int t8inc = (L && ORC_MB_T8(L)) + (T && ORC_MB_T8(T));
-    if (m->mb_type == ORC_MB_I4x4 && transform8x8) put(&s, 399 + t8inc, 0);
+    if (ORC_MB_IS_INXN(m) && transform8x8) put(&s, 399 + t8inc, m->mb_type == ORC_MB_I8x8);
+    if (m->mb_type == ORC_MB_I8x8)
+        for (int k = 0; k < 4; k++) {                                                      /* prev_intra8x8_pred_mode_flag / rem_intra8x8_pred_mode: same contexts */
+            int r = sd->i4_syn[k];
+            put(&s, 68, r == 8);
+            if (r != 8) { put(&s, 69, r & 1); put(&s, 69, (r >> 1) & 1); put(&s, 69, (r >> 2) & 1); }
+        }
     if (m->mb_type == ORC_MB_I4x4)
         for (int k = 0; k < 16; k++) {                                                     /* prev_intra4x4_pred_mode_flag / rem_intra4x4_pred_mode */
             int r = sd->i4_syn[k];

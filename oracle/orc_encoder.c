@@ -22,6 +22,7 @@
 #define ORC_MB_BINS_MAX 4096   /* bound of one MB's bin list: 384 levels of at most 2 + 14 + 27 + 1 bins (|level| <= 2064) is far above real use; checked */
 #define HP_M 4   /* margin of the half-pel planes, see build_halfpel() */
 #define T8X8_ON(e) ((e)->cfg.profile == 2 && !(e)->cfg.no_t8x8)   /* PPS transform_8x8_mode_flag */
+#define I8X8_ON(e) (T8X8_ON(e) && (e)->cfg.intra8x8)                /* Intra_8x8 on trial (oracle-only groundwork) */
 
 struct OrcEncoder {
     OrcConfig cfg;
@@ -627,10 +628,10 @@ static int i4_pred_mode(const OrcEncoder *e, int mx, int my, int b)
     static const uint8_t XY2B[4][4] = { { 0, 1, 4, 5 }, { 2, 3, 6, 7 }, { 8, 9, 12, 13 }, { 10, 11, 14, 15 } };
     if (bx > 0) ma = m->i4_mode[XY2B[by][bx - 1]];
     else if (mx == 0) return 2;
-    else ma = (m - 1)->mb_type == ORC_MB_I4x4 ? (m - 1)->i4_mode[XY2B[by][3]] : 2;
+    else ma = ORC_MB_IS_INXN(m - 1) ? (m - 1)->i4_mode[XY2B[by][3]] : 2;
     if (by > 0) mb_ = m->i4_mode[XY2B[by - 1][bx]];
     else if (row_is_slice_top(e, my)) return 2;
-    else mb_ = (m - e->mbw)->mb_type == ORC_MB_I4x4 ? (m - e->mbw)->i4_mode[XY2B[3][bx]] : 2;
+    else mb_ = ORC_MB_IS_INXN(m - e->mbw) ? (m - e->mbw)->i4_mode[XY2B[3][bx]] : 2;
     return ma < mb_ ? ma : mb_;
 }
 #define ORC_I4_BIAS_BITS 24   /* fixed cost of choosing Intra_4x4 (16 mode flags), in lambda units */
@@ -672,6 +673,156 @@ static int code_intra4x4_luma(OrcEncoder *e, int mx, int my, int qp, int lambda)
     return total;
 }
 
+/* ---- Intra_8x8 (High profile), 8.3.2. GROUNDWORK: oracle only (OrcConfig.intra8x8), pinned by the decoder round trip. ----
+ * Reference samples of an 8x8 block with the filtering of 8.3.2.2.1: T[0..15] = p'[x,-1], L[0..7] = p'[-1,y], X = p'[-1,-1].
+ * avail: I4_AV_T / _L / _X / _TR as for Intra_4x4 (top-right missing: p[8..15,-1] = p[7,-1]). */
+typedef struct { int T[16], L[8], X, top, left, corner; } I8Ref;
+static void i8_reference(const uint8_t *r, int st, int avail, I8Ref *o)
+{
+    int t[16], l[8], x = 128;
+    o->top = !!(avail & I4_AV_T); o->left = !!(avail & I4_AV_L); o->corner = !!(avail & I4_AV_X);
+    for (int i = 0; i < 16; i++) t[i] = 128;
+    for (int i = 0; i < 8; i++) l[i] = 128;
+    if (o->top) { for (int i = 0; i < 8; i++) t[i] = r[i - st]; for (int i = 8; i < 16; i++) t[i] = (avail & I4_AV_TR) ? r[i - st] : t[7]; }
+    if (o->left) for (int i = 0; i < 8; i++) l[i] = r[i * st - 1];
+    if (o->corner) x = r[-st - 1];
+    for (int i = 0; i < 16; i++) o->T[i] = t[i];
+    for (int i = 0; i < 8; i++) o->L[i] = l[i];
+    o->X = x;
+    if (o->top) {
+        o->T[0] = o->corner ? (x + 2 * t[0] + t[1] + 2) >> 2 : (3 * t[0] + t[1] + 2) >> 2;
+        for (int i = 1; i < 15; i++) o->T[i] = (t[i - 1] + 2 * t[i] + t[i + 1] + 2) >> 2;
+        o->T[15] = (t[14] + 3 * t[15] + 2) >> 2;
+    }
+    if (o->corner) {
+        if (o->top && o->left) o->X = (t[0] + 2 * x + l[0] + 2) >> 2;
+        else if (o->top) o->X = (3 * x + t[0] + 2) >> 2;
+        else if (o->left) o->X = (3 * x + l[0] + 2) >> 2;
+    }
+    if (o->left) {
+        o->L[0] = o->corner ? (x + 2 * l[0] + l[1] + 2) >> 2 : (3 * l[0] + l[1] + 2) >> 2;
+        for (int i = 1; i < 7; i++) o->L[i] = (l[i - 1] + 2 * l[i] + l[i + 1] + 2) >> 2;
+        o->L[7] = (l[6] + 3 * l[7] + 2) >> 2;
+    }
+}
+/* the nine Intra_8x8 predictors, 8.3.2.2.2 .. 8.3.2.2.10; returns 0 when the mode's neighbours are missing */
+static int pred_i8(const I8Ref *f, int mode, uint8_t *p /*64*/)
+{
+    const int *T = f->T, *L = f->L; int X = f->X, all = f->top && f->left && f->corner;
+#define PT8(i) ((i) < 0 ? X : T[i])
+#define PL8(i) ((i) < 0 ? X : L[i])
+    switch (mode) {
+    case 0: if (!f->top) return 0; for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) p[y * 8 + x] = (uint8_t)T[x]; return 1;
+    case 1: if (!f->left) return 0; for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) p[y * 8 + x] = (uint8_t)L[y]; return 1;
+    case 2: {
+        int sT = 0, sL = 0; for (int i = 0; i < 8; i++) { sT += T[i]; sL += L[i]; }
+        int v = f->top && f->left ? (sT + sL + 8) >> 4 : f->top ? (sT + 4) >> 3 : f->left ? (sL + 4) >> 3 : 128;
+        memset(p, v, 64); return 1; }
+    case 3: if (!f->top) return 0;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++)
+            p[y * 8 + x] = (uint8_t)(x == 7 && y == 7 ? (T[14] + 3 * T[15] + 2) >> 2 : (T[x + y] + 2 * T[x + y + 1] + T[x + y + 2] + 2) >> 2);
+        return 1;
+    case 4: if (!all) return 0;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++)
+            p[y * 8 + x] = (uint8_t)(x > y ? (PT8(x - y - 2) + 2 * PT8(x - y - 1) + PT8(x - y) + 2) >> 2
+                                   : x < y ? (PL8(y - x - 2) + 2 * PL8(y - x - 1) + PL8(y - x) + 2) >> 2 : (T[0] + 2 * X + L[0] + 2) >> 2);
+        return 1;
+    case 5: if (!all) return 0;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            int z = 2 * x - y, i = x - (y >> 1), v;
+            if (z >= 0 && !(z & 1)) v = (PT8(i - 1) + PT8(i) + 1) >> 1;
+            else if (z >= 0) v = (PT8(i - 2) + 2 * PT8(i - 1) + PT8(i) + 2) >> 2;
+            else if (z == -1) v = (L[0] + 2 * X + T[0] + 2) >> 2;
+            else v = (PL8(y - 2 * x - 1) + 2 * PL8(y - 2 * x - 2) + PL8(y - 2 * x - 3) + 2) >> 2;
+            p[y * 8 + x] = (uint8_t)v;
+        }
+        return 1;
+    case 6: if (!all) return 0;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            int z = 2 * y - x, i = y - (x >> 1), v;
+            if (z >= 0 && !(z & 1)) v = (PL8(i - 1) + PL8(i) + 1) >> 1;
+            else if (z >= 0) v = (PL8(i - 2) + 2 * PL8(i - 1) + PL8(i) + 2) >> 2;
+            else if (z == -1) v = (L[0] + 2 * X + T[0] + 2) >> 2;
+            else v = (PT8(x - 2 * y - 1) + 2 * PT8(x - 2 * y - 2) + PT8(x - 2 * y - 3) + 2) >> 2;
+            p[y * 8 + x] = (uint8_t)v;
+        }
+        return 1;
+    case 7: if (!f->top) return 0;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            int i = x + (y >> 1);
+            p[y * 8 + x] = (uint8_t)((y & 1) ? (T[i] + 2 * T[i + 1] + T[i + 2] + 2) >> 2 : (T[i] + T[i + 1] + 1) >> 1);
+        }
+        return 1;
+    default: if (!f->left) return 0;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            int z = x + 2 * y, i = y + (x >> 1), v;
+            if (z > 13) v = L[7];
+            else if (z == 13) v = (L[6] + 3 * L[7] + 2) >> 2;
+            else if (z & 1) v = (L[i] + 2 * L[i + 1] + L[i + 2] + 2) >> 2;
+            else v = (L[i] + L[i + 1] + 1) >> 1;
+            p[y * 8 + x] = (uint8_t)v;
+        }
+        return 1;
+    }
+#undef PT8
+#undef PL8
+}
+/* predIntra8x8PredMode of 8x8 block b (8.3.2.1): the neighbouring I_NxN MB's mode of the 4x4 block 4 * blk8 + 1 (left) / + 2 (above);
+ * Intra_8x8 MBs keep their block modes in all four entries, so one lookup serves both kinds */
+static int i8_pred_mode(const OrcEncoder *e, int mx, int my, int b)
+{
+    const OrcMbInfo *m = &e->mbi[my * e->mbw + mx]; int ma, mb_;
+    if (b & 1) ma = m->i4_mode[4 * (b - 1) + 1];
+    else if (mx == 0) return 2;
+    else ma = ORC_MB_IS_INXN(m - 1) ? (m - 1)->i4_mode[4 * (b + 1) + 1] : 2;
+    if (b & 2) mb_ = m->i4_mode[4 * (b - 2) + 2];
+    else if (row_is_slice_top(e, my)) return 2;
+    else mb_ = ORC_MB_IS_INXN(m - e->mbw) ? (m - e->mbw)->i4_mode[4 * (b + 2) + 2] : 2;
+    return ma < mb_ ? ma : mb_;
+}
+#define ORC_I8_BIAS_BITS 12   /* fixed cost of choosing Intra_8x8 (four mode flags, the transform flag), in lambda units */
+/* Try Intra_8x8 on the luma of one MB, the four blocks in decoding order, each reconstructed at once (the next one predicts from it).
+ * Returns the cost; fills i4_mode (replicated), the 8x8 levels, nnz, cbp luma bits; reconstruction in e->rec. */
+static int code_intra8x8_luma(OrcEncoder *e, int mx, int my, int qp, int lambda)
+{
+    int mb = my * e->mbw + mx, st = e->wc; OrcMbInfo *mi = &e->mbi[mb]; OrcMbCoef *co = &e->coef[mb];
+    int top = !row_is_slice_top(e, my), left = mx > 0, topright = top && mx + 1 < e->mbw;
+    const uint8_t *s = e->src[0] + (size_t)my * 16 * st + mx * 16; uint8_t *r = e->rec[0] + (size_t)my * 16 * st + mx * 16;
+    int total = lambda * ORC_I8_BIAS_BITS, cbp = 0;
+    mi->mb_type = ORC_MB_I8x8;
+    for (int b = 0; b < 4; b++) {
+        int bx = (b & 1) * 8, by = (b >> 1) * 8, avail = 0;
+        int at = by ? 1 : top, al = bx ? 1 : left;
+        int ax = b == 0 ? (top && left) : b == 1 ? top : b == 2 ? left : 1;
+        int atr = b == 0 ? top : b == 1 ? topright : b == 2 ? 1 : 0;
+        if (at) avail |= I4_AV_T;
+        if (al) avail |= I4_AV_L;
+        if (ax) avail |= I4_AV_X;
+        if (at && atr) avail |= I4_AV_TR;
+        const uint8_t *sb = s + by * st + bx; uint8_t *rb = r + by * st + bx;
+        I8Ref ref; i8_reference(rb, st, avail, &ref);
+        int pm = i8_pred_mode(e, mx, my, b); uint32_t best = 0xffffffffu; uint8_t pred[64], bp[64];
+        for (int m = 0; m < 9; m++) {
+            if (!pred_i8(&ref, m, pred)) continue;
+            int satd = orc_satd4x4(sb, st, pred, 8) + orc_satd4x4(sb + 4, st, pred + 4, 8) + orc_satd4x4(sb + 4 * st, st, pred + 32, 8) + orc_satd4x4(sb + 4 * st + 4, st, pred + 36, 8);
+            uint32_t key = ((uint32_t)(satd + lambda * (m == pm ? 1 : 4)) << 4) | (uint32_t)m;
+            if (key < best) { best = key; memcpy(bp, pred, 64); }
+        }
+        for (int k = 0; k < 4; k++) mi->i4_mode[4 * b + k] = (uint8_t)(best & 15);
+        total += (int)(best >> 4);
+        int16_t res[64]; int32_t c[64], d[64], rr[64];
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) res[y * 8 + x] = (int16_t)(sb[y * st + x] - bp[y * 8 + x]);
+        orc_dct8x8(res, c);
+        int n = orc_quant8x8(c, co->luma[4 * b], qp, 1);
+        for (int k = 0; k < 4; k++) mi->nnz[4 * b + k] = (uint8_t)n;
+        if (n) cbp |= 1 << b;
+        orc_dequant8x8(co->luma[4 * b], d, qp); orc_idct8x8(d, rr);
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) rb[y * st + x] = (uint8_t)clip255(bp[y * 8 + x] + rr[y * 8 + x]);
+    }
+    mi->cbp = (uint8_t)cbp;
+    return total;
+}
+
 /* ---- Phase C: one intra MB (roles of WelsMdI16x16, WelsMdI4x4, WelsIChromaPred*, WelsHadamardT4Dc_c, WelsDequantIHadamard4x4_c).
  * Intra_16x16 mode by SATD; Intra_4x4 is coded on trial and kept when its cost is below the Intra_16x16 SATD. ---- */
 static void code_intra_mb(OrcEncoder *e, int mx, int my, int qp)
@@ -688,7 +839,41 @@ static void code_intra_mb(OrcEncoder *e, int mx, int my, int qp)
         if (key < best) { best = key; mode = m; memcpy(best_pred, pred, 256); }
     }
     mi->mv[0] = mi->mv[1] = 0; mi->i16_mode = 0;
-    int use_i4 = e->cfg.no_i4x4 ? 0 : code_intra4x4_luma(e, mx, my, qp, LAMBDA_TAB[qp]) < (int)(best >> 2);
+    /* Intra_8x8 on trial first (High profile groundwork): its outcome is kept aside while Intra_4x4 is tried on the same samples. The two
+     * I_NxN codings are compared by J = 64 SSD + 27 lambda^2 B like the inter transform choice (B in half bits: levels + 2 x mode bits);
+     * the winner then meets Intra_16x16 with its SATD cost as before. */
+    int cost8 = 1 << 30, use_i8 = 0; OrcMbInfo keep_mi; int16_t keep_luma[16][16]; uint8_t keep_rec[256]; int64_t j8 = 0;
+    int64_t l2 = 27 * (int64_t)LAMBDA_TAB[qp] * LAMBDA_TAB[qp];
+    if (I8X8_ON(e)) {
+        cost8 = code_intra8x8_luma(e, mx, my, qp, LAMBDA_TAB[qp]);
+        keep_mi = *mi; memcpy(keep_luma, co->luma, sizeof keep_luma);
+        int rate = 2;
+        for (int b = 0; b < 4; b++) {
+            rate += 2 * (mi->i4_mode[4 * b] == i8_pred_mode(e, mx, my, b) ? 1 : 4);
+            if (mi->cbp & (1 << b)) rate += level_cost2(co->luma[4 * b], 64);
+        }
+        int64_t ssd = 0;
+        for (int y = 0; y < 16; y++) { memcpy(keep_rec + y * 16, r + y * st, 16); for (int x = 0; x < 16; x++) { int d = s[y * st + x] - r[y * st + x]; ssd += d * d; } }
+        j8 = 64 * ssd + l2 * rate;
+        memset(co, 0, sizeof *co); memset(mi->i4_mode, 0, 16); memset(mi->nnz, 0, 16);
+    }
+    int cost4 = e->cfg.no_i4x4 ? 1 << 30 : code_intra4x4_luma(e, mx, my, qp, LAMBDA_TAB[qp]);
+    if (I8X8_ON(e) && cost4 < (1 << 30)) {
+        int rate = 0; int64_t ssd = 0;
+        for (int k = 0; k < 16; k++) {
+            rate += 2 * (mi->i4_mode[k] == i4_pred_mode(e, mx, my, k) ? 1 : 4);
+            if (mi->cbp & (1 << (k >> 2))) rate += 1 + level_cost2(co->luma[k], 16);
+        }
+        for (int y = 0; y < 16; y++) for (int x = 0; x < 16; x++) { int d = s[y * st + x] - r[y * st + x]; ssd += d * d; }
+        if (j8 < 64 * ssd + l2 * rate) use_i8 = 1;
+    } else if (I8X8_ON(e)) use_i8 = 1;
+    int use_i4 = (use_i8 ? cost8 : cost4) < (int)(best >> 2);
+    if (use_i8 && use_i4) {                                      /* Intra_8x8 wins: put its outcome back */
+        *mi = keep_mi; memcpy(co->luma, keep_luma, sizeof keep_luma);
+        for (int y = 0; y < 16; y++) memcpy(r + y * st, keep_rec + y * 16, 16);
+        mi->i16_mode = 4;                                        /* transform_size_8x8_flag */
+    }
+    (void)use_i8;
     int luma_cbp = mi->cbp & 15;
     if (!use_i4) {
     memset(co, 0, sizeof *co); memset(mi->i4_mode, 0, 16);
@@ -860,6 +1045,8 @@ static void cabac_side_records(OrcEncoder *e, int is_idr)
                 }
             } else if (mi->mb_type == ORC_MB_I4x4) {
                 for (int k = 0; k < 16; k++) { int pm = i4_pred_mode(e, mx, my, k), m = mi->i4_mode[k]; sd->i4_syn[k] = (uint8_t)(m == pm ? 8 : m < pm ? m : m - 1); }
+            } else if (mi->mb_type == ORC_MB_I8x8) {
+                for (int k = 0; k < 4; k++) { int pm = i8_pred_mode(e, mx, my, k), m = mi->i4_mode[4 * k]; sd->i4_syn[k] = (uint8_t)(m == pm ? 8 : m < pm ? m : m - 1); }
             }
             if (mi->mb_type == ORC_MB_PSKIP) continue;
             int dc = 0;

@@ -326,7 +326,7 @@ static void filter_chroma(uint8_t *p, int step, int bs, int alpha, int beta, int
     }
 }
 
-static int mb_is_intra(const OrcMbInfo *m) { return m->mb_type == ORC_MB_I16x16 || m->mb_type == ORC_MB_I4x4; }
+static int mb_is_intra(const OrcMbInfo *m) { return ORC_MB_IS_INTRA(m); }
 
 /* bS between 4x4 block (bxq,byq) of MB q and the adjacent block (bxp,byp) of MB p; mb_edge = on a MB boundary */
 static int boundary_strength(const OrcMbInfo *mp, int bxp, int byp, const OrcMbInfo *mq, int bxq, int byq, int mb_edge)

@@ -246,6 +246,26 @@ def test_high_profile_random_geometries_decode(orc):
     assert total8 > 100
 
 
+@pytest.mark.parametrize("w,h,kind,qp,slices", [(176, 144, "A", 26, 1), (320, 240, "A", 40, 2), (320, 240, "B", 24, 1), (208, 160, "D", 33, 3), (48, 32, "A", 30, 1)])
+def test_intra8x8_groundwork_streams_decode(orc, w, h, kind, qp, slices):
+    """Intra_8x8 (8.3.2: reference sample filtering, nine predictors, mode prediction across Intra_4x4 / Intra_8x8 neighbours, I_NxN with
+    transform_size_8x8_flag = 1) exists in the oracle only (OrcConfig.intra8x8, off by default; the CUDA path follows next round). The
+    independent decoder must reproduce the reconstruction, key frames and intra MBs of P pictures alike."""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    o = orc.Encoder(w, h, num_slices=slices, profile=2, intra8x8=1); c = Content(kind, w, h)
+    aus, recs, n8 = [], [], 0
+    for t in range(4):
+        aus.append(o.encode(c.frame(t), t in (0, 3), qp)); recs.append(o.recon())
+        mi = o.mb_info(); i8 = mi["mb_type"] == 5; n8 += int(i8.sum())
+        assert (((mi["i16_mode"][i8] >> 2) & 1) == 1).all()
+        for m in np.flatnonzero(i8):
+            assert all(len(set(mi["i4_mode"][m][4 * b: 4 * b + 4])) == 1 for b in range(4))
+    assert n8 > 0
+    dec = avdec.decode_stream(aus)
+    assert len(dec) == 4 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+
+
 def test_sad_satd_definitions(orc):
     L = orc.lib(); rng = np.random.default_rng(2)
     a = rng.integers(0, 256, (16, 32), dtype=np.uint8); b = rng.integers(0, 256, (16, 32), dtype=np.uint8)
