@@ -35,3 +35,14 @@ for kind in "AB":
                 bits.append(len(au) * 8); ps.append(psnr(f[:W * H], e.recon()[:W * H]))
             mi = e.mb_info(); inter = (mi["mb_type"] == 0) | (mi["mb_type"] == 4)
             print(f"| {kind} | {qp} | {name} | {np.mean(bits[1:]) / 1000:.1f} | {np.mean(ps[1:]):.2f} | {int(((mi['i16_mode'] >> 2) & 1).sum())} of {int(inter.sum())} |")
+
+# High profile groundwork (oracle only so far): Intra_8x8 on key frames
+print()
+print("| content | QP | High profile key frame | IDR KB | Y-PSNR dB (IDR) | MBs Intra_16x16 / Intra_4x4 / Intra_8x8 |")
+print("|---|---|---|---|---|---|")
+for kind in "AB":
+    for qp in (24, 30, 36, 42):
+        for name, kw in (("I16x16 / I4x4", {}), ("+ Intra_8x8 (oracle only)", dict(intra8x8=1))):
+            e = orc_py.Encoder(W, H, profile=2, **kw); c = Content(kind, W, H)
+            f = c.frame(0); au = e.encode(f, True, qp); ty = e.mb_info()["mb_type"]
+            print(f"| {kind} | {qp} | {name} | {len(au) / 1024:.1f} | {psnr(f[:W * H], e.recon()[:W * H]):.2f} | {int((ty == 1).sum())} / {int((ty == 2).sum())} / {int((ty == 5).sum())} |")
