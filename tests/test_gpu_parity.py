@@ -667,3 +667,85 @@ def test_main_and_high_sessions_share_a_batch(enc, orc):
     for s in ss:
         s.close()
     b.close()
+
+
+# ---- BASELINE.json configs 2-4 at full size against the oracle (bitstream + reconstruction, bit-exact) ----
+def test_config2_1080p_cbr_4mbps_matches_the_oracle(enc, orc):
+    """BASELINE.json configs[1]: 1920x1080, content A, Baseline IPPP, CBR 4 Mbps -- rate control is host logic outside the oracle, so the
+    oracle is driven with the QP and the key-frame decisions the encoder reports per frame (reference: the wrapper's RC_BITRATE_MODE,
+    VideoEncoderOpenH264.cpp:274); every access unit and every reconstruction must then be identical"""
+    w, h = 1920, 1080
+    g = enc.Session(w, h, fps=30, bitrate=4_000_000, gop=300, const_qp=-1, device=0)
+    o = orc.Encoder(w, h)
+    c = Content("A", w, h)
+    qps = []
+    for t in range(9):
+        f = c.frame(t)
+        if t == 6:
+            g.force_idr()
+        bs, info = g.encode(f)
+        ref = o.encode(f, t in (0, 6), info.qp)
+        assert info.frame_type == int(o.last_was_idr()) == (1 if t in (0, 6) else 0), f"frame {t} kind"
+        assert bs == ref, f"frame {t}: bitstream differs from the oracle at QP {info.qp} ({len(bs)} vs {len(ref)} bytes)"
+        assert np.array_equal(g.recon(), o.recon()), f"frame {t}: reconstruction"
+        qps.append(info.qp)
+    assert len(set(qps)) > 1, "CBR never moved the QP: the test would not cover a QP change between pictures"
+    g.close()
+
+
+def test_config3_64_rgba_720p_sessions_in_one_batch(enc, orc):
+    """BASELINE.json configs[2]: 64 concurrent 1280x720 RGBA8888 framebuffers (content B, seed = base + session id) in ONE batch step,
+    on-GPU RGBA->I420 + encode, CBR 2 Mbps: every session's stream equals the stream it produces alone, and sessions 0, 21, 42, 63 equal
+    the oracle fed with the oracle's own colour conversion and the reported QPs"""
+    w, h, n, frames = 1280, 720, 64, 3
+    kw = dict(fps=30, bitrate=2_000_000, gop=300, const_qp=-1, device=0, input_format=enc.FMT_RGBA)
+    cs = [Content("B", w, h, seed=5000 + i) for i in range(n)]
+    data = [[np.ascontiguousarray(i420_to_rgba(cs[i].frame(t), w, h)).ravel() for t in range(frames)] for i in range(n)]
+    ss = [enc.Session(w, h, **kw) for _ in range(n)]
+    b = enc.Batch(0, ss)
+    got, qps = [], []
+    for t in range(frames):
+        out, infos = b.encode([data[i][t] for i in range(n)])
+        got.append(out); qps.append([x.qp for x in infos])
+    assert b.launches() < 30, "the 64 sessions did not travel in one chain of launches"
+    recs = {i: ss[i].recon() for i in (0, 21, 42, 63)}
+    b.close()
+    for s in ss:
+        s.close()
+    for i in range(n):
+        s = enc.Session(w, h, **kw)
+        for t in range(frames):
+            bs, info = s.encode(data[i][t])
+            assert info.qp == qps[t][i] and bs == got[t][i], f"session {i} frame {t}: batch step differs from the solo run"
+        s.close()
+    for i in (0, 21, 42, 63):
+        o = orc.Encoder(w, h)
+        for t in range(frames):
+            conv = np.zeros(w * h * 3 // 2, np.uint8); orc.lib().orc_rgba_to_i420(_p(data[i][t]), w, h, _p(conv))
+            assert got[t][i] == o.encode(conv, t == 0, qps[t][i]), f"session {i} frame {t}: bitstream differs from the oracle"
+        assert np.array_equal(recs[i], o.recon()), f"session {i}: reconstruction"
+
+
+def test_config4_2160p_8_slices_range64_matches_the_oracle(enc, orc):
+    """BASELINE.json configs[3]: 3840x2160, 8 slices, search +-64 with quarter-pel refinement, const QP 26, content A moving 40 px
+    per frame (beyond +-32, so the wide search decides): bitstream and reconstruction against the oracle, not only the decoder"""
+    w, h, qp = 3840, 2160, 26
+    base = Content("A", w, h).frame(0)
+    Y = base[:w * h].reshape(h, w); U = base[w * h:w * h * 5 // 4].reshape(h // 2, w // 2); V = base[w * h * 5 // 4:].reshape(h // 2, w // 2)
+    g = enc.Session(w, h, const_qp=qp, num_slices=8, search_range=64, gop=1000, device=0)
+    o = orc.Encoder(w, h, num_slices=8, search_range=64)
+    aus, recs = [], []
+    for t in range(3):
+        f = np.concatenate([np.roll(Y, (8 * t, 40 * t), (0, 1)).ravel(), np.roll(U, (4 * t, 20 * t), (0, 1)).ravel(), np.roll(V, (4 * t, 20 * t), (0, 1)).ravel()])
+        bs, _ = g.encode(f); ref = o.encode(f, t == 0, qp)
+        assert bs == ref, f"frame {t}: bitstream ({len(bs)} vs {len(ref)} bytes)"
+        rec = g.recon()
+        assert np.array_equal(rec, o.recon()), f"frame {t}: reconstruction"
+        aus.append(bs); recs.append(rec)
+    mv = g.stage("mbinfo")["mv"]
+    assert np.median(mv[:, 0]) == -160 and np.median(mv[:, 1]) == -32       # (-40, -8) px in quarter-pel units
+    assert sum(1 for i in range(len(aus[1]) - 4) if aus[1][i:i + 5] == b"\0\0\0\1\x61") == 8
+    if avdec.available():
+        dec = avdec.decode_stream(aus)
+        assert len(dec) == 3 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+    g.close()
