@@ -63,6 +63,11 @@ typedef struct b200enc_config {
                               scheduler thread into one batch step (what gives many single-threaded callers GPU-wide throughput) */
     int profile;           /* 0: Constrained Baseline, CAVLC; 1: Main, CABAC; 2: High, CABAC, 8x8 transform on inter MBs (transform_8x8_mode_flag) -- the wrapper's profile property
                               baseline / main / high (VideoEncoderOpenH264.cpp:186-188,248-253) with iEntropyCodingModeFlag = 1 (:291) */
+    int max_bitrate;       /* bits per second the one-second leaky bucket of the rate control drains at (iMaxBitrate; the wrapper sets it to the
+                              target, :239-240); 0 = bitrate */
+    int min_qp, max_qp;    /* QP bounds of the rate control (iMinQp / iMaxQp; the wrapper keeps GetDefaultParams' 0 / 51, :230); max_qp 0 = 51 */
+    int background_detection; /* bEnableBackgroundDetection (:282): static macroblocks are skipped on a pre-analysis of the source pictures */
+    int complexity;        /* iComplexityMode (:289; the wrapper asks for HIGH_COMPLEXITY): 0 LOW (no Intra_4x4 trial, no P_8x8), 1 MEDIUM (no P_8x8), 2 HIGH */
 } b200enc_config;
 
 typedef struct b200enc_frame_info {
@@ -99,6 +104,11 @@ void b200enc_batch_destroy(b200enc_batch *b);
 /* frames[i]: HOST pointer (device_input = 0) or DEVICE pointer already resident in HBM (device_input = 1). */
 int b200enc_batch_encode(b200enc_batch *b, b200enc_session *const *sessions, int n, const uint8_t *const *frames,
                          int device_input, const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *infos);
+/* Outcome per session of the last b200enc_batch_encode (B200ENC_OK / B200ENC_EOVERFLOW ...): one session's failure does not
+ * invalidate the others' access units. b200enc_batch_encode itself returns B200ENC_EOVERFLOW when any session overflowed. Returns the count. */
+int b200enc_batch_last_status(const b200enc_batch *b, int *rcs, int cap);
+/* pictures of this session the rate control coded twice (first attempt above the hard cap) */
+uint32_t b200enc_rc_retries(const b200enc_session *s);
 /* device time of the kernels of the last batch_encode / encode call, milliseconds (CUDA events on the encode stream) */
 float b200enc_batch_last_kernel_ms(const b200enc_batch *b);
 float b200enc_last_kernel_ms(const b200enc_session *s);
@@ -149,6 +159,15 @@ int b200k_cabac_code(int device, const uint16_t *bins, int n, int qp, int is_p, 
 /* the coder kernel `reps` times on `copies` independent copies of one list (one CTA each): average device ms per launch; stats[8]
  * = phase cycle counts in a -DCABAC_TIMING build, else zeros */
 int b200k_cabac_code_bench(int device, const uint16_t *bins, int n, int qp, int is_p, int reps, int copies, float *ms, long long *stats);
+/* the rate control object of the sessions (media_b200/csrc/rate_control.h) driven from outside with picture sizes -- host logic, no GPU:
+ * pick returns the QP for a picture of `type` (B200ENC_FRAME_*), retry_qp the QP of a second attempt or -1 (the picture was planned as
+ * planned_type and came out as coded_type: a scene-change promotion turns a P picture into an IDR), update commits a picture */
+void *b200k_rc_create(double bitrate, double max_bitrate, int fps, int min_qp, int max_qp, int width, int height);
+int b200k_rc_pick(void *rc, int type, double *budget_bits, double *hard_cap_bits);
+int b200k_rc_retry_qp(void *rc, int planned_type, int coded_type, double bits);
+void b200k_rc_update(void *rc, int type, int qp, double bits);
+double b200k_rc_vbv(void *rc, double *bucket_bits);
+void b200k_rc_destroy(void *rc);
 /* microbenchmark: register-resident VABSDIFF4.U8.ACC issue rate, giga lane-instructions per second, and the SM clock seen */
 int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz);
 

@@ -14,6 +14,7 @@
 #include "k_cavlc.cuh"
 #include "k_cabac.cuh"
 #include "k_test.cuh"
+#include "rate_control.h"
 #include <cuda.h>
 #include <cmath>
 #include <cstdio>
@@ -34,8 +35,9 @@ using namespace b200;
 
 namespace {
 
-thread_local int g_last_cuda_error = 0;
-#define CU_TRY(expr, fail) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_last_cuda_error = (int)e_; fail; } } while (0)
+// last CUDA error seen by any thread of the library (callers are served by scheduler worker threads, so a thread-local would hide it)
+std::atomic<int> g_last_cuda_error{ 0 };
+#define CU_TRY(expr, fail) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_last_cuda_error.store((int)e_); fail; } } while (0)
 
 // ---- session -> GPU placement: least load by pixel rate (analogue of the Netint path's EN_ALLOC_LEAST_LOAD,
 // reference video_codec/VideoEncoderNetint.cpp:300-302,552-554) ----
@@ -112,37 +114,6 @@ std::vector<uint8_t> make_parameter_sets(int w, int h, int level, int profile)
     return out;
 }
 
-// ---- rate control: frame-level QP from a bits ~ C / Qstep model with a virtual buffer (host logic; the
-// reference asks openh264 for RC_BITRATE_MODE at video_codec/VideoEncoderOpenH264.cpp:274, target = max bitrate :239-240) ----
-struct RateCtl {
-    double target = 0, vbv = 0, cplx[2] = { 0, 0 }; int last_qp[2] = { 30, 30 }; bool have[2] = { false, false }; int fps = 30;
-    static double qstep(int qp) { return std::pow(2.0, (qp - 4) / 6.0); }
-    int pick(int type, int w, int h)
-    {
-        if (!have[type]) {
-            if (type == 0 && have[1]) return std::max(12, last_qp[1] - 3);      // first P after the first IDR
-            const double bpp = target / ((double)w * h);
-            int qp = bpp > 0.2 ? 24 : bpp > 0.1 ? 28 : bpp > 0.05 ? 32 : bpp > 0.02 ? 36 : 40;
-            return type == 1 ? qp + 5 : qp;    // an intra picture costs ~10x a P picture at equal QP: start it coarser, not finer
-        }
-        // spread the buffer error over two seconds; an IDR may take four frame budgets
-        const double weight = type == 1 ? 4.0 : 1.0;
-        double want = target * weight - vbv / (2.0 * fps);
-        want = std::min(std::max(want, 0.5 * target * weight), 1.5 * target * weight);
-        int qp = (int)std::lround(4.0 + 6.0 * std::log2(cplx[type] / want));
-        qp = std::min(std::max(qp, last_qp[type] - 3), last_qp[type] + 3);
-        return std::min(std::max(qp, 12), 48);
-    }
-    void update(int type, int qp, double bits)
-    {
-        const double c = bits * qstep(qp);
-        cplx[type] = have[type] ? 0.5 * cplx[type] + 0.5 * c : c;
-        have[type] = true; last_qp[type] = qp;
-        vbv += bits - target;
-        vbv = std::min(std::max(vbv, -2.0 * fps * target), 4.0 * fps * target);
-    }
-};
-
 struct KernelTime { const char *name; cudaEvent_t ev0, ev1; };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -176,6 +147,7 @@ struct b200enc_batch {
     float last_ms = 0; int last_launches = 0;
     bool profiling = false;
     std::vector<KernelTime> ktimes; int n_ktimes = 0;
+    std::vector<int> last_rcs;                          // per-session outcome of the last b200enc_batch_encode
 };
 
 struct b200enc_session {
@@ -198,9 +170,13 @@ struct b200enc_session {
     bool cur_is_A = true;
     uint32_t frame_index = 0; int frames_since_idr = 0, frame_num = 0, idr_pic_id = 0; bool force_idr = true, have_ref = false;
     int last_qp = 26, last_type = 1;
-    RateCtl rc;
+    b200rc::RateCtl rc; b200rc::Decision rc_dec;
     b200enc_batch *own = nullptr;
     bool in_scheduler = false;
+    // upload path of b200enc_encode: the caller's thread copies its frame (through the pinned staging buffer when the caller's
+    // memory is pageable, as every reference caller's is) on the session's own stream; the batch step waits for ev_up
+    uint8_t *h_stage = nullptr; cudaStream_t up_stream = nullptr; cudaEvent_t ev_up = nullptr;
+    uint32_t retries = 0;                        // pictures coded twice by the rate control (hard cap)
 };
 
 namespace {
@@ -296,30 +272,54 @@ bool same_shape(const b200enc_session *a, const b200enc_session *c)
            (a->cfg.profile != 0) == (c->cfg.profile != 0);
 }
 
-int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8_t *const *frames, int device_input,
-                const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *infos)
+// where the frame of a step comes from
+enum { IN_HOST = 0,       // frames[i] is host memory: copied here (through the session's pinned staging buffer when it is pageable)
+       IN_DEVICE = 1,     // frames[i] is device memory of the batch's GPU (capture that already lives in HBM)
+       IN_UPLOADED = 2,   // the caller's thread already queued the copy on the session's upload stream (b200enc_encode): wait for ev_up
+       IN_RESIDENT = 3 }; // the frame is still in the session's input buffer (second attempt of the rate control)
+#define SC_MIN_DISTANCE 10   /* a P picture is only promoted to a scene-change IDR when at least this many pictures passed since the last IDR */
+
+bool host_ptr_is_pinned(const void *p)
 {
-    if (!b || !ss || n <= 0 || n > b->cap || !frames) return B200ENC_EINVAL;
-    for (int i = 0; i < n; i++) {
-        if (!ss[i] || !frames[i] || ss[i]->device != b->device || !same_shape(ss[0], ss[i])) return B200ENC_EINVAL;
-        for (int j = 0; j < i; j++) if (ss[j] == ss[i]) return B200ENC_EINVAL;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+// H2D copy of one frame on `st`. Caller-owned pageable memory (what the reference's callers hand to EncodeOneFrame,
+// video_codec/VideoCodecApi.h:57-58; zero-copy into openh264 at VideoEncoderOpenH264.cpp:354-365) goes through the session's pinned
+// staging buffer first -- the copy the Netint sibling also makes (VideoEncoderNetint.cpp:503-505) -- so the transfer itself is an
+// asynchronous DMA and concurrent sessions do not serialise on the driver's internal bounce buffer.
+int upload_frame(b200enc_session *s, const uint8_t *frame, cudaStream_t st)
+{
+    const size_t bytes = b200enc_frame_bytes(s);
+    const uint8_t *src = frame;
+    if (!host_ptr_is_pinned(frame)) {
+        if (!s->h_stage) CU_TRY(cudaHostAlloc(&s->h_stage, bytes, cudaHostAllocDefault), return B200ENC_ENOMEM);
+        memcpy(s->h_stage, frame, bytes);
+        src = s->h_stage;
     }
-    CU_TRY(cudaSetDevice(b->device), return B200ENC_ECUDA);
+    CU_TRY(cudaMemcpyAsync(s->input, src, bytes, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
+    return B200ENC_OK;
+}
+bool next_is_idr(const b200enc_session *s) { return s->force_idr || !s->have_ref || s->frames_since_idr >= s->cfg.gop; }
+
+// One chain of kernel launches over n sessions: descriptors, launches, one stream synchronisation. kinds[i] 1 = IDR; qps[i] the picture QP.
+// Does not touch the sessions' stream state (frame_num, reference roles, rate control): the caller commits or repeats the step.
+int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8_t *const *frames, int mode, const int *kinds, const int *qps)
+{
     const Geom g = ss[0]->g;
-    const size_t in_bytes = b200enc_frame_bytes(ss[0]);
     bool any_p = false;
-    for (int i = 0; i < n; i++) any_p |= !(ss[i]->force_idr || !ss[i]->have_ref || ss[i]->frames_since_idr >= ss[i]->cfg.gop);
+    for (int i = 0; i < n; i++) any_p |= !kinds[i];
     cudaStream_t st = any_p ? b->stream : b->stream_hi;      // a batch of key frames only gets the high-priority stream
     for (int i = 0; i < n; i++) {
         b200enc_session *s = ss[i];
-        const bool idr = s->force_idr || !s->have_ref || s->frames_since_idr >= s->cfg.gop;
-        const int qp = s->cfg.const_qp >= 0 ? s->cfg.const_qp : s->rc.pick(idr ? 1 : 0, s->cfg.width, s->cfg.height);
-        if (idr) { s->frame_num = 0; s->frames_since_idr = 0; }
-        s->last_qp = qp; s->last_type = idr ? 1 : 0;
+        const bool idr = kinds[i] != 0;
         uint8_t **cur = s->cur_is_A ? s->bufA : s->bufB, **ref = s->cur_is_A ? s->bufB : s->bufA;
         Sess &d = b->h_sess[i];
-        if (device_input) d.input = frames[i];
-        else { d.input = s->input; CU_TRY(cudaMemcpyAsync(s->input, frames[i], in_bytes, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA); }
+        d.input = s->input;
+        if (mode == IN_DEVICE) d.input = frames[i];
+        else if (mode == IN_HOST) { const int rc = upload_frame(s, frames[i], st); if (rc != B200ENC_OK) return rc; }
+        else if (mode == IN_UPLOADED) CU_TRY(cudaStreamWaitEvent(st, s->ev_up, 0), return B200ENC_ECUDA);
         for (int c = 0; c < 3; c++) { d.src[c] = s->src[c]; d.rec[c] = cur[c]; d.ref[c] = ref[c]; }
         {   // padded planes: hand the kernels the address of the interior sample (0,0)
             const size_t o1 = (size_t)g.p1 * g.s1 + g.p1, o2 = (size_t)g.p2 * g.s2 + g.p2, ol = (size_t)g.lp * g.ls + g.lp, oc = (size_t)g.cp * g.cs + g.cp;
@@ -333,7 +333,8 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         d.side = s->side; d.bins = s->bins; d.slice_nbins = s->slice_nbins;
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
-        d.qp = qp; d.is_idr = idr; d.frame_num = s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format; d.scene_change = s->cfg.scene_change && !idr;
+        d.qp = qps[i]; d.is_idr = idr; d.frame_num = idr ? 0 : s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
+        d.scene_change = s->cfg.scene_change && !idr && s->frames_since_idr >= SC_MIN_DISTANCE;
         d.t8x8 = s->cfg.profile == 2;
         d.rbsp_words_per_slice = s->rbsp_words_per_slice; d.out_cap = s->out_cap;
     }
@@ -422,35 +423,102 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     CU_TRY(cudaMemcpyAsync(&ctl, b->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, st), return B200ENC_ECUDA);
     CU_TRY(cudaStreamSynchronize(st), return B200ENC_ECUDA);
     CU_TRY(cudaGetLastError(), return B200ENC_ECUDA);
-    cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1);
-    b->last_launches = launches;
-    if (ctl.error) return B200ENC_EWAVE;
-    int rc = B200ENC_OK;
+    float ms = 0; cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+    b->last_ms += ms; b->last_launches += launches;
+    return ctl.error ? B200ENC_EWAVE : B200ENC_OK;
+}
+
+bool rc_retry_enabled()
+{
+    static const bool on = [] { const char *e = getenv("B200ENC_RC_RETRY"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
+
+// Advance n sessions of one GPU by one picture. Returns a whole-step failure (bad arguments, CUDA error, device watchdog) or B200ENC_OK /
+// B200ENC_EOVERFLOW when only individual sessions failed; rcs[i] (optional) is the outcome of session i. A session whose picture was not
+// delivered keeps its stream state and starts over with an IDR, so its decoder never predicts from a picture it did not get.
+int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8_t *const *frames, int mode,
+                const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *infos, int *rcs)
+{
+    if (!b || !ss || n <= 0 || n > b->cap || !frames) return B200ENC_EINVAL;
+    for (int i = 0; i < n; i++) {
+        if (!ss[i] || (!frames[i] && mode != IN_UPLOADED) || ss[i]->device != b->device || !same_shape(ss[0], ss[i])) return B200ENC_EINVAL;
+        for (int j = 0; j < i; j++) if (ss[j] == ss[i]) return B200ENC_EINVAL;
+    }
+    CU_TRY(cudaSetDevice(b->device), return B200ENC_ECUDA);
+    std::vector<int> kinds(n), qps(n);
     for (int i = 0; i < n; i++) {
         b200enc_session *s = ss[i];
-        const uint32_t size = *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap);
-        if (s->last_type == 0 && *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap + 4)) {
-            // scene change: the device coded this P picture as an IDR (k_scene_change); follow it on the host side
-            s->last_type = 1; s->frame_num = 0; s->frames_since_idr = 0;
+        kinds[i] = next_is_idr(s) ? 1 : 0;
+        if (s->cfg.const_qp >= 0) qps[i] = s->cfg.const_qp;
+        else { s->rc_dec = s->rc.pick(kinds[i]); qps[i] = s->rc_dec.qp; }
+    }
+    b->last_ms = 0; b->last_launches = 0;
+    int rc = launch_step(b, ss, n, frames, mode, kinds.data(), qps.data());
+    auto out_size = [](const b200enc_session *s) { return *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap); };
+    auto promoted = [](const b200enc_session *s) { return *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap + 4) != 0; };
+    if (rc == B200ENC_OK && rc_retry_enabled()) {
+        // rate control, second attempt: pictures that came out above their hard cap (an IDR many times the budget; a P picture after a cut)
+        // are coded once more with a coarser QP before anything is delivered or committed. The frames are still in the input buffers.
+        std::vector<b200enc_session *> again; std::vector<int> ak, aq, at; std::vector<const uint8_t *> af;
+        for (int i = 0; i < n; i++) {
+            b200enc_session *s = ss[i];
+            if (s->cfg.const_qp >= 0 || out_size(s) >= s->out_cap) continue;
+            const int coded = kinds[i] || (promoted(s) ? 1 : 0);
+            const int q2 = s->rc.second_attempt_qp(kinds[i], coded, s->rc_dec, 8.0 * out_size(s));
+            if (q2 < 0) continue;
+            again.push_back(s); ak.push_back(coded); aq.push_back(q2); at.push_back(i); af.push_back(frames[i]);
         }
-        if (size >= s->out_cap) rc = B200ENC_EOVERFLOW;
+        if (!again.empty()) {
+            rc = launch_step(b, again.data(), (int)again.size(), af.data(), mode == IN_DEVICE ? IN_DEVICE : IN_RESIDENT, ak.data(), aq.data());
+            for (size_t k = 0; k < again.size(); k++) { kinds[at[k]] = ak[k]; qps[at[k]] = aq[k]; again[k]->retries++; }
+        }
+    }
+    if (rc != B200ENC_OK) {
+        for (int i = 0; i < n; i++) { ss[i]->force_idr = true; if (rcs) rcs[i] = rc; }
+        return rc;
+    }
+    int worst = B200ENC_OK;
+    for (int i = 0; i < n; i++) {
+        b200enc_session *s = ss[i];
+        const uint32_t size = out_size(s);
+        const bool idr = kinds[i] || promoted(s);      // scene change: the device coded this P picture as an IDR (k_scene_change)
+        if (infos) { infos[i].frame_type = idr ? 1 : 0; infos[i].qp = qps[i]; infos[i].size_bytes = size; infos[i].frame_index = s->frame_index; }
+        if (size >= s->out_cap) {
+            // k_nal_pack clamped the access unit: nothing is delivered, the stream state stays where it was, the next picture is an IDR
+            s->force_idr = true; worst = B200ENC_EOVERFLOW;
+            if (rcs) rcs[i] = B200ENC_EOVERFLOW;
+            if (bs) bs[i] = nullptr;
+            if (bs_size) bs_size[i] = 0;
+            continue;
+        }
+        if (rcs) rcs[i] = B200ENC_OK;
+        s->last_qp = qps[i]; s->last_type = idr ? 1 : 0;
         if (s->cfg.const_qp < 0) s->rc.update(s->last_type, s->last_qp, 8.0 * size);
         if (bs) bs[i] = s->h_out;
         if (bs_size) bs_size[i] = size;
-        if (infos) { infos[i].frame_type = s->last_type; infos[i].qp = s->last_qp; infos[i].size_bytes = size; infos[i].frame_index = s->frame_index; }
-        if (s->last_type == 1) s->idr_pic_id = (s->idr_pic_id + 1) & 1;
+        if (idr) { s->frame_num = 0; s->frames_since_idr = 0; s->idr_pic_id = (s->idr_pic_id + 1) & 1; }
         s->frame_num = (s->frame_num + 1) & 255; s->frames_since_idr++; s->frame_index++;
         s->force_idr = false; s->have_ref = true; s->cur_is_A = !s->cur_is_A;
     }
-    return rc;
+    return worst;
 }
 
+
+// b200enc_encode's upload: runs on the CALLER's thread, so N sessions copy (and stage pageable frames) in parallel
+int session_upload(b200enc_session *s, const uint8_t *frame)
+{
+    CU_TRY(cudaSetDevice(s->device), return B200ENC_ECUDA);
+    const int rc = upload_frame(s, frame, s->up_stream);
+    if (rc != B200ENC_OK) return rc;
+    CU_TRY(cudaEventRecord(s->ev_up, s->up_stream), return B200ENC_ECUDA);
+    return B200ENC_OK;
+}
 
 // ---- per-GPU session scheduler (auto_batch): the reference runs one caller thread per session, each blocked in its own
 // EncodeOneFrame (video_codec/VideoEncoderOpenH264.cpp:304-352, iMultipleThreadIdc = 1 at :294). Here those concurrent calls
 // rendezvous in a per-GPU worker that advances all waiting sessions with ONE batch step; while a step runs, the next
 // callers queue up, so batches form by themselves under load and a lone caller only pays the short window. ----
-bool next_is_idr(const b200enc_session *s) { return s->force_idr || !s->have_ref || s->frames_since_idr >= s->cfg.gop; }
 struct SchedRequest {
     b200enc_session *s; const uint8_t *frame; const uint8_t *bs = nullptr; uint32_t size = 0; b200enc_frame_info info{};
     int rc = B200ENC_OK; bool done = false;
@@ -487,13 +555,18 @@ struct DeviceScheduler {
             const int n = (int)take.size();
             inflight += n;
             lk.unlock();
-            std::vector<b200enc_session *> ss(n); std::vector<const uint8_t *> fr(n), bs(n); std::vector<uint32_t> sz(n); std::vector<b200enc_frame_info> inf(n);
+            std::vector<b200enc_session *> ss(n); std::vector<const uint8_t *> fr(n), bs(n, nullptr); std::vector<uint32_t> sz(n, 0); std::vector<b200enc_frame_info> inf(n);
+            std::vector<int> rcs(n, B200ENC_OK);
             for (int i = 0; i < n; i++) { ss[i] = take[i]->s; fr[i] = take[i]->frame; }
-            const int rc = encode_impl(ctx[w], ss.data(), n, fr.data(), 0, bs.data(), sz.data(), inf.data());
+            // the callers' threads have already queued their uploads (scheduler_encode); every request gets its own outcome
+            const int rc = encode_impl(ctx[w], ss.data(), n, fr.data(), IN_UPLOADED, bs.data(), sz.data(), inf.data(), rcs.data());
             batches++; frames += n;
             lk.lock();
             inflight -= n;
-            for (int i = 0; i < n; i++) { take[i]->bs = bs[i]; take[i]->size = sz[i]; take[i]->info = inf[i]; take[i]->rc = rc; take[i]->done = true; }
+            for (int i = 0; i < n; i++) {
+                take[i]->bs = bs[i]; take[i]->size = sz[i]; take[i]->info = inf[i]; take[i]->done = true;
+                take[i]->rc = rc != B200ENC_OK && rc != B200ENC_EOVERFLOW ? rc : rcs[i];
+            }
             cv_done.notify_all();
         }
     }
@@ -533,6 +606,10 @@ int scheduler_encode(b200enc_session *s, const uint8_t *frame, const uint8_t **b
     DeviceScheduler *d = scheduler_for(s->device);
     if (!d) return B200ENC_ENODEV;
     SchedRequest req; req.s = s; req.frame = frame;
+    {   // this caller's H2D copy starts now, on the session's own stream, while the scheduler is still collecting the batch
+        const int rc = session_upload(s, frame);
+        if (rc != B200ENC_OK) return rc;
+    }
     std::unique_lock<std::mutex> lk(d->mu);
     d->pending.push_back(&req);
     d->cv_submit.notify_all();
@@ -564,10 +641,12 @@ void b200enc_default_config(b200enc_config *c)
     // defaults of the reference wrapper: 720x1280, 30 fps, 5 Mbps, gop 30 (video_codec/VideoEncoderOpenH264.h:13-24)
     c->width = 720; c->height = 1280; c->fps = 30; c->bitrate = 5000000; c->gop = 30; c->const_qp = -1;
     c->num_slices = 0; c->search_range = 16; c->input_format = B200ENC_FMT_I420; c->device = -1; c->scene_change = 1;
+    // rate-control bounds of openh264's GetDefaultParams (what the wrapper keeps, :230), max bitrate = target (:239-240), HIGH_COMPLEXITY (:289)
+    c->max_bitrate = 0; c->min_qp = 0; c->max_qp = 51; c->background_detection = 0; c->complexity = 2;
 }
 
 int b200enc_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
-int b200enc_last_cuda_error(void) { return g_last_cuda_error; }
+int b200enc_last_cuda_error(void) { return g_last_cuda_error.load(); }
 int b200enc_scheduler_stats(int device, uint64_t *batches, uint64_t *frames)
 {
     std::lock_guard<std::mutex> lk(g_scheds_mu);
@@ -604,6 +683,8 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
     if (c.input_format < 0 || c.input_format > 2) return B200ENC_EINVAL;
     if (c.const_qp < 0 && c.bitrate <= 0) return B200ENC_EINVAL;
     if (c.profile < 0 || c.profile > 2) return B200ENC_EINVAL;
+    if (c.min_qp < 0 || c.min_qp > 51 || c.max_qp < 0 || c.max_qp > 51 || (c.max_qp && c.max_qp < c.min_qp) || c.max_bitrate < 0) return B200ENC_EINVAL;
+    if (c.complexity < 0 || c.complexity > 2) return B200ENC_EINVAL;
     // num_slices <= 0 = automatic: one slice with CAVLC (the wrapper's SM_SINGLE_SLICE, VideoEncoderOpenH264.cpp:247); with CABAC one slice per
     // ~17 MB rows (1080p: 4, 720p: 2, 2160p: 7), because the arithmetic coder is a serial chain per slice and a frame's latency is its longest slice
     // (+0.6..0.9 % bits on P pictures at 1080p, measured with the oracle)
@@ -679,7 +760,14 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         s->own = new (std::nothrow) b200enc_batch();
         if (!s->own) { rc = B200ENC_ENOMEM; break; }
         rc = batch_init(s->own, s->device, 1);
-        s->rc.target = (double)c.bitrate / c.fps; s->rc.fps = c.fps;
+        if (rc != B200ENC_OK) break;
+        CU_TRY(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking), rc = B200ENC_ENODEV; break);
+        CU_TRY(cudaEventCreateWithFlags(&s->ev_up, cudaEventDisableTiming), rc = B200ENC_ENODEV; break);
+        {   // the wrapper's rate-control settings: RC_BITRATE_MODE, iMaxBitrate = iTargetBitrate, iMinQp / iMaxQp (VideoEncoderOpenH264.cpp:230,239-240,274)
+            b200rc::Config rcc; rcc.bitrate = c.bitrate; rcc.max_bitrate = c.max_bitrate; rcc.fps = c.fps; rcc.width = c.width; rcc.height = c.height;
+            rcc.min_qp = c.min_qp; rcc.max_qp = c.max_qp > 0 ? c.max_qp : 51;
+            s->rc.init(rcc);
+        }
         if (rc == B200ENC_OK && c.auto_batch) scheduler_register(s, +1);
     } while (0);
     if (rc != B200ENC_OK) { b200enc_destroy(s); return rc; }
@@ -693,6 +781,9 @@ void b200enc_destroy(b200enc_session *s)
     if (s->device >= 0) {
         if (s->in_scheduler) scheduler_register(s, -1);
         cudaSetDevice(s->device);
+        if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
+        if (s->ev_up) cudaEventDestroy(s->ev_up);
+        if (s->h_stage) cudaFreeHost(s->h_stage);
         if (s->own) batch_free(s->own);
         if (s->h_out) cudaFreeHost(s->h_out);
         if (s->d_pool) cudaFree(s->d_pool);
@@ -722,7 +813,9 @@ int b200enc_encode(b200enc_session *s, const uint8_t *frame, uint32_t size, cons
     if (!s || !frame) return B200ENC_EINVAL;
     if (size < b200enc_frame_bytes(s)) return B200ENC_ESIZE;
     if (s->in_scheduler) return scheduler_encode(s, frame, bs, bs_size, info);
-    return encode_impl(s->own, &s, 1, &frame, 0, bs, bs_size, info);
+    const int rc = session_upload(s, frame);
+    if (rc != B200ENC_OK) return rc;
+    return encode_impl(s->own, &s, 1, &frame, IN_UPLOADED, bs, bs_size, info, nullptr);
 }
 float b200enc_last_kernel_ms(const b200enc_session *s) { return s && s->own ? s->own->last_ms : 0.f; }
 
@@ -740,8 +833,18 @@ void b200enc_batch_destroy(b200enc_batch *b) { batch_free(b); }
 int b200enc_batch_encode(b200enc_batch *b, b200enc_session *const *sessions, int n, const uint8_t *const *frames, int device_input,
                          const uint8_t **bs, uint32_t *bs_size, b200enc_frame_info *infos)
 {
-    return encode_impl(b, sessions, n, frames, device_input, bs, bs_size, infos);
+    if (!b) return B200ENC_EINVAL;
+    b->last_rcs.assign(n > 0 ? n : 0, B200ENC_EINVAL);
+    return encode_impl(b, sessions, n, frames, device_input ? IN_DEVICE : IN_HOST, bs, bs_size, infos, b->last_rcs.data());
 }
+int b200enc_batch_last_status(const b200enc_batch *b, int *rcs, int cap)
+{
+    if (!b || !rcs) return 0;
+    int n = 0;
+    for (; n < (int)b->last_rcs.size() && n < cap; n++) rcs[n] = b->last_rcs[n];
+    return n;
+}
+uint32_t b200enc_rc_retries(const b200enc_session *s) { return s ? s->retries : 0; }
 float b200enc_batch_last_kernel_ms(const b200enc_batch *b) { return b ? b->last_ms : 0.f; }
 int b200enc_batch_last_launches(const b200enc_batch *b) { return b ? b->last_launches : 0; }
 int b200enc_batch_set_profiling(b200enc_batch *b, int on) { if (!b) return B200ENC_EINVAL; b->profiling = on != 0; return B200ENC_OK; }
@@ -817,3 +920,4 @@ int b200enc_get_recon(b200enc_session *s, uint8_t *i420, size_t cap)
 } // extern "C"
 
 #include "k_test_abi.inl"
+#include "rc_capi.inl"

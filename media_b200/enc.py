@@ -24,7 +24,8 @@ MBSIDE_DTYPE = np.dtype([("mvd", "<i2", (4, 2)), ("dc_cbf", "u1"), ("pad", "u1",
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "height", "fps", "bitrate", "gop", "const_qp", "num_slices",
-                                       "search_range", "input_format", "device", "level_idc", "debug", "scene_change", "auto_batch", "profile")]
+                                       "search_range", "input_format", "device", "level_idc", "debug", "scene_change", "auto_batch", "profile",
+                                       "max_bitrate", "min_qp", "max_qp", "background_detection", "complexity")]
 
 
 class FrameInfo(C.Structure):
@@ -64,6 +65,8 @@ def lib():
         L.b200enc_batch_destroy.argtypes = [vp]
         L.b200enc_batch_encode.restype = C.c_int
         L.b200enc_batch_encode.argtypes = [vp, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(FrameInfo)]
+        L.b200enc_batch_last_status.restype = C.c_int; L.b200enc_batch_last_status.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
+        L.b200enc_rc_retries.restype = C.c_uint32; L.b200enc_rc_retries.argtypes = [vp]
         L.b200enc_batch_last_kernel_ms.restype = C.c_float; L.b200enc_batch_last_kernel_ms.argtypes = [vp]
         L.b200enc_last_kernel_ms.restype = C.c_float; L.b200enc_last_kernel_ms.argtypes = [vp]
         L.b200enc_batch_last_launches.restype = C.c_int; L.b200enc_batch_last_launches.argtypes = [vp]
@@ -103,9 +106,11 @@ def _p(a):
 
 class Session:
     def __init__(self, width, height, fps=30, bitrate=4_000_000, gop=30, const_qp=-1, num_slices=1, search_range=16,
-                 input_format=FMT_I420, device=-1, level_idc=0, debug=0, auto_batch=0, scene_change=1, profile=PROFILE_BASELINE):
+                 input_format=FMT_I420, device=-1, level_idc=0, debug=0, auto_batch=0, scene_change=1, profile=PROFILE_BASELINE,
+                 max_bitrate=0, min_qp=0, max_qp=51, background_detection=0, complexity=2):
         L = lib()
-        self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug, scene_change, auto_batch, profile)
+        self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug, scene_change, auto_batch, profile,
+                          max_bitrate, min_qp, max_qp, background_detection, complexity)
         self.h = C.c_void_p()
         check(L.b200enc_create(C.byref(self.cfg), C.byref(self.h)), "b200enc_create")
         self.width, self.height = width, height

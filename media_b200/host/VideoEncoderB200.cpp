@@ -104,6 +104,9 @@ EncoderRetCode VideoEncoderB200::InitEncoder()
     b200enc_default_config(&cfg);
     cfg.width = (int)m_encParams.width; cfg.height = (int)m_encParams.height; cfg.fps = (int)m_encParams.framerate;
     cfg.bitrate = (int)m_encParams.bitrate; cfg.gop = (int)m_encParams.gopsize;
+    // the policy the reference wrapper fixes in InitParams (VideoEncoderOpenH264.cpp:239-240,282-283,289): max bitrate = target bitrate,
+    // background detection and scene-change detection on, HIGH_COMPLEXITY; QP bounds stay at the encoder's defaults (:230)
+    cfg.max_bitrate = cfg.bitrate; cfg.background_detection = 1; cfg.scene_change = 1; cfg.complexity = 2;
     // profile property -> uiProfileIdc as in the reference (VideoEncoderOpenH264.cpp:248-253); the wrapper asks for CABAC (:291), which the
     // Baseline profile does not have, so baseline stays CAVLC and main / high are coded with CABAC
     cfg.profile = m_encParams.profile == "high" ? 2 : m_encParams.profile == "main" ? 1 : 0;

@@ -50,6 +50,12 @@ public:
         if (cfg_.const_qp < 0 && cfg_.bitrate <= 0) cfg_.bitrate = 1000000;
         cfg_.num_slices = l.slice.mode == kSliceFixedNum && l.slice.num > 0 ? (int)l.slice.num : 1;       // SM_SINGLE_SLICE (the wrapper, :247)
         cfg_.scene_change = p->scene_change_detect ? 1 : 0;                       // bEnableSceneChangeDetect (the wrapper sets it, :283)
+        cfg_.background_detection = p->background_detection ? 1 : 0;              // bEnableBackgroundDetection (:282)
+        cfg_.complexity = p->complexity >= 0 && p->complexity <= 2 ? p->complexity : 2;       // iComplexityMode (:289)
+        // rate-control bounds: iMaxBitrate (the wrapper: = target, :239-240; 0 = UNSPECIFIED_BIT_RATE = no tighter than the target), iMinQp / iMaxQp (:230)
+        cfg_.max_bitrate = l.max_bitrate > 0 ? l.max_bitrate : p->max_bitrate > 0 ? p->max_bitrate : 0;
+        cfg_.min_qp = p->min_qp >= 0 && p->min_qp <= 51 ? p->min_qp : 0;
+        cfg_.max_qp = p->max_qp > 0 && p->max_qp <= 51 && p->max_qp >= cfg_.min_qp ? p->max_qp : 51;
         cfg_.auto_batch = 1;
         // entropy_mode = 1 (CABAC, requested by the wrapper at :291) takes effect for profile main (77) / high (100); Baseline has no CABAC
         cfg_.profile = !p->entropy_mode ? 0 : l.profile_idc == 100 ? 2 : l.profile_idc == 77 ? 1 : 0;
@@ -99,7 +105,7 @@ public:
         case kOptDataFormat: return *static_cast<int *>(v) == kVideoFormatI420 ? 0 : 1;
         case kOptIdrInterval: { int g = *static_cast<int *>(v); cfg_.gop = g > 0 ? g : 1 << 30; dirty_ = true; return 0; }
         case kOptFrameRate: { float f = *static_cast<float *>(v); if (f < 1.f) return 1; cfg_.fps = (int)(f + 0.5f); dirty_ = true; return 0; }
-        case kOptBitrate: case kOptMaxBitrate: { int b = static_cast<BitrateInfo *>(v)->bitrate; if (b <= 0) return 1; if (opt == kOptBitrate) { cfg_.bitrate = b; dirty_ = true; } return 0; }
+        case kOptBitrate: case kOptMaxBitrate: { int b = static_cast<BitrateInfo *>(v)->bitrate; if (b <= 0) return 1; (opt == kOptBitrate ? cfg_.bitrate : cfg_.max_bitrate) = b; dirty_ = true; return 0; }
         case kOptRcMode: { int m = *static_cast<int *>(v); if (m == kRcOff && cfg_.const_qp < 0) cfg_.const_qp = 26; if (m != kRcOff) cfg_.const_qp = -1; dirty_ = true; return 0; }
         case kOptParamExt: return InitializeExt(static_cast<EncParamExt *>(v));
         case kOptParamBase: return Initialize(static_cast<EncParamBase *>(v));
@@ -113,7 +119,8 @@ public:
         case kOptDataFormat: *static_cast<int *>(v) = kVideoFormatI420; return 0;
         case kOptIdrInterval: *static_cast<int *>(v) = cfg_.gop; return 0;
         case kOptFrameRate: *static_cast<float *>(v) = (float)cfg_.fps; return 0;
-        case kOptBitrate: case kOptMaxBitrate: static_cast<BitrateInfo *>(v)->bitrate = cfg_.bitrate; return 0;
+        case kOptBitrate: static_cast<BitrateInfo *>(v)->bitrate = cfg_.bitrate; return 0;
+        case kOptMaxBitrate: static_cast<BitrateInfo *>(v)->bitrate = cfg_.max_bitrate > 0 ? cfg_.max_bitrate : cfg_.bitrate; return 0;
         case kOptRcMode: *static_cast<int *>(v) = cfg_.const_qp >= 0 ? kRcOff : kRcBitrate; return 0;
         default: return 1;
         }

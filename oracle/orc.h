@@ -89,12 +89,15 @@ typedef struct {
     int intra8x8;            /* 1: High profile intra MBs may also take Intra_8x8 (8.3.2). GROUNDWORK for the next round: pinned by the decoder
                                 round trip on the CPU, not yet built in CUDA, so the product and every parity test run with 0 */
 } OrcConfig;
+#define ORC_SC_MIN_DISTANCE 10   /* scene-change promotion needs this many pictures since the last IDR (the IDR counts as the first) */
 #define ORC_MB_T8(m) (((m)->i16_mode >> 2) & 1)
 
 OrcEncoder *orc_create(const OrcConfig *cfg);
 void orc_destroy(OrcEncoder *e);
 /* Encode one frame. frame_type: 1 = IDR (SPS+PPS prepended), 0 = P. Returns bytes written or <0. */
 int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap);
+/* The same without advancing the stream state (reference picture, frame_num, idr_pic_id): a picture the rate control codes again. */
+int orc_encode_trial(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap);
 /* 1 when the last frame was coded as an IDR (requested, first frame, or scene change), else 0 */
 int orc_last_frame_was_idr(const OrcEncoder *e);
 /* Reconstruction of the last encoded frame (after deblocking), cropped to width x height I420. */

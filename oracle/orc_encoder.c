@@ -36,6 +36,7 @@ struct OrcEncoder {
     uint8_t *pred_y, *pred_c;        /* per-MB inter prediction: 256 luma, 2*64 chroma */
     int *slice_row0;                 /* num_slices+1 entries */
     int frame_num, idr_pic_id, have_ref, last_idr;
+    int since_idr;                   /* pictures since (and including) the last IDR */
     uint8_t *rbsp; int rbsp_cap;
     OrcMbSide *side;                 /* CABAC side records */
     uint16_t *bins; int bins_cap;    /* CABAC bin lists of the last frame, slice after slice */
@@ -1065,9 +1066,10 @@ int orc_cabac_code_bins(const uint16_t *bins, int n, int slice_qp, int is_p, uin
     return b.overflow ? -1 : b.pos;
 }
 
-int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap)
+static int encode_frame(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap, int commit)
 {
     int is_idr = frame_type == 1 || !e->have_ref, n = e->mbw * e->mbh, lambda = LAMBDA_TAB[qp];
+    const int frame_num_in = e->frame_num;
     load_source(e, i420);
     if (is_idr) { e->frame_num = 0; }
     if (!is_idr) {
@@ -1086,10 +1088,11 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
                 if (ie + lambda * ORC_INTRA_BIAS_BITS < e->inter_cost[mb]) { memset(&e->mbi[mb], 0, sizeof(OrcMbInfo)); e->mbi[mb].mb_type = ORC_MB_I16x16; }
             }
         /* Scene change (the wrapper enables openh264's detector, VideoEncoderOpenH264.cpp:283): when at least 2/5 of the MBs came out
-         * intra from the motion search, the picture is coded as an IDR instead */
+         * intra from the motion search, the picture is coded as an IDR instead -- but not within ORC_SC_MIN_DISTANCE pictures of the last
+         * IDR: noise or sustained violent motion must not turn every picture into a key frame */
         int n_intra = 0;
         for (int i = 0; i < n; i++) n_intra += e->mbi[i].mb_type == ORC_MB_I16x16;
-        if (!e->cfg.no_scene_change && 5 * n_intra >= 2 * n) {
+        if (!e->cfg.no_scene_change && e->since_idr >= ORC_SC_MIN_DISTANCE && 5 * n_intra >= 2 * n) {
             is_idr = 1; e->frame_num = 0;
             memset(e->mbi, 0, (size_t)n * sizeof(OrcMbInfo));
             for (int i = 0; i < n; i++) e->mbi[i].mb_type = ORC_MB_I16x16;
@@ -1161,9 +1164,15 @@ int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8
         out[o] = 0; out[o + 1] = 0; out[o + 2] = 0; out[o + 3] = 1; out[o + 4] = is_idr ? 0x65 : 0x61;
         o += 5 + orc_escape_rbsp(e->rbsp, b.pos, out + o + 5);
     }
+    e->last_idr = is_idr;
+    if (!commit) { e->frame_num = frame_num_in; return o; }      /* a trial leaves the stream state (reference, frame_num, idr_pic_id) untouched */
     /* the deblocked picture becomes the reference of the next frame */
     for (int c = 0; c < 3; c++) memcpy(e->ref[c], e->dbk[c], (size_t)(c ? e->wc / 2 * e->hc / 2 : e->wc * e->hc));
-    e->have_ref = 1; e->frame_num = (e->frame_num + 1) & 255; e->last_idr = is_idr;
+    e->have_ref = 1; e->frame_num = (e->frame_num + 1) & 255;
+    e->since_idr = is_idr ? 1 : e->since_idr + 1;
     if (is_idr) e->idr_pic_id = (e->idr_pic_id + 1) & 1;
     return o;
 }
+int orc_encode(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap) { return encode_frame(e, i420, frame_type, qp, out, out_cap, 1); }
+/* the same picture coded without advancing the stream: what a rate-control retry at another QP discards (tools/rc_sim.py) */
+int orc_encode_trial(OrcEncoder *e, const uint8_t *i420, int frame_type, int qp, uint8_t *out, int out_cap) { return encode_frame(e, i420, frame_type, qp, out, out_cap, 0); }

@@ -43,6 +43,7 @@ def lib():
         L.orc_create.restype = vp; L.orc_create.argtypes = [C.POINTER(OrcConfig)]
         L.orc_destroy.argtypes = [vp]
         L.orc_encode.restype = C.c_int; L.orc_encode.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_encode_trial.restype = C.c_int; L.orc_encode_trial.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int]
         L.orc_get_recon.argtypes = [vp, vp]
         L.orc_last_frame_was_idr.restype = C.c_int; L.orc_last_frame_was_idr.argtypes = [vp]
         L.orc_mb_info.restype = vp; L.orc_mb_info.argtypes = [vp]
@@ -98,10 +99,11 @@ class Encoder:
     def __del__(self):
         self.close()
 
-    def encode(self, i420, idr, qp):
+    def encode(self, i420, idr, qp, trial=False):
+        """trial=True codes the picture without advancing the stream state (a rate-control attempt that is thrown away)"""
         i420 = np.ascontiguousarray(i420, np.uint8).ravel()
         assert i420.size >= self.width * self.height * 3 // 2
-        n = self.L.orc_encode(self.h, _p(i420), 1 if idr else 0, int(qp), _p(self._out), self._out.size)
+        n = (self.L.orc_encode_trial if trial else self.L.orc_encode)(self.h, _p(i420), 1 if idr else 0, int(qp), _p(self._out), self._out.size)
         if n < 0:
             raise RuntimeError("orc_encode failed")
         return self._out[:n].tobytes()
