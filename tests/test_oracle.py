@@ -444,16 +444,17 @@ def test_downstream_consumer_finds_the_parameter_sets(orc):
 @needs_decoder
 def test_scene_change_turns_a_p_frame_into_an_idr(orc):
     """a cut to unrelated content makes >= 2/5 of the macroblocks intra after the motion search: the picture is coded as an IDR
-    (SPS + PPS in front, frame_num restarts) and the stream stays decodable; with the detector off it remains a P picture"""
+    (SPS + PPS in front, frame_num restarts) and the stream stays decodable; with the detector off it remains a P picture, and so does a
+    cut within ORC_SC_MIN_DISTANCE = 10 pictures of the last IDR"""
     w, h = 256, 160
     a, b = Content("A", w, h, seed=1), Content("A", w, h, seed=99)
     for detect in (1, 0):
         e = orc.Encoder(w, h, scene_change=detect)
-        frames = [a.frame(0), a.frame(1), b.frame(2), b.frame(3)]
+        frames = [a.frame(t) for t in range(3)] + [b.frame(t) for t in range(3, 11)] + [a.frame(11), a.frame(12)]      # cuts at 3 and 11
         aus, recs, kinds = [], [], []
         for t, f in enumerate(frames):
             aus.append(e.encode(f, t == 0, 28)); recs.append(e.recon()); kinds.append(e.last_was_idr())
-        assert kinds == ([True, False, True, False] if detect else [True, False, False, False])
-        assert (aus[2][4] == 0x67) == bool(detect)
+        assert kinds == [True] + [False] * 10 + [bool(detect), False]
+        assert (aus[11][4] == 0x67) == bool(detect) and aus[3][4] == 0x61
         dec = avdec.decode_stream(aus)
-        assert len(dec) == 4 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+        assert len(dec) == 13 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
