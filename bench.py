@@ -3,11 +3,16 @@
 
 Workload (config.workload): S concurrent 1920x1080 sessions per GPU, Baseline IPPP, CBR 4 Mbps at 30 fps each
 (BASELINE.json configs[1] scaled to the session count the metric's "real-time sessions" figure needs). A step is
-one frame for every session of the GPU: S frames. `value` = frames/s with the input frames resident in HBM;
-`e2e` = the same through the C ABI with HOST (pinned) input frames and host-visible bitstreams.
-`--impl reference` times the CPU restatement of the path (oracle/, one single-threaded encoder per host core, as
-the reference configures openh264 at video_codec/VideoEncoderOpenH264.cpp:294); libopenh264 itself is not in the
-image, so its `kind` is "port".
+one frame for every session of the GPU: S frames. `value` = frames/s with the input frames resident in HBM (batch API, CUDA-event and host timing around a device synchronize).
+`e2e` = the same metric through the REFERENCE-FACING boundary: tools/libe2e_plugin.so dlopens media_b200/host/libVideoCodec.so and
+drives CreateVideoEncoder -> InitEncoder -> EncodeOneFrame with one C++ caller thread per session and frames in plain malloc
+(pageable) memory (video_codec/VideoCodecApi.h:57-58,80-96; the reference's threading model, VideoEncoderOpenH264.cpp:294);
+`realtime` = the same sessions paced at 30 fps through that boundary (late frames, latency percentiles).
+`roofline` = algorithmic integer operations of the dominant kernel over its live CUDA-event time against the measured
+issue peaks of those instructions (b200k_int_peaks, SM clock measured inside the microbenchmark).
+`--impl reference` first looks for the real libopenh264.so (LD_LIBRARY_PATH, baseline/_ref/) to run the unmodified
+VideoEncoderOpenH264 through it; it is absent from this image, so the arm that runs is the CPU restatement of the path (oracle/,
+one single-threaded encoder per host core, as the reference configures openh264 at VideoEncoderOpenH264.cpp:294), kind "port".
 """
 import argparse
 import json
@@ -121,9 +126,11 @@ def run_b200(args):
     rank, local_rank, world = dist_env()
     use_dist = world > 1
     if use_dist:
+        # the path has no data-path collective (sessions are sharded): the process group only carries the barrier and the
+        # max-over-ranks of the timings, so it is gloo on CPU tensors -- no NCCL communicator is ever created
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo")
     dev = local_rank if use_dist else 0
     try:        # keep this rank's caller threads and its pinned frame pool on the NUMA node of its GPU (8 ranks share a two-socket host)
         import pynvml
@@ -143,13 +150,6 @@ def run_b200(args):
         assert p, "device allocation failed"
         enc.check(L.b200enc_dev_upload(dev, p, f.ctypes.data, fb))
         dpool.append(p)
-    hpool = []
-    for f in pool:
-        p = L.b200enc_host_alloc(fb)
-        assert p, "pinned allocation failed"
-        C.memmove(p, f.ctypes.data, fb)
-        hpool.append(p)
-
     G = max(1, min(args.groups, S))          # independent batches (own stream each) driven by G host threads
     group_sizes = [S // G + (1 if i < S % G else 0) for i in range(G)]
 
@@ -166,12 +166,16 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    trace_qps = []          # QP of session 0 for every frame it encoded (IDR first): drives the CPU arm with the same quantisers
+
     def run_group(grp, ptr_pool, device_input, first, count, acc):
         ss, batch, ids = grp
         dev_ms = launches = out_bytes = 0
         for k in range(first, first + count):
             sizes = batch.encode_ptrs([ptr_pool[pool_index(k, i)] for i in ids], device_input)
             dev_ms += batch.kernel_ms(); launches += batch.launches(); out_bytes += sum(sizes[j] for j in range(len(ids)))
+            if ids[0] == 0:
+                trace_qps.append(batch._infos[0].qp)
         acc.append((dev_ms, launches, out_bytes))
 
     def run_all(groups, ptr_pool, device_input, first, count):
@@ -194,7 +198,7 @@ def run_b200(args):
         barrier()
         el = time.perf_counter() - t0
         if use_dist:
-            t = torch.tensor([el, dev_ms], device="cuda", dtype=torch.float64)
+            t = torch.tensor([el, dev_ms], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el, dev_ms = t[0].item(), t[1].item()
         return el, dev_ms, launches, out_bytes
@@ -206,47 +210,60 @@ def run_b200(args):
     el, dev_ms, launches, out_bytes = timed(groups, dpool, 1, args.steps, args.warmup)
     clocks = sampler.summary()
     value = world * S * args.steps / el
-    # end to end: host pinned frames in, host-visible bitstreams out
-    el_e, dev_ms_e, _, out_bytes_e = timed(groups, hpool, 0, args.steps, 1, step0=args.warmup + args.steps)
-    e2e = world * S * args.steps / el_e
-    # the reference's threading model: one caller thread per session, each blocked in b200enc_encode (what EncodeOneFrame
-    # does); the per-GPU auto_batch scheduler coalesces them. Python threads add overhead, so this is a lower bound.
-    thr = None
-    if args.threads_e2e:
-        for x in sess:
-            x.close()
-        sess = [new_session(enc, dev, auto_batch=1) for _ in range(S)]
-        b0, f0, b1, f1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
-        nst = max(4, args.steps)
-
-        def caller(i, first, count):
-            bs, n = C.c_void_p(), C.c_uint32()
-            for k in range(first, first + count):
-                L.b200enc_encode(sess[i].h, hpool[pool_index(k, i)], fb, C.byref(bs), C.byref(n), None)
-
-        def run_callers(first, count):
-            ths = [threading.Thread(target=caller, args=(i, first, count)) for i in range(S)]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
-        run_callers(0, 3)
-        barrier()
-        L.b200enc_scheduler_stats(dev, C.byref(b0), C.byref(f0))
-        t0 = time.perf_counter(); run_callers(3, nst); barrier(); el_t = time.perf_counter() - t0
-        L.b200enc_scheduler_stats(dev, C.byref(b1), C.byref(f1))
-        if use_dist:
-            tt = torch.tensor([el_t], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); el_t = tt[0].item()
-        thr = {"value": round(world * S * nst / el_t, 2), "unit": "frames/s", "caller_threads": S,
-               "avg_batch": round((f1.value - f0.value) / max(1, b1.value - b0.value), 1),
-               "note": "one Python thread per session blocked in b200enc_encode (auto_batch scheduler); host frames in, bitstreams out"}
-        groups = new_groups(); batch = groups[0][1]; sess += [x for g in groups for x in g[0]]
-    # per-kernel shares of one P step over ALL sessions of the GPU in a single batch (CUDA events around each launch on the
-    # batch's stream); fresh sessions, so two untimed frames first (IDR + one P)
+    # ---- end to end through the reference's boundary (tools/e2e_plugin.cpp): dlopen libVideoCodec.so, CreateVideoEncoder / InitEncoder /
+    # EncodeOneFrame, one C++ caller thread per session, frames in pageable malloc memory; H2D and the bitstream read-back are inside
     for g_ in groups:
         g_[1].close()
     for x in sess:
         x.close()
+    sess, groups = [], []
+    E = e2e_lib()
+    flat = np.ascontiguousarray(np.stack([np.asarray(f, np.uint8).ravel() for f in pool]))
+    prof_name = {0: b"baseline", 1: b"main", 2: b"high"}[PROFILE]
+    os.environ["PROP_persist_vmi_b200_encode_slices"] = str(SLICES)
+    os.environ["PROP_persist_vmi_b200_encode_search_range"] = str(SR)
+    if CQP >= 0:
+        os.environ["PROP_persist_vmi_b200_encode_const_qp"] = str(CQP)
+    h = E.e2e_open(os.path.join(ROOT, "media_b200", "host", "libVideoCodec.so").encode(), S, W, H, FPS, BITRATE, GOP, prof_name,
+                   b"rgba" if FMT == 2 else b"i420", dev, flat.ctypes.data, len(pool), fb)
+    err = E.e2e_last_error(h).decode()
+    assert not err, f"e2e plugin driver: {err}"
+    res = E2EResult()
+    assert E.e2e_run(h, 0, max(3, args.warmup), 0, C.byref(res)) == 0 and res.errors == 0, "e2e warm-up failed"
+    barrier()
+    t0 = time.perf_counter()
+    assert E.e2e_run(h, max(3, args.warmup), args.steps, 0, C.byref(res)) == 0
+    barrier()
+    el_e = time.perf_counter() - t0
+    e2e_frames, out_bytes_e, e2e_errors = res.frames, res.bytes, res.errors
+    e2e_lat = {"p50": round(res.lat_p50_ms, 2), "p99": round(res.lat_p99_ms, 2), "max": round(res.lat_max_ms, 2)}
+    if use_dist:
+        t = torch.tensor([el_e], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); el_e = t[0].item()
+        t = torch.tensor([float(e2e_frames), float(out_bytes_e), float(e2e_errors)], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_frames, out_bytes_e, e2e_errors = int(t[0].item()), int(t[1].item()), int(t[2].item())
+    else:
+        e2e_frames, out_bytes_e = int(e2e_frames), int(out_bytes_e)
+    e2e = e2e_frames / el_e
+    # ---- the same sessions paced at FPS through the same boundary (BASELINE config 5 in one point): every frame must be back before
+    # the next capture time. args.realtime_seconds = 0 skips it.
+    realtime = None
+    if args.realtime_seconds > 0 and S > 1:
+        barrier()
+        rsteps = int(args.realtime_seconds * FPS)
+        assert E.e2e_run(h, max(3, args.warmup) + args.steps, rsteps, 1, C.byref(res)) == 0
+        barrier()
+        rt = [float(res.late), float(res.errors), res.lat_p99_ms, res.lat_max_ms, res.lat_p50_ms]
+        if use_dist:
+            t = torch.tensor(rt[:2], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            u = torch.tensor(rt[2:], dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.MAX)
+            rt = t.tolist() + u.tolist()
+        realtime = {"sessions_per_gpu": S, "sessions": S * world, "fps": FPS, "seconds": args.realtime_seconds, "frames": S * world * rsteps,
+                    "late_frames": int(rt[0]), "errors": int(rt[1]), "latency_ms": {"p50": round(rt[4], 2), "p99": round(rt[2], 2), "max": round(rt[3], 2)},
+                    "realtime": bool(rt[0] == 0 and rt[1] == 0 and rt[2] <= 1000.0 / FPS),
+                    "via": "VideoEncoder::EncodeOneFrame, one paced caller thread per session (staggered phases), pageable input"}
+    E.e2e_close(h)
+    # per-kernel shares of one P step over ALL sessions of the GPU in a single batch (CUDA events around each launch on the
+    # batch's stream); fresh sessions, so two untimed frames first (IDR + one P)
     sess = [new_session(enc, dev) for _ in range(S)]
     batch = enc.Batch(dev, sess)
     groups = [(sess, batch, list(range(S)))]
@@ -259,6 +276,8 @@ def run_b200(args):
     batch.set_profiling(False)
     tot = sum(ms for _, ms in kt) or 1.0
     top = max(kt, key=lambda x: x[1])
+    # the QP / frame-type trace of one session of the device-resident run: what the CPU arm is driven with
+    qp_trace = [int(x) for x in trace_qps]
     line = None
     if rank == 0:
         peaks = {}
@@ -269,44 +288,61 @@ def run_b200(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         npx = ((W + 15) // 16 * 16) * ((H + 15) // 16 * 16)
         nmb = npx // 256
-        # algorithmic bytes per P frame: src 1.5 + ref 1.5 + recon 1.5 B/px for ME+coding, +3.0 for the in-place deblock pass
+        ktd = dict(kt)
+        # ---- INT roofline of the motion-search / inter-coding kernels: ALGORITHMIC integer operations per macroblock of the
+        # implemented search, per instruction class, over the live kernel time, against the issue peak of each class measured on this GPU
+        # in this process (b200k_int_peaks: register-resident chains on all SMs, clock from clock64 / globaltimer inside the kernel)
+        ops = me_ops_per_mb(SR)
+        pk = (C.c_double * 36)()
+        enc.check(L.b200k_int_peaks(dev, pk, 9))
+        names = ["vabsdiff4", "iadd3", "lop3", "idp4a", "imad", "vimnmx+lop3", "iabs+2iadd", "shf", "satd4x4"]
+        peak_tab = {n: {"gwarp_instr_s": round(pk[4 * i], 1), "per_clk_per_sm": round(pk[4 * i + 1], 3), "sm_mhz_in_run": round(pk[4 * i + 2], 1)} for i, n in enumerate(names)}
+        cls_peak = {"vabsdiff4": pk[0], "idp4a": pk[12], "alu": min(pk[4], pk[8]), "imad": pk[16], "shift": pk[28]}
+        fine_ops = {c: sum(v for (k, cc), v in ops.items() if cc == c and k != "coarse") for c in cls_peak}
+        coarse_ops = {c: sum(v for (k, cc), v in ops.items() if cc == c and k == "coarse") for c in cls_peak}
+
+        def int_roof(kname, by_class):
+            ms = ktd.get(kname, 0.0)
+            lane_ops = sum(by_class.values())
+            if ms <= 0 or lane_ops <= 0:
+                return None
+            warp_instr = lane_ops / 32.0 * nmb * Sp                     # at full lane use
+            t_peak = sum(v / 32.0 * nmb * Sp / (cls_peak[c] * 1e9) for c, v in by_class.items() if v)      # seconds at each class's own issue peak
+            ach = warp_instr / (ms * 1e-3) / 1e9
+            peak = warp_instr / t_peak / 1e9                              # mix-weighted (harmonic) issue peak of this operation mix
+            return {"kernel": kname, "ms": round(ms, 4), "lane_ops_per_mb": int(lane_ops), "warp_instr_per_mb": round(lane_ops / 32.0, 1),
+                    "achieved": round(ach, 1), "peak": round(peak, 1), "unit": "G warp-instr/s", "frac": round(ach / peak, 4)}
+        r_fine, r_coarse = int_roof("k_me_fine", fine_ops), int_roof("k_me_coarse", coarse_ops)
+        # DRAM traffic and executed instructions of the dominant kernel from the committed `ncu --set full` capture of THIS round's binary
+        # (profiles/r02_ncu_kernels.json, written by tools/final_capture.sh as the last step), scaled from its sessions per launch
+        traffic, ncu_note = None, None
+        for prof_file in ("r02_ncu_kernels.json", "r01_ncu_kernels.json"):
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", prof_file)))
+                k = prof["kernels"][top[0]]
+                traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) * Sp / prof["sessions_per_launch"]
+                ncu_note = {"source": "profiles/" + prof_file, "alu_pipe_pct_of_peak": k["alu_pipe_pct"], "sm_throughput_pct_of_peak": k["sm_throughput_pct"],
+                            "executed_warp_instr_per_mb_1080p": round(k["warp_instructions"] / (8160 * prof["sessions_per_launch"]), 1),
+                            "registers": k.get("registers"), "warps_active_pct": k.get("warps_active_pct")}
+                break
+            except Exception:
+                continue
+        # HBM view of the same kernel: algorithmic bytes per P frame = src 1.5 + ref 1.5 + recon 1.5 B/px
         alg_bytes = {"k_me_fine": 4.5 * npx, "k_me_coarse": 2 * 0.3125 * npx, "k_deblock_wave": 3.0 * npx, "k_intra_wave": 3.0 * npx,
                      "k_cavlc_mb": nmb * 864.0, "k_ingest_planar": 3.0 * npx, "k_ingest_rgba": 5.5 * npx, "k_refplanes": 5.0 * npx}.get(top[0], 4.5 * npx) * Sp
-        ach = alg_bytes / (top[1] * 1e-3) / 1e9
-        gi, clk = C.c_double(), C.c_int()
-        L.b200k_vabsdiff4_peak(dev, C.byref(gi), C.byref(clk))
-        me_fine = dict(kt).get("k_me_fine", 0.0); me_coarse = dict(kt).get("k_me_coarse", 0.0)
-        # implemented search, pixel absolute differences per MB: L2 81*64, L1 25*64, L0 26*256; SATD stage counted as 17*256
-        absdiff_mb = (2 * SR // 4 + 1) ** 2 * 64 + 25 * 64 + 26 * 256 + 17 * 256 + 3 * 256      # + the intra estimate's three 16x16 SATDs
-        me_ms = me_fine + me_coarse
-        int_ach = (absdiff_mb / 4.0) * nmb * Sp / 32.0 / (me_ms * 1e-3) / 1e9 if me_ms > 0 else 0.0   # warp-instructions -> G lane... see DESIGN 5
-        cpu = cpu_baseline_sample(threads=1, frames=args.cpu_frames) if world == 1 and not args.no_cpu else None
-        # DRAM traffic and pipe utilisation of the dominant kernel from the committed `ncu --set full` capture (profiles/), scaled
-        # from that capture's sessions per launch to this run's
-        traffic, ncu_note = None, None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))
-            k = prof["kernels"][top[0]]
-            traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) * Sp / prof["sessions_per_launch"]
-            ncu_note = {"source": "profiles/r01_ncu_kernels.json", "alu_pipe_pct_of_peak": k["alu_pipe_pct"], "sm_throughput_pct_of_peak": k["sm_throughput_pct"],
-                        "warp_instructions_per_mb_1080p": round(k["warp_instructions"] / (8160 * prof["sessions_per_launch"]), 1)}
-        except Exception:
-            pass
-        # instruction-issue roofline of the dominant kernel: executed warp-instructions per launch (committed ncu capture, scaled to this
-        # run's sessions and macroblock count) over its live CUDA-event time, against SMs x 4 schedulers x the SM clock sampled under load
-        issue = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))
-            wi = prof["kernels"][top[0]]["warp_instructions"] * Sp / prof["sessions_per_launch"] * nmb / 8160.0
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            mhz = (clocks or {}).get("sm_mhz") or 1965.0
-            peak_issue = sms * 4 * mhz * 1e6 / 1e9
-            ach_issue = wi / (top[1] * 1e-3) / 1e9
-            issue = {"kernel": top[0], "warp_instructions_per_launch": round(wi), "achieved_gwarp_instr_s": round(ach_issue, 1), "peak_gwarp_instr_s": round(peak_issue, 1),
-                     "frac": round(ach_issue / peak_issue, 4), "sms": sms, "sm_mhz": mhz,
-                     "note": "all executed warp-instructions (ncu smsp__inst_executed.sum of the committed capture) over the live kernel time; the kernel is issue-bound, this is the roofline that bounds it"}
-        except Exception:
-            pass
+        ach_hbm = alg_bytes / (top[1] * 1e-3) / 1e9
+        roof_top = r_fine if top[0] == "k_me_fine" else r_coarse if top[0] == "k_me_coarse" else None
+        if roof_top:
+            roofline = {"bound": "int-issue", "kernel": top[0], "share_of_step": round(top[1] / tot, 3), "achieved": roof_top["achieved"], "peak": roof_top["peak"],
+                        "unit": roof_top["unit"], "frac": roof_top["frac"], "traffic": traffic, "lane_ops_per_mb": roof_top["lane_ops_per_mb"],
+                        "ops_per_mb_by_class": {c: int(v) for c, v in fine_ops.items()} if top[0] == "k_me_fine" else {c: int(v) for c, v in coarse_ops.items()},
+                        "peak_is": "mix-weighted issue peak of the kernel's algorithmic operation classes, each class measured live (int_peaks)",
+                        "hbm": {"achieved_gbs": round(ach_hbm, 1), "peak_gbs": hbm_peak, "frac": round(ach_hbm / hbm_peak, 4), "algorithmic_bytes_per_launch": int(alg_bytes)},
+                        "ncu": ncu_note}
+        else:
+            roofline = {"bound": "hbm", "kernel": top[0], "share_of_step": round(top[1] / tot, 3), "achieved": round(ach_hbm, 1), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(ach_hbm / hbm_peak, 4), "traffic": traffic, "ncu": ncu_note}
+        cpu = cpu_baseline_sample(threads=1, frames=args.cpu_frames, qps=qp_trace) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(el / args.steps * 1e3, 4), "device_ms_per_step": round(dev_ms / args.steps, 4),
@@ -315,28 +351,27 @@ def run_b200(args):
             "config": {"workload": f"{S} concurrent {W}x{H} sessions per GPU, {LABEL}; step = one frame of every session; {G} batch(es) of {group_sizes[0]} on own streams",
                        "sessions_per_gpu": S, "frames_per_step": S * world, "l2_policy": (f"inputs larger than L2: per-step working set ~{S * npx * 10 // 1000000} MB" if S * npx * 10 > 130e6 else
                                      f"working set ~{S * npx * 10 // 1000000} MB fits L2; every step encodes a different frame of the pool, reference planes are rewritten each step"),
-                       "parallelism": f"sessions sharded over {world} GPU(s), no collective",
+                       "parallelism": f"sessions sharded over {world} GPU(s), no collective (process group: gloo, barrier + timing reductions only)",
                        "timing": "value/ms_per_step: host clock between a device synchronize + barrier on both sides (max over ranks; an upper bound of the device time of "
                                  "the overlapping batch streams); device_ms_per_step: CUDA events on the batch streams (slowest batch group); kernel_ms: CUDA events per launch"},
-            "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": world * S * fb, "d2h_bytes_per_step": int(world * out_bytes_e / args.steps),
-                    "ms_per_step": round(el_e / args.steps * 1e3, 4)},
+            "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": world * S * fb, "d2h_bytes_per_step": int(out_bytes_e / args.steps),
+                    "ms_per_step": round(el_e / args.steps * 1e3, 4), "errors": e2e_errors, "call_latency_ms": e2e_lat,
+                    "via": "VideoEncoder::EncodeOneFrame through dlopen(libVideoCodec.so) + CreateVideoEncoder, one C++ caller thread per session, pageable (malloc) input, "
+                           "encoder-owned output read by the caller; H2D staging and copies inside the timed region"},
             "gpu_launches": launches,
             "bitrate_mbps_per_session": round(out_bytes * 8 / (S * args.steps) * FPS / 1e6, 3),
             "kernel_ms": {k: round(v, 4) for k, v in kt},
-            "roofline": {"bound": "hbm", "kernel": top[0], "share_of_step": round(top[1] / tot, 3), "achieved": round(ach, 1), "peak": hbm_peak,
-                         "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": traffic, "ncu": ncu_note,
-                         "note": "the encode path is INT-ALU/latency bound, not HBM bound (SURVEY 8d); see roofline_int"},
-            "roofline_int": {"kernels": "k_me_coarse+k_me_fine", "achieved_gwarp_instr_s": round(int_ach, 2),
-                             "peak_gwarp_instr_s": round(gi.value / 32.0, 2), "peak_glane_instr_s": round(gi.value, 1), "sm_clock_mhz_in_peak_run": clk.value,
-                             "frac": round(int_ach / (gi.value / 32.0), 4) if gi.value else None,
-                             "unit": "G warp-instr/s of VABSDIFF4-equivalent work (px-absdiff/4/32)"},
-            "roofline_issue": issue,
+            "roofline": roofline,
+            "roofline_me": {"k_me_fine": r_fine, "k_me_coarse": r_coarse,
+                            "note": "algorithmic lane-operations per MB (DESIGN.md 5: SAD as VABSDIFF4 words, SATD as its dp4a/butterfly work, interpolation averages, "
+                                    "chroma MC, 24-block transform/quant/recon) / 32 = warp-instructions at full lane use"},
+            "int_peaks": peak_tab,
             "clocks": clocks,
         }
+        if realtime:
+            line["realtime"] = realtime
         if cpu:
             line["cpu_baseline"] = cpu
-        if thr:
-            line["e2e_caller_threads"] = thr
     for s in sess:
         s.close()
     batch.close()
@@ -344,6 +379,51 @@ def run_b200(args):
         dist.barrier(); dist.destroy_process_group()
     if line:
         print(json.dumps(line), flush=True)
+
+
+def me_ops_per_mb(sr):
+    """ALGORITHMIC integer lane-operations per macroblock of the implemented P-picture path, keyed by (stage, instruction class).
+    Classes: vabsdiff4 (one op = 4 pixel absolute differences), idp4a, alu (add / logic / abs / min / max), imad, shift."""
+    o = {}
+    r4 = sr // 4
+    # k_me_coarse: level 2 = (2 R/4 + 1)^2 candidates x 8x8 px, level 1 = 25 x 8x8 px; a VABSDIFF4 covers 4 px
+    o[("coarse", "vabsdiff4")] = ((2 * r4 + 1) ** 2 * 64 + 25 * 64) / 4
+    # k_me_fine: level 0 = 25 candidates + the zero vector, 16x16 px each
+    o[("sad0", "vabsdiff4")] = 26 * 256 / 4
+    # SATD: 17 sub-pel candidates + 3 intra-estimate predictors, 16 4x4 blocks each; per block 16 IDP.4A (horizontal transform with the
+    # source folded in), 16 add/sub (vertical butterflies), 8 abs + 4 max + 4 add (|x+y| + |x-y| = 2 max(|x|, |y|))
+    nb = 20 * 16
+    o[("satd", "idp4a")] = nb * 16; o[("satd", "alu")] = nb * (16 + 8 + 4 + 4)
+    # quarter-pel prediction: 8 candidates x 64 words, per-byte rounded average = 4 logic/add ops; the 9 half-pel candidates are plain fetches
+    o[("qpel", "alu")] = 8 * 64 * 4
+    # final MC: luma average (64 words x 4) + chroma bilinear 128 px x (4 IMAD + 1 shift)
+    o[("mc", "alu")] = 64 * 4; o[("mc", "imad")] = 128 * 4; o[("mc", "shift")] = 128
+    # transform / quant / recon of 24 4x4 blocks (SURVEY 8d: 240 ops per block): fwd 64 add, quant 16 mul + 16 add + 16 shift, dequant 16 mul,
+    # inverse 64 add + 16 shift, recon 16 add + 32 min/max
+    o[("tq", "alu")] = 24 * (64 + 16 + 64 + 16 + 32); o[("tq", "imad")] = 24 * 32; o[("tq", "shift")] = 24 * 32
+    return o
+
+
+class E2EResult(__import__("ctypes").Structure):
+    _fields_ = [("seconds", __import__("ctypes").c_double), ("frames", __import__("ctypes").c_uint64), ("bytes", __import__("ctypes").c_uint64),
+                ("errors", __import__("ctypes").c_uint64), ("late", __import__("ctypes").c_uint64),
+                ("lat_p50_ms", __import__("ctypes").c_double), ("lat_p99_ms", __import__("ctypes").c_double), ("lat_max_ms", __import__("ctypes").c_double)]
+
+
+def e2e_lib():
+    """tools/libe2e_plugin.so: the C++ caller of the reference boundary (built by __graft_entry__.build())"""
+    import ctypes as C
+    path = os.path.join(ROOT, "tools", "libe2e_plugin.so")
+    if not os.path.exists(path):
+        import __graft_entry__ as ge
+        ge.build()
+    E = C.CDLL(path)
+    E.e2e_open.restype = C.c_void_p
+    E.e2e_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
+    E.e2e_run.restype = C.c_int; E.e2e_run.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.POINTER(E2EResult)]
+    E.e2e_close.argtypes = [C.c_void_p]
+    E.e2e_last_error.restype = C.c_char_p; E.e2e_last_error.argtypes = [C.c_void_p]
+    return E
 
 
 def _cpu_worker(args):
@@ -360,18 +440,72 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline_sample(threads, frames):
-    """CPU restatement (oracle/, 'port'), `threads` single-threaded sessions in parallel, `frames` P frames each after one IDR."""
+def cpu_baseline_sample(threads, frames, qps=None):
+    """CPU restatement (oracle/, 'port'), `threads` single-threaded sessions in parallel, `frames` P frames each after one IDR, coded with
+    the QPs the GPU arm's rate control chose for the same frames (qps; without a trace: the QP 4 Mbps settles at on this content)."""
     import multiprocessing as mp
-    qps = [34] * (frames + 1)
+    qps = list(qps)[:frames + 1] if qps else []
+    qps += [qps[-1] if qps else 34] * (frames + 1 - len(qps))
     if threads == 1:
         times = [_cpu_worker((frames, qps))]
     else:
         with mp.get_context("fork").Pool(threads) as pool:
             times = pool.map(_cpu_worker, [(frames, qps)] * threads)
     fps = sum(frames / t for t in times)
-    return {"value": round(fps, 3), "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"{threads} session(s) x {frames} P frames of {W}x{H} content {KIND} at QP 34 after one IDR (CPU restatement oracle/, gcc -O2, NOT openh264: libopenh264 is absent from the image)"}
+    return {"value": round(fps, 3), "unit": "frames/s", "cores": threads, "kind": "port", "qp_trace": qps,
+            "sample": f"{threads} session(s) x {frames} P frames of {W}x{H} content {KIND} after one IDR, QPs = the GPU arm's rate-control trace {qps[:4]}..{qps[-1]} "
+                      "(CPU restatement oracle/, gcc -O2, NOT openh264: libopenh264 is absent from the image)"}
+
+
+def find_real_openh264():
+    """cisco's libopenh264.so on LD_LIBRARY_PATH or in baseline/_ref/ (BASELINE.md 3 step 1). The repo's own ABI look-alike
+    (media_b200/shim/libopenh264.so) does not count: the real library also exports the decoder factory."""
+    import ctypes as C
+    import glob
+    dirs = [d for d in os.environ.get("LD_LIBRARY_PATH", "").split(":") if d] + [os.path.join(ROOT, "baseline", "_ref"), os.path.join(ROOT, "oracle", "_ref")]
+    for d in dirs:
+        for path in sorted(glob.glob(os.path.join(d, "libopenh264.so*"))):
+            try:
+                lib = C.CDLL(path)
+                if hasattr(lib, "WelsCreateSVCEncoder") and hasattr(lib, "WelsCreateDecoder"):
+                    return path
+            except OSError:
+                continue
+    return None
+
+
+def _openh264_worker(args):
+    """one single-threaded reference encoder (the UNMODIFIED VideoEncoderOpenH264 of oracle/_ref/libVideoCodecRef.so, built from
+    /root/reference by oracle/ref_adapter.mk) over real libopenh264: frames/s of `frames` P pictures after the IDR"""
+    lib_path, frames = args
+    import ctypes as C
+    from media_b200.synth import Content
+    C.CDLL(lib_path, mode=C.RTLD_GLOBAL)                 # dlopen("libopenh264.so") inside the wrapper then resolves to this object by SONAME
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libVideoCodecRef.so"))
+    L.vc_create.argtypes = [C.POINTER(C.c_void_p)]
+    for f in ("vc_init", "vc_start", "vc_stop", "vc_destroy"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.vc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    L.vc_prop_set.argtypes = [C.c_char_p, C.c_char_p]
+    for k, v in (("ro.vmi.demo.video.encode.format", "0"), ("ro.sys.vmi.cloudphone", "video"), ("ro.hardware.width", W), ("ro.hardware.height", H),
+                 ("ro.hardware.fps", FPS), ("persist.vmi.video.encode.bitrate", BITRATE), ("persist.vmi.video.encode.gopsize", GOP),
+                 ("persist.vmi.video.encode.profile", {0: "baseline", 1: "main", 2: "high"}[PROFILE]),
+                 ("persist.vmi.video.encode.param_adjusting", "0"), ("persist.vmi.video.encode.keyframe", "0")):
+        L.vc_prop_set(k.encode(), str(v).encode())
+    e = C.c_void_p()
+    if L.vc_create(C.byref(e)) or L.vc_init(e) or L.vc_start(e):
+        return None
+    c = Content(KIND, W, H)
+    fs = [c.frame(t) for t in range(frames + 1)]
+    out, n = C.c_void_p(), C.c_uint32()
+    L.vc_encode(e, fs[0].ctypes.data, fs[0].size, C.byref(out), C.byref(n))
+    t0 = time.perf_counter()
+    for t in range(1, frames + 1):
+        if L.vc_encode(e, fs[t].ctypes.data, fs[t].size, C.byref(out), C.byref(n)):
+            return None
+    el = time.perf_counter() - t0
+    L.vc_stop(e); L.vc_destroy(e)
+    return el
 
 
 def run_reference(args):
@@ -380,16 +514,43 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     frames = max(2, args.cpu_frames // 2)
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(cpu_baseline_sample(threads, frames))
-    best = max(vals, key=lambda v: v["value"])
+    real = find_real_openh264()
+    adapter = os.path.join(ROOT, "oracle", "_ref", "libVideoCodecRef.so")
+    best, arm = None, None
+    if real and os.path.exists(adapter):
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(threads) as pool:
+            times = pool.map(_openh264_worker, [(real, 4 * frames)] * threads)
+        if all(times):
+            fps = sum(4 * frames / t for t in times)
+            arm = f"openh264: {real} through the unmodified VideoEncoderOpenH264 (oracle/_ref/libVideoCodecRef.so), RC_BITRATE_MODE {BITRATE} bps"
+            best = {"value": round(fps, 3), "unit": "frames/s", "cores": threads, "kind": "reference",
+                    "sample": f"{threads} single-threaded sessions x {4 * frames} P frames of {W}x{H} content {KIND} after one IDR; {arm}"}
+    if best is None:
+        # libopenh264 is not in this image: the arm that runs is the CPU restatement, driven with the QPs the rate control
+        # of the GPU arm settles at for this workload (profiles/: bench line's cpu_baseline.qp_trace), one single-threaded encoder per core
+        arm = "openh264 baseline: not measurable in this image (no libopenh264.so on LD_LIBRARY_PATH or in baseline/_ref/); CPU restatement oracle/ instead"
+        qps = reference_qp_trace(frames)
+        vals = [cpu_baseline_sample(threads, frames, qps) for _ in range(max(1, min(args.steps, 3)))]
+        best = max(vals, key=lambda v: v["value"])
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": best["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{W}x{H} sessions, {LABEL}; CPU restatement of the path, one single-threaded encoder per host core"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "arm": arm,
+        "config": {"workload": f"{W}x{H} sessions, {LABEL}; one single-threaded encoder per host core ({threads} cores, all of the host's; the same at every N)"},
         "cpu_baseline": best, "e2e": {"value": best["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+def reference_qp_trace(frames):
+    """QPs for the CPU arm: what the encoder's own rate control (the same object, through the b200k_rc_* hooks -- host logic, no GPU) asks for
+    when it is fed the sizes the CPU restatement produces: the closed loop of tools/rc_sim.py on the first frames of the workload"""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import rc_sim
+        r = rc_sim.simulate(W, H, KIND, BITRATE, min(frames + 1, 8), gop=GOP)
+        return r["qps"]
+    except Exception:
+        return [34] * (frames + 1)
 
 
 def main():
@@ -404,7 +565,7 @@ def main():
     ap.add_argument("--slices", type=int, default=None, help="override the workload's slice count (0 = the engine's automatic count)")
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--threads-e2e", action="store_true", help="also measure one caller thread per session through the auto_batch scheduler")
+    ap.add_argument("--realtime-seconds", type=float, default=2.0, help="length of the paced real-time leg through the plugin boundary (0 = skip)")
     args = ap.parse_args()
     apply_workload(args)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -56,7 +56,8 @@ typedef struct b200enc_config {
     int input_format;      /* B200ENC_FMT_* */
     int device;            /* CUDA ordinal, or -1: least-loaded device by pixel rate */
     int level_idc;         /* 0: derive from size and fps (the wrapper's LEVEL_3_2 at :255 is too small for 1080p) */
-    int debug;             /* 1: keep stage dumps (pre-deblock reconstruction) for b200enc_get_stage */
+    int debug;             /* bit 0: keep stage dumps (pre-deblock reconstruction) for b200enc_get_stage; bit 1 (test hook): 8 KB output buffer, so that
+                              the overflow path can be exercised */
     int scene_change;      /* 1 (default): a P frame whose macroblocks come out >= 2/5 intra after motion estimation is coded as an
                               IDR instead (the wrapper asks openh264 for bEnableSceneChangeDetect, VideoEncoderOpenH264.cpp:283) */
     int auto_batch;        /* 1: concurrent b200enc_encode calls of sessions living on the same GPU are coalesced by a per-GPU
@@ -170,6 +171,10 @@ double b200k_rc_vbv(void *rc, double *bucket_bits);
 void b200k_rc_destroy(void *rc);
 /* microbenchmark: register-resident VABSDIFF4.U8.ACC issue rate, giga lane-instructions per second, and the SM clock seen */
 int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz);
+/* issue-rate microbenchmarks behind the INT roofline: kind 0 VABSDIFF4.U8.ACC, 1 IADD3, 2 LOP3, 3 IDP.4A, 4 IMAD, 5 VIMNMX, 6 IABS + IADD, 7 SHF,
+ * 8 the 4x4 Hadamard SATD of the motion search counted as 64 lane-operations. out[4 * kind + 0..3] = G warp-instructions/s of the whole GPU,
+ * warp-instructions per clock per SM, the SM clock of the run in MHz (clock64 / globaltimer measured inside the kernel), instructions per unit */
+int b200k_int_peaks(int device, double *out, int kinds);
 
 #ifdef __cplusplus
 }

@@ -384,7 +384,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     // resident (floor: one CTA per SM), because there the wavefront's own latency is all that matters.
     auto resident_ctas = [&](int pct) { return std::max(1, std::min(wave_ctas, std::max(148, (n * ((g.mbh * pct + 99) / 100) + WAVE_WARPS - 1) / WAVE_WARPS))); };
     pf.begin("k_intra_wave", sw); k_intra_wave<<<wave_ctas, WAVE_WARPS * 32, 0, sw>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
-    for (int i = 0; i < n; i++) if (ss[i]->cfg.debug) {
+    for (int i = 0; i < n; i++) if (ss[i]->cfg.debug & 1) {
         uint8_t **cur = ss[i]->cur_is_A ? ss[i]->bufA : ss[i]->bufB;
         for (int c = 0; c < 3; c++) cudaMemcpyAsync(ss[i]->rec_pre[c], cur[c], (size_t)g.wc * g.hc / (c ? 4 : 1), cudaMemcpyDeviceToDevice, sw);
     }
@@ -722,7 +722,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         std::vector<Item> items;
         auto add = [&](auto &ptr, size_t bytes) { items.push_back({ reinterpret_cast<void **>(&ptr), bytes }); };
         add(s->input, b200enc_frame_bytes(s));
-        for (int k = 0; k < 3; k++) { const size_t b = k ? nc : ny; add(s->src[k], b); add(s->bufA[k], b); add(s->bufB[k], b); add(s->rec_pre[k], c.debug ? b : 16); }
+        for (int k = 0; k < 3; k++) { const size_t b = k ? nc : ny; add(s->src[k], b); add(s->bufA[k], b); add(s->bufB[k], b); add(s->rec_pre[k], (c.debug & 1) ? b : 16); }
         const size_t l1 = (size_t)g.s1 * (g.hc / 2 + 2 * g.p1) + 64, l2 = (size_t)g.s2 * (g.hc / 4 + 2 * g.p2) + 64;
         const size_t lplane = (size_t)g.ls * (g.hc + 2 * g.lp), cplane = (size_t)g.cs * (g.hc / 2 + 2 * g.cp) + 64;
         add(s->srcL1, l1); add(s->refL1, l1); add(s->srcL2, l2); add(s->refL2, l2);
@@ -754,6 +754,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         // output buffer: twice the raw frame + 64 KB (CAVLC without I_PCM can exceed the raw size on noise at very low QP:
         // 1.75x measured at QP 0); a frame that still does not fit is reported as B200ENC_EOVERFLOW, never truncated silently
         s->out_cap = (uint32_t)align_up(std::max<size_t>(ny * 3, 1 << 16) + (1 << 16), 256);
+        if (c.debug & 2) s->out_cap = 8192;          // test hook: a buffer small enough to exercise the overflow path
         CU_TRY(cudaHostAlloc(&s->h_out, s->out_cap + 256, cudaHostAllocMapped), rc = B200ENC_ENOMEM; break);
         CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s->d_out), s->h_out, 0), rc = B200ENC_ECUDA; break);
         memset(s->h_out, 0, s->out_cap + 256);
@@ -886,7 +887,7 @@ int b200enc_get_stage(b200enc_session *s, int stage, void *out, size_t cap, size
     case B200ENC_STAGE_BIN_OFF: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->mb_off; bytes = nmb * 4; break;
     case B200ENC_STAGE_BINS: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->bins; bytes = nmb * B200_MB_BIN_SLOT * sizeof(uint16_t); break;
     case B200ENC_STAGE_SRC: planes = s->src; break;
-    case B200ENC_STAGE_REC_PRE: if (!s->cfg.debug) return B200ENC_EINVAL; planes = s->rec_pre; break;
+    case B200ENC_STAGE_REC_PRE: if (!(s->cfg.debug & 1)) return B200ENC_EINVAL; planes = s->rec_pre; break;
     case B200ENC_STAGE_REC: planes = last; break;
     default: return B200ENC_EINVAL;
     }

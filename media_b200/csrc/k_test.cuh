@@ -3,6 +3,7 @@
 // C functions in the same roles), plus the VABSDIFF4 issue-rate microbenchmark that defines the ME roofline.
 #pragma once
 #include "h264_dev.cuh"
+#include "k_me.cuh"
 
 namespace b200 {
 
@@ -61,6 +62,64 @@ __global__ void __launch_bounds__(256) k_vabsdiff4_peak(uint32_t seed, int iters
     }
     const long long t1 = clock64();
     if (threadIdx.x == 0) clocks[blockIdx.x] = t1 - t0;
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s0 ^ s1 ^ s2 ^ s3 ^ s4 ^ s5 ^ s6 ^ s7;
+}
+
+// Issue-rate microbenchmarks of the integer instructions the motion search and the transform chain are made of (the denominators of the
+// INT roofline): register-resident, 8 independent dependency chains per thread, 2 048 resident threads per SM.
+// KIND 0 VABSDIFF4.U8.ACC, 1 IADD3, 2 LOP3, 3 IDP.4A, 4 IMAD, 5 VIMNMX (max), 6 IABS + IADD (abs as the kernels use it), 7 SHF (funnel shift),
+// 8 = the kernel's own 4x4 Hadamard SATD (satd_rows of k_me.cuh: 16 IDP.4A + butterflies + abs / max) counted as 64 lane-operations.
+// Every block records its own cycle count (clock64) and its own duration in ns (globaltimer): the SM clock of the run is their ratio,
+// measured inside the kernel and not read from the driver afterwards.
+template <int KIND>
+__device__ __forceinline__ uint32_t int_peak_op(uint32_t a, uint32_t b, uint32_t c)
+{
+    if (KIND == 0) return sad4(a, b, c);
+    if (KIND == 1) return a + b + c;
+    if (KIND == 2) return (a & b) ^ c;
+    if (KIND == 3) return (uint32_t)dp4a_us(a, b, (int)c);
+    if (KIND == 4) return a * b + c;
+    if (KIND == 5) return (uint32_t)max((int)a ^ (int)c, (int)b);
+    if (KIND == 6) return (uint32_t)abs((int)(c - a)) + b;
+    return __funnelshift_r(a, c, b);
+}
+template <int KIND>
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t seed, int iters, uint32_t *sink, long long *clocks, unsigned long long *ns)
+{
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+    uint32_t s0 = 0, s1 = 1, s2 = 2, s3 = 3, s4 = 4, s5 = 5, s6 = 6, s7 = 7;
+    unsigned long long n0, n1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n0));
+    const long long t0 = clock64();
+    if (KIND == 8) {
+        // 8 independent SATD evaluations per iteration on rotating prediction words
+        int Ts[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) Ts[k] = (int)(a0 >> k) & 1023;
+        uint32_t P[4] = { a0, a1, a2, a3 };
+#pragma unroll 1
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int v = satd_rows(P, Ts);
+                s0 += (uint32_t)v;
+                // every prediction word depends on the result, so no part of an evaluation can be reused by the next (+9 instructions, not counted)
+                P[0] = P[0] * 5u + s0; P[1] = P[1] * 3u + s0; P[2] += s0 + (uint32_t)u; P[3] ^= s0;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                s0 = int_peak_op<KIND>(a0, s1, s0); s1 = int_peak_op<KIND>(a1, s2, s1); s2 = int_peak_op<KIND>(a2, s3, s2); s3 = int_peak_op<KIND>(a3, s4, s3);
+                s4 = int_peak_op<KIND>(a4, s5, s4); s5 = int_peak_op<KIND>(a5, s6, s5); s6 = int_peak_op<KIND>(a6, s7, s6); s7 = int_peak_op<KIND>(a7, s0, s7);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
+    if (threadIdx.x == 0) { clocks[blockIdx.x] = t1 - t0; ns[blockIdx.x] = n1 - n0; }
     sink[blockIdx.x * blockDim.x + threadIdx.x] = s0 ^ s1 ^ s2 ^ s3 ^ s4 ^ s5 ^ s6 ^ s7;
 }
 

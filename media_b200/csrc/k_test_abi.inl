@@ -155,6 +155,57 @@ int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz)
 }
 
 
+} // extern "C"
+// out[kind * 4 + {0,1,2,3}] = G warp-instructions/s over the whole GPU (CUDA events), warp-instructions per clock per SM, SM clock in MHz of the
+// run (clock64 / globaltimer inside the kernel, median block), lane-operations per counted unit (32, or 64 x 32 for the SATD kind)
+template <int KIND> static int run_int_peak(int sms, double *out)
+{
+    const int ctas = sms * 8, iters = KIND == 8 ? 1 << 11 : 1 << 15;
+    DevBuf dsink((size_t)ctas * 256 * 4), dclk((size_t)ctas * 8), dns((size_t)ctas * 8);
+    if (!dsink.p || !dclk.p || !dns.p) return B200ENC_ENOMEM;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_int_peak<KIND><<<ctas, 256>>>(1u, 64, dsink.as<uint32_t>(), dclk.as<long long>(), dns.as<unsigned long long>());
+    float best_ms = 1e30f;
+    std::vector<long long> clk(ctas); std::vector<unsigned long long> ns(ctas);
+    double mhz = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_int_peak<KIND><<<ctas, 256>>>(rep + 2u, iters, dsink.as<uint32_t>(), dclk.as<long long>(), dns.as<unsigned long long>());
+        cudaEventRecord(e1);
+        K_TRY(cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best_ms) {
+            best_ms = ms;
+            K_TRY(cudaMemcpy(clk.data(), dclk.p, (size_t)ctas * 8, cudaMemcpyDeviceToHost));
+            K_TRY(cudaMemcpy(ns.data(), dns.p, (size_t)ctas * 8, cudaMemcpyDeviceToHost));
+            std::vector<double> r;
+            for (int i = 0; i < ctas; i++) if (ns[i] > 1000) r.push_back((double)clk[i] / (double)ns[i] * 1e3);
+            std::sort(r.begin(), r.end());
+            mhz = r.empty() ? 0 : r[r.size() / 2];
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double units_per_thread = (double)iters * (KIND == 8 ? 8.0 * 64.0 : 32.0);      // SATD: 8 evaluations of 64 lane-operations per iteration
+    const double warp_instr = (double)ctas * 8 * units_per_thread;
+    out[0] = warp_instr / (best_ms * 1e-3) / 1e9;
+    out[2] = mhz;
+    out[1] = mhz > 0 ? out[0] * 1e9 / sms / (mhz * 1e6) : 0;
+    out[3] = KIND == 8 ? 64.0 : 1.0;
+    return B200ENC_OK;
+}
+extern "C" {
+int b200k_int_peaks(int device, double *out, int kinds)
+{
+    if (!out || kinds < 1) return B200ENC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ENC_ENODEV;
+    cudaDeviceProp prop; K_TRY(cudaGetDeviceProperties(&prop, device));
+    const int sms = prop.multiProcessorCount;
+    typedef int (*Fn)(int, double *);
+    const Fn fns[9] = { run_int_peak<0>, run_int_peak<1>, run_int_peak<2>, run_int_peak<3>, run_int_peak<4>, run_int_peak<5>, run_int_peak<6>, run_int_peak<7>, run_int_peak<8> };
+    for (int k = 0; k < kinds && k < 9; k++) { const int rc = fns[k](sms, out + 4 * k); if (rc != B200ENC_OK) return rc; }
+    return B200ENC_OK;
+}
+
 int b200k_cabac_code(int device, const uint16_t *bins, int n, int qp, int is_p, uint8_t *out, int cap, int *out_len)
 {
     if (!bins || n <= 0 || !out || !out_len || cap <= 0) return B200ENC_EINVAL;
