@@ -230,11 +230,15 @@ def run_b200(args):
     assert not err, f"e2e plugin driver: {err}"
     res = E2EResult()
     assert E.e2e_run(h, 0, max(3, args.warmup), 0, C.byref(res)) == 0 and res.errors == 0, "e2e warm-up failed"
+    sb0, sf0, sb1, sf1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
     barrier()
+    L.b200enc_scheduler_stats(dev, C.byref(sb0), C.byref(sf0))
     t0 = time.perf_counter()
     assert E.e2e_run(h, max(3, args.warmup), args.steps, 0, C.byref(res)) == 0
     barrier()
     el_e = time.perf_counter() - t0
+    L.b200enc_scheduler_stats(dev, C.byref(sb1), C.byref(sf1))
+    e2e_avg_batch = round((sf1.value - sf0.value) / max(1, sb1.value - sb0.value), 1)
     e2e_frames, out_bytes_e, e2e_errors = res.frames, res.bytes, res.errors
     e2e_lat = {"p50": round(res.lat_p50_ms, 2), "p99": round(res.lat_p99_ms, 2), "max": round(res.lat_max_ms, 2)}
     if use_dist:
@@ -355,7 +359,7 @@ def run_b200(args):
                        "timing": "value/ms_per_step: host clock between a device synchronize + barrier on both sides (max over ranks; an upper bound of the device time of "
                                  "the overlapping batch streams); device_ms_per_step: CUDA events on the batch streams (slowest batch group); kernel_ms: CUDA events per launch"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": world * S * fb, "d2h_bytes_per_step": int(out_bytes_e / args.steps),
-                    "ms_per_step": round(el_e / args.steps * 1e3, 4), "errors": e2e_errors, "call_latency_ms": e2e_lat,
+                    "ms_per_step": round(el_e / args.steps * 1e3, 4), "errors": e2e_errors, "call_latency_ms": e2e_lat, "avg_sessions_per_batch_step": e2e_avg_batch,
                     "via": "VideoEncoder::EncodeOneFrame through dlopen(libVideoCodec.so) + CreateVideoEncoder, one C++ caller thread per session, pageable (malloc) input, "
                            "encoder-owned output read by the caller; H2D staging and copies inside the timed region"},
             "gpu_launches": launches,

@@ -522,14 +522,16 @@ int session_upload(b200enc_session *s, const uint8_t *frame)
 struct SchedRequest {
     b200enc_session *s; const uint8_t *frame; const uint8_t *bs = nullptr; uint32_t size = 0; b200enc_frame_info info{};
     int rc = B200ENC_OK; bool done = false;
+    std::condition_variable cv;      // one per request: a finished batch wakes exactly its own callers, not every blocked session thread
 };
 struct DeviceScheduler {
-    static constexpr int WORKERS = 3;      // two batch contexts (streams): one batch uploads/queues while the other computes
-    int device = -1, registered = 0, inflight = 0;
-    std::mutex mu; std::condition_variable cv_submit, cv_done;
+    static constexpr int WORKERS = 4;      // batch contexts (own streams): up to four batches in flight, so the latency-bound wavefront kernels of one
+                                           // batch run underneath the throughput kernels of the others
+    int device = -1, registered = 0, inflight = 0, active = 0;       // active: batches on the GPU right now
+    std::mutex mu; std::condition_variable cv_submit;
     std::vector<SchedRequest *> pending;
     std::thread worker[WORKERS]; bool stop = false;
-    b200enc_batch *ctx[WORKERS] = { nullptr, nullptr, nullptr }; int window_us = 300;
+    b200enc_batch *ctx[WORKERS] = { nullptr, nullptr, nullptr, nullptr }; int window_us = 300, fill_us = 4000;
     std::atomic<uint64_t> batches{ 0 }, frames{ 0 };
 
     void run(int w)
@@ -539,11 +541,20 @@ struct DeviceScheduler {
         for (;;) {
             cv_submit.wait(lk, [&] { return stop || !pending.empty(); });
             if (stop && pending.empty()) return;
-            // short rendezvous window: leave early once every session that is not already being encoded has a frame waiting
-            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(window_us);
-            while ((int)pending.size() < registered - inflight && !stop)
-                if (cv_submit.wait_until(lk, deadline) == std::cv_status::timeout) break;
-            if (pending.empty()) continue;                 // the other worker took them
+            // Rendezvous. A batch should carry about a quarter of the GPU's sessions (four batches in flight fill the machine and hide each
+            // other's dependent chains). While fewer than two batches are on the GPU, waiting is lost time: leave after the short window (a
+            // lone caller pays at most that). With two or more in flight the GPU is busy anyway, so wait for the fuller batch -- until enough
+            // callers arrived, a running batch finished, or fill_us passed. Leaves at once when every session not being encoded is waiting.
+            const auto t0 = std::chrono::steady_clock::now();
+            const int target = std::max(1, std::min(ctx[w]->cap, (registered + 3) / 4));
+            while (!stop && !pending.empty()) {
+                const int want = std::min(target, std::max(1, registered - inflight));
+                if ((int)pending.size() >= want) break;
+                const auto limit = t0 + std::chrono::microseconds(active >= 2 ? fill_us : window_us);
+                if (std::chrono::steady_clock::now() >= limit) break;
+                cv_submit.wait_until(lk, limit);
+            }
+            if (pending.empty()) continue;                 // another worker took them
             // one batch = the requests that share the first request's shape AND frame kind (others wait for the next round or
             // the other worker): an IDR costs several times a P frame on the intra wavefront, so key frames travel in their own
             // batch and do not hold back the P frames of the sessions that happen to arrive with them
@@ -553,7 +564,7 @@ struct DeviceScheduler {
                 (same_shape(pending[0]->s, r->s) && next_is_idr(r->s) == kind0 && (int)take.size() < ctx[w]->cap ? take : rest).push_back(r);
             pending.swap(rest);
             const int n = (int)take.size();
-            inflight += n;
+            inflight += n; active++;
             lk.unlock();
             std::vector<b200enc_session *> ss(n); std::vector<const uint8_t *> fr(n), bs(n, nullptr); std::vector<uint32_t> sz(n, 0); std::vector<b200enc_frame_info> inf(n);
             std::vector<int> rcs(n, B200ENC_OK);
@@ -562,12 +573,13 @@ struct DeviceScheduler {
             const int rc = encode_impl(ctx[w], ss.data(), n, fr.data(), IN_UPLOADED, bs.data(), sz.data(), inf.data(), rcs.data());
             batches++; frames += n;
             lk.lock();
-            inflight -= n;
+            inflight -= n; active--;
             for (int i = 0; i < n; i++) {
                 take[i]->bs = bs[i]; take[i]->size = sz[i]; take[i]->info = inf[i]; take[i]->done = true;
                 take[i]->rc = rc != B200ENC_OK && rc != B200ENC_EOVERFLOW ? rc : rcs[i];
+                take[i]->cv.notify_one();
             }
-            cv_done.notify_all();
+            cv_submit.notify_all();                        // workers holding out for a fuller batch re-evaluate (one batch fewer on the GPU)
         }
     }
 };
@@ -582,6 +594,7 @@ DeviceScheduler *scheduler_for(int device)
         std::unique_ptr<DeviceScheduler> d(new DeviceScheduler());
         d->device = device;
         if (const char *e = getenv("B200ENC_BATCH_WINDOW_US")) d->window_us = std::max(0, atoi(e));
+        if (const char *e = getenv("B200ENC_BATCH_FILL_US")) d->fill_us = std::max(0, atoi(e));
         for (int w = 0; w < DeviceScheduler::WORKERS; w++) {
             d->ctx[w] = new (std::nothrow) b200enc_batch();
             if (!d->ctx[w] || batch_init(d->ctx[w], device, 512) != B200ENC_OK) return nullptr;
@@ -613,7 +626,7 @@ int scheduler_encode(b200enc_session *s, const uint8_t *frame, const uint8_t **b
     std::unique_lock<std::mutex> lk(d->mu);
     d->pending.push_back(&req);
     d->cv_submit.notify_all();
-    d->cv_done.wait(lk, [&] { return req.done; });
+    req.cv.wait(lk, [&] { return req.done; });
     if (bs) *bs = req.bs;
     if (bs_size) *bs_size = req.size;
     if (info) *info = req.info;

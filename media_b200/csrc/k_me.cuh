@@ -376,14 +376,15 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
         mbar_expect_tx(&sm.bar[1], 4 * PL_ROWS * PL_STRIDE);
         tma_load_3d(sm.plane, tmaps + 256, X1 & ~15, g.lp + y0 + fy - 1, 0, &sm.bar[1]);
     }
-    // sub-pel refinement by SATD: 16 lanes (one per 4x4 block) evaluate one candidate, two candidates per pass
-    const int hw = lane >> 4, b = lane & 15, bx = blk_x(b) * 4, by = blk_y(b) * 4, rx = (b >> 3) & 1;
-    int Ts[16];                                         // horizontal Hadamard of the four source rows (row y ^ rx) of this lane's block
+    // sub-pel refinement by SATD: lane = (half-warp hw, 4x4 block b). A half-warp evaluates one candidate at a time over its 16 blocks, the
+    // two half-warps evaluate different candidates in the same instruction stream.
+    const int hw = lane >> 4, b = lane & 15, bx = blk_x(b) * 4, by = blk_y(b) * 4;
+    int Ts[16];                                         // horizontal Hadamard of the four source rows of this lane's block
     {
         const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            const uint32_t w = sm.src[(by + (y ^ rx)) * 4 + (bx >> 2)];
+            const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
 #pragma unroll
             for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(w, H[k], 0);
         }
@@ -398,43 +399,96 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     __syncwarp();
     // se(v) lengths of the 7 possible vector components per axis: lane l holds x offset l-3 (l < 8) or y offset l-11 (l >= 8)
     const int mvb = se_len(((lane & 8) ? 4 * fy - ppy : 4 * fx - ppx) + (lane & 7) - 3);
-    int qx = 0, qy = 0;                                 // offset from 4*(fx,fy), quarter-pel units
-    uint32_t centre_key = 0;
+    // DC predictor of the intra estimate (source neighbours): evaluated by the second half-warp in the slot the first one spends on the centre
+    uint32_t dcw;
+    {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) sum = dp4a_us(sm.nb_top[k], 0x01010101u, dp4a_us(sm.nb_left[k], 0x01010101u, sum));
+        const int dc = top && left ? (sum + 16) >> 5 : (top || left) ? (sum + 8) >> 4 : 128;
+        dcw = 0x01010101u * (uint32_t)dc;
+    }
+    const uint32_t *pw = sm.plane[0];                   // word view of the planes G, b, h, j (PLW words each)
+    constexpr int PLW = PL_ROWS * PL_STRIDE / 4, RW = PL_STRIDE / 4;
+    const int ob = by * PL_STRIDE + o1 + bx + 3;         // byte offset inside a plane of sample (bx - 1, by - 1) of the best full-pel block
+    // P_8x8: every candidate's SATD is also summed per 8x8 quadrant (the first two steps of the 16-lane reduction) and each quadrant keeps its
+    // own best candidate: key = (SATD8x8 + lambda * bits) << 5 | sequence number (0..8 half-pel ring, 9..16 quarter-pel ring).
+    uint32_t bk = 0xffffffffu, bq = 0xffffffffu;
+    // one candidate per half-warp: SATD of the lane's block, quadrant and macroblock sums, rate term, the two running minima
+    auto slot = [&](const uint32_t P[4], int idx, int ox, int oy, int seq, bool live) -> int {
+        int sq = satd_rows(P, Ts);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2);       // this lane's 8x8 quadrant
+        int sat = sq + __shfl_xor_sync(0xffffffffu, sq, 4); sat += __shfl_xor_sync(0xffffffffu, sat, 8);
+        const int bits = __shfl_sync(0xffffffffu, mvb, ox + 3) + __shfl_sync(0xffffffffu, mvb, oy + 11);
+        if (live) {
+            bk = min(bk, ((uint32_t)(sat + lambda * bits) << 4) | (uint32_t)idx);
+            bq = min(bq, ((uint32_t)(sq + lambda * bits) << 5) | (uint32_t)seq);
+        }
+        return sat;
+    };
+    // ---- half-pel ring + centre: the nine candidates are single planes at integer offsets (-1 | 0): i = 1 j(-1,-1), 2 h(0,-1), 3 j(0,-1),
+    // 4 b(-1,0), 5 b(0,0), 6 j(-1,0), 7 h(0,0), 8 j(0,0), 0 G(0,0). A lane fetches the 5 x 5 samples around its block once per plane
+    // (rows by-1 .. by+3; A = the four bytes from x-1, B = from x) and takes every candidate of that plane from those registers.
+    int ie_dc;
+    {
+        uint32_t A[5], B[5];
+        {   // region 1: b for the first half-warp, j for the second
+            const uint32_t *w = pw + (hw ? 3 : 1) * PLW + (ob >> 2); const int sa = (ob & 3) * 8;
+#pragma unroll
+            for (int r = 0; r < 5; r++) { const uint32_t lo = w[r * RW], hi = w[r * RW + 1]; A[r] = __funnelshift_r(lo, hi, sa); B[r] = __funnelshift_rc(lo, hi, sa + 8); }
+        }
+        {   // b(-1,0) [4] | j(-1,-1) [1]
+            const uint32_t P[4] = { hw ? A[0] : A[1], hw ? A[1] : A[2], hw ? A[2] : A[3], hw ? A[3] : A[4] };
+            slot(P, hw ? 1 : 4, -2, hw ? -2 : 0, hw ? 1 : 4, true);
+        }
+        {   // b(0,0) [5] | j(-1,0) [6]
+            const uint32_t P[4] = { hw ? A[1] : B[1], hw ? A[2] : B[2], hw ? A[3] : B[3], hw ? A[4] : B[4] };
+            slot(P, hw ? 6 : 5, hw ? -2 : 2, hw ? 2 : 0, hw ? 6 : 5, true);
+        }
+        {   // region 2: h for the first half-warp, j again for the second; only the bytes from x
+            const uint32_t *w = pw + (hw ? 3 : 2) * PLW + ((ob + 1) >> 2); const int sb = ((ob + 1) & 3) * 8;
+#pragma unroll
+            for (int r = 0; r < 5; r++) B[r] = __funnelshift_r(w[r * RW], w[r * RW + 1], sb);
+        }
+        {   // h(0,-1) [2] | j(0,-1) [3]
+            const uint32_t P[4] = { B[0], B[1], B[2], B[3] };
+            slot(P, hw ? 3 : 2, hw ? 2 : 0, -2, hw ? 3 : 2, true);
+        }
+        {   // h(0,0) [7] | j(0,0) [8]
+            const uint32_t P[4] = { B[1], B[2], B[3], B[4] };
+            slot(P, hw ? 8 : 7, hw ? 2 : 0, 2, hw ? 8 : 7, true);
+        }
+        {   // G(0,0) [0] | the DC predictor of the intra estimate
+            const uint32_t *w = pw + ((ob + 1 + PL_STRIDE) >> 2); const int sb = ((ob + 1) & 3) * 8;
+            uint32_t P[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) P[r] = hw ? dcw : __funnelshift_r(w[r * RW], w[r * RW + 1], sb);
+            const int sat = slot(P, 0, 0, 0, 0, hw == 0);
+            ie_dc = __shfl_sync(0xffffffffu, sat, 16);
+        }
+    }
+    bk = min(bk, __shfl_xor_sync(0xffffffffu, bk, 16)); bq = min(bq, __shfl_xor_sync(0xffffffffu, bq, 16));
     // candidate i: 0 centre, then (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1); packed 2-bit (offset + 1) tables
     const uint32_t OXP = 0x24891u, OYP = 0x2A501u;
-    // P_8x8: every candidate's SATD is also summed per 8x8 quadrant (the first two steps of the 16-lane reduction) and each
-    // quadrant keeps its own best candidate: key = (SATD8x8 + lambda * bits) << 5 | sequence number (0..8 half-pel ring,
-    // 9..16 quarter-pel ring). All lanes of a quadrant hold the same bq.
-    uint32_t bq = 0xffffffffu;
-    int hx = 0, hy = 0;                                 // half-pel winner = centre of the quarter-pel ring
+    const int hx = 2 * ((int)((OXP >> (2 * (bk & 15))) & 3) - 1), hy = 2 * ((int)((OYP >> (2 * (bk & 15))) & 3) - 1);   // half-pel winner = centre of the quarter-pel ring
+    // ---- quarter-pel ring: every candidate is the rounded average of two of the planes' samples (8.4.2.2.1, c_qpel_off)
+    bk &= ~15u;                                         // the centre competes as candidate 0 of this ring
 #pragma unroll 1
-    for (int step = 2; step >= 1; step--) {
-        uint32_t bk = step == 1 ? (centre_key & ~15u) : 0xffffffffu;
-        const int npass = step == 2 ? 5 : 4;
-#pragma unroll 1
-        for (int pass = 0; pass < npass; pass++) {
-            const int i = 2 * pass + hw + (step == 1 ? 1 : 0);      // step 2: 0..8 (+ one idle slot); step 1: 1..8 (centre known)
-            const int ci = i <= 8 ? i : 0;
-            const int ox = qx + step * ((int)((OXP >> (2 * ci)) & 3) - 1), oy = qy + step * ((int)((OYP >> (2 * ci)) & 3) - 1);
-            uint32_t P[4]; pred_rows_qpel(sm, o1, bx, by, ox, oy, rx, P);
-            int sq = satd_rows(P, Ts);
-            sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2);       // this lane's 8x8 quadrant
-            int sat = sq + __shfl_xor_sync(0xffffffffu, sq, 4); sat += __shfl_xor_sync(0xffffffffu, sat, 8);
-            uint32_t key = 0xffffffffu, kq = 0xffffffffu;
-            const int bits = __shfl_sync(0xffffffffu, mvb, ox + 3) + __shfl_sync(0xffffffffu, mvb, oy + 11);
-            if (i <= 8) {
-                key = ((uint32_t)(sat + lambda * bits) << 4) | (uint32_t)i;
-                kq = ((uint32_t)(sq + lambda * bits) << 5) | (uint32_t)(step == 2 ? i : 8 + i);
-            }
-            key = min(key, __shfl_xor_sync(0xffffffffu, key, 16));
-            kq = min(kq, __shfl_xor_sync(0xffffffffu, kq, 16));
-            bk = min(bk, key); bq = min(bq, kq);
-        }
-        const int ci = bk & 15;
-        qx += step * ((int)((OXP >> (2 * ci)) & 3) - 1); qy += step * ((int)((OYP >> (2 * ci)) & 3) - 1); centre_key = bk;
-        if (step == 2) { hx = qx; hy = qy; }
+    for (int pass = 0; pass < 4; pass++) {
+        const int i = 2 * pass + hw + 1;
+        const int ox = hx + (int)((OXP >> (2 * i)) & 3) - 1, oy = hy + (int)((OYP >> (2 * i)) & 3) - 1;
+        const uint32_t t = c_qpel_off[(oy & 3) * 4 + (ox & 3)];
+        const int common = (by + (oy >> 2) + 1) * PL_STRIDE + o1 + bx + (ox >> 2) + 4;
+        const int oa = common + (int)(t & 0xffffu), obb = common + (int)(t >> 16);
+        const uint32_t *wa = pw + (oa >> 2), *wb = pw + (obb >> 2); const int sa = (oa & 3) * 8, sb = (obb & 3) * 8;
+        uint32_t P[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) P[r] = avg4(__funnelshift_r(wa[r * RW], wa[r * RW + 1], sa), __funnelshift_r(wb[r * RW], wb[r * RW + 1], sb));
+        slot(P, i, ox, oy, 8 + i, true);
     }
-    const int cost16 = (int)(centre_key >> 4);
+    bk = min(bk, __shfl_xor_sync(0xffffffffu, bk, 16)); bq = min(bq, __shfl_xor_sync(0xffffffffu, bq, 16));
+    const int qx = hx + (int)((OXP >> (2 * (bk & 15))) & 3) - 1, qy = hy + (int)((OYP >> (2 * (bk & 15))) & 3) - 1;     // offset from 4*(fx,fy), quarter-pel units
+    const int cost16 = (int)(bk >> 4);
     // this lane's quadrant vector (offset from the full-pel winner) and the P_8x8 cost
     int lx, ly;
     {
@@ -448,25 +502,19 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     if (!use8) { lx = qx; ly = qy; }
     const int inter_cost = use8 ? cost8 : cost16;
 
-    // intra estimate from source neighbours (staged above): V, H, DC 16x16 by SATD
+    // intra estimate from source neighbours (staged above): V, H, DC 16x16 by SATD (the DC predictor was evaluated beside the centre candidate)
     int ie = 1 << 30;
     {
         const uint8_t *nl = reinterpret_cast<const uint8_t *>(sm.nb_left);
         uint32_t P[4];
 #pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = hw == 0 ? sm.nb_top[bx >> 2] : 0x01010101u * nl[by + (y ^ rx)];
+        for (int y = 0; y < 4; y++) P[y] = hw == 0 ? sm.nb_top[bx >> 2] : 0x01010101u * nl[by + y];
         const int sat = half_reduce16(satd_rows(P, Ts));
         const int other = __shfl_xor_sync(0xffffffffu, sat, 16);
         const int sv = hw == 0 ? sat : other, sh = hw == 0 ? other : sat;
         if (top) ie = min(ie, sv);
         if (left) ie = min(ie, sh);
-        int sum = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) sum = dp4a_us(sm.nb_top[k], 0x01010101u, dp4a_us(sm.nb_left[k], 0x01010101u, sum));
-        const int dc = top && left ? (sum + 16) >> 5 : (top || left) ? (sum + 8) >> 4 : 128;
-#pragma unroll
-        for (int y = 0; y < 4; y++) P[y] = 0x01010101u * (uint32_t)dc;
-        ie = min(ie, half_reduce16(satd_rows(P, Ts)));
+        ie = min(ie, ie_dc);
     }
     const bool intra = ie + lambda * 16 < inter_cost;
 
