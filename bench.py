@@ -210,62 +210,70 @@ def run_b200(args):
     el, dev_ms, launches, out_bytes = timed(groups, dpool, 1, args.steps, args.warmup)
     clocks = sampler.summary()
     value = world * S * args.steps / el
-    # ---- end to end through the reference's boundary (tools/e2e_plugin.cpp): dlopen libVideoCodec.so, CreateVideoEncoder / InitEncoder /
-    # EncodeOneFrame, one C++ caller thread per session, frames in pageable malloc memory; H2D and the bitstream read-back are inside
-    for g_ in groups:
-        g_[1].close()
-    for x in sess:
-        x.close()
-    sess, groups = [], []
-    E = e2e_lib()
-    flat = np.ascontiguousarray(np.stack([np.asarray(f, np.uint8).ravel() for f in pool]))
-    prof_name = {0: b"baseline", 1: b"main", 2: b"high"}[PROFILE]
-    os.environ["PROP_persist_vmi_b200_encode_slices"] = str(SLICES)
-    os.environ["PROP_persist_vmi_b200_encode_search_range"] = str(SR)
-    if CQP >= 0:
-        os.environ["PROP_persist_vmi_b200_encode_const_qp"] = str(CQP)
-    h = E.e2e_open(os.path.join(ROOT, "media_b200", "host", "libVideoCodec.so").encode(), S, W, H, FPS, BITRATE, GOP, prof_name,
-                   b"rgba" if FMT == 2 else b"i420", dev, flat.ctypes.data, len(pool), fb)
-    err = E.e2e_last_error(h).decode()
-    assert not err, f"e2e plugin driver: {err}"
-    res = E2EResult()
-    assert E.e2e_run(h, 0, max(3, args.warmup), 0, C.byref(res)) == 0 and res.errors == 0, "e2e warm-up failed"
-    sb0, sf0, sb1, sf1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
-    barrier()
-    L.b200enc_scheduler_stats(dev, C.byref(sb0), C.byref(sf0))
-    t0 = time.perf_counter()
-    assert E.e2e_run(h, max(3, args.warmup), args.steps, 0, C.byref(res)) == 0
-    barrier()
-    el_e = time.perf_counter() - t0
-    L.b200enc_scheduler_stats(dev, C.byref(sb1), C.byref(sf1))
-    e2e_avg_batch = round((sf1.value - sf0.value) / max(1, sb1.value - sb0.value), 1)
-    e2e_frames, out_bytes_e, e2e_errors = res.frames, res.bytes, res.errors
-    e2e_lat = {"p50": round(res.lat_p50_ms, 2), "p99": round(res.lat_p99_ms, 2), "max": round(res.lat_max_ms, 2)}
-    if use_dist:
-        t = torch.tensor([el_e], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); el_e = t[0].item()
-        t = torch.tensor([float(e2e_frames), float(out_bytes_e), float(e2e_errors)], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e_frames, out_bytes_e, e2e_errors = int(t[0].item()), int(t[1].item()), int(t[2].item())
+    e2e = el_e = out_bytes_e = e2e_errors = 0; e2e_lat, e2e_avg_batch, realtime = {}, 0, None
+    if args.no_e2e:
+        for g_ in groups:
+            g_[1].close()
+        for x in sess:
+            x.close()
+        sess, groups = [], []
     else:
-        e2e_frames, out_bytes_e = int(e2e_frames), int(out_bytes_e)
-    e2e = e2e_frames / el_e
-    # ---- the same sessions paced at FPS through the same boundary (BASELINE config 5 in one point): every frame must be back before
-    # the next capture time. args.realtime_seconds = 0 skips it.
-    realtime = None
-    if args.realtime_seconds > 0 and S > 1:
+        # ---- end to end through the reference's boundary (tools/e2e_plugin.cpp): dlopen libVideoCodec.so, CreateVideoEncoder / InitEncoder /
+        # EncodeOneFrame, one C++ caller thread per session, frames in pageable malloc memory; H2D and the bitstream read-back are inside
+        for g_ in groups:
+            g_[1].close()
+        for x in sess:
+            x.close()
+        sess, groups = [], []
+        E = e2e_lib()
+        flat = np.ascontiguousarray(np.stack([np.asarray(f, np.uint8).ravel() for f in pool]))
+        prof_name = {0: b"baseline", 1: b"main", 2: b"high"}[PROFILE]
+        os.environ["PROP_persist_vmi_b200_encode_slices"] = str(SLICES)
+        os.environ["PROP_persist_vmi_b200_encode_search_range"] = str(SR)
+        if CQP >= 0:
+            os.environ["PROP_persist_vmi_b200_encode_const_qp"] = str(CQP)
+        h = E.e2e_open(os.path.join(ROOT, "media_b200", "host", "libVideoCodec.so").encode(), S, W, H, FPS, BITRATE, GOP, prof_name,
+                       b"rgba" if FMT == 2 else b"i420", dev, flat.ctypes.data, len(pool), fb)
+        err = E.e2e_last_error(h).decode()
+        assert not err, f"e2e plugin driver: {err}"
+        res = E2EResult()
+        assert E.e2e_run(h, 0, max(3, args.warmup), 0, C.byref(res)) == 0 and res.errors == 0, "e2e warm-up failed"
+        sb0, sf0, sb1, sf1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         barrier()
-        rsteps = int(args.realtime_seconds * FPS)
-        assert E.e2e_run(h, max(3, args.warmup) + args.steps, rsteps, 1, C.byref(res)) == 0
+        L.b200enc_scheduler_stats(dev, C.byref(sb0), C.byref(sf0))
+        t0 = time.perf_counter()
+        assert E.e2e_run(h, max(3, args.warmup), args.steps, 0, C.byref(res)) == 0
         barrier()
-        rt = [float(res.late), float(res.errors), res.lat_p99_ms, res.lat_max_ms, res.lat_p50_ms]
+        el_e = time.perf_counter() - t0
+        L.b200enc_scheduler_stats(dev, C.byref(sb1), C.byref(sf1))
+        e2e_avg_batch = round((sf1.value - sf0.value) / max(1, sb1.value - sb0.value), 1)
+        e2e_frames, out_bytes_e, e2e_errors = res.frames, res.bytes, res.errors
+        e2e_lat = {"p50": round(res.lat_p50_ms, 2), "p99": round(res.lat_p99_ms, 2), "max": round(res.lat_max_ms, 2)}
         if use_dist:
-            t = torch.tensor(rt[:2], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            u = torch.tensor(rt[2:], dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.MAX)
-            rt = t.tolist() + u.tolist()
-        realtime = {"sessions_per_gpu": S, "sessions": S * world, "fps": FPS, "seconds": args.realtime_seconds, "frames": S * world * rsteps,
-                    "late_frames": int(rt[0]), "errors": int(rt[1]), "latency_ms": {"p50": round(rt[4], 2), "p99": round(rt[2], 2), "max": round(rt[3], 2)},
-                    "realtime": bool(rt[0] == 0 and rt[1] == 0 and rt[2] <= 1000.0 / FPS),
-                    "via": "VideoEncoder::EncodeOneFrame, one paced caller thread per session (staggered phases), pageable input"}
-    E.e2e_close(h)
+            t = torch.tensor([el_e], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); el_e = t[0].item()
+            t = torch.tensor([float(e2e_frames), float(out_bytes_e), float(e2e_errors)], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            e2e_frames, out_bytes_e, e2e_errors = int(t[0].item()), int(t[1].item()), int(t[2].item())
+        else:
+            e2e_frames, out_bytes_e = int(e2e_frames), int(out_bytes_e)
+        e2e = e2e_frames / el_e
+        # ---- the same sessions paced at FPS through the same boundary (BASELINE config 5 in one point): every frame must be back before
+        # the next capture time. args.realtime_seconds = 0 skips it.
+        if args.realtime_seconds > 0 and S > 1:
+            barrier()
+            rsteps = int(args.realtime_seconds * FPS)
+            assert E.e2e_run(h, max(3, args.warmup) + args.steps, rsteps, 1, C.byref(res)) == 0
+            barrier()
+            rt = [float(res.late), float(res.errors), res.lat_p99_ms, res.lat_max_ms, res.lat_p50_ms]
+            if use_dist:
+                t = torch.tensor(rt[:2], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                u = torch.tensor(rt[2:], dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.MAX)
+                rt = t.tolist() + u.tolist()
+            realtime = {"sessions_per_gpu": S, "sessions": S * world, "fps": FPS, "seconds": args.realtime_seconds, "frames": S * world * rsteps,
+                        "late_frames": int(rt[0]), "errors": int(rt[1]), "latency_ms": {"p50": round(rt[4], 2), "p99": round(rt[2], 2), "max": round(rt[3], 2)},
+                        "realtime": bool(rt[0] == 0 and rt[1] == 0 and rt[2] <= 1000.0 / FPS),
+                        "via": "VideoEncoder::EncodeOneFrame, one paced caller thread per session (staggered phases), pageable input"}
+        E.e2e_close(h)
+
     # per-kernel shares of one P step over ALL sessions of the GPU in a single batch (CUDA events around each launch on the
     # batch's stream); fresh sessions, so two untimed frames first (IDR + one P)
     sess = [new_session(enc, dev) for _ in range(S)]
@@ -569,6 +577,7 @@ def main():
     ap.add_argument("--slices", type=int, default=None, help="override the workload's slice count (0 = the engine's automatic count)")
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end and real-time legs (the line then carries no e2e)")
     ap.add_argument("--realtime-seconds", type=float, default=2.0, help="length of the paced real-time leg through the plugin boundary (0 = skip)")
     args = ap.parse_args()
     apply_workload(args)

@@ -335,7 +335,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
         d.qp = qps[i]; d.is_idr = idr; d.frame_num = idr ? 0 : s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
         d.scene_change = s->cfg.scene_change && !idr && s->frames_since_idr >= SC_MIN_DISTANCE;
-        d.t8x8 = s->cfg.profile == 2;
+        d.t8x8 = s->cfg.profile == 2; d.dump = s->cfg.debug & 1;
         d.rbsp_words_per_slice = s->rbsp_words_per_slice; d.out_cap = s->out_cap;
     }
     CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);

@@ -88,6 +88,7 @@ struct Sess {
     int *row_prog_intra, *row_prog_dbk; // wavefront progress counters, one per MB row
     int qp, is_idr, frame_num, idr_pic_id, input_format;
     int scene_change;             // 1: k_scene_change may turn this P picture into an IDR (then is_idr / frame_num are rewritten on the device)
+    int dump;                     // 1: stage dumps are read back (debug bit 0): cbp-0 macroblocks also store their all-zero level records
     int t8x8;                     // 1: PPS transform_8x8_mode_flag (High profile): inter MBs may take the 8x8 transform (k_inter_t8)
     uint32_t rbsp_words_per_slice, out_cap;
 };

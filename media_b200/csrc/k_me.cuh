@@ -148,8 +148,8 @@ struct __align__(128) FineSmem {
     uint32_t pad_[20];
 };
 static_assert(sizeof(FineSmem) % 128 == 0 && offsetof(FineSmem, src) % 128 == 0 && offsetof(FineSmem, win) % 128 == 0, "TMA destinations must be 128-byte aligned");
-// the four byte-shifted copies of the 20x20 window live in the plane area until the planes are fetched
-#define WIN0_WORDS 127          /* >= 20 * 5 + 2; 127 makes the 25 candidate reads of a row hit 25 different banks */
+// the five byte-shifted copies of the 20-row window live in the plane area until the planes are fetched
+#define WIN_COPY 336            /* bytes between the byte-shifted copies of the full-pel window: 20 rows x 16 bytes + 16 */
 #define P8X8_BIAS_BITS 8        /* extra header bits of P_8x8 over P_L0_16x16: mb_type ue(3) vs ue(0), four sub_mb_type ue(0) */
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -333,34 +333,37 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
             const size_t co_ = (size_t)(my * 8 + crow) * cw + mx * 8 + chalf * 4;
             *reinterpret_cast<uint2 *>(s.rec[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8) = zref;
             *reinterpret_cast<uint32_t *>(s.rec[1 + cpl] + co_) = *reinterpret_cast<const uint32_t *>(s.ref[1 + cpl] + co_);
-            uint4 *cz = reinterpret_cast<uint4 *>(s.coef + mb);
-            cz[lane] = make_uint4(0, 0, 0, 0);
-            if (lane < 51 - 32) cz[32 + lane] = make_uint4(0, 0, 0, 0);
+            if (s.dump) {      // nobody reads the levels of a cbp-0 macroblock except the stage dumps of the parity tests
+                uint4 *cz = reinterpret_cast<uint4 *>(s.coef + mb);
+                cz[lane] = make_uint4(0, 0, 0, 0);
+                if (lane < 51 - 32) cz[32 + lane] = make_uint4(0, 0, 0, 0);
+            }
             if (lane < 12) reinterpret_cast<uint32_t *>(s.mbi + mb)[lane] = 0u;      // P_L0_16x16, cbp 0, zero vectors, nnz 0
             if (lane == 0) { s.me0[mb * 2] = 0; s.me0[mb * 2 + 1] = 0; s.inter_cost[mb] = 0; }
             return;
         }
     }
-    uint32_t *win0 = sm.plane[0];                       // four byte-shifted copies of the 20x20 window: aligned candidate reads
+    // Five byte-shifted copies of the 20-row window, one per candidate column (copy k = the window from column k: 16 bytes per row), so a
+    // candidate row is ONE aligned 128-bit load against one 128-bit load of the source row. Copies are WIN_COPY bytes apart: the quarter-warps
+    // of both the 128-bit stores here and the 25 candidate loads below then touch distinct 16-byte bank groups (k * 336 mod 128 = 0, 80, 32, 112, 64).
+    uint8_t *cpb = reinterpret_cast<uint8_t *>(sm.plane[0]);
     for (int i = lane; i < 100; i += 32) {
-        const int r = i / 5, j = i - r * 5;
-        const uint32_t *row = sm.win + r * (PL_STRIDE / 4);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int off = o0 + 4 * j + k;
-            win0[k * WIN0_WORDS + i] = __funnelshift_r(row[off >> 2], row[(off >> 2) + 1], (off & 3) * 8);
-        }
+        const int r = i / 5, k = i - r * 5, off = o0 + k, sh = (off & 3) * 8;
+        const uint32_t *row = sm.win + r * (PL_STRIDE / 4) + (off >> 2);
+        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3], w4 = row[4];
+        *reinterpret_cast<uint4 *>(cpb + k * WIN_COPY + r * 16) =
+            make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
     }
     __syncwarp();
     uint32_t best = 0xffffffffu;
     if (lane < 25) {
         const int dy = lane / 5, dx = lane - dy * 5;
-        const uint32_t *p = win0 + (dx & 3) * WIN0_WORDS + dy * 5 + (dx >> 2);
+        const uint4 *p = reinterpret_cast<const uint4 *>(cpb + dx * WIN_COPY + dy * 16), *sp = reinterpret_cast<const uint4 *>(sm.src);
         uint32_t sad = 0;
 #pragma unroll 4
         for (int r = 0; r < 16; r++) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) sad = sad4(sm.src[r * 4 + k], p[r * 5 + k], sad);
+            const uint4 a = sp[r], w = p[r];
+            sad = sad4(a.x, w.x, sad); sad = sad4(a.y, w.y, sad); sad = sad4(a.z, w.z, sad); sad = sad4(a.w, w.w, sad);
         }
         best = ((sad + lambda * (se_len(4 * (cx + dx - 2) - ppx) + se_len(4 * (cy + dy - 2) - ppy))) << 5) | (uint32_t)lane;
     } else if (lane == 25) best = ((zsad + lambda * (se_len(-ppx) + se_len(-ppy))) << 5) | 25u;
@@ -528,57 +531,106 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     }
 
     // ---- phase B: code the inter macroblock ----
-    // lanes 0-15 own the luma 4x4 blocks, lanes 16-23 the chroma blocks; only the prediction differs between them,
-    // the transform / quantiser / reconstruction below is ONE instruction stream for all 24 lanes.
+    // lanes 0-15 own the luma 4x4 blocks, lanes 16-23 the chroma blocks. Prediction and source stay packed (four samples per word) through the
+    // forward transform (IDP.4A against the transform's rows) and the reconstruction (16x2 adds and clamps); only the coefficients are scalars.
     MbCoef *co = s.coef + mb;
     const bool is_luma = lane < 16, active = lane < 24;
     const int pl = (lane >> 2) & 1, cb = lane & 3;                 // chroma plane / block of lanes 16-23
     const int cw = wc / 2;
     const int cx0 = mx * 8 + (cb & 1) * 4, cy0 = my * 8 + (cb >> 1) * 4;
-    int nnz = 0; bool dc_nz = false;
-    int p[16], c[16];
-    // the vector of this lane's 8x8 partition: luma lanes own it, chroma block cb lies under partition cb
-    const int plx = __shfl_sync(0xffffffffu, lx, is_luma ? lane : 4 * cb), ply = __shfl_sync(0xffffffffu, ly, is_luma ? lane : 4 * cb);
+    // the vector of this lane's 8x8 partition (lanes 16-31 mirror 0-15)
+    const int plx = __shfl_sync(0xffffffffu, lx, lane & 15), ply = __shfl_sync(0xffffffffu, ly, lane & 15);
     const int mvx = 4 * fx + plx, mvy = 4 * fy + ply;
-    if (is_luma) {
-        uint32_t P[4]; pred_rows_qpel(sm, o1, bx, by, plx, ply, 0, P);
+    uint32_t P[4], S[4];
+    pred_rows_qpel(sm, o1, bx, by, plx, ply, 0, P);
+    {
+        // chroma motion compensation, 1/8-pel bilinear (8.4.2.2.2), from the edge-extended reference chroma planes, by all 32 lanes: lane =
+        // (plane, row 0..7, half): four samples = two IDP.4A each against the packed weights; chroma block cb lies under luma partition cb
+        const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1, cbk = (crow >> 2) * 2 + chalf;
+        const int cvx = 4 * fx + __shfl_sync(0xffffffffu, lx, 4 * cbk), cvy = 4 * fy + __shfl_sync(0xffffffffu, ly, 4 * cbk);
+        const int fxc = cvx & 7, fyc = cvy & 7;
+        const uint8_t *rp = s.rpc[cpl] + (ptrdiff_t)(my * 8 + crow + (cvy >> 3)) * g.cs + mx * 8 + chalf * 4 + (cvx >> 3);
+        const uint32_t *q0 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(rp) & ~(uintptr_t)3), *q1 = q0 + (g.cs >> 2);
+        const int sh = (int)(reinterpret_cast<uintptr_t>(rp) & 3) * 8;
+        const uint32_t a_lo = __ldg(q0), a_hi = __ldg(q0 + 1), b_lo = __ldg(q1), b_hi = __ldg(q1 + 1);
+        const uint32_t R0 = __funnelshift_r(a_lo, a_hi, sh), S0 = __funnelshift_rc(a_lo, a_hi, sh + 8);     // samples x .. x+3 and x+1 .. x+4 of the upper row
+        const uint32_t R1 = __funnelshift_r(b_lo, b_hi, sh), S1 = __funnelshift_rc(b_lo, b_hi, sh + 8);     // ... of the lower row
+        const uint32_t WA = (uint32_t)((8 - fxc) * (8 - fyc)) | ((uint32_t)(fxc * (8 - fyc)) << 8), WB = (uint32_t)((8 - fxc) * fyc) | ((uint32_t)(fxc * fyc) << 8);
+        const uint32_t TA0 = __byte_perm(R0, S0, 0x5140), TA1 = __byte_perm(R0, S0, 0x7362), TB0 = __byte_perm(R1, S1, 0x5140), TB1 = __byte_perm(R1, S1, 0x7362);
+        const int p0 = dp4a_us(TB0, WB, dp4a_us(TA0, WA, 32)) >> 6, p1 = dp4a_us(TB0, WB << 16, dp4a_us(TA0, WA << 16, 32)) >> 6;
+        const int p2 = dp4a_us(TB1, WB, dp4a_us(TA1, WA, 32)) >> 6, p3 = dp4a_us(TB1, WB << 16, dp4a_us(TA1, WA << 16, 32)) >> 6;
+        const uint32_t cword = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16) | ((uint32_t)p3 << 24);
+        // the chroma block lanes collect their four rows; source rows: luma from the staged macroblock, chroma from the source planes
+        const int srcl = pl * 16 + (cb >> 1) * 8 + (cb & 1);
+        const uint8_t *sp_c = s.src[1 + pl] + (size_t)cy0 * cw + cx0;
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
-#pragma unroll
-            for (int x = 0; x < 4; x++) { p[y * 4 + x] = (P[y] >> (8 * x)) & 255; c[y * 4 + x] = (int)((w >> (8 * x)) & 255) - p[y * 4 + x]; }
-        }
-    } else {
-        // chroma motion compensation, 1/8-pel bilinear (8.4.2.2.2), from the edge-extended reference chroma planes
-        const int pc = active ? pl : 0;
-        const int xi = cx0 + (mvx >> 3), yi = cy0 + (mvy >> 3), fxc = mvx & 7, fyc = mvy & 7;
-        const uint8_t *rp = s.rpc[pc] + (ptrdiff_t)yi * g.cs + xi;
-        int smp[25];
-#pragma unroll
-        for (int y = 0; y < 5; y++)
-#pragma unroll
-            for (int x = 0; x < 5; x++) smp[y * 5 + x] = __ldg(rp + y * g.cs + x);
-        const uint8_t *sp_c = s.src[1 + pc] + (size_t)cy0 * cw + cx0;
-        const int w00 = (8 - fxc) * (8 - fyc), w01 = fxc * (8 - fyc), w10 = (8 - fxc) * fyc, w11 = fxc * fyc;
-#pragma unroll
-        for (int y = 0; y < 4; y++) {
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(sp_c + (size_t)y * cw);
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                p[y * 4 + x] = (w00 * smp[y * 5 + x] + w01 * smp[y * 5 + x + 1] + w10 * smp[y * 5 + 5 + x] + w11 * smp[y * 5 + 6 + x] + 32) >> 6;
-                c[y * 4 + x] = (int)((w >> (8 * x)) & 255) - p[y * 4 + x];
-            }
+            const uint32_t gw = __shfl_sync(0xffffffffu, cword, srcl + 2 * y);
+            if (!is_luma) { P[y] = gw; S[y] = *reinterpret_cast<const uint32_t *>(sp_c + (size_t)y * cw); }
+            else S[y] = sm.src[(by + y) * 4 + (bx >> 2)];
         }
     }
-    fdct4x4(c);
+    // forward core transform of (S - P): rows as IDP.4A of the packed samples against the transform rows {1,1,1,1}, {2,1,-1,-2}, {1,-1,-1,1}, {1,-2,2,-1}
+    // (the prediction against their negation), then the column butterflies
+    int c[16];
+    {
+        const uint32_t BK[4] = { 0x01010101u, 0xFEFF0102u, 0x01FFFF01u, 0xFF02FE01u }, NK[4] = { 0xFFFFFFFFu, 0x0201FFFEu, 0xFF0101FFu, 0x01FE02FFu };
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) c[y * 4 + k] = dp4a_us(S[y], BK[k], dp4a_us(P[y], NK[k], 0));
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const int a0 = c[x] + c[12 + x], a1 = c[4 + x] + c[8 + x], a2 = c[4 + x] - c[8 + x], a3 = c[x] - c[12 + x];
+            c[x] = a0 + a1; c[4 + x] = 2 * a3 + a2; c[8 + x] = a0 - a1; c[12 + x] = a3 - 2 * a2;
+        }
+    }
     const QParam q = make_qparam(is_luma ? qp : (int)c_chroma_qp[qp]);
+    // 2x2 Hadamard of the four DC terms of this lane's chroma plane (lanes 16+4pl .. 19+4pl)
+    int hd[4];
+    {
+        int dcs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) dcs[k] = __shfl_sync(0xffffffffu, c[0], 16 + pl * 4 + k);
+        hd[0] = dcs[0] + dcs[1] + dcs[2] + dcs[3]; hd[1] = dcs[0] - dcs[1] + dcs[2] - dcs[3]; hd[2] = dcs[0] + dcs[1] - dcs[2] - dcs[3]; hd[3] = dcs[0] - dcs[1] - dcs[2] + dcs[3];
+    }
+    // Does anything of this macroblock quantise to a nonzero level? The quantiser is monotone in |coefficient|, so the largest magnitude per
+    // multiplier class decides (position 0 of a chroma block is coded through the DC Hadamard). Most macroblocks of a P picture at the
+    // session bitrates answer no: their reconstruction is the prediction and no level leaves the warp.
+    bool nzl;
+    {
+        const int m0 = max(max(is_luma ? abs(c[0]) : 0, abs(c[2])), max(abs(c[8]), abs(c[10])));
+        const int m1 = max(max(abs(c[5]), abs(c[7])), max(abs(c[13]), abs(c[15])));
+        const int m2 = max(max(max(abs(c[1]), abs(c[3])), max(abs(c[4]), abs(c[6]))), max(max(abs(c[9]), abs(c[11])), max(abs(c[12]), abs(c[14]))));
+        unsigned t = (((unsigned)m0 * (unsigned)q.mf[0] + (unsigned)q.f_inter) | ((unsigned)m1 * (unsigned)q.mf[1] + (unsigned)q.f_inter) |
+                      ((unsigned)m2 * (unsigned)q.mf[2] + (unsigned)q.f_inter)) >> q.qbits;
+        const int md = max(max(abs(hd[0]), abs(hd[1])), max(abs(hd[2]), abs(hd[3])));
+        if (!is_luma) t |= ((unsigned)md * (unsigned)q.mf[0] + 2u * (unsigned)q.f_inter) >> (q.qbits + 1);
+        nzl = t != 0u;
+    }
+    uint8_t *recp = is_luma ? s.rec[0] + (size_t)(y0 + by) * wc + x0 + bx : s.rec[1 + pl] + (size_t)cy0 * cw + cx0;
+    const int rst = is_luma ? wc : cw;
+    const uint32_t mvw = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
+    const uint32_t mvq = __shfl_sync(0xffffffffu, mvw, lane == 0 ? 0 : 4 * ((lane - 1) & 3));
+    if (__ballot_sync(0xffffffffu, active && nzl) == 0u) {
+        if (active) {
+#pragma unroll
+            for (int y = 0; y < 4; y++) *reinterpret_cast<uint32_t *>(recp + (size_t)y * rst) = P[y];
+        }
+        // nobody reads the levels of a macroblock whose cbp is 0 (CAVLC / CABAC / the 8x8 pass all go by cbp); the stage dumps of the parity tests do
+        if (s.dump) { uint4 *cz = reinterpret_cast<uint4 *>(co); cz[lane] = make_uint4(0, 0, 0, 0); if (lane < 51 - 32) cz[32 + lane] = make_uint4(0, 0, 0, 0); }
+        // word 0: type, cbp 0; word 1: vector of partition 0; words 2-5: the four partition vectors; words 6-11: nnz 0
+        uint32_t *miw = reinterpret_cast<uint32_t *>(mi);
+        if (lane == 0) { miw[0] = use8 ? (uint32_t)MB_P8x8 : (uint32_t)MB_P16x16; miw[1] = mvq; }
+        else if (lane < 5) miw[1 + lane] = mvq;
+        else if (lane < 11) miw[1 + lane] = 0u;
+        return;
+    }
+    int nnz = 0; bool dc_nz = false;
     int dcC = 0;
     if (!is_luma && active) {
-        // 2x2 DC of this plane (lanes 16+4pl .. 19+4pl): Hadamard, quantise, and the normative inverse (8.5.11)
-        int dcs[4], lv[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) dcs[k] = __shfl_sync(0x00ff0000u, c[0], 16 + pl * 4 + k);
-        const int hd[4] = { dcs[0] + dcs[1] + dcs[2] + dcs[3], dcs[0] - dcs[1] + dcs[2] - dcs[3], dcs[0] + dcs[1] - dcs[2] - dcs[3], dcs[0] - dcs[1] - dcs[2] + dcs[3] };
+        // chroma DC: quantise, and the normative inverse (8.5.11)
+        int lv[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) { lv[k] = quant_dc(hd[k], q, q.f_inter); dc_nz |= lv[k] != 0; }
         const int fi[4] = { lv[0] + lv[1] + lv[2] + lv[3], lv[0] - lv[1] + lv[2] - lv[3], lv[0] + lv[1] - lv[2] - lv[3], lv[0] - lv[1] - lv[2] + lv[3] };
@@ -595,14 +647,12 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
         if (active) {
             uint4 *dst = reinterpret_cast<uint4 *>(is_luma ? co->luma[b] : co->chroma_ac[pl][cb]);
             dst[0] = reinterpret_cast<uint4 *>(lz)[0]; dst[1] = reinterpret_cast<uint4 *>(lz)[1];
-            uint8_t *rp = is_luma ? s.rec[0] + (size_t)(y0 + by) * wc + x0 + bx : s.rec[1 + pl] + (size_t)cy0 * cw + cx0;
-            const int rst = is_luma ? wc : cw;
+            // reconstruction on 16x2 lanes: prediction bytes widened, residual pairs packed, one add and one clamp to [0, 255] per pair
 #pragma unroll
             for (int y = 0; y < 4; y++) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int x = 0; x < 4; x++) w |= (uint32_t)clip255(p[y * 4 + x] + c[y * 4 + x]) << (8 * x);
-                *reinterpret_cast<uint32_t *>(rp + (size_t)y * rst) = w;
+                const uint32_t lo = __vimin_s16x2_relu(__vadd2(__byte_perm(P[y], 0u, 0x4140), __byte_perm((uint32_t)c[y * 4], (uint32_t)c[y * 4 + 1], 0x5410)), 0x00ff00ffu);
+                const uint32_t hi = __vimin_s16x2_relu(__vadd2(__byte_perm(P[y], 0u, 0x4342), __byte_perm((uint32_t)c[y * 4 + 2], (uint32_t)c[y * 4 + 3], 0x5410)), 0x00ff00ffu);
+                *reinterpret_cast<uint32_t *>(recp + (size_t)y * rst) = __byte_perm(lo, hi, 0x6420);
             }
         } else {
             nnz = 0;
@@ -616,8 +666,6 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     cbp |= ((nzmask >> 16) & 255) ? 32 : ((dcmask ? 16 : 0));
     if (lane < 24) mi->nnz[lane] = (uint8_t)nnz;
     // word 0: type, cbp; word 1: vector of partition 0 (= the 16x16 vector); words 2-5: the four partition vectors
-    const uint32_t mvw = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
-    const uint32_t mvq = __shfl_sync(0xffffffffu, mvw, lane == 0 ? 0 : 4 * ((lane - 1) & 3));
     if (lane == 0) {
         reinterpret_cast<uint32_t *>(mi)[0] = (use8 ? (uint32_t)MB_P8x8 : (uint32_t)MB_P16x16) | ((uint32_t)cbp << 24);
         reinterpret_cast<uint32_t *>(mi)[1] = mvq;
