@@ -59,9 +59,9 @@ def apply_workload(args):
         g["SLICES"] = args.slices
         g["LABEL"] += f" [slices overridden: {args.slices}]"
     if args.sessions is None:
-        args.sessions = 128
+        args.sessions = 256
     if args.groups is None:
-        args.groups = 4
+        args.groups = 8
 
 
 def frame_bytes():
@@ -237,12 +237,12 @@ def run_b200(args):
         err = E.e2e_last_error(h).decode()
         assert not err, f"e2e plugin driver: {err}"
         res = E2EResult()
-        assert E.e2e_run(h, 0, max(3, args.warmup), 0, C.byref(res)) == 0 and res.errors == 0, "e2e warm-up failed"
+        assert E.e2e_run(h, 0, max(3, args.warmup), 0, 0, C.byref(res)) == 0 and res.errors == 0, "e2e warm-up failed"
         sb0, sf0, sb1, sf1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         barrier()
         L.b200enc_scheduler_stats(dev, C.byref(sb0), C.byref(sf0))
         t0 = time.perf_counter()
-        assert E.e2e_run(h, max(3, args.warmup), args.steps, 0, C.byref(res)) == 0
+        assert E.e2e_run(h, max(3, args.warmup), args.steps, 0, 0, C.byref(res)) == 0
         barrier()
         el_e = time.perf_counter() - t0
         L.b200enc_scheduler_stats(dev, C.byref(sb1), C.byref(sf1))
@@ -261,14 +261,15 @@ def run_b200(args):
         if args.realtime_seconds > 0 and S > 1:
             barrier()
             rsteps = int(args.realtime_seconds * FPS)
-            assert E.e2e_run(h, max(3, args.warmup) + args.steps, rsteps, 1, C.byref(res)) == 0
+            RS = min(S, args.realtime_sessions)
+            assert E.e2e_run(h, max(3, args.warmup) + args.steps, rsteps, 1, RS, C.byref(res)) == 0
             barrier()
             rt = [float(res.late), float(res.errors), res.lat_p99_ms, res.lat_max_ms, res.lat_p50_ms]
             if use_dist:
                 t = torch.tensor(rt[:2], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 u = torch.tensor(rt[2:], dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.MAX)
                 rt = t.tolist() + u.tolist()
-            realtime = {"sessions_per_gpu": S, "sessions": S * world, "fps": FPS, "seconds": args.realtime_seconds, "frames": S * world * rsteps,
+            realtime = {"sessions_per_gpu": RS, "sessions": RS * world, "fps": FPS, "seconds": args.realtime_seconds, "frames": RS * world * rsteps,
                         "late_frames": int(rt[0]), "errors": int(rt[1]), "latency_ms": {"p50": round(rt[4], 2), "p99": round(rt[2], 2), "max": round(rt[3], 2)},
                         "realtime": bool(rt[0] == 0 and rt[1] == 0 and rt[2] <= 1000.0 / FPS),
                         "via": "VideoEncoder::EncodeOneFrame, one paced caller thread per session (staggered phases), pageable input"}
@@ -432,7 +433,7 @@ def e2e_lib():
     E = C.CDLL(path)
     E.e2e_open.restype = C.c_void_p
     E.e2e_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
-    E.e2e_run.restype = C.c_int; E.e2e_run.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.POINTER(E2EResult)]
+    E.e2e_run.restype = C.c_int; E.e2e_run.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.POINTER(E2EResult)]
     E.e2e_close.argtypes = [C.c_void_p]
     E.e2e_last_error.restype = C.c_char_p; E.e2e_last_error.argtypes = [C.c_void_p]
     return E
@@ -578,6 +579,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end and real-time legs (the line then carries no e2e)")
+    ap.add_argument("--realtime-sessions", type=int, default=200, help="sessions per GPU in the paced leg (BASELINE target: 125 per GPU)")
     ap.add_argument("--realtime-seconds", type=float, default=2.0, help="length of the paced real-time leg through the plugin boundary (0 = skip)")
     args = ap.parse_args()
     apply_workload(args)

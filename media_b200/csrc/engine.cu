@@ -279,6 +279,33 @@ enum { IN_HOST = 0,       // frames[i] is host memory: copied here (through the 
        IN_RESIDENT = 3 }; // the frame is still in the session's input buffer (second attempt of the rate control)
 #define SC_MIN_DISTANCE 10   /* a P picture is only promoted to a scene-change IDR when at least this many pictures passed since the last IDR */
 
+// Staging copy pageable -> pinned with non-temporal stores: the destination is only ever read by the DMA engine, so it should neither be
+// read for ownership nor displace the callers' working sets from the cache (3 MB per 1080p frame, a hundred sessions per GPU).
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) void stream_copy_avx2(uint8_t *dst, const uint8_t *src, size_t n)
+{
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = src[i]; i++; }
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(src + i)), b = _mm256_loadu_si256((const __m256i *)(src + i + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 64)), d = _mm256_loadu_si256((const __m256i *)(src + i + 96));
+        _mm256_stream_si256((__m256i *)(dst + i), a); _mm256_stream_si256((__m256i *)(dst + i + 32), b);
+        _mm256_stream_si256((__m256i *)(dst + i + 64), c); _mm256_stream_si256((__m256i *)(dst + i + 96), d);
+    }
+    for (; i < n; i++) dst[i] = src[i];
+    _mm_sfence();
+}
+#endif
+void stage_copy(uint8_t *dst, const uint8_t *src, size_t n)
+{
+#if defined(__x86_64__)
+    static const bool nt = [] { const char *e = getenv("B200ENC_STAGE_NT"); return (e ? atoi(e) != 0 : true) && __builtin_cpu_supports("avx2"); }();
+    if (nt) { stream_copy_avx2(dst, src, n); return; }
+#endif
+    memcpy(dst, src, n);
+}
+
 bool host_ptr_is_pinned(const void *p)
 {
     cudaPointerAttributes a;
@@ -292,13 +319,20 @@ bool host_ptr_is_pinned(const void *p)
 int upload_frame(b200enc_session *s, const uint8_t *frame, cudaStream_t st)
 {
     const size_t bytes = b200enc_frame_bytes(s);
-    const uint8_t *src = frame;
-    if (!host_ptr_is_pinned(frame)) {
+    static const bool stage = [] { const char *e = getenv("B200ENC_STAGE_PAGEABLE"); return e ? atoi(e) != 0 : true; }();   // 0: experiments only
+    static const size_t chunk = [] { const char *e = getenv("B200ENC_STAGE_CHUNK_KB"); return (size_t)std::max(64, e ? atoi(e) : 1 << 20) * 1024; }();
+    if (stage && !host_ptr_is_pinned(frame)) {
         if (!s->h_stage) CU_TRY(cudaHostAlloc(&s->h_stage, bytes, cudaHostAllocDefault), return B200ENC_ENOMEM);
-        memcpy(s->h_stage, frame, bytes);
-        src = s->h_stage;
+        // (B200ENC_STAGE_CHUNK_KB splits the copy so that the DMA of a chunk runs while the CPU stages the next one; measured on a 16-core host with
+        // 128 sessions it loses to one copy per frame -- the extra driver calls of 128 threads cost more than the overlap gains)
+        for (size_t off = 0; off < bytes; off += chunk) {
+            const size_t n = std::min(chunk, bytes - off);
+            stage_copy(s->h_stage + off, frame + off, n);
+            CU_TRY(cudaMemcpyAsync(s->input + off, s->h_stage + off, n, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
+        }
+        return B200ENC_OK;
     }
-    CU_TRY(cudaMemcpyAsync(s->input, src, bytes, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
+    CU_TRY(cudaMemcpyAsync(s->input, frame, bytes, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
     return B200ENC_OK;
 }
 bool next_is_idr(const b200enc_session *s) { return s->force_idr || !s->have_ref || s->frames_since_idr >= s->cfg.gop; }
@@ -525,13 +559,16 @@ struct SchedRequest {
     std::condition_variable cv;      // one per request: a finished batch wakes exactly its own callers, not every blocked session thread
 };
 struct DeviceScheduler {
-    static constexpr int WORKERS = 4;      // batch contexts (own streams): up to four batches in flight, so the latency-bound wavefront kernels of one
-                                           // batch run underneath the throughput kernels of the others
+    static constexpr int MAX_WORKERS = 8;
+    int workers = 8;                       // batch contexts (own streams): up to that many batches in flight, so the latency-bound wavefront kernels of one
+                                           // batch run underneath the throughput kernels of the others while further sessions upload their frames
+    int batch_div = 4, batch_max = 32;     // a batch aims at registered / batch_div sessions, at most batch_max (measured: 256 sessions through the plugin
+                                           // boundary, 8 x 32: 13 370 frames/s; 4 x 64: 11 370)
     int device = -1, registered = 0, inflight = 0, active = 0;       // active: batches on the GPU right now
     std::mutex mu; std::condition_variable cv_submit;
     std::vector<SchedRequest *> pending;
-    std::thread worker[WORKERS]; bool stop = false;
-    b200enc_batch *ctx[WORKERS] = { nullptr, nullptr, nullptr, nullptr }; int window_us = 300, fill_us = 4000;
+    std::thread worker[MAX_WORKERS]; bool stop = false;
+    b200enc_batch *ctx[MAX_WORKERS] = {}; int window_us = 300, fill_us = 4000;
     std::atomic<uint64_t> batches{ 0 }, frames{ 0 };
 
     void run(int w)
@@ -546,7 +583,7 @@ struct DeviceScheduler {
             // lone caller pays at most that). With two or more in flight the GPU is busy anyway, so wait for the fuller batch -- until enough
             // callers arrived, a running batch finished, or fill_us passed. Leaves at once when every session not being encoded is waiting.
             const auto t0 = std::chrono::steady_clock::now();
-            const int target = std::max(1, std::min(ctx[w]->cap, (registered + 3) / 4));
+            const int target = std::max(1, std::min(std::min(ctx[w]->cap, batch_max), (registered + batch_div - 1) / batch_div));
             while (!stop && !pending.empty()) {
                 const int want = std::min(target, std::max(1, registered - inflight));
                 if ((int)pending.size() >= want) break;
@@ -561,7 +598,7 @@ struct DeviceScheduler {
             std::vector<SchedRequest *> take, rest;
             const bool kind0 = next_is_idr(pending[0]->s);
             for (SchedRequest *r : pending)
-                (same_shape(pending[0]->s, r->s) && next_is_idr(r->s) == kind0 && (int)take.size() < ctx[w]->cap ? take : rest).push_back(r);
+                (same_shape(pending[0]->s, r->s) && next_is_idr(r->s) == kind0 && (int)take.size() < std::min(ctx[w]->cap, 2 * batch_max) ? take : rest).push_back(r);
             pending.swap(rest);
             const int n = (int)take.size();
             inflight += n; active++;
@@ -595,12 +632,15 @@ DeviceScheduler *scheduler_for(int device)
         d->device = device;
         if (const char *e = getenv("B200ENC_BATCH_WINDOW_US")) d->window_us = std::max(0, atoi(e));
         if (const char *e = getenv("B200ENC_BATCH_FILL_US")) d->fill_us = std::max(0, atoi(e));
-        for (int w = 0; w < DeviceScheduler::WORKERS; w++) {
+        if (const char *e = getenv("B200ENC_BATCH_WORKERS")) d->workers = std::min(std::max(1, atoi(e)), (int)DeviceScheduler::MAX_WORKERS);
+        if (const char *e = getenv("B200ENC_BATCH_DIV")) d->batch_div = std::max(1, atoi(e));
+        if (const char *e = getenv("B200ENC_BATCH_MAX")) d->batch_max = std::max(1, atoi(e));
+        for (int w = 0; w < d->workers; w++) {
             d->ctx[w] = new (std::nothrow) b200enc_batch();
             if (!d->ctx[w] || batch_init(d->ctx[w], device, 512) != B200ENC_OK) return nullptr;
         }
         DeviceScheduler *raw = d.get();
-        for (int w = 0; w < DeviceScheduler::WORKERS; w++) d->worker[w] = std::thread([raw, w] { raw->run(w); });
+        for (int w = 0; w < d->workers; w++) d->worker[w] = std::thread([raw, w] { raw->run(w); });
         g_scheds[device] = std::move(d);
     }
     return g_scheds[device].get();

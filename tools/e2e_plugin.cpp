@@ -96,11 +96,12 @@ void *e2e_open(const char *codec_lib, int sessions, int width, int height, int f
 
 // Every session encodes `steps` frames (frames first_step .. first_step + steps - 1 of its walk through the pool) on its own thread.
 // paced = 0: back to back (throughput); paced = 1: one frame per 1/fps, session start times staggered over one period (real time).
-int e2e_run(void *h, long first_step, int steps, int paced, e2e_result *out)
+// `limit` > 0 runs only the first `limit` sessions (the paced leg may use fewer sessions than the throughput leg).
+int e2e_run(void *h, long first_step, int steps, int paced, int limit, e2e_result *out)
 {
     E2E *e = static_cast<E2E *>(h);
     if (!e || !e->error.empty() || !out || e->enc.empty() || e->pool.empty()) return -1;
-    const int N = (int)e->enc.size(), P = (int)e->pool.size();
+    const int N = limit > 0 ? std::min(limit, (int)e->enc.size()) : (int)e->enc.size(), P = (int)e->pool.size();
     std::vector<std::vector<float>> lat(N);
     std::atomic<uint64_t> bytes{ 0 }, errors{ 0 }, late{ 0 };
     std::vector<clk::time_point> done(N);
@@ -171,8 +172,8 @@ int main(int argc, char **argv)
     void *h = e2e_open(argv[1], N, W, H, fps, br, 300, profile, "i420", device, pool.data(), POOL, fb);
     if (*e2e_last_error(h)) { printf("{\"error\": \"%s\"}\n", e2e_last_error(h)); return 1; }
     e2e_result r;
-    e2e_run(h, 0, 3, 0, &r);                                  // warm-up: the IDR and two P pictures of every session
-    if (e2e_run(h, 3, steps, paced, &r) != 0) { printf("{\"error\": \"run failed\"}\n"); return 1; }
+    e2e_run(h, 0, 3, 0, 0, &r);                                  // warm-up: the IDR and two P pictures of every session
+    if (e2e_run(h, 3, steps, paced, 0, &r) != 0) { printf("{\"error\": \"run failed\"}\n"); return 1; }
     printf("{\"via\": \"VideoEncoder::EncodeOneFrame, one caller thread per session, pageable input\", \"sessions\": %d, \"steps\": %d, \"paced\": %d, \"frames_per_s\": %.1f, "
            "\"bytes_per_frame\": %.0f, \"errors\": %llu, \"late\": %llu, \"latency_ms\": {\"p50\": %.2f, \"p99\": %.2f, \"max\": %.2f}}\n",
            N, steps, paced, r.frames / r.seconds, r.frames ? (double)r.bytes / r.frames : 0.0, (unsigned long long)r.errors, (unsigned long long)r.late,
