@@ -156,7 +156,8 @@ struct b200enc_session {
     int device = -1; double load = 0;
     uint8_t *d_pool = nullptr; size_t pool_bytes = 0;
     // device buffers (sub-allocated from d_pool)
-    uint8_t *input = nullptr, *src[3], *bufA[3], *bufB[3], *rec_pre[3];
+    uint8_t *input = nullptr, *src[3], *srcB[3], *bufA[3], *bufB[3], *rec_pre[3];     // src / srcB: the source planes alternate, so the previous picture's stay (background detection)
+    bool src_is_A = true, have_psrc = false;
     uint8_t *srcL1, *srcL2, *refL1, *refL2;      // padded pyramid planes (allocation bases)
     uint8_t *rpl, *rpc[2];                       // padded reference planes: G,b,h,j contiguous; Cb, Cr
     void *tmaps;                                 // CUtensorMap[3] in HBM
@@ -354,7 +355,12 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         if (mode == IN_DEVICE) d.input = frames[i];
         else if (mode == IN_HOST) { const int rc = upload_frame(s, frames[i], st); if (rc != B200ENC_OK) return rc; }
         else if (mode == IN_UPLOADED) CU_TRY(cudaStreamWaitEvent(st, s->ev_up, 0), return B200ENC_ECUDA);
-        for (int c = 0; c < 3; c++) { d.src[c] = s->src[c]; d.rec[c] = cur[c]; d.ref[c] = ref[c]; }
+        for (int c = 0; c < 3; c++) {
+            d.src[c] = s->src_is_A ? s->src[c] : s->srcB[c]; d.src_prev[c] = s->have_psrc ? (s->src_is_A ? s->srcB[c] : s->src[c]) : nullptr;
+            d.rec[c] = cur[c]; d.ref[c] = ref[c];
+        }
+        d.src_tmap = s->src_is_A ? 0 : 3 * (int)sizeof(CUtensorMap);
+        d.bgd = s->cfg.background_detection; d.no_p8x8 = s->cfg.complexity <= 1; d.no_i4x4 = s->cfg.complexity == 0;
         {   // padded planes: hand the kernels the address of the interior sample (0,0)
             const size_t o1 = (size_t)g.p1 * g.s1 + g.p1, o2 = (size_t)g.p2 * g.s2 + g.p2, ol = (size_t)g.lp * g.ls + g.lp, oc = (size_t)g.cp * g.cs + g.cp;
             const size_t plane = (size_t)g.ls * (g.hc + 2 * g.lp);
@@ -534,6 +540,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         if (idr) { s->frame_num = 0; s->frames_since_idr = 0; s->idr_pic_id = (s->idr_pic_id + 1) & 1; }
         s->frame_num = (s->frame_num + 1) & 255; s->frames_since_idr++; s->frame_index++;
         s->force_idr = false; s->have_ref = true; s->cur_is_A = !s->cur_is_A;
+        s->src_is_A = !s->src_is_A; s->have_psrc = true;        // this picture's source planes are the next picture's "previous source"
     }
     return worst;
 }
@@ -775,11 +782,11 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         std::vector<Item> items;
         auto add = [&](auto &ptr, size_t bytes) { items.push_back({ reinterpret_cast<void **>(&ptr), bytes }); };
         add(s->input, b200enc_frame_bytes(s));
-        for (int k = 0; k < 3; k++) { const size_t b = k ? nc : ny; add(s->src[k], b); add(s->bufA[k], b); add(s->bufB[k], b); add(s->rec_pre[k], (c.debug & 1) ? b : 16); }
+        for (int k = 0; k < 3; k++) { const size_t b = k ? nc : ny; add(s->src[k], b); add(s->srcB[k], b); add(s->bufA[k], b); add(s->bufB[k], b); add(s->rec_pre[k], (c.debug & 1) ? b : 16); }
         const size_t l1 = (size_t)g.s1 * (g.hc / 2 + 2 * g.p1) + 64, l2 = (size_t)g.s2 * (g.hc / 4 + 2 * g.p2) + 64;
         const size_t lplane = (size_t)g.ls * (g.hc + 2 * g.lp), cplane = (size_t)g.cs * (g.hc / 2 + 2 * g.cp) + 64;
         add(s->srcL1, l1); add(s->refL1, l1); add(s->srcL2, l2); add(s->refL2, l2);
-        add(s->rpl, 4 * lplane + 256); add(s->rpc[0], cplane); add(s->rpc[1], cplane); add(s->tmaps, 3 * sizeof(CUtensorMap));
+        add(s->rpl, 4 * lplane + 256); add(s->rpc[0], cplane); add(s->rpc[1], cplane); add(s->tmaps, 4 * sizeof(CUtensorMap));
         add(s->mbi, nmb * sizeof(MbInfo)); add(s->coef, nmb * sizeof(MbCoef)); add(s->dbk_bs, nmb * sizeof(uint4));
         add(s->me2, nmb * 4); add(s->me1, nmb * 4); add(s->me0, nmb * 4); add(s->inter_cost, nmb * 4);
         add(s->skip_run, (nmb + B200_MAX_SLICES) * 4); add(s->mb_bits, nmb * 4); add(s->mb_off, nmb * 4);
@@ -797,11 +804,12 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         for (auto &it : items) { *it.p = s->d_pool + off; off += align_up(it.bytes, 256); }
         CU_TRY(cudaMemcpy(s->hdr, ps.data(), ps.size(), cudaMemcpyHostToDevice), rc = B200ENC_ECUDA; break);
         {   // TMA descriptors of the tiles k_me_fine fetches (u8 elements, no swizzle, zero fill outside the tensor)
-            CUtensorMap tm[3];
+            CUtensorMap tm[4];
             const uint64_t H = (uint64_t)g.hc + 2 * g.lp;
             if (!encode_tmap(&tm[0], s->src[0], 2, (uint64_t)g.wc, (uint64_t)g.hc, 1, (uint64_t)g.wc, 0, 16, 16, 1) ||
                 !encode_tmap(&tm[1], s->rpl, 2, (uint64_t)g.ls, H, 1, (uint64_t)g.ls, 0, 48, 20, 1) ||
-                !encode_tmap(&tm[2], s->rpl, 3, (uint64_t)g.ls, H, 4, (uint64_t)g.ls, (uint64_t)g.ls * H, 48, 18, 4)) { rc = B200ENC_ENODEV; break; }
+                !encode_tmap(&tm[2], s->rpl, 3, (uint64_t)g.ls, H, 4, (uint64_t)g.ls, (uint64_t)g.ls * H, 48, 18, 4) ||
+                !encode_tmap(&tm[3], s->srcB[0], 2, (uint64_t)g.wc, (uint64_t)g.hc, 1, (uint64_t)g.wc, 0, 16, 16, 1)) { rc = B200ENC_ENODEV; break; }
             CU_TRY(cudaMemcpy(s->tmaps, tm, sizeof tm, cudaMemcpyHostToDevice), rc = B200ENC_ECUDA; break);
         }
         // output buffer: twice the raw frame + 64 KB (CAVLC without I_PCM can exceed the raw size on noise at very low QP:
@@ -939,7 +947,7 @@ int b200enc_get_stage(b200enc_session *s, int stage, void *out, size_t cap, size
     case B200ENC_STAGE_BIN_COUNT: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->mb_bits; bytes = nmb * 4; break;
     case B200ENC_STAGE_BIN_OFF: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->mb_off; bytes = nmb * 4; break;
     case B200ENC_STAGE_BINS: if (!s->cfg.profile) return B200ENC_EINVAL; src = s->bins; bytes = nmb * B200_MB_BIN_SLOT * sizeof(uint16_t); break;
-    case B200ENC_STAGE_SRC: planes = s->src; break;
+    case B200ENC_STAGE_SRC: planes = s->src_is_A ? s->srcB : s->src; break;       // the picture just encoded (roles were swapped after it)
     case B200ENC_STAGE_REC_PRE: if (!(s->cfg.debug & 1)) return B200ENC_EINVAL; planes = s->rec_pre; break;
     case B200ENC_STAGE_REC: planes = last; break;
     default: return B200ENC_EINVAL;

@@ -62,13 +62,14 @@ struct Geom {
 struct Sess {
     const uint8_t *input;         // display-size frame in HBM: I420, NV12 or RGBA
     uint8_t *src[3];              // coded-size source planes
+    const uint8_t *src_prev[3];   // source planes of the previous committed picture (background detection); null before the second picture
     uint8_t *rec[3];              // reconstruction of this frame (deblocked in place at the end)
     uint8_t *ref[3];              // previous frame's deblocked reconstruction
     // padded planes; every pointer addresses sample (0,0) of the plane's interior, rows are g.ls / g.cs / g.s1 / g.s2 apart
     uint8_t *rpl[4];              // reference luma: G (full-pel copy), b, h, j half-pel planes (8.4.2.2.1), built once per frame
     uint8_t *rpc[2];              // reference Cb, Cr
     uint8_t *srcL1, *srcL2, *refL1, *refL2;
-    const void *tmaps;            // CUtensorMap[3] in HBM: source luma (box 16x16), plane G (box 48x20), planes G,b,h,j (box 48x18x4)
+    const void *tmaps;            // CUtensorMap[4] in HBM: source luma A (box 16x16), plane G (box 48x20), planes G,b,h,j (box 48x18x4), source luma B
     MbInfo *mbi; MbCoef *coef;
     uint4 *dbk_bs;                // per MB: the 32 boundary strengths as bit planes (k_deblock_bs)
     int16_t *me2, *me1, *me0;     // per-level vectors (debug / parity dumps)
@@ -88,6 +89,9 @@ struct Sess {
     int *row_prog_intra, *row_prog_dbk; // wavefront progress counters, one per MB row
     int qp, is_idr, frame_num, idr_pic_id, input_format;
     int scene_change;             // 1: k_scene_change may turn this P picture into an IDR (then is_idr / frame_num are rewritten on the device)
+    int bgd;                      // 1: background detection (static macroblocks against src_prev are skipped)
+    int no_p8x8, no_i4x4;         // complexity modes: LOW drops both, MEDIUM drops P_8x8 (iComplexityMode, VideoEncoderOpenH264.cpp:289)
+    int src_tmap;                 // byte offset inside tmaps of the source-luma descriptor of this picture's source planes (they alternate)
     int dump;                     // 1: stage dumps are read back (debug bit 0): cbp-0 macroblocks also store their all-zero level records
     int t8x8;                     // 1: PPS transform_8x8_mode_flag (High profile): inter MBs may take the 8x8 transform (k_inter_t8)
     uint32_t rbsp_words_per_slice, out_cap;

@@ -92,7 +92,7 @@ static __device__ __constant__ uint32_t c_i4_idx[9][4] = {
 // the session fields the row loop needs, in registers (every fence / strong access is a compiler memory barrier, and the L1
 // invalidation behind the acquire makes re-reading them through `const Sess &` an L2 round trip each)
 struct IntraCtx {
-    uint8_t *rec0, *rec1, *rec2; const uint8_t *src0, *src1, *src2; MbInfo *mbi; MbCoef *coef; int qp, is_idr;
+    uint8_t *rec0, *rec1, *rec2; const uint8_t *src0, *src1, *src2; MbInfo *mbi; MbCoef *coef; int qp, is_idr, no_i4x4;
     __device__ __forceinline__ uint8_t *rec(int c) const { return c == 0 ? rec0 : c == 1 ? rec1 : rec2; }
     __device__ __forceinline__ const uint8_t *src(int c) const { return c == 0 ? src0 : c == 1 ? src1 : src2; }
 };
@@ -349,7 +349,7 @@ __device__ void intra_code_mb(const IntraCtx &s, const Geom &g, IntraSmem &sm, i
     // Intra_4x4 on trial against the Intra_16x16 SATD
     int cbp_luma4 = 0; unsigned long long modes4 = 0ull;
     INTRA_T(1);
-    const bool use_i4 = intra_try_i4x4(s, g, sm, mx, my, lane, (int)(__shfl_sync(0xffffffffu, best, 0) >> 2), top, left, cbp_luma4, modes4);
+    const bool use_i4 = !s.no_i4x4 && intra_try_i4x4(s, g, sm, mx, my, lane, (int)(__shfl_sync(0xffffffffu, best, 0) >> 2), top, left, cbp_luma4, modes4);
 
     int p[16], c[16]; intra_pred_block(kind, T, L, bx, by, dcv, pa, pb, pc, off, p);
 #pragma unroll
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_intra_wave(const Sess *ss, 
     IntraSmem &sm = sm_all[warp];
     int *prog = sg.row_prog_intra;
     IntraCtx s; s.rec0 = sg.rec[0]; s.rec1 = sg.rec[1]; s.rec2 = sg.rec[2]; s.src0 = sg.src[0]; s.src1 = sg.src[1]; s.src2 = sg.src[2];
-    s.mbi = sg.mbi; s.coef = sg.coef; s.qp = sg.qp; s.is_idr = sg.is_idr;
+    s.mbi = sg.mbi; s.coef = sg.coef; s.qp = sg.qp; s.is_idr = sg.is_idr; s.no_i4x4 = sg.no_i4x4;
     const bool slice_top = row_is_slice_top(g, my);
     int mx = 0;
     while (mx < g.mbw) {

@@ -286,17 +286,17 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
         mbar_init(&sm.bar[0]); mbar_init(&sm.bar[1]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&sm.bar[0], 256 + 20 * PL_STRIDE);
-        tma_load_2d(sm.src, tmaps, x0, y0, &sm.bar[0]);
+        tma_load_2d(sm.src, tmaps + s.src_tmap, x0, y0, &sm.bar[0]);
         tma_load_2d(sm.win, tmaps + 128, X0 & ~15, g.lp + y0 + cy - 2, &sm.bar[0]);
     }
     // zero-vector candidate, computed cooperatively straight from HBM while the tiles are in flight
     uint32_t zsad;
-    uint2 zref;
+    uint2 zref, zsrc;
     {
         const uint8_t *rp = s.ref[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8;
         const uint8_t *sp = s.src[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8;
         uint2 a = *reinterpret_cast<const uint2 *>(rp), b = *reinterpret_cast<const uint2 *>(sp);
-        zsad = sad4(a.x, b.x, sad4(a.y, b.y, 0)); zref = a;
+        zsad = sad4(a.x, b.x, sad4(a.y, b.y, 0)); zref = a; zsrc = b;
 #pragma unroll
         for (int o = 16; o; o >>= 1) zsad += __shfl_xor_sync(0xffffffffu, zsad, o);
     }
@@ -328,7 +328,26 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
             const int hd[4] = { dcs[0] + dcs[1] + dcs[2] + dcs[3], dcs[0] - dcs[1] + dcs[2] - dcs[3], dcs[0] + dcs[1] - dcs[2] - dcs[3], dcs[0] - dcs[1] - dcs[2] + dcs[3] };
             if (!isl) for (int k = 0; k < 4; k++) nz |= quant_dc(hd[k], q, q.f_inter) != 0;
         }
-        if (__ballot_sync(0xffffffffu, act && nz) == 0) {
+        // BACKGROUND DETECTION (the wrapper's bEnableBackgroundDetection, VideoEncoderOpenH264.cpp:282): static against the PREVIOUS
+        // SOURCE picture -- every 8x8 unit of luma and both chroma blocks with SAD <= 128 and no sample off by more than 12 -- and close enough to
+        // the reference (zero-vector luma SAD <= 64 (8 + lambda)): skipped like a macroblock whose residual vanishes
+        bool bg = false;
+        if (s.bgd && s.src_prev[0]) {
+            const uint2 pv = *reinterpret_cast<const uint2 *>(s.src_prev[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8);
+            uint32_t ou = sad4(zsrc.x, pv.x, sad4(zsrc.y, pv.y, 0));       // lane = (row, half): its unit's lanes differ in bits 1-3
+            ou += __shfl_xor_sync(0xffffffffu, ou, 2); ou += __shfl_xor_sync(0xffffffffu, ou, 4); ou += __shfl_xor_sync(0xffffffffu, ou, 8);
+            const uint32_t d0 = __vabsdiffu4(zsrc.x, pv.x), d1 = __vabsdiffu4(zsrc.y, pv.y);
+            uint32_t big = ((((d0 & 0x7f7f7f7fu) + 0x73737373u) | d0) | (((d1 & 0x7f7f7f7fu) + 0x73737373u) | d1)) & 0x80808080u;     // a byte above 12
+            const int cp_ = (lane >> 3) & 1, cr_ = lane & 7;
+            const size_t coff = (size_t)(my * 8 + cr_) * cw + mx * 8;
+            const uint2 cc = *reinterpret_cast<const uint2 *>(s.src[1 + cp_] + coff), cq = *reinterpret_cast<const uint2 *>(s.src_prev[1 + cp_] + coff);
+            uint32_t cs_ = sad4(cc.x, cq.x, sad4(cc.y, cq.y, 0));
+            cs_ += __shfl_xor_sync(0xffffffffu, cs_, 1); cs_ += __shfl_xor_sync(0xffffffffu, cs_, 2); cs_ += __shfl_xor_sync(0xffffffffu, cs_, 4);
+            const uint32_t e0 = __vabsdiffu4(cc.x, cq.x), e1 = __vabsdiffu4(cc.y, cq.y);
+            big |= ((((e0 & 0x7f7f7f7fu) + 0x73737373u) | e0) | (((e1 & 0x7f7f7f7fu) + 0x73737373u) | e1)) & 0x80808080u;
+            bg = __ballot_sync(0xffffffffu, ou > 128u || cs_ > 128u || big != 0u) == 0u && zsad <= 64u * (8u + (uint32_t)lambda);
+        }
+        if (bg || __ballot_sync(0xffffffffu, act && nz) == 0) {
             const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
             const size_t co_ = (size_t)(my * 8 + crow) * cw + mx * 8 + chalf * 4;
             *reinterpret_cast<uint2 *>(s.rec[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8) = zref;
@@ -501,7 +520,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     const int c8q = (int)(bq >> 5);
     const int cost8 = __shfl_sync(0xffffffffu, c8q, 0) + __shfl_sync(0xffffffffu, c8q, 4) + __shfl_sync(0xffffffffu, c8q, 8) +
                       __shfl_sync(0xffffffffu, c8q, 12) + lambda * P8X8_BIAS_BITS;
-    const bool use8 = cost8 < cost16;
+    const bool use8 = !s.no_p8x8 && cost8 < cost16;
     if (!use8) { lx = qx; ly = qy; }
     const int inter_cost = use8 ? cost8 : cost16;
 

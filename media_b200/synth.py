@@ -16,13 +16,14 @@ def _stretch(a, lo=16, hi=235):
 
 
 class Content:
-    """kind: 'A' moving texture, 'B' screen-like, 'C' static, 'D' white noise."""
+    """kind: 'A' moving texture, 'B' screen-like, 'C' static, 'D' white noise, 'E' static scene with sensor noise (sigma 1.2) and one moving
+    object -- the content background detection is for."""
 
     def __init__(self, kind, width, height, seed=SEED):
         self.kind, self.w, self.h = kind, width, height
         self.rng = np.random.default_rng(seed)
         w, h = width, height
-        if kind in ("A", "C"):
+        if kind in ("A", "C", "E"):
             self.ty = _stretch(_blur(self.rng.random((h + 64, w + 64))))
             self.tu = _stretch(_blur(self.rng.random((h // 2 + 32, w // 2 + 32))), 64, 192)
             self.tv = _stretch(_blur(self.rng.random((h // 2 + 32, w // 2 + 32))), 64, 192)
@@ -52,6 +53,14 @@ class Content:
                 y[y0:y0 + bh, x0:x0 + bw] = val
         elif self.kind == "C":
             y, u, v = self.ty[:h, :w], self.tu[:h // 2, :w // 2], self.tv[:h // 2, :w // 2]
+        elif self.kind == "E":
+            r = np.random.default_rng(SEED + 104729 * t)
+            noisy = lambda p, lo, hi: np.clip(p.astype(np.float32) + r.normal(0.0, 1.2, p.shape), lo, hi).round().astype(np.uint8)
+            y = noisy(self.ty[:h, :w], 16, 235)
+            u, v = noisy(self.tu[:h // 2, :w // 2], 16, 240), noisy(self.tv[:h // 2, :w // 2], 16, 240)
+            bw, bh = max(16, w // 6), max(16, h // 6)
+            x0, y0 = (w // 5 + 5 * t) % max(1, w - bw), (h // 3 + 2 * t) % max(1, h - bh)
+            y[y0:y0 + bh, x0:x0 + bw] = 60
         elif self.kind == "B":
             # cumulative screen updates: frame t = base picture with the updates of steps 0..t applied (stateless for the caller)
             if getattr(self, "_b_t", None) is None or self._b_t > t:

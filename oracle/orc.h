@@ -86,9 +86,13 @@ typedef struct {
     int profile;             /* 0 Constrained Baseline / CAVLC; 1 Main / CABAC; 2 High / CABAC with the 8x8 transform on inter MBs, the
                                 wrapper's persist.vmi.video.encode.profile values (VideoEncoderOpenH264.cpp:248-253) */
     int no_t8x8;             /* 1: High profile without the 8x8 transform (transform_8x8_mode_flag = 0; quality A/B runs) */
+    int background_detection;/* 1: static macroblocks (against the previous source picture) are skipped (b200enc_config.background_detection) */
+    int complexity_set, complexity; /* complexity_set = 1: iComplexityMode 0 LOW (no Intra_4x4 trial, no P_8x8), 1 MEDIUM (no P_8x8), 2 HIGH */
     int intra8x8;            /* 1: High profile intra MBs may also take Intra_8x8 (8.3.2). GROUNDWORK for the next round: pinned by the decoder
                                 round trip on the CPU, not yet built in CUDA, so the product and every parity test run with 0 */
 } OrcConfig;
+#define ORC_BGD_OU_SAD 128       /* background detection: largest SAD of an 8x8 unit against the previous source picture (mean |d| <= 2) */
+#define ORC_BGD_MAXDIFF 12       /* ... and largest single sample difference */
 #define ORC_SC_MIN_DISTANCE 10   /* scene-change promotion needs this many pictures since the last IDR (the IDR counts as the first) */
 #define ORC_MB_T8(m) (((m)->i16_mode >> 2) & 1)
 

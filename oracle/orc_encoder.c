@@ -28,6 +28,8 @@ struct OrcEncoder {
     OrcConfig cfg;
     int mbw, mbh, wc, hc;
     uint8_t *src[3], *rec[3], *dbk[3], *ref[3];
+    uint8_t *bg_skip;                /* per MB: 1 = skipped as static background (no residual is coded) */
+    uint8_t *psrc[3]; int have_psrc, src_committed;   /* source planes of the last committed picture (background detection) */
     uint8_t *srcL1, *srcL2, *refL1, *refL2;
     uint8_t *hpb, *hph, *hpj;        /* half-pel planes of ref luma, (wc+2M) x (hc+2M) */
     OrcMbInfo *mbi; OrcMbCoef *coef;
@@ -53,6 +55,8 @@ OrcEncoder *orc_create(const OrcConfig *cfg)
 {
     OrcEncoder *e = (OrcEncoder *)calloc(1, sizeof *e);
     e->cfg = *cfg;
+    /* iComplexityMode (the wrapper asks for HIGH_COMPLEXITY = 2, VideoEncoderOpenH264.cpp:289): 0 LOW drops the Intra_4x4 trial and P_8x8, 1 MEDIUM drops P_8x8 */
+    if (e->cfg.complexity_set) { if (e->cfg.complexity <= 1) e->cfg.no_p8x8 = 1; if (e->cfg.complexity == 0) e->cfg.no_i4x4 = 1; }
     if (e->cfg.num_slices < 1) e->cfg.num_slices = 1;
     if (e->cfg.search_range < 4) e->cfg.search_range = 16;
     if (e->cfg.fps <= 0) e->cfg.fps = 30;
@@ -60,14 +64,14 @@ OrcEncoder *orc_create(const OrcConfig *cfg)
     if (e->cfg.num_slices > e->mbh) e->cfg.num_slices = e->mbh;
     e->wc = e->mbw * 16; e->hc = e->mbh * 16;
     size_t ny = (size_t)e->wc * e->hc, nc = ny / 4;
-    uint8_t **sets[4] = { e->src, e->rec, e->dbk, e->ref };
-    for (int s = 0; s < 4; s++) { sets[s][0] = calloc(1, ny); sets[s][1] = calloc(1, nc); sets[s][2] = calloc(1, nc); }
+    uint8_t **sets[5] = { e->src, e->rec, e->dbk, e->ref, e->psrc };
+    for (int s = 0; s < 5; s++) { sets[s][0] = calloc(1, ny); sets[s][1] = calloc(1, nc); sets[s][2] = calloc(1, nc); }
     e->srcL1 = calloc(1, ny / 4); e->refL1 = calloc(1, ny / 4);
     e->srcL2 = calloc(1, ny / 16); e->refL2 = calloc(1, ny / 16);
     size_t nh = (size_t)(e->wc + 2 * HP_M) * (e->hc + 2 * HP_M);
     e->hpb = malloc(nh); e->hph = malloc(nh); e->hpj = malloc(nh);
     int n = e->mbw * e->mbh;
-    e->mbi = calloc(n, sizeof(OrcMbInfo)); e->coef = calloc(n, sizeof(OrcMbCoef));
+    e->mbi = calloc(n, sizeof(OrcMbInfo)); e->coef = calloc(n, sizeof(OrcMbCoef)); e->bg_skip = calloc(n, 1);
     for (int l = 0; l < 3; l++) e->me[l] = calloc(n * 2, sizeof(int16_t));
     e->inter_cost = calloc(n, sizeof(int32_t));
     e->pred_y = malloc((size_t)n * 256); e->pred_c = malloc((size_t)n * 128);
@@ -85,11 +89,11 @@ OrcEncoder *orc_create(const OrcConfig *cfg)
 void orc_destroy(OrcEncoder *e)
 {
     if (!e) return;
-    uint8_t **sets[4] = { e->src, e->rec, e->dbk, e->ref };
-    for (int s = 0; s < 4; s++) for (int c = 0; c < 3; c++) free(sets[s][c]);
+    uint8_t **sets[5] = { e->src, e->rec, e->dbk, e->ref, e->psrc };
+    for (int s = 0; s < 5; s++) for (int c = 0; c < 3; c++) free(sets[s][c]);
     free(e->srcL1); free(e->srcL2); free(e->refL1); free(e->refL2);
     free(e->hpb); free(e->hph); free(e->hpj);
-    free(e->mbi); free(e->coef); for (int l = 0; l < 3; l++) free(e->me[l]);
+    free(e->mbi); free(e->coef); free(e->bg_skip); for (int l = 0; l < 3; l++) free(e->me[l]);
     free(e->inter_cost); free(e->pred_y); free(e->pred_c); free(e->slice_row0); free(e->rbsp); free(e->side); free(e->bins); free(e->slice_bin0); free(e);
 }
 
@@ -129,6 +133,8 @@ static int row_is_slice_top(const OrcEncoder *e, int my) { return e->slice_row0[
 static void load_source(OrcEncoder *e, const uint8_t *in)
 {
     int w = e->cfg.width, h = e->cfg.height;
+    /* the planes of the last COMMITTED picture become the previous source (a trial is overwritten, not remembered) */
+    if (e->src_committed) { for (int c = 0; c < 3; c++) { uint8_t *t = e->src[c]; e->src[c] = e->psrc[c]; e->psrc[c] = t; } e->have_psrc = 1; e->src_committed = 0; }
     for (int c = 0; c < 3; c++) {
         int pw = c ? w / 2 : w, ph = c ? h / 2 : h, cw = c ? e->wc / 2 : e->wc, ch = c ? e->hc / 2 : e->hc;
         for (int y = 0; y < ch; y++) {
@@ -258,6 +264,41 @@ static int zero_vector_residual_vanishes(const OrcEncoder *e, int mx, int my, in
     return 1;
 }
 
+/* Background detection (the wrapper sets bEnableBackgroundDetection = 1, VideoEncoderOpenH264.cpp:282; openh264's pre-analysis compares the
+ * current with the previous SOURCE picture per 8x8 unit and lets static macroblocks be skipped). OUR definition: a macroblock
+ * is static background when, against the previous source picture at the same position, every 8x8 unit of luma and both 8x8 chroma blocks
+ * have SAD <= ORC_BGD_OU_SAD and no sample differs by more than ORC_BGD_MAXDIFF, and its luma SAD against the REFERENCE at the zero
+ * vector is at most 64 * (8 + lambda) -- what bounds the error a run of skips can accumulate. Such a macroblock is skipped like one
+ * whose residual quantises to nothing. */
+static int mb_is_static_background(const OrcEncoder *e, int mx, int my, int lambda)
+{
+    if (!e->cfg.background_detection || !e->have_psrc) return 0;
+    int st = e->wc, cs = st / 2;
+    const uint8_t *s = e->src[0] + (size_t)my * 16 * st + mx * 16, *p = e->psrc[0] + (size_t)my * 16 * st + mx * 16;
+    const uint8_t *r = e->ref[0] + (size_t)my * 16 * st + mx * 16;
+    int zsad = 0;
+    for (int q = 0; q < 4; q++) {
+        int sad = 0, o = (q >> 1) * 8 * st + (q & 1) * 8;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            int d = iabs(s[o + y * st + x] - p[o + y * st + x]);
+            if (d > ORC_BGD_MAXDIFF) return 0;
+            sad += d; zsad += iabs(s[o + y * st + x] - r[o + y * st + x]);
+        }
+        if (sad > ORC_BGD_OU_SAD) return 0;
+    }
+    for (int pl = 0; pl < 2; pl++) {
+        const uint8_t *sc = e->src[1 + pl] + (size_t)my * 8 * cs + mx * 8, *pc = e->psrc[1 + pl] + (size_t)my * 8 * cs + mx * 8;
+        int sad = 0;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            int d = iabs(sc[y * cs + x] - pc[y * cs + x]);
+            if (d > ORC_BGD_MAXDIFF) return 0;
+            sad += d;
+        }
+        if (sad > ORC_BGD_OU_SAD) return 0;
+    }
+    return zsad <= 64 * (8 + lambda);
+}
+
 static void motion_search(OrcEncoder *e, int mx, int my, int lambda, int qp)
 {
     int mb = my * e->mbw + mx, R4 = e->cfg.search_range / 4, span = 2 * R4 + 1;
@@ -295,7 +336,8 @@ static void motion_search(OrcEncoder *e, int mx, int my, int lambda, int qp)
     /* EARLY SKIP: with a zero predictor estimate, a macroblock whose zero-vector residual quantises to nothing is
      * final -- P_L0_16x16, vector (0,0), cbp 0 (P_Skip follows in phase D when the normative skip vector is zero too). Static
      * screen content never enters the search. */
-    if (ppx == 0 && ppy == 0 && zero_vector_residual_vanishes(e, mx, my, qp)) {
+    e->bg_skip[mb] = 0;
+    if (ppx == 0 && ppy == 0 && (zero_vector_residual_vanishes(e, mx, my, qp) || (e->bg_skip[mb] = (uint8_t)mb_is_static_background(e, mx, my, lambda)))) {
         OrcMbInfo *mi0 = &e->mbi[mb];
         mi0->mb_type = ORC_MB_P16x16; e->me[0][mb * 2] = e->me[0][mb * 2 + 1] = 0; e->inter_cost[mb] = 0;
         return;                              /* mbi was zeroed by the caller: mv = mv8 = 0 */
@@ -458,6 +500,13 @@ static void code_inter_mb(OrcEncoder *e, int mx, int my, int qp)
     const uint8_t *s = e->src[0] + (size_t)my * 16 * st + mx * 16; uint8_t *r = e->rec[0] + (size_t)my * 16 * st + mx * 16;
     int cbp = 0;
     memset(co, 0, sizeof *co);
+    if (e->bg_skip[mb]) {              /* static background: the prediction (the reference at the zero vector) IS the reconstruction */
+        int cs = st / 2;
+        for (int y = 0; y < 16; y++) memcpy(r + y * st, py + y * 16, 16);
+        for (int pl = 0; pl < 2; pl++) for (int y = 0; y < 8; y++) memcpy(e->rec[1 + pl] + (size_t)(my * 8 + y) * cs + mx * 8, pc + pl * 64 + y * 8, 8);
+        memset(mi->nnz, 0, sizeof mi->nnz); mi->cbp = 0;
+        return;
+    }
     for (int b = 0; b < 16; b++) {
         int bx = BLK_X[b] * 4, by = BLK_Y[b] * 4; int16_t res[16], c[16]; int32_t d[16], rr[16];
         for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) res[y * 4 + x] = (int16_t)(s[(by + y) * st + bx + x] - py[(by + y) * 16 + bx + x]);
@@ -1165,7 +1214,8 @@ static int encode_frame(OrcEncoder *e, const uint8_t *i420, int frame_type, int 
         o += 5 + orc_escape_rbsp(e->rbsp, b.pos, out + o + 5);
     }
     e->last_idr = is_idr;
-    if (!commit) { e->frame_num = frame_num_in; return o; }      /* a trial leaves the stream state (reference, frame_num, idr_pic_id) untouched */
+    if (!commit) { e->frame_num = frame_num_in; return o; }
+    e->src_committed = 1;      /* a trial leaves the stream state (reference, frame_num, idr_pic_id) untouched */
     /* the deblocked picture becomes the reference of the next frame */
     for (int c = 0; c < 3; c++) memcpy(e->ref[c], e->dbk[c], (size_t)(c ? e->wc / 2 * e->hc / 2 : e->wc * e->hc));
     e->have_ref = 1; e->frame_num = (e->frame_num + 1) & 255;

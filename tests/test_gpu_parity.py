@@ -561,6 +561,47 @@ def test_scene_change_idr_matches_the_oracle(enc, orc):
         g.close()
 
 
+@pytest.mark.parametrize("profile", [0, 1, 2])
+def test_background_detection_matches_the_oracle(enc, orc, profile):
+    """bEnableBackgroundDetection (VideoEncoderOpenH264.cpp:282): a static scene with sensor noise and one moving object (content E). Macroblocks
+    that are static against the previous SOURCE picture are skipped; bit-exact with the oracle's definition, and it must change the stream"""
+    w, h, qp = 640, 368, 30
+    c = Content("E", w, h)
+    g = enc.Session(w, h, const_qp=qp, gop=1000, device=0, background_detection=1, profile=profile)
+    g0 = enc.Session(w, h, const_qp=qp, gop=1000, device=0, background_detection=0, profile=profile)
+    o = orc.Encoder(w, h, background_detection=1, profile=profile)
+    on = off = 0
+    for t in range(7):
+        f = c.frame(t)
+        bs, _ = g.encode(f); ref = o.encode(f, t == 0, qp)
+        assert bs == ref, f"frame {t}: bitstream"
+        assert np.array_equal(g.recon(), o.recon()), f"frame {t}: reconstruction"
+        assert np.array_equal(g.stage("mbinfo")["mb_type"], o.mb_info()["mb_type"])
+        on += len(bs); off += len(g0.encode(f)[0])
+    assert on < off, (on, off)
+    g.close(); g0.close()
+
+
+@pytest.mark.parametrize("complexity", [0, 1, 2])
+def test_complexity_modes_match_the_oracle(enc, orc, complexity):
+    """iComplexityMode (the wrapper asks for HIGH_COMPLEXITY, VideoEncoderOpenH264.cpp:289): LOW drops the Intra_4x4 trial and P_8x8, MEDIUM drops
+    P_8x8; bit-exact with the oracle in each mode, and the modes differ"""
+    w, h, qp = 352, 288, 28
+    c = Content("A", w, h)
+    g = enc.Session(w, h, const_qp=qp, gop=1000, device=0, complexity=complexity)
+    o = orc.Encoder(w, h, complexity=complexity)
+    for t in range(4):
+        f = c.frame(t)
+        bs, _ = g.encode(f)
+        assert bs == o.encode(f, t == 0, qp), f"frame {t}"
+        mt = g.stage("mbinfo")["mb_type"]
+        assert np.array_equal(mt, o.mb_info()["mb_type"])
+        if t == 0:
+            assert (int((mt == 2).sum()) > 0) == (complexity >= 1)        # Intra_4x4 macroblocks only above LOW
+        assert complexity == 2 or int((mt == 4).sum()) == 0               # P_8x8 only at HIGH
+    g.close()
+
+
 def test_config1_portrait_720x1280_60_frames_const_qp26(enc, orc):
     """BASELINE.json configs[0]: 720x1280 portrait I420, 60 frames, Baseline CAVLC, const QP 26 -- the CUDA stream decodes to the
     encoder's reconstruction over all 60 frames and is bit-exact with the oracle on the first 6"""

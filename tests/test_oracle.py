@@ -458,3 +458,32 @@ def test_scene_change_turns_a_p_frame_into_an_idr(orc):
         assert (aus[11][4] == 0x67) == bool(detect) and aus[3][4] == 0x61
         dec = avdec.decode_stream(aus)
         assert len(dec) == 13 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+
+
+@needs_decoder
+@pytest.mark.parametrize("profile", [0, 2])
+def test_background_detection_streams_decode_and_save_bits(orc, profile):
+    """bEnableBackgroundDetection (VideoEncoderOpenH264.cpp:282), OUR definition: on a static scene with sensor noise and one moving
+    object the static macroblocks are skipped -- the stream still decodes to the oracle's reconstruction, costs far fewer bits, and the moving
+    object is still coded; complexity modes only remove tools (LOW: no Intra_4x4, no P_8x8)"""
+    w, h, qp = 320, 192, 28
+    c = Content("E", w, h)
+    on, off = orc.Encoder(w, h, background_detection=1, profile=profile), orc.Encoder(w, h, profile=profile)
+    aus, recs, b_on, b_off = [], [], 0, 0
+    for t in range(8):
+        f = c.frame(t)
+        a = on.encode(f, t == 0, qp); aus.append(a); recs.append(on.recon())
+        if t:
+            b_on += len(a); b_off += len(off.encode(f, False, qp))
+        else:
+            off.encode(f, True, qp)
+    dec = avdec.decode_stream(aus)
+    assert len(dec) == 8 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
+    assert b_on < 0.7 * b_off, (b_on, b_off)
+    mt = on.mb_info()["mb_type"]
+    assert (mt == 3).mean() > 0.8 and (mt != 3).sum() >= 2              # mostly P_Skip, the moving object is not
+    lo = orc.Encoder(w, h, complexity=0, profile=profile)
+    a = Content("A", w, h)
+    for t in range(3):
+        lo.encode(a.frame(t), t == 0, qp)
+        assert not np.isin(lo.mb_info()["mb_type"], [2, 4]).any()
