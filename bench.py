@@ -310,22 +310,12 @@ def run_b200(args):
         enc.check(L.b200k_int_peaks(dev, pk, 9))
         names = ["vabsdiff4", "iadd3", "lop3", "idp4a", "imad", "vimnmx+lop3", "iabs+2iadd", "shf", "satd4x4"]
         peak_tab = {n: {"gwarp_instr_s": round(pk[4 * i], 1), "per_clk_per_sm": round(pk[4 * i + 1], 3), "sm_mhz_in_run": round(pk[4 * i + 2], 1)} for i, n in enumerate(names)}
-        cls_peak = {"vabsdiff4": pk[0], "idp4a": pk[12], "alu": min(pk[4], pk[8]), "imad": pk[16], "shift": pk[28]}
-        fine_ops = {c: sum(v for (k, cc), v in ops.items() if cc == c and k != "coarse") for c in cls_peak}
-        coarse_ops = {c: sum(v for (k, cc), v in ops.items() if cc == c and k == "coarse") for c in cls_peak}
-
-        def int_roof(kname, by_class):
-            ms = ktd.get(kname, 0.0)
-            lane_ops = sum(by_class.values())
-            if ms <= 0 or lane_ops <= 0:
-                return None
-            warp_instr = lane_ops / 32.0 * nmb * Sp                     # at full lane use
-            t_peak = sum(v / 32.0 * nmb * Sp / (cls_peak[c] * 1e9) for c, v in by_class.items() if v)      # seconds at each class's own issue peak
-            ach = warp_instr / (ms * 1e-3) / 1e9
-            peak = warp_instr / t_peak / 1e9                              # mix-weighted (harmonic) issue peak of this operation mix
-            return {"kernel": kname, "ms": round(ms, 4), "lane_ops_per_mb": int(lane_ops), "warp_instr_per_mb": round(lane_ops / 32.0, 1),
-                    "achieved": round(ach, 1), "peak": round(peak, 1), "unit": "G warp-instr/s", "frac": round(ach / peak, 4)}
-        r_fine, r_coarse = int_roof("k_me_fine", fine_ops), int_roof("k_me_coarse", coarse_ops)
+        classes = ("vabsdiff4", "logic", "add", "idp4a", "imad")
+        fine_ops = {c: sum(v for (k, cc), v in ops.items() if cc == c and k != "coarse") for c in classes}
+        coarse_ops = {c: sum(v for (k, cc), v in ops.items() if cc == c and k == "coarse") for c in classes}
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        r_fine = int_roofline("k_me_fine", fine_ops, ktd.get("k_me_fine", 0.0), nmb * Sp, pk, sms)
+        r_coarse = int_roofline("k_me_coarse", coarse_ops, ktd.get("k_me_coarse", 0.0), nmb * Sp, pk, sms)
         # DRAM traffic and executed instructions of the dominant kernel from the committed `ncu --set full` capture of THIS round's binary
         # (profiles/r02_ncu_kernels.json, written by tools/final_capture.sh as the last step), scaled from its sessions per launch
         traffic, ncu_note = None, None
@@ -349,7 +339,9 @@ def run_b200(args):
             roofline = {"bound": "int-issue", "kernel": top[0], "share_of_step": round(top[1] / tot, 3), "achieved": roof_top["achieved"], "peak": roof_top["peak"],
                         "unit": roof_top["unit"], "frac": roof_top["frac"], "traffic": traffic, "lane_ops_per_mb": roof_top["lane_ops_per_mb"],
                         "ops_per_mb_by_class": {c: int(v) for c, v in fine_ops.items()} if top[0] == "k_me_fine" else {c: int(v) for c, v in coarse_ops.items()},
-                        "peak_is": "mix-weighted issue peak of the kernel's algorithmic operation classes, each class measured live (int_peaks)",
+                        "bound_by": roof_top["bound_by"], "issue_peak": roof_top["issue_peak"], "sm_mhz_in_peak_run": roof_top["sm_mhz_in_peak_run"],
+                        "peak_is": "the rate at which the SMs could retire exactly this algorithmic operation mix: max over (ALU-pipe-only work at its measured rate, "
+                                   "FMA-pipe-only work at its measured rate, all work at 4 warp-instructions per clock per SM, clock measured inside the microbenchmark)",
                         "hbm": {"achieved_gbs": round(ach_hbm, 1), "peak_gbs": hbm_peak, "frac": round(ach_hbm / hbm_peak, 4), "algorithmic_bytes_per_launch": int(alg_bytes)},
                         "ncu": ncu_note}
         else:
@@ -396,7 +388,9 @@ def run_b200(args):
 
 def me_ops_per_mb(sr):
     """ALGORITHMIC integer lane-operations per macroblock of the implemented P-picture path, keyed by (stage, instruction class).
-    Classes: vabsdiff4 (one op = 4 pixel absolute differences), idp4a, alu (add / logic / abs / min / max), imad, shift."""
+    Classes by the pipe that can execute them on sm_100a (measured, int_peaks): vabsdiff4 (ALU pipe, one op = 4 pixel absolute differences),
+    logic (ALU pipe only: LOP3 / IABS / VIMNMX / SHF), idp4a and imad (FMA pipe only), add (either pipe: IADD3 on the ALU pipe, IMAD.IADD on the
+    FMA pipe -- the compiler balances them)."""
     o = {}
     r4 = sr // 4
     # k_me_coarse: level 2 = (2 R/4 + 1)^2 candidates x 8x8 px, level 1 = 25 x 8x8 px; a VABSDIFF4 covers 4 px
@@ -404,17 +398,40 @@ def me_ops_per_mb(sr):
     # k_me_fine: level 0 = 25 candidates + the zero vector, 16x16 px each
     o[("sad0", "vabsdiff4")] = 26 * 256 / 4
     # SATD: 17 sub-pel candidates + 3 intra-estimate predictors, 16 4x4 blocks each; per block 16 IDP.4A (horizontal transform with the
-    # source folded in), 16 add/sub (vertical butterflies), 8 abs + 4 max + 4 add (|x+y| + |x-y| = 2 max(|x|, |y|))
+    # source folded in), 16 add/sub (vertical butterflies), 8 abs + 4 max (|x+y| + |x-y| = 2 max(|x|, |y|)), 4 add
     nb = 20 * 16
-    o[("satd", "idp4a")] = nb * 16; o[("satd", "alu")] = nb * (16 + 8 + 4 + 4)
-    # quarter-pel prediction: 8 candidates x 64 words, per-byte rounded average = 4 logic/add ops; the 9 half-pel candidates are plain fetches
-    o[("qpel", "alu")] = 8 * 64 * 4
-    # final MC: luma average (64 words x 4) + chroma bilinear 128 px x (4 IMAD + 1 shift)
-    o[("mc", "alu")] = 64 * 4; o[("mc", "imad")] = 128 * 4; o[("mc", "shift")] = 128
-    # transform / quant / recon of 24 4x4 blocks (240 ops per block): fwd 64 add, quant 16 mul + 16 add + 16 shift, dequant 16 mul,
+    o[("satd", "idp4a")] = nb * 16; o[("satd", "add")] = nb * (16 + 4); o[("satd", "logic")] = nb * (8 + 4)
+    # quarter-pel prediction: 8 candidates x 64 words, per-byte rounded average = 3 logic/shift + 1 add; the 9 half-pel candidates are plain fetches
+    o[("qpel", "logic")] = 8 * 64 * 3; o[("qpel", "add")] = 8 * 64
+    # final MC: luma average (64 words) + chroma bilinear 128 px x (4 multiply-adds + 1 shift)
+    o[("mc", "logic")] = 64 * 3; o[("mc", "add")] = 64; o[("mc", "imad")] = 128 * 4; o[("mc", "logic2")] = 128
+    # transform / quant / recon of 24 4x4 blocks (240 ops per block): fwd 64 add, quant 16 mul-add + 16 shift, dequant 16 mul,
     # inverse 64 add + 16 shift, recon 16 add + 32 min/max
-    o[("tq", "alu")] = 24 * (64 + 16 + 64 + 16 + 32); o[("tq", "imad")] = 24 * 32; o[("tq", "shift")] = 24 * 32
-    return o
+    o[("tq", "add")] = 24 * (64 + 64 + 16); o[("tq", "imad")] = 24 * 32; o[("tq", "logic")] = 24 * (16 + 16 + 32)
+    return {(k, "logic" if c == "logic2" else c): v for (k, c), v in o.items()}
+
+
+def int_roofline(kname, by_class, ms, n_mb, pk, sms):
+    """by_class: algorithmic lane-operations per MB per class. Peak = the fastest the two integer pipes and the four issue slots of every SM could
+    retire exactly this operation mix: time >= max(ALU-pipe-only work / its measured rate, FMA-pipe-only work / its measured rate, all work /
+    (4 warp-instructions per clock per SM at the clock measured inside the microbenchmark))."""
+    lane_ops = sum(by_class.values())
+    if ms <= 0 or lane_ops <= 0:
+        return None
+    w = {c: v / 32.0 * n_mb for c, v in by_class.items()}                  # warp-instructions at full lane use
+    rate = lambda i: pk[4 * i] * 1e9
+    clk = max(pk[4 * i + 2] for i in range(5)) * 1e6
+    issue = 4.0 * sms * clk
+    t_alu = w.get("vabsdiff4", 0) / rate(0) + w.get("logic", 0) / rate(2)
+    t_fma = (w.get("idp4a", 0) + w.get("imad", 0)) / min(rate(3), rate(4))
+    t_all = sum(w.values()) / issue
+    t_peak = max(t_alu, t_fma, t_all)
+    total = sum(w.values())
+    ach = total / (ms * 1e-3) / 1e9
+    return {"kernel": kname, "ms": round(ms, 4), "lane_ops_per_mb": int(lane_ops), "warp_instr_per_mb": round(lane_ops / 32.0, 1),
+            "achieved": round(ach, 1), "peak": round(total / t_peak / 1e9, 1), "unit": "G warp-instr/s", "frac": round(ach / (total / t_peak / 1e9), 4),
+            "bound_by": "issue slots" if t_peak == t_all else "ALU pipe" if t_peak == t_alu else "FMA pipe",
+            "issue_peak": round(issue / 1e9, 1), "sm_mhz_in_peak_run": round(clk / 1e6, 1)}
 
 
 class E2EResult(__import__("ctypes").Structure):
