@@ -590,7 +590,8 @@ struct DeviceScheduler {
             // lone caller pays at most that). With two or more in flight the GPU is busy anyway, so wait for the fuller batch -- until enough
             // callers arrived, a running batch finished, or fill_us passed. Leaves at once when every session not being encoded is waiting.
             const auto t0 = std::chrono::steady_clock::now();
-            const int target = std::max(1, std::min(std::min(ctx[w]->cap, batch_max), (registered + batch_div - 1) / batch_div));
+            // a batch aims at a quarter of the GPU's sessions, never fewer than 8 (a handful of sessions travels together), never more than batch_max
+            const int target = std::max(1, std::min(std::min(ctx[w]->cap, batch_max), std::max((registered + batch_div - 1) / batch_div, std::min(registered, 8))));
             while (!stop && !pending.empty()) {
                 const int want = std::min(target, std::max(1, registered - inflight));
                 if ((int)pending.size() >= want) break;

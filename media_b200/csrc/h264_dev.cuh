@@ -9,7 +9,8 @@
 
 namespace b200 {
 
-enum { MB_P16x16 = 0, MB_I16x16 = 1, MB_I4x4 = 2, MB_PSKIP = 3, MB_P8x8 = 4 };
+enum { MB_P16x16 = 0, MB_I16x16 = 1, MB_I4x4 = 2, MB_PSKIP = 3, MB_P8x8 = 4,
+       MB_I8x8 = 5 /* I_NxN with transform_size_8x8_flag = 1 (High profile): Intra8x8PredMode of block b in i4_mode[4b .. 4b+3] */ };
 
 // Per-MB side information, 48 bytes. nnz: 0..15 luma blkIdx, 16..19 Cb, 20..23 Cr.
 struct __align__(16) MbInfo {

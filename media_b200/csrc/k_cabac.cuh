@@ -132,7 +132,8 @@ template <int W> __device__ void bin_residual8(BinSink<W> &s, const int16_t *lv)
     }
 }
 
-__device__ __forceinline__ bool is_intra_type(int t) { return t == MB_I16x16 || t == MB_I4x4; }
+__device__ __forceinline__ bool is_intra_type(int t) { return t == MB_I16x16 || t == MB_I4x4 || t == MB_I8x8; }
+__device__ __forceinline__ bool is_inxn_type(int t) { return t == MB_I4x4 || t == MB_I8x8; }
 
 // grid: (ceil(n_mb / 256), 1, sessions)
 __global__ void __launch_bounds__(256) k_cabac_side(const Sess *ss, Geom g)
@@ -153,12 +154,23 @@ __global__ void __launch_bounds__(256) k_cabac_side(const Sess *ss, Geom g)
     } else if (t == MB_I4x4) {
         const bool left = mx > 0, top = !row_is_slice_top(g, my);
         const MbInfo *ml = mi - 1, *mt = mi - g.mbw;
-        const bool l4 = left && ml->mb_type == MB_I4x4, t4 = top && mt->mb_type == MB_I4x4;
+        const bool l4 = left && is_inxn_type(ml->mb_type), t4 = top && is_inxn_type(mt->mb_type);
         for (int k = 0; k < 16; k++) {       // predIntra4x4PredMode, 8.3.1.1
             const int bx = blk_x(k), by = blk_y(k);
             const int ma = bx > 0 ? mi->i4_mode[xy2blk(bx - 1, by)] : !left ? -1 : l4 ? ml->i4_mode[xy2blk(3, by)] : 2;
             const int mb_ = by > 0 ? mi->i4_mode[xy2blk(bx, by - 1)] : !top ? -1 : t4 ? mt->i4_mode[xy2blk(bx, 3)] : 2;
             const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_), m = mi->i4_mode[k];
+            sd.i4_syn[k] = (uint8_t)(m == pm ? 8 : m < pm ? m : m - 1);
+        }
+    }
+    else if (t == MB_I8x8) {                 // predIntra8x8PredMode, 8.3.2.1: the neighbouring I_NxN macroblock's mode at the block's first row / column
+        const bool left = mx > 0, top = !row_is_slice_top(g, my);
+        const MbInfo *ml = mi - 1, *mt = mi - g.mbw;
+        const bool l4 = left && is_inxn_type(ml->mb_type), t4 = top && is_inxn_type(mt->mb_type);
+        for (int k = 0; k < 4; k++) {
+            const int ma = (k & 1) ? mi->i4_mode[4 * (k - 1) + 1] : !left ? -1 : l4 ? ml->i4_mode[4 * (k + 1) + 1] : 2;
+            const int mb_ = (k & 2) ? mi->i4_mode[4 * (k - 2) + 2] : !top ? -1 : t4 ? mt->i4_mode[4 * (k + 2) + 2] : 2;
+            const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_), m = mi->i4_mode[4 * k];
             sd.i4_syn[k] = (uint8_t)(m == pm ? 8 : m < pm ? m : m - 1);
         }
     }
@@ -194,7 +206,7 @@ template <int W> __device__ void bin_mb_header(BinSink<W> &s, const Sess &se, co
     } else {
         int b0, c_cl, c_cc, c_cc2, c_m1, c_m0;
         if (is_p) { s.put(14, 1); b0 = 17; c_cl = 18; c_cc = 19; c_cc2 = 19; c_m1 = 20; c_m0 = 20; }
-        else { b0 = 3 + (L && L->mb_type != MB_I4x4) + (T && T->mb_type != MB_I4x4); c_cl = 6; c_cc = 7; c_cc2 = 8; c_m1 = 9; c_m0 = 10; }
+        else { b0 = 3 + (L && !is_inxn_type(L->mb_type)) + (T && !is_inxn_type(T->mb_type)); c_cl = 6; c_cc = 7; c_cc2 = 8; c_m1 = 9; c_m0 = 10; }
         s.put(b0, t == MB_I16x16);
         if (t == MB_I16x16) {
             s.put(276, 0);
@@ -205,9 +217,9 @@ template <int W> __device__ void bin_mb_header(BinSink<W> &s, const Sess &se, co
     }
     // transform_size_8x8_flag (7.3.5; ctxIdx 399 + the neighbours' flags): 0 for I_NxN (Intra_4x4 only), coded for inter MBs behind the cbp
     const int t8inc = (L && mb_t8(L)) + (T && mb_t8(T));
-    if (t == MB_I4x4 && se.t8x8) s.put(399 + t8inc, 0);
-    if (t == MB_I4x4)
-        for (int k = 0; k < 16; k++) {
+    if (is_inxn_type(t) && se.t8x8) s.put(399 + t8inc, t == MB_I8x8);
+    if (is_inxn_type(t))
+        for (int k = 0; k < (t == MB_I8x8 ? 4 : 16); k++) {      // prev_intra{4x4,8x8}_pred_mode_flag / rem_...: same contexts
             const int r = sd->i4_syn[k];
             s.put(68, r == 8);
             if (r != 8) { s.put(69, r & 1); s.put(69, (r >> 1) & 1); s.put(69, (r >> 2) & 1); }

@@ -88,7 +88,7 @@ __device__ __forceinline__ void filter_edge(uint8_t *p, int step, int bs, int al
 // boundary strength between 4x4 block (bxp,byp) of MB p and block (bxq,byq) of MB q (8.7.2.1, frame pictures, one reference)
 __device__ __forceinline__ int bs_of(const MbInfo *p, int bxp, int byp, const MbInfo *q, int bxq, int byq, bool mb_edge)
 {
-    const bool ip = p->mb_type == MB_I16x16 || p->mb_type == MB_I4x4, iq = q->mb_type == MB_I16x16 || q->mb_type == MB_I4x4;
+    const bool ip = p->mb_type == MB_I16x16 || p->mb_type == MB_I4x4 || p->mb_type == MB_I8x8, iq = q->mb_type == MB_I16x16 || q->mb_type == MB_I4x4 || q->mb_type == MB_I8x8;
     if (ip || iq) return mb_edge ? 4 : 3;
     if (p->nnz[xy2blk(bxp, byp)] || q->nnz[xy2blk(bxq, byq)]) return 2;
     const int16_t *vp = p->mv8[(byp >> 1) * 2 + (bxp >> 1)], *vq = q->mv8[(byq >> 1) * 2 + (bxq >> 1)];

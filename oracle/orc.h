@@ -30,7 +30,7 @@ extern "C" {
 
 /* ---- macroblock types used in the per-MB side arrays (shared layout with the CUDA path) ---- */
 enum { ORC_MB_P16x16 = 0, ORC_MB_I16x16 = 1, ORC_MB_I4x4 = 2, ORC_MB_PSKIP = 3, ORC_MB_P8x8 = 4,
-       ORC_MB_I8x8 = 5 /* I_NxN with transform_size_8x8_flag = 1; oracle only so far (OrcConfig.intra8x8), the CUDA path does not produce it */ };
+       ORC_MB_I8x8 = 5 /* I_NxN with transform_size_8x8_flag = 1 (High profile) */ };
 #define ORC_MB_IS_INTRA(m) ((m)->mb_type == ORC_MB_I16x16 || (m)->mb_type == ORC_MB_I4x4 || (m)->mb_type == ORC_MB_I8x8)
 #define ORC_MB_IS_INXN(m) ((m)->mb_type == ORC_MB_I4x4 || (m)->mb_type == ORC_MB_I8x8)
 
@@ -88,8 +88,8 @@ typedef struct {
     int no_t8x8;             /* 1: High profile without the 8x8 transform (transform_8x8_mode_flag = 0; quality A/B runs) */
     int background_detection;/* 1: static macroblocks (against the previous source picture) are skipped (b200enc_config.background_detection) */
     int complexity_set, complexity; /* complexity_set = 1: iComplexityMode 0 LOW (no Intra_4x4 trial, no P_8x8), 1 MEDIUM (no P_8x8), 2 HIGH */
-    int intra8x8;            /* 1: High profile intra MBs may also take Intra_8x8 (8.3.2). GROUNDWORK for the next round: pinned by the decoder
-                                round trip on the CPU, not yet built in CUDA, so the product and every parity test run with 0 */
+    int intra8x8;            /* 1 (what the product does): High profile intra MBs may also take Intra_8x8 (8.3.2), tried before Intra_4x4 and chosen
+                                against it by J = 64 SSD + 27 lambda^2 B; 0: Intra_4x4 / Intra_16x16 only (quality A/B runs) */
 } OrcConfig;
 #define ORC_BGD_OU_SAD 128       /* background detection: largest SAD of an 8x8 unit against the previous source picture (mean |d| <= 2) */
 #define ORC_BGD_MAXDIFF 12       /* ... and largest single sample difference */
@@ -159,6 +159,8 @@ void orc_deblock_frame(uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs, int m
                        const OrcMbInfo *mbi, int qp);
 /* Intra_4x4 predictor of one block (8.3.1.2); avail bits: 1 top, 2 left, 4 corner, 8 top-right. Returns 0 if the mode is unavailable */
 int  orc_pred_i4(const uint8_t *r, int stride, int mode, int avail, uint8_t *pred16);
+/* Intra_8x8 predictor of one block (8.3.2.2, reference sample filter included); avail bits as orc_pred_i4. Returns 0 if the mode is unavailable */
+int  orc_pred_i8(const uint8_t *r, int stride, int mode, int avail, uint8_t *pred64);
 /* emulation prevention: returns output length */
 int  orc_escape_rbsp(const uint8_t *in, int n, uint8_t *out);
 

@@ -22,7 +22,7 @@
 #define ORC_MB_BINS_MAX 4096   /* bound of one MB's bin list: 384 levels of at most 2 + 14 + 27 + 1 bins (|level| <= 2064) is far above real use; checked */
 #define HP_M 4   /* margin of the half-pel planes, see build_halfpel() */
 #define T8X8_ON(e) ((e)->cfg.profile == 2 && !(e)->cfg.no_t8x8)   /* PPS transform_8x8_mode_flag */
-#define I8X8_ON(e) (T8X8_ON(e) && (e)->cfg.intra8x8)                /* Intra_8x8 on trial (oracle-only groundwork) */
+#define I8X8_ON(e) (T8X8_ON(e) && (e)->cfg.intra8x8)                /* Intra_8x8 on trial (High profile) */
 
 struct OrcEncoder {
     OrcConfig cfg;
@@ -723,7 +723,7 @@ static int code_intra4x4_luma(OrcEncoder *e, int mx, int my, int qp, int lambda)
     return total;
 }
 
-/* ---- Intra_8x8 (High profile), 8.3.2. GROUNDWORK: oracle only (OrcConfig.intra8x8), pinned by the decoder round trip. ----
+/* ---- Intra_8x8 (High profile), 8.3.2; pinned by the decoder round trip. ----
  * Reference samples of an 8x8 block with the filtering of 8.3.2.2.1: T[0..15] = p'[x,-1], L[0..7] = p'[-1,y], X = p'[-1,-1].
  * avail: I4_AV_T / _L / _X / _TR as for Intra_4x4 (top-right missing: p[8..15,-1] = p[7,-1]). */
 typedef struct { int T[16], L[8], X, top, left, corner; } I8Ref;
@@ -817,6 +817,8 @@ static int pred_i8(const I8Ref *f, int mode, uint8_t *p /*64*/)
 #undef PT8
 #undef PL8
 }
+/* kernel-level oracle of the Intra_8x8 predictors: r = the block's top-left sample inside a reconstruction with its neighbours, avail bits as orc_pred_i4 */
+int orc_pred_i8(const uint8_t *r, int stride, int mode, int avail, uint8_t *pred64) { I8Ref ref; i8_reference(r, stride, avail, &ref); return pred_i8(&ref, mode, pred64); }
 /* predIntra8x8PredMode of 8x8 block b (8.3.2.1): the neighbouring I_NxN MB's mode of the 4x4 block 4 * blk8 + 1 (left) / + 2 (above);
  * Intra_8x8 MBs keep their block modes in all four entries, so one lookup serves both kinds */
 static int i8_pred_mode(const OrcEncoder *e, int mx, int my, int b)

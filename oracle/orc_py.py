@@ -73,6 +73,7 @@ def lib():
         L.orc_interp_luma.restype = C.c_int; L.orc_interp_luma.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_interp_chroma.restype = C.c_int; L.orc_interp_chroma.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_deblock_frame.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_pred_i8.restype = C.c_int; L.orc_pred_i8.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
         L.orc_escape_rbsp.restype = C.c_int; L.orc_escape_rbsp.argtypes = [vp, C.c_int, vp]
         _lib = L
     return _lib
@@ -85,7 +86,7 @@ def _p(a):
 class Encoder:
     """One oracle session: encode(i420, idr, qp) -> Annex-B bytes; stage dumps as numpy arrays."""
 
-    def __init__(self, width, height, num_slices=1, search_range=16, fps=30, level_idc=0, no_i4x4=0, no_p8x8=0, scene_change=1, profile=0, no_t8x8=0, intra8x8=0,
+    def __init__(self, width, height, num_slices=1, search_range=16, fps=30, level_idc=0, no_i4x4=0, no_p8x8=0, scene_change=1, profile=0, no_t8x8=0, intra8x8=1,
                  background_detection=0, complexity=None):
         self.L = lib()
         self.cfg = OrcConfig(width, height, num_slices, search_range, level_idc, fps, no_i4x4, no_p8x8, 0 if scene_change else 1, profile, no_t8x8,

@@ -218,7 +218,9 @@ def test_high_profile_8x8_transform_streams_decode(orc, w, h, kind, qp, slices):
         f = c.frame(t)
         aus.append(o.encode(f, t == 0, qp)); recs.append(o.recon()); o4.encode(f, t == 0, qp)
         mi = o.mb_info(); t8 = (mi["i16_mode"] >> 2) & 1
-        assert not t8[(mi["mb_type"] != 0) & (mi["mb_type"] != 4)].any() and ((mi["cbp"][t8 == 1] & 15) != 0).all()
+        inter = (mi["mb_type"] == 0) | (mi["mb_type"] == 4)
+        assert not t8[~inter & (mi["mb_type"] != 5)].any() and t8[mi["mb_type"] == 5].all()      # inter MBs by choice, Intra_8x8 MBs always
+        assert ((mi["cbp"][(t8 == 1) & inter] & 15) != 0).all()
         for m in np.flatnonzero(t8):                               # the four nnz of an 8x8 block carry its level count
             assert all(len(set(mi["nnz"][m][4 * b: 4 * b + 4])) == 1 for b in range(4))
         n8 += int(t8.sum())
@@ -487,3 +489,62 @@ def test_background_detection_streams_decode_and_save_bits(orc, profile):
     for t in range(3):
         lo.encode(a.frame(t), t == 0, qp)
         assert not np.isin(lo.mb_info()["mb_type"], [2, 4]).any()
+
+
+def i8_filtered_edge(rec, st, o, avail):
+    """numpy model of what the CUDA path does for one Intra_8x8 block: the raw edge L7..L0 X T0..T15 with the substitutions for missing
+    neighbours, then the reference sample filter of 8.3.2.2.1 as ONE three-tap pass with doubled ends; returns (E', top, left, corner)"""
+    top, left, corner, tr = bool(avail & 1), bool(avail & 2), bool(avail & 4), bool(avail & 8)
+    t = [int(rec[o - st + i]) if top and (i < 8 or tr) else (int(rec[o - st + 7]) if top else 128) for i in range(16)]
+    l = [int(rec[o + i * st - 1]) if left else 128 for i in range(8)]
+    x = int(rec[o - st - 1]) if corner else 128
+    raw = l[::-1] + [x] + t                                    # E index: L[i] = 7 - i, X = 8, T[i] = 9 + i
+    E = list(raw)
+    for k in range(25):
+        a = raw[k - 1] if k > 0 else raw[0]
+        d = raw[k + 1] if k < 24 else raw[24]
+        if k == 7 and not corner: d = raw[7]                   # L'[0] without the corner: (3 l0 + l1 + 2) >> 2
+        if k == 9 and not corner: a = raw[9]                   # T'[0] without the corner
+        f = (a + 2 * raw[k] + d + 2) >> 2
+        if k < 8: E[k] = f if left else 128
+        elif k == 8:
+            E[k] = f if (corner and top and left) else ((3 * x + t[0] + 2) >> 2 if corner and top else (3 * x + l[0] + 2) >> 2 if corner and left else x)
+        else: E[k] = f if top else 128
+    return E, top, left, corner
+
+
+def test_intra8x8_lookup_tables_reproduce_the_oracle_predictors(orc):
+    """media_b200/csrc/i8_tables.cuh (tools/make_i8_tables.py): the nine Intra_8x8 predictors as lookups into the one / two / three-tap tables of the
+    filtered edge, against the oracle's direct transcription of 8.3.2.2.1-10 (orc_pred_i8), for every availability combination"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_i8_tables as mk
+    gen = open(os.path.join(ROOT, "media_b200", "csrc", "i8_tables.cuh")).read()
+    words = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{8})u", gen)]
+    flat = [b for w in words for b in (w & 255, (w >> 8) & 255, (w >> 16) & 255, w >> 24)]
+    assert flat == [v for m in range(9) for v in mk.TABLE[m]], "i8_tables.cuh is stale: run tools/make_i8_tables.py"
+    rng = np.random.default_rng(88)
+    st = 40
+    L = orc.lib()
+    for trial in range(60):
+        rec = rng.integers(0, 256, st * 24, dtype=np.uint8) if trial % 3 else np.full(st * 24, rng.integers(0, 256), np.uint8)
+        o = 9 * st + 9
+        for avail in (0, 1, 2, 3, 7, 15, 5 | 2, 1 | 8, 3 | 8):
+            if (avail & 4) and (avail & 3) != 3: continue
+            if (avail & 8) and not (avail & 1): continue
+            E, top, left, corner = i8_filtered_edge(rec, st, o, avail)
+            Ed = [E[0]] + E + [E[24], E[24]]                                    # E[-1] .. E[26] with doubled ends
+            F = {}
+            for k in range(25):
+                F[k] = E[k]; F[64 + k] = (Ed[k] + 2 * Ed[k + 1] + Ed[k + 2] + 2) >> 2
+                if k < 24: F[32 + k] = (E[k] + E[k + 1] + 1) >> 1
+            sT, sL = sum(E[9:17]), sum(E[0:8])
+            F[95] = (sT + sL + 8) >> 4 if top and left else (sT + 4) >> 3 if top else (sL + 4) >> 3 if left else 128
+            for m in range(9):
+                want = np.zeros(64, np.uint8)
+                ok = L.orc_pred_i8(rec.ctypes.data + o, st, m, avail, want.ctypes.data)
+                allowed = m == 2 or ((m in (0, 3, 7)) and top) or ((m in (1, 8)) and left) or ((m in (4, 5, 6)) and top and left and corner)
+                assert bool(ok) == allowed, (m, avail)
+                if ok:
+                    got = np.array([F[i] for i in mk.TABLE[m]], np.uint8)
+                    assert np.array_equal(got, want), (trial, avail, m, got.reshape(8, 8), want.reshape(8, 8))

@@ -64,7 +64,7 @@ int main(int argc, char **argv)
         // sessions start staggered over the first frame period (capture clocks of different phones are not aligned)
         auto next = t_start + std::chrono::nanoseconds((long long)(period.count() * (double)i / N));
         const auto t_end = t_start + std::chrono::nanoseconds((long long)(seconds * 1e9));
-        int k = i;
+        int k = 1;          // the untimed first frame was pool[0]: continue with its temporal neighbour (a jump would be a scene cut, not steady state)
         while (next < t_end) {
             std::this_thread::sleep_until(next);
             const auto t0 = clk::now();
@@ -72,7 +72,7 @@ int main(int argc, char **argv)
             const int p = k % (2 * POOL - 2), idx = p < POOL ? p : 2 * POOL - 2 - p; k++;
             // IDR phases are spread over the GOP like sessions that started at different times: session i refreshes at frame
             // (37 i) mod 300 of the run and every 300 frames after that
-            if ((k - i) == (37 * i) % 300) { b200enc_force_idr(sess[i]); idr_frames++; }
+            if ((k - 1) == (37 * i) % 300) { b200enc_force_idr(sess[i]); idr_frames++; }
             if (b200enc_encode(sess[i], pool[idx], (uint32_t)fb, &bs, &n, nullptr) != 0) errors++;
             const auto t1 = clk::now();
             lat[i].push_back(std::chrono::duration<float, std::milli>(t1 - t0).count());
