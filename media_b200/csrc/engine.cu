@@ -163,7 +163,7 @@ struct b200enc_session {
     void *tmaps;                                 // CUtensorMap[3] in HBM
     MbInfo *mbi; MbCoef *coef; uint4 *dbk_bs; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
     uint32_t *mb_bits, *mb_off, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
-    MbSide *side; uint16_t *bins; uint32_t *slice_nbins;   // CABAC (profile main / high)
+    MbSide *side; uint16_t *bins, *bins_mb, *bin_lane_cnt, *bins_hdr; uint32_t *slice_nbins;   // CABAC (profile main / high)
     uint32_t rbsp_words_per_slice = 0;
     std::vector<uint8_t> param_sets;
     // pinned, device-mapped output: [0..cap) bitstream, then one uint32 size
@@ -370,7 +370,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         }
         d.mbi = s->mbi; d.coef = s->coef; d.dbk_bs = s->dbk_bs; d.me2 = s->me2; d.me1 = s->me1; d.me0 = s->me0; d.inter_cost = s->inter_cost;
         d.skip_run = s->skip_run; d.mb_bits = s->mb_bits; d.mb_off = s->mb_off; d.mb_slot = s->mb_slot; d.rbsp = s->rbsp; d.slice_bits = s->slice_bits;
-        d.side = s->side; d.bins = s->bins; d.slice_nbins = s->slice_nbins;
+        d.side = s->side; d.bins = s->bins; d.bins_mb = s->bins_mb; d.bin_lane_cnt = s->bin_lane_cnt; d.bins_hdr = s->bins_hdr; d.slice_nbins = s->slice_nbins;
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
         d.qp = qps[i]; d.is_idr = idr; d.frame_num = idr ? 0 : s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
@@ -440,17 +440,19 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     if (ss[0]->cfg.profile) {
         // CABAC: side records, entry counts, offsets, bin lists (all parallel over MBs), then one warp per slice runs the coder
         const dim3 gb((nmb + CABAC_WARPS - 1) / CABAC_WARPS, 1, n);
+        static const int xskip = [] { const char *e = getenv("B200ENC_X_SKIP"); return e ? atoi(e) : 0; }();    // timing experiments only (output invalid)
         pf.begin("k_cabac_side", s2); k_cabac_side<<<dim3((nmb + 255) / 256, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
-        pf.begin("k_cabac_count", s2); k_cabac_bins<0><<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_hdr", s2); k_cabac_hdr<<<dim3((nmb + 255) / 256, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_bins", s2); if (!(xskip & 1)) k_cabac_bins<<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
         pf.begin("k_cabac_scan", s2); k_cabac_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
-        pf.begin("k_cabac_bins", s2); k_cabac_bins<1><<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_compact", s2); if (!(xskip & 2)) k_cabac_compact<<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
         // the coder threads are latency chains: every slot they lose to a co-resident throughput kernel's warps stretches the frame. Asking for
         // a slab of dynamic shared memory they do not use keeps the shared-memory-hungry kernels of the other batches off their SMs
         // (paced sessions: small batches, tail latency counts). Big batches are throughput work: there the slab only takes shared memory
         // from the other batches' motion search (96 x 1080p Main in batches of 32: 8 550 frames/s with it, 9 380 without)
         const int hog_kb = n <= 16 ? cabac_slab_kb() : 0;
-        pf.begin("k_cabac_code", s2); k_cabac_code<<<dim3(g.num_slices, 1, n), 96, (size_t)hog_kb * 1024, s2>>>(b->d_sess, g); pf.end();
-        launches += 5;
+        pf.begin("k_cabac_code", s2); if (!(xskip & 4)) k_cabac_code<<<dim3(g.num_slices, 1, n), 96, (size_t)hog_kb * 1024, s2>>>(b->d_sess, g); pf.end();
+        launches += 6;
     } else {
     pf.begin("k_cavlc_mb", s2); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_slice_scan", s2); k_slice_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
@@ -795,6 +797,9 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         add(s->rbsp, (size_t)s->rbsp_words_per_slice * g.num_slices * 4);
         add(s->side, c.profile ? nmb * sizeof(MbSide) : 16); add(s->slice_nbins, B200_MAX_SLICES * 4);
         add(s->bins, c.profile ? (nmb * B200_MB_BIN_SLOT + 64) * sizeof(uint16_t) : 16);
+        add(s->bins_mb, c.profile ? (nmb * CABAC_MB_SLOT + 64) * sizeof(uint16_t) : 16);
+        add(s->bin_lane_cnt, c.profile ? nmb * 32 * sizeof(uint16_t) : 16);
+        add(s->bins_hdr, c.profile ? nmb * CABAC_HDR_SLOT * sizeof(uint16_t) : 16);
         add(s->slice_bits, B200_MAX_SLICES * 4); add(s->hdr, 256); add(s->row_prog, (size_t)g.mbh * 2 * 4);
         size_t total = 0;
         for (auto &it : items) total += align_up(it.bytes, 256);

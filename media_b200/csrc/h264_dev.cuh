@@ -84,6 +84,9 @@ struct Sess {
     // CABAC (profile main / high): side records, the slices' bin lists (slice base = first MB * B200_MB_BIN_SLOT entries; mb_bits /
     // mb_off then hold every MB's entry count / offset inside its slice's list), entries per slice
     MbSide *side; uint16_t *bins; uint32_t *slice_nbins;
+    uint16_t *bins_mb;            // per-MB slots (CABAC_MB_SLOT entries, one sub-slot per syntax-group lane) the bin kernel writes before the lists are compacted
+    uint16_t *bin_lane_cnt;       // per MB: the 32 lanes' entry counts
+    uint16_t *bins_hdr;           // per MB: the header entries (CABAC_HDR_SLOT each), written by k_cabac_hdr
     uint8_t *out;                 // Annex-B access unit (mapped pinned host memory or HBM)
     uint32_t *out_size;           // bytes written to out
     const uint8_t *hdr; int hdr_len;   // SPS+PPS NALs, prepended on IDR

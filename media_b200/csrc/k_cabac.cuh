@@ -290,39 +290,67 @@ __device__ __forceinline__ CabacItem cabac_item(const Sess &se, const Geom &g, i
 }
 
 #define CABAC_WARPS 8
-// grid: (ceil(n_mb / CABAC_WARPS), 1, sessions). WRITE = 0: mb_bits[mb] = number of entries of the MB. WRITE = 1: the entries are
-// stored at bins[slice base + mb_off[mb]]; the slice base is first_mb * B200_MB_BIN_SLOT (room for the worst case of every MB).
-template <int WRITE> __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac_bins(const Sess *ss, Geom g)
+// Per-MB slot of the bin kernel: every lane (syntax group) writes into its own fixed sub-slot, sized for the worst case of its group --
+// at most 8 entries per level (significance 2, magnitude prefix 2, Exp-Golomb suffix + sign 4 for |level| <= 2063) plus the coded_block_flag;
+// an 8x8 block (ctxBlockCat 5, 512 entries) is written by the lane of its first 4x4 block over the four sub-slots of its 8x8 quadrant.
+//   lane 0 header (<= 98: skip flag, mb_type, 16 mode syntax elements of 4 or 8 mvd components of <= 10, cbp, flags)   112 entries at 0
+//   lane 1 Intra16x16DCLevel                                                                                            132 at 112
+//   lanes 2-17 luma 4x4 blocks                                                                                     16 x 132 at 244
+//   lanes 18-19 chroma DC (4 levels)                                                                                 2 x 40 at 2356
+//   lanes 20-27 chroma AC (15 levels)                                                                               8 x 124 at 2436
+//   lane 28 end_of_slice_flag                                                                                            1 at 3428
+#define CABAC_MB_SLOT 3456
+#define CABAC_HDR_SLOT 112
+__device__ __forceinline__ int cabac_lane_slot(int lane)
+{
+    return lane == 0 ? 0 : lane == 1 ? 112 : lane < 18 ? 244 + 132 * (lane - 2) : lane < 20 ? 2356 + 40 * (lane - 18) : lane < 28 ? 2436 + 124 * (lane - 20) : 3428;
+}
+// grid: (ceil(n_mb / 256), 1, sessions), THREAD per MB (after k_cabac_side: the mvd contexts read the neighbours' side records): the header
+// entries of the macroblock (everything of macroblock_layer() before the residual, mb_skip_flag first) into sub-slot 0 and its
+// end_of_slice_flag is counted (k_cabac_compact writes it); clears the MB's 32 lane counts and sets those two; mb_bits[mb] = their sum. A header is a short serial
+// walk with few entries, which a warp per MB would run on one lane in 32; here the 32 lanes of a warp walk 32 headers.
+__global__ void __launch_bounds__(256) k_cabac_hdr(const Sess *ss, Geom g)
+{
+    const int mb = blockIdx.x * 256 + threadIdx.x;
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    const int mx = mb % g.mbw, my = mb / g.mbw;
+    // the headers have their own dense array (CABAC_HDR_SLOT entries per MB): neighbouring threads write neighbouring lines, not lines 7 KB apart
+    BinSink<1> bs; bs.p = s.bins_hdr + (size_t)mb * CABAC_HDR_SLOT; bs.n = 0;
+    bin_mb_header<1>(bs, s, g, mx, my, s.mbi + mb);
+    uint4 *cnt = reinterpret_cast<uint4 *>(s.bin_lane_cnt + (size_t)mb * 32);
+    cnt[0] = make_uint4((uint32_t)bs.n, 0u, 0u, 0u); cnt[1] = make_uint4(0u, 0u, 0u, 0u); cnt[2] = make_uint4(0u, 0u, 0u, 0u); cnt[3] = make_uint4(0u, 0u, 1u, 0u);   // lanes 0 and 28
+    s.mb_bits[mb] = (uint32_t)bs.n + 1u;
+}
+
+// grid: (ceil(n_mb / CABAC_WARPS), 1, sessions), warp per MB: the residual blocks -- lane 1 Intra16x16DCLevel, 2-17 the luma blocks, 18-19 chroma
+// DC, 20-27 chroma AC -- ONE evaluation each, into the lane's sub-slot of bins_mb[mb * CABAC_MB_SLOT ..], the count into bin_lane_cnt, the
+// total added to mb_bits. Macroblocks without residual (P_Skip, cbp 0 and not Intra_16x16: most of a P picture) leave at once.
+// k_cabac_scan turns the totals into offsets and k_cabac_compact moves the sub-slots, in lane order, to bins[slice base + mb_off[mb]] (slice
+// base = first_mb * B200_MB_BIN_SLOT), the contiguous list the coder walks.
+__global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac_bins(const Sess *ss, Geom g)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = blockIdx.x * CABAC_WARPS + warp;
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
     const MbInfo *mi = s.mbi + mb; const MbCoef *co = s.coef + mb;
+    {
+        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(mi);
+        const int t = w0 & 255, cbp = (int)(w0 >> 24);
+        if (t == MB_PSKIP || (cbp == 0 && t != MB_I16x16)) return;
+    }
     const int mx = mb % g.mbw, my = mb / g.mbw;
     __align__(16) int16_t lv[16];
     CabacItem it = cabac_item(s, g, mx, my, lane, mi, co);
-    if (lane >= 1 && lane < 28 && it.present && it.cat != 5)
+    const bool mine = lane >= 1 && lane < 28 && it.present;
+    if (mine && it.cat != 5)
         for (int i = 0; i < it.n; i++) lv[i] = it.lv[i];
-    int sl = 0;
-    for (int k = 1; k < g.num_slices; k++) sl += (my >= g.slice_row0[k]);
-    const bool last_mb = mb == g.slice_row0[sl + 1] * g.mbw - 1;
-    int cnt;
-    {
-        BinSink<0> bs; bs.p = nullptr; bs.n = 0;
-        if (lane == 0) bin_mb_header<0>(bs, s, g, mx, my, mi);
-        else if (lane < 28) { if (it.present) { if (it.cat == 5) bin_residual8<0>(bs, it.lv); else bin_residual<0>(bs, lv, it.n, it.cat, it.inc); } }
-        else if (lane == 28) bs.put(276, last_mb);
-        cnt = bs.n;
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (!WRITE) { if (lane == 31) s.mb_bits[mb] = (uint32_t)incl; return; }
-    BinSink<1> bs; bs.p = s.bins + (size_t)g.slice_row0[sl] * g.mbw * B200_MB_BIN_SLOT + s.mb_off[mb] + (incl - cnt); bs.n = 0;
-    if (lane == 0) bin_mb_header<1>(bs, s, g, mx, my, mi);
-    else if (lane < 28) { if (it.present) { if (it.cat == 5) bin_residual8<1>(bs, it.lv); else bin_residual<1>(bs, lv, it.n, it.cat, it.inc); } }
-    else if (lane == 28) bs.put(276, last_mb);
+    BinSink<1> bs; bs.p = s.bins_mb + (size_t)mb * CABAC_MB_SLOT + cabac_lane_slot(lane); bs.n = 0;
+    if (mine) { if (it.cat == 5) bin_residual8<1>(bs, it.lv); else bin_residual<1>(bs, lv, it.n, it.cat, it.inc); }
+    if (lane >= 1 && lane < 28) s.bin_lane_cnt[(size_t)mb * 32 + lane] = (uint16_t)bs.n;
+    const int total = __reduce_add_sync(0xffffffffu, bs.n);
+    if (lane == 0) s.mb_bits[mb] += (uint32_t)total;
 }
 
 // grid: (num_slices, 1, sessions), 256 threads: entry offset of every MB inside its slice's bin list, slice total
@@ -340,6 +368,26 @@ __global__ void __launch_bounds__(256) k_cabac_scan(const Sess *ss, Geom g)
         carry += chunk_total;
     }
     if (threadIdx.x == 0) s.slice_nbins[sl] = (uint32_t)carry;
+}
+
+// grid: (ceil(n_mb / CABAC_WARPS), 1, sessions): warp per MB, lane l moves the entries of its sub-slot to their place in the slice's list
+__global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac_compact(const Sess *ss, Geom g)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * CABAC_WARPS + warp;
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    const int my = mb / g.mbw;
+    int sl = 0;
+    for (int k = 1; k < g.num_slices; k++) sl += (my >= g.slice_row0[k]);
+    const int n = (int)s.bin_lane_cnt[(size_t)mb * 32 + lane];
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const uint16_t *src = lane == 0 ? s.bins_hdr + (size_t)mb * CABAC_HDR_SLOT : s.bins_mb + (size_t)mb * CABAC_MB_SLOT + cabac_lane_slot(lane);
+    uint16_t *dst = s.bins + (size_t)g.slice_row0[sl] * g.mbw * B200_MB_BIN_SLOT + s.mb_off[mb] + (incl - n);
+    if (lane == 28) dst[0] = (uint16_t)(276 | ((mb == g.slice_row0[sl + 1] * g.mbw - 1) << 10));      // end_of_slice_flag
+    else for (int i = 0; i < n; i++) dst[i] = src[i];
 }
 
 // ---- the arithmetic coder (9.3.4.2) ----

@@ -15,7 +15,7 @@ for r in rows[hi + 1:]:
     if r and r[0] == "Kernel Name":
         break                      # next launch of the same kernel
     if len(r) >= len(hdr) and r[ix["Instructions Executed"]].isdigit():
-        sass.append((r[ix["Source"]].strip(), int(r[ix["Instructions Executed"]] or 0), int(r[ix["# Samples"]] or 0), int(r[ix["L1 Wavefronts Shared Excessive"]] or 0)))
+        sass.append((r[ix["Source"]].strip(), int(r[ix["Instructions Executed"]] or 0), int(r[ix["# Samples"]] or 0), int(r[ix["L1 Wavefronts Shared Excessive"]] or 0) if "L1 Wavefronts Shared Excessive" in ix else 0))
 tmp = tempfile.mkdtemp()
 lib = os.environ.get("NCU_LINES_LIB", os.path.join(ROOT, "media_b200", "csrc", "libb200enc.so"))   # the build the report was taken with
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
