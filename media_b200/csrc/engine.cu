@@ -451,7 +451,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         // (paced sessions: small batches, tail latency counts). Big batches are throughput work: there the slab only takes shared memory
         // from the other batches' motion search (96 x 1080p Main in batches of 32: 8 550 frames/s with it, 9 380 without)
         const int hog_kb = n <= 16 ? cabac_slab_kb() : 0;
-        pf.begin("k_cabac_code", s2); if (!(xskip & 4)) k_cabac_code<<<dim3(g.num_slices, 1, n), 96, (size_t)hog_kb * 1024, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_code", s2); if (!(xskip & 4)) k_cabac_code<<<dim3(g.num_slices, 1, n), 96, (size_t)hog_kb * 1024, s2>>>(b->d_sess, g, b->d_ctl); pf.end();
         launches += 6;
     } else {
     pf.begin("k_cavlc_mb", s2); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;

@@ -101,7 +101,7 @@ struct Sess {
     uint32_t rbsp_words_per_slice, out_cap;
 };
 
-// per-batch control block: wavefront tickets and the error flag (1 wavefront watchdog, 2 TMA transaction timeout)
+// per-batch control block: wavefront tickets and the error flag (1 wavefront watchdog, 2 TMA transaction timeout, 3 CABAC coder watchdog)
 struct WaveCtl { int ticket_intra, ticket_dbk, error, pad; };
 
 // ---- normative tables ----
@@ -307,6 +307,17 @@ __device__ __forceinline__ int quant_dc(int y, const QParam &q, int f)
     int l = min((int)(((unsigned)abs(y) * (unsigned)q.mf[0] + 2u * (unsigned)f) >> (q.qbits + 1)), B200_MAX_LEVEL);
     return y < 0 ? -l : l;
 }
+
+// ---- checked build (-DB200_CHECKED, libb200enc_checked.so): device-side bound checks on every COMPUTED index into a slot, ring, list or tile.
+// compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer.md), so this is the memory-safety evidence: the parity workloads run through
+// this build and b200k_check_failures() must report none. Site ids: 1 CAVLC bit slot, 2 CABAC sub-slot, 3 CABAC list compaction, 4 slice copy,
+// 6-8 motion-search tiles, 9-10 intra tiles / tables, 11 coder ring, 12 coder output.
+#ifdef B200_CHECKED
+__device__ int g_check_fail[2];
+#define B200_CHECK(cond, site) do { if (!(cond)) { if (atomicAdd(&g_check_fail[0], 1) == 0) g_check_fail[1] = (site); } } while (0)
+#else
+#define B200_CHECK(cond, site) do { } while (0)
+#endif
 
 // acquire/release on the wavefront progress counters
 __device__ __forceinline__ int ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }

@@ -28,13 +28,20 @@ namespace b200 {
 
 template <int WRITE> struct BinSink {
     uint16_t *p; int n;
-    __device__ __forceinline__ void put(int ctx, int bin) { if (WRITE) p[n] = (uint16_t)(ctx | (bin << 10)); n++; }
-    __device__ __forceinline__ void run(int ctx, int bin, int rep) { if (WRITE) p[n] = (uint16_t)(ctx | (bin << 10) | ((rep - 1) << 11)); n++; }
+#ifdef B200_CHECKED
+    int cap = 1 << 30;                                  // entries of room behind p
+#define BINSINK_CHECK() B200_CHECK(!WRITE || n < cap, 2)
+#else
+#define BINSINK_CHECK() do { } while (0)
+#endif
+    __device__ __forceinline__ void put(int ctx, int bin) { BINSINK_CHECK(); if (WRITE) p[n] = (uint16_t)(ctx | (bin << 10)); n++; }
+    __device__ __forceinline__ void run(int ctx, int bin, int rep) { BINSINK_CHECK(); if (WRITE) p[n] = (uint16_t)(ctx | (bin << 10) | ((rep - 1) << 11)); n++; }
     // a string of bypass bins, first bin = most significant of `len` bits: entries of six, the remainder last
     __device__ __forceinline__ void bypass(uint32_t bits, int len)
     {
         while (len > 0) {
             const int k = min(len, 6);
+            BINSINK_CHECK();
             if (WRITE) p[n] = (uint16_t)((CABAC_BYPASS0 + k) | (((bits >> (len - k)) & ((1u << k) - 1u)) << 10));
             n++; len -= k;
         }
@@ -317,6 +324,9 @@ __global__ void __launch_bounds__(256) k_cabac_hdr(const Sess *ss, Geom g)
     const int mx = mb % g.mbw, my = mb / g.mbw;
     // the headers have their own dense array (CABAC_HDR_SLOT entries per MB): neighbouring threads write neighbouring lines, not lines 7 KB apart
     BinSink<1> bs; bs.p = s.bins_hdr + (size_t)mb * CABAC_HDR_SLOT; bs.n = 0;
+#ifdef B200_CHECKED
+    bs.cap = CABAC_HDR_SLOT;
+#endif
     bin_mb_header<1>(bs, s, g, mx, my, s.mbi + mb);
     uint4 *cnt = reinterpret_cast<uint4 *>(s.bin_lane_cnt + (size_t)mb * 32);
     cnt[0] = make_uint4((uint32_t)bs.n, 0u, 0u, 0u); cnt[1] = make_uint4(0u, 0u, 0u, 0u); cnt[2] = make_uint4(0u, 0u, 0u, 0u); cnt[3] = make_uint4(0u, 0u, 1u, 0u);   // lanes 0 and 28
@@ -347,6 +357,9 @@ __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac_bins(const Sess *ss,
     if (mine && it.cat != 5)
         for (int i = 0; i < it.n; i++) lv[i] = it.lv[i];
     BinSink<1> bs; bs.p = s.bins_mb + (size_t)mb * CABAC_MB_SLOT + cabac_lane_slot(lane); bs.n = 0;
+#ifdef B200_CHECKED
+    bs.cap = mine && it.cat == 5 ? 4 * 132 : cabac_lane_slot(lane + 1) - cabac_lane_slot(lane);
+#endif
     if (mine) { if (it.cat == 5) bin_residual8<1>(bs, it.lv); else bin_residual<1>(bs, lv, it.n, it.cat, it.inc); }
     if (lane >= 1 && lane < 28) s.bin_lane_cnt[(size_t)mb * 32 + lane] = (uint16_t)bs.n;
     const int total = __reduce_add_sync(0xffffffffu, bs.n);
@@ -386,6 +399,7 @@ __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac_compact(const Sess *
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     const uint16_t *src = lane == 0 ? s.bins_hdr + (size_t)mb * CABAC_HDR_SLOT : s.bins_mb + (size_t)mb * CABAC_MB_SLOT + cabac_lane_slot(lane);
     uint16_t *dst = s.bins + (size_t)g.slice_row0[sl] * g.mbw * B200_MB_BIN_SLOT + s.mb_off[mb] + (incl - n);
+    B200_CHECK((size_t)s.mb_off[mb] + (size_t)incl <= (size_t)(g.slice_row0[sl + 1] - g.slice_row0[sl]) * g.mbw * B200_MB_BIN_SLOT, 3);
     if (lane == 28) dst[0] = (uint16_t)(276 | ((mb == g.slice_row0[sl + 1] * g.mbw - 1) << 10));      // end_of_slice_flag
     else for (int i = 0; i < n; i++) dst[i] = src[i];
 }
@@ -395,8 +409,8 @@ __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac_compact(const Sess *
 // the standard drops the first bit). A byte leaves as soon as nb reaches 8; it may carry into the bytes before it, so the last
 // byte that is not 0xFF is held back together with the count of 0xFF bytes behind it.
 template <bool SWAP> struct CabacOut {
-    uint8_t *base; int pos; int hold, n_ff;
-    __device__ __forceinline__ void store(int v) { base[SWAP ? (pos ^ 3) : pos] = (uint8_t)v; pos++; }
+    uint8_t *base; int pos; int hold, n_ff; int cap;       // cap: bytes of room (a slice that does not fit is cut there; k_nal_pack reports the overflow)
+    __device__ __forceinline__ void store(int v) { B200_CHECK(pos < cap, 12); if (pos < cap) base[SWAP ? (pos ^ 3) : pos] = (uint8_t)v; pos++; }
     __device__ __forceinline__ void byte(int out)          // 9 bits: a byte and the carry into the earlier ones
     {
         if ((out & 0xff) == 0xff) { n_ff++; return; }
@@ -449,7 +463,21 @@ __device__ __forceinline__ void cabac_tables_init(CabacTables &t, int qp, bool i
 //   bypass bins : .x = .z = 0 (an "MPS" that leaves the range alone), .y = value, .w = number of bins in every byte
 //   terminate 0 : an MPS with rangeTabLPS = 2 (9.3.4.5: codIRange -= 2, RenormE)
 // the terminate bin of value 1 that ends the slice is not queued: the consumer flushes when the ring has drained
-struct CabacRing { uint4 rec[CABAC_RING]; volatile uint32_t wr, rd; volatile int done; };
+struct CabacRing { uint4 rec[CABAC_RING]; volatile uint32_t wr, rd; volatile int done, abort; };
+// Watchdog of the coder's three spin loops (ring room, ring data / output-queue room, output data): like the wavefront and TMA waits, a wait
+// longer than 2 s is an internal error (an inconsistent bin list) that must end the kernel and reach the host as B200ENC_EWAVE, never hang the GPU.
+struct CabacSpin {
+    unsigned spins = 0; unsigned long long t0 = 0;
+    __device__ __forceinline__ bool expired(CabacRing &ring)
+    {
+        if (ring.abort) return true;
+        if ((++spins & 4095u) != 0u) return false;
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (!t0) { t0 = t; return false; }
+        if (t - t0 > 2000000000ull) { ring.abort = 1; return true; }
+        return false;
+    }
+};
 #ifdef CABAC_TIMING       // phase cycle counts of the coder pair (tools/cabac_coder_bench.py): [0] consumer total [1] consumer waiting [2] records
 __device__ long long g_cabac_t[8];   // [3] producer total [4] producer waiting for room [5] producer turn loops [6] steps [7] turns
 #define CT_CLK() clock64()
@@ -477,7 +505,9 @@ __device__ __forceinline__ void cabac_produce(CabacRing &ring, CabacTables &t, c
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         uint32_t at = wr + (uint32_t)(incl - nrec);
         const long long t0 = CT_CLK();
-        while (wr + (uint32_t)total - ring.rd > CABAC_RING) __nanosleep(64);       // room in the ring
+        B200_CHECK(total <= CABAC_RING, 11);
+        { CabacSpin sg; while (wr + (uint32_t)total - ring.rd > CABAC_RING) { if (sg.expired(ring)) break; __nanosleep(64); } }       // room in the ring
+        if (ring.abort) break;
         const long long t1 = CT_CLK(); t_wait += t1 - t0;
         const uint32_t peers = __match_any_sync(0xffffffffu, regular ? ctx : 0x10000 + lane);
         const uint32_t before = peers & ((1u << lane) - 1u);
@@ -552,15 +582,18 @@ __device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
     uint32_t low = 0, range = 510; int nb = -1;
     uint32_t rd = 0, qw = 0;
     [[maybe_unused]] const long long t_begin = CT_CLK(); [[maybe_unused]] long long t_wait = 0;
+    CabacSpin idle;
     for (;;) {
         uint32_t wr = ring.wr;
         if (wr == rd) {
             const long long t0 = CT_CLK();
-            if (ring.done) { wr = ring.wr; if (wr == rd) break; } else { __nanosleep(32); t_wait += CT_CLK() - t0; continue; }
+            if (ring.done) { wr = ring.wr; if (wr == rd) break; } else { if (idle.expired(ring)) break; __nanosleep(32); t_wait += CT_CLK() - t0; continue; }
         }
         __threadfence_block();
         uint32_t avail = min(wr - rd, 256u);
-        while (qw + avail - oq.rd > CABAC_OUTQ) __nanosleep(32);            // a record emits at most one byte
+        { CabacSpin sg; while (qw + avail - oq.rd > CABAC_OUTQ) { if (sg.expired(ring)) break; __nanosleep(32); } }            // a record emits at most one byte
+        if (ring.abort) break;
+        idle.spins = 0; idle.t0 = 0;
         for (; avail >= 8u; avail -= 8u, rd += 8u) {
             uint4 r[8];
 #pragma unroll
@@ -576,8 +609,8 @@ __device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
         range -= 2; low += range; low |= 1u;                                // the last of the ten bits is the rbsp_stop_one_bit
         int width = nb + 10; const int pad = (8 - (width & 7)) & 7;
         low <<= pad; width += pad;                                          // rbsp_alignment_zero_bit
-        while (qw + 8u - oq.rd > CABAC_OUTQ) __nanosleep(32);
-        while (width >= 8) { width -= 8; oq.v[qw++ & (CABAC_OUTQ - 1)] = (uint16_t)(low >> width); }
+        { CabacSpin sg; while (qw + 8u - oq.rd > CABAC_OUTQ) { if (sg.expired(ring)) break; __nanosleep(32); } }
+        while (!ring.abort && width >= 8) { width -= 8; oq.v[qw++ & (CABAC_OUTQ - 1)] = (uint16_t)(low >> width); }
         __threadfence_block();
         oq.wr = qw;
     }
@@ -586,12 +619,14 @@ __device__ __forceinline__ void cabac_consume(CabacRing &ring, CabacOutQ &oq)
     CT_ADD(0, CT_CLK() - t_begin); CT_ADD(1, t_wait); CT_ADD(2, rd);
 }
 // the calling thread turns the queue into bytes
-template <bool SWAP> __device__ __forceinline__ void cabac_write(CabacOutQ &oq, CabacOut<SWAP> &o)
+template <bool SWAP> __device__ __forceinline__ void cabac_write(CabacRing &ring, CabacOutQ &oq, CabacOut<SWAP> &o)
 {
     uint32_t rd = 0; int last = -1;                        // the byte taken before this one, as it was then
+    CabacSpin idle;
     for (;;) {
         uint32_t wr = oq.wr;
-        if (wr == rd) { if (oq.done) { wr = oq.wr; if (wr == rd) break; } else { __nanosleep(64); continue; } }
+        if (wr == rd) { if (oq.done) { wr = oq.wr; if (wr == rd) break; } else { if (idle.expired(ring)) break; __nanosleep(64); continue; } }
+        idle.spins = 0; idle.t0 = 0;
         __threadfence_block();
         for (; rd != wr; rd++) {
             const int v = oq.v[rd & (CABAC_OUTQ - 1)], cur = v & 255;
@@ -609,12 +644,12 @@ template <bool SWAP> __device__ __forceinline__ void cabac_code_list(CabacOut<SW
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 1) cabac_produce(ring, t, bins, n, lane);
     else if (warp == 0) { if (lane == 0) cabac_consume(ring, oq); }
-    else if (lane == 0) cabac_write<SWAP>(oq, o);
+    else if (lane == 0) cabac_write<SWAP>(ring, oq, o);
 }
-#define CABAC_INIT_QUEUES() do { if (threadIdx.x == 0) { ring.wr = 0; ring.rd = 0; ring.done = 0; oq.wr = 0; oq.rd = 0; oq.done = 0; } } while (0)
+#define CABAC_INIT_QUEUES() do { if (threadIdx.x == 0) { ring.wr = 0; ring.rd = 0; ring.done = 0; ring.abort = 0; oq.wr = 0; oq.rd = 0; oq.done = 0; } } while (0)
 
 // grid: (num_slices, 1, sessions), 96 threads
-__global__ void __launch_bounds__(96) k_cabac_code(const Sess *ss, Geom g)
+__global__ void __launch_bounds__(96) k_cabac_code(const Sess *ss, Geom g, WaveCtl *ctl)
 {
     const Sess &s = ss[blockIdx.z];
     const int sl = blockIdx.x, m0 = g.slice_row0[sl] * g.mbw, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -646,9 +681,9 @@ __global__ void __launch_bounds__(96) k_cabac_code(const Sess *ss, Geom g)
         }
     }
     __syncthreads();
-    CabacOut<true> o; o.base = reinterpret_cast<uint8_t *>(rb); o.pos = hdr_bytes_s; o.hold = -1; o.n_ff = 0;
+    CabacOut<true> o; o.base = reinterpret_cast<uint8_t *>(rb); o.pos = hdr_bytes_s; o.hold = -1; o.n_ff = 0; o.cap = (int)s.rbsp_words_per_slice * 4;
     cabac_code_list<true>(o, tabs, ring, oq, s.bins + (size_t)m0 * B200_MB_BIN_SLOT, (int)s.slice_nbins[sl]);
-    if (threadIdx.x == 64) s.slice_bits[sl] = (uint32_t)o.pos * 8u;
+    if (threadIdx.x == 64) { s.slice_bits[sl] = (uint32_t)min(o.pos, o.cap) * 8u; if (ring.abort) atomicExch(&ctl->error, 3); }
 }
 
 // test entry: code one bin list into plain bytes (b200k_cabac_code)
@@ -661,7 +696,7 @@ __global__ void __launch_bounds__(96) k_cabac_code_test(const uint16_t *bins, in
     CABAC_INIT_QUEUES();
     if (warp == 1) cabac_tables_init(tabs, qp, is_p != 0, lane);
     __syncthreads();
-    CabacOut<false> o; o.base = out; o.pos = 0; o.hold = -1; o.n_ff = 0;
+    CabacOut<false> o; o.base = out; o.pos = 0; o.hold = -1; o.n_ff = 0; o.cap = 0x7fffffff;
     cabac_code_list<false>(o, tabs, ring, oq, bins, n);
     if (threadIdx.x == 64) *out_len = o.pos;
 }
@@ -676,7 +711,7 @@ __global__ void __launch_bounds__(96) k_cabac_code_multi(const uint16_t *bins, i
     CABAC_INIT_QUEUES();
     if (warp == 1) cabac_tables_init(tabs, qp, is_p != 0, lane);
     __syncthreads();
-    CabacOut<false> o; o.base = out + (size_t)blockIdx.x * out_stride; o.pos = 0; o.hold = -1; o.n_ff = 0;
+    CabacOut<false> o; o.base = out + (size_t)blockIdx.x * out_stride; o.pos = 0; o.hold = -1; o.n_ff = 0; o.cap = 0x7fffffff;
     cabac_code_list<false>(o, tabs, ring, oq, bins + (size_t)blockIdx.x * bins_stride, n);
     if (threadIdx.x == 64) out_len[blockIdx.x] = o.pos;
 }

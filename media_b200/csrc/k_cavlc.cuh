@@ -106,8 +106,14 @@ __global__ void __launch_bounds__(256) k_pskip_scan(const Sess *ss, Geom g)
 // MODE 2: collect up to 64 bits in a register (pos keeps counting past 64, which is how the caller sees an overflow) ----
 template <int MODE> struct BitSink {
     uint32_t *w; int pos; unsigned long long acc;
+#ifdef B200_CHECKED
+    int cap = 0;                                        // bits of room behind w (0: not tracked)
+#endif
     __device__ __forceinline__ void put(int n, uint32_t v)
     {
+#ifdef B200_CHECKED
+        if (MODE == 1) B200_CHECK(cap == 0 || pos + n <= cap, 1);
+#endif
         if (MODE == 1 && n > 0) {
             const int o = pos & 31, wi = pos >> 5;
             if (o + n <= 32) atomicOr(w + wi, v << (32 - o - n));
@@ -311,6 +317,9 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, G
     } else {
         // pass 2 (long groups: high-rate intra blocks): code again, writing at the lane's bit offset
         BitSink<1> bs; bs.w = slot; bs.pos = incl - len; bs.acc = 0ull;
+#ifdef B200_CHECKED
+        bs.cap = B200_MB_SLOT_WORDS * 32;
+#endif
         if (lane == 0) code_mb_header<1>(bs, s, g, mx, my, mi, skip_run, mvd);
         else if (lane < 28 && it.present) code_residual<1>(bs, lv, it.maxn, it.nC);
     }
@@ -401,6 +410,7 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_slice_copy(const Sess *ss,
     uint32_t *rb = s.rbsp + (size_t)sl * s.rbsp_words_per_slice;
     const uint32_t *src = s.mb_slot + (size_t)mb * B200_MB_SLOT_WORDS;
     const int D = (int)s.mb_off[mb], nw = (l + 31) >> 5, dw = D >> 5, sh = D & 31;
+    B200_CHECK((size_t)dw + (size_t)nw + 1 <= (size_t)s.rbsp_words_per_slice && nw <= B200_MB_SLOT_WORDS, 4);
     for (int i = lane; i <= nw; i += 32) {          // destination word dw + i
         const uint32_t hi = i > 0 ? src[i - 1] : 0u, lo = i < nw ? src[i] : 0u;
         const uint32_t v = sh ? (hi << (32 - sh)) | (lo >> sh) : lo;

@@ -26,26 +26,24 @@ __device__ long long g_intra_t[8];
 
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-// wait until the row above has finished `need` macroblocks; returns false on timeout / global error
+// wait until the row above has finished `need` macroblocks; returns false on timeout / global error. EVERY lane performs the acquire load
+// (one request per warp: same address), so each lane's later reads of the neighbour row's samples and MbInfo are ordered after the
+// producer's release by the memory model itself, not by a shuffle from the one lane that polled.
 __device__ __forceinline__ bool wave_wait(const int *prog_above, int need, WaveCtl *ctl, int lane)
 {
-    int ok = 1;
-    if (lane == 0) {
-        int cur = ld_acquire(prog_above);
-        if (cur < need) {
-            const unsigned long long t0 = global_ns();
-            int spins = 0;
-            do {
-                // a row that is d macroblocks short of what we need takes d MB-steps (a few us each): sleep accordingly, so
-                // that far-behind rows do not burn the issue slots of the SMs they share with other kernels
-                const int d = need - cur;
-                __nanosleep(d > 1 ? min(d * 1500, 30000) : 32);
-                if ((++spins & 15) == 0 && (ld_acquire(&ctl->error) || global_ns() - t0 > WAVE_TIMEOUT_NS)) { atomicExch(&ctl->error, 1); ok = 0; break; }
-            } while ((cur = ld_acquire(prog_above)) < need);
-        }
-    }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    return ok != 0;
+    (void)lane;
+    int cur = ld_acquire(prog_above);
+    if (cur >= need) return true;
+    const unsigned long long t0 = global_ns();
+    int spins = 0;
+    do {
+        // a row that is d macroblocks short of what we need takes d MB-steps (a few us each): sleep accordingly, so
+        // that far-behind rows do not burn the issue slots of the SMs they share with other kernels
+        const int d = need - cur;
+        __nanosleep(d > 1 ? min(d * 1500, 30000) : 32);
+        if ((++spins & 15) == 0 && (ld_acquire(&ctl->error) || global_ns() - t0 > WAVE_TIMEOUT_NS)) { if (lane == 0) atomicExch(&ctl->error, 1); return false; }
+    } while ((cur = ld_acquire(prog_above)) < need);
+    return true;
 }
 
 __device__ __forceinline__ void hadamard16(int v[16])
@@ -153,6 +151,7 @@ __device__ int intra_try_i8x8(const IntraCtx &s, const Geom &g, IntraSmem &sm, c
         const bool aTR = aT && (b == 0 ? top : b == 1 ? topright : b == 2);
         // raw edge sample of lane k: L[7-k] (k < 8), the corner (k = 8), T[k-9] (k > 8; without a top-right neighbour T8..T15 repeat T7)
         int e = 128;
+        B200_CHECK((by8 + 8) * NBP + 3 + bx8 < 17 * NBP && by8 * NBP + 4 + bx8 + 15 < 17 * NBP, 9);
         if (lane < 8) { if (aL) e = nb[(by8 + 8 - lane) * NBP + 3 + bx8]; }
         else if (lane == 8) { if (aX) e = nb[by8 * NBP + 3 + bx8]; }
         else if (lane < 25) { const int i = lane - 9; if (aT) e = nb[by8 * NBP + 4 + bx8 + ((i < 8 || aTR) ? i : 7)]; }
@@ -195,6 +194,7 @@ __device__ int intra_try_i8x8(const IntraCtx &s, const Geom &g, IntraSmem &sm, c
 #pragma unroll
             for (int y = 0; y < 4; y++) {
                 const uint32_t ix = i8idx[m * 16 + (4 * qy + y) * 2 + qx];
+                B200_CHECK((ix & 255) < 96 && ((ix >> 8) & 255) < 96 && ((ix >> 16) & 255) < 96 && (ix >> 24) < 96 && m < 9, 10);
                 P[y] = (uint32_t)sm.F[ix & 255] | ((uint32_t)sm.F[(ix >> 8) & 255] << 8) | ((uint32_t)sm.F[(ix >> 16) & 255] << 16) | ((uint32_t)sm.F[ix >> 24] << 24);
             }
             int sat = satd_rows(P, Ts);

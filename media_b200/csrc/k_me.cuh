@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     for (int i = lane; i < 100; i += 32) {
         const int r = i / 5, k = i - r * 5, off = o0 + k, sh = (off & 3) * 8;
         const uint32_t *row = sm.win + r * (PL_STRIDE / 4) + (off >> 2);
+        B200_CHECK(r * (PL_STRIDE / 4) + (off >> 2) + 4 < 20 * PL_STRIDE / 4 && k * WIN_COPY + r * 16 + 16 <= (int)sizeof(sm.plane), 8);
         const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3], w4 = row[4];
         *reinterpret_cast<uint4 *>(cpb + k * WIN_COPY + r * 16) =
             make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     const uint32_t *pw = sm.plane[0];                   // word view of the planes G, b, h, j (PLW words each)
     constexpr int PLW = PL_ROWS * PL_STRIDE / 4, RW = PL_STRIDE / 4;
     const int ob = by * PL_STRIDE + o1 + bx + 3;         // byte offset inside a plane of sample (bx - 1, by - 1) of the best full-pel block
+    B200_CHECK(((ob + 1 + PL_STRIDE) >> 2) + 3 * (PL_STRIDE / 4) + 1 < PL_ROWS * PL_STRIDE / 4 && (ob >> 2) + 4 * (PL_STRIDE / 4) + 1 < PL_ROWS * PL_STRIDE / 4, 6);
     // P_8x8: every candidate's SATD is also summed per 8x8 quadrant (the first two steps of the 16-lane reduction) and each quadrant keeps its
     // own best candidate: key = (SATD8x8 + lambda * bits) << 5 | sequence number (0..8 half-pel ring, 9..16 quarter-pel ring).
     uint32_t bk = 0xffffffffu, bq = 0xffffffffu;
@@ -503,6 +505,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
         const int common = (by + (oy >> 2) + 1) * PL_STRIDE + o1 + bx + (ox >> 2) + 4;
         const int oa = common + (int)(t & 0xffffu), obb = common + (int)(t >> 16);
         const uint32_t *wa = pw + (oa >> 2), *wb = pw + (obb >> 2); const int sa = (oa & 3) * 8, sb = (obb & 3) * 8;
+        B200_CHECK(oa >= 0 && obb >= 0 && (oa >> 2) + 3 * RW + 1 < 4 * PLW && (obb >> 2) + 3 * RW + 1 < 4 * PLW, 7);
         uint32_t P[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) P[r] = avg4(__funnelshift_r(wa[r * RW], wa[r * RW + 1], sa), __funnelshift_r(wb[r * RW], wb[r * RW + 1], sb));

@@ -194,6 +194,20 @@ template <int KIND> static int run_int_peak(int sms, double *out)
     return B200ENC_OK;
 }
 extern "C" {
+// checked build: number of device-side bound-check failures since the library was loaded and the id of the first failing site; -1 = not a checked build
+int b200k_check_failures(int device, int *first_site)
+{
+#ifdef B200_CHECKED
+    int v[2] = { 0, 0 };
+    if (cudaSetDevice(device) != cudaSuccess) return -2;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(v, g_check_fail, sizeof v) != cudaSuccess) return -2;
+    if (first_site) *first_site = v[1];
+    return v[0];
+#else
+    (void)device; if (first_site) *first_site = 0;
+    return -1;
+#endif
+}
 int b200k_int_peaks(int device, double *out, int kinds)
 {
     if (!out || kinds < 1) return B200ENC_EINVAL;

@@ -923,3 +923,18 @@ def test_config4_2160p_8_slices_range64_matches_the_oracle(enc, orc):
         dec = avdec.decode_stream(aus)
         assert len(dec) == 3 and all(np.array_equal(d, r) for d, r in zip(dec, recs))
     g.close()
+
+
+def test_checked_build_reports_no_bound_violation():
+    """compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer.md): libb200enc_checked.so carries device-side bound checks on every computed
+    slot / ring / list / tile index (h264_dev.cuh B200_CHECK). The sanitizer workloads and the worst cases for the slots (noise at QP 0 with CAVLC and
+    with CABAC, slices, Intra_8x8) run through it in a child process (tools/sanitize_case.py checked); the streams still equal the oracle's and no
+    check may have fired"""
+    import subprocess
+    import sys
+    lib = os.path.join(ROOT, "media_b200", "csrc", "libb200enc_checked.so")
+    if not os.path.exists(lib):
+        pytest.skip("libb200enc_checked.so not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_case.py"), "checked"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, B200ENC_LIB=lib))
+    assert r.returncode == 0 and "check failures 0 " in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

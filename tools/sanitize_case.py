@@ -11,6 +11,11 @@ from media_b200.synth import Content  # noqa: E402
 from oracle import orc_py           # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+# "checked": everything, plus the worst cases for the slots / rings / lists, through libb200enc_checked.so (B200ENC_LIB); prints the count of
+# device-side bound-check failures (tests/test_gpu_parity.py::test_checked_build_reports_no_bound_violation)
+checked = which == "checked"
+if checked:
+    which = "all"
 if which in ("smoke", "all"):
     w, h, qp = 176, 144, 26
     g = enc.Session(w, h, const_qp=qp, gop=1000, device=0); o = orc_py.Encoder(w, h); c = Content("A", w, h)
@@ -35,3 +40,18 @@ if which in ("cabac", "all"):
     for s in ss:
         s.close()
     print("cabac batch case ok")
+if checked:
+    import ctypes as C
+    for (w, h, kind, qp, slices, profile) in ((96, 80, "D", 0, 1, 0), (96, 80, "D", 0, 2, 1), (176, 144, "D", 4, 3, 2), (640, 368, "A", 20, 2, 2), (1280, 720, "B", 30, 0, 1)):
+        g = enc.Session(w, h, const_qp=qp, num_slices=slices, gop=3, device=0, profile=profile)
+        o = orc_py.Encoder(w, h, num_slices=slices if slices else max(1, min(8, ((h + 15) // 16 + 8) // 17)), profile=profile)
+        c = Content(kind, w, h)
+        for t in range(4):
+            f = c.frame(t)
+            assert g.encode(f)[0] == o.encode(f, t % 3 == 0, qp), (w, h, kind, qp, t)
+        g.close()
+    L = enc.lib()
+    L.b200k_check_failures.restype = C.c_int; L.b200k_check_failures.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    site = C.c_int()
+    n = L.b200k_check_failures(0, C.byref(site))
+    print(f"check failures {n} first site {site.value}" if n >= 0 else "not a checked build")
