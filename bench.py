@@ -210,7 +210,7 @@ def run_b200(args):
     el, dev_ms, launches, out_bytes = timed(groups, dpool, 1, args.steps, args.warmup)
     clocks = sampler.summary()
     value = world * S * args.steps / el
-    e2e = el_e = out_bytes_e = e2e_errors = 0; e2e_lat, e2e_avg_batch, realtime = {}, 0, None
+    e2e = el_e = out_bytes_e = e2e_errors = 0; e2e_lat, e2e_avg_batch, realtime, h2d = {}, 0, None, None
     if args.no_e2e:
         for g_ in groups:
             g_[1].close()
@@ -274,6 +274,30 @@ def run_b200(args):
                         "realtime": bool(rt[0] == 0 and rt[1] == 0 and rt[2] <= 1000.0 / FPS),
                         "via": "VideoEncoder::EncodeOneFrame, one paced caller thread per session (staggered phases), pageable input"}
         E.e2e_close(h)
+        # ---- the ceiling the host-input path cannot beat: pinned host -> device copy bandwidth of this rank's GPU with every rank copying at
+        # once (the frames of a step are S x fb bytes per GPU), and the staging memcpy rate of this host (pageable -> pinned, all caller threads)
+        h2d = None
+        try:
+            nbuf = 32
+            hp = torch.empty(nbuf * fb, dtype=torch.uint8).pin_memory(); dp_ = torch.empty(nbuf * fb, dtype=torch.uint8, device=f"cuda:{dev}")
+            dp_.copy_(hp, non_blocking=True); torch.cuda.synchronize()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(6):
+                dp_.copy_(hp, non_blocking=True)
+            e1.record(); torch.cuda.synchronize()
+            gbs = 6 * nbuf * fb / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            t = torch.tensor([gbs], dtype=torch.float64)
+            if use_dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            h2d = {"pinned_h2d_gbs_per_gpu_all_ranks_copying": round(t[0].item(), 1),
+                   "frames_per_s_ceiling": round(world * t[0].item() * 1e9 / fb, 0),
+                   "note": "PCIe ceiling of the host-input path: no end-to-end number with host frames can exceed it; the staging copy of pageable caller "
+                           "memory (one memcpy per frame on the caller's thread) comes on top on the CPU side"}
+            del hp, dp_
+        except Exception as ex:
+            h2d = {"error": str(ex)}
 
     # per-kernel shares of one P step over ALL sessions of the GPU in a single batch (CUDA events around each launch on the
     # batch's stream); fresh sessions, so two untimed frames first (IDR + one P)
@@ -360,7 +384,7 @@ def run_b200(args):
                        "timing": "value/ms_per_step: host clock between a device synchronize + barrier on both sides (max over ranks; an upper bound of the device time of "
                                  "the overlapping batch streams); device_ms_per_step: CUDA events on the batch streams (slowest batch group); kernel_ms: CUDA events per launch"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": world * S * fb, "d2h_bytes_per_step": int(out_bytes_e / args.steps),
-                    "ms_per_step": round(el_e / args.steps * 1e3, 4), "errors": e2e_errors, "call_latency_ms": e2e_lat, "avg_sessions_per_batch_step": e2e_avg_batch,
+                    "ms_per_step": round(el_e / args.steps * 1e3, 4), "errors": e2e_errors, "call_latency_ms": e2e_lat, "avg_sessions_per_batch_step": e2e_avg_batch, "h2d_ceiling": h2d,
                     "via": "VideoEncoder::EncodeOneFrame through dlopen(libVideoCodec.so) + CreateVideoEncoder, one C++ caller thread per session, pageable (malloc) input, "
                            "encoder-owned output read by the caller; H2D staging and copies inside the timed region"},
             "gpu_launches": launches,

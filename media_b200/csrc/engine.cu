@@ -163,6 +163,7 @@ struct b200enc_session {
     void *tmaps;                                 // CUtensorMap[3] in HBM
     MbInfo *mbi; MbCoef *coef; uint4 *dbk_bs; int16_t *me2, *me1, *me0; int32_t *inter_cost, *skip_run;
     uint32_t *mb_bits, *mb_off, *mb_slot, *rbsp, *slice_bits; uint8_t *hdr; int hdr_len = 0; int *row_prog;
+    uint2 *dbk_ll; uint32_t dbk_seq = 0;          // deblocking hand-over messages between MB rows, launch counter
     MbSide *side; uint16_t *bins, *bins_mb, *bin_lane_cnt, *bins_hdr; uint32_t *slice_nbins;   // CABAC (profile main / high)
     uint32_t rbsp_words_per_slice = 0;
     std::vector<uint8_t> param_sets;
@@ -373,6 +374,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         d.side = s->side; d.bins = s->bins; d.bins_mb = s->bins_mb; d.bin_lane_cnt = s->bin_lane_cnt; d.bins_hdr = s->bins_hdr; d.slice_nbins = s->slice_nbins;
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
+        d.dbk_ll = s->dbk_ll; d.dbk_seq = ++s->dbk_seq;
         d.qp = qps[i]; d.is_idr = idr; d.frame_num = idr ? 0 : s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
         d.scene_change = s->cfg.scene_change && !idr && s->frames_since_idr >= SC_MIN_DISTANCE;
         d.t8x8 = s->cfg.profile == 2; d.dump = s->cfg.debug & 1;
@@ -801,6 +803,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         add(s->bin_lane_cnt, c.profile ? nmb * 32 * sizeof(uint16_t) : 16);
         add(s->bins_hdr, c.profile ? nmb * CABAC_HDR_SLOT * sizeof(uint16_t) : 16);
         add(s->slice_bits, B200_MAX_SLICES * 4); add(s->hdr, 256); add(s->row_prog, (size_t)g.mbh * 2 * 4);
+        add(s->dbk_ll, (size_t)g.mbh * (g.mbw + 1) * DBK_LL_PER_MB * sizeof(uint2));
         size_t total = 0;
         for (auto &it : items) total += align_up(it.bytes, 256);
         CU_TRY(cudaMalloc(&s->d_pool, total), rc = B200ENC_ENOMEM; break);

@@ -91,6 +91,8 @@ struct Sess {
     uint32_t *out_size;           // bytes written to out
     const uint8_t *hdr; int hdr_len;   // SPS+PPS NALs, prepended on IDR
     int *row_prog_intra, *row_prog_dbk; // wavefront progress counters, one per MB row
+    uint2 *dbk_ll;                // deblocking: the bottom rows every MB row hands to the row below, as {4 samples, dbk_seq} messages (k_deblock.cuh)
+    uint32_t dbk_seq;             // sequence number of this launch for this session (never 0, never repeated)
     int qp, is_idr, frame_num, idr_pic_id, input_format;
     int scene_change;             // 1: k_scene_change may turn this P picture into an IDR (then is_idr / frame_num are rewritten on the device)
     int bgd;                      // 1: background detection (static macroblocks against src_prev are skipped)

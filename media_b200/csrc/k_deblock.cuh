@@ -24,10 +24,32 @@ namespace b200 {
 
 // the few session fields the row loop needs, held in registers: every fence / strong access in the loop is a compiler memory
 // barrier, so reading them through `const Sess &` re-fetched them from L2 several times per macroblock (1 800 cycles measured)
-struct DbkCtx { uint8_t *rec[3]; const uint4 *bs; int qp; };
+struct DbkCtx { uint8_t *rec[3]; const uint4 *bs; int qp; uint32_t seq; };
+
+// Row-to-row hand-over ("flag in the data", the scheme of NCCL's LL protocol). The only samples a macroblock row takes from the row above are
+// its 4 bottom luma rows and 2 bottom chroma rows (the p side of the horizontal MB edge). The upper row publishes them per macroblock as 24
+// 8-byte messages {4 samples, sequence number of this launch}: an aligned 64-bit store is single-copy atomic, so a reader that sees the
+// sequence number has the samples -- no fence on the writer's side, no acquire + second load on the reader's, and the messages can be
+// fetched one macroblock ahead like the rest of the prefetch. Message chunk k of a row = columns 16k-4 .. 16k+11 (chroma 8k-4 .. 8k+3):
+// exactly what is final once macroblock k has been filtered (its left edge changed up to 3 columns of k-1, its right 3 are still open).
+// chunk mbw carries the last 4 columns of the row. Layout: [row][chunk 0..mbw][24].
+#define DBK_LL_PER_MB 24
+__device__ __forceinline__ uint2 ld_ll(const uint2 *p)
+{
+    unsigned long long v; asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+}
+__device__ __forceinline__ void st_ll(uint2 *p, uint32_t data, uint32_t seq)
+{
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" :: "l"(p), "l"((unsigned long long)data | ((unsigned long long)seq << 32)) : "memory");
+}
 
 // write-back slots of a lane: word lane + 32k of the luma tile (20 rows x 5 words) / of the two chroma tiles (2 x 12 rows x 3 words);
-// flags: 1 slot exists and is ever stored, 2 it lies in the rows above the MB, 4 it is not in the 4 left columns, 8 (chroma) plane
+// flags: 1 slot exists and is ever stored, 2 it lies in the rows above the MB, 4 it is not in the 4 left columns, 8 (chroma) plane,
+// 16 it lies in the bottom rows the MB row below may still filter (luma 13-15, chroma 6-7).
+// Every sample has ONE writer: the rows above an MB are stored by that MB iff its upper edge is filtered at all (any bS != 0 there) -- and
+// then the MB above leaves its bottom rows alone; otherwise the MB above stores them itself. No two warps ever store the same word, so the
+// global stores need no ordering between rows.
 struct DbkWb { int oy[4], oc[3]; int fy[4], fc[3]; };
 __device__ __forceinline__ void dbk_wb_init(DbkWb &wb, int wc, int lane)
 {
@@ -36,13 +58,13 @@ __device__ __forceinline__ void dbk_wb_init(DbkWb &wb, int wc, int lane)
     for (int k = 0; k < 4; k++) {
         const int i = lane + 32 * k, r = i / 5 - 4, c4 = (i % 5) * 4 - 4;
         wb.oy[k] = r * wc + c4;
-        wb.fy[k] = ((i < 100 && r >= -3) ? 1 : 0) | (r < 0 ? 2 : 0) | (c4 >= 0 ? 4 : 0);
+        wb.fy[k] = ((i < 100 && r >= -3) ? 1 : 0) | (r < 0 ? 2 : 0) | (c4 >= 0 ? 4 : 0) | (r >= 13 ? 16 : 0);
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int i = lane + 32 * k, pl = i / 36, j = i - pl * 36, r = j / 3 - 4, c4 = (j % 3) * 4 - 4;
         wb.oc[k] = r * cw + c4;
-        wb.fc[k] = ((i < 72 && r >= -2) ? 1 : 0) | (r < 0 ? 2 : 0) | (c4 >= 0 ? 4 : 0) | (pl ? 8 : 0);
+        wb.fc[k] = ((i < 72 && r >= -2) ? 1 : 0) | (r < 0 ? 2 : 0) | (c4 >= 0 ? 4 : 0) | (pl ? 8 : 0) | (r >= 6 ? 16 : 0);
     }
 }
 
@@ -131,9 +153,10 @@ __global__ void __launch_bounds__(256) k_deblock_bs(const Sess *ss, Geom g)
 // One MB of the row. Software pipeline of the row loop: the MB's own samples and its MbInfo were prefetched into
 // registers one iteration earlier (nobody else touches them before this MB runs), the 4 left columns are carried over
 // from the previous tile in shared memory, and only the rows above are loaded after the wavefront wait.
-struct DbkPrefetch { uint32_t y0, y1, c; uint4 bs; };
+struct DbkPrefetch { uint32_t y0, y1, c, below; uint4 bs; uint2 ll; };
 
-__device__ __forceinline__ void dbk_prefetch(const DbkCtx &s, const Geom &g, int mx, int my, int lane, DbkPrefetch &pf)
+// ll_above: the messages of the row above (null on row 0); ll_off: this lane's message inside the two chunks macroblock mx reads
+__device__ __forceinline__ void dbk_prefetch(const DbkCtx &s, const Geom &g, int mx, int my, int lane, DbkPrefetch &pf, const uint2 *ll_above, int ll_off)
 {
     const int wc = g.wc, cw = wc / 2, mb = my * g.mbw + mx;
     const uint8_t *Y = s.rec[0] + (size_t)my * 16 * wc + mx * 16;
@@ -144,11 +167,15 @@ __device__ __forceinline__ void dbk_prefetch(const DbkCtx &s, const Geom &g, int
     const uint8_t *C = ((lane >> 4) ? s.rec[2] : s.rec[1]) + (size_t)(my * 8 + ((lane >> 1) & 7)) * cw + mx * 8 + (lane & 1) * 4;
     pf.c = __ldcg(reinterpret_cast<const uint32_t *>(C));
     pf.bs = __ldg(s.bs + mb);        // the MB's 32 boundary strengths (k_deblock_bs), one broadcast load
+    // does the MB below filter its upper edge (bits 16-19 = horizontal edge 0)? Then the bottom rows of this MB are its to store.
+    pf.below = my + 1 < g.mbh ? (__ldg(&s.bs[mb + g.mbw].w) >> 16) & 15u : 0u;
+    pf.ll = make_uint2(0u, 0u);
+    if (ll_above && lane < DBK_LL_PER_MB) pf.ll = ld_ll(ll_above + mx * DBK_LL_PER_MB + ll_off);     // maybe not published yet: checked (and repeated) at use
 }
 
 // returns true when the MB wrote samples (a fence is needed before publishing)
 __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const DbkWb &wb, int mx, int my, int lane, const DbkPrefetch &pf,
-                           const int *prog_above, WaveCtl *ctl, bool &ok
+                           const uint2 *ll_above, int ll_off, const int *prog_above, uint32_t below_prev, WaveCtl *ctl, bool &ok
 #ifdef DBK_TIMING
                            , long long *dbk_t, long long &dbk_last
 #endif
@@ -174,14 +201,30 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
 
     uint8_t *Y = s.rec[0] + (size_t)my * 16 * wc + mx * 16;
     uint8_t *C[2] = { s.rec[1] + (size_t)my * 8 * cw + mx * 8, s.rec[2] + (size_t)my * 8 * cw + mx * 8 };
-    if (my > 0) {
-        // the rows above are final once the upper-right neighbour is done
-        if (!wave_wait(prog_above, min(mx + 2, g.mbw), ctl, lane)) { ok = false; return false; }
-        if (lane < 16) sm.y[(lane >> 2) * 5 + 1 + (lane & 3)] = __ldcg(reinterpret_cast<const uint32_t *>(Y + (ptrdiff_t)((lane >> 2) - 4) * wc + (lane & 3) * 4));
-        else if (lane < 24) {
-            const int pl = (lane >> 2) & 1, r = 2 + ((lane >> 1) & 1), w = lane & 1;     // chroma rows -2, -1
-            sm.c[pl][r * 3 + 1 + w] = __ldcg(reinterpret_cast<const uint32_t *>(C[pl] + (ptrdiff_t)(r - 4) * cw + w * 4));
+    const bool topf = ((pf.bs.w >> 16) & 15u) != 0u;      // the upper MB edge is filtered: the only case that needs (and then stores) the rows above
+    if (topf) {
+        // the rows above are final once the upper-right neighbour is done: their messages carry this launch's sequence number then
+        uint2 v = pf.ll;
+        const bool mine = lane < DBK_LL_PER_MB;
+        if (__ballot_sync(0xffffffffu, mine && v.y != s.seq)) {
+            const uint2 *p = ll_above + mx * DBK_LL_PER_MB + ll_off;
+            unsigned long long t0 = 0; int spins = 0;
+            for (;;) {
+                if (mine && v.y != s.seq) v = ld_ll(p);
+                if (!__ballot_sync(0xffffffffu, mine && v.y != s.seq)) break;
+                // a row that is d macroblocks short of what we need takes d MB-steps: sleep accordingly, so that far-behind rows do not burn
+                // the issue slots of the SMs they share with other kernels (the counter is only this hint, it orders nothing)
+                const int d = min(mx + 2, g.mbw) - ld_relaxed(prog_above);
+                __nanosleep(d > 1 ? min(d * 700, 20000) : 20);
+                if ((++spins & 15) == 0) {
+                    const unsigned long long t = global_ns();
+                    if (!t0) t0 = t;
+                    if (ld_relaxed(&ctl->error) || t - t0 > WAVE_TIMEOUT_NS) { if (lane == 0) atomicExch(&ctl->error, 1); ok = false; return false; }
+                }
+            }
         }
+        if (lane < 16) sm.y[(lane >> 2) * 5 + 1 + (lane & 3)] = v.x;
+        else if (lane < 24) sm.c[(lane >> 2) & 1][(2 + ((lane >> 1) & 1)) * 3 + 1 + (lane & 1)] = v.x;     // chroma rows -2, -1
     }
     __syncwarp();
     DBK_T(2);
@@ -210,16 +253,19 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
     __syncwarp();
     DBK_T(4);
     // write back: the MB with its 4 left columns, and the 3 rows above it (per-lane store slots precomputed once per row)
+    // (one writer per sample, see DbkWb: rows above only when this MB filters its upper edge; bottom rows only when the MB below them does not)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int f = wb.fy[k];
-        const bool st = (f & 1) && ((f & 2) ? ((f & 4) && my > 0) : ((f & 4) || mx > 0));
+        bool st = (f & 1) && ((f & 2) ? ((f & 4) && topf) : ((f & 4) || mx > 0));
+        if ((f & 16) && ((f & 4) ? pf.below : below_prev)) st = false;
         if (st) *reinterpret_cast<uint32_t *>(Y + wb.oy[k]) = sm.y[lane + 32 * k];
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int f = wb.fc[k];
-        const bool st = (f & 1) && ((f & 2) ? ((f & 4) && my > 0) : ((f & 4) || mx > 0));
+        bool st = (f & 1) && ((f & 2) ? ((f & 4) && topf) : ((f & 4) || mx > 0));
+        if ((f & 16) && ((f & 4) ? pf.below : below_prev)) st = false;
         if (st) *reinterpret_cast<uint32_t *>(C[(f >> 3) & 1] + wb.oc[k]) = sm.c[0][lane + 32 * k];
     }
     DBK_T(5);
@@ -233,6 +279,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, DBK_MIN_CTAS) k_deblock_wave(
     __shared__ DbkSmem sm_all[WAVE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     DbkWb wb; dbk_wb_init(wb, g.wc, lane);
+    // this lane's message among the two chunks a macroblock reads: luma lane = (row r, word w) takes columns 4w .. 4w+3 = word w + 1 of the MB's
+    // own chunk, or word 0 of the next chunk for w = 3; chroma lane = (plane, row, word) alike with two words per row
+    const int ll_off = lane < 16 ? ((lane & 3) < 3 ? (lane >> 2) * 4 + (lane & 3) + 1 : DBK_LL_PER_MB + (lane >> 2) * 4)
+                                 : ((lane & 1) == 0 ? 16 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + 1 : DBK_LL_PER_MB + 16 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2);
     // persistent warps: a warp takes the next (row, session) ticket until none is left. Tickets are handed out in wavefront order and a
     // row only ever waits on a row with an earlier ticket, so any number of resident warps makes progress; the grid is sized to the rows a
     // wavefront keeps busy at once (engine.cu) instead of one warp per row holding its registers while it waits for its turn.
@@ -244,33 +294,39 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, DBK_MIN_CTAS) k_deblock_wave(
     const int my = t / nsess;
     const Sess &sg = ss[t % nsess];
     int *prog = sg.row_prog_dbk;
-    DbkCtx s; s.rec[0] = sg.rec[0]; s.rec[1] = sg.rec[1]; s.rec[2] = sg.rec[2]; s.bs = sg.dbk_bs; s.qp = sg.qp;
+    DbkCtx s; s.rec[0] = sg.rec[0]; s.rec[1] = sg.rec[1]; s.rec[2] = sg.rec[2]; s.bs = sg.dbk_bs; s.qp = sg.qp; s.seq = sg.dbk_seq;
+    uint2 *ll_row = sg.dbk_ll + (size_t)my * (g.mbw + 1) * DBK_LL_PER_MB;
+    const uint2 *ll_above = my > 0 ? ll_row - (size_t)(g.mbw + 1) * DBK_LL_PER_MB : nullptr;
+    const bool ll_out = my + 1 < g.mbh;
+    DbkSmem &sm = sm_all[warp];
     DbkPrefetch cur, nxt;
-    dbk_prefetch(s, g, 0, my, lane, cur);
-    int published = 0;
+    dbk_prefetch(s, g, 0, my, lane, cur, ll_above, ll_off);
+    uint32_t below_prev = 0;
 #ifdef DBK_TIMING
     long long dbk_t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, dbk_last = clock64(); int dbk_n = 0;
 #endif
     for (int mx = 0; mx < g.mbw; mx++) {
-        if (mx + 1 < g.mbw) dbk_prefetch(s, g, mx + 1, my, lane, nxt);
+        if (mx + 1 < g.mbw) dbk_prefetch(s, g, mx + 1, my, lane, nxt, ll_above, ll_off);
         DBK_T(0);
         bool ok;
 #ifdef DBK_TIMING
-        const bool wrote = deblock_mb(s, g, sm_all[warp], wb, mx, my, lane, cur, prog + my - 1, ctl, ok, dbk_t, dbk_last); dbk_n += wrote;
+        const bool wrote = deblock_mb(s, g, sm, wb, mx, my, lane, cur, ll_above, ll_off, prog + my - 1, below_prev, ctl, ok, dbk_t, dbk_last); dbk_n += wrote;
 #else
-        const bool wrote = deblock_mb(s, g, sm_all[warp], wb, mx, my, lane, cur, prog + my - 1, ctl, ok);
+        deblock_mb(s, g, sm, wb, mx, my, lane, cur, ll_above, ll_off, prog + my - 1, below_prev, ctl, ok);
 #endif
         if (!ok) return;
-        if (wrote) {
-            fence_acq_rel_gpu();
-            __syncwarp();
-            if (lane == 0) st_relaxed(prog + my, mx + 1);
-            published = mx + 1;
-        } else if (mx + 1 - published >= 4 || mx + 1 == g.mbw) {   // nothing written: publish lazily, in strides
-            if (lane == 0) st_relaxed(prog + my, mx + 1);
-            published = mx + 1;
+        // publish what became final with this MB for the row below (the tile is complete in shared memory, filtered or not)
+        if (ll_out) {
+            uint2 *o = ll_row + mx * DBK_LL_PER_MB;
+            if (lane < DBK_LL_PER_MB) st_ll(o + lane, lane < 16 ? sm.y[(16 + (lane >> 2)) * 5 + (lane & 3)] : sm.c[(lane >> 2) & 1][(10 + ((lane >> 1) & 1)) * 3 + (lane & 1)], s.seq);
+            if (mx + 1 == g.mbw) {      // the last four columns of the row: word 0 of the extra chunk
+                if (lane < 16 && (lane & 3) == 0) st_ll(o + DBK_LL_PER_MB + lane, sm.y[(16 + (lane >> 2)) * 5 + 4], s.seq);
+                else if (lane >= 16 && lane < DBK_LL_PER_MB && (lane & 1) == 0) st_ll(o + DBK_LL_PER_MB + lane, sm.c[(lane >> 2) & 1][(10 + ((lane >> 1) & 1)) * 3 + 2], s.seq);
+            }
+            if (lane == 0) st_relaxed(prog + my, mx + 1);       // distance hint for the sleeping readers
         }
         DBK_T(6);
+        below_prev = cur.below;
         cur = nxt;
     }
 #ifdef DBK_TIMING

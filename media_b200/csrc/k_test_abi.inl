@@ -112,10 +112,13 @@ int b200k_deblock(int device, uint8_t *i420, int mbw, int mbh, const void *mbinf
     Geom g; fill_geom(g, mbw * 16, mbh * 16, 1, 16);
     const size_t ny = (size_t)g.wc * g.hc, nmb = (size_t)mbw * mbh;
     DevBuf dpix(ny * 3 / 2), dmbi(nmb * sizeof(MbInfo)), dbs(nmb * sizeof(uint4)), dprog((size_t)mbh * 8), dsess(sizeof(Sess)), dctl(sizeof(WaveCtl));
-    if (!dpix.p || !dmbi.p || !dbs.p || !dprog.p || !dsess.p || !dctl.p) return B200ENC_ENOMEM;
+    DevBuf dll((size_t)mbh * (mbw + 1) * DBK_LL_PER_MB * sizeof(uint2));
+    if (!dpix.p || !dmbi.p || !dbs.p || !dprog.p || !dsess.p || !dctl.p || !dll.p) return B200ENC_ENOMEM;
+    K_TRY(cudaMemset(dll.p, 0, (size_t)mbh * (mbw + 1) * DBK_LL_PER_MB * sizeof(uint2)));
     Sess s; memset(&s, 0, sizeof s);
     s.rec[0] = dpix.as<uint8_t>(); s.rec[1] = s.rec[0] + ny; s.rec[2] = s.rec[1] + ny / 4; s.mbi = dmbi.as<MbInfo>(); s.dbk_bs = dbs.as<uint4>();
     s.row_prog_intra = dprog.as<int>(); s.row_prog_dbk = dprog.as<int>() + mbh; s.qp = qp;
+    s.dbk_ll = dll.as<uint2>(); s.dbk_seq = 1;
     K_TRY(cudaMemcpy(dpix.p, i420, ny * 3 / 2, cudaMemcpyHostToDevice));
     K_TRY(cudaMemcpy(dmbi.p, mbinfo, nmb * sizeof(MbInfo), cudaMemcpyHostToDevice));
     K_TRY(cudaMemcpy(dsess.p, &s, sizeof s, cudaMemcpyHostToDevice));
