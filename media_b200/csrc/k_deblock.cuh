@@ -14,7 +14,7 @@
 namespace b200 {
 
 #ifndef DBK_MIN_CTAS
-#define DBK_MIN_CTAS 6      /* resident CTAs per SM the register allocation must allow: 76 registers, no spills (8 -> 64 registers spills and is slower) */
+#define DBK_MIN_CTAS 4      /* resident CTAs per SM the register allocation must allow (128 registers: the column of 20 samples of the horizontal pass lives in registers) */
 #endif
 #ifdef DBK_TIMING
 #define DBK_T(i) do { const long long t_ = clock64(); dbk_t[i] += t_ - dbk_last; dbk_last = t_; } while (0)
@@ -25,6 +25,8 @@ namespace b200 {
 // the few session fields the row loop needs, held in registers: every fence / strong access in the loop is a compiler memory
 // barrier, so reading them through `const Sess &` re-fetched them from L2 several times per macroblock (1 800 cycles measured)
 struct DbkCtx { uint8_t *rec[3]; const uint4 *bs; int qp; uint32_t seq; };
+// per-lane filter constants of a row (one QP per picture): lanes 0-15 the luma values, lanes 16-31 the chroma ones; tc0 for bS 1, 2, 3
+struct DbkK { int alpha, beta, tc0[3]; };
 
 // Row-to-row hand-over ("flag in the data", the scheme of NCCL's LL protocol). The only samples a macroblock row takes from the row above are
 // its 4 bottom luma rows and 2 bottom chroma rows (the p side of the horizontal MB edge). The upper row publishes them per macroblock as 24
@@ -73,38 +75,44 @@ struct DbkSmem {
     uint32_t c[2][12 * 3];     // rows -4..7, cols -4..7 (stride 12 bytes)
 };
 
-// One edge position of one line of samples, luma or chroma in the same instruction stream (8.7.2.3 / 8.7.2.4): the 16 luma
-// lines and the 16 chroma lines of a macroblock edge are filtered by the 32 lanes at once instead of one after the other.
-// Chroma uses only p1..q1, tc = tc0 + 1 and the weak bS = 4 filter; the selects below fold that in.
-__device__ __forceinline__ void filter_edge(uint8_t *p, int step, int bs, int alpha, int beta, int tc0, bool chroma)
+// One line of samples across one edge, in registers and branch-free (8.7.2.3 / 8.7.2.4): p3 p2 p1 p0 | q0 q1 q2 q3. The 16 luma lines and the
+// 16 chroma lines of a macroblock edge are filtered by the 32 lanes in one instruction stream. Chroma uses only p1..q1, tc = tc0 + 1 and the
+// weak bS = 4 filter; the selects fold that in. ANY_STRONG: some lane of the warp has bS = 4 (warp-uniform, so the strong filter's
+// arithmetic is only issued on macroblock edges of intra macroblocks).
+template <bool ANY_STRONG>
+__device__ __forceinline__ void filter_line(int p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int q3, int bs, int alpha, int beta, int tc0, bool chroma)
 {
-    const int p0 = p[-step], p1 = p[-2 * step], q0 = p[0], q1 = p[step];
-    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-    int p2 = 0, q2 = 0;
-    if (!chroma) { p2 = p[-3 * step]; q2 = p[2 * step]; }
+    const int d = abs(p0 - q0);
+    const bool on = bs != 0 && d < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
     const bool ap = !chroma && abs(p2 - p0) < beta, aq = !chroma && abs(q2 - q0) < beta;
-    if (bs < 4) {
-        const int tc = chroma ? tc0 + 1 : tc0 + (int)ap + (int)aq;
-        const int delta = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
-        p[-step] = (uint8_t)clip255(p0 + delta);
-        p[0] = (uint8_t)clip255(q0 - delta);
-        if (ap) p[-2 * step] = (uint8_t)(p1 + clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1));
-        if (aq) p[step] = (uint8_t)(q1 + clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1));
-    } else {
-        const bool small = abs(p0 - q0) < ((alpha >> 2) + 2);
-        if (ap && small) {
-            const int p3 = p[-4 * step];
-            p[-step] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-            p[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
-            p[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-        } else p[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        if (aq && small) {
-            const int q3 = p[3 * step];
-            p[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-            p[step] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
-            p[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
-        } else p[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+    const int tc = chroma ? tc0 + 1 : tc0 + (int)ap + (int)aq;
+    const int delta = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+    const int avg = (p0 + q0 + 1) >> 1;
+    int n0 = clip255(p0 + delta), m0 = clip255(q0 - delta);
+    int n1 = ap ? p1 + clip3(-tc0, tc0, (p2 + avg - (p1 << 1)) >> 1) : p1;
+    int m1 = aq ? q1 + clip3(-tc0, tc0, (q2 + avg - (q1 << 1)) >> 1) : q1;
+    int n2 = p2, m2 = q2;
+    if (ANY_STRONG) {
+        const bool strong = bs == 4, small = d < ((alpha >> 2) + 2), sp = ap && small, sq = aq && small;
+        const int s0 = sp ? (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3 : (2 * p1 + p0 + q1 + 2) >> 2;
+        const int s1 = sp ? (p2 + p1 + p0 + q0 + 2) >> 2 : p1;
+        const int s2 = sp ? (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3 : p2;
+        const int t0 = sq ? (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3 : (2 * q1 + q0 + p1 + 2) >> 2;
+        const int t1 = sq ? (p0 + q0 + q1 + q2 + 2) >> 2 : q1;
+        const int t2 = sq ? (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3 : q2;
+        if (strong) { n0 = s0; n1 = s1; n2 = s2; m0 = t0; m1 = t1; m2 = t2; }
     }
+    if (on) { p0 = n0; p1 = n1; p2 = n2; q0 = m0; q1 = m1; q2 = m2; }
+}
+// the filter across the boundary between two words of a row: wl = .. p3 p2 p1 p0 (low to high byte), wr = q0 q1 q2 q3
+template <bool ANY_STRONG>
+__device__ __forceinline__ void filter_words(uint32_t &wl, uint32_t &wr, int bs, int alpha, int beta, int tc0, bool chroma)
+{
+    int p3 = wl & 255, p2 = (wl >> 8) & 255, p1 = (wl >> 16) & 255, p0 = wl >> 24;
+    int q0 = wr & 255, q1 = (wr >> 8) & 255, q2 = (wr >> 16) & 255, q3 = wr >> 24;
+    filter_line<ANY_STRONG>(p3, p2, p1, p0, q0, q1, q2, q3, bs, alpha, beta, tc0, chroma);
+    wl = (uint32_t)p3 | ((uint32_t)p2 << 8) | ((uint32_t)p1 << 16) | ((uint32_t)p0 << 24);
+    wr = (uint32_t)q0 | ((uint32_t)q1 << 8) | ((uint32_t)q2 << 16) | ((uint32_t)q3 << 24);
 }
 
 // boundary strength between 4x4 block (bxp,byp) of MB p and block (bxq,byq) of MB q (8.7.2.1, frame pictures, one reference)
@@ -168,20 +176,20 @@ __device__ __forceinline__ void dbk_prefetch(const DbkCtx &s, const Geom &g, int
     pf.c = __ldcg(reinterpret_cast<const uint32_t *>(C));
     pf.bs = __ldg(s.bs + mb);        // the MB's 32 boundary strengths (k_deblock_bs), one broadcast load
     // does the MB below filter its upper edge (bits 16-19 = horizontal edge 0)? Then the bottom rows of this MB are its to store.
-    pf.below = my + 1 < g.mbh ? (__ldg(&s.bs[mb + g.mbw].w) >> 16) & 15u : 0u;
+    pf.below = my + 1 < g.mbh ? __ldg(&s.bs[mb + g.mbw].w) : 0u;      // (used as (below >> 16) & 15 -- not here: that would wait for the load)
     pf.ll = make_uint2(0u, 0u);
     if (ll_above && lane < DBK_LL_PER_MB) pf.ll = ld_ll(ll_above + mx * DBK_LL_PER_MB + ll_off);     // maybe not published yet: checked (and repeated) at use
 }
 
 // returns true when the MB wrote samples (a fence is needed before publishing)
-__device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const DbkWb &wb, int mx, int my, int lane, const DbkPrefetch &pf,
+__device__ bool deblock_mb(const DbkCtx &s, const DbkK &k, const Geom &g, DbkSmem &sm, const DbkWb &wb, int mx, int my, int lane, const DbkPrefetch &pf,
                            const uint2 *ll_above, int ll_off, const int *prog_above, uint32_t below_prev, WaveCtl *ctl, bool &ok
 #ifdef DBK_TIMING
                            , long long *dbk_t, long long &dbk_last
 #endif
                            )
 {
-    const int wc = g.wc, cw = wc / 2, qp = s.qp, qpc = c_chroma_qp[qp];
+    const int wc = g.wc, cw = wc / 2;
     ok = true;
     __syncwarp();
     // carry the previous tile's right columns / MbInfo over as this MB's left neighbour, then drop in the prefetched data
@@ -194,8 +202,6 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
     sm.y[((lane >> 2) + 12) * 5 + 1 + (lane & 3)] = pf.y1;
     sm.c[lane >> 4][(((lane >> 1) & 7) + 4) * 3 + 1 + (lane & 1)] = pf.c;
     __syncwarp();
-    // lanes 0-15: bS of vertical edge e, segment k; lanes 16-31: horizontal edge e, segment k (precomputed by k_deblock_bs)
-    const int bs = (int)(((pf.bs.x >> lane) & 1u) | (((pf.bs.y >> lane) & 1u) << 1) | (((pf.bs.z >> lane) & 1u) << 2));
     DBK_T(1);
     if (pf.bs.w == 0u) return false;
 
@@ -228,27 +234,67 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
     }
     __syncwarp();
     DBK_T(2);
-    const int alphaY = c_alpha[qp], betaY = c_beta[qp], alphaC = c_alpha[qpc], betaC = c_beta[qpc];
-    uint8_t *ty = reinterpret_cast<uint8_t *>(sm.y) + 4 * 20 + 4;            // sample (0,0) of the MB
-    uint8_t *tc = reinterpret_cast<uint8_t *>(sm.c[(lane >> 3) & 1]) + 4 * 12 + 4;
+    // lane's boundary strength at edge e of the given direction (bit planes of k_deblock_bs: lane 4e + seg vertical, 16 + 4e + seg horizontal)
     const bool isc = lane >= 16;
-    const int qpl = isc ? qpc : qp, alphaL = isc ? alphaC : alphaY, betaL = isc ? betaC : betaY;
     const int seg = isc ? (lane & 7) >> 1 : lane >> 2;
-    // vertical edges (filtering across columns), left to right; chroma lines take part in the even ones
-#pragma unroll 1
-    for (int e = 0; e < 4; e++) {
-        const int b = __shfl_sync(0xffffffffu, bs, e * 4 + seg);
-        uint8_t *p = isc ? tc + (lane & 7) * 12 + 2 * e : ty + lane * 20 + 4 * e;
-        if (b && !(isc && (e & 1))) filter_edge(p, 1, b, alphaL, betaL, b < 4 ? c_tc0[qpl][b - 1] : 0, isc);
+    auto bs_at = [&](int i) { return (int)(((pf.bs.x >> i) & 1u) | (((pf.bs.y >> i) & 1u) << 1) | (((pf.bs.z >> i) & 1u) << 2)); };
+    auto tc0_of = [&](int b) { return b == 1 ? k.tc0[0] : b == 2 ? k.tc0[1] : k.tc0[2]; };
+    // vertical edges (filtering across columns), left to right: lane = row (lanes 0-15 luma rows, 16-31 the 2 x 8 chroma rows), the row in
+    // registers across all four edges. Chroma rows take part in edges 0 and 2 (their columns 0 and 4): word pairs (W0,W1) and (W2,W3), where
+    // W2 is the chroma row's middle word again (refreshed after edge 0) and W3 its last.
+    if (pf.bs.w & 0xffffu) {
+        uint32_t *row = isc ? sm.c[(lane >> 3) & 1] + ((lane & 7) + 4) * 3 : sm.y + (lane + 4) * 5;
+        uint32_t W0 = row[0], W1 = row[1], W2 = row[2], W3 = 0, W4 = 0;
+        if (!isc) { W3 = row[3]; W4 = row[4]; } else { W3 = W2; W2 = W1; }
+        {
+            const int b = bs_at(seg);
+            if ((pf.bs.w & 0xfu) != 0u) {
+                if (__any_sync(0xffffffffu, b == 4)) filter_words<true>(W0, W1, b, k.alpha, k.beta, tc0_of(b), isc);
+                else filter_words<false>(W0, W1, b, k.alpha, k.beta, tc0_of(b), isc);
+            }
+            if (isc) W2 = W1;
+        }
+        if ((pf.bs.w & 0xf0u) != 0u) { const int b = isc ? 0 : bs_at(4 + seg); filter_words<false>(W1, W2, b, k.alpha, k.beta, tc0_of(b), false); }
+        if ((pf.bs.w & 0xf00u) != 0u) { const int b = bs_at(8 + seg); filter_words<false>(W2, W3, b, k.alpha, k.beta, tc0_of(b), isc); }
+        if ((pf.bs.w & 0xf000u) != 0u) { const int b = isc ? 0 : bs_at(12 + seg); filter_words<false>(W3, W4, b, k.alpha, k.beta, tc0_of(b), false); }
+        row[0] = W0;
+        if (!isc) { row[1] = W1; row[2] = W2; row[3] = W3; row[4] = W4; } else { row[1] = W2; row[2] = W3; }
     }
     __syncwarp();
     DBK_T(3);
-    // horizontal edges (filtering across rows), top to bottom
-#pragma unroll 1
-    for (int e = 0; e < 4; e++) {
-        const int b = __shfl_sync(0xffffffffu, bs, 16 + e * 4 + seg);
-        uint8_t *p = isc ? tc + 2 * e * 12 + (lane & 7) : ty + 4 * e * 20 + lane;
-        if (b && !(isc && (e & 1))) filter_edge(p, isc ? 12 : 20, b, alphaL, betaL, b < 4 ? c_tc0[qpl][b - 1] : 0, isc);
+    // horizontal edges (filtering across rows), top to bottom: lane = column (lanes 0-15 luma, 16-31 the 2 x 8 chroma columns), the column in
+    // registers across all four edges. v[i] = luma row i - 4; a chroma column keeps rows -2 .. 1 in v[2..5] (edge 0) and rows 2 .. 5 in
+    // v[10..13] (edge 2), exactly where the luma edges' p1 p0 q0 q1 sit, so both share one instruction stream.
+    if (pf.bs.w & 0xffff0000u) {
+        uint8_t *colA = isc ? reinterpret_cast<uint8_t *>(sm.c[(lane >> 3) & 1]) + 4 + (lane & 7) : reinterpret_cast<uint8_t *>(sm.y) + 4 + lane;
+        uint8_t *colB = isc ? colA + 4 * 12 : colA + 8 * 20;          // v[8 + j] = row j of colB
+        const int st = isc ? 12 : 20;
+        int v[20];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (!isc || (i >= 2 && i < 6)) ? colA[i * st] : 0;
+#pragma unroll
+        for (int i = 8; i < 16; i++) v[i] = (!isc || (i >= 10 && i < 14)) ? colB[(i - 8) * st] : 0;
+#pragma unroll
+        for (int i = 16; i < 20; i++) v[i] = !isc ? colB[(i - 8) * st] : 0;
+        {
+            const int b = bs_at(16 + seg);
+            if ((pf.bs.w & 0xf0000u) != 0u) {
+                if (__any_sync(0xffffffffu, b == 4)) filter_line<true>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], b, k.alpha, k.beta, tc0_of(b), isc);
+                else filter_line<false>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], b, k.alpha, k.beta, tc0_of(b), isc);
+            }
+        }
+        if ((pf.bs.w & 0xf00000u) != 0u) { const int b = isc ? 0 : bs_at(20 + seg); filter_line<false>(v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], b, k.alpha, k.beta, tc0_of(b), false); }
+        if ((pf.bs.w & 0xf000000u) != 0u) { const int b = bs_at(24 + seg); filter_line<false>(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], b, k.alpha, k.beta, tc0_of(b), isc); }
+        if ((pf.bs.w & 0xf0000000u) != 0u) { const int b = isc ? 0 : bs_at(28 + seg); filter_line<false>(v[12], v[13], v[14], v[15], v[16], v[17], v[18], v[19], b, k.alpha, k.beta, tc0_of(b), false); }
+        // a luma column stores rows -3 .. 14 (bS < 4 inside the MB: row 15 is nobody's p or q side here); a chroma column rows -1, 0, 3, 4
+        if (!isc) {
+#pragma unroll
+            for (int i = 1; i < 8; i++) colA[i * 20] = (uint8_t)v[i];
+#pragma unroll
+            for (int i = 8; i < 19; i++) colB[(i - 8) * 20] = (uint8_t)v[i];
+        } else {
+            colA[3 * 12] = (uint8_t)v[3]; colA[4 * 12] = (uint8_t)v[4]; colB[3 * 12] = (uint8_t)v[11]; colB[4 * 12] = (uint8_t)v[12];
+        }
     }
     __syncwarp();
     DBK_T(4);
@@ -258,14 +304,14 @@ __device__ bool deblock_mb(const DbkCtx &s, const Geom &g, DbkSmem &sm, const Db
     for (int k = 0; k < 4; k++) {
         const int f = wb.fy[k];
         bool st = (f & 1) && ((f & 2) ? ((f & 4) && topf) : ((f & 4) || mx > 0));
-        if ((f & 16) && ((f & 4) ? pf.below : below_prev)) st = false;
+        if ((f & 16) && (((f & 4) ? pf.below : below_prev) & 0xf0000u)) st = false;
         if (st) *reinterpret_cast<uint32_t *>(Y + wb.oy[k]) = sm.y[lane + 32 * k];
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int f = wb.fc[k];
         bool st = (f & 1) && ((f & 2) ? ((f & 4) && topf) : ((f & 4) || mx > 0));
-        if ((f & 16) && ((f & 4) ? pf.below : below_prev)) st = false;
+        if ((f & 16) && (((f & 4) ? pf.below : below_prev) & 0xf0000u)) st = false;
         if (st) *reinterpret_cast<uint32_t *>(C[(f >> 3) & 1] + wb.oc[k]) = sm.c[0][lane + 32 * k];
     }
     DBK_T(5);
@@ -299,6 +345,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, DBK_MIN_CTAS) k_deblock_wave(
     const uint2 *ll_above = my > 0 ? ll_row - (size_t)(g.mbw + 1) * DBK_LL_PER_MB : nullptr;
     const bool ll_out = my + 1 < g.mbh;
     DbkSmem &sm = sm_all[warp];
+    DbkK kc;
+    { const int q_ = lane < 16 ? s.qp : (int)c_chroma_qp[s.qp]; kc.alpha = c_alpha[q_]; kc.beta = c_beta[q_]; kc.tc0[0] = c_tc0[q_][0]; kc.tc0[1] = c_tc0[q_][1]; kc.tc0[2] = c_tc0[q_][2]; }
     DbkPrefetch cur, nxt;
     dbk_prefetch(s, g, 0, my, lane, cur, ll_above, ll_off);
     uint32_t below_prev = 0;
@@ -310,9 +358,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, DBK_MIN_CTAS) k_deblock_wave(
         DBK_T(0);
         bool ok;
 #ifdef DBK_TIMING
-        const bool wrote = deblock_mb(s, g, sm, wb, mx, my, lane, cur, ll_above, ll_off, prog + my - 1, below_prev, ctl, ok, dbk_t, dbk_last); dbk_n += wrote;
+        const bool wrote = deblock_mb(s, kc, g, sm, wb, mx, my, lane, cur, ll_above, ll_off, prog + my - 1, below_prev, ctl, ok, dbk_t, dbk_last); dbk_n += wrote;
 #else
-        deblock_mb(s, g, sm, wb, mx, my, lane, cur, ll_above, ll_off, prog + my - 1, below_prev, ctl, ok);
+        deblock_mb(s, kc, g, sm, wb, mx, my, lane, cur, ll_above, ll_off, prog + my - 1, below_prev, ctl, ok);
 #endif
         if (!ok) return;
         // publish what became final with this MB for the row below (the tile is complete in shared memory, filtered or not)
