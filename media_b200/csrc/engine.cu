@@ -435,7 +435,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     // the latency-bound wavefront and the issue-bound CAVLC chain overlap on two streams and join before the read-back
     cudaStream_t s2 = b->stream2;
     cudaEventRecord(b->ev_fork, sw); cudaStreamWaitEvent(s2, b->ev_fork, 0);
-    pf.begin("k_deblock_bs", sw); k_deblock_bs<<<dim3((nmb + 7) / 8, 1, n), 256, 0, sw>>>(b->d_sess, g); pf.end(); launches++;
+    pf.begin("k_deblock_bs", sw); k_deblock_bs<<<dim3((nmb + 127) / 128, 1, n), 128, 0, sw>>>(b->d_sess, g); pf.end(); launches++;
     const int dbk_ctas = resident_ctas(dbk_resident_pct());
     pf.begin("k_deblock_wave", sw); k_deblock_wave<<<dbk_ctas, WAVE_WARPS * 32, 0, sw>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
     if (sw != st) { cudaEventRecord(b->ev_wave1, sw); cudaStreamWaitEvent(st, b->ev_wave1, 0); }

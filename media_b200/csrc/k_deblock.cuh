@@ -127,35 +127,82 @@ __device__ __forceinline__ int bs_of(const MbInfo *p, int bxp, int byp, const Mb
 }
 
 // Boundary strengths of every macroblock, ahead of the wavefront: they only depend on the MbInfo records (types, nnz, vectors), not on
-// samples, so they are computed fully in parallel -- warp per MB, lanes 0-15 = vertical edge e, segment k (lane = 4e + k), lanes 16-31 the
-// horizontal ones -- and stored as three bit planes of the 32 values (x, y, z = bits 0, 1, 2 of bS by lane; w = their OR). In the row loop
-// of k_deblock_wave this was 48 % of the executed instructions and a third of the stall samples (ncu, profiles/r01_ncu_summary.md).
-// grid: (ceil(n_mb / 8), 1, sessions), 256 threads
-__global__ void __launch_bounds__(256) k_deblock_bs(const Sess *ss, Geom g)
+// samples, so they are computed fully in parallel and stored as three bit planes of the 32 values (index 4e + k = vertical edge e, segment k;
+// 16 + 4e + k horizontal; x, y, z = bits 0, 1, 2 of bS; w = their OR). In the row loop of k_deblock_wave this was 48 % of the executed
+// instructions (ncu, profiles/r01_ncu_summary.md); as a warp per MB with a lane per value it still was 331 warp-instructions per MB
+// (profiles/r02a_ncu_summary.md). Here a THREAD owns a macroblock and works on whole bit masks: the nonzero flags of the 16 luma blocks as a
+// raster 4x4 mask (an OR with its shifts gives every internal edge at once), vector differences only where partitions meet (edge 2 and the
+// MB edges), the intra / 8x8-transform rules as mask selects.
+// grid: (ceil(n_mb / 128), 1, sessions), 128 threads
+__device__ __forceinline__ uint32_t nz_bits4(uint32_t w)     // bit i = byte i of w is nonzero
 {
-    __shared__ uint32_t info_all[8][3][12];                           // per warp: MbInfo of the current, left and upper MB
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, mb = blockIdx.x * 8 + warp;
+    const uint32_t m = ((w & 0x7f7f7f7fu) + 0x7f7f7f7fu | w) & 0x80808080u;
+    return ((m >> 7) * 0x00204081u >> 21) & 15u;
+}
+__device__ __forceinline__ uint32_t blk_to_raster(uint32_t m)   // 16 flags in blkIdx order (Figure 6-10) -> raster order y * 4 + x: index bits 1 and 2 swap
+{
+    return (m & 0xC3C3u) | ((m & 0x0C0Cu) << 2) | ((m & 0x3030u) >> 2);
+}
+__device__ __forceinline__ bool mv_far(uint32_t a, uint32_t b)  // packed (x, y) int16 vectors at least 4 quarter-samples apart in a component
+{
+    const int dx = (int)(short)(a & 0xffffu) - (int)(short)(b & 0xffffu), dy = ((int)a >> 16) - ((int)b >> 16);
+    return abs(dx) >= 4 || abs(dy) >= 4;
+}
+__device__ __forceinline__ bool type_is_intra(uint32_t w0) { const uint32_t t = w0 & 255u; return t == MB_I16x16 || t == MB_I4x4 || t == MB_I8x8; }
+__global__ void __launch_bounds__(128) k_deblock_bs(const Sess *ss, Geom g)
+{
+    const int mb = blockIdx.x * 128 + threadIdx.x;
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
     const int mx = mb % g.mbw, my = mb / g.mbw;
-    uint32_t (*info)[12] = info_all[warp];
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(s.mbi + mb);
-        if (lane < 12) info[0][lane] = src[lane];
-        else if (lane < 24) { if (mx > 0) info[1][lane - 12] = src[lane - 24]; }                       // (mb - 1) * 12 + lane - 12
-        if (lane < 12 && my > 0) info[2][lane] = src[lane - 12 * g.mbw];
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(s.mbi + mb);
+    const uint4 a = *reinterpret_cast<const uint4 *>(q), b = *reinterpret_cast<const uint4 *>(q + 4), c = *reinterpret_cast<const uint4 *>(q + 8);
+    // a.x type word, a.z a.w b.x b.y the four partition vectors, b.z b.w c.x c.y the 16 luma nnz
+    const bool intra = type_is_intra(a.x), t8 = (a.x >> 10) & 1u;
+    const uint32_t nzr = blk_to_raster(nz_bits4(b.z) | (nz_bits4(b.w) << 4) | (nz_bits4(c.x) << 8) | (nz_bits4(c.y) << 12));
+    uint32_t p1 = 0, p2 = 0, p4 = 0;       // planes: value 1 (vector), value 2 (coefficients) or 3 (intra, both), value 4
+    if (intra) { p1 = p2 = 0xfff0fff0u; }
+    else {
+        // internal edges: a block or its neighbour across the edge has coefficients
+        const uint32_t V = (nzr | (nzr << 1)) & 0xeeeeu;             // bit 4y + e: vertical edge e >= 1, row y
+        // transpose the 4x4 bit matrix (index 4y + e -> 4e + y)
+        uint32_t t = V;
+        t = (t & 0xA5A5u) | ((t & 0x0A0Au) << 3) | ((t & 0x5050u) >> 3);
+        t = (t & 0xCC33u) | ((t & 0x00CCu) << 6) | ((t & 0x3300u) >> 6);
+        const uint32_t H = (nzr | (nzr << 4)) & 0xfff0u;             // bit 4e + x: horizontal edge e >= 1, column x
+        p2 = t | (H << 16);
+        // vectors only differ where 8x8 partitions meet: edge 2
+        const uint32_t v2 = (mv_far(a.z, a.w) ? 0x300u : 0u) | (mv_far(b.x, b.y) ? 0xC00u : 0u);
+        const uint32_t h2 = (mv_far(a.z, b.x) ? 0x300u : 0u) | (mv_far(a.w, b.y) ? 0xC00u : 0u);
+        p1 = (v2 | (h2 << 16)) & ~p2;
     }
-    __syncwarp();
-    const MbInfo *q = reinterpret_cast<const MbInfo *>(info[0]), *ql = reinterpret_cast<const MbInfo *>(info[1]), *qt = reinterpret_cast<const MbInfo *>(info[2]);
-    const int e = (lane >> 2) & 3, k = lane & 3; const bool vert = lane < 16;
-    int bs;
-    if (e == 0) {
-        if (vert) bs = mx > 0 ? bs_of(ql, 3, k, q, 0, k, true) : 0;
-        else bs = my > 0 ? bs_of(qt, k, 3, q, k, 0, true) : 0;
-    } else if ((e & 1) && mb_t8(q)) bs = 0;                           // transform_size_8x8_flag: only the 8x8 transform edges are filtered
-    else bs = vert ? bs_of(q, e - 1, k, q, e, k, false) : bs_of(q, k, e - 1, q, k, e, false);
-    const uint32_t b0 = __ballot_sync(0xffffffffu, bs & 1), b1 = __ballot_sync(0xffffffffu, bs & 2), b2 = __ballot_sync(0xffffffffu, bs & 4);
-    if (lane == 0) s.dbk_bs[mb] = make_uint4(b0, b1, b2, b0 | b1 | b2);
+    if (mx > 0) {
+        const uint32_t *l = q - 12;
+        if (intra || type_is_intra(l[0])) p4 |= 0xfu;
+        else {
+            // left MB: blocks (3, y) = blkIdx 5, 7, 13, 15; this MB: blocks (0, y) = raster bits 0, 4, 8, 12
+            const uint32_t n1 = l[7], n3 = l[9];
+            const uint32_t ln = ((n1 >> 8) & 255u ? 1u : 0u) | ((n1 >> 24) ? 2u : 0u) | ((n3 >> 8) & 255u ? 4u : 0u) | ((n3 >> 24) ? 8u : 0u);
+            const uint32_t cn = (nzr & 1u) | ((nzr >> 3) & 2u) | ((nzr >> 6) & 4u) | ((nzr >> 9) & 8u);
+            const uint32_t e2 = ln | cn;
+            const uint32_t e1 = (mv_far(l[3], a.z) ? 0x3u : 0u) | (mv_far(l[5], b.x) ? 0xCu : 0u);
+            p2 |= e2; p1 |= e1 & ~e2;
+        }
+    }
+    if (my > 0) {
+        const uint32_t *u = q - 12 * g.mbw;
+        if (intra || type_is_intra(u[0])) p4 |= 0xf0000u;
+        else {
+            // upper MB: blocks (x, 3) = blkIdx 10, 11, 14, 15; this MB: blocks (x, 0) = raster bits 0..3
+            const uint32_t n2 = u[8], n3 = u[9];
+            const uint32_t un = ((n2 >> 16) & 255u ? 1u : 0u) | ((n2 >> 24) ? 2u : 0u) | ((n3 >> 16) & 255u ? 4u : 0u) | ((n3 >> 24) ? 8u : 0u);
+            const uint32_t e2 = un | (nzr & 15u);
+            const uint32_t e1 = (mv_far(u[4], a.z) ? 0x3u : 0u) | (mv_far(u[5], a.w) ? 0xCu : 0u);
+            p2 |= e2 << 16; p1 |= (e1 & ~e2) << 16;
+        }
+    }
+    if (t8) { p1 &= 0x0f0f0f0fu; p2 &= 0x0f0f0f0fu; }          // transform_size_8x8_flag: only the 8x8 transform edges are filtered
+    s.dbk_bs[mb] = make_uint4(p1, p2, p4, p1 | p2 | p4);
 }
 
 // One MB of the row. Software pipeline of the row loop: the MB's own samples and its MbInfo were prefetched into

@@ -123,7 +123,7 @@ int b200k_deblock(int device, uint8_t *i420, int mbw, int mbh, const void *mbinf
     K_TRY(cudaMemcpy(dmbi.p, mbinfo, nmb * sizeof(MbInfo), cudaMemcpyHostToDevice));
     K_TRY(cudaMemcpy(dsess.p, &s, sizeof s, cudaMemcpyHostToDevice));
     k_reset<<<(mbh + 255) / 256, 256>>>(dsess.as<Sess>(), g, 1, dctl.as<WaveCtl>());
-    k_deblock_bs<<<dim3((unsigned)((nmb + 7) / 8), 1, 1), 256>>>(dsess.as<Sess>(), g);
+    k_deblock_bs<<<dim3((unsigned)((nmb + 127) / 128), 1, 1), 128>>>(dsess.as<Sess>(), g);
     k_deblock_wave<<<(mbh + WAVE_WARPS - 1) / WAVE_WARPS, WAVE_WARPS * 32>>>(dsess.as<Sess>(), g, 1, dctl.as<WaveCtl>());
     K_TRY(cudaGetLastError());
     K_TRY(cudaMemcpy(i420, dpix.p, ny * 3 / 2, cudaMemcpyDeviceToHost));
