@@ -278,14 +278,22 @@ def run_b200(args):
         # once (the frames of a step are S x fb bytes per GPU), and the staging memcpy rate of this host (pageable -> pinned, all caller threads)
         h2d = None
         try:
-            nbuf = 32
+            # four streams, a frame per copy: what the sessions' upload streams do (one stream alone stays below the link's rate)
+            nbuf, nst = 32, 4
             hp = torch.empty(nbuf * fb, dtype=torch.uint8).pin_memory(); dp_ = torch.empty(nbuf * fb, dtype=torch.uint8, device=f"cuda:{dev}")
             dp_.copy_(hp, non_blocking=True); torch.cuda.synchronize()
+            sts = [torch.cuda.Stream(device=dev) for _ in range(nst)]
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(6):
-                dp_.copy_(hp, non_blocking=True)
+            for st_ in sts:
+                st_.wait_stream(torch.cuda.current_stream())
+            for rep in range(6):
+                for k in range(nbuf):
+                    with torch.cuda.stream(sts[k % nst]):
+                        dp_[k * fb:(k + 1) * fb].copy_(hp[k * fb:(k + 1) * fb], non_blocking=True)
+            for st_ in sts:
+                torch.cuda.current_stream().wait_stream(st_)
             e1.record(); torch.cuda.synchronize()
             gbs = 6 * nbuf * fb / (e0.elapsed_time(e1) * 1e-3) / 1e9
             t = torch.tensor([gbs], dtype=torch.float64)

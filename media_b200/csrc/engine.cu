@@ -148,6 +148,7 @@ struct b200enc_batch {
     bool profiling = false;
     std::vector<KernelTime> ktimes; int n_ktimes = 0;
     std::vector<int> last_rcs;                          // per-session outcome of the last b200enc_batch_encode
+    double t_pre = 0, t_launch = 0, t_sync = 0, t_dev = 0; int t_steps = 0;   // B200ENC_TRACE=1: host-clock split of launch_step, printed when the batch closes
 };
 
 struct b200enc_session {
@@ -228,6 +229,8 @@ int batch_init(b200enc_batch *b, int device, int cap)
 void batch_free(b200enc_batch *b)
 {
     if (!b) return;
+    if (b->t_steps) fprintf(stderr, "[b200enc trace] batch %p: %d steps, per step: descriptors+upload %.3f ms, launches %.3f ms, wait %.3f ms (host clock); device ev0..ev1 %.3f ms\n",
+                            (void *)b, b->t_steps, b->t_pre / b->t_steps, b->t_launch / b->t_steps, b->t_sync / b->t_steps, b->t_dev / b->t_steps);
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (auto &k : b->ktimes) { cudaEventDestroy(k.ev0); cudaEventDestroy(k.ev1); }
@@ -344,6 +347,8 @@ bool next_is_idr(const b200enc_session *s) { return s->force_idr || !s->have_ref
 int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8_t *const *frames, int mode, const int *kinds, const int *qps)
 {
     const Geom g = ss[0]->g;
+    static const bool trace = [] { const char *e = getenv("B200ENC_TRACE"); return e && atoi(e) != 0; }();
+    const auto tr0 = std::chrono::steady_clock::now();
     bool any_p = false;
     for (int i = 0; i < n; i++) any_p |= !kinds[i];
     cudaStream_t st = any_p ? b->stream : b->stream_hi;      // a batch of key frames only gets the high-priority stream
@@ -383,6 +388,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
     const int nmb = g.mbw * g.mbh;
     int launches = 0; b->n_ktimes = 0; Prof pf{ b, st, st };
+    const auto tr1 = std::chrono::steady_clock::now();
     cudaEventRecord(b->ev0, st);
     pf.begin("k_reset"); k_reset<<<(n * g.mbh + 255) / 256, 256, 0, st>>>(b->d_sess, g, n, b->d_ctl); pf.end(); launches++;
     if (ss[0]->cfg.input_format == B200ENC_FMT_RGBA) {
@@ -464,10 +470,16 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     cudaEventRecord(b->ev_join, s2); cudaStreamWaitEvent(st, b->ev_join, 0);
     cudaEventRecord(b->ev1, st);
     WaveCtl ctl;
+    const auto tr2 = std::chrono::steady_clock::now();
     CU_TRY(cudaMemcpyAsync(&ctl, b->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, st), return B200ENC_ECUDA);
     CU_TRY(cudaStreamSynchronize(st), return B200ENC_ECUDA);
     CU_TRY(cudaGetLastError(), return B200ENC_ECUDA);
     float ms = 0; cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+    if (trace) {
+        const auto tr3 = std::chrono::steady_clock::now();
+        auto d = [](auto a, auto c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+        b->t_pre += d(tr0, tr1); b->t_launch += d(tr1, tr2); b->t_sync += d(tr2, tr3); b->t_dev += ms; b->t_steps++;
+    }
     b->last_ms += ms; b->last_launches += launches;
     return ctl.error ? B200ENC_EWAVE : B200ENC_OK;
 }

@@ -175,13 +175,9 @@ __device__ int intra_try_i8x8(const IntraCtx &s, const Geom &g, IntraSmem &sm, c
         // source quadrant of this lane: rows by8 + 4 qy .., word (bx8 >> 2) + qx
         uint32_t Sq[4]; int Ts[16];
         {
-            const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
 #pragma unroll
-            for (int y = 0; y < 4; y++) {
-                Sq[y] = sm.srcw[(by8 + 4 * qy + y) * 4 + (bx8 >> 2) + qx];
-#pragma unroll
-                for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(Sq[y], H[k], 0);
-            }
+            for (int y = 0; y < 4; y++) Sq[y] = sm.srcw[(by8 + 4 * qy + y) * 4 + (bx8 >> 2) + qx];
+            satd_source_terms(Sq, Ts);
         }
         const int ma = sm.mg[(2 * (b >> 1) + 1) * 5 + 2 * (b & 1)], mb_ = sm.mg[(2 * (b >> 1)) * 5 + 2 * (b & 1) + 1];
         const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
@@ -297,13 +293,9 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
         // transforms, the predicted mode and this lane's cost terms
         uint32_t S[4]; int Ts[16];
         {
-            const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
 #pragma unroll
-            for (int y = 0; y < 4; y++) {
-                S[y] = sm.srcw[(by + y) * 4 + bxb];
-#pragma unroll
-                for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(S[y], H[k], 0);
-            }
+            for (int y = 0; y < 4; y++) S[y] = sm.srcw[(by + y) * 4 + bxb];
+            satd_source_terms(S, Ts);
         }
         const int ma = sm.mg[(byb + 1) * 5 + bxb], mb_ = sm.mg[byb * 5 + bxb + 1];
         const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);

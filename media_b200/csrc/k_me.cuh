@@ -232,17 +232,26 @@ __device__ __forceinline__ void pred_rows_qpel(const FineSmem &sm, int o1, int b
         P[2] = avg4(A2, __funnelshift_r(b0[PL_STRIDE / 2], b0[PL_STRIDE / 2 + 1], sb)); P[3] = avg4(A3, __funnelshift_r(b1[PL_STRIDE / 2], b1[PL_STRIDE / 2 + 1], sb));
     }
 }
-// 4x4 Hadamard SATD of (source block - P): Ts holds the horizontal transforms of the source rows, the prediction
-// rows are folded in with dp4a against the negated +-1 basis; |x+y|+|x-y| = 2 max(|x|,|y|) finishes the columns.
+// 4x4 Hadamard SATD of (source block - P). Ts holds the source's part of the first vertical butterfly stage: for basis k,
+// Ts[k] / Ts[4+k] = horizontal transform of source row 0 +/- row 1, Ts[8+k] / Ts[12+k] = row 2 +/- row 3. The prediction rows are folded in
+// with chained dp4a against the negated / plain +-1 basis, so the butterfly's additions run as IDP.4A on the FMA pipe (the kernel is bound
+// by the ALU pipe: math-pipe throttle was its second stall reason, profiles/r02a_ncu_summary.md); |x+y|+|x-y| = 2 max(|x|,|y|) finishes the columns.
+__device__ __forceinline__ void satd_source_terms(const uint32_t S[4], int Ts[16])    // S: the four source rows (packed samples)
+{
+    const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u }, NH[4] = { 0xffffffffu, 0x0101ffffu, 0xff0101ffu, 0x01ff01ffu };
+#pragma unroll
+    for (int y = 0; y < 4; y += 2)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int h0 = dp4a_us(S[y], H[k], 0); Ts[y * 4 + k] = dp4a_us(S[y + 1], H[k], h0); Ts[y * 4 + 4 + k] = dp4a_us(S[y + 1], NH[k], h0); }
+}
 __device__ __forceinline__ int satd_rows(const uint32_t P[4], const int Ts[16])
 {
-    const uint32_t NH[4] = { 0xffffffffu, 0x0101ffffu, 0xff0101ffu, 0x01ff01ffu };
+    const uint32_t NH[4] = { 0xffffffffu, 0x0101ffffu, 0xff0101ffu, 0x01ff01ffu }, PH[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
     int s = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int t0 = dp4a_us(P[0], NH[k], Ts[k]), t1 = dp4a_us(P[1], NH[k], Ts[4 + k]);
-        const int t2 = dp4a_us(P[2], NH[k], Ts[8 + k]), t3 = dp4a_us(P[3], NH[k], Ts[12 + k]);
-        const int a0 = t0 + t1, a1 = t0 - t1, a2 = t2 + t3, a3 = t2 - t3;
+        const int a0 = dp4a_us(P[0], NH[k], dp4a_us(P[1], NH[k], Ts[k])), a1 = dp4a_us(P[0], NH[k], dp4a_us(P[1], PH[k], Ts[4 + k]));
+        const int a2 = dp4a_us(P[2], NH[k], dp4a_us(P[3], NH[k], Ts[8 + k])), a3 = dp4a_us(P[2], NH[k], dp4a_us(P[3], PH[k], Ts[12 + k]));
         s += max(abs(a0), abs(a2)) + max(abs(a1), abs(a3));
     }
     return s;
@@ -402,15 +411,12 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     // sub-pel refinement by SATD: lane = (half-warp hw, 4x4 block b). A half-warp evaluates one candidate at a time over its 16 blocks, the
     // two half-warps evaluate different candidates in the same instruction stream.
     const int hw = lane >> 4, b = lane & 15, bx = blk_x(b) * 4, by = blk_y(b) * 4;
-    int Ts[16];                                         // horizontal Hadamard of the four source rows of this lane's block
+    int Ts[16];                                         // horizontal Hadamard of the source rows of this lane's block, rows 0 +/- 1 and 2 +/- 3 (see satd_rows)
     {
-        const uint32_t H[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };
+        uint32_t S[4];
 #pragma unroll
-        for (int y = 0; y < 4; y++) {
-            const uint32_t w = sm.src[(by + y) * 4 + (bx >> 2)];
-#pragma unroll
-            for (int k = 0; k < 4; k++) Ts[y * 4 + k] = dp4a_us(w, H[k], 0);
-        }
+        for (int y = 0; y < 4; y++) S[y] = sm.src[(by + y) * 4 + (bx >> 2)];
+        satd_source_terms(S, Ts);
     }
     {
         uint8_t *nt = reinterpret_cast<uint8_t *>(sm.nb_top), *nl = reinterpret_cast<uint8_t *>(sm.nb_left);

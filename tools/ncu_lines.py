@@ -22,7 +22,7 @@ subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
 # locate the function
-start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and re.search(kern, l))
+start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and re.search(os.environ.get("NCU_LINES_FUNC", kern), l))   # NCU_LINES_FUNC: mangled-name regex when templates share the name
 lines = []; cur = ("?", 0)
 for l in dis[start + 1:]:
     if l.startswith("//---------------------"):
