@@ -453,6 +453,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         pf.begin("k_cabac_hdr", s2); k_cabac_hdr<<<dim3((nmb + 255) / 256, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
         pf.begin("k_cabac_bins", s2); if (!(xskip & 1)) k_cabac_bins<<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
         pf.begin("k_cabac_scan", s2); k_cabac_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
+        pf.begin("k_cabac_place_hdr", s2); if (!(xskip & 2)) k_cabac_place_hdr<<<dim3((nmb + 255) / 256, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end();
         pf.begin("k_cabac_compact", s2); if (!(xskip & 2)) k_cabac_compact<<<gb, CABAC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end();
         // the coder threads are latency chains: every slot they lose to a co-resident throughput kernel's warps stretches the frame. Asking for
         // a slab of dynamic shared memory they do not use keeps the shared-memory-hungry kernels of the other batches off their SMs
@@ -460,7 +461,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         // from the other batches' motion search (96 x 1080p Main in batches of 32: 8 550 frames/s with it, 9 380 without)
         const int hog_kb = n <= 16 ? cabac_slab_kb() : 0;
         pf.begin("k_cabac_code", s2); if (!(xskip & 4)) k_cabac_code<<<dim3(g.num_slices, 1, n), 96, (size_t)hog_kb * 1024, s2>>>(b->d_sess, g, b->d_ctl); pf.end();
-        launches += 6;
+        launches += 7;
     } else {
     pf.begin("k_cavlc_mb", s2); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_slice_scan", s2); k_slice_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end(); launches++;

@@ -383,25 +383,51 @@ __global__ void __launch_bounds__(256) k_cabac_scan(const Sess *ss, Geom g)
     if (threadIdx.x == 0) s.slice_nbins[sl] = (uint32_t)carry;
 }
 
-// grid: (ceil(n_mb / CABAC_WARPS), 1, sessions): warp per MB, lane l moves the entries of its sub-slot to their place in the slice's list
+// The slices' lists are put together by two kernels after the scan. Most macroblocks of a P picture have no residual (P_Skip: one entry, the
+// mb_skip_flag): a warp per MB spent ~290 instructions moving one or two entries (profiles/r02_cabac_ncu.md), so
+//   k_cabac_place_hdr : THREAD per MB -- the header entries (dense bins_hdr slot) and the end_of_slice_flag to their place;
+//   k_cabac_compact   : warp per MB, only macroblocks WITH residual: lane l (1..27) moves the entries of its sub-slot.
+// grid: (ceil(n_mb / 256), 1, sessions), 256 threads
+__global__ void __launch_bounds__(256) k_cabac_place_hdr(const Sess *ss, Geom g)
+{
+    const int mb = blockIdx.x * 256 + threadIdx.x;
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    const int my = mb / g.mbw;
+    int sl = 0;
+    for (int k = 1; k < g.num_slices; k++) sl += (my >= g.slice_row0[k]);
+    const int n = (int)s.bin_lane_cnt[(size_t)mb * 32];
+    const uint16_t *src = s.bins_hdr + (size_t)mb * CABAC_HDR_SLOT;
+    uint16_t *dst = s.bins + (size_t)g.slice_row0[sl] * g.mbw * B200_MB_BIN_SLOT + s.mb_off[mb];
+    const int total = (int)s.mb_bits[mb];
+    B200_CHECK((size_t)s.mb_off[mb] + (size_t)total <= (size_t)(g.slice_row0[sl + 1] - g.slice_row0[sl]) * g.mbw * B200_MB_BIN_SLOT, 3);
+    for (int i = 0; i < n; i++) dst[i] = src[i];
+    dst[total - 1] = (uint16_t)(276 | ((mb == g.slice_row0[sl + 1] * g.mbw - 1) << 10));      // end_of_slice_flag
+}
+// grid: (ceil(n_mb / CABAC_WARPS), 1, sessions)
 __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac_compact(const Sess *ss, Geom g)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = blockIdx.x * CABAC_WARPS + warp;
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
+    {
+        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(s.mbi + mb);
+        const int t = w0 & 255, cbp = (int)(w0 >> 24);
+        if (t == MB_PSKIP || (cbp == 0 && t != MB_I16x16)) return;             // the same test as k_cabac_bins: nothing but the header
+    }
     const int my = mb / g.mbw;
     int sl = 0;
     for (int k = 1; k < g.num_slices; k++) sl += (my >= g.slice_row0[k]);
-    const int n = (int)s.bin_lane_cnt[(size_t)mb * 32 + lane];
+    const int n = lane == 28 ? 0 : (int)s.bin_lane_cnt[(size_t)mb * 32 + lane];      // lane 0 = the header (its count is part of the offsets), 28 = the end flag
     int incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const uint16_t *src = lane == 0 ? s.bins_hdr + (size_t)mb * CABAC_HDR_SLOT : s.bins_mb + (size_t)mb * CABAC_MB_SLOT + cabac_lane_slot(lane);
+    if (lane == 0 || n == 0) return;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(s.bins_mb + (size_t)mb * CABAC_MB_SLOT + cabac_lane_slot(lane));   // sub-slots start at even entries
     uint16_t *dst = s.bins + (size_t)g.slice_row0[sl] * g.mbw * B200_MB_BIN_SLOT + s.mb_off[mb] + (incl - n);
-    B200_CHECK((size_t)s.mb_off[mb] + (size_t)incl <= (size_t)(g.slice_row0[sl + 1] - g.slice_row0[sl]) * g.mbw * B200_MB_BIN_SLOT, 3);
-    if (lane == 28) dst[0] = (uint16_t)(276 | ((mb == g.slice_row0[sl + 1] * g.mbw - 1) << 10));      // end_of_slice_flag
-    else for (int i = 0; i < n; i++) dst[i] = src[i];
+    for (int i = 0; i + 1 < n; i += 2) { const uint32_t w = src[i >> 1]; dst[i] = (uint16_t)w; dst[i + 1] = (uint16_t)(w >> 16); }
+    if (n & 1) dst[n - 1] = (uint16_t)src[n >> 1];
 }
 
 // ---- the arithmetic coder (9.3.4.2) ----
