@@ -299,7 +299,10 @@ __device__ bool intra_try_i4x4(const IntraCtx &s, const Geom &g, IntraSmem &sm, 
         }
         const int ma = sm.mg[(byb + 1) * 5 + bxb], mb_ = sm.mg[byb * 5 + bxb + 1];
         const int pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
-        const bool ok = lane < 9 && (lane == 2 || ((lane == 0 || lane == 3 || lane == 7) ? aT : (lane == 1 || lane == 8) ? aL : aX));
+        // (block 5 never predicts from the upper-right MACROBLOCK outside High-profile sessions: modes 3 and 7 are left out there, which is what lets the
+        // wavefront run at a lag of one macroblock -- see k_intra_wave and oracle/orc_encoder.c: code_intra4x4_luma)
+        const bool ok = lane < 9 && (lane == 2 || ((lane == 0 || lane == 3 || lane == 7) ? aT : (lane == 1 || lane == 8) ? aL : aX)) &&
+                        !(b == 5 && topright && !s.i8 && (lane == 3 || lane == 7));
         const int mode_cost = lambda * (lane == pm ? 1 : 4);
         // filtered edge of this block
         int e = 128;
@@ -643,7 +646,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) k_intra_wave(const Sess *ss, 
             if (nx >= g.mbw) break;
             if (nx > mx && lane == 0) { __threadfence(); st_release(prog + my, nx); }
         }
-        if (!slice_top && !wave_wait(prog + my - 1, min(nx + 2, g.mbw), ctl, lane)) return;
+        // the row above must be past the upper neighbour -- and past the upper-right one only where a predictor reads it (Intra_8x8: High profile)
+        if (!slice_top && !wave_wait(prog + my - 1, min(nx + (s.i8 ? 2 : 1), g.mbw), ctl, lane)) return;
         intra_code_mb(s, g, sm, i8idx, nx, my, lane);
         fence_acq_rel_gpu();
         __syncwarp();

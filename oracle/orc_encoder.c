@@ -706,6 +706,12 @@ static int code_intra4x4_luma(OrcEncoder *e, int mx, int my, int qp, int lambda)
         const uint8_t *sb = s + by * 4 * st + bx * 4; uint8_t *rb = r + by * 4 * st + bx * 4;
         int pm = i4_pred_mode(e, mx, my, b); uint32_t best = 0xffffffffu; uint8_t pred[16], bp[16];
         for (int m = 0; m < 9; m++) {
+            /* Block 5 (the MB's upper-right 4x4 block) is the only Intra_4x4 block that predicts from the UPPER-RIGHT macroblock, and only in
+             * modes 3 (diagonal down-left) and 7 (vertical-left). Without them -- an encoder's choice, the stream stays conformant -- a
+             * macroblock depends on its left, upper-left and upper neighbours only, and the wavefront of the GPU runs at a lag of one macroblock
+             * per row instead of two (critical path mbw + mbh steps instead of mbw + 2 mbh). High-profile sessions keep both modes: there
+             * Intra_8x8 needs the upper-right macroblock anyway (8.3.2.2.1 filters p[15,-1] with p[16,-1]). */
+            if (b == 5 && topright && (m == 3 || m == 7) && !I8X8_ON(e)) continue;
             if (!pred_i4(rb, st, m, avail, pred)) continue;
             uint32_t key = ((uint32_t)(orc_satd4x4(sb, st, pred, 4) + lambda * (m == pm ? 1 : 4)) << 4) | (uint32_t)m;
             if (key < best) { best = key; memcpy(bp, pred, 16); }
