@@ -61,7 +61,10 @@ def apply_workload(args):
     if args.sessions is None:
         args.sessions = 256
     if args.groups is None:
-        args.groups = 8
+        # device-resident leg: two batches of 128 (measured after the round-2 wavefront work, 256 x 1080p: 2 batches 16.8k / 13.5k frames/s CAVLC / CABAC,
+        # 4: 16.7k / 13.0k, 8: 16.4k / 11.7k -- fewer, larger batches amortise the latency chains; the end-to-end leg goes through the plugin's own
+        # scheduler, which keeps batches of <= 32 because there the uploads of the next batches must overlap the kernels)
+        args.groups = 2
 
 
 def frame_bytes():
@@ -299,10 +302,30 @@ def run_b200(args):
             t = torch.tensor([gbs], dtype=torch.float64)
             if use_dist:
                 dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            # the CPU side of the same path: every frame is copied once from the caller's pageable memory into the session's pinned staging buffer
+            # (on the caller's thread); measured here as this rank's host cores copying frame-sized buffers all at once
+            import numpy as _np
+            ncpu = max(1, min(len(os.sched_getaffinity(0)), 32) // max(1, world if use_dist else 1))
+            srcs = [_np.ones(fb, _np.uint8) for _ in range(ncpu)]; dsts = [hp[k * fb:(k + 1) * fb].numpy() for k in range(min(ncpu, nbuf))]
+            reps = 8
+            def _cp(k):
+                for _ in range(reps):
+                    _np.copyto(dsts[k % len(dsts)], srcs[k])
+            ths = [threading.Thread(target=_cp, args=(k,)) for k in range(ncpu)]
+            barrier(); tc0 = time.perf_counter()
+            for th in ths: th.start()
+            for th in ths: th.join()
+            stage_gbs = ncpu * reps * fb / (time.perf_counter() - tc0) / 1e9
+            ts = torch.tensor([stage_gbs], dtype=torch.float64)
+            if use_dist:
+                dist.all_reduce(ts, op=dist.ReduceOp.MIN)
             h2d = {"pinned_h2d_gbs_per_gpu_all_ranks_copying": round(t[0].item(), 1),
                    "frames_per_s_ceiling": round(world * t[0].item() * 1e9 / fb, 0),
-                   "note": "PCIe ceiling of the host-input path: no end-to-end number with host frames can exceed it; the staging copy of pageable caller "
-                           "memory (one memcpy per frame on the caller's thread) comes on top on the CPU side"}
+                   "host_staging_copy_gbs_per_rank_all_ranks_copying": round(ts[0].item(), 1), "host_threads_per_rank": ncpu,
+                   "frames_per_s_staging_ceiling": round(world * ts[0].item() * 1e9 / fb, 0),
+                   "note": "ceilings of the host-input path: PCIe (pinned host -> device, four copy streams per GPU, all ranks at once) and the staging copy "
+                           "of pageable caller memory into pinned memory (one copy per frame on the caller's thread; numpy copies on this rank's share of "
+                           "the host cores, all ranks at once; the DMA reads the same memory a third time). No end-to-end number with host frames exceeds either"}
             del hp, dp_
         except Exception as ex:
             h2d = {"error": str(ex)}
