@@ -69,6 +69,11 @@ typedef struct b200enc_config {
     int min_qp, max_qp;    /* QP bounds of the rate control (iMinQp / iMaxQp; the wrapper keeps GetDefaultParams' 0 / 51, :230); max_qp 0 = 51 */
     int background_detection; /* bEnableBackgroundDetection (:282): static macroblocks are skipped on a pre-analysis of the source pictures */
     int complexity;        /* iComplexityMode (:289; the wrapper asks for HIGH_COMPLEXITY): 0 LOW (no Intra_4x4 trial, no P_8x8), 1 MEDIUM (no P_8x8), 2 HIGH */
+    int key_slices;        /* MB-row groups of KEY pictures (1..35). A key frame is the longest dependent chain of a session: the intra wavefront's critical
+                              path is mbw + mbh-of-the-slice steps and the CABAC coder walks a slice's bins one after the other, so key pictures may take
+                              more slices than P pictures (a picture's slice count is free per picture, 7.3.3). 0 = automatic: num_slices when that was
+                              given explicitly or with CAVLC; with CABAC and automatic num_slices one slice per 4 MB rows (1080p: 17). A P picture the
+                              scene-change detector promotes on the device keeps the P pictures' slices */
 } b200enc_config;
 
 typedef struct b200enc_frame_info {
@@ -126,6 +131,9 @@ void b200enc_host_free(void *p);
 void *b200enc_dev_alloc(int device, size_t bytes);
 int b200enc_dev_upload(int device, void *dst, const void *src, size_t bytes);
 void b200enc_dev_free(int device, void *p);
+
+/* the session's slice counts after the automatic rules: P pictures / key pictures (b200enc_config.num_slices / key_slices) */
+int b200enc_slice_counts(b200enc_session *s, int *p_slices, int *key_slices);
 
 /* ---- test / parity hooks ---- */
 enum {

@@ -153,7 +153,8 @@ struct b200enc_batch {
 
 struct b200enc_session {
     b200enc_config cfg;
-    Geom g;
+    Geom g, g_key;                               // slice layout of P pictures / of key pictures (b200enc_config.key_slices); everything else is equal
+    uint32_t rbsp_words_per_slice_key = 0;
     int device = -1; double load = 0;
     uint8_t *d_pool = nullptr; size_t pool_bytes = 0;
     // device buffers (sub-allocated from d_pool)
@@ -272,7 +273,7 @@ struct Prof {
 
 bool same_shape(const b200enc_session *a, const b200enc_session *c)
 {
-    return a->cfg.width == c->cfg.width && a->cfg.height == c->cfg.height && a->cfg.num_slices == c->cfg.num_slices &&
+    return a->cfg.width == c->cfg.width && a->cfg.height == c->cfg.height && a->cfg.num_slices == c->cfg.num_slices && a->cfg.key_slices == c->cfg.key_slices &&
            a->cfg.search_range == c->cfg.search_range && a->cfg.input_format == c->cfg.input_format && a->device == c->device &&
            (a->cfg.profile != 0) == (c->cfg.profile != 0);
 }
@@ -346,7 +347,9 @@ bool next_is_idr(const b200enc_session *s) { return s->force_idr || !s->have_ref
 // Does not touch the sessions' stream state (frame_num, reference roles, rate control): the caller commits or repeats the step.
 int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8_t *const *frames, int mode, const int *kinds, const int *qps)
 {
-    const Geom g = ss[0]->g;
+    bool all_key = true;
+    for (int i = 0; i < n; i++) all_key &= kinds[i] != 0;
+    const Geom g = all_key ? ss[0]->g_key : ss[0]->g;          // key pictures travel in steps of their own (encode_impl) and take their own slice layout
     static const bool trace = [] { const char *e = getenv("B200ENC_TRACE"); return e && atoi(e) != 0; }();
     const auto tr0 = std::chrono::steady_clock::now();
     bool any_p = false;
@@ -383,7 +386,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         d.qp = qps[i]; d.is_idr = idr; d.frame_num = idr ? 0 : s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
         d.scene_change = s->cfg.scene_change && !idr && s->frames_since_idr >= SC_MIN_DISTANCE;
         d.t8x8 = s->cfg.profile == 2; d.dump = s->cfg.debug & 1;
-        d.rbsp_words_per_slice = s->rbsp_words_per_slice; d.out_cap = s->out_cap;
+        d.rbsp_words_per_slice = all_key ? s->rbsp_words_per_slice_key : s->rbsp_words_per_slice; d.out_cap = s->out_cap;
     }
     CU_TRY(cudaMemcpyAsync(b->d_sess, b->h_sess, sizeof(Sess) * n, cudaMemcpyHostToDevice, st), return B200ENC_ECUDA);
     const int nmb = g.mbw * g.mbh;
@@ -485,6 +488,22 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     return ctl.error ? B200ENC_EWAVE : B200ENC_OK;
 }
 
+// launch_step over pictures of both kinds: key pictures and P pictures differ in their slice layout (b200enc_config.key_slices), so a mixed set
+// runs as two steps -- key pictures first (the longer chain), each subset with its own geometry.
+int launch_steps_by_kind(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8_t *const *frames, int mode, const int *kinds, const int *qps)
+{
+    bool any_key = false, any_p = false;
+    for (int i = 0; i < n; i++) { if (kinds[i]) any_key = true; else any_p = true; }
+    if (!(any_key && any_p) || ss[0]->g_key.num_slices == ss[0]->g.num_slices) return launch_step(b, ss, n, frames, mode, kinds, qps);
+    for (int pass = 1; pass >= 0; pass--) {
+        std::vector<b200enc_session *> sub; std::vector<const uint8_t *> fr; std::vector<int> k, q;
+        for (int i = 0; i < n; i++) if ((kinds[i] != 0) == (pass == 1)) { sub.push_back(ss[i]); fr.push_back(frames[i]); k.push_back(kinds[i]); q.push_back(qps[i]); }
+        const int rc = launch_step(b, sub.data(), (int)sub.size(), fr.data(), mode, k.data(), q.data());
+        if (rc != B200ENC_OK) return rc;
+    }
+    return B200ENC_OK;
+}
+
 bool rc_retry_enabled()
 {
     static const bool on = [] { const char *e = getenv("B200ENC_RC_RETRY"); return e ? atoi(e) != 0 : true; }();
@@ -511,7 +530,7 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         else { s->rc_dec = s->rc.pick(kinds[i]); qps[i] = s->rc_dec.qp; }
     }
     b->last_ms = 0; b->last_launches = 0;
-    int rc = launch_step(b, ss, n, frames, mode, kinds.data(), qps.data());
+    int rc = launch_steps_by_kind(b, ss, n, frames, mode, kinds.data(), qps.data());
     auto out_size = [](const b200enc_session *s) { return *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap); };
     auto promoted = [](const b200enc_session *s) { return *reinterpret_cast<volatile uint32_t *>(s->h_out + s->out_cap + 4) != 0; };
     if (rc == B200ENC_OK && rc_retry_enabled()) {
@@ -524,10 +543,13 @@ int encode_impl(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
             const int coded = kinds[i] || (promoted(s) ? 1 : 0);
             const int q2 = s->rc.second_attempt_qp(kinds[i], coded, s->rc_dec, 8.0 * out_size(s));
             if (q2 < 0) continue;
+            { static const bool tr = [] { const char *e = getenv("B200ENC_TRACE"); return e && atoi(e) != 0; }(); static std::atomic<int> shown{ 0 };
+              if (tr && shown.fetch_add(1) < 40) fprintf(stderr, "[b200enc trace] coded twice: frame %u planned %d coded %d qp %d -> %d, %u bytes, budget %.0f cap %.0f bytes\n",
+                                                         s->frame_index, kinds[i], coded, qps[i], q2, out_size(s), s->rc_dec.budget / 8, s->rc_dec.hard_cap / 8); }
             again.push_back(s); ak.push_back(coded); aq.push_back(q2); at.push_back(i); af.push_back(frames[i]);
         }
         if (!again.empty()) {
-            rc = launch_step(b, again.data(), (int)again.size(), af.data(), mode == IN_DEVICE ? IN_DEVICE : IN_RESIDENT, ak.data(), aq.data());
+            rc = launch_steps_by_kind(b, again.data(), (int)again.size(), af.data(), mode == IN_DEVICE ? IN_DEVICE : IN_RESIDENT, ak.data(), aq.data());
             for (size_t k = 0; k < again.size(); k++) { kinds[at[k]] = ak[k]; qps[at[k]] = aq[k]; again[k]->retries++; }
         }
     }
@@ -720,7 +742,7 @@ void b200enc_default_config(b200enc_config *c)
     c->width = 720; c->height = 1280; c->fps = 30; c->bitrate = 5000000; c->gop = 30; c->const_qp = -1;
     c->num_slices = 0; c->search_range = 16; c->input_format = B200ENC_FMT_I420; c->device = -1; c->scene_change = 1;
     // rate-control bounds of openh264's GetDefaultParams (what the wrapper keeps, :230), max bitrate = target (:239-240), HIGH_COMPLEXITY (:289)
-    c->max_bitrate = 0; c->min_qp = 0; c->max_qp = 51; c->background_detection = 0; c->complexity = 2;
+    c->max_bitrate = 0; c->min_qp = 0; c->max_qp = 51; c->background_detection = 0; c->complexity = 2; c->key_slices = 0;
 }
 
 int b200enc_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
@@ -766,18 +788,26 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
     // num_slices <= 0 = automatic: one slice with CAVLC (the wrapper's SM_SINGLE_SLICE, VideoEncoderOpenH264.cpp:247); with CABAC one slice per
     // ~17 MB rows (1080p: 4, 720p: 2, 2160p: 7), because the arithmetic coder is a serial chain per slice and a frame's latency is its longest slice
     // (+0.6..0.9 % bits on P pictures at 1080p, measured with the oracle)
+    const bool auto_slices = c.num_slices < 1;
     if (c.num_slices < 1) c.num_slices = c.profile ? std::min(std::max(((c.height + 15) / 16 + 8) / 17, 1), 8) : 1;
+    // key pictures: their own slice count (b200enc_config.key_slices); automatic = one slice per 4 MB rows for CABAC sessions with automatic slices
+    if (c.key_slices < 0 || c.key_slices > B200_MAX_SLICES) return B200ENC_EINVAL;
+    if (c.key_slices < 1) c.key_slices = auto_slices && c.profile ? std::min(std::max(((c.height + 15) / 16 + 3) / 4, c.num_slices), (int)B200_MAX_SLICES) : c.num_slices;
     b200enc_session *s = new (std::nothrow) b200enc_session();
     if (!s) return B200ENC_ENOMEM;
     s->cfg = c;
     Geom &g = s->g;
     g.width = c.width; g.height = c.height; g.mbw = (c.width + 15) / 16; g.mbh = (c.height + 15) / 16; g.wc = g.mbw * 16; g.hc = g.mbh * 16;
-    g.num_slices = std::min(c.num_slices, g.mbh); g.search_range = c.search_range; s->cfg.num_slices = g.num_slices;
-    { const int base = g.mbh / g.num_slices, rem = g.mbh % g.num_slices; int r = 0;
-      for (int i = 0; i < g.num_slices; i++) { g.slice_row0[i] = r; r += base + (i < rem); }
-      for (int i = g.num_slices; i <= B200_MAX_SLICES; i++) g.slice_row0[i] = r;
-      memset(g.slice_top, 0, sizeof g.slice_top);
-      for (int i = 0; i < g.num_slices; i++) g.slice_top[g.slice_row0[i] >> 5] |= 1u << (g.slice_row0[i] & 31); }
+    g.search_range = c.search_range;
+    auto slice_layout = [](Geom &q, int count) {
+        q.num_slices = std::min(count, q.mbh);
+        const int base = q.mbh / q.num_slices, rem = q.mbh % q.num_slices; int r = 0;
+        for (int i = 0; i < q.num_slices; i++) { q.slice_row0[i] = r; r += base + (i < rem); }
+        for (int i = q.num_slices; i <= B200_MAX_SLICES; i++) q.slice_row0[i] = r;
+        memset(q.slice_top, 0, sizeof q.slice_top);
+        for (int i = 0; i < q.num_slices; i++) q.slice_top[q.slice_row0[i] >> 5] |= 1u << (q.slice_row0[i] & 31);
+    };
+    slice_layout(g, c.num_slices); s->cfg.num_slices = g.num_slices;
     {   // borders of the padded planes: the widest reach of a search window / interpolation tap past the picture edge
         auto up = [](int v, int a) { return (v + a - 1) / a * a; };
         g.lp = up(c.search_range + 10, 16); g.ls = g.wc + 2 * g.lp;
@@ -792,8 +822,11 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
     do {
         CU_TRY(cudaSetDevice(s->device), rc = B200ENC_ENODEV; break);
         const size_t ny = (size_t)g.wc * g.hc, nc = ny / 4, nmb = (size_t)g.mbw * g.mbh;
+        s->g_key = g; slice_layout(s->g_key, c.key_slices); s->cfg.key_slices = s->g_key.num_slices;
         const int max_slice_rows = g.mbh / g.num_slices + (g.mbh % g.num_slices ? 1 : 0);
         s->rbsp_words_per_slice = (uint32_t)((size_t)max_slice_rows * g.mbw * B200_MB_SLOT_WORDS + 64);
+        const int max_key_rows = g.mbh / s->g_key.num_slices + (g.mbh % s->g_key.num_slices ? 1 : 0);
+        s->rbsp_words_per_slice_key = (uint32_t)((size_t)max_key_rows * g.mbw * B200_MB_SLOT_WORDS + 64);
         const std::vector<uint8_t> ps = make_parameter_sets(c.width, c.height, c.level_idc ? c.level_idc : level_for(c.width, c.height, c.fps), c.profile);
         s->hdr_len = (int)ps.size(); s->param_sets = ps;
         struct Item { void **p; size_t bytes; };
@@ -809,7 +842,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
         add(s->me2, nmb * 4); add(s->me1, nmb * 4); add(s->me0, nmb * 4); add(s->inter_cost, nmb * 4);
         add(s->skip_run, (nmb + B200_MAX_SLICES) * 4); add(s->mb_bits, nmb * 4); add(s->mb_off, nmb * 4);
         add(s->mb_slot, nmb * B200_MB_SLOT_WORDS * 4);
-        add(s->rbsp, (size_t)s->rbsp_words_per_slice * g.num_slices * 4);
+        add(s->rbsp, std::max((size_t)s->rbsp_words_per_slice * g.num_slices, (size_t)s->rbsp_words_per_slice_key * s->g_key.num_slices) * 4);
         add(s->side, c.profile ? nmb * sizeof(MbSide) : 16); add(s->slice_nbins, B200_MAX_SLICES * 4);
         add(s->bins, c.profile ? (nmb * B200_MB_BIN_SLOT + 64) * sizeof(uint16_t) : 16);
         add(s->bins_mb, c.profile ? (nmb * CABAC_MB_SLOT + 64) * sizeof(uint16_t) : 16);
@@ -950,6 +983,14 @@ int b200enc_dev_upload(int device, void *dst, const void *src, size_t bytes)
     return B200ENC_OK;
 }
 void b200enc_dev_free(int device, void *p) { if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p); }
+
+int b200enc_slice_counts(b200enc_session *s, int *p_slices, int *key_slices)
+{
+    if (!s) return B200ENC_EINVAL;
+    if (p_slices) *p_slices = s->g.num_slices;
+    if (key_slices) *key_slices = s->g_key.num_slices;
+    return B200ENC_OK;
+}
 
 int b200enc_get_stage(b200enc_session *s, int stage, void *out, size_t cap, size_t *written)
 {

@@ -46,7 +46,7 @@ public:
         T = cfg.bitrate / cfg.fps; drain = cfg.max_bitrate / cfg.fps; bucket = cfg.max_bitrate;
         level = 0; vbv = 0;
         m[0] = Model(); m[1] = Model();
-        last_qp[0] = last_qp[1] = -1;
+        last_qp[0] = last_qp[1] = -1; prev_type = -1;
     }
     int lo() const { return std::max(cfg.min_qp, std::min(QP_FLOOR, cfg.max_qp)); }
     int hi() const { return cfg.max_qp; }
@@ -68,9 +68,16 @@ public:
             const double dq = m[0].dqp_for(want);
             const int step = std::fabs(dq) < 0.8 ? 0 : (int)std::lround(0.75 * dq);
             qp = last_qp[0] + std::min(std::max(step, -2), 3);
+            // the first P picture behind a key picture predicts from it: coded much finer than the key picture it would pay for the whole
+            // picture's quantisation error at once (measured: 12 QP steps finer = 10-40 picture budgets); it starts 3 steps below the key
+            // picture's QP and the usual -2 per picture bring the sequence back
+            if (prev_type == 1 && last_qp[1] >= 0) qp = std::max(qp, last_qp[1] - 3);
         } else if (m[type].have) {
             qp = m[type].qp_for(want);
             if (last_qp[0] >= 0) qp = std::min(std::max(qp, last_qp[0] - 3), last_qp[0] + 8);
+            // ... but never a QP at which the key-frame model itself predicts a picture above the hard cap: that attempt would be thrown away and
+            // coded again (content whose P pictures are cheap and whose key pictures are not -- a translating texture -- sits 15+ steps apart)
+            while (qp < hi() && m[type].predict_l2(qp) > std::log2(0.9 * d.hard_cap)) qp++;
         } else if (type == 0 && last_qp[1] >= 0) {
             qp = last_qp[1] - 3;                                         // first P picture after the first IDR
         } else if (type == 1 && m[0].have) {
@@ -95,17 +102,22 @@ public:
     }
     // The whole second-attempt rule, shared by the engine and the simulation: `planned` is the picture type the QP was picked for (decision
     // d), `coded` what it came out as (a P picture the device promoted to a scene-change IDR is judged against an IDR's cap).
-    int second_attempt_qp(int planned, int coded, const Decision &d, double bits) const
+    int second_attempt_qp(int planned, int coded, const Decision &d, double bits)
     {
         Decision e = d;
         if (coded && !planned) { e = pick(1); e.qp = d.qp; }
-        return retry_qp(coded, e, bits);
+        const int q2 = retry_qp(coded, e, bits);
+        if (q2 >= 0) note_discarded(coded, d.qp, bits);      // the attempt is thrown away, what it measured is not
+        return q2;
     }
+    // A first attempt that was thrown away (coded again at another QP) still measured the picture: the model learns from it -- two points
+    // of the same picture give the exponent alpha at once -- but the buffers only ever see the delivered picture.
+    void note_discarded(int type, int qp, double bits) { m[type].observe(qp, std::max(bits, 64.0)); }
     void update(int type, int qp, double bits)
     {
         bits = std::max(bits, 64.0);
         m[type].observe(qp, bits);
-        last_qp[type] = qp;
+        last_qp[type] = qp; prev_type = type;
         level += bits - T;
         level = std::min(std::max(level, -1.0 * cfg.fps * T), 4.0 * cfg.fps * T);
         vbv = std::max(0.0, vbv + bits - drain);
@@ -133,7 +145,7 @@ private:
         }
     };
     Config cfg; double T = 0, drain = 0, bucket = 0, level = 0, vbv = 0;
-    Model m[2]; int last_qp[2] = { -1, -1 };
+    Model m[2]; int last_qp[2] = { -1, -1 }, prev_type = -1;
 };
 
 } // namespace b200rc

@@ -25,7 +25,7 @@ MBSIDE_DTYPE = np.dtype([("mvd", "<i2", (4, 2)), ("dc_cbf", "u1"), ("pad", "u1",
 class Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "height", "fps", "bitrate", "gop", "const_qp", "num_slices",
                                        "search_range", "input_format", "device", "level_idc", "debug", "scene_change", "auto_batch", "profile",
-                                       "max_bitrate", "min_qp", "max_qp", "background_detection", "complexity")]
+                                       "max_bitrate", "min_qp", "max_qp", "background_detection", "complexity", "key_slices")]
 
 
 class FrameInfo(C.Structure):
@@ -80,6 +80,7 @@ def lib():
         L.b200enc_dev_free.argtypes = [C.c_int, vp]
         L.b200enc_get_stage.restype = C.c_int; L.b200enc_get_stage.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.b200enc_get_recon.restype = C.c_int; L.b200enc_get_recon.argtypes = [vp, vp, C.c_size_t]
+        L.b200enc_slice_counts.restype = C.c_int; L.b200enc_slice_counts.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.b200k_convert_to_i420.restype = C.c_int
         L.b200k_convert_to_i420.argtypes = [C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.b200k_downsample2.restype = C.c_int; L.b200k_downsample2.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp]
@@ -107,16 +108,22 @@ def _p(a):
 class Session:
     def __init__(self, width, height, fps=30, bitrate=4_000_000, gop=30, const_qp=-1, num_slices=1, search_range=16,
                  input_format=FMT_I420, device=-1, level_idc=0, debug=0, auto_batch=0, scene_change=1, profile=PROFILE_BASELINE,
-                 max_bitrate=0, min_qp=0, max_qp=51, background_detection=0, complexity=2):
+                 max_bitrate=0, min_qp=0, max_qp=51, background_detection=0, complexity=2, key_slices=0):
         L = lib()
         self.cfg = Config(width, height, fps, bitrate, gop, const_qp, num_slices, search_range, input_format, device, level_idc, debug, scene_change, auto_batch, profile,
-                          max_bitrate, min_qp, max_qp, background_detection, complexity)
+                          max_bitrate, min_qp, max_qp, background_detection, complexity, key_slices)
         self.h = C.c_void_p()
         check(L.b200enc_create(C.byref(self.cfg), C.byref(self.h)), "b200enc_create")
         self.width, self.height = width, height
         self.mbw, self.mbh = (width + 15) // 16, (height + 15) // 16
         self.frame_bytes = L.b200enc_frame_bytes(self.h)
         self.device = L.b200enc_device_of(self.h)
+
+    def slice_counts(self):
+        """(slices of P pictures, slices of key pictures) after the automatic rules"""
+        a, b = C.c_int(), C.c_int()
+        check(lib().b200enc_slice_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:

@@ -90,6 +90,8 @@ typedef struct {
     int complexity_set, complexity; /* complexity_set = 1: iComplexityMode 0 LOW (no Intra_4x4 trial, no P_8x8), 1 MEDIUM (no P_8x8), 2 HIGH */
     int intra8x8;            /* 1 (what the product does): High profile intra MBs may also take Intra_8x8 (8.3.2), tried before Intra_4x4 and chosen
                                 against it by J = 64 SSD + 27 lambda^2 B; 0: Intra_4x4 / Intra_16x16 only (quality A/B runs) */
+    int key_slices;          /* MB-row groups of pictures REQUESTED as key pictures (b200enc_config.key_slices); < 1: num_slices. A P picture the
+                                scene-change rule promotes keeps num_slices */
 } OrcConfig;
 #define ORC_BGD_OU_SAD 128       /* background detection: largest SAD of an 8x8 unit against the previous source picture (mean |d| <= 2) */
 #define ORC_BGD_MAXDIFF 12       /* ... and largest single sample difference */

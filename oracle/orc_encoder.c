@@ -36,7 +36,8 @@ struct OrcEncoder {
     int16_t *me[3];                  /* [level][mb*2] */
     int32_t *inter_cost;
     uint8_t *pred_y, *pred_c;        /* per-MB inter prediction: 256 luma, 2*64 chroma */
-    int *slice_row0;                 /* num_slices+1 entries */
+    int *slice_row0;                 /* the layout of the picture being coded: cur_slices + 1 entries (one of row0_tab) */
+    int *row0_tab[2]; int cur_slices;
     int frame_num, idr_pic_id, have_ref, last_idr;
     int since_idr;                   /* pictures since (and including) the last IDR */
     uint8_t *rbsp; int rbsp_cap;
@@ -75,14 +76,19 @@ OrcEncoder *orc_create(const OrcConfig *cfg)
     for (int l = 0; l < 3; l++) e->me[l] = calloc(n * 2, sizeof(int16_t));
     e->inter_cost = calloc(n, sizeof(int32_t));
     e->pred_y = malloc((size_t)n * 256); e->pred_c = malloc((size_t)n * 128);
-    e->slice_row0 = calloc(e->cfg.num_slices + 1, sizeof(int));
-    { int base = e->mbh / e->cfg.num_slices, rem = e->mbh % e->cfg.num_slices, r = 0;
-      for (int s = 0; s < e->cfg.num_slices; s++) { e->slice_row0[s] = r; r += base + (s < rem); }
-      e->slice_row0[e->cfg.num_slices] = r; }
+    if (e->cfg.key_slices < 1) e->cfg.key_slices = e->cfg.num_slices;
+    if (e->cfg.key_slices > e->mbh) e->cfg.key_slices = e->mbh;
+    for (int k = 0; k < 2; k++) {     /* slice layouts: [0] P pictures, [1] key pictures -- equal MB-row groups */
+        int cnt = k ? e->cfg.key_slices : e->cfg.num_slices, base = e->mbh / cnt, rem = e->mbh % cnt, r = 0;
+        e->row0_tab[k] = calloc(cnt + 1, sizeof(int));
+        for (int s = 0; s < cnt; s++) { e->row0_tab[k][s] = r; r += base + (s < rem); }
+        e->row0_tab[k][cnt] = r;
+    }
+    e->slice_row0 = e->row0_tab[0]; e->cur_slices = e->cfg.num_slices;
     e->rbsp_cap = n * 1024 + 4096; e->rbsp = malloc(e->rbsp_cap);
     e->side = calloc(n, sizeof(OrcMbSide));
     e->bins_cap = n * ORC_MB_BINS_MAX; e->bins = malloc((size_t)e->bins_cap * 2);
-    e->slice_bin0 = calloc(e->cfg.num_slices + 1, sizeof(int));
+    e->slice_bin0 = calloc((e->cfg.num_slices > e->cfg.key_slices ? e->cfg.num_slices : e->cfg.key_slices) + 1, sizeof(int));
     return e;
 }
 
@@ -94,7 +100,7 @@ void orc_destroy(OrcEncoder *e)
     free(e->srcL1); free(e->srcL2); free(e->refL1); free(e->refL2);
     free(e->hpb); free(e->hph); free(e->hpj);
     free(e->mbi); free(e->coef); free(e->bg_skip); for (int l = 0; l < 3; l++) free(e->me[l]);
-    free(e->inter_cost); free(e->pred_y); free(e->pred_c); free(e->slice_row0); free(e->rbsp); free(e->side); free(e->bins); free(e->slice_bin0); free(e);
+    free(e->inter_cost); free(e->pred_y); free(e->pred_c); free(e->row0_tab[0]); free(e->row0_tab[1]); free(e->rbsp); free(e->side); free(e->bins); free(e->slice_bin0); free(e);
 }
 
 int orc_last_frame_was_idr(const OrcEncoder *e) { return e->last_idr; }
@@ -1127,6 +1133,8 @@ static int encode_frame(OrcEncoder *e, const uint8_t *i420, int frame_type, int 
 {
     int is_idr = frame_type == 1 || !e->have_ref, n = e->mbw * e->mbh, lambda = LAMBDA_TAB[qp];
     const int frame_num_in = e->frame_num;
+    /* requested key pictures take the key layout; a promoted P picture (scene change, below) keeps the P layout it was searched with */
+    e->slice_row0 = e->row0_tab[is_idr]; e->cur_slices = is_idr ? e->cfg.key_slices : e->cfg.num_slices;
     load_source(e, i420);
     if (is_idr) { e->frame_num = 0; }
     if (!is_idr) {
@@ -1187,7 +1195,7 @@ static int encode_frame(OrcEncoder *e, const uint8_t *i420, int frame_type, int 
         o += orc_write_pps(out + o, e->cfg.profile, T8X8_ON(e));
     }
     if (e->cfg.profile) cabac_side_records(e, is_idr);
-    for (int s = 0; s < e->cfg.num_slices; s++) {
+    for (int s = 0; s < e->cur_slices; s++) {
         BitWriter b; bw_init(&b, e->rbsp, e->rbsp_cap);
         int r0 = e->slice_row0[s], r1 = e->slice_row0[s + 1], run = 0;
         orc_write_slice_header(&b, r0 * e->mbw, is_idr, e->frame_num, e->idr_pic_id, qp, e->cfg.profile != 0);

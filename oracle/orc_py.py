@@ -23,7 +23,7 @@ def build(force=False):
 class OrcConfig(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("num_slices", C.c_int),
                 ("search_range", C.c_int), ("level_idc", C.c_int), ("fps", C.c_int), ("no_i4x4", C.c_int), ("no_p8x8", C.c_int), ("no_scene_change", C.c_int), ("profile", C.c_int), ("no_t8x8", C.c_int),
-                ("background_detection", C.c_int), ("complexity_set", C.c_int), ("complexity", C.c_int), ("intra8x8", C.c_int)]
+                ("background_detection", C.c_int), ("complexity_set", C.c_int), ("complexity", C.c_int), ("intra8x8", C.c_int), ("key_slices", C.c_int)]
 
 
 MBINFO_DTYPE = np.dtype([("mb_type", "u1"), ("i16_mode", "u1"), ("chroma_mode", "u1"), ("cbp", "u1"),
@@ -87,10 +87,10 @@ class Encoder:
     """One oracle session: encode(i420, idr, qp) -> Annex-B bytes; stage dumps as numpy arrays."""
 
     def __init__(self, width, height, num_slices=1, search_range=16, fps=30, level_idc=0, no_i4x4=0, no_p8x8=0, scene_change=1, profile=0, no_t8x8=0, intra8x8=1,
-                 background_detection=0, complexity=None):
+                 background_detection=0, complexity=None, key_slices=0):
         self.L = lib()
         self.cfg = OrcConfig(width, height, num_slices, search_range, level_idc, fps, no_i4x4, no_p8x8, 0 if scene_change else 1, profile, no_t8x8,
-                             background_detection, 0 if complexity is None else 1, complexity or 0, intra8x8)
+                             background_detection, 0 if complexity is None else 1, complexity or 0, intra8x8, key_slices)
         self.h = self.L.orc_create(C.byref(self.cfg))
         self.width, self.height = width, height
         self.mbw, self.mbh = (width + 15) // 16, (height + 15) // 16

@@ -471,8 +471,9 @@ def test_openh264_abi_shim_serves_the_wrapper_flow(enc, tmp_path, profile_idc, p
         _, ftype, size, layers, nals, nal_sum, l0type = (int(x) for x in rows[t])
         idr = t in (0, force_at)
         assert size == len(want[t]) == nal_sum
-        ns = 1 if profile == 0 else max(1, min(8, ((h + 15) // 16 + 8) // 17))              # slice NALs per picture
-        assert (ftype, layers, nals, l0type) == ((1, 2, 2 + ns, 0) if idr else (3, 1, ns, 1))    # IDR: [SPS PPS] + [slices]; P: [slices]
+        ns = 1 if profile == 0 else max(1, min(8, ((h + 15) // 16 + 8) // 17))              # slice NALs per P picture
+        nk = ns if profile == 0 else max(ns, min(35, ((h + 15) // 16 + 3) // 4))            # ... per key picture (b200enc_config.key_slices, automatic)
+        assert (ftype, layers, nals, l0type) == ((1, 2, 2 + nk, 0) if idr else (3, 1, ns, 1))    # IDR: [SPS PPS] + [slices]; P: [slices]
     assert rows[n][0] == "ps" and int(rows[n][2]) == 1 and int(rows[n][3]) == 2
     if avdec.available():
         assert len(avdec.decode_stream(want)) == n
@@ -846,6 +847,48 @@ def test_main_and_high_sessions_share_a_batch(enc, orc):
     assert t8[0] == 0 and t8[3] == 0 and t8[1] + t8[2] > 0
     for s in ss:
         s.close()
+    b.close()
+
+
+def test_key_pictures_take_their_own_slice_count(enc, orc):
+    """b200enc_config.key_slices: a CABAC session with automatic slices codes its key pictures with one slice per 4 MB rows (the longest chains of
+    a session: intra wavefront + serial coder), P pictures with the usual count; explicit counts work for CAVLC too. Single sessions (first
+    picture, forced IDR) and a batch step with both kinds of picture (split into two steps) equal the oracle's streams and decode."""
+    w, h, qp = 640, 368, 30
+    for profile, kw in ((1, dict(num_slices=0)), (2, dict(num_slices=0)), (0, dict(num_slices=2, key_slices=5))):
+        g = enc.Session(w, h, const_qp=qp, gop=1000, device=0, profile=profile, **kw)
+        ps, ks = g.slice_counts()
+        assert (ps, ks) == ((1, 6) if profile else (2, 5))
+        o = orc.Encoder(w, h, num_slices=ps, key_slices=ks, profile=profile)
+        c = Content("A", w, h); aus = []
+        for t in range(5):
+            f = c.frame(t)
+            if t == 3:
+                g.force_idr()
+            bs, info = g.encode(f)
+            assert bs == o.encode(f, t in (0, 3), qp), (profile, t)
+            assert np.array_equal(g.recon(), o.recon())
+            nal = [i for i in range(len(bs) - 4) if bs[i:i + 4] == b"\x00\x00\x00\x01"]
+            assert sum((bs[i + 4] & 31) in (1, 5) for i in nal) == (ks if t in (0, 3) else ps)
+            aus.append(bs)
+        if avdec.available():
+            assert len(avdec.decode_stream(aus)) == 5
+        g.close()
+    # one batch step with key and P pictures: session 1 is forced to a key picture at t = 2
+    n = 3
+    ss = [enc.Session(w, h, const_qp=qp, gop=1000, device=0, profile=1, num_slices=0) for _ in range(n)]
+    os_ = [orc.Encoder(w, h, num_slices=1, key_slices=6, profile=1) for _ in range(n)]
+    cs = [Content("A", w, h, seed=500 + i) for i in range(n)]
+    b = enc.Batch(0, ss)
+    for t in range(4):
+        frames = [cs[i].frame(t) for i in range(n)]
+        if t == 2:
+            ss[1].force_idr()
+        out, _ = b.encode(frames)
+        for i in range(n):
+            assert out[i] == os_[i].encode(frames[i], t == 0 or (t == 2 and i == 1), qp), (i, t)
+    for s_ in ss:
+        s_.close()
     b.close()
 
 

@@ -548,3 +548,22 @@ def test_intra8x8_lookup_tables_reproduce_the_oracle_predictors(orc):
                 if ok:
                     got = np.array([F[i] for i in mk.TABLE[m]], np.uint8)
                     assert np.array_equal(got, want), (trial, avail, m, got.reshape(8, 8), want.reshape(8, 8))
+
+
+def test_key_pictures_with_their_own_slice_count_decode(orc):
+    """OrcConfig.key_slices: pictures requested as key pictures take their own slice layout (here 5 against 2 for P pictures, CAVLC and CABAC);
+    the independent decoder reproduces the oracle's reconstruction, and the NAL counts follow the picture kind"""
+    if not avdec.available():
+        pytest.skip("no libavcodec")
+    w, h, qp = 176, 144, 28
+    for profile in (0, 1):
+        e = orc.Encoder(w, h, num_slices=2, key_slices=5, profile=profile); c = Content("A", w, h)
+        aus, recs = [], []
+        for t in range(5):
+            au = e.encode(c.frame(t), t in (0, 3), qp); aus.append(au); recs.append(e.recon().copy())
+            starts = [i for i in range(len(au) - 4) if au[i:i + 4] == b"\x00\x00\x00\x01"]
+            assert sum((au[i + 4] & 31) in (1, 5) for i in starts) == (5 if t in (0, 3) else 2)
+        dec = avdec.decode_stream(aus)
+        assert len(dec) == 5
+        for t in range(5):
+            assert np.array_equal(dec[t], recs[t]), (profile, t)

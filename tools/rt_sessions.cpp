@@ -92,6 +92,7 @@ int main(int argc, char **argv)
            "\"latency_ms\": {\"p50\": %.2f, \"p95\": %.2f, \"p99\": %.2f, \"max\": %.2f}, \"late_frames\": %ld, \"idr_frames\": %ld, \"errors\": %ld, \"avg_batch\": %.1f, \"realtime\": %s}\n",
            N, ndev, W, H, fps, seconds, frames.load(), frames.load() / wall / N, pct(0.5), pct(0.95), pct(0.99), all.empty() ? 0.f : all.back(), late.load(), idr_frames.load(), errors.load(),
            nd ? avg_batch / nd : 0.0, (late.load() == 0 && errors.load() == 0 && pct(0.99) <= 1000.0 / fps) ? "true" : "false");
+    { unsigned long r = 0; for (auto s : sess) r += b200enc_rc_retries(s); fprintf(stderr, "rate control: %lu pictures coded twice (hard cap)\n", r); }
     for (auto s : sess) b200enc_destroy(s);
     for (auto p : pool) b200enc_host_free(p);
     return 0;

@@ -44,7 +44,8 @@ if checked:
     import ctypes as C
     for (w, h, kind, qp, slices, profile) in ((96, 80, "D", 0, 1, 0), (96, 80, "D", 0, 2, 1), (176, 144, "D", 4, 3, 2), (640, 368, "A", 20, 2, 2), (1280, 720, "B", 30, 0, 1)):
         g = enc.Session(w, h, const_qp=qp, num_slices=slices, gop=3, device=0, profile=profile)
-        o = orc_py.Encoder(w, h, num_slices=slices if slices else max(1, min(8, ((h + 15) // 16 + 8) // 17)), profile=profile)
+        ps, ks = g.slice_counts()       # the engine's automatic rules (key pictures of CABAC sessions take more slices)
+        o = orc_py.Encoder(w, h, num_slices=ps, key_slices=ks, profile=profile)
         c = Content(kind, w, h)
         for t in range(4):
             f = c.frame(t)
