@@ -397,7 +397,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     if (ss[0]->cfg.input_format == B200ENC_FMT_RGBA) {
         pf.begin("k_ingest_rgba"); k_ingest_rgba<<<dim3(((g.wc / 8) * (g.hc / 2) + 255) / 256, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end();
     } else {
-        pf.begin("k_ingest_planar"); k_ingest_planar<<<dim3(((g.wc / 8) * g.hc * 3 / 2 + 255) / 256, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end();
+        pf.begin("k_ingest_planar"); k_ingest_planar<<<dim3((INGEST_UNITS(g.wc, g.hc) + 255) / 256, 1, n), 256, 0, st>>>(b->d_sess, g); pf.end();
     }
     launches++;
     if (any_p) {

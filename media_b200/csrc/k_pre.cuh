@@ -11,42 +11,57 @@ namespace b200 {
 
 enum { FMT_I420 = 0, FMT_NV12 = 1, FMT_RGBA = 2 };
 
-// grid: (ceil(units/256), 1, sessions); a unit is 8 output bytes of one plane row.
+// grid: (ceil(units/256), 1, sessions); a unit is 16 output bytes of one plane row (8 at the end of a chroma row whose coded width is 8 mod 16):
+// one 128-bit load and one 128-bit store per thread wherever the input row and the address allow it.
+#define INGEST_UNITS(wc, hc) (((wc) / 16) * (hc) + 2 * (((wc) / 2 + 15) / 16) * ((hc) / 2))
 __global__ void __launch_bounds__(256) k_ingest_planar(const Sess *ss, Geom g)
 {
     const Sess &s = ss[blockIdx.z];
     const int w = g.width, h = g.height, wc = g.wc, hc = g.hc;
-    const int ly = (wc / 8) * hc, lc = (wc / 16) * (hc / 2);
+    const int ly = (wc / 16) * hc, upc = (wc / 2 + 15) / 16, lc = upc * (hc / 2);
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= ly + 2 * lc) return;
-    int comp = u < ly ? 0 : (u < ly + lc ? 1 : 2);
+    const int comp = u < ly ? 0 : (u < ly + lc ? 1 : 2);
     if (comp) u -= ly + (comp - 1) * lc;
     const int cw = comp ? wc / 2 : wc, pw = comp ? w / 2 : w, ph = comp ? h / 2 : h;
-    const int upr = cw / 8, y = u / upr, x = (u % upr) * 8, sy = min(y, ph - 1);
-    uint2 v;
+    const int upr = comp ? upc : wc / 16, y = u / upr, x = (u - y * upr) * 16, sy = min(y, ph - 1);
+    uint32_t v[4];
     if (s.input_format == FMT_I420 || comp == 0) {
         const uint8_t *in = s.input + (comp == 0 ? 0 : (size_t)w * h + (comp == 2 ? (size_t)pw * ph : 0)) + (size_t)sy * pw;
-        if (x + 8 <= pw && (pw & 7) == 0) v = *reinterpret_cast<const uint2 *>(in + x);
-        else {
-            uint32_t a = 0, b = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) { a |= (uint32_t)in[min(x + i, pw - 1)] << (8 * i); b |= (uint32_t)in[min(x + 4 + i, pw - 1)] << (8 * i); }
-            v = make_uint2(a, b);
-        }
-    } else {   // NV12 chroma: de-interleave 16 bytes of UV pairs
-        const uint8_t *in = s.input + (size_t)w * h + (size_t)sy * w + (comp - 1);
-        uint32_t a = 0, b = 0;
-        if (x + 8 <= pw && (w & 15) == 0) {
-            uint4 q = *reinterpret_cast<const uint4 *>(in - (comp - 1) + 2 * x);
-            uint32_t sel = comp == 1 ? 0x6420 : 0x7531;
-            a = __byte_perm(q.x, q.y, sel); b = __byte_perm(q.z, q.w, sel);
+        if (x + 16 <= pw && (reinterpret_cast<uintptr_t>(in + x) & 15) == 0) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(in + x);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) { a |= (uint32_t)in[2 * min(x + i, pw - 1)] << (8 * i); b |= (uint32_t)in[2 * min(x + 4 + i, pw - 1)] << (8 * i); }
+            for (int k = 0; k < 4; k++) {
+                uint32_t a = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) a |= (uint32_t)in[min(x + 4 * k + i, pw - 1)] << (8 * i);
+                v[k] = a;
+            }
         }
-        v = make_uint2(a, b);
+    } else {   // NV12 chroma: de-interleave 32 bytes of UV pairs
+        const uint8_t *in = s.input + (size_t)w * h + (size_t)sy * w + (comp - 1);
+        if (x + 16 <= pw && (reinterpret_cast<uintptr_t>(in - (comp - 1) + 2 * x) & 15) == 0) {
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(in - (comp - 1) + 2 * x), q1 = *reinterpret_cast<const uint4 *>(in - (comp - 1) + 2 * x + 16);
+            const uint32_t sel = comp == 1 ? 0x6420 : 0x7531;
+            v[0] = __byte_perm(q0.x, q0.y, sel); v[1] = __byte_perm(q0.z, q0.w, sel); v[2] = __byte_perm(q1.x, q1.y, sel); v[3] = __byte_perm(q1.z, q1.w, sel);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t a = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) a |= (uint32_t)in[2 * min(x + 4 * k + i, pw - 1)] << (8 * i);
+                v[k] = a;
+            }
+        }
     }
-    *reinterpret_cast<uint2 *>(s.src[comp] + (size_t)y * cw + x) = v;
+    uint8_t *out = s.src[comp] + (size_t)y * cw + x;
+    if (x + 16 <= cw && (reinterpret_cast<uintptr_t>(out) & 15) == 0) *reinterpret_cast<uint4 *>(out) = make_uint4(v[0], v[1], v[2], v[3]);
+    else {
+        *reinterpret_cast<uint2 *>(out) = make_uint2(v[0], v[1]);
+        if (x + 16 <= cw) *reinterpret_cast<uint2 *>(out + 8) = make_uint2(v[2], v[3]);
+    }
 }
 
 // BT.601 limited range, 8-bit fixed point; chroma from the rounded 2x2 mean RGB (no reference

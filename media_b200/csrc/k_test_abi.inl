@@ -32,7 +32,7 @@ int b200k_convert_to_i420(int device, int fmt, const uint8_t *in, int w, int h, 
     K_TRY(cudaMemcpy(din.p, in, in_bytes, cudaMemcpyHostToDevice));
     K_TRY(cudaMemcpy(dsess.p, &s, sizeof s, cudaMemcpyHostToDevice));
     if (fmt == B200ENC_FMT_RGBA) k_ingest_rgba<<<dim3(((g.wc / 8) * (g.hc / 2) + 255) / 256, 1, 1), 256>>>(dsess.as<Sess>(), g);
-    else k_ingest_planar<<<dim3(((g.wc / 8) * g.hc * 3 / 2 + 255) / 256, 1, 1), 256>>>(dsess.as<Sess>(), g);
+    else k_ingest_planar<<<dim3((INGEST_UNITS(g.wc, g.hc) + 255) / 256, 1, 1), 256>>>(dsess.as<Sess>(), g);
     K_TRY(cudaGetLastError());
     K_TRY(cudaMemcpy(out, dout.p, ny * 3 / 2, cudaMemcpyDeviceToHost));
     if (coded_w) *coded_w = g.wc;
