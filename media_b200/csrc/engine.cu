@@ -402,9 +402,9 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
     launches++;
     if (any_p) {
         pf.begin("k_refplanes"); k_refplanes<<<dim3((g.ls + RP_TW - 1) / RP_TW, (g.hc + 2 * g.lp + RP_TH - 1) / RP_TH, n), 256, 0, st>>>(b->d_sess, g); pf.end();
-        pf.begin("k_refchroma"); k_refchroma<<<dim3(((g.cs / 4) * (g.hc / 2 + 2 * g.cp) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g); pf.end();
-        pf.begin("k_downsample0"); k_downsample<<<dim3((((g.wc / 2 + 2 * g.p1) / 4) * (g.hc / 2 + 2 * g.p1) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 0); pf.end();
-        pf.begin("k_downsample1"); k_downsample<<<dim3((((g.wc / 4 + 2 * g.p2) / 4) * (g.hc / 4 + 2 * g.p2) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 1); pf.end();
+        pf.begin("k_refchroma"); k_refchroma<<<dim3(((g.cs / 16) * (g.hc / 2 + 2 * g.cp) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g); pf.end();
+        pf.begin("k_downsample0"); k_downsample<<<dim3((DOWNSAMPLE_UNITS(g.wc / 2, g.hc / 2, g.p1) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 0); pf.end();
+        pf.begin("k_downsample1"); k_downsample<<<dim3((DOWNSAMPLE_UNITS(g.wc / 4, g.hc / 4, g.p2) + 255) / 256, 2, n), 256, 0, st>>>(b->d_sess, g, 1); pf.end();
         pf.begin("k_me_coarse");
         {
             const dim3 g8((nmb + 7) / 8, 1, n), g4((nmb + 3) / 4, 1, n);

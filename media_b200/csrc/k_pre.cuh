@@ -123,7 +123,15 @@ __global__ void __launch_bounds__(256) k_ingest_rgba(const Sess *ss, Geom g)
 // 2x2 box filter with rounding (role of DyadicBilinearDownsampler_c). level 0: full -> 1/2, level 1: 1/2 -> 1/4.
 // The output planes carry an edge-replicated border of g.p1 / g.p2 samples (the coarse search windows reach outside the
 // picture and the oracle clamps coordinates per level), so the kernel covers the padded area and clamps into the interior.
-// grid: (ceil(units/256), 2 {src, ref}, sessions); a unit is 4 output pixels.
+// grid: (ceil(units/256), 2 {src, ref}, sessions); a unit is 8 output pixels (two 64-bit loads per input row, one 64-bit store).
+#define DOWNSAMPLE_UNITS(ow, oh, po) ((((ow) + 2 * (po) + 7) / 8) * ((oh) + 2 * (po)))
+__device__ __forceinline__ uint32_t box4(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1)     // four outputs from 8 + 8 input samples
+{
+    // horizontal pair sums on 16x2 lanes: (even bytes) + (odd bytes), both rows, then + 2 and >> 2 per lane
+    const uint32_t s0 = (a0 & 0x00ff00ffu) + ((a0 >> 8) & 0x00ff00ffu) + (b0 & 0x00ff00ffu) + ((b0 >> 8) & 0x00ff00ffu) + 0x00020002u;
+    const uint32_t s1 = (a1 & 0x00ff00ffu) + ((a1 >> 8) & 0x00ff00ffu) + (b1 & 0x00ff00ffu) + ((b1 >> 8) & 0x00ff00ffu) + 0x00020002u;
+    return __byte_perm((s0 >> 2) & 0x00ff00ffu, (s1 >> 2) & 0x00ff00ffu, 0x6420);
+}
 __global__ void __launch_bounds__(256) k_downsample(const Sess *ss, Geom g, int level)
 {
     const Sess &s = ss[blockIdx.z];
@@ -132,29 +140,32 @@ __global__ void __launch_bounds__(256) k_downsample(const Sess *ss, Geom g, int 
     const int is = level == 0 ? g.wc : g.s1, os = level == 0 ? g.s1 : g.s2, po = level == 0 ? g.p1 : g.p2;
     const uint8_t *in = blockIdx.y == 0 ? (level == 0 ? s.src[0] : s.srcL1) : (level == 0 ? s.ref[0] : s.refL1);
     uint8_t *out = blockIdx.y == 0 ? (level == 0 ? s.srcL1 : s.srcL2) : (level == 0 ? s.refL1 : s.refL2);
-    const int upr = (ow + 2 * po) / 4;
+    const int upr = (ow + 2 * po + 7) / 8;
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= upr * (oh + 2 * po)) return;
-    const int x = (u % upr) * 4 - po, y = u / upr - po, cy = min(max(y, 0), oh - 1);
-    uint32_t o = 0;
-    if (x >= 0 && x + 4 <= ow) {
-        uint2 a = *reinterpret_cast<const uint2 *>(in + (size_t)(2 * cy) * is + 2 * x);
-        uint2 b = *reinterpret_cast<const uint2 *>(in + (size_t)(2 * cy + 1) * is + 2 * x);
-        uint32_t aw[2] = { a.x, a.y }, bw[2] = { b.x, b.y };
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t p = aw[i >> 1] >> (16 * (i & 1)), q = bw[i >> 1] >> (16 * (i & 1));
-            o |= (((p & 255) + ((p >> 8) & 255) + (q & 255) + ((q >> 8) & 255) + 2) >> 2) << (8 * i);
-        }
+    const int y = u / upr - po, x = (u - (y + po) * upr) * 8 - po, cy = min(max(y, 0), oh - 1);
+    const int n = min(8, ow + po - x);                 // outputs of this unit that exist (the padded row need not be a multiple of 8)
+    uint32_t o[2];
+    const uint8_t *r0 = in + (size_t)(2 * cy) * is, *r1 = r0 + is;
+    if (x >= 0 && x + 8 <= ow && ((reinterpret_cast<uintptr_t>(r0 + 2 * x) | (uintptr_t)is) & 7) == 0) {
+        const uint2 a0 = *reinterpret_cast<const uint2 *>(r0 + 2 * x), a1 = *reinterpret_cast<const uint2 *>(r0 + 2 * x + 8);
+        const uint2 b0 = *reinterpret_cast<const uint2 *>(r1 + 2 * x), b1 = *reinterpret_cast<const uint2 *>(r1 + 2 * x + 8);
+        o[0] = box4(a0.x, a0.y, b0.x, b0.y); o[1] = box4(a1.x, a1.y, b1.x, b1.y);
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int cx = min(max(x + i, 0), ow - 1);
-            const uint8_t *p = in + (size_t)(2 * cy) * is + 2 * cx;
-            o |= (uint32_t)((p[0] + p[1] + p[is] + p[is + 1] + 2) >> 2) << (8 * i);
+        for (int k = 0; k < 2; k++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int cx = min(max(x + 4 * k + i, 0), ow - 1);
+                w |= (uint32_t)((r0[2 * cx] + r0[2 * cx + 1] + r1[2 * cx] + r1[2 * cx + 1] + 2) >> 2) << (8 * i);
+            }
+            o[k] = w;
         }
     }
-    *reinterpret_cast<uint32_t *>(out + (ptrdiff_t)y * os + x) = o;
+    uint8_t *dst = out + (ptrdiff_t)y * os + x;
+    if (n == 8 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) *reinterpret_cast<uint2 *>(dst) = make_uint2(o[0], o[1]);
+    else { *reinterpret_cast<uint32_t *>(dst) = o[0]; if (n > 4) *reinterpret_cast<uint32_t *>(dst + 4) = o[1]; }
 }
 
 // Reference planes of a P picture, built once per frame from the previous deblocked reconstruction: plane G is the
@@ -241,24 +252,31 @@ __global__ void __launch_bounds__(256) k_refplanes(const Sess *ss, Geom g)
     }
 }
 
-// edge-extended copies of the reference chroma planes (border g.cp). grid: (ceil(units/256), 2 {Cb, Cr}, sessions); unit = 4 samples
+// edge-extended copies of the reference chroma planes (border g.cp). grid: (ceil(units/256), 2 {Cb, Cr}, sessions); unit = 16 samples
+// (the padded row g.cs is a multiple of 16 and so is every unit's destination address)
 __global__ void __launch_bounds__(256) k_refchroma(const Sess *ss, Geom g)
 {
     const Sess &s = ss[blockIdx.z];
     if (s.is_idr) return;
-    const int cw = g.wc / 2, ch = g.hc / 2, upr = g.cs / 4;
+    const int cw = g.wc / 2, ch = g.hc / 2, upr = g.cs / 16;
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= upr * (ch + 2 * g.cp)) return;
-    const int x = (u % upr) * 4 - g.cp, y = u / upr - g.cp;
+    const int y = u / upr - g.cp, x = (u - (y + g.cp) * upr) * 16 - g.cp;
     const uint8_t *row = s.ref[1 + blockIdx.y] + (size_t)min(max(y, 0), ch - 1) * cw;
-    uint32_t o;
-    if (x >= 0 && x + 4 <= cw) o = *reinterpret_cast<const uint32_t *>(row + x);
-    else {
-        o = 0;
+    uint32_t o[4];
+    if (x >= 0 && x + 16 <= cw && (reinterpret_cast<uintptr_t>(row + x) & 7) == 0) {
+        const uint2 a = *reinterpret_cast<const uint2 *>(row + x), b = *reinterpret_cast<const uint2 *>(row + x + 8);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    } else {
 #pragma unroll
-        for (int i = 0; i < 4; i++) o |= (uint32_t)row[min(max(x + i, 0), cw - 1)] << (8 * i);
+        for (int k = 0; k < 4; k++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) w |= (uint32_t)row[min(max(x + 4 * k + i, 0), cw - 1)] << (8 * i);
+            o[k] = w;
+        }
     }
-    *reinterpret_cast<uint32_t *>(s.rpc[blockIdx.y] + (ptrdiff_t)y * g.cs + x) = o;
+    *reinterpret_cast<uint4 *>(s.rpc[blockIdx.y] + (ptrdiff_t)y * g.cs + x) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 } // namespace b200

@@ -51,7 +51,7 @@ int b200k_downsample2(int device, const uint8_t *in, int w, int h, uint8_t *out)
     s.src[0] = din.as<uint8_t>(); s.srcL1 = dout.as<uint8_t>();
     K_TRY(cudaMemcpy(din.p, in, (size_t)w * h, cudaMemcpyHostToDevice));
     K_TRY(cudaMemcpy(dsess.p, &s, sizeof s, cudaMemcpyHostToDevice));
-    k_downsample<<<dim3(((w / 8) * (h / 2) + 255) / 256, 1, 1), 256>>>(dsess.as<Sess>(), g, 0);
+    k_downsample<<<dim3((DOWNSAMPLE_UNITS(w / 2, h / 2, 0) + 255) / 256, 1, 1), 256>>>(dsess.as<Sess>(), g, 0);
     K_TRY(cudaGetLastError());
     K_TRY(cudaMemcpy(out, dout.p, (size_t)w * h / 4, cudaMemcpyDeviceToHost));
     return B200ENC_OK;
