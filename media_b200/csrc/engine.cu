@@ -206,10 +206,28 @@ int dbk_resident_pct()
     return pct;
 }
 
+// CUDA loads a kernel's code on its first launch (lazy module loading): 38 ms for k_me_fine, measured as the first P picture of a process
+// (tools/frame_kernel_times.py) -- a late frame for every session that happens to be in that step. Asking for the attributes loads the code.
+__global__ void k_reset(const Sess *ss, Geom g, int nsess, WaveCtl *ctl);
+void preload_kernels()
+{
+    cudaFuncAttributes a;
+#define PRELOAD(k) cudaFuncGetAttributes(&a, k)
+    PRELOAD(k_reset); PRELOAD(k_ingest_rgba); PRELOAD(k_ingest_planar); PRELOAD(k_refplanes); PRELOAD(k_refchroma); PRELOAD(k_downsample);
+    PRELOAD((k_me_coarse<4, 8, true>)); PRELOAD((k_me_coarse<4, 8, false>)); PRELOAD((k_me_coarse<8, 8, true>)); PRELOAD((k_me_coarse<8, 8, false>));
+    PRELOAD((k_me_coarse<16, 4, true>)); PRELOAD((k_me_coarse<16, 4, false>));
+    PRELOAD(k_me_fine); PRELOAD(k_scene_change); PRELOAD(k_inter_t8); PRELOAD(k_intra_wave); PRELOAD(k_pskip_scan); PRELOAD(k_deblock_bs); PRELOAD(k_deblock_wave);
+    PRELOAD(k_cabac_side); PRELOAD(k_cabac_hdr); PRELOAD(k_cabac_bins); PRELOAD(k_cabac_scan); PRELOAD(k_cabac_place_hdr); PRELOAD(k_cabac_compact); PRELOAD(k_cabac_code);
+    PRELOAD(k_cavlc_mb); PRELOAD(k_slice_scan); PRELOAD(k_slice_copy); PRELOAD(k_nal_pack);
+#undef PRELOAD
+    cudaGetLastError();
+}
+
 int batch_init(b200enc_batch *b, int device, int cap)
 {
     b->device = device; b->cap = cap;
     CU_TRY(cudaSetDevice(device), return B200ENC_ENODEV);
+    preload_kernels();
     // function attributes are per device: every batch context sets the coder's dynamic shared-memory limit on its own device
     if (cabac_slab_kb() > 0) CU_TRY(cudaFuncSetAttribute(k_cabac_code, cudaFuncAttributeMaxDynamicSharedMemorySize, cabac_slab_kb() * 1024), return B200ENC_ENODEV);
     CU_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), return B200ENC_ENODEV);

@@ -1,9 +1,9 @@
-"""tools/roofline_table.py -- per-kernel roofline table of one P step from the committed ncu counters (profiles/r01_ncu_kernels.json):
+"""tools/roofline_table.py -- per-kernel roofline table of one P step from the committed ncu counters (profiles/r02_ncu_kernels.json):
 algorithmic bytes (SURVEY 8d / DESIGN 5) over the kernel's time alone against the HBM peak, DRAM traffic, and executed warp-instructions
 over the same time against the issue peak (SMs x 4 schedulers x SM clock). Writes markdown to stdout."""
 import json, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))
+prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")))
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 HBM = peaks.get("hbm_gbs", 6546.6)
 S = prof["sessions_per_launch"]
@@ -20,8 +20,8 @@ ALG = {
     "k_me_coarse": (2 * 0.3125 * px, "INT (VABSDIFF4)", "pyramid levels of source and reference"),
     "k_me_fine": (4.5 * px + nmb * 816.0, "INT issue", "source 1.5 + reference 1.5 + reconstruction 1.5 B/px + 816 B levels per MB"),
     "k_intra_wave": (3.0 * px, "latency", "only intra MBs"),
-    "k_deblock_bs": (nmb * (48.0 + 16.0), "INT / LSU", "48 B MbInfo read (neighbours from L2), 16 B written per MB"),
-    "k_deblock_wave": (3.0 * px + nmb * 16.0, "latency", "1.5 B/px read + written in place, 16 B boundary strengths per MB"),
+    "k_deblock_bs": (nmb * (48.0 + 16.0), "LSU", "48 B MbInfo read (neighbours from L2), 16 B written per MB"),
+    "k_deblock_wave": (3.0 * px + nmb * (16.0 + 192.0), "latency", "1.5 B/px read + written in place, 16 B boundary strengths and 192 B of hand-over messages per MB"),
     "k_cavlc_mb": (nmb * (816.0 + 48.0), "INT / LSU", "816 B levels + 48 B MbInfo per MB"),
     "k_slice_copy": (nmb * 64.0, "LSU", "the MB's bits, read and written (actual bitstream size)"),
 }
