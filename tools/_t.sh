@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | grep -E "^(FAILED|ERROR|E  )|passed|failed|Error" | head
-python tools/frame_kernel_times.py A 2>&1 | head -2 | cut -c1-200
-for n in 300 350; do echo "baseline $n: $(./tools/rt_sessions.bin $n 10 2>&1 | tail -2 | tr '\n' ' ' | cut -c1-60,150-470)"; done
+for n in 250 300 350 400 450 500; do echo "baseline $n: $(./tools/rt_sessions.bin $n 10 2>&1 | tail -2 | tr '\n' ' ')"; done
+for n in 125 150 175 200; do echo "main $n: $(./tools/rt_sessions.bin $n 10 1920 1080 30 4000000 0 1 1 0 2>&1 | tail -2 | tr '\n' ' ')"; done
+for n in 125 150 175; do echo "high $n: $(./tools/rt_sessions.bin $n 10 1920 1080 30 4000000 0 1 2 0 2>&1 | tail -2 | tr '\n' ' ')"; done
