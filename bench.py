@@ -281,24 +281,27 @@ def run_b200(args):
         # once (the frames of a step are S x fb bytes per GPU), and the staging memcpy rate of this host (pageable -> pinned, all caller threads)
         h2d = None
         try:
-            # four streams, a frame per copy: what the sessions' upload streams do (one stream alone stays below the link's rate)
-            nbuf, nst = 32, 4
+            # eight streams, a frame per copy: what the sessions' upload streams do (one stream alone stays below the link's rate); best of three
+            # windows (a ceiling is the most the link delivered, and the first window still sees the tail of the end-to-end leg)
+            nbuf, nst = 32, 8
             hp = torch.empty(nbuf * fb, dtype=torch.uint8).pin_memory(); dp_ = torch.empty(nbuf * fb, dtype=torch.uint8, device=f"cuda:{dev}")
             dp_.copy_(hp, non_blocking=True); torch.cuda.synchronize()
             sts = [torch.cuda.Stream(device=dev) for _ in range(nst)]
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for st_ in sts:
-                st_.wait_stream(torch.cuda.current_stream())
-            for rep in range(6):
-                for k in range(nbuf):
-                    with torch.cuda.stream(sts[k % nst]):
-                        dp_[k * fb:(k + 1) * fb].copy_(hp[k * fb:(k + 1) * fb], non_blocking=True)
-            for st_ in sts:
-                torch.cuda.current_stream().wait_stream(st_)
-            e1.record(); torch.cuda.synchronize()
-            gbs = 6 * nbuf * fb / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            gbs = 0.0
+            for window in range(3):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for st_ in sts:
+                    st_.wait_stream(torch.cuda.current_stream())
+                for rep in range(4):
+                    for k in range(nbuf):
+                        with torch.cuda.stream(sts[k % nst]):
+                            dp_[k * fb:(k + 1) * fb].copy_(hp[k * fb:(k + 1) * fb], non_blocking=True)
+                for st_ in sts:
+                    torch.cuda.current_stream().wait_stream(st_)
+                e1.record(); torch.cuda.synchronize()
+                gbs = max(gbs, 4 * nbuf * fb / (e0.elapsed_time(e1) * 1e-3) / 1e9)
             t = torch.tensor([gbs], dtype=torch.float64)
             if use_dist:
                 dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -323,7 +326,7 @@ def run_b200(args):
                    "frames_per_s_ceiling": round(world * t[0].item() * 1e9 / fb, 0),
                    "host_staging_copy_gbs_per_rank_all_ranks_copying": round(ts[0].item(), 1), "host_threads_per_rank": ncpu,
                    "frames_per_s_staging_ceiling": round(world * ts[0].item() * 1e9 / fb, 0),
-                   "note": "ceilings of the host-input path: PCIe (pinned host -> device, four copy streams per GPU, all ranks at once) and the staging copy "
+                   "note": "ceilings of the host-input path: PCIe (pinned host -> device, eight copy streams per GPU, best of three windows, all ranks at once) and the staging copy "
                            "of pageable caller memory into pinned memory (one copy per frame on the caller's thread; numpy copies on this rank's share of "
                            "the host cores, all ranks at once; the DMA reads the same memory a third time). No end-to-end number with host frames exceeds either"}
             del hp, dp_
