@@ -1,3 +1,7 @@
-for n in 250 300 350 400 450 500; do echo "baseline $n: $(./tools/rt_sessions.bin $n 10 2>&1 | tail -2 | tr '\n' ' ')"; done
-for n in 125 150 175 200; do echo "main $n: $(./tools/rt_sessions.bin $n 10 1920 1080 30 4000000 0 1 1 0 2>&1 | tail -2 | tr '\n' ' ')"; done
-for n in 125 150 175; do echo "high $n: $(./tools/rt_sessions.bin $n 10 1920 1080 30 4000000 0 1 2 0 2>&1 | tail -2 | tr '\n' ' ')"; done
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; tail -2 gpurun_out/r02_bench_final.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r02_bench_final.json").read().strip().splitlines()[-1])
+e=d["e2e"]
+print("N=1 value", d["value"], "e2e", e["value"], "pinned", e.get("pinned_input"), "h2d", {k:v for k,v in (e.get("h2d_ceiling") or {}).items() if k!='note'}, "rt", d.get("realtime",{}).get("late_frames"), d.get("realtime",{}).get("latency_ms"), d.get("realtime",{}).get("sessions"))
+PY

@@ -33,6 +33,7 @@ struct E2E {
     void *lib = nullptr; CreateFn create = nullptr; DestroyFn destroy = nullptr; PropSetFn prop_set = nullptr;
     std::vector<VideoEncoder *> enc;
     std::vector<uint8_t *> pool; size_t frame_bytes = 0;
+    void (*pinned_free)(void *) = nullptr;          // E2E_POOL_PINNED=1: the frames live in memory from b200enc_host_alloc (an integrator that owns its capture buffers)
     int fps = 30;
     std::string error;
 };
@@ -78,8 +79,16 @@ void *e2e_open(const char *codec_lib, int sessions, int width, int height, int f
     set("persist.vmi.b200.encode.input_format", input_format && *input_format ? input_format : "i420");
     set("persist.vmi.b200.encode.device", device >= 0 ? std::to_string(device) : std::string(""));
     e->fps = fps; e->frame_bytes = frame_bytes;
+    // the secondary leg of bench.py: frames in pinned memory handed out by the encoder library instead of malloc memory -- what an
+    // integrator who owns the capture buffers can do; the symbols are found through libVideoCodec.so's dependency, nothing else of that API is used
+    void *(*pinned_alloc)(size_t) = nullptr;
+    if (const char *pe = getenv("E2E_POOL_PINNED")) if (atoi(pe)) {
+        pinned_alloc = reinterpret_cast<void *(*)(size_t)>(dlsym(e->lib, "b200enc_host_alloc"));
+        e->pinned_free = reinterpret_cast<void (*)(void *)>(dlsym(e->lib, "b200enc_host_free"));
+        if (!pinned_alloc || !e->pinned_free) { e->error = "E2E_POOL_PINNED: b200enc_host_alloc / b200enc_host_free not found"; return e; }
+    }
     for (int t = 0; t < pool_frames; t++) {
-        uint8_t *p = static_cast<uint8_t *>(malloc(frame_bytes));
+        uint8_t *p = static_cast<uint8_t *>(pinned_alloc ? pinned_alloc(frame_bytes) : malloc(frame_bytes));
         if (!p) { e->error = "malloc"; return e; }
         memcpy(p, pool + (size_t)t * frame_bytes, frame_bytes);
         e->pool.push_back(p);
@@ -142,7 +151,7 @@ void e2e_close(void *h)
     E2E *e = static_cast<E2E *>(h);
     if (!e) return;
     for (VideoEncoder *v : e->enc) { v->StopEncoder(); v->DestroyEncoder(); e->destroy(v); }
-    for (uint8_t *p : e->pool) free(p);
+    for (uint8_t *p : e->pool) { if (e->pinned_free) e->pinned_free(p); else free(p); }
     // the library stays loaded: its scheduler threads and CUDA context live until process exit
     delete e;
 }
