@@ -401,6 +401,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         d.out = s->d_out; d.out_size = reinterpret_cast<uint32_t *>(s->d_out + s->out_cap); d.hdr = s->hdr; d.hdr_len = s->hdr_len;
         d.row_prog_intra = s->row_prog; d.row_prog_dbk = s->row_prog + g.mbh;
         d.dbk_ll = s->dbk_ll; d.dbk_seq = ++s->dbk_seq;
+        if (!d.dbk_seq) d.dbk_seq = ++s->dbk_seq;          // 0 is what never-written messages hold
         d.qp = qps[i]; d.is_idr = idr; d.frame_num = idr ? 0 : s->frame_num; d.idr_pic_id = s->idr_pic_id; d.input_format = s->cfg.input_format;
         d.scene_change = s->cfg.scene_change && !idr && s->frames_since_idr >= SC_MIN_DISTANCE;
         d.t8x8 = s->cfg.profile == 2; d.dump = s->cfg.debug & 1;
@@ -480,7 +481,8 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         // a slab of dynamic shared memory they do not use keeps the shared-memory-hungry kernels of the other batches off their SMs
         // (paced sessions: small batches, tail latency counts). Big batches are throughput work: there the slab only takes shared memory
         // from the other batches' motion search (96 x 1080p Main in batches of 32: 8 550 frames/s with it, 9 380 without)
-        const int hog_kb = n <= 16 ? cabac_slab_kb() : 0;
+        static const int slab_max_n = [] { const char *e = getenv("B200ENC_CABAC_SLAB_MAXN"); return e ? atoi(e) : 16; }();
+        const int hog_kb = n <= slab_max_n ? cabac_slab_kb() : 0;
         pf.begin("k_cabac_code", s2); if (!(xskip & 4)) k_cabac_code<<<dim3(g.num_slices, 1, n), 96, (size_t)hog_kb * 1024, s2>>>(b->d_sess, g, b->d_ctl); pf.end();
         launches += 7;
     } else {

@@ -1,8 +1,6 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err
-tail -2 gpurun_out/r02_bench_n8.err | cut -c1-300
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/r02_bench_n8.json").read().strip().splitlines()[-1])
-e=d["e2e"]
-print("N=8 value", d["value"], "e2e", e["value"], "pinned", (e.get("pinned_input") or {}).get("value"), (e.get("pinned_input") or {}).get("error"), "h2d", {k:v for k,v in (e.get("h2d_ceiling") or {}).items() if k!='note'}, "rt", d.get("realtime",{}).get("late_frames"), d.get("realtime",{}).get("latency_ms"), d.get("realtime",{}).get("sessions"))
-PY
+run() { python bench.py --no-cpu --workload 1080p-main --steps 20 --realtime-seconds 0 $2 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('$1 value', d['value'], 'e2e', e['value'], 'pinned', (e.get('pinned_input') or {}).get('value'))"; }
+run base ""
+B200ENC_CABAC_SLAB_MAXN=512 run slab100_all ""
+B200ENC_CABAC_SLAB_MAXN=512 B200ENC_CABAC_SMEM_KB=60 run slab60_all ""
+B200ENC_CABAC_SLAB_MAXN=512 run slab100_all_g8 "--groups 8"
+run base_g8 "--groups 8"
