@@ -218,7 +218,7 @@ void preload_kernels()
     PRELOAD((k_me_coarse<16, 4, true>)); PRELOAD((k_me_coarse<16, 4, false>));
     PRELOAD(k_me_fine); PRELOAD(k_scene_change); PRELOAD(k_inter_t8); PRELOAD(k_intra_wave); PRELOAD(k_pskip_scan); PRELOAD(k_deblock_bs); PRELOAD(k_deblock_wave);
     PRELOAD(k_cabac_side); PRELOAD(k_cabac_hdr); PRELOAD(k_cabac_bins); PRELOAD(k_cabac_scan); PRELOAD(k_cabac_place_hdr); PRELOAD(k_cabac_compact); PRELOAD(k_cabac_code);
-    PRELOAD(k_cavlc_mb); PRELOAD(k_slice_scan); PRELOAD(k_slice_copy); PRELOAD(k_nal_pack);
+    PRELOAD(k_cavlc_hdr); PRELOAD(k_cavlc_mb); PRELOAD(k_slice_scan); PRELOAD(k_slice_copy); PRELOAD(k_nal_pack);
 #undef PRELOAD
     cudaGetLastError();
 }
@@ -486,6 +486,7 @@ int launch_step(b200enc_batch *b, b200enc_session *const *ss, int n, const uint8
         pf.begin("k_cabac_code", s2); if (!(xskip & 4)) k_cabac_code<<<dim3(g.num_slices, 1, n), 96, (size_t)hog_kb * 1024, s2>>>(b->d_sess, g, b->d_ctl); pf.end();
         launches += 7;
     } else {
+    pf.begin("k_cavlc_hdr", s2); k_cavlc_hdr<<<dim3((nmb + 127) / 128, 1, n), 128, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_cavlc_mb", s2); k_cavlc_mb<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_slice_scan", s2); k_slice_scan<<<dim3(g.num_slices, 1, n), 256, 0, s2>>>(b->d_sess, g); pf.end(); launches++;
     pf.begin("k_slice_copy", s2); k_slice_copy<<<dim3((nmb + CAVLC_WARPS - 1) / CAVLC_WARPS, 1, n), CAVLC_WARPS * 32, 0, s2>>>(b->d_sess, g); pf.end(); launches++;

@@ -270,8 +270,34 @@ template <int MODE> __device__ void code_mb_header(BitSink<MODE> &bs, const Sess
     }
 }
 
+// The header of a macroblock (mb_skip_run, mb_type, prediction modes or mvd, coded_block_pattern, mb_qp_delta) is a serial walk with the MV prediction
+// in front of it: as lane 0 of a warp per MB it kept 31 lanes idle for ~200 instructions. Here a THREAD owns a macroblock: the header goes left-aligned
+// into words 0-1 of the MB's bit slot and its length into mb_bits. Inter macroblocks without residual (cbp 0) are complete with that -- the warp kernel
+// leaves them at once; for the others its lane 0 takes the header from the slot. A header longer than 64 bits (Intra_4x4 with many explicit modes, huge
+// skip runs) is marked and coded by the warp kernel's lane 0 as before.
+// grid: (ceil(n_mb / 128), 1, sessions), 128 threads
+#define CAVLC_HDR_LONG 0xffffffffu
+__device__ __forceinline__ bool cavlc_header_only(uint32_t w0) { const uint32_t t = w0 & 255u; return (w0 >> 24) == 0u && (t == MB_P16x16 || t == MB_P8x8); }
+__global__ void __launch_bounds__(128) k_cavlc_hdr(const Sess *ss, Geom g)
+{
+    const int mb = blockIdx.x * 128 + threadIdx.x;
+    if (mb >= g.mbw * g.mbh) return;
+    const Sess &s = ss[blockIdx.z];
+    const MbInfo *mi = s.mbi + mb;
+    if (mi->mb_type == MB_PSKIP) { s.mb_bits[mb] = 0; return; }
+    const int mx = mb % g.mbw, my = mb / g.mbw;
+    int mvd[8];
+    mb_mvds(s, g, mx, my, mi, mvd);
+    BitSink<2> bs; bs.w = nullptr; bs.pos = 0; bs.acc = 0ull;
+    code_mb_header<2>(bs, s, g, mx, my, mi, s.is_idr ? 0 : s.skip_run[mb], mvd);
+    if (bs.pos > 64) { s.mb_bits[mb] = CAVLC_HDR_LONG; return; }
+    uint32_t *dst = s.mb_slot + (size_t)mb * B200_MB_SLOT_WORDS;
+    *reinterpret_cast<uint2 *>(dst) = make_uint2((uint32_t)(bs.acc >> 32), (uint32_t)bs.acc);
+    s.mb_bits[mb] = (uint32_t)bs.pos;
+}
+
 #define CAVLC_WARPS 8
-// grid: (ceil(n_mb / CAVLC_WARPS), 1, sessions)
+// grid: (ceil(n_mb / CAVLC_WARPS), 1, sessions); after k_cavlc_hdr
 __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, Geom g)
 {
     __shared__ uint32_t slot_all[CAVLC_WARPS][B200_MB_SLOT_WORDS];
@@ -280,22 +306,28 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, G
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
     const MbInfo *mi = s.mbi + mb; const MbCoef *co = s.coef + mb;
-    if (mi->mb_type == MB_PSKIP) { if (lane == 0) s.mb_bits[mb] = 0; return; }
+    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(mi);
+    if ((w0 & 255u) == MB_PSKIP) return;                          // mb_bits = 0 was written by k_cavlc_hdr
+    const uint32_t hdr_len = s.mb_bits[mb];                       // the header's length (its bits are in words 0-1 of the MB's slot), or CAVLC_HDR_LONG
+    if (hdr_len != CAVLC_HDR_LONG && cavlc_header_only(w0)) return;     // no residual: the header is the whole macroblock, k_cavlc_hdr wrote it
     const int mx = mb % g.mbw, my = mb / g.mbw;
     uint32_t *slot = slot_all[warp];
+    uint32_t *dst = s.mb_slot + (size_t)mb * B200_MB_SLOT_WORDS;
     const int skip_run = s.is_idr ? 0 : s.skip_run[mb];
     __align__(16) int16_t lv[16];
     MbItem it = mb_item(s, g, mx, my, lane, mi, co);
     if (lane >= 1 && lane < 28 && it.present)
         for (int i = 0; i < it.maxn; i++) lv[i] = it.lv[i];
     int mvd[8];
-    if (lane == 0) mb_mvds(s, g, mx, my, mi, mvd);
+    if (lane == 0 && hdr_len == CAVLC_HDR_LONG) mb_mvds(s, g, mx, my, mi, mvd);
     // pass 1: every lane codes its syntax group into a 64-bit register (and counts its length)
     int len = 0; unsigned long long acc = 0ull;
     {
         BitSink<2> bs; bs.w = nullptr; bs.pos = 0; bs.acc = 0ull;
-        if (lane == 0) code_mb_header<2>(bs, s, g, mx, my, mi, skip_run, mvd);
-        else if (lane < 28 && it.present) code_residual<2>(bs, lv, it.maxn, it.nC);
+        if (lane == 0) {
+            if (hdr_len == CAVLC_HDR_LONG) code_mb_header<2>(bs, s, g, mx, my, mi, skip_run, mvd);
+            else { const uint2 h = *reinterpret_cast<const uint2 *>(dst); bs.pos = (int)hdr_len; bs.acc = ((unsigned long long)h.x << 32) | h.y; }
+        } else if (lane < 28 && it.present) code_residual<2>(bs, lv, it.maxn, it.nC);
         len = bs.pos; acc = bs.acc;
     }
     int incl = len;
@@ -320,11 +352,16 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, G
 #ifdef B200_CHECKED
         bs.cap = B200_MB_SLOT_WORDS * 32;
 #endif
-        if (lane == 0) code_mb_header<1>(bs, s, g, mx, my, mi, skip_run, mvd);
-        else if (lane < 28 && it.present) code_residual<1>(bs, lv, it.maxn, it.nC);
+        if (lane == 0) {
+            if (hdr_len == CAVLC_HDR_LONG) code_mb_header<1>(bs, s, g, mx, my, mi, skip_run, mvd);
+            else {      // the precomputed header: len bits, left-aligned in acc
+                const int n1 = min(len, 32), n2 = len - n1;
+                if (n1) bs.put(n1, (uint32_t)(acc >> (64 - n1)));
+                if (n2) bs.put(n2, (uint32_t)(acc >> (32 - n2)) & (n2 == 32 ? 0xffffffffu : (1u << n2) - 1u));
+            }
+        } else if (lane < 28 && it.present) code_residual<1>(bs, lv, it.maxn, it.nC);
     }
     __syncwarp();
-    uint32_t *dst = s.mb_slot + (size_t)mb * B200_MB_SLOT_WORDS;
     for (int i = lane; i < nwords; i += 32) dst[i] = slot[i];
     if (lane == 0) s.mb_bits[mb] = (uint32_t)total;
 }
