@@ -312,14 +312,14 @@ def run_b200(args):
         # once (the frames of a step are S x fb bytes per GPU), and the staging memcpy rate of this host (pageable -> pinned, all caller threads)
         h2d = None
         try:
-            # eight streams, a frame per copy: what the sessions' upload streams do (one stream alone stays below the link's rate); best of three
+            # eight streams, a frame per copy: what the sessions' upload streams do (one stream alone stays below the link's rate); best of six
             # windows (a ceiling is the most the link delivered, and the first window still sees the tail of the end-to-end leg)
-            nbuf, nst = 32, 8
+            nbuf, nst = 48, 8
             hp = torch.empty(nbuf * fb, dtype=torch.uint8).pin_memory(); dp_ = torch.empty(nbuf * fb, dtype=torch.uint8, device=f"cuda:{dev}")
             dp_.copy_(hp, non_blocking=True); torch.cuda.synchronize()
             sts = [torch.cuda.Stream(device=dev) for _ in range(nst)]
             gbs = 0.0
-            for window in range(3):
+            for window in range(6):
                 barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -357,7 +357,7 @@ def run_b200(args):
                    "frames_per_s_ceiling": round(world * t[0].item() * 1e9 / fb, 0),
                    "host_staging_copy_gbs_per_rank_all_ranks_copying": round(ts[0].item(), 1), "host_threads_per_rank": ncpu,
                    "frames_per_s_staging_ceiling": round(world * ts[0].item() * 1e9 / fb, 0),
-                   "note": "ceilings of the host-input path: PCIe (pinned host -> device, eight copy streams per GPU, best of three windows, all ranks at once) and the staging copy "
+                   "note": "ceilings of the host-input path: PCIe (pinned host -> device, eight copy streams per GPU, best of six windows, all ranks at once) and the staging copy "
                            "of pageable caller memory into pinned memory (one copy per frame on the caller's thread; numpy copies on this rank's share of "
                            "the host cores, all ranks at once; the DMA reads the same memory a third time). No end-to-end number with host frames exceeds either"}
             del hp, dp_

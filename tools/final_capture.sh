@@ -13,7 +13,7 @@ for n in 125 150 175; do echo "main $n: $(./tools/rt_sessions.bin $n 10 1920 108
 for n in 125 150; do echo "high $n: $(./tools/rt_sessions.bin $n 10 1920 1080 30 4000000 0 1 2 0 2>&1 | tail -2 | tr '\n' ' ')"; done >> gpurun_out/rt_sessions_$T.txt 2>&1
 B="python bench.py --steps 3 --warmup 3 --sessions 32 --groups 1 --no-cpu --no-e2e"
 $B > gpurun_out/plain_n.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$T.csv $B > gpurun_out/ncu_ln.log 2>&1
-ncu --set full --clock-control none --import-source on --launch-skip 44 -c 17 -f -o gpurun_out/prof_$T $B > gpurun_out/ncu_fn.log 2>&1
+ncu --set full --clock-control none --import-source on --launch-skip 46 -c 18 -f -o gpurun_out/prof_$T $B > gpurun_out/ncu_fn.log 2>&1
 BM="$B --workload 1080p-main"
 $BM > gpurun_out/plain_m.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_cabac --launch-skip 21 -c 7 -f -o gpurun_out/prof_cabac_$T $BM > gpurun_out/ncu_fm.log 2>&1
 BR="python bench.py --steps 3 --warmup 3 --sessions 32 --groups 1 --no-cpu --no-e2e --workload rgba720"
