@@ -819,6 +819,7 @@ int b200enc_create(const b200enc_config *cfg, b200enc_session **out)
     s->cfg = c;
     Geom &g = s->g;
     g.width = c.width; g.height = c.height; g.mbw = (c.width + 15) / 16; g.mbh = (c.height + 15) / 16; g.wc = g.mbw * 16; g.hc = g.mbh * 16;
+    geom_set_magic(g);
     g.search_range = c.search_range;
     auto slice_layout = [](Geom &q, int count) {
         q.num_slices = std::min(count, q.mbh);

@@ -57,7 +57,10 @@ struct Geom {
     // pad and row stride of the luma reference planes, of the chroma reference planes, and of pyramid levels 1 and 2
     int lp, ls, cp, cs, p1, s1, p2, s2;
     uint32_t slice_top[8];        // bit my set: MB row my is the first row of a slice (mbh <= 256)
+    uint32_t mbw_magic;           // floor(2^32 / mbw) (clamped to 2^32 - 1): macroblock index -> (mx, my) by one multiply and one correction (mb_xy)
 };
+// host side: fills Geom::mbw_magic (every place that sets g.mbw calls this)
+inline void geom_set_magic(Geom &g) { const unsigned long long m = (1ull << 32) / (unsigned)(g.mbw > 0 ? g.mbw : 1); g.mbw_magic = m > 0xffffffffull ? 0xffffffffu : (uint32_t)m; }
 
 // Per-session, per-frame device descriptor (one array element per session in the batch).
 struct Sess {
@@ -217,6 +220,14 @@ __device__ __forceinline__ int se_len(int v) { unsigned x = (v > 0 ? 2u * v - 1u
 __device__ __forceinline__ int ue_len(unsigned v) { return 2 * (31 - __clz(v + 1u)) + 1; }
 __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
 __device__ __forceinline__ bool mb_t8(const MbInfo *m) { return (m->i16_mode >> 2) & 1; }   // transform_size_8x8_flag
+// Macroblock coordinates without an integer division (the I2F / MUFU.RCP / F2I chain costs ~22 instructions per warp): q' = mulhi(mb, floor(2^32 / mbw))
+// is the quotient or one below it for every mb < 2^32, one compare fixes it.
+__device__ __forceinline__ void mb_xy(const Geom &g, int mb, int &mx, int &my)
+{
+    int q = (int)__umulhi((uint32_t)mb, g.mbw_magic), r = mb - q * g.mbw;
+    if (r >= g.mbw) { q++; r -= g.mbw; }
+    mx = r; my = q;
+}
 __device__ __forceinline__ bool row_is_slice_top(const Geom &g, int my) { return (g.slice_top[my >> 5] >> (my & 31)) & 1u; }
 
 // forward core transform of a 4x4 residual held in registers (role of WelsDctT4_c)

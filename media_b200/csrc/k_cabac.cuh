@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) k_cabac_side(const Sess *ss, Geom g)
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
     const MbInfo *mi = s.mbi + mb; const MbCoef *co = s.coef + mb;
-    const int mx = mb % g.mbw, my = mb / g.mbw;
+    int mx, my; mb_xy(g, mb, mx, my);
     MbSide sd; uint32_t *w = reinterpret_cast<uint32_t *>(&sd);
 #pragma unroll
     for (int i = 0; i < 5; i++) w[i] = 0;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) k_cabac_hdr(const Sess *ss, Geom g)
     const int mb = blockIdx.x * 256 + threadIdx.x;
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
-    const int mx = mb % g.mbw, my = mb / g.mbw;
+    int mx, my; mb_xy(g, mb, mx, my);
     // the headers have their own dense array (CABAC_HDR_SLOT entries per MB): neighbouring threads write neighbouring lines, not lines 7 KB apart
     BinSink<1> bs; bs.p = s.bins_hdr + (size_t)mb * CABAC_HDR_SLOT; bs.n = 0;
 #ifdef B200_CHECKED
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(CABAC_WARPS * 32) k_cabac_bins(const Sess *ss,
         const int t = w0 & 255, cbp = (int)(w0 >> 24);
         if (t == MB_PSKIP || (cbp == 0 && t != MB_I16x16)) return;
     }
-    const int mx = mb % g.mbw, my = mb / g.mbw;
+    int mx, my; mb_xy(g, mb, mx, my);
     __align__(16) int16_t lv[16];
     CabacItem it = cabac_item(s, g, mx, my, lane, mi, co);
     const bool mine = lane >= 1 && lane < 28 && it.present;

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(128) k_cavlc_hdr(const Sess *ss, Geom g)
     const Sess &s = ss[blockIdx.z];
     const MbInfo *mi = s.mbi + mb;
     if (mi->mb_type == MB_PSKIP) { s.mb_bits[mb] = 0; return; }
-    const int mx = mb % g.mbw, my = mb / g.mbw;
+    int mx, my; mb_xy(g, mb, mx, my);
     int mvd[8];
     mb_mvds(s, g, mx, my, mi, mvd);
     BitSink<2> bs; bs.w = nullptr; bs.pos = 0; bs.acc = 0ull;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(CAVLC_WARPS * 32) k_cavlc_mb(const Sess *ss, G
     if ((w0 & 255u) == MB_PSKIP) return;                          // mb_bits = 0 was written by k_cavlc_hdr
     const uint32_t hdr_len = s.mb_bits[mb];                       // the header's length (its bits are in words 0-1 of the MB's slot), or CAVLC_HDR_LONG
     if (hdr_len != CAVLC_HDR_LONG && cavlc_header_only(w0)) return;     // no residual: the header is the whole macroblock, k_cavlc_hdr wrote it
-    const int mx = mb % g.mbw, my = mb / g.mbw;
+    int mx, my; mb_xy(g, mb, mx, my);
     uint32_t *slot = slot_all[warp];
     uint32_t *dst = s.mb_slot + (size_t)mb * B200_MB_SLOT_WORDS;
     const int skip_run = s.is_idr ? 0 : s.skip_run[mb];

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) k_deblock_bs(const Sess *ss, Geom g)
     const int mb = blockIdx.x * 128 + threadIdx.x;
     if (mb >= g.mbw * g.mbh) return;
     const Sess &s = ss[blockIdx.z];
-    const int mx = mb % g.mbw, my = mb / g.mbw;
+    int mx, my; mb_xy(g, mb, mx, my);
     const uint32_t *q = reinterpret_cast<const uint32_t *>(s.mbi + mb);
     const uint4 a = *reinterpret_cast<const uint4 *>(q), b = *reinterpret_cast<const uint4 *>(q + 4), c = *reinterpret_cast<const uint4 *>(q + 8);
     // a.x type word, a.z a.w b.x b.y the four partition vectors, b.z b.w c.x c.y the 16 luma nnz

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_me_coarse(const Sess *ss, Geom g
     const Sess &s = ss[blockIdx.z];
     if (s.is_idr) return;
     Smem &sm = sm_all[warp];
-    const int mx = mb % g.mbw, my = mb / g.mbw;
+    int mx, my; mb_xy(g, mb, mx, my);
     const int R4 = EXACT ? MAXR4 : g.search_range / 4, span = 2 * R4 + 1, W = 8 + 2 * R4, wpr = W >> 2;
 
     // level 2: 8x8 block centred on the MB (origin 4mx-2, 4my-2), all (2R4+1)^2 displacements
@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     const Sess &s = ss[blockIdx.z];
     if (s.is_idr) return;
     FineSmem &sm = sm_all[warp];
-    const int mx = mb % g.mbw, my = mb / g.mbw, x0 = mx * 16, y0 = my * 16, wc = g.wc;
+    int mx, my; mb_xy(g, mb, mx, my);
+    const int x0 = mx * 16, y0 = my * 16, wc = g.wc;
     const int qp = s.qp, lambda = c_lambda[qp];
     const char *tmaps = static_cast<const char *>(s.tmaps);
 
@@ -306,8 +307,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
         const uint8_t *sp = s.src[0] + (size_t)(y0 + (lane >> 1)) * wc + x0 + (lane & 1) * 8;
         uint2 a = *reinterpret_cast<const uint2 *>(rp), b = *reinterpret_cast<const uint2 *>(sp);
         zsad = sad4(a.x, b.x, sad4(a.y, b.y, 0)); zref = a; zsrc = b;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) zsad += __shfl_xor_sync(0xffffffffu, zsad, o);
+        zsad = __reduce_add_sync(0xffffffffu, zsad);         // one REDUX.SUM instead of five shuffle + add steps
     }
     __syncwarp();
     bool tma_ok = mbar_wait(&sm.bar[0]);
@@ -375,13 +375,26 @@ __global__ void __launch_bounds__(ME_WARPS * 32, ME_FINE_MIN_CTAS) k_me_fine(con
     // candidate row is ONE aligned 128-bit load against one 128-bit load of the source row. Copies are WIN_COPY bytes apart: the quarter-warps
     // of both the 128-bit stores here and the 25 candidate loads below then touch distinct 16-byte bank groups (k * 336 mod 128 = 0, 80, 32, 112, 64).
     uint8_t *cpb = reinterpret_cast<uint8_t *>(sm.plane[0]);
-    for (int i = lane; i < 100; i += 32) {
-        const int r = i / 5, k = i - r * 5, off = o0 + k, sh = (off & 3) * 8;
-        const uint32_t *row = sm.win + r * (PL_STRIDE / 4) + (off >> 2);
-        B200_CHECK(r * (PL_STRIDE / 4) + (off >> 2) + 4 < 20 * PL_STRIDE / 4 && k * WIN_COPY + r * 16 + 16 <= (int)sizeof(sm.plane), 8);
-        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3], w4 = row[4];
-        *reinterpret_cast<uint4 *>(cpb + k * WIN_COPY + r * 16) =
-            make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    // One lane per window row: the row's 48 bytes as three conflict-free 128-bit loads (a quarter-warp's rows start at 16-byte groups 3r mod 8),
+    // the five words from byte o0 by ONE data-dependent funnel shift each (u_j = bytes o0 + 4j ..), copies 1-3 from those by constant shifts,
+    // copy 4 = the same words one further: 5 + 12 shifts and 5 stores per row instead of 4 shifts, 5 loads and a division per (row, copy).
+    if (lane < 20) {
+        const uint4 *rowv = reinterpret_cast<const uint4 *>(sm.win + lane * (PL_STRIDE / 4));
+        const uint4 q0 = rowv[0], q1 = rowv[1], q2 = rowv[2];
+        const uint32_t w[12] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w };
+        const int sh = (o0 & 3) * 8;
+        uint32_t u0, u1, u2, u3, u4;
+#define ME_WSEL(A) { u0 = __funnelshift_r(w[A], w[A + 1], sh); u1 = __funnelshift_r(w[A + 1], w[A + 2], sh); u2 = __funnelshift_r(w[A + 2], w[A + 3], sh); \
+                     u3 = __funnelshift_r(w[A + 3], w[A + 4], sh); u4 = __funnelshift_r(w[A + 4], w[A + 5], sh); }
+        switch (o0 >> 2) { case 0: ME_WSEL(0) break; case 1: ME_WSEL(1) break; case 2: ME_WSEL(2) break; default: ME_WSEL(3) break; }
+#undef ME_WSEL
+        uint8_t *d = cpb + lane * 16;
+        B200_CHECK((o0 >> 2) + 5 < PL_STRIDE / 4 && lane * 16 + 4 * WIN_COPY + 16 <= (int)sizeof(sm.plane), 8);
+        *reinterpret_cast<uint4 *>(d) = make_uint4(u0, u1, u2, u3);
+        *reinterpret_cast<uint4 *>(d + WIN_COPY) = make_uint4(__funnelshift_r(u0, u1, 8), __funnelshift_r(u1, u2, 8), __funnelshift_r(u2, u3, 8), __funnelshift_r(u3, u4, 8));
+        *reinterpret_cast<uint4 *>(d + 2 * WIN_COPY) = make_uint4(__funnelshift_r(u0, u1, 16), __funnelshift_r(u1, u2, 16), __funnelshift_r(u2, u3, 16), __funnelshift_r(u3, u4, 16));
+        *reinterpret_cast<uint4 *>(d + 3 * WIN_COPY) = make_uint4(__funnelshift_r(u0, u1, 24), __funnelshift_r(u1, u2, 24), __funnelshift_r(u2, u3, 24), __funnelshift_r(u3, u4, 24));
+        *reinterpret_cast<uint4 *>(d + 4 * WIN_COPY) = make_uint4(u1, u2, u3, u4);
     }
     __syncwarp();
     uint32_t best = 0xffffffffu;

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(T8_WARPS * 32) k_inter_t8(const Sess *ss, Geom
     const uint32_t w0 = reinterpret_cast<const uint32_t *>(mi)[0];
     const int type = w0 & 255, cbp = (int)(w0 >> 24);
     if ((type != MB_P16x16 && type != MB_P8x8) || !(cbp & 15)) return;        // early-skip and all-zero MBs keep the flag 0 (not coded)
-    const int mx = mb % g.mbw, my = mb / g.mbw, x0 = mx * 16, y0 = my * 16, wc = g.wc, qp = s.qp;
+    int mx, my; mb_xy(g, mb, mx, my);
+    const int x0 = mx * 16, y0 = my * 16, wc = g.wc, qp = s.qp;
     const int b8 = lane >> 3, r = lane & 7, ox = (b8 & 1) * 8, oy = (b8 >> 1) * 8;
     int (*t)[9] = sm_all[warp].t[b8];
     MbCoef *co = s.coef + mb;

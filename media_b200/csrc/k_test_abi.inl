@@ -10,6 +10,7 @@ void fill_geom(Geom &g, int w, int h, int slices, int range)
 {
     memset(&g, 0, sizeof g);
     g.width = w; g.height = h; g.mbw = (w + 15) / 16; g.mbh = (h + 15) / 16; g.wc = g.mbw * 16; g.hc = g.mbh * 16;
+    geom_set_magic(g);
     g.num_slices = slices; g.search_range = range;
     for (int i = 1; i <= B200_MAX_SLICES; i++) g.slice_row0[i] = g.mbh;
     g.slice_top[0] = 1u;

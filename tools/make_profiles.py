@@ -4,14 +4,21 @@ roofline table, the paced-session table, the SASS summary and the GPU test log. 
 import json, os, re, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 T = sys.argv[1]
+SCRIPT = sys.argv[2] if len(sys.argv) > 2 else "tools/final_capture.sh"     # which capture script produced gpurun_out/*_<tag>
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 run = lambda *a, **k: subprocess.run(list(a), capture_output=True, text=True, cwd=ROOT, **k).stdout
+def copy_if_there(src, dst):        # a partial capture (tools/variant_gate.sh) only refreshes what it re-measured
+    if os.path.exists(src) and os.path.getsize(src) > 0: shutil.copy(src, dst)
+    else: print("kept (not in this capture):", os.path.basename(dst))
 for f in ("bench", "bench_long", "bench_reference"):
-    shutil.copy(f"{G}/{f}_{T}.json", f"{P}/r02_{f}.json")
+    copy_if_there(f"{G}/{f}_{T}.json", f"{P}/r02_{f}.json")
 for w in ("1080p-main", "1080p-high", "single", "4k", "rgba720", "portrait720"):
-    shutil.copy(f"{G}/bench_{w}_{T}.json", f"{P}/r02_bench_{w}.json")
-shutil.copy(f"{G}/launches_{T}.csv", f"{P}/r02_launches_bench_s32.csv")
-shutil.copy(f"{G}/gpu_tests_{T}.log", f"{P}/r02_gpu_tests.log")
+    copy_if_there(f"{G}/bench_{w}_{T}.json", f"{P}/r02_bench_{w}.json")
+copy_if_there(f"{G}/launches_{T}.csv", f"{P}/r02_launches_bench_s32.csv")
+copy_if_there(f"{G}/gpu_tests_{T}.log", f"{P}/r02_gpu_tests.log")
+_old_summary = open(f"{P}/r02_ncu_summary.md").read() if os.path.exists(f"{P}/r02_ncu_summary.md") else ""
+def old_rows(prefixes):           # rows of the previous summary for kernels this capture did not profile (with their capture's tag)
+    return "\n".join(l for l in _old_summary.splitlines() if l.startswith("| ") and any(l[2:].startswith(k) for k in prefixes))
 main = run(sys.executable, "tools/ncu_summary.py", f"gpurun_out/prof_{T}.ncu-rep", "profiles/r02_ncu_kernels.json", "32").strip()
 # the capture window is 17 launches and a P step has 18 since k_cavlc_hdr: what fell out of the window (k_refchroma, unchanged since) comes from the
 # capture one commit earlier, if that report is still there
@@ -25,8 +32,8 @@ if os.path.exists(f"{G}/prof_{FALLBACK}.ncu-rep") and FALLBACK != T:
         if name and name not in have and name.split("<")[0] in fbk and "cavlc" not in name:
             main += "\n" + l.replace(f"| {name} |", f"| {name} (capture `{FALLBACK}`) |"); kj_["kernels"][name.split("<")[0]] = fbk[name.split("<")[0]]
     json.dump(kj_, open(f"{P}/r02_ncu_kernels.json", "w"), indent=1)
-cab = "\n".join(run(sys.executable, "tools/ncu_summary.py", f"gpurun_out/prof_cabac_{T}.ncu-rep").strip().splitlines()[2:])
-rg = "\n".join(run(sys.executable, "tools/ncu_summary.py", f"gpurun_out/prof_rgba_{T}.ncu-rep").strip().splitlines()[2:])
+cab = "\n".join(run(sys.executable, "tools/ncu_summary.py", f"gpurun_out/prof_cabac_{T}.ncu-rep").strip().splitlines()[2:]) if os.path.exists(f"{G}/prof_cabac_{T}.ncu-rep") else old_rows(("k_cabac",))
+rg = "\n".join(run(sys.executable, "tools/ncu_summary.py", f"gpurun_out/prof_rgba_{T}.ncu-rep").strip().splitlines()[2:]) if os.path.exists(f"{G}/prof_rgba_{T}.ncu-rep") else old_rows(("k_ingest_rgba",))
 run(sys.executable, "tools/sass_summary.py", "r02")
 # ---- per-phase table of k_me_fine: phases are found by their marker comments, so the table follows the source
 src = open(f"{ROOT}/media_b200/csrc/k_me.cuh").read().splitlines()
@@ -69,9 +76,11 @@ dp, av = line_of('asm("dp4a.u32.s32'), line_of("__device__ __forceinline__ uint3
 s0, s1 = line_of("__device__ __forceinline__ int satd_rows"), line_of("__device__ __forceinline__ int half_reduce16")
 sat = [sum(v[j] for k, v in inl.items() if k[0] == "k_me.cuh" and s0 <= k[1] < s1 and k[1] not in (dp, av)) for j in (0, 1)]
 ph.append(f"| inlined: `satd_rows` second stage (abs / max / add of the column butterflies) | {sat[0]:.1f} % | {sat[0] * per_mb / 100:.0f} | {sat[1]:.1f} % |")
+hdev = open(f"{ROOT}/media_b200/csrc/h264_dev.cuh").read().splitlines()
+hline = lambda marker: next(i + 1 for i, l in enumerate(hdev) if marker in l)
 named = {("k_me.cuh", dp): "`dp4a_us` (SATD first stage 32 per block-candidate, source terms, transform rows, chroma MC)", ("k_me.cuh", av): "`avg4` (rounded byte average of the quarter-pel candidates)",
-         ("h264_dev.cuh", 209): "`sad4` (VABSDIFF4.ACC)", ("math_functions.hpp", 870): "abs / min / max", ("sm_32_intrinsics.hpp", 570): "funnel shifts (byte alignment of window rows)",
-         ("sm_30_intrinsics.hpp", 409): "`__shfl_xor_sync` (reductions)", ("sm_30_intrinsics.hpp", 373): "`__shfl_sync`", ("h264_dev.cuh", 216): "`se_len`"}
+         ("h264_dev.cuh", hline("uint32_t sad4(")): "`sad4` (VABSDIFF4.ACC)", ("math_functions.hpp", 870): "abs / min / max", ("sm_32_intrinsics.hpp", 570): "funnel shifts (byte alignment of window rows)",
+         ("sm_30_intrinsics.hpp", 409): "`__shfl_xor_sync` (reductions)", ("sm_30_intrinsics.hpp", 373): "`__shfl_sync`", ("h264_dev.cuh", hline("int se_len(int v)")): "`se_len`"}
 used = sat[0]
 for k, n in named.items():
     if k in inl:
@@ -81,7 +90,7 @@ ph.append(f"| other inlined helpers (quantiser, transforms, TMA / mbarrier wrapp
 hdr = "| kernel | time | warp instr | grid | regs | warps active % | ALU pipe % | SM throughput % | DRAM throughput % | dram read | dram written | smem bank conflicts |\n|---|---|---|---|---|---|---|---|---|---|---|---|"
 kj = json.load(open(f"{P}/r02_ncu_kernels.json"))["kernels"]
 step_instr = sum(v["warp_instructions"] for v in kj.values())
-open(f"{P}/r02_ncu_summary.md", "w").write(f"""# ncu summary, round 2 (final capture of the round: `tools/final_capture.sh {T}`, one B200, SM clock 1965 MHz)
+open(f"{P}/r02_ncu_summary.md", "w").write(f"""# ncu summary, round 2 (capture `{SCRIPT} {T}`, one B200, SM clock 1965 MHz)
 
 `ncu --set full --clock-control none --import-source on` over one P step of 32 x 1080p sessions in ONE batch (`python bench.py --steps 3 --warmup 3 --sessions 32
 --groups 1 --no-cpu --no-e2e`, after the same command ran to exit 0 without ncu); first profiled launch of every kernel. Per-launch times under ncu are
@@ -91,7 +100,7 @@ cold-cache and serialised: the kernels' SHARES are what the bench line's `kernel
 
 {main}
 
-CABAC kernels (`--workload 1080p-main`, 32 sessions x 4 slices) and the RGBA ingest (`--workload rgba720`, 32 x 1280x720 RGBA framebuffers):
+CABAC kernels (`--workload 1080p-main`, 32 sessions x 4 slices) and the RGBA ingest (`--workload rgba720`, 32 x 1280x720 RGBA framebuffers){"" if os.path.exists(f"{G}/prof_cabac_{T}.ncu-rep") else " -- capture `tools/final_capture.sh r02z` (since then the CABAC kernels only lost their index division, the RGBA ingest is unchanged)"}:
 
 {hdr}
 {cab}
