@@ -182,6 +182,9 @@ int b200k_vabsdiff4_peak(int device, double *ginstr_per_s, int *sm_clock_mhz);
 /* libb200enc_checked.so (-DB200_CHECKED: device-side bound checks on every computed slot / ring / list / tile index): failures counted since
  * load, *first_site = id of the first failing check; returns -1 when the library is not the checked build */
 int b200k_check_failures(int device, int *first_site);
+/* host-only (no device needed): the division-free macroblock-index arithmetic of the warp-per-MB kernels (h264_dev.cuh: mb_xy) checked against / and % for
+ * every mb in [0, n) at a picture width of mbw macroblocks; returns the number of mismatches (0 expected), -1 for invalid arguments */
+int b200k_mb_xy_mismatches(int mbw, int n);
 /* issue-rate microbenchmarks behind the INT roofline: kind 0 VABSDIFF4.U8.ACC, 1 IADD3, 2 LOP3, 3 IDP.4A, 4 IMAD, 5 VIMNMX, 6 IABS + IADD, 7 SHF,
  * 8 the 4x4 Hadamard SATD of the motion search counted as 64 lane-operations. out[4 * kind + 0..3] = G warp-instructions/s of the whole GPU,
  * warp-instructions per clock per SM, the SM clock of the run in MHz (clock64 / globaltimer measured inside the kernel), instructions per unit */

@@ -222,12 +222,18 @@ __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, 
 __device__ __forceinline__ bool mb_t8(const MbInfo *m) { return (m->i16_mode >> 2) & 1; }   // transform_size_8x8_flag
 // Macroblock coordinates without an integer division (the I2F / MUFU.RCP / F2I chain costs ~22 instructions per warp): q' = mulhi(mb, floor(2^32 / mbw))
 // is the quotient or one below it for every mb < 2^32, one compare fixes it.
-__device__ __forceinline__ void mb_xy(const Geom &g, int mb, int &mx, int &my)
+__host__ __device__ __forceinline__ void mb_xy_core(uint32_t magic, int mbw, int mb, int &mx, int &my)    // host side: b200k_mb_xy_mismatches (CPU test)
 {
-    int q = (int)__umulhi((uint32_t)mb, g.mbw_magic), r = mb - q * g.mbw;
-    if (r >= g.mbw) { q++; r -= g.mbw; }
+#ifdef __CUDA_ARCH__
+    int q = (int)__umulhi((uint32_t)mb, magic);
+#else
+    int q = (int)(((unsigned long long)(uint32_t)mb * magic) >> 32);
+#endif
+    int r = mb - q * mbw;
+    if (r >= mbw) { q++; r -= mbw; }
     mx = r; my = q;
 }
+__device__ __forceinline__ void mb_xy(const Geom &g, int mb, int &mx, int &my) { mb_xy_core(g.mbw_magic, g.mbw, mb, mx, my); }
 __device__ __forceinline__ bool row_is_slice_top(const Geom &g, int my) { return (g.slice_top[my >> 5] >> (my & 31)) & 1u; }
 
 // forward core transform of a 4x4 residual held in registers (role of WelsDctT4_c)

@@ -199,6 +199,15 @@ template <int KIND> static int run_int_peak(int sms, double *out)
 }
 extern "C" {
 // checked build: number of device-side bound-check failures since the library was loaded and the id of the first failing site; -1 = not a checked build
+// host-only: the macroblock-index arithmetic of every warp-per-MB kernel (mb_xy) against / and % for mb in [0, n); returns the number of mismatches
+int b200k_mb_xy_mismatches(int mbw, int n)
+{
+    if (mbw < 1 || n < 0) return -1;
+    Geom g; memset(&g, 0, sizeof g); g.mbw = mbw; geom_set_magic(g);
+    int bad = 0;
+    for (int mb = 0; mb < n; mb++) { int mx, my; mb_xy_core(g.mbw_magic, g.mbw, mb, mx, my); bad += mx != mb % mbw || my != mb / mbw; }
+    return bad;
+}
 int b200k_check_failures(int device, int *first_site)
 {
 #ifdef B200_CHECKED

@@ -29,6 +29,18 @@ def test_c_abi_exports_every_declared_symbol(built):
         assert hasattr(L, n), f"{n} declared in include/b200enc.h but not exported"
 
 
+def test_macroblock_index_arithmetic_is_exact_for_every_accepted_width(built):
+    """Every warp-per-MB kernel turns its macroblock index into (mx, my) with one multiply-high by floor(2^32 / mbw) and one correction
+    (h264_dev.cuh: mb_xy) instead of a division; the host build of the same function must agree with / and % for every picture width the
+    encoder accepts (16..4096 samples = 1..256 macroblocks) and every index of a 256-row picture."""
+    L = C.CDLL(os.path.join(ROOT, "media_b200", "csrc", "libb200enc.so"))
+    L.b200k_mb_xy_mismatches.argtypes = [C.c_int, C.c_int]; L.b200k_mb_xy_mismatches.restype = C.c_int
+    for mbw in range(1, 257):
+        assert L.b200k_mb_xy_mismatches(mbw, mbw * 256 + 3) == 0, mbw
+    assert L.b200k_mb_xy_mismatches(120, 1 << 24) == 0 and L.b200k_mb_xy_mismatches(1, 1 << 20) == 0
+    assert L.b200k_mb_xy_mismatches(0, 10) == -1
+
+
 def test_codec_library_exports_the_reference_factory(built):
     out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "media_b200", "host", "libVideoCodec.so")], text=True)
     syms = {l.split()[-1] for l in out.splitlines() if " T " in l}
