@@ -10,8 +10,9 @@
  * vectors, so PARITY WITH OPENH264 IS UNPINNED. What IS pinned:
  *   - every normative stage (CAVLC, intra/inter prediction, dequant/IDCT, deblocking) by decoding the
  *     oracle's streams with FFmpeg's independent h264 decoder and comparing with the oracle's own
- *     reconstruction bit-exactly (tests/test_oracle_decode.py);
- *   - the CAVLC/deblock/cbp tables against the copies inside that decoder (tests/test_tables.py).
+ *     reconstruction bit-exactly (tests/test_oracle.py::test_oracle_stream_decodes_to_its_reconstruction and the other *_decode tests);
+ *   - the CAVLC/deblock/cbp tables against the copies inside that decoder (tests/test_oracle.py::test_tables_match_the_independent_decoder,
+ *     ::test_cabac_tables_match_the_independent_decoder).
  * Encoder-side free choices (search pattern, costs, quantiser rounding) follow the standard JM-style
  * definitions named in SURVEY.md section 2b and are the specification the CUDA path must reproduce
  * bit-for-bit (same bitstream bytes, same reconstruction).
