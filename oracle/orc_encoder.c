@@ -177,7 +177,7 @@ static inline int hp(const OrcEncoder *e, const uint8_t *pl, int x, int y)
 {
     return pl[(size_t)(clip3(-HP_M, e->hc + HP_M - 1, y) + HP_M) * (e->wc + 2 * HP_M) + clip3(-HP_M, e->wc + HP_M - 1, x) + HP_M];
 }
-/* same value as orc_interp_luma(ref, ...) -- tests/test_oracle_kernels.py checks the identity */
+/* same value as orc_interp_luma(ref, ...) -- tests/test_oracle.py::test_qpel_planes_equal_the_normative_interpolation checks the identity */
 static int qpel_sample(const OrcEncoder *e, int xq, int yq)
 {
     int x = xq >> 2, y = yq >> 2, w = e->wc, h = e->hc; const uint8_t *r = e->ref[0];
